@@ -1,0 +1,124 @@
+// Shared device/host helpers for libdpsttc (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/dpsttc.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libdpsttc is written for sm_100a (B200) only"
+#endif
+
+// ---------------------------------------------------------------------------------------------
+// host side: error reporting + launch accounting
+// ---------------------------------------------------------------------------------------------
+void dps_set_error(const char* fmt, ...);
+void dps_count_launch(int n = 1);
+
+#define DPS_REQUIRE(cond, code, ...)  \
+  do {                                \
+    if (!(cond)) {                    \
+      dps_set_error(__VA_ARGS__);     \
+      return (code);                  \
+    }                                 \
+  } while (0)
+
+#define DPS_CUDA(call)                                                                  \
+  do {                                                                                  \
+    cudaError_t e_ = (call);                                                            \
+    if (e_ != cudaSuccess) {                                                            \
+      dps_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__,   \
+                    __LINE__);                                                          \
+      return DPS_ERR_CUDA;                                                              \
+    }                                                                                   \
+  } while (0)
+
+#define DPS_LAUNCH_CHECK(name)                                                          \
+  do {                                                                                  \
+    cudaError_t e_ = cudaGetLastError();                                                \
+    if (e_ != cudaSuccess) {                                                            \
+      dps_set_error("launch of %s failed: %s", name, cudaGetErrorString(e_));           \
+      return DPS_ERR_CUDA;                                                              \
+    }                                                                                   \
+    dps_count_launch();                                                                 \
+  } while (0)
+
+static inline bool dps_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// ---------------------------------------------------------------------------------------------
+// device side
+// ---------------------------------------------------------------------------------------------
+#define DPS_DEV __device__ __forceinline__
+
+// Streaming 128-bit accesses: every particle tensor is touched once per kernel, so keep it out of
+// L1 (ld.global.nc.L1::no_allocate) and let L2/HBM stream.
+DPS_DEV float4 ldg_stream4(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+DPS_DEV float ldg_stream(const float* p) {
+  float r;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+  return r;
+}
+DPS_DEV void stg_stream4(float* p, const float4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x),
+               "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+// x̂₀ = clamp(c1·x − c2·ε): separate mul, mul, sub — never contracted into an FMA, so the value is
+// bit-identical to the reference's three ATen kernels (posterior_mean_variance.py:120-123) and to
+// itself wherever it is recomputed (forward, adjoint mask, update).
+DPS_DEV float x0_pre(float x, float e, float c1, float c2) {
+  return __fsub_rn(__fmul_rn(c1, x), __fmul_rn(c2, e));
+}
+DPS_DEV float clamp1(float v) { return fminf(fmaxf(v, -1.0f), 1.0f); }
+DPS_DEV float x0_of(float x, float e, float c1, float c2, int clip) {
+  float p = x0_pre(x, e, c1, c2);
+  return clip ? clamp1(p) : p;
+}
+// clamp backward: gradient passes where −1 ≤ pre ≤ 1 (inclusive, torch clamp_backward)
+DPS_DEV float clamp_pass(float pre) { return (pre >= -1.0f && pre <= 1.0f) ? 1.0f : 0.0f; }
+
+DPS_DEV float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+DPS_DEV double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-wide sum of two values with a fixed tree (xor-shuffle inside warps, then warp 0 over the
+// per-warp results).  Result valid in thread 0.  `red` must hold 2*32 floats.  The order depends
+// only on blockDim, never on the grid, so partial sums are reproducible.
+DPS_DEV void block_sum2(float& a, float& b, float* red) {
+  a = warp_sum(a);
+  b = warp_sum(b);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  if (lane == 0) {
+    red[warp] = a;
+    red[32 + warp] = b;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    a = lane < nw ? red[lane] : 0.0f;
+    b = lane < nw ? red[32 + lane] : 0.0f;
+    a = warp_sum(a);
+    b = warp_sum(b);
+  }
+  __syncthreads();
+}
+
+DPS_DEV int reflect_idx(int i, int n) {  // ReflectionPad2d semantics (no edge repeat), |excursion| < n
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * (n - 1) - i;
+  return i;
+}

@@ -1,0 +1,92 @@
+// Inpainting operator (measurements.py:151-168): A x = mask ⊙ x, Aᵀ = A.  Pure streaming.
+// Bytes per particle: forward 2T (x, ε) + T (write r) [mask/y are shared and stay in L2];
+// adjoint T (r) + 2T (x, ε for the clamp mask) + T (write g).  HBM-bound.
+#include "operator.cuh"
+
+namespace {
+constexpr int kThreads = 256;
+constexpr int kVec = 2;
+constexpr int kPerBlock4 = kThreads * kVec;  // float4 per CTA
+
+__global__ void __launch_bounds__(kThreads) inpaint_fwd_kernel(const FwdArgs a, const float* __restrict__ mask,
+                                                               int64_t chw4, int hw4, int P) {
+  __shared__ float red[64];
+  const int n = blockIdx.y;
+  const float* x = a.src.x + n * a.src.x_stride;
+  const float* eps = a.src.eps ? a.src.eps + n * a.src.eps_stride : nullptr;
+  const float* y = a.y ? a.y + n * a.y_stride : nullptr;
+  float* out = a.out + n * chw4 * 4;
+  float sq = 0.f, ab = 0.f;
+#pragma unroll
+  for (int u = 0; u < kVec; ++u) {
+    const int64_t i4 = (int64_t)blockIdx.x * kPerBlock4 + u * kThreads + threadIdx.x;
+    if (i4 >= chw4) continue;
+    const float4 x0 = src_load4(x, eps, i4 * 4, a.src.c1, a.src.c2, a.src.clip);
+    const float4 m = *reinterpret_cast<const float4*>(mask + (i4 % hw4) * 4);
+    float4 o = make_float4(__fmul_rn(x0.x, m.x), __fmul_rn(x0.y, m.y), __fmul_rn(x0.z, m.z),
+                           __fmul_rn(x0.w, m.w));
+    if (y) {
+      const float4 yv = *reinterpret_cast<const float4*>(y + i4 * 4);
+      o = make_float4(__fsub_rn(yv.x, o.x), __fsub_rn(yv.y, o.y), __fsub_rn(yv.z, o.z),
+                      __fsub_rn(yv.w, o.w));
+    }
+    stg_stream4(out + i4 * 4, o);
+    sq += o.x * o.x + o.y * o.y + o.z * o.z + o.w * o.w;
+    ab += fabsf(o.x) + fabsf(o.y) + fabsf(o.z) + fabsf(o.w);
+  }
+  if (a.partials) {
+    block_sum2(sq, ab, red);
+    if (threadIdx.x == 0) {
+      float* p = a.partials + ((int64_t)n * P + blockIdx.x) * 2;
+      p[0] = sq;
+      p[1] = ab;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) inpaint_adj_kernel(const AdjArgs a, const float* __restrict__ mask,
+                                                               int64_t chw4, int hw4) {
+  const int n = blockIdx.y;
+  const float* r = a.r + n * chw4 * 4;
+  const float coef = a.coef ? a.coef[n] : 1.0f;
+  const float* extra = a.extra ? a.extra + n * a.extra_stride : nullptr;
+  float* g = a.g + n * a.g_stride;
+#pragma unroll
+  for (int u = 0; u < kVec; ++u) {
+    const int64_t i4 = (int64_t)blockIdx.x * kPerBlock4 + u * kThreads + threadIdx.x;
+    if (i4 >= chw4) continue;
+    const float4 rv = ldg_stream4(r + i4 * 4);
+    const float4 m = *reinterpret_cast<const float4*>(mask + (i4 % hw4) * 4);
+    const float4 pass = mask_load4(a.mask_src, a.has_mask, n, i4 * 4);
+    float4 o = make_float4(coef * (m.x * rv.x), coef * (m.y * rv.y), coef * (m.z * rv.z),
+                           coef * (m.w * rv.w));
+    if (extra) {
+      const float4 e = ldg_stream4(extra + i4 * 4);
+      o.x += e.x; o.y += e.y; o.z += e.z; o.w += e.w;
+    }
+    o.x *= pass.x; o.y *= pass.y; o.z *= pass.z; o.w *= pass.w;
+    stg_stream4(g + i4 * 4, o);
+  }
+}
+}  // namespace
+
+int inpaint_partials(int C, int H, int W) {
+  const int64_t chw4 = (int64_t)C * H * W / 4;
+  return (int)((chw4 + kPerBlock4 - 1) / kPerBlock4);
+}
+
+int inpaint_forward(const dps_operator* op, const FwdArgs& a, cudaStream_t st) {
+  const int64_t chw4 = (int64_t)op->C * op->H * op->W / 4;
+  dim3 grid((unsigned)op->P, (unsigned)a.n);
+  inpaint_fwd_kernel<<<grid, kThreads, 0, st>>>(a, op->mask_dev, chw4, op->H * op->W / 4, op->P);
+  DPS_LAUNCH_CHECK("inpaint_forward");
+  return DPS_OK;
+}
+
+int inpaint_adjoint(const dps_operator* op, const AdjArgs& a, cudaStream_t st) {
+  const int64_t chw4 = (int64_t)op->C * op->H * op->W / 4;
+  dim3 grid((unsigned)op->P, (unsigned)a.n);
+  inpaint_adj_kernel<<<grid, kThreads, 0, st>>>(a, op->mask_dev, chw4, op->H * op->W / 4);
+  DPS_LAUNCH_CHECK("inpaint_adjoint");
+  return DPS_OK;
+}

@@ -1,0 +1,102 @@
+// Operator plan (immutable device tables) shared by the operator translation units.
+#pragma once
+#include "common.cuh"
+
+struct SepTables;     // blur_separable.cu
+struct SparseTables;  // blur_sparse.cu
+struct ResizeTables;  // resize.cu
+struct PhaseTables;   // phase.cu
+
+struct dps_operator {
+  int kind = 0;
+  int C = 0, H = 0, W = 0;
+  int oC = 0, oH = 0, oW = 0;
+  int P = 0;               // partial sums per particle written by forward
+  int64_t aux_floats = 0;  // per particle
+  int taps = 0;
+  int device = 0;
+  float* mask_dev = nullptr;  // inpainting: (H*W)
+  SepTables* sep = nullptr;
+  SparseTables* sparse = nullptr;
+  ResizeTables* resize = nullptr;
+  PhaseTables* phase = nullptr;
+};
+
+// Arguments common to every forward / adjoint launch (already validated by operator.cu).
+struct FwdArgs {
+  dps_source src;
+  const float* y;  // nullable
+  int64_t y_stride;
+  float* out;
+  float* partials;  // nullable, (N, P, 2)
+  float* aux;       // nullable
+  int n;
+};
+struct AdjArgs {
+  const float* r;
+  const float* coef;  // nullable
+  dps_source mask_src;
+  int has_mask;
+  const float* extra;  // nullable
+  int64_t extra_stride;
+  float* g;
+  int64_t g_stride;
+  const float* aux;
+  int n;
+};
+
+// x̂₀ of one element given the source descriptor and per-particle base pointers
+DPS_DEV float src_load(const float* x, const float* eps, int64_t i, float c1, float c2, int clip) {
+  const float xv = ldg_stream(x + i);
+  if (!eps) return xv;
+  return x0_of(xv, ldg_stream(eps + i), c1, c2, clip);
+}
+DPS_DEV float4 src_load4(const float* x, const float* eps, int64_t i, float c1, float c2, int clip) {
+  float4 xv = ldg_stream4(x + i);
+  if (!eps) return xv;
+  const float4 ev = ldg_stream4(eps + i);
+  xv.x = x0_of(xv.x, ev.x, c1, c2, clip);
+  xv.y = x0_of(xv.y, ev.y, c1, c2, clip);
+  xv.z = x0_of(xv.z, ev.z, c1, c2, clip);
+  xv.w = x0_of(xv.w, ev.w, c1, c2, clip);
+  return xv;
+}
+// clamp-backward mask of one element (1 when no mask source / no eps / no clipping)
+DPS_DEV float mask_load(const dps_source& s, int has_mask, int n, int64_t i) {
+  if (!has_mask || !s.eps || !s.clip) return 1.0f;
+  const float xv = ldg_stream(s.x + n * s.x_stride + i);
+  const float ev = ldg_stream(s.eps + n * s.eps_stride + i);
+  return clamp_pass(x0_pre(xv, ev, s.c1, s.c2));
+}
+DPS_DEV float4 mask_load4(const dps_source& s, int has_mask, int n, int64_t i) {
+  if (!has_mask || !s.eps || !s.clip) return make_float4(1.f, 1.f, 1.f, 1.f);
+  const float4 xv = ldg_stream4(s.x + n * s.x_stride + i);
+  const float4 ev = ldg_stream4(s.eps + n * s.eps_stride + i);
+  return make_float4(clamp_pass(x0_pre(xv.x, ev.x, s.c1, s.c2)), clamp_pass(x0_pre(xv.y, ev.y, s.c1, s.c2)),
+                     clamp_pass(x0_pre(xv.z, ev.z, s.c1, s.c2)), clamp_pass(x0_pre(xv.w, ev.w, s.c1, s.c2)));
+}
+
+// per-operator launchers (each returns DPS_OK / error)
+int inpaint_forward(const dps_operator* op, const FwdArgs& a, cudaStream_t st);
+int inpaint_adjoint(const dps_operator* op, const AdjArgs& a, cudaStream_t st);
+
+int sep_create(dps_operator* op, const float* taps1d_v, const float* taps1d_h, int rv, int rh);
+void sep_destroy(dps_operator* op);
+int sep_forward(const dps_operator* op, const FwdArgs& a, cudaStream_t st);
+int sep_adjoint(const dps_operator* op, const AdjArgs& a, cudaStream_t st);
+
+int sparse_create(dps_operator* op, const float* kernel, int ksize);
+void sparse_destroy(dps_operator* op);
+int sparse_forward(const dps_operator* op, const FwdArgs& a, cudaStream_t st);
+int sparse_adjoint(const dps_operator* op, const AdjArgs& a, cudaStream_t st);
+
+int resize_create(dps_operator* op, const int32_t* fov_h, const float* w_h, int taps_h, int out_h,
+                  const int32_t* fov_w, const float* w_w, int taps_w, int out_w);
+void resize_destroy(dps_operator* op);
+int resize_forward(const dps_operator* op, const FwdArgs& a, cudaStream_t st);
+int resize_adjoint(const dps_operator* op, const AdjArgs& a, cudaStream_t st);
+
+int phase_create(dps_operator* op, int pad);
+void phase_destroy(dps_operator* op);
+int phase_forward(const dps_operator* op, const FwdArgs& a, cudaStream_t st);
+int phase_adjoint(const dps_operator* op, const AdjArgs& a, cudaStream_t st);

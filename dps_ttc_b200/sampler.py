@@ -1,0 +1,456 @@
+"""Samplers with the reference's names, constructor and `p_sample_loop` signatures
+(guided_diffusion/gaussian_diffusion.py), re-designed around the fused kernels.
+
+One guided step (ddpm/ddim + ps / ps_anneal / ps_semantic / mcg) is
+
+    UNet forward (reference module, under autograd)                                   [torch]
+    residual      r = y − A(clamp(c1·x − c2·ε)), per-CTA Σr²                         [kernel 1]
+    coefficients  ‖r‖ₙ, −ζ/‖r‖ₙ                                                      [kernel 2, O(N)]
+    cotangent     g = 1[|pre| ≤ 1] ⊙ (coefₙ·Aᵀr + semantic term) → ε-channels of G6  [kernel 3]
+    UNet VJP      vjp = autograd.grad(model_out, x, G6)                               [torch]
+    update        x' = μ(x̂₀,x) + σ(v)·z − (c1·g − c2·vjp)                            [kernel 4]
+
+with no host synchronisation, no table upload and no intermediate particle tensor other than r, g and
+vjp.  The reference does the same work in ~430-650 ATen calls with ≥3 device→host syncs per step
+(SURVEY §3, App. A.6).
+
+Per-step RNG draw order on the particle device is the reference's: z ~ randn_like(x), then
+randn_like(measurement) for q_sample, then the resampling uniforms.
+"""
+from __future__ import annotations
+
+import functools
+import math
+
+import numpy as np
+import torch
+
+from . import kernels
+from ._lib import DPS_COEF_NORM, DpsError
+from .conditioning import ConditioningMethod, GuidanceSpec
+from .operators import B200Operator
+from .registry import get_sampler, register_sampler
+from .schedule import Schedule, anneal_factor, named_beta_schedule, space_timesteps
+
+
+def create_sampler(sampler, steps, noise_schedule, model_mean_type, model_var_type, dynamic_threshold,
+                   clip_denoised, rescale_timesteps, timestep_respacing=""):
+    """gaussian_diffusion.py:34-56, same arguments (the YAML of configs/diffusion_config.yaml)."""
+    cls = get_sampler(name=sampler)
+    betas = named_beta_schedule(noise_schedule, steps)
+    respacing = timestep_respacing if timestep_respacing else [steps]
+    return cls(use_timesteps=space_timesteps(steps, respacing), betas=betas, model_mean_type=model_mean_type,
+               model_var_type=model_var_type, dynamic_threshold=dynamic_threshold, clip_denoised=clip_denoised,
+               rescale_timesteps=rescale_timesteps)
+
+
+# ------------------------------------------------------------------------------------------------
+# noise sources
+# ------------------------------------------------------------------------------------------------
+class TorchNoise:
+    """Draws from torch's global generators exactly where the reference does."""
+
+    def z(self, idx, like):
+        return torch.randn_like(like)
+
+    def q(self, idx, like):
+        return torch.randn_like(like)
+
+    def uniforms(self, idx, n, device):
+        # torch.multinomial on CPU consumes n fp64 uniforms of the global CPU generator (pinned in tests)
+        return torch.rand(n, dtype=torch.float64).to(device, non_blocking=True)
+
+
+class NoiseTape:
+    """Pre-recorded draws (e.g. captured from a reference run, or produced on the host): per step a
+    pinned host tensor that is copied to the device inside the step — the e2e / parity path."""
+
+    def __init__(self, z=None, q=None, uniforms=None, pin=True):
+        def prep(d):
+            if d is None:
+                return {}
+            out = {}
+            for k, t in d.items():
+                t = t.contiguous()
+                out[k] = t.pin_memory() if (pin and torch.cuda.is_available() and not t.is_cuda) else t
+            return out
+        self._z, self._q, self._u = prep(z), prep(q), prep(uniforms)
+        self.h2d_bytes = 0
+
+    def _get(self, table, idx, like_shape, device, dtype):
+        if idx not in table:
+            raise DpsError(f"noise tape has no entry for step {idx}")
+        t = table[idx]
+        self.h2d_bytes += t.numel() * t.element_size()
+        return t.to(device, non_blocking=True).to(dtype).reshape(like_shape)
+
+    def z(self, idx, like):
+        return self._get(self._z, idx, like.shape, like.device, like.dtype)
+
+    def q(self, idx, like):
+        if idx not in self._q:
+            return None
+        return self._get(self._q, idx, like.shape, like.device, like.dtype)
+
+    def uniforms(self, idx, n, device):
+        return self._get(self._u, idx, (n,), device, torch.float64)
+
+
+def _resolve_cond_fn(fn):
+    """Unwrap functools.partial layers (the drivers bind mask=…/l1=… this way) down to the bound method."""
+    bound = {}
+    while isinstance(fn, functools.partial):
+        bound = {**fn.keywords, **bound}
+        fn = fn.func
+    return getattr(fn, "__self__", None), fn, bound
+
+
+# ------------------------------------------------------------------------------------------------
+# base chain
+# ------------------------------------------------------------------------------------------------
+class SpacedSampler:
+    """GaussianDiffusion + SpacedDiffusion (gaussian_diffusion.py:59-117, :395-463) on fp64 host tables."""
+    kind = "ddpm"
+    _VAR_MODES = {"learned_range": 0, "fixed_small": 1, "fixed_large": 1, "learned": 2}
+
+    def __init__(self, use_timesteps, betas, model_mean_type, model_var_type, dynamic_threshold, clip_denoised,
+                 rescale_timesteps):
+        if model_mean_type != "epsilon":
+            raise NotImplementedError(f"model_mean_type={model_mean_type!r}: the fused kernels cover the 'epsilon' "
+                                      "processor that configs/diffusion_config.yaml selects (SURVEY §8f row 4)")
+        if model_var_type not in self._VAR_MODES:
+            raise NameError(f"Name {model_var_type} is not defined.")
+        if dynamic_threshold:
+            raise NotImplementedError("dynamic_threshold (quantile clipping) is not covered (SURVEY §8f row 4)")
+        self.schedule = Schedule(betas, use_timesteps, rescale_timesteps)
+        s = self.schedule
+        self.betas, self.num_timesteps, self.timestep_map = s.betas, s.num_timesteps, s.timestep_map
+        self.original_num_steps, self.rescale_timesteps = s.original_num_steps, s.rescale_timesteps
+        for name in ("alphas_cumprod", "alphas_cumprod_prev", "sqrt_alphas_cumprod", "sqrt_one_minus_alphas_cumprod",
+                     "sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod", "posterior_variance",
+                     "posterior_log_variance_clipped", "posterior_mean_coef1", "posterior_mean_coef2"):
+            setattr(self, name, getattr(s, name))
+        self.model_var_type = model_var_type
+        self.var_mode = self._VAR_MODES[model_var_type]
+        self.clip_denoised = bool(clip_denoised)
+        self.eta = 0.0
+        self.noise = TorchNoise()
+        self.parity_rng = True      # also draw the (unused) q_sample noise, keeping the reference's RNG stream
+        self.last_stats = {}
+
+    # -- helpers ----------------------------------------------------------------------------------
+    def _idx(self, t) -> int:
+        return int(t.reshape(-1)[0]) if torch.is_tensor(t) else int(t)
+
+    def _max_log(self, k):
+        if self.model_var_type == "fixed_small":
+            return k.fixed_small_log
+        if self.model_var_type == "fixed_large":
+            return k.fixed_large_log
+        return None
+
+    def _model_out(self, model, x, k):
+        t = torch.full((1,), k.model_t, device=x.device, dtype=torch.float32)
+        out = model(x, t)
+        C = x.shape[1]
+        if out.shape[1] == 2 * C:
+            return out, out[:, :C], out[:, C:]
+        if self.var_mode in (0, 2):
+            raise DpsError(f"model_var_type={self.model_var_type} needs a model with 2·C output channels")
+        return out, out, None
+
+    def _needs_z(self, k):
+        return bool(k.noise_on and (self.kind == "ddpm" or k.ddim_sigma != 0.0))
+
+    def _draws(self, idx, img, y, k, need_q=False):
+        """z then q — the reference's per-step draw order (p_sample :472/:494, then q_sample :145)."""
+        z = self.noise.z(idx, img) if (self.parity_rng or self._needs_z(k)) else None
+        q = self.noise.q(idx, y) if (self.parity_rng or need_q) else None
+        return z, q
+
+    # -- reference API ----------------------------------------------------------------------------
+    def q_sample(self, x_start, t):
+        """gaussian_diffusion.py:134-151 (draws randn_like(x_start))."""
+        k = self.schedule.consts(self._idx(t))
+        noise = torch.randn_like(x_start)
+        if x_start.is_cuda:
+            return kernels.q_sample(x_start, noise, k.sqrt_acp, k.sqrt_1macp)
+        return k.sqrt_acp * x_start + k.sqrt_1macp * noise
+
+    def p_mean_variance(self, model, x, t):
+        """gaussian_diffusion.py:308-330 — differentiable w.r.t. x through the model like the original."""
+        k = self.schedule.consts(self._idx(t))
+        _, eps, v = self._model_out(model, x, k)
+        pre = k.c1 * x - k.c2 * eps
+        x0 = pre.clamp(-1, 1) if self.clip_denoised else pre
+        mean = k.p1 * x0 + k.p2 * x
+        if self.var_mode == 0:
+            frac = (v + 1.0) / 2.0
+            logvar = frac * k.max_log + (1 - frac) * k.min_log
+        elif self.var_mode == 1:
+            logvar = torch.full_like(x, self._max_log(k))
+        else:
+            logvar = v
+        return {"mean": mean, "variance": torch.exp(logvar), "log_variance": logvar, "pred_xstart": x0}
+
+    def p_sample(self, model, x, t):
+        """DDPM.p_sample / DDIM.p_sample (:468-509): returns {'sample', 'pred_xstart'}; pred_xstart stays
+        connected to x for autograd-based conditioning, the sample comes from the fused kernel."""
+        idx = self._idx(t)
+        k = self.schedule.consts(idx, self.eta)
+        out, eps, v = self._model_out(model, x, k)
+        pre = k.c1 * x - k.c2 * eps
+        x0 = pre.clamp(-1, 1) if self.clip_denoised else pre
+        z = self.noise.z(idx, x)
+        xd, ed = x.detach(), eps.detach()
+        sample, _, _ = kernels.posterior_update(self.kind, xd, ed, None if v is None else v.detach(), z, k,
+                                                clip=self.clip_denoised, var_mode=self.var_mode,
+                                                max_log=self._max_log(k))
+        return {"sample": sample, "pred_xstart": x0}
+
+    # -- the fused guided step --------------------------------------------------------------------
+    def _buffers(self, x):
+        key = (tuple(x.shape), x.device)
+        if getattr(self, "_buf_key", None) != key:
+            n, C, H, W = x.shape
+            self._buf_key = key
+            self._g6 = torch.zeros((n, 2 * C, H, W), device=x.device, dtype=torch.float32)  # ε | v cotangent, v half stays 0
+            self._g3 = torch.zeros((n, C, H, W), device=x.device, dtype=torch.float32)
+        return self._g6, self._g3
+
+    def guided_step(self, model, x, idx, measurement, method, spec: GuidanceSpec, cond_kwargs, noisy_measurement=None,
+                    z=None):
+        """One reverse step with measurement guidance.  Returns (x_next, meas_dist (N,), sem_dist or None)."""
+        k = self.schedule.consts(idx, self.eta)
+        op = method.operator
+        x = x.detach().requires_grad_(True)
+        with torch.enable_grad():
+            out, eps, v = self._model_out(model, x, k)
+        xd = x.detach()
+        out_d = out.detach()
+        C = x.shape[1]
+        eps_d = out_d[:, :C] if out_d.shape[1] == 2 * C else out_d
+        v_d = out_d[:, C:] if out_d.shape[1] == 2 * C else None
+        # kernel 1: residual + partial sums, x̂₀ formed on the fly
+        r, partials, aux = op.residual(xd, eps_d, k, self.clip_denoised, measurement, **cond_kwargs)
+        # kernel 2: ‖r‖ and the per-particle coefficient
+        dist, coef = kernels.guidance_coef(partials, spec.coef_mode, spec.scale)
+        # optional semantic term: gradient w.r.t. x̂₀ of s_t·ℓ_sem (external embedder stays PyTorch)
+        extra, sem_dist = None, None
+        if spec.semantic is not None:
+            x0 = kernels.x0_from_eps(xd, eps_d, k, self.clip_denoised).requires_grad_(True)
+            with torch.enable_grad():
+                sem_loss, sem_dist = spec.semantic(x0)
+                extra = torch.autograd.grad(sem_loss.sum(), x0)[0].contiguous()
+            sem_dist = sem_dist.detach()
+        # kernel 3: cotangent w.r.t. the pre-clamp x̂₀ written into the ε-channels of the cotangent buffer
+        g6, g3 = self._buffers(xd)
+        two_c = out.shape[1] == 2 * C
+        g = g6[:, :C] if two_c else g3
+        op.cotangent(r, coef, xd, eps_d, k, self.clip_denoised, extra, out=g, aux=aux, **cond_kwargs)
+        # UNet VJP
+        vjp = None
+        if out.requires_grad:
+            vjp = torch.autograd.grad(out, x, grad_outputs=g6 if two_c else g3)[0]
+        # kernel 4: fused posterior update
+        if z is None and self._needs_z(k):
+            z = self.noise.z(idx, xd)
+        x_next, _, _ = kernels.posterior_update(self.kind, xd, eps_d, v_d, z, k, clip=self.clip_denoised, g=g, vjp=vjp,
+                                                var_mode=self.var_mode, max_log=self._max_log(k))
+        if spec.project:  # mcg: x_t = operator.project(x_t, noisy_measurement)
+            x_next = method.project(data=x_next, noisy_measurement=noisy_measurement, **cond_kwargs)
+        return x_next, dist, sem_dist
+
+    def _generic_step(self, model, img, idx, measurement, cond_fn, extra_kw):
+        """Foreign conditioning function (e.g. the reference's own class): autograd end to end, the
+        x̂₀/sample arithmetic still fused.  Handles every return arity of HEAD."""
+        img = img.detach().requires_grad_(True)
+        with torch.enable_grad():
+            out = self.p_sample(model=model, x=img, t=idx)   # draws z
+            k = self.schedule.consts(idx, self.eta)
+            q_noise = self.noise.q(idx, measurement)            # then the q_sample draw
+            noisy_measurement = None if q_noise is None else kernels.q_sample(measurement, q_noise, k.sqrt_acp, k.sqrt_1macp)
+            sample = out["sample"].clone()
+            res = cond_fn(x_t=sample, measurement=measurement, noisy_measurement=noisy_measurement, x_prev=img,
+                          x_0_hat=out["pred_xstart"], **extra_kw)
+        if not isinstance(res, tuple):
+            return res.detach(), None, None
+        first, dist = res[0], (res[1] if len(res) > 1 else None)
+        third = res[2] if len(res) > 2 else None
+        obj = getattr(getattr(cond_fn, "func", cond_fn), "__self__", None)
+        returns_grad = type(obj).__name__ == "PosteriorSamplingSemanticGuid"
+        x_next = out["sample"] - first if returns_grad else first
+        return x_next.detach(), (dist.detach() if torch.is_tensor(dist) else dist), (third if returns_grad else None)
+
+    def _prepare(self, x_start, measurement, measurement_cond_fn):
+        if not x_start.is_cuda:
+            raise DpsError("x_start must be a CUDA tensor: the B200 samplers have no CPU path")
+        img = x_start.detach().to(torch.float32).contiguous()
+        y = measurement.detach().to(img.device, torch.float32).contiguous()
+        method, fn, bound = _resolve_cond_fn(measurement_cond_fn)
+        fused = isinstance(method, ConditioningMethod) and isinstance(method.operator, B200Operator) \
+            and getattr(method.noiser, "__name__", "gaussian") == "gaussian" \
+            and method.guidance().kind != "none"
+        return img, y, method, bound, fused
+
+    # -- base loop (GaussianDiffusion.p_sample_loop, :175-303) --------------------------------------
+    def p_sample_loop(self, model, x_start, measurement, measurement_cond_fn, record=False, save_root=None, **kwargs):
+        img, y, method, bound, fused = self._prepare(x_start, measurement, measurement_cond_fn)
+        anneal_kw = {k_: kwargs[k_] for k_ in ("anneal_amp", "anneal_scale", "anneal_loc") if k_ in kwargs}
+        callback = kwargs.get("callback")
+        meas_d = sem_d = None
+        for idx in reversed(range(self.num_timesteps)):
+            k = self.schedule.consts(idx, self.eta)
+            t = idx / self.num_timesteps
+            if fused:
+                anneal = anneal_factor(t, kwargs.get("anneal_amp", 1.0), kwargs.get("anneal_scale", 10.0),
+                                       kwargs.get("anneal_loc", 0.5)) if anneal_kw else 1.0
+                spec = method.guidance(beta_scale=k.beta, t=t, anneal=anneal)
+                z, q_noise = self._draws(idx, img, y, k, need_q=spec.project)
+                noisy = kernels.q_sample(y, q_noise, k.sqrt_acp, k.sqrt_1macp) if spec.project else None
+                img, meas_d, sem_d = self.guided_step(model, img, idx, y, method, spec, bound, noisy, z)
+            else:
+                img, meas_d, sem_d = self._generic_step(model, img, idx, y, measurement_cond_fn,
+                                                        {"beta_scale": k.beta, "t": t})
+            if callback is not None:
+                callback(idx, img, meas_d, sem_d)
+        if sem_d is None:
+            sem_d = torch.zeros((), device=img.device)
+        return img, meas_d, sem_d
+
+
+@register_sampler(name="ddpm")
+class DDPM(SpacedSampler):
+    kind = "ddpm"
+
+
+@register_sampler(name="ddim")
+class DDIM(SpacedSampler):
+    kind = "ddim"
+
+    def predict_eps_from_x_start(self, x_t, t, pred_xstart):
+        k = self.schedule.consts(self._idx(t))
+        return (k.c1 * x_t - pred_xstart) / k.c2
+
+
+# ------------------------------------------------------------------------------------------------
+# particle search
+# ------------------------------------------------------------------------------------------------
+class Resampler:
+    """weights → CDF → ancestors → gather, optionally across ranks (dist.ParticleShards)."""
+
+    def __init__(self, scheme="multinomial", linear_weights=True, sync_free=True, shards=None):
+        self.scheme, self.linear, self.sync_free, self.shards = scheme, linear_weights, sync_free, shards
+
+    def ancestors_from(self, logw_all, uniforms, n_draws):
+        w, cdf, lse, degenerate = kernels.weights_cdf(logw_all, linear_mode=self.linear)
+        ids = kernels.ancestors(cdf, uniforms, n_draws, systematic=(self.scheme == "systematic"), degenerate=degenerate)
+        return ids, w, degenerate
+
+
+@register_sampler(name="search_ddpm")
+class SearchDDPM(DDPM):
+    """Greedy best-of-N inside the loop (gaussian_diffusion.py:592-641) and the resample_update
+    potentials (:516-587)."""
+
+    @torch.no_grad()
+    def resample_update(self, candidates, denoised_candidates, operator, measurement, resample=True, rs_temp=0.01,
+                        prev_costs=None, potential_type="min", steps_done=1, uniforms=None, **op_kwargs):
+        n = denoised_candidates.shape[0]
+        if resample and prev_costs is not None:
+            tau = rs_temp / steps_done if potential_type == "mean" else rs_temp
+            logw = kernels.particle_logweights(prev_costs.float().contiguous(), tau=tau)
+            w, cdf, _, degenerate = kernels.weights_cdf(logw, linear_mode=True)
+            if bool(degenerate.item()) is False:  # the reference also syncs here (:545)
+                u = self.noise.uniforms(-1, n, candidates.device) if uniforms is None else uniforms
+                ids = kernels.ancestors(cdf, u, n)
+                candidates = kernels.gather_particles(candidates, ids)
+                denoised_candidates = kernels.gather_particles(denoised_candidates, ids)
+                prev_costs = prev_costs[ids]
+        _, partials, _ = operator.residual(denoised_candidates.contiguous(), y=measurement, **op_kwargs)
+        _, l1 = kernels.particle_norms(partials, want_l1=True)
+        _, C, H, W = denoised_candidates.shape
+        curr = l1 ** 2 / (C * H * W)
+        if prev_costs is None or potential_type == "curr":
+            net = curr
+        elif potential_type == "mean":
+            net = curr + prev_costs
+        elif potential_type == "min":
+            net = torch.minimum(curr, prev_costs)
+        elif potential_type == "diff":
+            net = curr - prev_costs
+        else:
+            raise NotImplementedError
+        return candidates, net
+
+    def p_sample_loop(self, model, x_start, measurement, measurement_cond_fn, record=False, save_root=None,
+                      operator=None, potential_type="min", resample_every_steps=10, rs_temp=0.1, **kwargs):
+        if operator is None:
+            raise TypeError("search_ddpm.p_sample_loop needs operator=")
+        img, y, _, bound, _ = self._prepare(x_start, measurement, measurement_cond_fn)
+        shards = kwargs.get("shards")
+        n = img.shape[0]
+        self.last_stats = {"best": []}
+        for idx in reversed(range(self.num_timesteps)):
+            k = self.schedule.consts(idx)
+            with torch.no_grad():
+                _, eps, v = self._model_out(model, img, k)
+                z = self.noise.z(idx, img)
+                img, _, _ = kernels.posterior_update("ddpm", img, eps, v, z, k, clip=self.clip_denoised,
+                                                     var_mode=self.var_mode, max_log=self._max_log(k))
+                _, partials, _ = operator.residual(img, y=y, **bound)      # ‖y − A(x_{t−1})‖₂, :626-630
+                costs = kernels.particle_norms(partials)
+                if shards is None:
+                    best, _ = kernels.argmin(costs)                            # first minimum, :631
+                    img = kernels.broadcast_particle(img, best, n)             # img[best.repeat(n)], :633
+                else:
+                    img = shards.greedy_broadcast(img, costs)
+        return img
+
+
+@register_sampler(name="ttc_ddim")
+class TTC_DDIM(DDIM):
+    """DDIM + guidance + multinomial particle resampling every 10th index with w = exp(−d/100)
+    (gaussian_diffusion.py:644-707).  `scheme`, `resample_every_steps`, `resample_scale` generalise the
+    constants the reference hard-codes (:661, :689); `shards` spreads the particles over ranks."""
+    resample_every_steps = 10
+    resample_scale = 100.0
+    scheme = "multinomial"
+    lse_weights = False      # True: w = exp(logw − max) instead of the reference's exp(logw)
+    sync_free = True         # False: host check of w.max() != w.min() like the reference (:693)
+
+    def p_sample_loop(self, model, x_start, measurement, measurement_cond_fn, record=False, save_root=None, **kwargs):
+        img, y, method, bound, fused = self._prepare(x_start, measurement, measurement_cond_fn)
+        shards = kwargs.get("shards")
+        sem_weight = kwargs.get("semantic_weight", 0.0)  # config 5: semantic term in the reweighting
+        distance = None
+        self.last_stats = {"ancestors": {}}
+        for idx in reversed(range(self.num_timesteps)):
+            k = self.schedule.consts(idx, self.eta)
+            t = idx / self.num_timesteps
+            sem_d = None
+            if fused:
+                spec = method.guidance(beta_scale=k.beta, t=t)
+                z, q_noise = self._draws(idx, img, y, k, need_q=spec.project)
+                noisy = kernels.q_sample(y, q_noise, k.sqrt_acp, k.sqrt_1macp) if spec.project else None
+                img, distance, sem_d = self.guided_step(model, img, idx, y, method, spec, bound, noisy, z)
+            else:
+                img, distance, _ = self._generic_step(model, img, idx, y, measurement_cond_fn, {})
+            n_local = img.shape[0]
+            n_total = n_local if shards is None else shards.total
+            if n_total > 1 and idx % self.resample_every_steps == 0:
+                logw = kernels.particle_logweights(distance.contiguous(), sem_d if sem_weight else None,
+                                                   tau=1.0 / self.resample_scale, sem_scale=sem_weight)
+                logw_all = logw if shards is None else shards.all_gather_scalars(logw)
+                w, cdf, _, degenerate = kernels.weights_cdf(logw_all, linear_mode=not self.lse_weights)
+                if not self.sync_free and bool(degenerate.item()):
+                    continue
+                u = self.noise.uniforms(idx, 1 if self.scheme == "systematic" else n_total, img.device)
+                ids = kernels.ancestors(cdf, u, n_total, systematic=(self.scheme == "systematic"), degenerate=degenerate)
+                self.last_stats["ancestors"][idx] = ids
+                if shards is None:
+                    img = kernels.gather_particles(img, ids)
+                    distance = distance[ids]
+                else:
+                    img, distance = shards.exchange(img, distance, ids)
+        return img, distance

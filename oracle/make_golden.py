@@ -1,0 +1,251 @@
+"""Generate tests/golden/*.npz by RUNNING THE REFERENCE ITSELF (CPU, this container only).
+
+    python oracle/make_golden.py            # needs /root/reference (read-only) — never runs on the GPU box
+
+The reference has no tests or golden vectors; these fixtures are what pins the oracle
+(oracle/dps_oracle.py) and, through it, the CUDA kernels.  Everything is seeded; draws made inside the
+reference's loops (torch.randn_like, torch.multinomial) are recorded by wrapping the torch functions, so
+the fixtures do not depend on torch's RNG staying bit-stable across versions.
+"""
+from __future__ import annotations
+
+import os
+import sys
+from functools import partial
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(HERE)
+sys.path.insert(0, REPO)
+sys.path.insert(0, os.path.join(REPO, "tests"))
+
+from dps_ttc_b200 import _ref  # noqa: E402  (only for locating the reference + import stubs)
+from helpers import GOLDEN, TinyEps  # noqa: E402
+
+_ref.ensure_reference()
+with _ref.quiet():
+    from guided_diffusion.condition_methods import get_conditioning_method
+    from guided_diffusion.gaussian_diffusion import create_sampler
+    from guided_diffusion.measurements import get_noise, get_operator
+    from util.img_utils import mask_generator
+    from util.resizer import Resizer
+
+torch.set_num_threads(4)
+DIFF = dict(steps=1000, noise_schedule="linear", model_mean_type="epsilon", model_var_type="learned_range",
+            dynamic_threshold=False, clip_denoised=True, rescale_timesteps=True)
+
+
+def save(name, **arrays):
+    os.makedirs(GOLDEN, exist_ok=True)
+    out = {}
+    for k, v in arrays.items():
+        if torch.is_tensor(v):
+            v = v.detach().cpu().numpy()
+        out[k] = np.asarray(v)
+    path = os.path.join(GOLDEN, name)
+    np.savez_compressed(path, **out)
+    print(f"{name}: {os.path.getsize(path) / 1024:.0f} KiB, {len(out)} arrays")
+
+
+class Recorder:
+    """Records every torch.randn_like / torch.multinomial / torch.rand call made while active."""
+
+    def __enter__(self):
+        self.randn, self.multinomial = [], []
+        self._randn_like, self._multinomial = torch.randn_like, torch.multinomial
+
+        def randn_like(t, *a, **k):
+            out = self._randn_like(t, *a, **k)
+            self.randn.append(out.detach().clone())
+            return out
+
+        def multinomial(w, n, replacement=False, **k):
+            state = torch.get_rng_state()
+            out = self._multinomial(w, n, replacement, **k)
+            after = torch.get_rng_state()
+            torch.set_rng_state(state)
+            u = torch.rand(n, dtype=torch.float64)          # the uniforms the CPU kernel consumed
+            assert torch.equal(torch.get_rng_state(), after), "torch.multinomial RNG consumption changed"
+            self.multinomial.append((w.detach().clone(), out.detach().clone(), u))
+            return out
+
+        torch.randn_like, torch.multinomial = randn_like, multinomial
+        return self
+
+    def __exit__(self, *exc):
+        torch.randn_like, torch.multinomial = self._randn_like, self._multinomial
+
+
+def sampler(name, respacing):
+    with _ref.quiet():
+        return create_sampler(sampler=name, timestep_respacing=respacing, **DIFF)
+
+
+# ---------------------------------------------------------------------------------------------
+def gen_schedule():
+    out = {}
+    for tag, resp in (("full", ""), ("r50", "50"), ("r12", "12")):
+        s = sampler("ddpm", resp)
+        out[f"{tag}_timestep_map"] = np.array(s.timestep_map)
+        for attr in ("betas", "alphas_cumprod", "alphas_cumprod_prev", "sqrt_recip_alphas_cumprod",
+                     "sqrt_recipm1_alphas_cumprod", "posterior_mean_coef1", "posterior_mean_coef2",
+                     "posterior_log_variance_clipped", "sqrt_alphas_cumprod", "sqrt_one_minus_alphas_cumprod"):
+            out[f"{tag}_{attr}"] = getattr(s, attr)
+    save("schedule.npz", **out)
+
+
+def gen_resizer():
+    out = {}
+    for n, s in ((256, 4), (256, 8), (64, 4), (32, 4)):
+        r = Resizer((1, 3, n, n), 1 / s)
+        out[f"fov_{n}_{s}"] = r.field_of_view[0].numpy()
+        out[f"w_{n}_{s}"] = r.weights[0].numpy().reshape(r.weights[0].shape[0], -1)
+        out[f"sorted_dims_{n}_{s}"] = np.array(r.sorted_dims)
+    save("resizer.npz", **out)
+
+
+def norm_grad(op, x, y, **kw):
+    x = x.clone().requires_grad_(True)
+    diff = y - op.forward(x, **kw)
+    norm = torch.linalg.norm(diff.reshape(diff.shape[0], -1), dim=-1)
+    (g,) = torch.autograd.grad(norm.sum(), x)
+    return norm.detach(), g
+
+
+def gen_operators():
+    g = torch.Generator().manual_seed(1234)
+    out = {}
+    x = torch.rand(2, 3, 64, 64, generator=g) * 2 - 1
+    out["x"] = x
+    with _ref.quiet():
+        ops = {"gaussian_blur": (get_operator("gaussian_blur", kernel_size=61, intensity=3.0, device="cpu"), {}),
+               "super_resolution": (get_operator("super_resolution", in_shape=(1, 3, 64, 64), scale_factor=4, device="cpu"), {}),
+               "phase_retrieval": (get_operator("phase_retrieval", oversample=2.0, device="cpu"), {})}
+        np.random.seed(8)
+        ops["motion_blur"] = (get_operator("motion_blur", kernel_size=61, intensity=0.5, device="cpu"), {})
+        out["motion_kernel"] = ops["motion_blur"][0].kernel.kernelMatrix
+        np.random.seed(8)
+        mask = mask_generator("random", mask_prob_range=(0.3, 0.7), image_size=64)(x[:1])[:, 0].unsqueeze(0)
+        out["mask"] = mask
+        ops["inpainting"] = (get_operator("inpainting", device="cpu"), {"mask": mask})
+    out["gaussian_kernel"] = ops["gaussian_blur"][0].kernel.numpy()
+    for name, (op, kw) in ops.items():
+        with torch.no_grad():
+            ax = op.forward(x, **kw)
+        y = op.forward(x[:1], **kw).detach() + 0.05 * torch.randn(ax[:1].shape, generator=g)
+        norm, grad = norm_grad(op, x, y, **kw)
+        out[f"{name}_Ax"], out[f"{name}_y"], out[f"{name}_norm"], out[f"{name}_grad"] = ax, y, norm, grad
+    save("operators.npz", **out)
+
+
+def run_trace(tag, sampler_name, respacing, method, params, op_name, op_cfg, n, size, seed, use_loop=True, mask=None,
+              noise_sigma=0.05, anneal=False):
+    """Run the reference's own loop (or an upstream-arity loop assembled from its classes) and record."""
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    model = TinyEps(seed=seed)
+    with _ref.quiet():
+        op = get_operator(op_name, device="cpu", **op_cfg)
+        noiser = get_noise("gaussian", sigma=noise_sigma)
+        cond = get_conditioning_method(method, op, noiser, **params)
+    s = sampler(sampler_name, respacing)
+    kw = {"mask": mask} if mask is not None else {}
+    x_true = torch.rand(1, 3, size, size) * 2 - 1
+    y = noiser(op.forward(x_true, **kw)).detach()
+    x_start = torch.randn(n, 3, size, size)
+    steps = []
+
+    def cond_fn(**k):
+        res = cond.conditioning(**kw, **k)
+        rec = {"x_prev": k["x_prev"].detach().clone(), "x0": k["x_0_hat"].detach().clone()}
+        if method == "ps_semantic":
+            rec["sample"] = k["x_t"].detach().clone()
+            rec["grad"], rec["dist"] = res[0].detach().clone(), res[1].detach().clone()
+        else:
+            rec["x_t_out"], rec["dist"] = res[0].detach().clone(), res[1].detach().clone()
+        steps.append(rec)
+        return res
+
+    with Recorder() as rec, _ref.quiet():
+        if use_loop:
+            extra = {"operator": op} if sampler_name == "search_ddpm" else {}
+            result = s.p_sample_loop(model=model, x_start=x_start.clone(), measurement=y, measurement_cond_fn=cond_fn,
+                                     record=False, save_root=None, **extra)
+        else:
+            img = x_start.clone()
+            for idx in reversed(range(s.num_timesteps)):
+                t = torch.tensor([idx])
+                img = img.requires_grad_()
+                out = s.p_sample(x=img, t=t, model=model)
+                extra = {"beta_scale": s.betas[idx], "anneal": 1.0} if anneal else {}
+                res = cond_fn(x_t=out["sample"], measurement=y, x_prev=img, x_0_hat=out["pred_xstart"], **extra)
+                img = res[0].detach()
+            result = (img, res[1].detach())
+    final = result if torch.is_tensor(result) else result[0]
+    out = {"x_start": x_start, "y": y, "final": final.detach(), "n_steps": np.array(s.num_timesteps)}
+    if not torch.is_tensor(result):
+        out["final_dist"] = result[1].detach()
+    if mask is not None:
+        out["mask"] = mask
+    if op_name == "motion_blur":
+        out["kernel"] = op.kernel.kernelMatrix
+    for i, r in enumerate(rec.randn):
+        out[f"randn_{i}"] = r
+    for i, (w, ids, u) in enumerate(rec.multinomial):
+        out[f"mn_w_{i}"], out[f"mn_ids_{i}"], out[f"mn_u_{i}"] = w, ids, u
+    for i, st in enumerate(steps):
+        for k2, v in st.items():
+            out[f"step{i}_{k2}"] = v
+    save(f"trace_{tag}.npz", **out)
+
+
+def gen_multinomial():
+    out = {}
+    for i, n in enumerate((4, 8, 64, 256)):
+        g = torch.Generator().manual_seed(100 + i)
+        d = torch.rand(n, generator=g) * 40 + 60
+        w = torch.exp(-d / 100)
+        torch.manual_seed(200 + i)
+        ids = torch.multinomial(w, n, replacement=True)
+        torch.manual_seed(200 + i)
+        u = torch.rand(n, dtype=torch.float64)
+        out[f"d_{i}"], out[f"w_{i}"], out[f"ids_{i}"], out[f"u_{i}"] = d, w, ids, u
+    save("multinomial.npz", **out)
+
+
+def gen_masks():
+    out = {}
+    img = torch.zeros(1, 3, 256, 256)
+    for seed in (0, 8):
+        np.random.seed(seed)
+        out[f"random_{seed}"] = mask_generator("random", mask_prob_range=(0.3, 0.7), image_size=256)(img)[0, 0].numpy().astype(np.uint8)
+        np.random.seed(seed)
+        out[f"box_{seed}"] = mask_generator("box", mask_len_range=(128, 129), image_size=256)(img)[0, 0].numpy().astype(np.uint8)
+    save("masks.npz", **out)
+
+
+if __name__ == "__main__":
+    gen_schedule()
+    gen_resizer()
+    gen_operators()
+    gen_multinomial()
+    gen_masks()
+    # the combinations that run at HEAD …
+    run_trace("ddpm_ps_semantic_gblur", "ddpm", "4", "ps_semantic", dict(scale=0.3, sem_guid_scale=0.0),
+              "gaussian_blur", dict(kernel_size=61, intensity=3.0), n=2, size=32, seed=11)
+    run_trace("ttc_ddim_mcg_sr", "ttc_ddim", "12", "mcg", dict(scale=0.5),
+              "super_resolution", dict(in_shape=(1, 3, 32, 32), scale_factor=4), n=4, size=32, seed=12)
+    run_trace("search_ddpm_gblur", "search_ddpm", "4", "ps", dict(scale=0.3),
+              "gaussian_blur", dict(kernel_size=61, intensity=3.0), n=4, size=32, seed=13)
+    # … and upstream-arity loops assembled from the reference's own classes (ps / ps_anneal zero the image
+    # inside HEAD's base loop, App. B)
+    np.random.seed(8)
+    m = mask_generator("random", mask_prob_range=(0.3, 0.7), image_size=32)(torch.zeros(1, 3, 32, 32))[:, 0].unsqueeze(0)
+    run_trace("ddpm_ps_inpaint", "ddpm", "4", "ps", dict(scale=0.5), "inpainting", {}, n=2, size=32, seed=14,
+              use_loop=False, mask=m)
+    run_trace("ddpm_ps_anneal_phase", "ddpm", "3", "ps_anneal", dict(scale=1.0), "phase_retrieval",
+              dict(oversample=2.0), n=2, size=64, seed=15, use_loop=False, anneal=True)
+    run_trace("ddim_ps_motion", "ddim", "3", "ps", dict(scale=0.3), "motion_blur", dict(kernel_size=61, intensity=0.5),
+              n=2, size=64, seed=16, use_loop=False)

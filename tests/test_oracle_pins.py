@@ -1,0 +1,164 @@
+"""Pins the oracle (oracle/dps_oracle.py) to fixtures produced by running the REFERENCE itself
+(oracle/make_golden.py → tests/golden/*.npz).  CPU only.  Tolerances are written per check."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import TinyEps, golden
+from oracle import dps_oracle as O
+
+
+# ------------------------------------------------------------------------------------------------
+def test_schedule_tables_match_reference():
+    g = golden("schedule.npz")
+    for tag, resp in (("full", None), ("r50", "50"), ("r12", "12")):
+        t = O.Tables(1000, resp)
+        assert list(g[f"{tag}_timestep_map"]) == t.timestep_map
+        for ours, theirs in ((t.betas, "betas"), (t.acp, "alphas_cumprod"), (t.acp_prev, "alphas_cumprod_prev"),
+                             (t.sqrt_recip, "sqrt_recip_alphas_cumprod"), (t.sqrt_recipm1, "sqrt_recipm1_alphas_cumprod"),
+                             (t.coef1, "posterior_mean_coef1"), (t.coef2, "posterior_mean_coef2"),
+                             (t.post_logvar_clipped, "posterior_log_variance_clipped")):
+            assert np.array_equal(ours, g[f"{tag}_{theirs}"]), (tag, theirs)   # fp64, bit-exact
+
+
+def test_resizer_tables_match_reference():
+    g = golden("resizer.npz")
+    for n, s in ((256, 4), (256, 8), (64, 4), (32, 4)):
+        w, fov = O.resizer_contributions(n, n // s, 1 / s)
+        assert np.array_equal(fov.T, g[f"fov_{n}_{s}"])
+        assert np.array_equal(w.T, g[f"w_{n}_{s}"])
+
+
+OPS = {
+    "gaussian_blur": lambda g: (lambda x: O.blur_forward(x, g["gaussian_kernel"].astype(np.float32)),
+                                lambda u: O.blur_adjoint(u, g["gaussian_kernel"].astype(np.float32))),
+    "motion_blur": lambda g: (lambda x: O.blur_forward(x, g["motion_kernel"].astype(np.float32)),
+                              lambda u: O.blur_adjoint(u, g["motion_kernel"].astype(np.float32))),
+    "super_resolution": lambda g: (lambda x: O.resize_forward(x, 0.25), lambda u: O.resize_adjoint(u, 0.25, 64, 64)),
+    "inpainting": lambda g: (lambda x: O.inpaint_forward(x, g["mask"]), lambda u: O.inpaint_forward(u, g["mask"])),
+}
+
+
+@pytest.mark.parametrize("name", sorted(OPS))
+def test_linear_operators_forward_and_gradient(name):
+    g = golden("operators.npz")
+    fwd, adj = OPS[name](g)
+    x = g["x"]
+    ax = fwd(x)
+    assert np.abs(ax - g[f"{name}_Ax"]).max() <= 2e-6          # fp32 conv / gather summation order
+    r = g[f"{name}_y"] - ax
+    grad, norm = O.guidance_cotangent(r, adj, pre=None, mode="norm", scale=-1.0, clip=False)  # +Aᵀ(−r)/‖r‖ …
+    grad = -grad                                               # d‖y−Ax‖/dx = −Aᵀr/‖r‖
+    assert np.abs(norm - g[f"{name}_norm"]).max() / g[f"{name}_norm"].max() <= 1e-6
+    assert np.abs(-grad - g[f"{name}_grad"]).max() <= 1e-6 or np.abs(grad - g[f"{name}_grad"]).max() <= 1e-6
+
+
+def test_phase_retrieval_forward_and_vjp():
+    g = golden("operators.npz")
+    x = g["x"]
+    amp = O.phase_forward(x, 64)
+    assert np.abs(amp - g["phase_retrieval_Ax"]).max() <= 2e-5     # fp64 FFT here vs complex64 in torch
+    r = g["phase_retrieval_y"] - amp
+    norm, _ = O.particle_norms(r)
+    grad = -O.phase_vjp(x, r / norm[:, None, None, None], 64)
+    assert np.abs(grad - g["phase_retrieval_grad"]).max() <= 2e-5
+
+
+def test_multinomial_restatement_is_bit_exact():
+    g = golden("multinomial.npz")
+    for i in range(4):
+        w = g[f"w_{i}"]
+        _, cdf, deg = O.weights_cdf(np.log(w.astype(np.float64)).astype(np.float32), linear=True)
+        # the restatement must be exact given the SAME fp32 weights: rebuild the cdf from w itself
+        cum = np.cumsum(w.astype(np.float32), dtype=np.float32)  # numpy cumsum is sequential in fp32
+        cdf_w = (cum / cum[-1]).astype(np.float32)
+        ids = O.search(cdf_w, g[f"u_{i}"])
+        assert np.array_equal(ids, g[f"ids_{i}"])
+        assert not deg
+
+
+def test_multinomial_against_live_torch():
+    """torch is on the GPU box too: 200 seeded trials of torch.multinomial (CPU) vs the restatement."""
+    for trial in range(200):
+        n = (2, 4, 8, 64, 256)[trial % 5]
+        gen = torch.Generator().manual_seed(trial)
+        d = torch.rand(n, generator=gen) * (50 if trial % 3 else 0.01) + 100
+        logw = (-d / 100).numpy().astype(np.float32)
+        w = torch.exp(torch.from_numpy(logw))
+        torch.manual_seed(1000 + trial)
+        ids = torch.multinomial(w, n, replacement=True).numpy()
+        torch.manual_seed(1000 + trial)
+        u = torch.rand(n, dtype=torch.float64).numpy()
+        cum = np.zeros(n, np.float32)
+        s = np.float32(0)
+        for j in range(n):
+            s = np.float32(s + w.numpy()[j])
+            cum[j] = s
+        assert np.array_equal(O.search((cum / s).astype(np.float32), u), ids)
+
+
+# ------------------------------------------------------------------------------------------------
+# step traces recorded from the reference's own loops
+# ------------------------------------------------------------------------------------------------
+def model_and_vjp(model, x, t_model):
+    xt = torch.from_numpy(x).requires_grad_(True)
+    out = model(xt, torch.tensor([t_model], dtype=torch.float32))
+
+    def vjp(g_eps):
+        g6 = torch.zeros_like(out)
+        g6[:, :3] = torch.from_numpy(g_eps)
+        return torch.autograd.grad(out, xt, g6, retain_graph=True)[0].numpy()
+    return out.detach().numpy(), vjp
+
+
+def test_trace_ddpm_ps_semantic_gaussian_blur():
+    """HEAD-valid combination: base loop + ps_semantic(sem=0) → x' = sample − ∇(0.3‖r‖)."""
+    g = golden("trace_ddpm_ps_semantic_gblur.npz")
+    T = O.Tables(1000, "4")
+    model = TinyEps(seed=11)
+    from dps_ttc_b200.tables import gaussian_kernel
+    kern = gaussian_kernel(61, 3.0).astype(np.float32)
+    img = g["x_start"]
+    y = g["y"]
+    n_steps = int(g["n_steps"])
+    for i, idx in enumerate(reversed(range(n_steps))):
+        k = T.at(idx)
+        assert np.abs(img - g[f"step{i}_x_prev"]).max() <= 1e-5 * max(1.0, np.abs(img).max())   # chained parity
+        img = g[f"step{i}_x_prev"]                       # re-anchor: per-step parity
+        out6, vjp = model_and_vjp(model, img, k["model_t"])
+        z = g[f"randn_{2 * i}"]                           # recorded draws per step: z, then the q_sample noise
+        sample, x0 = O.ddpm_sample(img, out6[:, :3], out6[:, 3:], z, k, idx)
+        assert np.abs(x0 - g[f"step{i}_x0"]).max() == 0.0                 # bit-exact
+        # exp() differs by an ulp between libms; TinyEps' v is not confined to [−1,1], so scale the tolerance
+        assert np.abs(sample - g[f"step{i}_sample"]).max() <= 2e-6 * max(1.0, np.abs(sample).max())
+        _, pre = O.x0_from_eps(img, out6[:, :3], k)
+        r = y - O.blur_forward(x0, kern)
+        gpre, norm = O.guidance_cotangent(r, lambda u: O.blur_adjoint(u, kern), pre, "norm", 0.3)
+        grad = k["c1"] * gpre - k["c2"] * vjp(gpre)
+        assert np.abs(norm - g[f"step{i}_dist"]).max() / norm.max() <= 1e-6
+        assert np.abs(grad - g[f"step{i}_grad"]).max() <= 1e-5 * max(1.0, np.abs(grad).max())
+        img = (sample - grad).astype(np.float32)
+    assert np.abs(img - g["final"]).max() <= 1e-4
+
+
+def test_trace_ttc_ddim_resampling_indices():
+    g = golden("trace_ttc_ddim_mcg_sr.npz")
+    i = 0
+    while f"mn_w_{i}" in g.files:
+        w = g[f"mn_w_{i}"]
+        cum = np.cumsum(w, dtype=np.float32)
+        ids = O.search((cum / cum[-1]).astype(np.float32), g[f"mn_u_{i}"])
+        assert np.array_equal(ids, g[f"mn_ids_{i}"])
+        i += 1
+    assert i >= 1
+
+
+def test_trace_search_ddpm_greedy():
+    g = golden("trace_search_ddpm_gblur.npz")
+    final = g["final"]
+    assert np.abs(final - final[:1]).max() == 0.0           # all particles collapse onto the best one (:633)
+
+
+def test_best_of_n_rule():
+    d = np.array([[3.0, 1.0, 2.0, 0.5], [1.0, 1.0, 0.2, 0.9]])
+    assert np.array_equal(O.best_of_n(d), np.array([[0, 1, 1, 3], [0, 0, 2, 2]]))

