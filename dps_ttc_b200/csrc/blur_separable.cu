@@ -3,8 +3,9 @@
 //
 // Formulation.  In 1-D, "reflect-pad then correlate" is the banded matrix
 //     A[i][m] = Σ_{d : reflect(i+d) = m} w[d+r],   |i − m| ≤ r,
-// which equals the plain taps w[m−i+r] except in the r rows next to each border, where the mirrored
-// taps fold back onto the band.  Forward applies A_v ⊗ A_h, the adjoint A_vᵀ ⊗ A_hᵀ: the SAME kernel
+// which equals the plain taps w[m−i+r] except next to each border, where the mirrored taps fold back
+// onto the band: rows i < r of A, and rows m ≤ r of Aᵀ (column r of A still receives w[0] from row 0) —
+// hence R+1 border rows per side in the tables below.  Forward applies A_v ⊗ A_h, the adjoint A_vᵀ ⊗ A_hᵀ: the SAME kernel
 // with different tap tables (interior taps as kernel parameters → constant-bank FFMA operands,
 // border rows from a small table in shared memory).  No padded image is ever materialised.
 //
@@ -31,7 +32,7 @@ template <int R>
 struct SepParams {
   float wv[2 * R + 1];  // interior vertical taps, index e+R multiplies input row i+e
   float wh[2 * R + 1];
-  const float* bv;  // border rows: (2R, 2R+1); rows [0,R) top, [R,2R) bottom
+  const float* bv;  // border rows: (2(R+1), 2R+1); rows [0,R] top, then rows [L-1-R, L-1] bottom
   const float* bh;
   int C, H, W;
   int strips;  // ceil(H / kRows)
@@ -60,9 +61,10 @@ __global__ void __launch_bounds__(kThreads) sep_kernel(const SepParams<R> p, con
   const int SW = W + 2 * R;             // tile row stride (multiple of 4)
   const int tile_rows = kRows + 2 * R;  // staged rows
   float* tile = smem;
-  float* bvs = tile + tile_rows * SW;   // (2R)(2R+1)
-  float* bhs = bvs + 2 * R * (2 * R + 1);
-  float* red = bhs + 2 * R * (2 * R + 1);  // 64 floats
+  constexpr int kBorder = 2 * (R + 1) * (2 * R + 1);
+  float* bvs = tile + tile_rows * SW;
+  float* bhs = bvs + kBorder;
+  float* red = bhs + kBorder;  // 64 floats
 
   const int strip = blockIdx.x % p.strips;
   const int c = blockIdx.x / p.strips;
@@ -71,7 +73,7 @@ __global__ void __launch_bounds__(kThreads) sep_kernel(const SepParams<R> p, con
   const int tid = threadIdx.x;
   const int64_t plane = (int64_t)c * H * W;
 
-  for (int i = tid; i < 2 * R * (2 * R + 1); i += kThreads) {
+  for (int i = tid; i < kBorder; i += kThreads) {
     bvs[i] = p.bv[i];
     bhs[i] = p.bh[i];
   }
@@ -117,11 +119,11 @@ __global__ void __launch_bounds__(kThreads) sep_kernel(const SepParams<R> p, con
       for (int o = 0; o < kGroup; ++o) {
         const int row = r0 + g0 + o;  // image row of this output (uniform across the CTA)
         float acc = 0.f;
-        if (row >= R && row < H - R) {
+        if (row > R && row < H - 1 - R) {
 #pragma unroll
           for (int k = 0; k <= 2 * R; ++k) acc = fmaf(p.wv[k], in[o + k], acc);
         } else if (row < H) {
-          const float* bt = bvs + (row < R ? row : R + (row - (H - R))) * (2 * R + 1);
+          const float* bt = bvs + (row <= R ? row : (R + 1) + (row - (H - 1 - R))) * (2 * R + 1);
 #pragma unroll
           for (int k = 0; k <= 2 * R; ++k) acc = fmaf(bt[k], in[o + k], acc);
         }
@@ -147,7 +149,7 @@ __global__ void __launch_bounds__(kThreads) sep_kernel(const SepParams<R> p, con
       in[s * 4 + 0] = v.x; in[s * 4 + 1] = v.y; in[s * 4 + 2] = v.z; in[s * 4 + 3] = v.w;
     }
     float o[4];
-    if (col >= R && col + 3 < W - R) {
+    if (col > R && col + 3 < W - 1 - R) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         float acc = 0.f;
@@ -160,11 +162,11 @@ __global__ void __launch_bounds__(kThreads) sep_kernel(const SepParams<R> p, con
       for (int j = 0; j < 4; ++j) {
         const int cc = col + j;
         float acc = 0.f;
-        if (cc >= R && cc < W - R) {
+        if (cc > R && cc < W - 1 - R) {
 #pragma unroll
           for (int k = 0; k <= 2 * R; ++k) acc = fmaf(p.wh[k], in[j + k], acc);
         } else {
-          const float* bt = bhs + (cc < R ? cc : R + (cc - (W - R))) * (2 * R + 1);
+          const float* bt = bhs + (cc <= R ? cc : (R + 1) + (cc - (W - 1 - R))) * (2 * R + 1);
 #pragma unroll
           for (int k = 0; k <= 2 * R; ++k) acc = fmaf(bt[k], in[j + k], acc);
         }
@@ -206,7 +208,7 @@ __global__ void __launch_bounds__(kThreads) sep_kernel(const SepParams<R> p, con
 
 template <int R>
 size_t sep_smem_bytes(int W) {
-  return sizeof(float) * ((size_t)(kRows + 2 * R) * (W + 2 * R) + 2 * (size_t)(2 * R) * (2 * R + 1) + 64);
+  return sizeof(float) * ((size_t)(kRows + 2 * R) * (W + 2 * R) + 2 * (size_t)(2 * (R + 1)) * (2 * R + 1) + 64);
 }
 
 template <int R, bool kAdjoint>
@@ -276,9 +278,9 @@ int build_set(const std::vector<double>& wv, int rv, int H, const std::vector<do
     interior->assign(2 * R + 1, 0.f);
     const int mid = L / 2;  // an interior row (L >= 2R+1 checked by the caller)
     for (int e = -R; e <= R; ++e) (*interior)[e + R] = (float)at(mid, mid + e);
-    std::vector<float> border((size_t)2 * R * (2 * R + 1), 0.f);
-    for (int b = 0; b < 2 * R; ++b) {
-      const int i = b < R ? b : (L - R) + (b - R);
+    std::vector<float> border((size_t)2 * (R + 1) * (2 * R + 1), 0.f);
+    for (int b = 0; b < 2 * (R + 1); ++b) {
+      const int i = b <= R ? b : (L - 1 - R) + (b - (R + 1));
       for (int e = -R; e <= R; ++e) border[(size_t)b * (2 * R + 1) + e + R] = (float)at(i, i + e);
     }
     DPS_CUDA(cudaMalloc(border_dev, border.size() * sizeof(float)));
@@ -299,9 +301,9 @@ int sep_create(dps_operator* op, const float* taps1d_v, const float* taps1d_h, i
   for (int cand : {4, 8, 12, 16, 24, 32})
     if (cand >= r) { R = cand; break; }
   DPS_REQUIRE(R > 0, DPS_ERR_UNSUPPORTED, "separable blur: radius %d > 32", r);
-  DPS_REQUIRE(op->H >= 2 * R + 1 && op->W >= 2 * R + 4 && op->W % 4 == 0, DPS_ERR_UNSUPPORTED,
+  DPS_REQUIRE(op->H >= 2 * R + 3 && op->W >= 2 * R + 4 && op->W % 4 == 0, DPS_ERR_UNSUPPORTED,
               "separable blur: image %dx%d too small / W not a multiple of 4 for radius %d", op->H, op->W, R);
-  size_t smem = sizeof(float) * ((size_t)(kRows + 2 * R) * (op->W + 2 * R) + 2 * (size_t)(2 * R) * (2 * R + 1) + 64);
+  size_t smem = sizeof(float) * ((size_t)(kRows + 2 * R) * (op->W + 2 * R) + 2 * (size_t)(2 * (R + 1)) * (2 * R + 1) + 64);
   DPS_REQUIRE(smem <= 227 * 1024, DPS_ERR_UNSUPPORTED, "separable blur: tile of %zu bytes exceeds shared memory", smem);
   std::vector<double> wv(taps1d_v, taps1d_v + 2 * rv + 1), wh(taps1d_h, taps1d_h + 2 * rh + 1);
   SepTables* t = new SepTables();

@@ -213,8 +213,8 @@ int sparse_create(dps_operator* op, const float* kernel, int ksize) {
   Rx = (Rx + 3) / 4 * 4;
   if (Rx == 0) Rx = 4;
   DPS_REQUIRE(Ry <= kRows - 1 && Rx <= 32, DPS_ERR_UNSUPPORTED, "sparse blur: radius (%d,%d) > 31", Ry, Rx);
-  DPS_REQUIRE(op->H % kRows == 0 && op->W % 4 == 0 && op->H > 2 * Ry + 1 && op->W > 2 * Rx + 1,
-              DPS_ERR_UNSUPPORTED, "sparse blur: need H %% 32 == 0, W %% 4 == 0 and image larger than the kernel");
+  DPS_REQUIRE(op->H % kRows == 0 && op->W % 4 == 0 && op->H > Ry && op->W > Rx, DPS_ERR_UNSUPPORTED,
+              "sparse blur: need H %% 32 == 0, W %% 4 == 0 and the kernel radius below the image size");
   SparseTables* t = new SparseTables();
   t->ntaps = (int)taps.size();
   t->Ry = Ry;

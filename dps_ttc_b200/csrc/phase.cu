@@ -1,24 +1,440 @@
-// Phase retrieval operator — placeholder until the FFT kernels land (see below in this round).
+// Phase retrieval operator (measurements.py:179-189, util/img_utils.py:26-30, util/fastmri_utils.py:67-89):
+//   A(x) = | fftshift( FFT2_ortho( ifftshift( zero-pad(x) ) ) ) |  =  fftshift( |FFT2(pad(x))| ) / L
+// (the input ifftshift only multiplies the spectrum by (−1)^{k1+k2}), and its
+// Jacobian-transpose
+//   Jᵀg [p] = (1/L)·Re Σ_k G[k]·conj(F[k])/|F[k]|·e^{−2πi k·p/L},   G = ifftshift(g),  zero where |F| = 0.
+//
+// L = H + 2·pad = 384 = 8·8·6: hand-written mixed-radix Stockham FFT in shared memory, three
+// register-blocked stages (radix 8, 8, 6), twiddles from a 384-entry table.  What makes it cheap:
+//   * real input  → two image rows ride one complex FFT; only the half spectrum k2 ∈ [0,192] is kept and
+//     the other half of the magnitude is written by Hermitian symmetry |F[−k]| = |F[k]|;
+//   * zero padding → only the 256 non-zero rows are row-transformed, the column pass reads 256 of 384;
+//   * Re(·) in the VJP → G is symmetrised (G[k]+G[−k])/2 so the back-transform is Hermitian too and again
+//     runs on the half spectrum with two rows per complex FFT, cropped to the 256×256 image.
+// forward : K1 rows  (x, ε) → Rt[k2][row]        (scratch, L2-resident at small N)
+//           K2 cols  Rt → |F|/L → out = y − A(x̂₀) (or A(x̂₀)), Σr², Σ|r|, unit phase conj(F)/|F| → aux
+// adjoint : A1 cols  (r, phase) → T[row][k2]      (scratch)
+//           A2 rows  T → g = clamp-mask ⊙ (coef/L·Re(·) + extra)
+// Roofline: ~16 MFLOP per particle against ≥ 13 MB of traffic: memory-bound; the scratch round trips
+// (1.5T each way) are the price of not fitting a 384² complex plane in one SM's shared memory.
+#include <math.h>
+
+#include <vector>
+
 #include "operator.cuh"
 
+namespace {
+constexpr int kL = 384;
+constexpr int kHalf = kL / 2 + 1;  // 193
+constexpr int kImg = 256;
+constexpr int kPad = 64;
+constexpr int kThreads = 256;
+constexpr int kRowsPerCta = 32;  // K1 / A2: image rows per CTA → 16 packed FFTs
+constexpr int kColsPerCta = 16;  // K2 / A1: spectrum columns per CTA
+constexpr int kColGroups = (kHalf + kColsPerCta - 1) / kColsPerCta;  // 13
+}  // namespace
+
 struct PhaseTables {
-  int pad = 0;
+  float2* tw = nullptr;  // exp(−2πi j/384), j ∈ [0,384)
 };
 
-int phase_create(dps_operator* op, int pad) {
-  (void)op; (void)pad;
-  dps_set_error("phase retrieval: not built yet");
-  return DPS_ERR_UNSUPPORTED;
+namespace {
+
+DPS_DEV float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+DPS_DEV float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+DPS_DEV float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+DPS_DEV float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
+DPS_DEV float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }  // a·(−i)
+
+// in-register DFT-8, forward sign, natural order in and out
+DPS_DEV void dft8(float2* v) {
+  const float h = 0.70710678118654752440f;
+  // stage 1 (stride 4)
+  float2 a0 = cadd(v[0], v[4]), a4 = csub(v[0], v[4]);
+  float2 a1 = cadd(v[1], v[5]), a5 = csub(v[1], v[5]);
+  float2 a2 = cadd(v[2], v[6]), a6 = csub(v[2], v[6]);
+  float2 a3 = cadd(v[3], v[7]), a7 = csub(v[3], v[7]);
+  // twiddles on the odd half: W8^0, W8^1, W8^2, W8^3
+  a5 = make_float2(h * (a5.x + a5.y), h * (a5.y - a5.x));   // ·(1−i)/√2
+  a6 = mul_mi(a6);                                          // ·(−i)
+  a7 = make_float2(h * (a7.y - a7.x), -h * (a7.x + a7.y));  // ·(−1−i)/√2
+  // stage 2 (two DFT-4 halves)
+  float2 b0 = cadd(a0, a2), b2 = csub(a0, a2);
+  float2 b1 = cadd(a1, a3), b3 = mul_mi(csub(a1, a3));
+  float2 b4 = cadd(a4, a6), b6 = csub(a4, a6);
+  float2 b5 = cadd(a5, a7), b7 = mul_mi(csub(a5, a7));
+  // stage 3 → natural order: even outputs from the first half, odd outputs from the second
+  v[0] = cadd(b0, b1); v[4] = csub(b0, b1);
+  v[2] = cadd(b2, b3); v[6] = csub(b2, b3);
+  v[1] = cadd(b4, b5); v[5] = csub(b4, b5);
+  v[3] = cadd(b6, b7); v[7] = csub(b6, b7);
 }
+
+// in-register DFT-3 (forward sign)
+DPS_DEV void dft3(float2& x0, float2& x1, float2& x2) {
+  const float s = 0.86602540378443864676f;  // sin(2π/3)
+  const float2 t = cadd(x1, x2);
+  const float2 d = csub(x1, x2);
+  const float2 m = make_float2(x0.x - 0.5f * t.x, x0.y - 0.5f * t.y);
+  const float2 r = make_float2(s * d.y, -s * d.x);  // −i·s·d
+  x0 = cadd(x0, t);
+  x1 = cadd(m, r);
+  x2 = csub(m, r);
+}
+
+// in-register DFT-6 (forward sign): V[q] = E[q mod 3] + W6^q·O[q mod 3]
+DPS_DEV void dft6(float2* v) {
+  float2 e0 = v[0], e1 = v[2], e2 = v[4];
+  float2 o0 = v[1], o1 = v[3], o2 = v[5];
+  dft3(e0, e1, e2);
+  dft3(o0, o1, o2);
+  const float s = 0.86602540378443864676f;
+  const float2 w1 = make_float2(0.5f, -s), w2 = make_float2(-0.5f, -s);  // W6^1, W6^2
+  const float2 t1 = cmul(o1, w1), t2 = cmul(o2, w2);
+  v[0] = cadd(e0, o0); v[3] = csub(e0, o0);   // W6^3 = −1
+  v[1] = cadd(e1, t1); v[4] = csub(e1, t1);   // W6^4 = −W6^1
+  v[2] = cadd(e2, t2); v[5] = csub(e2, t2);   // W6^5 = −W6^2
+}
+
+// `nfft` independent forward FFTs of length 384, sequence f at a[f*384 ...]; the result lands in b.
+// Stockham autosort, radices 8·8·6 (natural order in, natural order out).  All threads must call it.
+__device__ void fft384_batch(float2* a, float2* b, const float2* tw, int nfft) {
+  const int tid = threadIdx.x;
+  // stage 1: R = 8, Ns = 1 (no twiddles): b[8j + r] = DFT8(a[j + 48r])
+  for (int it = tid; it < nfft * 48; it += kThreads) {
+    const int f = it / 48, j = it - f * 48;
+    const float2* src = a + f * kL;
+    float2* dst = b + f * kL;
+    float2 v[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) v[r] = src[j + 48 * r];
+    dft8(v);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) dst[8 * j + r] = v[r];
+  }
+  __syncthreads();
+  // stage 2: R = 8, Ns = 8: twiddle exp(−2πi·k·r/64) = tw[6·k·r]
+  for (int it = tid; it < nfft * 48; it += kThreads) {
+    const int f = it / 48, j = it - f * 48;
+    const int k = j & 7;
+    const float2* src = b + f * kL;
+    float2* dst = a + f * kL;
+    float2 v[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      v[r] = src[j + 48 * r];
+      if (r) v[r] = cmul(v[r], tw[6 * k * r]);
+    }
+    dft8(v);
+    const int j0 = (j >> 3) * 64 + k;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) dst[j0 + 8 * r] = v[r];
+  }
+  __syncthreads();
+  // stage 3: R = 6, Ns = 64: twiddle exp(−2πi·k·r/384) = tw[k·r]
+  for (int it = tid; it < nfft * 64; it += kThreads) {
+    const int f = it >> 6, j = it & 63;
+    const float2* src = a + f * kL;
+    float2* dst = b + f * kL;
+    float2 v[6];
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+      v[r] = src[j + 64 * r];
+      if (r) v[r] = cmul(v[r], tw[j * r]);
+    }
+    dft6(v);
+#pragma unroll
+    for (int r = 0; r < 6; ++r) dst[j + 64 * r] = v[r];
+  }
+  __syncthreads();
+}
+
+struct PhaseSmem {
+  float2* a;
+  float2* b;
+  float2* tw;
+  float* red;
+};
+DPS_DEV PhaseSmem carve(float* smem, int nfft) {
+  PhaseSmem s;
+  s.a = reinterpret_cast<float2*>(smem);
+  s.b = s.a + nfft * kL;
+  s.tw = s.b + nfft * kL;
+  s.red = reinterpret_cast<float*>(s.tw + kL);
+  return s;
+}
+size_t smem_bytes(int nfft) { return sizeof(float2) * ((size_t)2 * nfft * kL + kL) + 64 * sizeof(float); }
+
+// aux layout per particle (floats): [phase: C·193·384·2][scratch: C·193·256·2]
+DPS_DEV float2* aux_phase(float* aux, int n, int C, int c) {
+  return reinterpret_cast<float2*>(aux + (int64_t)n * C * kHalf * (kL + kImg) * 2) + (int64_t)c * kHalf * kL;
+}
+DPS_DEV float2* aux_scratch(float* aux, int n, int C, int c) {
+  return reinterpret_cast<float2*>(aux + (int64_t)n * C * kHalf * (kL + kImg) * 2) + (int64_t)C * kHalf * kL +
+         (int64_t)c * kHalf * kImg;
+}
+
+// ---- K1: row transforms of the 256 image rows, two real rows per complex FFT ---------------------
+__global__ void __launch_bounds__(kThreads) phase_rows_fwd(const FwdArgs fa, const float2* __restrict__ tw_g, int C) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int nfft = kRowsPerCta / 2;
+  PhaseSmem s = carve(smem, nfft);
+  const int tid = threadIdx.x;
+  const int groups = kImg / kRowsPerCta;
+  const int grp = blockIdx.x % groups, c = blockIdx.x / groups, n = blockIdx.y;
+  const int r0 = grp * kRowsPerCta;
+  for (int i = tid; i < kL; i += kThreads) s.tw[i] = tw_g[i];
+  // zero the padding columns [0,64) and [320,384) of every sequence
+  for (int i = tid; i < nfft * 2 * kPad; i += kThreads) {
+    const int f = i / (2 * kPad), q = i - f * (2 * kPad);
+    s.a[f * kL + (q < kPad ? q : kImg + q)] = make_float2(0.f, 0.f);
+  }
+  const int64_t plane = (int64_t)c * kImg * kImg;
+  const float* x = fa.src.x + n * fa.src.x_stride + plane;
+  const float* eps = fa.src.eps ? fa.src.eps + n * fa.src.eps_stride + plane : nullptr;
+  for (int i = tid; i < nfft * (kImg / 4); i += kThreads) {
+    const int f = i / (kImg / 4), q = i - f * (kImg / 4);
+    const float4 re = src_load4(x, eps, (int64_t)(r0 + 2 * f) * kImg + q * 4, fa.src.c1, fa.src.c2, fa.src.clip);
+    const float4 im = src_load4(x, eps, (int64_t)(r0 + 2 * f + 1) * kImg + q * 4, fa.src.c1, fa.src.c2, fa.src.clip);
+    float2* d = s.a + f * kL + kPad + q * 4;
+    d[0] = make_float2(re.x, im.x); d[1] = make_float2(re.y, im.y);
+    d[2] = make_float2(re.z, im.z); d[3] = make_float2(re.w, im.w);
+  }
+  __syncthreads();
+  fft384_batch(s.a, s.b, s.tw, nfft);
+  // split Z = A + iB (A, B spectra of the even / odd row) and store Rt[k2][row] for k2 ∈ [0,192]
+  float2* rt = aux_scratch(fa.aux, n, C, c);
+  for (int i = tid; i < kHalf * nfft; i += kThreads) {
+    const int k = i / nfft, f = i - k * nfft;
+    const float2 z = s.b[f * kL + k];
+    const float2 zc = cconj(s.b[f * kL + (k ? kL - k : 0)]);
+    const float2 A = make_float2(0.5f * (z.x + zc.x), 0.5f * (z.y + zc.y));
+    const float2 d = make_float2(0.5f * (z.x - zc.x), 0.5f * (z.y - zc.y));
+    const float2 B = make_float2(d.y, -d.x);  // d / i
+    *reinterpret_cast<float4*>(rt + (int64_t)k * kImg + r0 + 2 * f) = make_float4(A.x, A.y, B.x, B.y);
+  }
+}
+
+DPS_DEV int shift_idx(int k) { return k + kL / 2 >= kL ? k - kL / 2 : k + kL / 2; }  // fftshift position of bin k
+
+// ---- K2: column transforms, magnitude, residual, partial sums, unit phase -----------------------
+__global__ void __launch_bounds__(kThreads) phase_cols_fwd(const FwdArgs fa, const float2* __restrict__ tw_g, int C) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int nfft = kColsPerCta;
+  PhaseSmem s = carve(smem, nfft);
+  const int tid = threadIdx.x;
+  const int grp = blockIdx.x % kColGroups, c = blockIdx.x / kColGroups, n = blockIdx.y;
+  const int k20 = grp * kColsPerCta;
+  const int ncols = min(kColsPerCta, kHalf - k20);
+  for (int i = tid; i < kL; i += kThreads) s.tw[i] = tw_g[i];
+  for (int i = tid; i < nfft * 2 * kPad; i += kThreads) {
+    const int f = i / (2 * kPad), q = i - f * (2 * kPad);
+    s.a[f * kL + (q < kPad ? q : kImg + q)] = make_float2(0.f, 0.f);
+  }
+  const float2* rt = aux_scratch(fa.aux, n, C, c);
+  for (int i = tid; i < nfft * (kImg / 2); i += kThreads) {
+    const int f = i / (kImg / 2), q = i - f * (kImg / 2);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (f < ncols) v = *reinterpret_cast<const float4*>(rt + (int64_t)(k20 + f) * kImg + q * 2);
+    float2* d = s.a + f * kL + kPad + q * 2;
+    d[0] = make_float2(v.x, v.y);
+    d[1] = make_float2(v.z, v.w);
+  }
+  __syncthreads();
+  fft384_batch(s.a, s.b, s.tw, nfft);
+  // unit phase conj(F)/|F| → aux[k2][k1] (contiguous in k1), magnitude → s.a reused as float storage
+  float2* ph = aux_phase(fa.aux, n, C, c);
+  float* amp = reinterpret_cast<float*>(s.a);  // (nfft, 384)
+  const float inv_l = 1.0f / (float)kL;
+  for (int i = tid; i < ncols * kL; i += kThreads) {
+    const int f = i / kL, k1 = i - f * kL;
+    const float2 F = s.b[f * kL + k1];
+    const float mag = sqrtf(F.x * F.x + F.y * F.y);
+    const float inv = mag > 0.f ? 1.0f / mag : 0.f;
+    ph[(int64_t)(k20 + f) * kL + k1] = make_float2(F.x * inv, -F.y * inv);
+    amp[f * kL + k1] = mag * inv_l;
+  }
+  __syncthreads();
+  // outputs: direct position (u, v) = shift(k1, k2) and, for 0 < k2 < 192, the mirror shift(−k1, −k2)
+  float sq = 0.f, ab = 0.f;
+  const int64_t oplane = ((int64_t)n * C + c) * kL * kL;
+  const float* y = fa.y ? fa.y + n * fa.y_stride + (int64_t)c * kL * kL : nullptr;
+  for (int i = tid; i < kL * ncols; i += kThreads) {
+    const int k1 = i / ncols, f = i - k1 * ncols;
+    const int k2 = k20 + f;
+    const float a = amp[f * kL + k1];
+    {
+      const int64_t o = (int64_t)shift_idx(k1) * kL + shift_idx(k2);
+      const float res = y ? __fsub_rn(y[o], a) : a;
+      if (fa.out) fa.out[oplane + o] = res;
+      sq += res * res;
+      ab += fabsf(res);
+    }
+    if (k2 > 0 && k2 < kL / 2) {
+      const int64_t o = (int64_t)shift_idx(k1 ? kL - k1 : 0) * kL + shift_idx(kL - k2);
+      const float res = y ? __fsub_rn(y[o], a) : a;
+      if (fa.out) fa.out[oplane + o] = res;
+      sq += res * res;
+      ab += fabsf(res);
+    }
+  }
+  if (fa.partials) {
+    block_sum2(sq, ab, s.red);
+    if (tid == 0) {
+      float* pp = fa.partials + ((int64_t)n * (C * kColGroups) + blockIdx.x) * 2;
+      pp[0] = sq;
+      pp[1] = ab;
+    }
+  }
+}
+
+// ---- A1: H_s[k1][k2] = ½(g[k]+g[−k])·conj(F)/|F|, column transform, keep rows 64..319 ------------
+__global__ void __launch_bounds__(kThreads) phase_cols_adj(const AdjArgs aa, float* __restrict__ aux_rw,
+                                                           const float2* __restrict__ tw_g, int C) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int nfft = kColsPerCta;
+  PhaseSmem s = carve(smem, nfft);
+  const int tid = threadIdx.x;
+  const int grp = blockIdx.x % kColGroups, c = blockIdx.x / kColGroups, n = blockIdx.y;
+  const int k20 = grp * kColsPerCta;
+  const int ncols = min(kColsPerCta, kHalf - k20);
+  for (int i = tid; i < kL; i += kThreads) s.tw[i] = tw_g[i];
+  const float* r = aa.r + ((int64_t)n * C + c) * kL * kL;
+  const float2* ph = aux_phase(aux_rw, n, C, c);
+  // symmetrised cotangent (coalesced over the CTA's columns), staged as floats in s.b
+  float* gs = reinterpret_cast<float*>(s.b);
+  for (int i = tid; i < kL * ncols; i += kThreads) {
+    const int k1 = i / ncols, f = i - k1 * ncols;
+    const int k2 = k20 + f;
+    const float g1 = ldg_stream(r + (int64_t)shift_idx(k1) * kL + shift_idx(k2));
+    const float g2 = ldg_stream(r + (int64_t)shift_idx(k1 ? kL - k1 : 0) * kL + shift_idx(k2 ? kL - k2 : 0));
+    gs[f * kL + k1] = 0.5f * (g1 + g2);
+  }
+  __syncthreads();
+  for (int i = tid; i < nfft * kL; i += kThreads) {
+    const int f = i / kL, k1 = i - f * kL;
+    float2 v = make_float2(0.f, 0.f);
+    if (f < ncols) {
+      const float2 p = ph[(int64_t)(k20 + f) * kL + k1];
+      const float g = gs[f * kL + k1];
+      v = make_float2(g * p.x, g * p.y);
+    }
+    s.a[f * kL + k1] = v;
+  }
+  __syncthreads();
+  fft384_batch(s.a, s.b, s.tw, nfft);
+  // T[row][k2] for padded rows 64..319 → image rows 0..255; row stride 193 complex
+  float2* t = aux_scratch(aux_rw, n, C, c);
+  for (int i = tid; i < kImg * ncols; i += kThreads) {
+    const int row = i / ncols, f = i - row * ncols;
+    t[(int64_t)row * kHalf + k20 + f] = s.b[f * kL + kPad + row];
+  }
+}
+
+// ---- A2: Hermitian row back-transform, two real rows per complex FFT, crop + epilogue ------------
+__global__ void __launch_bounds__(kThreads) phase_rows_adj(const AdjArgs aa, const float* __restrict__ aux_r,
+                                                           const float2* __restrict__ tw_g, int C) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int nfft = kRowsPerCta / 2;
+  PhaseSmem s = carve(smem, nfft);
+  const int tid = threadIdx.x;
+  const int groups = kImg / kRowsPerCta;
+  const int grp = blockIdx.x % groups, c = blockIdx.x / groups, n = blockIdx.y;
+  const int r0 = grp * kRowsPerCta;
+  for (int i = tid; i < kL; i += kThreads) s.tw[i] = tw_g[i];
+  const float2* t = aux_scratch(const_cast<float*>(aux_r), n, C, c);
+  // X[k] = T1[k] + i·T2[k] with T[384−k] = conj(T[k]) for k > 192
+  for (int i = tid; i < nfft * kL; i += kThreads) {
+    const int f = i / kL, k = i - f * kL;
+    const int kk = k < kHalf ? k : kL - k;
+    float2 t1 = t[(int64_t)(r0 + 2 * f) * kHalf + kk];
+    float2 t2 = t[(int64_t)(r0 + 2 * f + 1) * kHalf + kk];
+    if (k >= kHalf) { t1.y = -t1.y; t2.y = -t2.y; }
+    s.a[f * kL + k] = make_float2(t1.x - t2.y, t1.y + t2.x);
+  }
+  __syncthreads();
+  fft384_batch(s.a, s.b, s.tw, nfft);
+  const float coef = (aa.coef ? aa.coef[n] : 1.0f) * (1.0f / (float)kL);
+  const int64_t plane = (int64_t)c * kImg * kImg;
+  for (int i = tid; i < kRowsPerCta * (kImg / 4); i += kThreads) {
+    const int rr = i / (kImg / 4), q = i - rr * (kImg / 4);
+    const int f = rr >> 1, odd = rr & 1;
+    const float2* z = s.b + f * kL + kPad + q * 4;
+    float4 res;
+    res.x = coef * (odd ? z[0].y : z[0].x);
+    res.y = coef * (odd ? z[1].y : z[1].x);
+    res.z = coef * (odd ? z[2].y : z[2].x);
+    res.w = coef * (odd ? z[3].y : z[3].x);
+    const int64_t off = plane + (int64_t)(r0 + rr) * kImg + q * 4;
+    if (aa.extra) {
+      const float4 e = ldg_stream4(aa.extra + n * aa.extra_stride + off);
+      res.x += e.x; res.y += e.y; res.z += e.z; res.w += e.w;
+    }
+    const float4 pass = mask_load4(aa.mask_src, aa.has_mask, n, off);
+    res.x *= pass.x; res.y *= pass.y; res.z *= pass.z; res.w *= pass.w;
+    stg_stream4(aa.g + n * aa.g_stride + off, res);
+  }
+}
+
+int set_smem(const void* fn, size_t bytes) {
+  DPS_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return DPS_OK;
+}
+
+}  // namespace
+
+int phase_create(dps_operator* op, int pad) {
+  DPS_REQUIRE(op->H == kImg && op->W == kImg && pad == kPad, DPS_ERR_UNSUPPORTED,
+              "phase retrieval: kernels are built for 256x256 images padded to 384x384 (got %dx%d, pad %d)", op->H,
+              op->W, pad);
+  PhaseTables* t = new PhaseTables();
+  op->phase = t;
+  std::vector<float2> tw(kL);
+  for (int j = 0; j < kL; ++j) {
+    const double a = -2.0 * M_PI * j / kL;
+    tw[j] = make_float2((float)cos(a), (float)sin(a));
+  }
+  DPS_CUDA(cudaMalloc(&t->tw, sizeof(float2) * kL));
+  DPS_CUDA(cudaMemcpy(t->tw, tw.data(), sizeof(float2) * kL, cudaMemcpyHostToDevice));
+  if (int rc = set_smem((const void*)phase_rows_fwd, smem_bytes(kRowsPerCta / 2))) return rc;
+  if (int rc = set_smem((const void*)phase_cols_fwd, smem_bytes(kColsPerCta))) return rc;
+  if (int rc = set_smem((const void*)phase_cols_adj, smem_bytes(kColsPerCta))) return rc;
+  if (int rc = set_smem((const void*)phase_rows_adj, smem_bytes(kRowsPerCta / 2))) return rc;
+  op->oC = op->C;
+  op->oH = op->oW = kL;
+  op->P = op->C * kColGroups;
+  op->aux_floats = (int64_t)op->C * kHalf * (kL + kImg) * 2;
+  op->taps = kL;
+  return DPS_OK;
+}
+
 void phase_destroy(dps_operator* op) {
+  if (!op->phase) return;
+  cudaFree(op->phase->tw);
   delete op->phase;
   op->phase = nullptr;
 }
-int phase_forward(const dps_operator*, const FwdArgs&, cudaStream_t) {
-  dps_set_error("phase retrieval: not built yet");
-  return DPS_ERR_UNSUPPORTED;
+
+int phase_forward(const dps_operator* op, const FwdArgs& a, cudaStream_t st) {
+  DPS_REQUIRE(a.aux, DPS_ERR_INVALID, "phase retrieval forward needs the aux workspace (%lld floats per particle)",
+              (long long)op->aux_floats);
+  dim3 g1((unsigned)(op->C * (kImg / kRowsPerCta)), (unsigned)a.n);
+  phase_rows_fwd<<<g1, kThreads, smem_bytes(kRowsPerCta / 2), st>>>(a, op->phase->tw, op->C);
+  DPS_LAUNCH_CHECK("phase_rows_fwd");
+  dim3 g2((unsigned)(op->C * kColGroups), (unsigned)a.n);
+  phase_cols_fwd<<<g2, kThreads, smem_bytes(kColsPerCta), st>>>(a, op->phase->tw, op->C);
+  DPS_LAUNCH_CHECK("phase_cols_fwd");
+  return DPS_OK;
 }
-int phase_adjoint(const dps_operator*, const AdjArgs&, cudaStream_t) {
-  dps_set_error("phase retrieval: not built yet");
-  return DPS_ERR_UNSUPPORTED;
+
+int phase_adjoint(const dps_operator* op, const AdjArgs& a, cudaStream_t st) {
+  DPS_REQUIRE(a.aux && a.r, DPS_ERR_INVALID, "phase retrieval adjoint needs r and the aux workspace of the forward pass");
+  float* aux = const_cast<float*>(a.aux);
+  dim3 g1((unsigned)(op->C * kColGroups), (unsigned)a.n);
+  phase_cols_adj<<<g1, kThreads, smem_bytes(kColsPerCta), st>>>(a, aux, op->phase->tw, op->C);
+  DPS_LAUNCH_CHECK("phase_cols_adj");
+  dim3 g2((unsigned)(op->C * (kImg / kRowsPerCta)), (unsigned)a.n);
+  phase_rows_adj<<<g2, kThreads, smem_bytes(kRowsPerCta / 2), st>>>(a, aux, op->phase->tw, op->C);
+  DPS_LAUNCH_CHECK("phase_rows_adj");
+  return DPS_OK;
 }
