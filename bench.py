@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""bench.py — DPS particle-steps/sec on B200 (BASELINE.json metric) + guidance-kernel roofline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c2|c1|c3|c4|c5]
+
+A "step" is one measurement-guided reverse-diffusion step over this rank's batch of particles:
+UNet forward (the reference's own module, random-init, fp32) + residual / coefficient / cotangent kernels +
+UNet VJP + fused posterior update.  Default workload = BASELINE.json configs[1]: 4× super-resolution
+(Resizer bicubic), ps ζ=0.01, ddpm 1000-step chain, 8 particles per GPU, synthetic 256×256 data.
+Multi-GPU (torchrun, one rank per GPU): particles shard, no data-path collective for this workload
+(best-of-N selects after the loop), weak scaling: 8 particles per GPU.
+
+--impl reference : the reference's own CPU implementation of the same step (from baseline/_ref, staged by
+__graft_entry__.build(); else the oracle port) on the host cores — rank 0 only.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+T_BYTES = 3 * 256 * 256 * 4
+DIFF = dict(steps=1000, noise_schedule="linear", model_mean_type="epsilon", model_var_type="learned_range",
+            dynamic_threshold=False, clip_denoised=True, rescale_timesteps=True)
+WORKLOADS = {
+    # name: (operator name, operator cfg, method, params, measurement bytes per particle M, description)
+    "c1": ("gaussian_blur", dict(kernel_size=61, intensity=3.0), "ps", dict(scale=0.3), T_BYTES,
+           "DPS Gaussian deblur k=61 sigma=3, ps zeta=0.3, ddpm"),
+    "c2": ("super_resolution", dict(in_shape=(1, 3, 256, 256), scale_factor=4), "ps", dict(scale=0.01), T_BYTES // 16,
+           "best-of-N N=8/GPU, 4x super-resolution (Resizer bicubic), ps zeta=0.01, ddpm 1000-step chain"),
+    "c3": ("motion_blur", dict(kernel_size=61, intensity=0.5), "ps", dict(scale=0.3), T_BYTES,
+           "motion deblur k=61 (synthetic sparse kernel, np seed 8), ps zeta=0.3, ddpm"),
+    "c4": ("phase_retrieval", dict(oversample=2.0), "ps_anneal", dict(scale=1.0), T_BYTES * 9 // 4,
+           "phase retrieval (oversample 2 -> 384x384 |FFT|), ps_anneal, ddpm"),
+    "c5": ("inpainting", {}, "ps", dict(scale=0.5), T_BYTES,
+           "inpainting random mask p in (0.3,0.7) np seed 8, ps zeta=0.5, ddpm"),
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--particles", type=int, default=8, help="particles per GPU")
+    ap.add_argument("--model", default="auto", choices=["auto", "ffhq", "imagenet", "tiny"])
+    ap.add_argument("--cpu-particles", type=int, default=1, help="particles per step of the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+def load_model(kind, device):
+    """The reference's UNet (random init + seeded re-init of the zeroed output convs) or, when the
+    reference tree is not available, a small stand-in — reported in config.model either way."""
+    from dps_ttc_b200 import _ref
+    if kind in ("auto", "ffhq", "imagenet") and _ref.reference_root() is not None:
+        cfg = "imagenet_model_config.yaml" if kind == "imagenet" else "model_config.yaml"
+        model = _ref.create_unet(cfg, reinit_zero_seed=0, device=device)
+        name = "ImageNet-256 ADM UNet (552.8M)" if kind == "imagenet" else "FFHQ-256 ADM UNet (93.6M)"
+        return model, name + ", reference module, random-init + seeded re-init of zeroed convs"
+    if kind in ("ffhq", "imagenet"):
+        raise RuntimeError("reference tree (baseline/_ref) not found: run __graft_entry__.build() in the build container")
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import TinyEps
+    return TinyEps(seed=0, width=64).to(device).eval(), "STAND-IN TinyEps conv net (reference UNet unavailable)"
+
+
+def make_inputs(workload, n, seed):
+    """Synthetic inputs on the HOST: x_true = 2U−1, y = A(x_true) + 0.05·randn, x_start = randn."""
+    g = torch.Generator().manual_seed(1234)
+    x_true = torch.rand(1, 3, 256, 256, generator=g) * 2 - 1
+    gs = torch.Generator().manual_seed(42 + seed)
+    x_start = torch.randn(n, 3, 256, 256, generator=gs)
+    return x_true, x_start
+
+
+def build_b200(workload, device):
+    from dps_ttc_b200.registry import get_conditioning_method, get_noise, get_operator
+    from dps_ttc_b200.sampler import create_sampler
+    op_name, op_cfg, method, params, _, _ = WORKLOADS[workload]
+    np.random.seed(8)
+    op = get_operator(op_name, device=device, **op_cfg)
+    cond = get_conditioning_method(method, op, get_noise("gaussian", sigma=0.05), **params)
+    sampler = create_sampler(sampler="ddpm", **DIFF)
+    kw = {}
+    if op_name == "inpainting":
+        from dps_ttc_b200.tables import MaskGenerator
+        np.random.seed(8)
+        mask = MaskGenerator("random", mask_prob_range=(0.3, 0.7), image_size=256)(np.zeros((1, 3, 256, 256)))[:, :1]
+        kw["mask"] = torch.from_numpy(mask).to(device)
+    return op, cond, sampler, kw
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.proc = index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:  # noqa: BLE001
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        mhz = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) >= 6 and r[2 + i].lower() == "active"})
+        return {"sm_mhz": float(np.median(mhz)) if mhz else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(mhz)}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own implementation (or the oracle port) on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_particle_steps(workload, n_particles, steps, warmup):
+    """Times `steps` guided steps of `n_particles` particles on the CPU after `warmup` steps.
+    Returns (particle_steps_per_sec, kind, cores, description)."""
+    from dps_ttc_b200 import _ref
+    op_name, op_cfg, method, params, _, _ = WORKLOADS[workload]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    x_true, x_start = make_inputs(workload, n_particles, 0)
+    if _ref.reference_root() is not None:
+        _ref.ensure_reference()
+        with _ref.quiet():
+            from guided_diffusion.condition_methods import get_conditioning_method
+            from guided_diffusion.gaussian_diffusion import create_sampler
+            from guided_diffusion.measurements import get_noise, get_operator
+        model = _ref.create_unet("model_config.yaml", reinit_zero_seed=0, device="cpu")
+        np.random.seed(8)
+        with _ref.quiet():
+            op = get_operator(op_name, device="cpu", **op_cfg)
+            noiser = get_noise("gaussian", sigma=0.05)
+            # ps_semantic(sem_guid_scale=0) is the HEAD-valid spelling of ps inside the base loop
+            scale = params.get("scale", 0.3)
+            cond = get_conditioning_method("ps_semantic", op, noiser, scale=scale, sem_guid_scale=0.0)
+        kw = {}
+        if op_name == "inpainting":
+            from util.img_utils import mask_generator
+            np.random.seed(8)
+            kw["mask"] = mask_generator("random", mask_prob_range=(0.3, 0.7), image_size=256)(x_true)[:, 0].unsqueeze(0)
+        y = noiser(op.forward(x_true, **kw)).detach()
+        import functools
+        fn = functools.partial(cond.conditioning, **kw) if kw else cond.conditioning
+
+        def run(n_steps):
+            with _ref.quiet():
+                s = create_sampler(sampler="ddpm", timestep_respacing=str(n_steps), **DIFF)
+                t0 = time.perf_counter()
+                s.p_sample_loop(model=model, x_start=x_start.clone(), measurement=y, measurement_cond_fn=fn,
+                                record=False, save_root=None)
+            return time.perf_counter() - t0
+        steps = max(2, steps)  # the reference's tables need a chain of at least 2 steps (posterior_variance[1])
+        if warmup > 0:
+            run(max(2, warmup))
+        dt = run(steps)
+        what = (f"reference p_sample_loop (ddpm + ps_semantic sem=0 ≡ ps) on CPU, {n_particles} particle(s) x {steps} "
+                f"steps of a {steps}-step respaced chain, FFHQ UNet fp32")
+        return n_particles * steps / dt, "reference", cores, what
+    # oracle port (numpy) with the stand-in model
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import TinyEps, oracle_guided_step
+    from oracle import dps_oracle as O
+    model = TinyEps(seed=0, width=64)
+    tab = O.Tables(1000)
+    fwd = lambda a: O.resize_forward(a, 0.25)  # noqa: E731
+    adj = lambda u: O.resize_adjoint(u, 0.25, 256, 256)  # noqa: E731
+    rng = np.random.default_rng(0)
+    y = fwd(x_true.numpy())
+    img = x_start.numpy()
+    t0 = None
+    for i, idx in enumerate(range(999, 999 - warmup - steps, -1)):
+        if i == warmup:
+            t0 = time.perf_counter()
+        img, _, _ = oracle_guided_step(O, model, tab, img, idx, y, fwd, adj, rng.standard_normal(img.shape).astype(np.float32),
+                                       "norm", 0.01)
+    dt = time.perf_counter() - t0
+    return n_particles * steps / dt, "port", 1, f"oracle port (numpy) + stand-in model, {n_particles} particle(s) x {steps} steps, SR x4"
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    desc = WORKLOADS[args.workload][5]
+    val, kind, cores, what = cpu_particle_steps(args.workload, args.cpu_particles, args.steps, args.warmup)
+    line = {"impl": "reference", "metric": "DPS particle-steps/sec", "value": val, "unit": "particle-steps/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1000.0 * args.cpu_particles / val, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {desc}", "device": "cpu"},
+            "cpu_baseline": {"value": val, "unit": "particle-steps/s", "cores": cores, "kind": kind, "sample": what},
+            "e2e": {"value": val, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def run_b200(args, rank, world, local_rank):
+    import torch.distributed as dist
+    from dps_ttc_b200 import _lib, kernels
+    from dps_ttc_b200.sampler import NoiseTape, TorchNoise
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py --impl b200 needs a GPU: dps_ttc_b200 has no CPU fallback")
+    device = torch.device(f"cuda:{local_rank}")
+    torch.cuda.set_device(device)
+    n, K, W = args.particles, args.steps, args.warmup
+    op_name, op_cfg, method, params, m_bytes, desc = WORKLOADS[args.workload]
+    model, model_name = load_model(args.model, device)
+    op, cond, sampler, kw = build_b200(args.workload, device)
+    import functools
+    cond_fn = functools.partial(cond.conditioning, **kw) if kw else cond.conditioning
+    x_true, x_start_h = make_inputs(args.workload, n, rank)
+    x_start_h = x_start_h.pin_memory()
+    with torch.no_grad():
+        y_dev = op.forward(x_true.to(device), **kw)
+        y_dev = y_dev + 0.05 * torch.randn(y_dev.shape, device=device, generator=torch.Generator(device).manual_seed(1235))
+    y_h = y_dev.cpu().pin_memory()
+    torch.manual_seed(1000 + rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def loop(x0, y, start, steps, **extra):
+        return sampler.p_sample_loop(model=model, x_start=x0, measurement=y, measurement_cond_fn=cond_fn, record=False,
+                                     save_root=None, start_idx=start, num_steps=steps, **extra)
+
+    # ---------------- device-resident throughput (`value`) ----------------
+    sampler.noise, sampler.parity_rng = TorchNoise(), False
+    x_dev = x_start_h.to(device)
+    img, _, _ = loop(x_dev, y_dev, 999, W)                      # warm-up steps (untimed)
+    kernels.TIMER = kernels.KernelTimer()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    barrier()
+    _lib.reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    img, dist_dev, _ = loop(img, y_dev, 999 - W, K)            # exactly K timed steps
+    e1.record()
+    barrier()
+    launches = _lib.launch_count()
+    ms = e0.elapsed_time(e1)
+    clock_info = clocks.stop()
+    spans = kernels.TIMER.summary()
+    kernels.TIMER = None
+
+    # ---------------- end to end through the public API with HOST buffers (`e2e`) ----------------
+    gz = torch.Generator().manual_seed(77 + rank)
+    idxs = list(range(999 - W - K, 999 - W - 2 * K, -1))
+    tape = NoiseTape(z={i: torch.randn(n, 3, 256, 256, generator=gz) for i in idxs})
+    sampler.noise = tape
+    d2h = {"bytes": 0}
+    host_dist = torch.empty(n, dtype=torch.float32).pin_memory()
+
+    def read_back(idx, im, d, sd):                             # the reference reads the distance every step (:295)
+        host_dist.copy_(d, non_blocking=False)
+        d2h["bytes"] += d.numel() * 4
+
+    barrier()
+    t0 = time.perf_counter()
+    x_in = x_start_h.to(device, non_blocking=True)             # H2D of the particles and the measurement
+    y_in = y_h.to(device, non_blocking=True)
+    out, _, _ = loop(x_in, y_in, idxs[0], K, callback=read_back)
+    out_h = out.cpu()                                          # D2H of the result
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    h2d_step = (tape.h2d_bytes + x_start_h.numel() * 4 + y_h.numel() * 4) / K
+    d2h_step = (d2h["bytes"] + out_h.numel() * 4) / K
+
+    # ---------------- max over ranks ----------------
+    t = torch.tensor([ms / 1000.0, e2e_s], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    sec, e2e_sec = float(t[0]), float(t[1])
+    if rank != 0:
+        return
+    value = world * n * K / sec
+    e2e_value = world * n * K / e2e_sec
+
+    # ---------------- roofline of the dominant graft kernel ----------------
+    kind = op.plan_for(x_dev, **kw).kind
+    alg_bytes = {f"{kind}_forward": n * (2 * T_BYTES + m_bytes), f"{kind}_adjoint": n * (3 * T_BYTES + m_bytes),
+                 "posterior_update_ddpm": n * 7 * T_BYTES, "guidance_coef": 0}
+    peak, peak_src = peaks()
+    ktab = {}
+    for name, (cnt, mean_ms) in spans.items():
+        b = alg_bytes.get(name, 0)
+        ktab[name] = {"launches": cnt, "mean_us": round(mean_ms * 1e3, 2), "alg_bytes": b,
+                      "gbs": round(b / (mean_ms * 1e-3) / 1e9, 1) if mean_ms > 0 else None}
+    dom = max((k for k in ktab if alg_bytes.get(k, 0) > 0), key=lambda k: ktab[k]["mean_us"] * ktab[k]["launches"])
+    achieved = ktab[dom]["gbs"]
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                "note": f"N={n} particles/launch: working set {alg_bytes[dom] / 1e6:.0f} MB is L2-sized and the kernel lasts "
+                        f"{ktab[dom]['mean_us']} us, so launch latency weighs in; HBM-regime numbers (N>=128) are in profiles/",
+                "kernels": ktab}
+    graft_ms = sum(v["mean_us"] * v["launches"] for v in ktab.values()) / 1e3
+    roofline["graft_share_of_step"] = round(graft_ms / ms, 5)
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        v, ckind, cores, what = cpu_particle_steps(args.workload, args.cpu_particles, 2, 1)
+        cpu = {"value": v, "unit": "particle-steps/s", "cores": cores, "kind": ckind, "sample": what}
+    line = {"metric": "DPS particle-steps/sec", "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": 1000.0 * sec / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {desc}", "particles_per_gpu": n, "global_particles": n * world,
+                       "image": "3x256x256", "chain": "ddpm 1000 steps, timed window idx %d..%d" % (999 - W, 999 - W - K + 1),
+                       "unet": model_name, "unet_math": "fp32 weights/activations; cuDNN conv TF32 = torch default "
+                       f"({torch.backends.cudnn.allow_tf32}), matmul TF32 {torch.backends.cuda.matmul.allow_tf32}",
+                       "parallelism": f"particle-sharded dp{world}, no data-path collective (best-of-N selects after the loop)",
+                       "l2_policy": "inputs larger than L2: between two launches of any graft kernel the UNet forward+VJP "
+                                    "streams several GB of activations (1.9 GB saved per particle), so no explicit flush is needed"},
+            "clocks": clock_info, "gpu_launches": int(launches),
+            "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": int(h2d_step),
+                    "d2h_bytes_per_step": int(d2h_step), "ms_per_step": 1000.0 * e2e_sec / K},
+            "roofline": roofline, "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    try:
+        run_b200(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

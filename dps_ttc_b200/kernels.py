@@ -13,6 +13,31 @@ from . import _lib
 from ._lib import DpsError, check, lib, make_consts, make_source, particle_view, ptr, require_cuda_f32, stream_ptr
 
 
+class KernelTimer:
+    """CUDA-event brackets around libdpsttc launches on the launching (current) stream.  Off by default;
+    bench.py installs one (`kernels.TIMER = KernelTimer()`) to measure per-kernel durations live."""
+
+    def __init__(self):
+        self.spans = {}
+
+    def start(self, name):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return name, e
+
+    def stop(self, tok):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        self.spans.setdefault(tok[0], []).append((tok[1], e))
+
+    def summary(self):
+        """name → (launches, mean ms); call after a synchronize."""
+        return {n: (len(v), sum(a.elapsed_time(b) for a, b in v) / len(v)) for n, v in self.spans.items()}
+
+
+TIMER = None
+
+
 def _chw(x: torch.Tensor) -> int:
     n = 1
     for s in x.shape[1:]:
@@ -49,6 +74,7 @@ def posterior_update(sampler: str, x, eps, v, z, k, *, clip=True, g=None, vjp=No
         vjp = _lib.dense(vjp, "vjp")
     if z is not None:
         z = _lib.dense(z, "z")
+    tok = TIMER.start(f"posterior_update_{sampler}") if TIMER else None
     if sampler == "ddpm":
         vp, vs = (None, 0) if v is None else particle_view(v, "v")
         rc = lib().dps_posterior_update_ddpm(C.byref(src), vp, vs, ptr(z), gp, gs, ptr(vjp), C.byref(kc),
@@ -59,6 +85,8 @@ def posterior_update(sampler: str, x, eps, v, z, k, *, clip=True, g=None, vjp=No
     else:
         raise DpsError(f"unknown sampler kind {sampler!r}")
     check(rc, f"dps_posterior_update_{sampler}")
+    if tok:
+        TIMER.stop(tok)
     return x_next, sample, x0
 
 
@@ -165,8 +193,11 @@ class OperatorPlan:
                     if want_partials else None)
         if self.aux_floats and aux is None:
             aux = self.new_aux(n)
+        tok = TIMER.start(f"{self.kind}_forward") if TIMER else None
         check(lib().dps_operator_forward(self._h, C.byref(src), yp, ys, out.data_ptr(), ptr(partials), ptr(aux), n,
                                          stream_ptr(x.device)), f"dps_operator_forward[{self.kind}]")
+        if tok:
+            TIMER.stop(tok)
         return out, partials, aux
 
     def adjoint(self, r, coef=None, mask_x=None, mask_eps=None, k=None, clip=True, extra=None, out=None, aux=None):
@@ -186,8 +217,11 @@ class OperatorPlan:
         ep, es = (None, 0) if extra is None else particle_view(extra, "extra")
         if coef is not None:
             require_cuda_f32(coef, "coef")
+        tok = TIMER.start(f"{self.kind}_adjoint") if TIMER else None
         check(lib().dps_operator_adjoint(self._h, r.data_ptr(), ptr(coef), msrc, ep, es, gp, gs, ptr(aux), n,
                                          stream_ptr(r.device)), f"dps_operator_adjoint[{self.kind}]")
+        if tok:
+            TIMER.stop(tok)
         return out
 
 
@@ -208,8 +242,11 @@ def guidance_coef(partials, mode: int, scale: float):
     n, P, _ = partials.shape
     l2 = torch.empty(n, device=partials.device, dtype=torch.float32)
     coef = torch.empty(n, device=partials.device, dtype=torch.float32)
+    tok = TIMER.start("guidance_coef") if TIMER else None
     check(lib().dps_guidance_coef(partials.data_ptr(), P, n, int(mode), float(scale), l2.data_ptr(), coef.data_ptr(),
                                   stream_ptr(partials.device)), "dps_guidance_coef")
+    if tok:
+        TIMER.stop(tok)
     return l2, coef
 
 

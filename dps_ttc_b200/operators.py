@@ -249,6 +249,11 @@ class InpaintingOperator(B200Operator):
         _, m = self._mask_host(kwargs.get("mask"), H, W)
         return OperatorPlan.inpainting(m, C, H, W, device)
 
+    def forward(self, data, **kwargs):
+        if kwargs.get("mask", None) is None:
+            raise ValueError("Require mask")  # measurements.py:159-162
+        return super().forward(data, **kwargs)
+
     def ortho_project(self, data, **kwargs):  # measurements.py:167-168
         return data - self.forward(data, **kwargs)
 

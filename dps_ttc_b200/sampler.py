@@ -20,13 +20,11 @@ randn_like(measurement) for q_sample, then the resampling uniforms.
 from __future__ import annotations
 
 import functools
-import math
 
-import numpy as np
 import torch
 
 from . import kernels
-from ._lib import DPS_COEF_NORM, DpsError
+from ._lib import DpsError
 from .conditioning import ConditioningMethod, GuidanceSpec
 from .operators import B200Operator
 from .registry import get_sampler, register_sampler
@@ -282,6 +280,14 @@ class SpacedSampler:
         x_next = out["sample"] - first if returns_grad else first
         return x_next.detach(), (dist.detach() if torch.is_tensor(dist) else dist), (third if returns_grad else None)
 
+    def _step_indices(self, kwargs):
+        """All steps T−1 … 0 like the reference, or a window of the chain: `start_idx` (default T−1) and
+        `num_steps` — extra kwargs the reference's **kwargs signature tolerates; bench.py times K steps."""
+        hi = int(kwargs.get("start_idx", self.num_timesteps - 1))
+        n = kwargs.get("num_steps")
+        lo = 0 if n is None else max(0, hi - int(n) + 1)
+        return range(hi, lo - 1, -1)
+
     def _prepare(self, x_start, measurement, measurement_cond_fn):
         if not x_start.is_cuda:
             raise DpsError("x_start must be a CUDA tensor: the B200 samplers have no CPU path")
@@ -299,7 +305,7 @@ class SpacedSampler:
         anneal_kw = {k_: kwargs[k_] for k_ in ("anneal_amp", "anneal_scale", "anneal_loc") if k_ in kwargs}
         callback = kwargs.get("callback")
         meas_d = sem_d = None
-        for idx in reversed(range(self.num_timesteps)):
+        for idx in self._step_indices(kwargs):
             k = self.schedule.consts(idx, self.eta)
             t = idx / self.num_timesteps
             if fused:
@@ -336,18 +342,6 @@ class DDIM(SpacedSampler):
 # ------------------------------------------------------------------------------------------------
 # particle search
 # ------------------------------------------------------------------------------------------------
-class Resampler:
-    """weights → CDF → ancestors → gather, optionally across ranks (dist.ParticleShards)."""
-
-    def __init__(self, scheme="multinomial", linear_weights=True, sync_free=True, shards=None):
-        self.scheme, self.linear, self.sync_free, self.shards = scheme, linear_weights, sync_free, shards
-
-    def ancestors_from(self, logw_all, uniforms, n_draws):
-        w, cdf, lse, degenerate = kernels.weights_cdf(logw_all, linear_mode=self.linear)
-        ids = kernels.ancestors(cdf, uniforms, n_draws, systematic=(self.scheme == "systematic"), degenerate=degenerate)
-        return ids, w, degenerate
-
-
 @register_sampler(name="search_ddpm")
 class SearchDDPM(DDPM):
     """Greedy best-of-N inside the loop (gaussian_diffusion.py:592-641) and the resample_update
@@ -391,7 +385,7 @@ class SearchDDPM(DDPM):
         shards = kwargs.get("shards")
         n = img.shape[0]
         self.last_stats = {"best": []}
-        for idx in reversed(range(self.num_timesteps)):
+        for idx in self._step_indices(kwargs):
             k = self.schedule.consts(idx)
             with torch.no_grad():
                 _, eps, v = self._model_out(model, img, k)
@@ -425,7 +419,7 @@ class TTC_DDIM(DDIM):
         sem_weight = kwargs.get("semantic_weight", 0.0)  # config 5: semantic term in the reweighting
         distance = None
         self.last_stats = {"ancestors": {}}
-        for idx in reversed(range(self.num_timesteps)):
+        for idx in self._step_indices(kwargs):
             k = self.schedule.consts(idx, self.eta)
             t = idx / self.num_timesteps
             sem_d = None

@@ -42,3 +42,36 @@ def psnr(a, b, peak=2.0):
     """PSNR for images in [−1,1] (peak-to-peak 2), compute_metrics.py:93-98 convention."""
     mse = float(np.mean((np.asarray(a, np.float64) - np.asarray(b, np.float64)) ** 2))
     return float("inf") if mse == 0 else 10.0 * np.log10(peak ** 2 / mse)
+
+
+# ------------------------------------------------------------------------------------------------
+# oracle trajectories (numpy oracle + torch-CPU model for ε and its VJP)
+# ------------------------------------------------------------------------------------------------
+def model_and_vjp(model, x, t_model):
+    xt = torch.from_numpy(np.ascontiguousarray(x)).requires_grad_(True)
+    out = model(xt, torch.tensor([t_model], dtype=torch.float32))
+
+    def vjp(g_eps):
+        g6 = torch.zeros_like(out)
+        g6[:, :3] = torch.from_numpy(np.ascontiguousarray(g_eps))
+        return torch.autograd.grad(out, xt, g6, retain_graph=True)[0].numpy()
+    return out.detach().numpy(), vjp
+
+
+def oracle_guided_step(O, model, tables, img, idx, y, fwd, adj, z, mode="norm", scale=0.3, sampler="ddpm",
+                       extra=None, nonlinear_vjp=None):
+    """One guided reverse step restated with the oracle.  fwd/adj: numpy operator and adjoint;
+    nonlinear_vjp(x0, g): Jᵀg at x0 for nonlinear operators (replaces adj)."""
+    k = tables.at(idx)
+    out6, vjp = model_and_vjp(model, img, k["model_t"])
+    eps, v = out6[:, :3], out6[:, 3:]
+    if sampler == "ddpm":
+        sample, x0 = O.ddpm_sample(img, eps, v, z, k, idx)
+    else:
+        sample, x0 = O.ddim_sample(img, eps, z, k, idx)
+    _, pre = O.x0_from_eps(img, eps, k)
+    r = y - fwd(x0)
+    adjoint = adj if nonlinear_vjp is None else (lambda u: nonlinear_vjp(x0, u))
+    gpre, norm = O.guidance_cotangent(r, adjoint, pre, mode, scale, extra)
+    x_next = O.guided_update(sample, gpre, vjp(gpre), k)
+    return x_next, norm, dict(x0=x0, sample=sample, r=r, gpre=gpre)

@@ -1,0 +1,217 @@
+"""GPU parity of the fused samplers: (a) against traces recorded from the REFERENCE's own loops
+(tests/golden/trace_*.npz, produced by oracle/make_golden.py), (b) against the oracle run live at the
+BASELINE image size.  Everything goes through the registries → ctypes → libdpsttc.so."""
+import functools
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import TinyEps, golden, oracle_guided_step, psnr
+from oracle import dps_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+DIFF = dict(steps=1000, noise_schedule="linear", model_mean_type="epsilon", model_var_type="learned_range",
+            dynamic_threshold=False, clip_denoised=True, rescale_timesteps=True)
+
+
+@pytest.fixture(autouse=True)
+def _exact_fp32():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.deterministic = True
+    yield
+
+
+def build(sampler_name, respacing, method, params, op_name, op_cfg, noise_sigma=0.05):
+    from dps_ttc_b200.registry import get_conditioning_method, get_noise, get_operator
+    from dps_ttc_b200.sampler import create_sampler
+    dev = torch.device("cuda:0")
+    op = get_operator(op_name, device=dev, **op_cfg)
+    noiser = get_noise("gaussian", sigma=noise_sigma)
+    cond = get_conditioning_method(method, op, noiser, **params)
+    s = create_sampler(sampler=sampler_name, timestep_respacing=respacing, **DIFF)
+    return s, op, cond, dev
+
+
+def tape_from(g, n_steps, stride=2, first=0):
+    """NoiseTape from the recorded randn_like draws: per step z then the q_sample noise."""
+    from dps_ttc_b200.sampler import NoiseTape
+    z, q, u = {}, {}, {}
+    for i, idx in enumerate(reversed(range(n_steps))):
+        z[idx] = torch.from_numpy(g[f"randn_{first + stride * i}"])
+        if stride == 2:
+            q[idx] = torch.from_numpy(g[f"randn_{first + stride * i + 1}"])
+    return NoiseTape(z=z, q=q, uniforms=u)
+
+
+def close(a, b, tol=1e-4):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.abs(a - b).max() <= tol * max(1.0, np.abs(b).max())
+
+
+def test_trace_ddpm_ps_semantic_gaussian_blur():
+    g = golden("trace_ddpm_ps_semantic_gblur.npz")
+    s, op, cond, dev = build("ddpm", "4", "ps_semantic", dict(scale=0.3, sem_guid_scale=0.0), "gaussian_blur",
+                             dict(kernel_size=61, intensity=3.0))
+    s.noise = tape_from(g, 4)
+    model = TinyEps(seed=11).to(dev)
+    seen = {}
+    img, dist, sem = s.p_sample_loop(model=model, x_start=torch.from_numpy(g["x_start"]).to(dev),
+                                     measurement=torch.from_numpy(g["y"]).to(dev),
+                                     measurement_cond_fn=cond.conditioning, record=False, save_root=None,
+                                     callback=lambda idx, im, d, sd: seen.__setitem__(idx, (im.cpu().numpy(), d.cpu().numpy())))
+    for i, idx in enumerate(reversed(range(4))):
+        assert close(seen[idx][1], g[f"step{i}_dist"], 1e-5), f"distance at step {idx}"
+        if i < 3:
+            assert close(seen[idx][0], g[f"step{i + 1}_x_prev"], 1e-4), f"x after step {idx}"
+    assert close(img.cpu().numpy(), g["final"], 1e-4)
+
+
+def test_trace_ddpm_ps_inpainting_upstream_arity():
+    g = golden("trace_ddpm_ps_inpaint.npz")
+    s, op, cond, dev = build("ddpm", "4", "ps", dict(scale=0.5), "inpainting", {})
+    s.noise = tape_from(g, 4, stride=1)
+    s.parity_rng = False
+    model = TinyEps(seed=14).to(dev)
+    mask = torch.from_numpy(g["mask"]).to(dev)
+    fn = functools.partial(cond.conditioning, mask=mask)
+    img, dist, _ = s.p_sample_loop(model=model, x_start=torch.from_numpy(g["x_start"]).to(dev),
+                                   measurement=torch.from_numpy(g["y"]).to(dev), measurement_cond_fn=fn,
+                                   record=False, save_root=None)
+    assert close(img.cpu().numpy(), g["final"], 1e-4)
+    assert close(dist.cpu().numpy(), g["final_dist"], 1e-5)
+
+
+def test_trace_ddim_ps_motion_blur():
+    g = golden("trace_ddim_ps_motion.npz")
+    s, op, cond, dev = build("ddim", "3", "ps", dict(scale=0.3), "motion_blur", dict(kernel_size=61, intensity=0.5))
+    op.kernel.kernelMatrix = g["kernel"]
+    op._weights = np.asarray(g["kernel"], np.float32)
+    s.noise = tape_from(g, 3, stride=1)
+    s.parity_rng = False
+    model = TinyEps(seed=16).to(dev)
+    img, dist, _ = s.p_sample_loop(model=model, x_start=torch.from_numpy(g["x_start"]).to(dev),
+                                   measurement=torch.from_numpy(g["y"]).to(dev),
+                                   measurement_cond_fn=cond.conditioning, record=False, save_root=None)
+    assert close(img.cpu().numpy(), g["final"], 1e-4)
+    assert close(dist.cpu().numpy(), g["final_dist"], 1e-5)
+
+
+def test_trace_search_ddpm_greedy():
+    g = golden("trace_search_ddpm_gblur.npz")
+    s, op, cond, dev = build("search_ddpm", "4", "ps", dict(scale=0.3), "gaussian_blur", dict(kernel_size=61, intensity=3.0))
+    s.noise = tape_from(g, 4, stride=1)
+    model = TinyEps(seed=13).to(dev)
+    img = s.p_sample_loop(model=model, x_start=torch.from_numpy(g["x_start"]).to(dev),
+                          measurement=torch.from_numpy(g["y"]).to(dev), measurement_cond_fn=cond.conditioning,
+                          record=False, save_root=None, operator=op)
+    out = img.cpu().numpy()
+    assert np.abs(out - out[:1]).max() == 0.0
+    assert close(out, g["final"], 1e-4)
+
+
+def test_trace_ttc_ddim_mcg_resampling_indices_bit_exact():
+    g = golden("trace_ttc_ddim_mcg_sr.npz")
+    s, op, cond, dev = build("ttc_ddim", "12", "mcg", dict(scale=0.5), "super_resolution",
+                             dict(in_shape=(1, 3, 32, 32), scale_factor=4))
+    tape = tape_from(g, 12)
+    # the reference resamples when idx % 10 == 0 and the weights are not all equal: idx 10 and idx 0
+    k = 0
+    for idx in (10, 0):
+        if f"mn_u_{k}" in g.files:
+            tape._u[idx] = torch.from_numpy(g[f"mn_u_{k}"])
+            k += 1
+    s.noise = tape
+    s.sync_free = False
+    model = TinyEps(seed=12).to(dev)
+    img, dist = s.p_sample_loop(model=model, x_start=torch.from_numpy(g["x_start"]).to(dev),
+                                measurement=torch.from_numpy(g["y"]).to(dev), measurement_cond_fn=cond.conditioning,
+                                record=False, save_root=None)
+    got = [v.cpu().numpy() for _, v in sorted(s.last_stats["ancestors"].items(), reverse=True)]
+    want = [g[f"mn_ids_{i}"] for i in range(k)]
+    assert len(got) == len(want) >= 1
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b)                       # bit-exact ancestor indices
+    assert close(img.cpu().numpy(), g["final"], 1e-4)
+    assert close(dist.cpu().numpy(), g["final_dist"], 1e-5)
+
+
+# ------------------------------------------------------------------------------------------------
+# live oracle at the BASELINE image size (256×256), a few steps of the 1000-step chain
+# ------------------------------------------------------------------------------------------------
+def _live(op_name, op_cfg, method, params, fwd, adj, mode, scale_of, sampler="ddpm", n=2, steps=3, nl_vjp=None,
+          cond_kw=None, seed=0):
+    from dps_ttc_b200.sampler import NoiseTape
+    s, op, cond, dev = build(sampler, "", method, params, op_name, op_cfg)
+    rng = np.random.default_rng(seed)
+    x_true = (rng.random((1, 3, 256, 256)) * 2 - 1).astype(np.float32)
+    y = fwd(x_true)
+    y = (y + 0.05 * rng.standard_normal(y.shape)).astype(np.float32)
+    x = rng.standard_normal((n, 3, 256, 256)).astype(np.float32)
+    idxs = list(range(999, 999 - steps, -1))
+    zs = {i: rng.standard_normal(x.shape).astype(np.float32) for i in idxs}
+    s.noise = NoiseTape(z={i: torch.from_numpy(z) for i, z in zs.items()})
+    s.parity_rng = False
+    model_cpu, model_gpu = TinyEps(seed=3), TinyEps(seed=3).to(dev)
+    fn = cond.conditioning if not cond_kw else functools.partial(cond.conditioning, **cond_kw(dev))
+    res = s.p_sample_loop(model=model_gpu, x_start=torch.from_numpy(x).to(dev), measurement=torch.from_numpy(y).to(dev),
+                          measurement_cond_fn=fn, record=False, save_root=None, num_steps=steps)
+    tab = O.Tables(1000)
+    img = x
+    for i in idxs:
+        img, norm, _ = oracle_guided_step(O, model_cpu, tab, img, i, y, fwd, adj, zs[i], mode, scale_of(tab, i), sampler,
+                                          nonlinear_vjp=nl_vjp)
+    got = res[0].cpu().numpy()
+    assert np.abs(got - img).max() <= 1e-4 * max(1.0, np.abs(img).max())       # ≤ 1e-4 per step, fp32
+    assert np.abs(res[1].cpu().numpy() - norm).max() <= 1e-5 * norm.max()
+    assert psnr(got, img) >= 40.0
+
+
+def test_live_c1_gaussian_deblur_ps():
+    from dps_ttc_b200.tables import gaussian_kernel
+    kern = gaussian_kernel(61, 3.0).astype(np.float32)
+    _live("gaussian_blur", dict(kernel_size=61, intensity=3.0), "ps", dict(scale=0.3),
+          lambda x: O.blur_forward(x, kern), lambda u: O.blur_adjoint(u, kern), "norm", lambda t, i: 0.3)
+
+
+def test_live_c2_super_resolution_ps():
+    _live("super_resolution", dict(in_shape=(1, 3, 256, 256), scale_factor=4), "ps", dict(scale=0.01),
+          lambda x: O.resize_forward(x, 0.25), lambda u: O.resize_adjoint(u, 0.25, 256, 256), "norm", lambda t, i: 0.01)
+
+
+def test_live_c4_phase_retrieval_ps_anneal():
+    sigma2 = max(0.05, 0.05) ** 2
+    _live("phase_retrieval", dict(oversample=2.0), "ps_anneal", dict(scale=1.0),
+          lambda x: O.phase_forward(x, 64), None, "norm_sq", lambda t, i: t.at(i)["beta"] / (1.0 * sigma2),
+          nl_vjp=lambda x0, u: O.phase_vjp(x0, u, 64))
+
+
+def test_live_c5_inpainting_ps():
+    from dps_ttc_b200.tables import MaskGenerator
+    np.random.seed(8)
+    mask = MaskGenerator("random", mask_prob_range=(0.3, 0.7), image_size=256)(np.zeros((1, 3, 256, 256)))[:, :1]
+    _live("inpainting", {}, "ps", dict(scale=0.5), lambda x: O.inpaint_forward(x, mask),
+          lambda u: O.inpaint_forward(u, mask), "norm", lambda t, i: 0.5,
+          cond_kw=lambda dev: {"mask": torch.from_numpy(mask).to(dev)})
+
+
+def test_live_c3_motion_deblur_ddim():
+    from dps_ttc_b200.tables import motion_kernel
+    np.random.seed(8)
+    kern = motion_kernel(61, 0.5).astype(np.float32)
+    from dps_ttc_b200 import tables
+    import dps_ttc_b200.operators as ops
+
+    class FixedKernel:
+        def __init__(self, size, intensity):
+            self.kernelMatrix = kern
+    old = tables.MotionKernel
+    tables.MotionKernel = FixedKernel
+    try:
+        _live("motion_blur", dict(kernel_size=61, intensity=0.5), "ps", dict(scale=0.3),
+              lambda x: O.blur_forward(x, kern), lambda u: O.blur_adjoint(u, kern), "norm", lambda t, i: 0.3,
+              sampler="ddim")
+    finally:
+        tables.MotionKernel = old

@@ -20,11 +20,14 @@ from oracle import dps_oracle as O  # noqa: E402
 
 dev = torch.device("cuda:0")
 results = []
+failures = []
 
 
 def report(name, err, tol, extra=""):
     ok = err <= tol
     results.append(ok)
+    if not ok:
+        failures.append(f"{name}: max|Δ|={err:.3e} > tol {tol:.1e}")
     print(f"{'PASS' if ok else 'FAIL'}  {name:<46s} max|Δ|={err:.3e}  tol={tol:.1e}  {extra}", flush=True)
 
 
@@ -34,6 +37,7 @@ def check(name):
             fn()
         except Exception:  # noqa: BLE001
             results.append(False)
+            failures.append(f"{name}: exception {traceback.format_exc(limit=1)}")
             print(f"FAIL  {name}: exception\n{traceback.format_exc()}", flush=True)
         return fn
     return deco

@@ -1,0 +1,140 @@
+"""HBM-regime micro-benchmark of every graft kernel: N particles per launch (default 128 → tensors of
+100 MB, far beyond the 126 MB L2 once several streams are involved), buffers rotated between launches so no
+launch re-reads what the previous one left in L2, CUDA events on the launching stream, ≥3 warm-ups.
+Prints one JSON line per kernel: algorithmic bytes, mean µs, GB/s, fraction of the measured
+HBM peak.   python tools/kernel_bench.py [--n 128] [--iters 20] [--only update,gauss,...]"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+
+from dps_ttc_b200 import kernels, tables  # noqa: E402
+from dps_ttc_b200.kernels import OperatorPlan  # noqa: E402
+from dps_ttc_b200.schedule import Schedule, named_beta_schedule  # noqa: E402
+
+T = 3 * 256 * 256 * 4
+
+
+def peak_gbs():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    return float(json.load(open(p))["hbm_gbs"]) if os.path.exists(p) else 6650.0
+
+
+def time_it(fn, n_sets, iters, warm=3):
+    for i in range(warm):
+        fn(i % n_sets)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters):
+        fn(i % n_sets)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters * 1e3  # µs
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=128)
+    ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--sets", type=int, default=3, help="rotating buffer sets (each ≥ L2)")
+    ap.add_argument("--only", default="")
+    a = ap.parse_args()
+    dev = torch.device("cuda:0")
+    n, S = a.n, a.sets
+    only = set(filter(None, a.only.split(",")))
+    peak = peak_gbs()
+    k = Schedule(named_beta_schedule("linear", 1000)).consts(500)
+    gen = torch.Generator(dev).manual_seed(0)
+    rnd = lambda *s: torch.randn(*s, device=dev, generator=gen)  # noqa: E731
+    X = [rnd(n, 3, 256, 256) / k.c1 for _ in range(S)]
+    O6 = [rnd(n, 6, 256, 256) * 0.3 / k.c2 for _ in range(S)]
+    Z = [rnd(n, 3, 256, 256) for _ in range(S)]
+    G6 = [rnd(n, 6, 256, 256) * 1e-2 for _ in range(S)]
+    VJ = [rnd(n, 3, 256, 256) * 1e-2 for _ in range(S)]
+    OUT = [torch.empty(n, 3, 256, 256, device=dev) for _ in range(S)]
+
+    def emit(name, alg_bytes, us, extra=None):
+        gbs = alg_bytes / (us * 1e-6) / 1e9
+        rec = {"kernel": name, "n_particles": n, "alg_bytes": alg_bytes, "mean_us": round(us, 2), "gbs": round(gbs, 1),
+               "frac_of_measured_peak": round(gbs / peak, 4), "peak_gbs": peak}
+        if extra:
+            rec.update(extra)
+        print(json.dumps(rec), flush=True)
+
+    def want(tag):
+        return not only or tag in only
+
+    if want("copy"):
+        us = time_it(lambda i: OUT[i].copy_(X[(i + 1) % S]), S, a.iters)
+        emit("torch copy_ (reference point)", 2 * n * T, us)
+    if want("update"):
+        us = time_it(lambda i: kernels.posterior_update("ddpm", X[i], O6[i][:, :3], O6[i][:, 3:], Z[i], k, g=G6[i][:, :3],
+                                                        vjp=VJ[i], out=OUT[i]), S, a.iters)
+        emit("posterior_update_ddpm (7T)", 7 * n * T, us)
+        us = time_it(lambda i: kernels.posterior_update("ddim", X[i], O6[i][:, :3], None, None, k, g=G6[i][:, :3],
+                                                        vjp=VJ[i], out=OUT[i]), S, a.iters)
+        emit("posterior_update_ddim (5T)", 5 * n * T, us)
+        us = time_it(lambda i: kernels.x0_from_eps(X[i], O6[i][:, :3], k, out=OUT[i]), S, a.iters)
+        emit("x0_from_eps (3T)", 3 * n * T, us)
+
+    def op_bench(tag, plan, m_bytes):
+        if not want(tag):
+            return
+        oc, oh, ow = plan.out_shape
+        y = rnd(1, oc, oh, ow)
+        R = [torch.empty(n, oc, oh, ow, device=dev) for _ in range(S)]
+        P = [torch.empty(n, plan.partials_per_particle, 2, device=dev) for _ in range(S)]
+        AUX = [plan.new_aux(n) for _ in range(S)]
+        coef = torch.full((n,), -0.01, device=dev)
+
+        def fwd(i):
+            src = kernels.make_source(X[i], O6[i][:, :3], k.c1, k.c2, True)
+            import ctypes as C
+            kernels.check(kernels.lib().dps_operator_forward(plan._h, C.byref(src), y.data_ptr(), 0, R[i].data_ptr(),
+                                                             P[i].data_ptr(), kernels.ptr(AUX[i]), n,
+                                                             kernels.stream_ptr(dev)), "fwd")
+        us = time_it(fwd, S, a.iters)
+        emit(f"{tag}_forward (2T+M)", n * (2 * T + m_bytes), us, {"plan": plan.kind, "taps": plan.taps})
+        us = time_it(lambda i: plan.adjoint(R[i], coef, X[i], O6[i][:, :3], k, True, None, out=G6[i][:, :3], aux=AUX[i]),
+                     S, a.iters)
+        emit(f"{tag}_adjoint (3T+M)", n * (3 * T + m_bytes), us, {"plan": plan.kind, "taps": plan.taps})
+
+    np.random.seed(8)
+    mask = tables.MaskGenerator("random", mask_prob_range=(0.3, 0.7), image_size=256)(np.zeros((1, 3, 256, 256)))[0, 0]
+    op_bench("inpaint", OperatorPlan.inpainting(mask, 3, 256, 256, dev), T)
+    op_bench("gauss", OperatorPlan.blur(tables.gaussian_kernel(61, 3.0).astype(np.float32), 3, 256, 256, dev), T)
+    (fh, wh), (fw, ww), _ = tables.resizer_tables((1, 3, 256, 256), 0.25)
+    op_bench("sr4", OperatorPlan.resize(fh, wh, fw, ww, 3, 256, 256, dev), T // 16)
+    np.random.seed(8)
+    op_bench("motion", OperatorPlan.blur(tables.motion_kernel(61, 0.5).astype(np.float32), 3, 256, 256, dev), T)
+    if want("phase"):
+        nn = min(n, 32)
+        plan = OperatorPlan.phase(64, 3, 256, 256, dev)
+        y = rnd(1, 3, 384, 384)
+        R = [torch.empty(nn, 3, 384, 384, device=dev) for _ in range(S)]
+        AUX = [plan.new_aux(nn) for _ in range(S)]
+        coef = torch.full((nn,), -0.01, device=dev)
+        M = T * 9 // 4
+        us = time_it(lambda i: plan.forward(X[i][:nn], O6[i][:nn, :3], k, True, y, want_partials=True, aux=AUX[i], out=R[i]),
+                     S, a.iters)
+        emit("phase_forward (2T+M, 2 kernels)", nn * (2 * T + M), us, {"n_particles": nn})
+        us = time_it(lambda i: plan.adjoint(R[i], coef, X[i][:nn], O6[i][:nn, :3], k, True, None, out=G6[i][:nn, :3], aux=AUX[i]),
+                     S, a.iters)
+        emit("phase_adjoint (3T+M, 2 kernels)", nn * (3 * T + M), us, {"n_particles": nn})
+    if want("gather"):
+        ids = torch.randint(0, n, (n,), device=dev)
+        us = time_it(lambda i: kernels.gather_particles(X[i], ids, out=OUT[(i + 1) % S]), S, a.iters)
+        emit("gather_particles (2T)", 2 * n * T, us)
+
+
+if __name__ == "__main__":
+    main()
