@@ -2,28 +2,32 @@
 // arbitrary (k,k) kernel (measurements.py:93-126, util/img_utils.py:268-308) and its exact adjoint.
 //
 // The motion kernels of the reference are thin paths: a few hundred non-zero taps of 3 721.  The plan
-// keeps only the non-zero taps (dy, dx, w); one CTA stages a strip of the image with its halo in
-// shared memory (reflect-filled for A, zero-filled for Aᵀ) and every thread accumulates 8 vertically
-// adjacent outputs of one column, one LDS + one FMA per (tap, output).
+// keeps only the non-zero taps (dy, dx, w).
 //
-// Adjoint with reflect padding.  out[i] = Σ_d w[d]·x[refl(i+d)] scatters w[d]·u[i] into refl(i+d), so
-//   g[m] = Σ_d w[d]·( U(m−d) + [m≥1]·U(−m−d) + [m≤L−2]·U(2(L−1)−m−d) ),  U zero outside [0,L),
-// per axis; the 2-D adjoint is the product of the row and column variants.  Only pixels within the
-// kernel radius of a border have more than the first term, so interior CTAs run the plain path.
-//
-// Roofline: T_nz taps → 2·T_nz flop per pixel per direction against 8-16 B: LDS/FMA-bound, NOT
-// HBM-bound, for T_nz ≳ 40; stated as such in DESIGN.md.
+// forward : one CTA stages a strip of x̂₀ with its halo in shared memory, reflect-filled, and every thread
+//           accumulates 8 vertically adjacent outputs of one column: one LDS + one FFMA per (tap, output),
+//           the tap's tile offset precomputed once per CTA.
+// adjoint : A = C·P (P = reflect pad, C = valid correlation) ⇒ Aᵀ = Pᵀ·Cᵀ, done literally in two kernels:
+//           (1) t = Cᵀu on the PADDED domain (H+2Ry, W+2Rx) — the same gather kernel with negated offsets over
+//               a zero-filled tile, no border cases at all — into the operator's workspace (stays in L2);
+//           (2) fold: g[m] = Σ_{p : reflect(p) = m} t[p]  (1, 2 or 4 terms per pixel), fused with
+//               coef / extra / clamp mask.
+// Roofline: T_nz taps → 2·T_nz flop per pixel per direction against 8-16 B, one LDS per FMA: LDS/issue-bound,
+// NOT HBM-bound, for T_nz ≳ 20 — stated as such in DESIGN.md.
 #include <vector>
 
 #include "operator.cuh"
 
 namespace {
-constexpr int kThreads = 256;
 constexpr int kRows = 32;
 constexpr int kGroup = 8;
 
 struct Tap {
   int dydx;  // (dy << 16) | (dx & 0xffff)
+  float w;
+};
+struct TapOff {
+  int off;  // signed offset in the staged tile
   float w;
 };
 }  // namespace
@@ -39,27 +43,37 @@ namespace {
 DPS_DEV int tap_dy(int v) { return v >> 16; }
 DPS_DEV int tap_dx(int v) { return (int)(short)(v & 0xffff); }
 
+// kAdjoint = false: out rows/cols = image;   tile = rows [r0−Ry, r0+32+Ry) × cols [−Rx, W+Rx), reflect fill
+// kAdjoint = true : out rows/cols = padded t; tile = u rows [p0−2Ry, p0+32) (image coords p0−Ry …) zero fill,
+//                   cols [−2Rx, W+2Rx).  blockDim.x ≥ number of output columns is NOT required (columns loop).
 template <bool kAdjoint>
-__global__ void __launch_bounds__(kThreads) sparse_kernel(const Tap* __restrict__ taps_g, int ntaps, int Ry,
-                                                          int Rx, int C, int H, int W, int strips,
-                                                          const FwdArgs fa, const AdjArgs aa) {
+__global__ void __launch_bounds__(320) sparse_kernel(const Tap* __restrict__ taps_g, int ntaps, int Ry, int Rx, int C,
+                                                     int H, int W, int strips, const FwdArgs fa, const AdjArgs aa,
+                                                     float* __restrict__ t_out) {
   extern __shared__ __align__(16) float smem[];
-  const int SW = W + 2 * Rx;
+  const int OW = kAdjoint ? W + 2 * Rx : W;      // output columns
+  const int OH = kAdjoint ? H + 2 * Ry : H;      // output rows
+  const int halo_x = kAdjoint ? 2 * Rx : Rx;     // tile columns left of image column 0
+  const int SW = W + 2 * halo_x;
   const int tile_rows = kRows + 2 * Ry;
   float* tile = smem;
-  Tap* taps = reinterpret_cast<Tap*>(tile + tile_rows * SW);
+  TapOff* taps = reinterpret_cast<TapOff*>(tile + tile_rows * SW);
   float* red = reinterpret_cast<float*>(taps + ntaps);
 
   const int strip = blockIdx.x % strips;
   const int c = blockIdx.x / strips;
   const int n = blockIdx.y;
-  const int r0 = strip * kRows;
-  const int tid = threadIdx.x;
+  const int o0 = strip * kRows;                  // first output row of this CTA (padded coords for the adjoint)
+  const int img_row0 = kAdjoint ? o0 - 2 * Ry : o0 - Ry;  // image row held by tile row 0
+  const int tid = threadIdx.x, nthreads = blockDim.x;
   const int64_t plane = (int64_t)c * H * W;
 
-  for (int i = tid; i < ntaps; i += kThreads) taps[i] = taps_g[i];
-
-  // ---- stage the strip: rows [r0-Ry, r0+kRows+Ry), cols [-Rx, W+Rx) ---------------------------
+  for (int i = tid; i < ntaps; i += nthreads) {
+    const Tap tp = taps_g[i];
+    const int off = tap_dy(tp.dydx) * SW + tap_dx(tp.dydx);
+    taps[i].off = kAdjoint ? -off : off;
+    taps[i].w = tp.w;
+  }
   {
     const float* x;
     const float* eps = nullptr;
@@ -73,92 +87,62 @@ __global__ void __launch_bounds__(kThreads) sparse_kernel(const Tap* __restrict_
       c1 = fa.src.c1; c2 = fa.src.c2; clip = fa.src.clip;
     }
     const int w4 = W / 4;
-    for (int i = tid; i < tile_rows * w4; i += kThreads) {
+    for (int i = tid; i < tile_rows * w4; i += nthreads) {
       const int tr = i / w4, q = i - tr * w4;
-      int row = r0 - Ry + tr;
+      int row = img_row0 + tr;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (kAdjoint) {
-        if (row >= 0 && row < H) v = src_load4(x, eps, (int64_t)row * W + q * 4, c1, c2, clip);
+        if (row >= 0 && row < H) v = ldg_stream4(x + (int64_t)row * W + q * 4);
       } else {
         row = reflect_idx(row, H);
         v = src_load4(x, eps, (int64_t)row * W + q * 4, c1, c2, clip);
       }
-      *reinterpret_cast<float4*>(tile + tr * SW + Rx + q * 4) = v;
+      *reinterpret_cast<float4*>(tile + tr * SW + halo_x + q * 4) = v;
     }
     __syncthreads();
     // column halos: reflect (forward) from the staged interior, zero (adjoint)
-    for (int i = tid; i < tile_rows * 2 * Rx; i += kThreads) {
-      const int tr = i / (2 * Rx), q = i - tr * (2 * Rx);
-      const int colimg = q < Rx ? q - Rx : W + (q - Rx);  // image column of this halo cell
+    for (int i = tid; i < tile_rows * 2 * halo_x; i += nthreads) {
+      const int tr = i / (2 * halo_x), q = i - tr * (2 * halo_x);
+      const int colimg = q < halo_x ? q - halo_x : W + (q - halo_x);
       float v = 0.f;
-      if (!kAdjoint) v = tile[tr * SW + Rx + reflect_idx(colimg, W)];
-      tile[tr * SW + Rx + colimg] = v;
+      if (!kAdjoint) v = tile[tr * SW + halo_x + reflect_idx(colimg, W)];
+      tile[tr * SW + halo_x + colimg] = v;
     }
   }
   __syncthreads();
 
-  const bool row_variants = kAdjoint && (r0 <= Ry || r0 + kRows - 1 >= H - 1 - Ry);
   float sq = 0.f, ab = 0.f;
-  for (int col = tid; col < W; col += kThreads) {
-    const bool col_variants = kAdjoint && (col <= Rx || col >= W - 1 - Rx);
+  for (int col = tid; col < OW; col += nthreads) {
+    // tile element under output (o0+g0, col) with zero tap offset:
+    //   forward: image (o0+g0, col)            → tile row g0+Ry,      tile col halo_x+col
+    //   adjoint: padded (p, q) = image (p−Ry, q−Rx) → tile row g0+Ry, tile col halo_x+col−Rx
+    const float* base0 = tile + Ry * SW + halo_x + col - (kAdjoint ? Rx : 0);
 #pragma unroll 1
     for (int g0 = 0; g0 < kRows; g0 += kGroup) {
       float acc[kGroup];
 #pragma unroll
       for (int j = 0; j < kGroup; ++j) acc[j] = 0.f;
-      if (!(row_variants || col_variants)) {
-        // plain path: forward reads x̂₀[m+d], adjoint reads u[m−d]
-        const float* base = tile + (g0 + Ry) * SW + Rx + col;
-#pragma unroll 2
-        for (int t = 0; t < ntaps; ++t) {
-          const Tap tp = taps[t];
-          const int dy = tap_dy(tp.dydx), dx = tap_dx(tp.dydx);
-          const float* p = kAdjoint ? base - dy * SW - dx : base + dy * SW + dx;
+      const float* base = base0 + g0 * SW;
+#pragma unroll 4
+      for (int t = 0; t < ntaps; ++t) {
+        const TapOff tp = taps[t];
+        const float* p = base + tp.off;
 #pragma unroll
-          for (int j = 0; j < kGroup; ++j) acc[j] = fmaf(tp.w, p[j * SW], acc[j]);
-        }
-      } else {
-        // border path (adjoint only): up to 2 row variants × 2 column variants per tap
-        for (int t = 0; t < ntaps; ++t) {
-          const Tap tp = taps[t];
-          const int dy = tap_dy(tp.dydx), dx = tap_dx(tp.dydx);
-          int xs[3];
-          int nx = 0;
-          xs[nx++] = col - dx;  // may fall in the zero halo
-          if (col >= 1) { const int x1 = -col - dx; if (x1 >= 0 && x1 < W) xs[nx++] = x1; }
-          if (col <= W - 2) { const int x2 = 2 * (W - 1) - col - dx; if (x2 >= 0 && x2 < W) xs[nx++] = x2; }
-#pragma unroll
-          for (int j = 0; j < kGroup; ++j) {
-            const int my = r0 + g0 + j;
-            int ys[3];
-            int ny = 0;
-            { const int y0 = my - dy; if (y0 >= 0 && y0 < H) ys[ny++] = y0; }
-            if (my >= 1) { const int y1 = -my - dy; if (y1 >= 0 && y1 < H) ys[ny++] = y1; }
-            if (my <= H - 2) { const int y2 = 2 * (H - 1) - my - dy; if (y2 >= 0 && y2 < H) ys[ny++] = y2; }
-            float s = 0.f;
-            for (int a = 0; a < ny; ++a)
-              for (int b = 0; b < nx; ++b) s += tile[(ys[a] - (r0 - Ry)) * SW + Rx + xs[b]];
-            acc[j] = fmaf(tp.w, s, acc[j]);
-          }
-        }
+        for (int j = 0; j < kGroup; ++j) acc[j] = fmaf(tp.w, p[j * SW], acc[j]);
       }
-      // ---- epilogue for these kGroup outputs of column `col` ---------------------------------
 #pragma unroll
       for (int j = 0; j < kGroup; ++j) {
-        const int row = r0 + g0 + j;
-        if (row >= H) continue;
-        const int64_t off = plane + (int64_t)row * W + col;
+        const int row = o0 + g0 + j;
+        if (row >= OH) continue;
         if (!kAdjoint) {
+          const int64_t off = plane + (int64_t)row * W + col;
           float res = acc[j];
           if (fa.y) res = __fsub_rn(fa.y[n * fa.y_stride + off], res);
           fa.out[(int64_t)n * C * H * W + off] = res;
           sq += res * res;
           ab += fabsf(res);
         } else {
-          float res = (aa.coef ? aa.coef[n] : 1.0f) * acc[j];
-          if (aa.extra) res += ldg_stream(aa.extra + n * aa.extra_stride + off);
-          res *= mask_load(aa.mask_src, aa.has_mask, n, off);
-          aa.g[n * aa.g_stride + off] = res;
+          t_out[(((int64_t)n * C + c) * OH + row) * OW + col] = acc[j];
         }
       }
     }
@@ -173,27 +157,38 @@ __global__ void __launch_bounds__(kThreads) sparse_kernel(const Tap* __restrict_
   }
 }
 
-size_t sparse_smem(const dps_operator* op) {
-  const SparseTables* t = op->sparse;
-  return sizeof(float) * ((size_t)(kRows + 2 * t->Ry) * (op->W + 2 * t->Rx) + 64) + sizeof(Tap) * (size_t)t->ntaps;
+// g[my][mx] = Σ_{rows p : reflect(p−Ry)=my} Σ_{cols q : reflect(q−Rx)=mx} t[p][q], then the cotangent epilogue
+__global__ void __launch_bounds__(256) sparse_fold_kernel(const float* __restrict__ t, int Ry, int Rx, int C, int H,
+                                                          int W, const AdjArgs aa) {
+  const int n = blockIdx.z, c = blockIdx.y;
+  const int OH = H + 2 * Ry, OW = W + 2 * Rx;
+  const float* tp = t + ((int64_t)n * C + c) * OH * OW;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= H * W) return;
+  const int my = idx / W, mx = idx - my * W;
+  int rows[3], cols[3], nr = 0, nc = 0;
+  rows[nr++] = my + Ry;
+  if (my >= 1 && my <= Ry) rows[nr++] = Ry - my;
+  if (my <= H - 2 && my >= H - 1 - Ry) rows[nr++] = 2 * (H - 1) - my + Ry;
+  cols[nc++] = mx + Rx;
+  if (mx >= 1 && mx <= Rx) cols[nc++] = Rx - mx;
+  if (mx <= W - 2 && mx >= W - 1 - Rx) cols[nc++] = 2 * (W - 1) - mx + Rx;
+  float s = 0.f;
+  for (int a = 0; a < nr; ++a)
+    for (int b = 0; b < nc; ++b) s += tp[(int64_t)rows[a] * OW + cols[b]];
+  const int64_t off = (int64_t)c * H * W + idx;
+  float res = (aa.coef ? aa.coef[n] : 1.0f) * s;
+  if (aa.extra) res += ldg_stream(aa.extra + n * aa.extra_stride + off);
+  res *= mask_load(aa.mask_src, aa.has_mask, n, off);
+  aa.g[n * aa.g_stride + off] = res;
 }
 
-template <bool kAdjoint>
-int sparse_launch(const dps_operator* op, const FwdArgs& fa, const AdjArgs& aa, int n, cudaStream_t st) {
+size_t sparse_smem(const dps_operator* op, bool adjoint) {
   const SparseTables* t = op->sparse;
-  const size_t smem = sparse_smem(op);
-  static bool attr_set = false;
-  if (!attr_set) {
-    DPS_CUDA(cudaFuncSetAttribute(sparse_kernel<kAdjoint>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
-  const int strips = (op->H + kRows - 1) / kRows;
-  dim3 grid((unsigned)(op->C * strips), (unsigned)n);
-  sparse_kernel<kAdjoint><<<grid, kThreads, smem, st>>>(t->taps_dev, t->ntaps, t->Ry, t->Rx, op->C, op->H,
-                                                         op->W, strips, fa, aa);
-  DPS_LAUNCH_CHECK(kAdjoint ? "sparse_blur_adjoint" : "sparse_blur_forward");
-  return DPS_OK;
+  const int halo_x = adjoint ? 2 * t->Rx : t->Rx;
+  return sizeof(float) * ((size_t)(kRows + 2 * t->Ry) * (op->W + 2 * halo_x) + 64) + sizeof(TapOff) * (size_t)t->ntaps;
 }
+
 }  // namespace
 
 int sparse_create(dps_operator* op, const float* kernel, int ksize) {
@@ -210,21 +205,23 @@ int sparse_create(dps_operator* op, const float* kernel, int ksize) {
       Rx = abs(dx) > Rx ? abs(dx) : Rx;
     }
   DPS_REQUIRE(!taps.empty(), DPS_ERR_INVALID, "blur: kernel is all zero");
+  DPS_REQUIRE(Ry < op->H && Rx < op->W, DPS_ERR_UNSUPPORTED, "sparse blur: kernel radius (%d,%d) reaches the image size", Ry, Rx);
   Rx = (Rx + 3) / 4 * 4;
   if (Rx == 0) Rx = 4;
-  DPS_REQUIRE(Ry <= kRows - 1 && Rx <= 32, DPS_ERR_UNSUPPORTED, "sparse blur: radius (%d,%d) > 31", Ry, Rx);
-  DPS_REQUIRE(op->H % kRows == 0 && op->W % 4 == 0 && op->H > Ry && op->W > Rx, DPS_ERR_UNSUPPORTED,
-              "sparse blur: need H %% 32 == 0, W %% 4 == 0 and the kernel radius below the image size");
+  DPS_REQUIRE(op->W % 4 == 0, DPS_ERR_UNSUPPORTED, "sparse blur: W must be a multiple of 4");
   SparseTables* t = new SparseTables();
   t->ntaps = (int)taps.size();
   t->Ry = Ry;
   t->Rx = Rx;
   op->sparse = t;
-  DPS_REQUIRE(sparse_smem(op) <= 227 * 1024, DPS_ERR_UNSUPPORTED, "sparse blur: tile exceeds shared memory");
+  DPS_REQUIRE(sparse_smem(op, true) <= 227 * 1024, DPS_ERR_UNSUPPORTED, "sparse blur: tile exceeds shared memory");
   DPS_CUDA(cudaMalloc(&t->taps_dev, taps.size() * sizeof(Tap)));
   DPS_CUDA(cudaMemcpy(t->taps_dev, taps.data(), taps.size() * sizeof(Tap), cudaMemcpyHostToDevice));
+  DPS_CUDA(cudaFuncSetAttribute(sparse_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  DPS_CUDA(cudaFuncSetAttribute(sparse_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   op->P = op->C * ((op->H + kRows - 1) / kRows);
   op->taps = t->ntaps;
+  op->aux_floats = (int64_t)op->C * (op->H + 2 * Ry) * (op->W + 2 * Rx);  // padded t of the adjoint
   return DPS_OK;
 }
 
@@ -236,10 +233,31 @@ void sparse_destroy(dps_operator* op) {
 }
 
 int sparse_forward(const dps_operator* op, const FwdArgs& a, cudaStream_t st) {
+  const SparseTables* t = op->sparse;
   AdjArgs dummy = {};
-  return sparse_launch<false>(op, a, dummy, a.n, st);
+  const int strips = (op->H + kRows - 1) / kRows;
+  dim3 grid((unsigned)(op->C * strips), (unsigned)a.n);
+  sparse_kernel<false><<<grid, 256, sparse_smem(op, false), st>>>(t->taps_dev, t->ntaps, t->Ry, t->Rx, op->C, op->H,
+                                                                  op->W, strips, a, dummy, nullptr);
+  DPS_LAUNCH_CHECK("sparse_blur_forward");
+  return DPS_OK;
 }
+
 int sparse_adjoint(const dps_operator* op, const AdjArgs& a, cudaStream_t st) {
+  const SparseTables* t = op->sparse;
+  DPS_REQUIRE(a.aux, DPS_ERR_INVALID, "sparse blur adjoint needs the aux workspace (%lld floats per particle)",
+              (long long)op->aux_floats);
+  float* scratch = const_cast<float*>(a.aux);
   FwdArgs dummy = {};
-  return sparse_launch<true>(op, dummy, a, a.n, st);
+  const int OH = op->H + 2 * t->Ry, OW = op->W + 2 * t->Rx;
+  const int strips = (OH + kRows - 1) / kRows;
+  const int threads = OW >= 320 ? 320 : ((OW + 31) / 32) * 32;
+  dim3 grid((unsigned)(op->C * strips), (unsigned)a.n);
+  sparse_kernel<true><<<grid, threads, sparse_smem(op, true), st>>>(t->taps_dev, t->ntaps, t->Ry, t->Rx, op->C, op->H,
+                                                                    op->W, strips, dummy, a, scratch);
+  DPS_LAUNCH_CHECK("sparse_blur_adjoint_t");
+  dim3 fgrid((unsigned)((op->H * op->W + 255) / 256), (unsigned)op->C, (unsigned)a.n);
+  sparse_fold_kernel<<<fgrid, 256, 0, st>>>(scratch, t->Ry, t->Rx, op->C, op->H, op->W, a);
+  DPS_LAUNCH_CHECK("sparse_blur_adjoint_fold");
+  return DPS_OK;
 }

@@ -55,14 +55,14 @@ static inline bool dps_aligned16(const void* p) { return (reinterpret_cast<uintp
 // L1 (ld.global.nc.L1::no_allocate) and let L2/HBM stream.
 DPS_DEV float4 ldg_stream4(const float* p) {
   float4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+  asm("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
                : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
                : "l"(p));
   return r;
 }
 DPS_DEV float ldg_stream(const float* p) {
   float r;
-  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+  asm("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
   return r;
 }
 DPS_DEV void stg_stream4(float* p, const float4& v) {

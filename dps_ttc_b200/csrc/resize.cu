@@ -73,15 +73,30 @@ __global__ void __launch_bounds__(kThreads) resize_fwd_kernel(const ResizeTables
     float acc[kRO];
 #pragma unroll
     for (int j = 0; j < kRO; ++j) acc[j] = 0.f;
-#pragma unroll 4
-    for (int rr = 0; rr < rcnt; ++rr) {
-      const float v = src_load(x, eps, (int64_t)(rmin + rr) * W + col, a.src.c1, a.src.c2, a.src.clip);
-      const float4 w0 = *reinterpret_cast<const float4*>(dh + rr * kRO);
-      const float4 w1 = *reinterpret_cast<const float4*>(dh + rr * kRO + 4);
-      acc[0] = fmaf(w0.x, v, acc[0]); acc[1] = fmaf(w0.y, v, acc[1]);
-      acc[2] = fmaf(w0.z, v, acc[2]); acc[3] = fmaf(w0.w, v, acc[3]);
-      acc[4] = fmaf(w1.x, v, acc[4]); acc[5] = fmaf(w1.y, v, acc[5]);
-      acc[6] = fmaf(w1.z, v, acc[6]); acc[7] = fmaf(w1.w, v, acc[7]);
+    // rows in batches of kBatch: all loads of a batch are issued before the first use (2·kBatch requests in
+    // flight per thread), which is what hides the HBM latency in this otherwise serial walk down the column
+    constexpr int kBatch = 12;
+#pragma unroll 1
+    for (int rr0 = 0; rr0 < rcnt; rr0 += kBatch) {
+      float xv[kBatch], ev[kBatch];
+#pragma unroll
+      for (int b = 0; b < kBatch; ++b) {
+        const int rr = rr0 + b < rcnt ? rr0 + b : rcnt - 1;
+        xv[b] = ldg_stream(x + (int64_t)(rmin + rr) * W + col);
+        ev[b] = eps ? ldg_stream(eps + (int64_t)(rmin + rr) * W + col) : 0.f;
+      }
+#pragma unroll
+      for (int b = 0; b < kBatch; ++b) {
+        if (rr0 + b < rcnt) {
+          const float v = eps ? x0_of(xv[b], ev[b], a.src.c1, a.src.c2, a.src.clip) : xv[b];
+          const float4 w0 = *reinterpret_cast<const float4*>(dh + (rr0 + b) * kRO);
+          const float4 w1 = *reinterpret_cast<const float4*>(dh + (rr0 + b) * kRO + 4);
+          acc[0] = fmaf(w0.x, v, acc[0]); acc[1] = fmaf(w0.y, v, acc[1]);
+          acc[2] = fmaf(w0.z, v, acc[2]); acc[3] = fmaf(w0.w, v, acc[3]);
+          acc[4] = fmaf(w1.x, v, acc[4]); acc[5] = fmaf(w1.y, v, acc[5]);
+          acc[6] = fmaf(w1.z, v, acc[6]); acc[7] = fmaf(w1.w, v, acc[7]);
+        }
+      }
     }
 #pragma unroll
     for (int j = 0; j < kRO; ++j) V[j * W + col] = acc[j];
@@ -153,22 +168,40 @@ __global__ void __launch_bounds__(kThreads) resize_adj_kernel(const ResizeTables
       e[jj] = s;
     }
     // out[i][m] = Σ_jj A_h[jmin+jj][i]·E[jj]
-    for (int ii = 0; ii < kRA; ++ii) {
-      const int row = strip * kRA + ii;
-      if (row >= H) break;
-      const float4* dr = reinterpret_cast<const float4*>(dht + ii * kJMax);
-      float s = 0.f;
+    // rows in batches of 8: the clamp-mask sources (x, ε) and `extra` of a batch are loaded before any use
+    constexpr int kB = 8;
+    const bool masked = a.has_mask && a.mask_src.eps && a.mask_src.clip;
+    const float* mx = masked ? a.mask_src.x + n * a.mask_src.x_stride : nullptr;
+    const float* me = masked ? a.mask_src.eps + n * a.mask_src.eps_stride : nullptr;
+    const float* ex = a.extra ? a.extra + n * a.extra_stride : nullptr;
+#pragma unroll 1
+    for (int i0 = 0; i0 < kRA; i0 += kB) {
+      float xv[kB], ev[kB], xt[kB];
 #pragma unroll
-      for (int q = 0; q < kJMax / 4; ++q) {
-        const float4 w = dr[q];
-        s = fmaf(w.x, e[4 * q + 0], s); s = fmaf(w.y, e[4 * q + 1], s);
-        s = fmaf(w.z, e[4 * q + 2], s); s = fmaf(w.w, e[4 * q + 3], s);
+      for (int b = 0; b < kB; ++b) {
+        const int row = min(strip * kRA + i0 + b, H - 1);
+        const int64_t off = plane + (int64_t)row * W + m;
+        xv[b] = masked ? ldg_stream(mx + off) : 0.f;
+        ev[b] = masked ? ldg_stream(me + off) : 0.f;
+        xt[b] = ex ? ldg_stream(ex + off) : 0.f;
       }
-      const int64_t off = plane + (int64_t)row * W + m;
-      float res = coef * s;
-      if (a.extra) res += ldg_stream(a.extra + n * a.extra_stride + off);
-      res *= mask_load(a.mask_src, a.has_mask, n, off);
-      a.g[n * a.g_stride + off] = res;
+#pragma unroll
+      for (int b = 0; b < kB; ++b) {
+        const int row = strip * kRA + i0 + b;
+        if (row < H) {
+          const float4* dr = reinterpret_cast<const float4*>(dht + (i0 + b) * kJMax);
+          float s = 0.f;
+#pragma unroll
+          for (int q = 0; q < kJMax / 4; ++q) {
+            const float4 w = dr[q];
+            s = fmaf(w.x, e[4 * q + 0], s); s = fmaf(w.y, e[4 * q + 1], s);
+            s = fmaf(w.z, e[4 * q + 2], s); s = fmaf(w.w, e[4 * q + 3], s);
+          }
+          float res = coef * s + xt[b];
+          if (masked) res *= clamp_pass(x0_pre(xv[b], ev[b], a.mask_src.c1, a.mask_src.c2));
+          a.g[n * a.g_stride + plane + (int64_t)row * W + m] = res;
+        }
+      }
     }
   }
 }

@@ -217,6 +217,10 @@ class OperatorPlan:
         ep, es = (None, 0) if extra is None else particle_view(extra, "extra")
         if coef is not None:
             require_cuda_f32(coef, "coef")
+        if self.aux_floats and aux is None:
+            if self.kind == "phase":
+                raise DpsError("phase retrieval adjoint needs the aux tensor its forward pass returned (the phase)")
+            aux = self.new_aux(n)  # pure scratch (padded t of the sparse-blur adjoint)
         tok = TIMER.start(f"{self.kind}_adjoint") if TIMER else None
         check(lib().dps_operator_adjoint(self._h, r.data_ptr(), ptr(coef), msrc, ep, es, gp, gs, ptr(aux), n,
                                          stream_ptr(r.device)), f"dps_operator_adjoint[{self.kind}]")

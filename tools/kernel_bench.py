@@ -28,8 +28,11 @@ def peak_gbs():
     return float(json.load(open(p))["hbm_gbs"]) if os.path.exists(p) else 6650.0
 
 
-def time_it(fn, n_sets, iters, warm=3):
-    for i in range(warm):
+WARM = 3
+
+
+def time_it(fn, n_sets, iters, warm=None):
+    for i in range(WARM if warm is None else warm):
         fn(i % n_sets)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -47,7 +50,10 @@ def main():
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--sets", type=int, default=3, help="rotating buffer sets (each ≥ L2)")
     ap.add_argument("--only", default="")
+    ap.add_argument("--warm", type=int, default=3)
     a = ap.parse_args()
+    global WARM
+    WARM = a.warm
     dev = torch.device("cuda:0")
     n, S = a.n, a.sets
     only = set(filter(None, a.only.split(",")))
