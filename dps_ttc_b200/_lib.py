@@ -12,7 +12,7 @@ import threading
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdpsttc.so")
+LIB_PATH = os.environ.get("DPSTTC_LIB") or os.path.join(_HERE, "libdpsttc.so")  # env override: experiment builds
 CSRC_DIR = os.path.join(_HERE, "csrc")
 
 DPS_COEF_NORM = 1

@@ -346,6 +346,233 @@ size_t sep2_smem_bytes(int W) {
 }
 
 // =================================================================================================
+// streaming FFMA2 variant (R ≤ 16, W = 256, H % 32 == 0) — the one the 256×256 configs run
+//
+// The vertical pass no longer stages the input: a thread owns one column PAIR and walks its 32+2R rows straight
+// from global memory (64-bit loads, a warp reads 256 contiguous bytes per row and tensor), keeping the last
+// 2R+1 rows in registers.  Loads of the next 8 rows are in flight while the current 8 outputs are computed, so
+// HBM streams during the FFMA2 work instead of before it, and nothing is loaded twice inside a CTA.  Border rows
+// need no table: the mirrored taps are added from the same uniform registers, statically (≈R²/2 extra FFMA2
+// in the first and last strip only).
+// =================================================================================================
+constexpr int kT3 = 128;  // threads = column pairs of a 256-wide image
+#ifndef SEP3_LB
+#define SEP3_LB 8
+#endif
+#ifndef SEP3_MINB
+#define SEP3_MINB 4
+#endif
+constexpr int kLB = SEP3_LB;  // rows per load batch = outputs per compute batch
+
+DPS_DEV float2 ldg_stream2(const float2* p) {
+  float2 r;
+  asm("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+  return r;
+}
+// x̂₀ of a column pair, bit-identical to the scalar path (mul, mul, sub, clamp)
+DPS_DEV float2 x0_pair(float2 x, float2 e, float c1, float c2, int clip) {
+  const float2 a = __fmul2_rn(make_float2(c1, c1), x);
+  const float2 b = __fmul2_rn(make_float2(c2, c2), e);
+  float2 v = __fadd2_rn(a, make_float2(-b.x, -b.y));
+  if (clip) { v.x = clamp1(v.x); v.y = clamp1(v.y); }
+  return v;
+}
+// Mirrored-tap correction of output row `o` of a border strip (all indices compile-time after unrolling).
+// a / b = distance of the input / output row from the border, a = κ − R + b with κ the window position counted
+// from the border side; forward: a ≥ 1, b ≥ 0; adjoint: a ≥ 0, b ≥ 1; a + b ≤ R;
+// tap index in this direction's own array: R − (a+b) for top-forward / bottom-adjoint, R + (a+b) otherwise.
+template <int R, bool kAdjoint, bool kBottom, int O>
+DPS_DEV float2 border_fix(const float (&w)[2 * R + 1], const float2* win, float2 acc) {
+  constexpr int b = kBottom ? (kRows - 1 - O) : O;
+#pragma unroll
+  for (int k = 0; k <= 2 * R; ++k) {
+    const int kap = kBottom ? 2 * R - k : k;
+    const int a = kap - R + b;
+    const bool hit = (a >= (kAdjoint ? 0 : 1)) && (b >= (kAdjoint ? 1 : 0)) && (a + b <= R);
+    const int idx = (kBottom != kAdjoint) ? R + a + b : R - a - b;
+    if (hit) acc = __ffma2_rn(make_float2(w[idx], w[idx]), win[k], acc);
+  }
+  return acc;
+}
+
+template <int R, bool kAdjoint, int OB>
+struct BatchOut {  // the 8 outputs of compute batch OB (rows 8·OB … 8·OB+7), fully static
+  template <int J>
+  static DPS_DEV void run(const SepParams<R>& p, const float2* in, bool is_top, bool is_bot, float2* acc) {
+    constexpr int O = OB * kLB + J;
+    float2 a = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k <= 2 * R; ++k) a = __ffma2_rn(make_float2(p.wv[k], p.wv[k]), in[O + k], a);
+    if (O <= R && is_top) a = border_fix<R, kAdjoint, false, O>(p.wv, in + O, a);
+    if (kRows - 1 - O <= R && is_bot) a = border_fix<R, kAdjoint, true, O>(p.wv, in + O, a);
+    acc[J] = a;
+    if constexpr (J + 1 < kLB) run<J + 1>(p, in, is_top, is_bot, acc);
+  }
+};
+
+template <int R, bool kAdjoint>
+__global__ void __launch_bounds__(kT3, SEP3_MINB) sep3_kernel(const SepParams<R> p, const FwdArgs fa, const AdjArgs aa) {
+  constexpr int W = 256, W2 = W / 2, VW = W + 2 * R;
+  constexpr int NR = kRows + 2 * R;  // input rows walked by a thread
+  constexpr int NB = NR / kLB;       // load batches
+  constexpr int kLag = (kLB - 1 + 2 * R) / kLB;  // output batch ob reads in[kLB·ob … kLB·ob+kLB−1+2R]: input batches ≤ ob + kLag
+  static_assert(NB == kRows / kLB + kLag, "every output batch must be produced inside the load loop");
+  constexpr int kBorder = 2 * (R + 4) * (2 * R + 1);
+  static_assert(NR % kLB == 0 && R % 4 == 0 && (kLB == 4 || kLB == 8), "radius must be a multiple of 4");
+  extern __shared__ __align__(16) float smem[];
+  float2* V2 = reinterpret_cast<float2*>(smem);  // (kRows/2, VW) row-pair interleaved
+  float* bhs = reinterpret_cast<float*>(V2 + (kRows / 2) * VW);
+  float* red = bhs + kBorder;
+
+  const int H = p.H;
+  const int strip = blockIdx.x % p.strips;
+  const int c = blockIdx.x / p.strips;
+  const int n = blockIdx.y;
+  const int r0 = strip * kRows;
+  const int tid = threadIdx.x;
+  const int64_t plane = (int64_t)c * H * W;
+  const int64_t nchw = (int64_t)p.C * H * W;
+  const bool is_top = strip == 0, is_bot = strip == p.strips - 1;
+
+  for (int i = tid; i < kBorder; i += kT3) bhs[i] = p.bh[i];
+  for (int i = tid; i < (kRows / 2) * 2 * R; i += kT3) {
+    const int rp = i / (2 * R), q = i - rp * (2 * R);
+    V2[rp * VW + (q < R ? q : W + q)] = make_float2(0.f, 0.f);
+  }
+
+  // ---- phase 1: vertical pass straight from global memory -----------------------------------------
+  {
+    const float2* xs;
+    const float2* es = nullptr;
+    float c1 = 1.f, c2 = 0.f;
+    int clip = 0;
+    if (kAdjoint) {
+      xs = reinterpret_cast<const float2*>(aa.r + (int64_t)n * nchw + plane);
+    } else {
+      xs = reinterpret_cast<const float2*>(fa.src.x + n * fa.src.x_stride + plane);
+      if (fa.src.eps) es = reinterpret_cast<const float2*>(fa.src.eps + n * fa.src.eps_stride + plane);
+      c1 = fa.src.c1; c2 = fa.src.c2; clip = fa.src.clip;
+    }
+    const float2 zero2 = make_float2(0.f, 0.f);
+    float2 in[NR];
+    float2 rx[kLB], re[kLB];
+    auto issue = [&](int lb) {
+#pragma unroll
+      for (int j = 0; j < kLB; ++j) {
+        const int row = r0 - R + lb * kLB + j;
+        const bool inside = row >= 0 && row < H;
+        rx[j] = inside ? ldg_stream2(xs + row * W2 + tid) : zero2;
+        re[j] = (inside && es) ? ldg_stream2(es + row * W2 + tid) : zero2;
+      }
+    };
+    issue(0);
+#pragma unroll
+    for (int lb = 0; lb < NB; ++lb) {
+      float2 cx[kLB], ce[kLB];
+#pragma unroll
+      for (int j = 0; j < kLB; ++j) { cx[j] = rx[j]; ce[j] = re[j]; }
+      if (lb + 1 < NB) issue(lb + 1);  // next batch in flight while this one is consumed
+#pragma unroll
+      for (int j = 0; j < kLB; ++j) in[lb * kLB + j] = es ? x0_pair(cx[j], ce[j], c1, c2, clip) : cx[j];
+      if (lb >= kLag) {
+        float2 acc[kLB];
+        switch (lb - kLag) {  // lb is a compile-time constant after unrolling: one case survives
+          case 0: BatchOut<R, kAdjoint, 0>::template run<0>(p, in, is_top, is_bot, acc); break;
+          case 1: BatchOut<R, kAdjoint, 1>::template run<0>(p, in, is_top, is_bot, acc); break;
+          case 2: BatchOut<R, kAdjoint, 2>::template run<0>(p, in, is_top, is_bot, acc); break;
+          case 3: BatchOut<R, kAdjoint, 3>::template run<0>(p, in, is_top, is_bot, acc); break;
+#if SEP3_LB < 8
+          case 4: BatchOut<R, kAdjoint, 4>::template run<0>(p, in, is_top, is_bot, acc); break;
+          case 5: BatchOut<R, kAdjoint, 5>::template run<0>(p, in, is_top, is_bot, acc); break;
+          case 6: BatchOut<R, kAdjoint, 6>::template run<0>(p, in, is_top, is_bot, acc); break;
+          case 7: BatchOut<R, kAdjoint, 7>::template run<0>(p, in, is_top, is_bot, acc); break;
+#endif
+          default: break;
+        }
+        const int o0 = (lb - kLag) * kLB;
+#pragma unroll
+        for (int j = 0; j < kLB; j += 2)
+          *reinterpret_cast<float4*>(V2 + ((o0 + j) >> 1) * VW + R + 2 * tid) =
+              make_float4(acc[j].x, acc[j + 1].x, acc[j].y, acc[j + 1].y);
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 2: horizontal pass, a row pair × 4 columns per item (as sep2_kernel) -----------------
+  float sq = 0.f, ab = 0.f;
+  constexpr int q_lo = R / 4 + 1, q_hi = (W - 4 - R) / 4, nq_int = q_hi - q_lo;
+  {
+    constexpr int drp = kT3 / nq_int, dqi = kT3 - drp * nq_int;
+    int rp = tid / nq_int, qi = tid - rp * nq_int;
+    for (; rp < kRows / 2; rp += drp, qi += dqi) {
+      if (qi >= nq_int) { qi -= nq_int; if (++rp >= kRows / 2) break; }
+      const int col = (q_lo + qi) * 4;
+      const int row = r0 + 2 * rp;
+      const int64_t off = plane + (int64_t)row * W + col;
+      const RowIO ioA = row_prefetch<kAdjoint>(true, n, off, fa, aa);
+      const RowIO ioB = row_prefetch<kAdjoint>(true, n, off + W, fa, aa);
+      const float2* rowp = V2 + rp * VW + col;
+      float2 in2[4 + 2 * R];
+#pragma unroll
+      for (int s = 0; s < (4 + 2 * R) / 2; ++s) {
+        const float4 v = *reinterpret_cast<const float4*>(rowp + 2 * s);
+        in2[2 * s] = make_float2(v.x, v.y);
+        in2[2 * s + 1] = make_float2(v.z, v.w);
+      }
+      float2 o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float2 a = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k <= 2 * R; ++k) a = __ffma2_rn(make_float2(p.wh[k], p.wh[k]), in2[j + k], a);
+        o[j] = a;
+      }
+      row_finish<kAdjoint>(make_float4(o[0].x, o[1].x, o[2].x, o[3].x), ioA, true, n, off, nchw, fa, aa, sq, ab);
+      row_finish<kAdjoint>(make_float4(o[0].y, o[1].y, o[2].y, o[3].y), ioB, true, n, off + W, nchw, fa, aa, sq, ab);
+    }
+  }
+  constexpr int nq_b = q_lo + (W / 4 - q_hi);
+  for (int i = tid; i < (kRows / 2) * nq_b; i += kT3) {
+    const int rp = i / nq_b, bq = i - rp * nq_b;
+    const int q = bq < q_lo ? bq : q_hi + (bq - q_lo);
+    const int col = q * 4;
+    const int row = r0 + 2 * rp;
+    const int64_t off = plane + (int64_t)row * W + col;
+    const RowIO ioA = row_prefetch<kAdjoint>(true, n, off, fa, aa);
+    const RowIO ioB = row_prefetch<kAdjoint>(true, n, off + W, fa, aa);
+    const float2* rowp = V2 + rp * VW + col;
+    float2 o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float* bt = border_row<R>(bhs, col + j, W);
+      float2 a = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k <= 2 * R; ++k) {
+        const float w = bt[k];
+        a = __ffma2_rn(make_float2(w, w), rowp[j + k], a);
+      }
+      o[j] = a;
+    }
+    row_finish<kAdjoint>(make_float4(o[0].x, o[1].x, o[2].x, o[3].x), ioA, true, n, off, nchw, fa, aa, sq, ab);
+    row_finish<kAdjoint>(make_float4(o[0].y, o[1].y, o[2].y, o[3].y), ioB, true, n, off + W, nchw, fa, aa, sq, ab);
+  }
+  if (!kAdjoint && fa.partials) {
+    block_sum2(sq, ab, red);
+    if (tid == 0) {
+      float* pp = fa.partials + ((int64_t)n * (p.C * p.strips) + blockIdx.x) * 2;
+      pp[0] = sq;
+      pp[1] = ab;
+    }
+  }
+}
+
+template <int R>
+constexpr size_t sep3_smem_bytes() {
+  return sizeof(float) * ((size_t)(kRows / 2) * (256 + 2 * R) * 2 + (size_t)(2 * (R + 4)) * (2 * R + 1) + 64);
+}
+
+// =================================================================================================
 // scalar-FMA variant (R = 24, 32): same algorithm, one column / one row per thread item
 // =================================================================================================
 template <int R, bool kAdjoint>
@@ -472,7 +699,15 @@ int sep_launch(const dps_operator* op, const SepSet& set, const FwdArgs& fa, con
       DPS_CUDA(cudaFuncSetAttribute(sep2_kernel<R, 0, kAdjoint>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       attr_set = true;
     }
-    if (op->W == 256)
+    if (op->W == 256 && op->H % kRows == 0) {
+      static bool attr3_set = false;
+      if (!attr3_set) {
+        DPS_CUDA(cudaFuncSetAttribute(sep3_kernel<R, kAdjoint>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)sep3_smem_bytes<R>()));
+        attr3_set = true;
+      }
+      sep3_kernel<R, kAdjoint><<<grid, kT3, sep3_smem_bytes<R>(), st>>>(p, fa, aa);
+    } else if (op->W == 256)
       sep2_kernel<R, 256, kAdjoint><<<grid, kThreads, smem, st>>>(p, fa, aa);
     else
       sep2_kernel<R, 0, kAdjoint><<<grid, kThreads, smem, st>>>(p, fa, aa);

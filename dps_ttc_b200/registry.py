@@ -39,19 +39,28 @@ register_conditioning_method = CONDITIONING.register
 register_sampler = SAMPLERS.register
 
 
+def _populate():
+    """The classes register themselves on import; make the getters work whatever was imported first."""
+    from . import conditioning, operators, sampler  # noqa: F401
+
+
 def get_operator(name: str, **kwargs):
+    _populate()
     return OPERATORS.get(name)(**kwargs)
 
 
 def get_noise(name: str, **kwargs):
+    _populate()
     noiser = NOISES.get(name)(**kwargs)
     noiser.__name__ = name  # read by the conditioning methods (condition_methods.py:35, :50)
     return noiser
 
 
 def get_conditioning_method(name: str, operator, noiser, **kwargs):
+    _populate()
     return CONDITIONING.get(name)(operator=operator, noiser=noiser, **kwargs)
 
 
 def get_sampler(name: str):
+    _populate()
     return SAMPLERS.get(name)

@@ -142,9 +142,11 @@ def test_trace_ttc_ddim_mcg_resampling_indices_bit_exact():
 # live oracle at the BASELINE image size (256×256), a few steps of the 1000-step chain
 # ------------------------------------------------------------------------------------------------
 def _live(op_name, op_cfg, method, params, fwd, adj, mode, scale_of, sampler="ddpm", n=2, steps=3, nl_vjp=None,
-          cond_kw=None, seed=0, chain=True):
+          cond_kw=None, seed=0, chain=True, post_build=None):
     from dps_ttc_b200.sampler import NoiseTape
     s, op, cond, dev = build(sampler, "", method, params, op_name, op_cfg)
+    if post_build is not None:
+        post_build(op)
     rng = np.random.default_rng(seed)
     x_true = (rng.random((1, 3, 256, 256)) * 2 - 1).astype(np.float32)
     y = fwd(x_true)
@@ -213,17 +215,8 @@ def test_live_c3_motion_deblur_ddim():
     from dps_ttc_b200.tables import motion_kernel
     np.random.seed(8)
     kern = motion_kernel(61, 0.5).astype(np.float32)
-    from dps_ttc_b200 import tables
-    import dps_ttc_b200.operators as ops
-
-    class FixedKernel:
-        def __init__(self, size, intensity):
-            self.kernelMatrix = kern
-    old = tables.MotionKernel
-    tables.MotionKernel = FixedKernel
-    try:
-        _live("motion_blur", dict(kernel_size=61, intensity=0.5), "ps", dict(scale=0.3),
-              lambda x: O.blur_forward(x, kern), lambda u: O.blur_adjoint(u, kern), "norm", lambda t, i: 0.3,
-              sampler="ddim")
-    finally:
-        tables.MotionKernel = old
+    # the operator draws its own kernel at construction (like the reference); pin it to `kern` through the
+    # reference's set_kernel(), which stores the transpose of what it is given (measurements.py:119-126)
+    _live("motion_blur", dict(kernel_size=61, intensity=0.5), "ps", dict(scale=0.3),
+          lambda x: O.blur_forward(x, kern), lambda u: O.blur_adjoint(u, kern), "norm", lambda t, i: 0.3,
+          sampler="ddim", post_build=lambda op: op.set_kernel(kern.T))
