@@ -70,7 +70,7 @@ DPS_DEV void sep_epilogue(float4 o, int n, int64_t off, int64_t nchw, const FwdA
   if (!kAdjoint) {
     float4 res = o;
     if (fa.y) {
-      const float4 yv = *reinterpret_cast<const float4*>(fa.y + n * fa.y_stride + off);
+      const float4 yv = ldg_ro4(fa.y + n * fa.y_stride + off);
       res = make_float4(__fsub_rn(yv.x, o.x), __fsub_rn(yv.y, o.y), __fsub_rn(yv.z, o.z), __fsub_rn(yv.w, o.w));
     }
     stg_stream4(fa.out + n * nchw + off, res);
@@ -101,7 +101,7 @@ DPS_DEV RowIO row_prefetch(bool live, int n, int64_t off, const FwdArgs& fa, con
   io.a = io.mx = io.me = z;
   if (!live) return io;
   if (!kAdjoint) {
-    if (fa.y) io.a = *reinterpret_cast<const float4*>(fa.y + n * fa.y_stride + off);
+    if (fa.y) io.a = ldg_ro4(fa.y + n * fa.y_stride + off);
   } else {
     if (aa.extra) io.a = ldg_stream4(aa.extra + n * aa.extra_stride + off);
     if (aa.has_mask && aa.mask_src.eps && aa.mask_src.clip) {

@@ -137,12 +137,12 @@ __global__ void __launch_bounds__(320) sparse_kernel(const Tap* __restrict__ tap
         if (!kAdjoint) {
           const int64_t off = plane + (int64_t)row * W + col;
           float res = acc[j];
-          if (fa.y) res = __fsub_rn(fa.y[n * fa.y_stride + off], res);
-          fa.out[(int64_t)n * C * H * W + off] = res;
+          if (fa.y) res = __fsub_rn(ldg_ro(fa.y + n * fa.y_stride + off), res);
+          stg_stream(fa.out + (int64_t)n * C * H * W + off, res);
           sq += res * res;
           ab += fabsf(res);
         } else {
-          t_out[(((int64_t)n * C + c) * OH + row) * OW + col] = acc[j];
+          stg_stream(t_out + (((int64_t)n * C + c) * OH + row) * OW + col, acc[j]);
         }
       }
     }
@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(256) sparse_fold_kernel(const float* __restric
   float res = (aa.coef ? aa.coef[n] : 1.0f) * s;
   if (aa.extra) res += ldg_stream(aa.extra + n * aa.extra_stride + off);
   res *= mask_load(aa.mask_src, aa.has_mask, n, off);
-  aa.g[n * aa.g_stride + off] = res;
+  stg_stream(aa.g + n * aa.g_stride + off, res);
 }
 
 size_t sparse_smem(const dps_operator* op, bool adjoint) {

@@ -65,11 +65,19 @@ DPS_DEV float ldg_stream(const float* p) {
   asm("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
   return r;
 }
+// Stores: volatile (must not be dropped) but WITHOUT a "memory" clobber — no kernel here reads back what it
+// stores to global memory, and the clobber would pin every later load behind the store, serialising
+// "load → compute → store" loop iterations on the full HBM latency.
 DPS_DEV void stg_stream4(float* p, const float4& v) {
   asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x),
-               "f"(v.y), "f"(v.z), "f"(v.w)
-               : "memory");
+               "f"(v.y), "f"(v.z), "f"(v.w));
 }
+DPS_DEV void stg_stream(float* p, float v) {
+  asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(v));
+}
+// read-only data that is shared by many CTAs (the measurement y, operator tables): keep it in L1
+DPS_DEV float ldg_ro(const float* p) { return __ldg(p); }
+DPS_DEV float4 ldg_ro4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
 // x̂₀ = clamp(c1·x − c2·ε): separate mul, mul, sub — never contracted into an FMA, so the value is
 // bit-identical to the reference's three ATen kernels (posterior_mean_variance.py:120-123) and to

@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(kThreads) inpaint_fwd_kernel(const FwdArgs a, 
     float4 o = make_float4(__fmul_rn(x0.x, m.x), __fmul_rn(x0.y, m.y), __fmul_rn(x0.z, m.z),
                            __fmul_rn(x0.w, m.w));
     if (y) {
-      const float4 yv = *reinterpret_cast<const float4*>(y + i4 * 4);
+      const float4 yv = ldg_ro4(y + i4 * 4);
       o = make_float4(__fsub_rn(yv.x, o.x), __fsub_rn(yv.y, o.y), __fsub_rn(yv.z, o.z),
                       __fsub_rn(yv.w, o.w));
     }

@@ -26,12 +26,17 @@
 namespace {
 constexpr int kL = 384;
 constexpr int kHalf = kL / 2 + 1;  // 193
+constexpr int kLP = kL + kL / 8;     // padded length of a sequence in shared memory (432)
 constexpr int kImg = 256;
 constexpr int kPad = 64;
 constexpr int kThreads = 256;
-constexpr int kRowsPerCta = 32;  // K1 / A2: image rows per CTA → 16 packed FFTs
-constexpr int kColsPerCta = 16;  // K2 / A1: spectrum columns per CTA
-constexpr int kColGroups = (kHalf + kColsPerCta - 1) / kColsPerCta;  // 13
+constexpr int kRowsPerCta = 16;  // K1 / A2: image rows per CTA → 8 packed FFTs (56 KB of shared memory → 4 CTAs per SM)
+constexpr int kColsPerCta = 8;   // K2 / A1: spectrum columns per CTA
+constexpr int kColGroups = (kHalf + kColsPerCta - 1) / kColsPerCta;  // 25
+// the adjoint prefers wider CTAs: its scattered reads of r coalesce into 64-byte runs with 16 columns
+constexpr int kRowsAdj = 32;
+constexpr int kColsAdj = 16;
+constexpr int kColGroupsAdj = (kHalf + kColsAdj - 1) / kColsAdj;  // 13
 }  // namespace
 
 struct PhaseTables {
@@ -39,6 +44,10 @@ struct PhaseTables {
 };
 
 namespace {
+
+// Shared-memory sequences are padded by one element every 8: element i lives at i + (i >> 3).  With 8-byte
+// elements this makes the stride-8 / stride-64 scatter of the Stockham stages conflict-free (stride 9 / 72).
+DPS_DEV int P(int i) { return i + (i >> 3); }
 
 DPS_DEV float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 DPS_DEV float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
@@ -103,48 +112,47 @@ __device__ void fft384_batch(float2* a, float2* b, const float2* tw, int nfft) {
   // stage 1: R = 8, Ns = 1 (no twiddles): b[8j + r] = DFT8(a[j + 48r])
   for (int it = tid; it < nfft * 48; it += kThreads) {
     const int f = it / 48, j = it - f * 48;
-    const float2* src = a + f * kL;
-    float2* dst = b + f * kL;
+    const float2* src = a + f * kLP + P(j);   // P(j + 48r) = P(j) + 54r
+    float2* dst = b + f * kLP + 9 * j;         // P(8j + r)  = 9j + r
     float2 v[8];
 #pragma unroll
-    for (int r = 0; r < 8; ++r) v[r] = src[j + 48 * r];
+    for (int r = 0; r < 8; ++r) v[r] = src[54 * r];
     dft8(v);
 #pragma unroll
-    for (int r = 0; r < 8; ++r) dst[8 * j + r] = v[r];
+    for (int r = 0; r < 8; ++r) dst[r] = v[r];
   }
   __syncthreads();
   // stage 2: R = 8, Ns = 8: twiddle exp(−2πi·k·r/64) = tw[6·k·r]
   for (int it = tid; it < nfft * 48; it += kThreads) {
     const int f = it / 48, j = it - f * 48;
     const int k = j & 7;
-    const float2* src = b + f * kL;
-    float2* dst = a + f * kL;
+    const float2* src = b + f * kLP + P(j);
+    float2* dst = a + f * kLP + 72 * (j >> 3) + k;  // P(64·(j>>3) + k + 8r) = 72·(j>>3) + k + 9r
     float2 v[8];
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
-      v[r] = src[j + 48 * r];
+      v[r] = src[54 * r];
       if (r) v[r] = cmul(v[r], tw[6 * k * r]);
     }
     dft8(v);
-    const int j0 = (j >> 3) * 64 + k;
 #pragma unroll
-    for (int r = 0; r < 8; ++r) dst[j0 + 8 * r] = v[r];
+    for (int r = 0; r < 8; ++r) dst[9 * r] = v[r];
   }
   __syncthreads();
   // stage 3: R = 6, Ns = 64: twiddle exp(−2πi·k·r/384) = tw[k·r]
   for (int it = tid; it < nfft * 64; it += kThreads) {
     const int f = it >> 6, j = it & 63;
-    const float2* src = a + f * kL;
-    float2* dst = b + f * kL;
+    const float2* src = a + f * kLP + P(j);   // P(j + 64r) = P(j) + 72r
+    float2* dst = b + f * kLP + P(j);
     float2 v[6];
 #pragma unroll
     for (int r = 0; r < 6; ++r) {
-      v[r] = src[j + 64 * r];
+      v[r] = src[72 * r];
       if (r) v[r] = cmul(v[r], tw[j * r]);
     }
     dft6(v);
 #pragma unroll
-    for (int r = 0; r < 6; ++r) dst[j + 64 * r] = v[r];
+    for (int r = 0; r < 6; ++r) dst[72 * r] = v[r];
   }
   __syncthreads();
 }
@@ -158,12 +166,12 @@ struct PhaseSmem {
 DPS_DEV PhaseSmem carve(float* smem, int nfft) {
   PhaseSmem s;
   s.a = reinterpret_cast<float2*>(smem);
-  s.b = s.a + nfft * kL;
-  s.tw = s.b + nfft * kL;
+  s.b = s.a + nfft * kLP;
+  s.tw = s.b + nfft * kLP;
   s.red = reinterpret_cast<float*>(s.tw + kL);
   return s;
 }
-size_t smem_bytes(int nfft) { return sizeof(float2) * ((size_t)2 * nfft * kL + kL) + 64 * sizeof(float); }
+size_t smem_bytes(int nfft) { return sizeof(float2) * ((size_t)2 * nfft * kLP + kL) + 64 * sizeof(float); }
 
 // aux layout per particle (floats): [phase: C·193·384·2][scratch: C·193·256·2]
 DPS_DEV float2* aux_phase(float* aux, int n, int C, int c) {
@@ -187,7 +195,7 @@ __global__ void __launch_bounds__(kThreads) phase_rows_fwd(const FwdArgs fa, con
   // zero the padding columns [0,64) and [320,384) of every sequence
   for (int i = tid; i < nfft * 2 * kPad; i += kThreads) {
     const int f = i / (2 * kPad), q = i - f * (2 * kPad);
-    s.a[f * kL + (q < kPad ? q : kImg + q)] = make_float2(0.f, 0.f);
+    s.a[f * kLP + P(q < kPad ? q : kImg + q)] = make_float2(0.f, 0.f);
   }
   const int64_t plane = (int64_t)c * kImg * kImg;
   const float* x = fa.src.x + n * fa.src.x_stride + plane;
@@ -196,9 +204,10 @@ __global__ void __launch_bounds__(kThreads) phase_rows_fwd(const FwdArgs fa, con
     const int f = i / (kImg / 4), q = i - f * (kImg / 4);
     const float4 re = src_load4(x, eps, (int64_t)(r0 + 2 * f) * kImg + q * 4, fa.src.c1, fa.src.c2, fa.src.clip);
     const float4 im = src_load4(x, eps, (int64_t)(r0 + 2 * f + 1) * kImg + q * 4, fa.src.c1, fa.src.c2, fa.src.clip);
-    float2* d = s.a + f * kL + kPad + q * 4;
-    d[0] = make_float2(re.x, im.x); d[1] = make_float2(re.y, im.y);
-    d[2] = make_float2(re.z, im.z); d[3] = make_float2(re.w, im.w);
+    float2* d = s.a + f * kLP;
+    const int i0 = kPad + q * 4;
+    d[P(i0)] = make_float2(re.x, im.x); d[P(i0 + 1)] = make_float2(re.y, im.y);
+    d[P(i0 + 2)] = make_float2(re.z, im.z); d[P(i0 + 3)] = make_float2(re.w, im.w);
   }
   __syncthreads();
   fft384_batch(s.a, s.b, s.tw, nfft);
@@ -206,8 +215,8 @@ __global__ void __launch_bounds__(kThreads) phase_rows_fwd(const FwdArgs fa, con
   float2* rt = aux_scratch(fa.aux, n, C, c);
   for (int i = tid; i < kHalf * nfft; i += kThreads) {
     const int k = i / nfft, f = i - k * nfft;
-    const float2 z = s.b[f * kL + k];
-    const float2 zc = cconj(s.b[f * kL + (k ? kL - k : 0)]);
+    const float2 z = s.b[f * kLP + P(k)];
+    const float2 zc = cconj(s.b[f * kLP + P(k ? kL - k : 0)]);
     const float2 A = make_float2(0.5f * (z.x + zc.x), 0.5f * (z.y + zc.y));
     const float2 d = make_float2(0.5f * (z.x - zc.x), 0.5f * (z.y - zc.y));
     const float2 B = make_float2(d.y, -d.x);  // d / i
@@ -229,16 +238,16 @@ __global__ void __launch_bounds__(kThreads) phase_cols_fwd(const FwdArgs fa, con
   for (int i = tid; i < kL; i += kThreads) s.tw[i] = tw_g[i];
   for (int i = tid; i < nfft * 2 * kPad; i += kThreads) {
     const int f = i / (2 * kPad), q = i - f * (2 * kPad);
-    s.a[f * kL + (q < kPad ? q : kImg + q)] = make_float2(0.f, 0.f);
+    s.a[f * kLP + P(q < kPad ? q : kImg + q)] = make_float2(0.f, 0.f);
   }
   const float2* rt = aux_scratch(fa.aux, n, C, c);
   for (int i = tid; i < nfft * (kImg / 2); i += kThreads) {
     const int f = i / (kImg / 2), q = i - f * (kImg / 2);
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (f < ncols) v = *reinterpret_cast<const float4*>(rt + (int64_t)(k20 + f) * kImg + q * 2);
-    float2* d = s.a + f * kL + kPad + q * 2;
-    d[0] = make_float2(v.x, v.y);
-    d[1] = make_float2(v.z, v.w);
+    float2* d = s.a + f * kLP;
+    d[P(kPad + q * 2)] = make_float2(v.x, v.y);
+    d[P(kPad + q * 2 + 1)] = make_float2(v.z, v.w);
   }
   __syncthreads();
   fft384_batch(s.a, s.b, s.tw, nfft);
@@ -248,7 +257,7 @@ __global__ void __launch_bounds__(kThreads) phase_cols_fwd(const FwdArgs fa, con
   const float inv_l = 1.0f / (float)kL;
   for (int i = tid; i < ncols * kL; i += kThreads) {
     const int f = i / kL, k1 = i - f * kL;
-    const float2 F = s.b[f * kL + k1];
+    const float2 F = s.b[f * kLP + P(k1)];
     const float mag = sqrtf(F.x * F.x + F.y * F.y);
     const float inv = mag > 0.f ? 1.0f / mag : 0.f;
     ph[(int64_t)(k20 + f) * kL + k1] = make_float2(F.x * inv, -F.y * inv);
@@ -265,15 +274,15 @@ __global__ void __launch_bounds__(kThreads) phase_cols_fwd(const FwdArgs fa, con
     const float a = amp[f * kL + k1];
     {
       const int64_t o = (int64_t)shift_idx(k1) * kL + shift_idx(k2);
-      const float res = y ? __fsub_rn(y[o], a) : a;
-      if (fa.out) fa.out[oplane + o] = res;
+      const float res = y ? __fsub_rn(ldg_ro(y + o), a) : a;
+      if (fa.out) stg_stream(fa.out + oplane + o, res);
       sq += res * res;
       ab += fabsf(res);
     }
     if (k2 > 0 && k2 < kL / 2) {
       const int64_t o = (int64_t)shift_idx(k1 ? kL - k1 : 0) * kL + shift_idx(kL - k2);
-      const float res = y ? __fsub_rn(y[o], a) : a;
-      if (fa.out) fa.out[oplane + o] = res;
+      const float res = y ? __fsub_rn(ldg_ro(y + o), a) : a;
+      if (fa.out) stg_stream(fa.out + oplane + o, res);
       sq += res * res;
       ab += fabsf(res);
     }
@@ -292,12 +301,12 @@ __global__ void __launch_bounds__(kThreads) phase_cols_fwd(const FwdArgs fa, con
 __global__ void __launch_bounds__(kThreads) phase_cols_adj(const AdjArgs aa, float* __restrict__ aux_rw,
                                                            const float2* __restrict__ tw_g, int C) {
   extern __shared__ __align__(16) float smem[];
-  constexpr int nfft = kColsPerCta;
+  constexpr int nfft = kColsAdj;
   PhaseSmem s = carve(smem, nfft);
   const int tid = threadIdx.x;
-  const int grp = blockIdx.x % kColGroups, c = blockIdx.x / kColGroups, n = blockIdx.y;
-  const int k20 = grp * kColsPerCta;
-  const int ncols = min(kColsPerCta, kHalf - k20);
+  const int grp = blockIdx.x % kColGroupsAdj, c = blockIdx.x / kColGroupsAdj, n = blockIdx.y;
+  const int k20 = grp * kColsAdj;
+  const int ncols = min(kColsAdj, kHalf - k20);
   for (int i = tid; i < kL; i += kThreads) s.tw[i] = tw_g[i];
   const float* r = aa.r + ((int64_t)n * C + c) * kL * kL;
   const float2* ph = aux_phase(aux_rw, n, C, c);
@@ -319,7 +328,7 @@ __global__ void __launch_bounds__(kThreads) phase_cols_adj(const AdjArgs aa, flo
       const float g = gs[f * kL + k1];
       v = make_float2(g * p.x, g * p.y);
     }
-    s.a[f * kL + k1] = v;
+    s.a[f * kLP + P(k1)] = v;
   }
   __syncthreads();
   fft384_batch(s.a, s.b, s.tw, nfft);
@@ -327,7 +336,7 @@ __global__ void __launch_bounds__(kThreads) phase_cols_adj(const AdjArgs aa, flo
   float2* t = aux_scratch(aux_rw, n, C, c);
   for (int i = tid; i < kImg * ncols; i += kThreads) {
     const int row = i / ncols, f = i - row * ncols;
-    t[(int64_t)row * kHalf + k20 + f] = s.b[f * kL + kPad + row];
+    t[(int64_t)row * kHalf + k20 + f] = s.b[f * kLP + P(kPad + row)];
   }
 }
 
@@ -335,12 +344,12 @@ __global__ void __launch_bounds__(kThreads) phase_cols_adj(const AdjArgs aa, flo
 __global__ void __launch_bounds__(kThreads) phase_rows_adj(const AdjArgs aa, const float* __restrict__ aux_r,
                                                            const float2* __restrict__ tw_g, int C) {
   extern __shared__ __align__(16) float smem[];
-  constexpr int nfft = kRowsPerCta / 2;
+  constexpr int nfft = kRowsAdj / 2;
   PhaseSmem s = carve(smem, nfft);
   const int tid = threadIdx.x;
-  const int groups = kImg / kRowsPerCta;
+  const int groups = kImg / kRowsAdj;
   const int grp = blockIdx.x % groups, c = blockIdx.x / groups, n = blockIdx.y;
-  const int r0 = grp * kRowsPerCta;
+  const int r0 = grp * kRowsAdj;
   for (int i = tid; i < kL; i += kThreads) s.tw[i] = tw_g[i];
   const float2* t = aux_scratch(const_cast<float*>(aux_r), n, C, c);
   // X[k] = T1[k] + i·T2[k] with T[384−k] = conj(T[k]) for k > 192
@@ -350,21 +359,23 @@ __global__ void __launch_bounds__(kThreads) phase_rows_adj(const AdjArgs aa, con
     float2 t1 = t[(int64_t)(r0 + 2 * f) * kHalf + kk];
     float2 t2 = t[(int64_t)(r0 + 2 * f + 1) * kHalf + kk];
     if (k >= kHalf) { t1.y = -t1.y; t2.y = -t2.y; }
-    s.a[f * kL + k] = make_float2(t1.x - t2.y, t1.y + t2.x);
+    s.a[f * kLP + P(k)] = make_float2(t1.x - t2.y, t1.y + t2.x);
   }
   __syncthreads();
   fft384_batch(s.a, s.b, s.tw, nfft);
   const float coef = (aa.coef ? aa.coef[n] : 1.0f) * (1.0f / (float)kL);
   const int64_t plane = (int64_t)c * kImg * kImg;
-  for (int i = tid; i < kRowsPerCta * (kImg / 4); i += kThreads) {
+  for (int i = tid; i < kRowsAdj * (kImg / 4); i += kThreads) {
     const int rr = i / (kImg / 4), q = i - rr * (kImg / 4);
     const int f = rr >> 1, odd = rr & 1;
-    const float2* z = s.b + f * kL + kPad + q * 4;
+    const float2* zb = s.b + f * kLP;
+    const int i0 = kPad + q * 4;
+    const float2 z0 = zb[P(i0)], z1 = zb[P(i0 + 1)], z2 = zb[P(i0 + 2)], z3 = zb[P(i0 + 3)];
     float4 res;
-    res.x = coef * (odd ? z[0].y : z[0].x);
-    res.y = coef * (odd ? z[1].y : z[1].x);
-    res.z = coef * (odd ? z[2].y : z[2].x);
-    res.w = coef * (odd ? z[3].y : z[3].x);
+    res.x = coef * (odd ? z0.y : z0.x);
+    res.y = coef * (odd ? z1.y : z1.x);
+    res.z = coef * (odd ? z2.y : z2.x);
+    res.w = coef * (odd ? z3.y : z3.x);
     const int64_t off = plane + (int64_t)(r0 + rr) * kImg + q * 4;
     if (aa.extra) {
       const float4 e = ldg_stream4(aa.extra + n * aa.extra_stride + off);
@@ -398,8 +409,8 @@ int phase_create(dps_operator* op, int pad) {
   DPS_CUDA(cudaMemcpy(t->tw, tw.data(), sizeof(float2) * kL, cudaMemcpyHostToDevice));
   if (int rc = set_smem((const void*)phase_rows_fwd, smem_bytes(kRowsPerCta / 2))) return rc;
   if (int rc = set_smem((const void*)phase_cols_fwd, smem_bytes(kColsPerCta))) return rc;
-  if (int rc = set_smem((const void*)phase_cols_adj, smem_bytes(kColsPerCta))) return rc;
-  if (int rc = set_smem((const void*)phase_rows_adj, smem_bytes(kRowsPerCta / 2))) return rc;
+  if (int rc = set_smem((const void*)phase_cols_adj, smem_bytes(kColsAdj))) return rc;
+  if (int rc = set_smem((const void*)phase_rows_adj, smem_bytes(kRowsAdj / 2))) return rc;
   op->oC = op->C;
   op->oH = op->oW = kL;
   op->P = op->C * kColGroups;
@@ -430,11 +441,11 @@ int phase_forward(const dps_operator* op, const FwdArgs& a, cudaStream_t st) {
 int phase_adjoint(const dps_operator* op, const AdjArgs& a, cudaStream_t st) {
   DPS_REQUIRE(a.aux && a.r, DPS_ERR_INVALID, "phase retrieval adjoint needs r and the aux workspace of the forward pass");
   float* aux = const_cast<float*>(a.aux);
-  dim3 g1((unsigned)(op->C * kColGroups), (unsigned)a.n);
-  phase_cols_adj<<<g1, kThreads, smem_bytes(kColsPerCta), st>>>(a, aux, op->phase->tw, op->C);
+  dim3 g1((unsigned)(op->C * kColGroupsAdj), (unsigned)a.n);
+  phase_cols_adj<<<g1, kThreads, smem_bytes(kColsAdj), st>>>(a, aux, op->phase->tw, op->C);
   DPS_LAUNCH_CHECK("phase_cols_adj");
-  dim3 g2((unsigned)(op->C * (kImg / kRowsPerCta)), (unsigned)a.n);
-  phase_rows_adj<<<g2, kThreads, smem_bytes(kRowsPerCta / 2), st>>>(a, aux, op->phase->tw, op->C);
+  dim3 g2((unsigned)(op->C * (kImg / kRowsAdj)), (unsigned)a.n);
+  phase_rows_adj<<<g2, kThreads, smem_bytes(kRowsAdj / 2), st>>>(a, aux, op->phase->tw, op->C);
   DPS_LAUNCH_CHECK("phase_rows_adj");
   return DPS_OK;
 }

@@ -169,6 +169,32 @@ __global__ void __launch_bounds__(kCopyThreads) gather_kernel(const float* __res
   }
 }
 
+// dst[i] = particle `ancestors[i]` read straight from its owner's memory: rank = a / n_per_rank, slot = a % n_per_rank.
+// peer_bases[] are device pointers that are valid in THIS process for every rank's particle buffer (CUDA IPC /
+// symmetric memory over NVLink); loads to a peer go over NVSwitch, loads to the own rank stay in local HBM.
+__global__ void __launch_bounds__(kCopyThreads) gather_p2p_kernel(const float* const* __restrict__ peer_bases,
+                                                                  int n_per_rank,
+                                                                  const int64_t* __restrict__ ancestors,
+                                                                  float* __restrict__ dst, int64_t elems4) {
+  const int i = blockIdx.y;
+  const int64_t a = ancestors[i];
+  const int owner = (int)(a / n_per_rank);
+  const float4* s = reinterpret_cast<const float4*>(peer_bases[owner]) + (a - (int64_t)owner * n_per_rank) * elems4;
+  float* d = dst + (int64_t)i * elems4 * 4;
+  const int64_t base = (int64_t)blockIdx.x * (kCopyThreads * kCopyVec) + threadIdx.x;
+  float4 v[kCopyVec];
+#pragma unroll
+  for (int u = 0; u < kCopyVec; ++u) {
+    const int64_t j = base + (int64_t)u * kCopyThreads;
+    if (j < elems4) v[u] = s[j];  // plain ld.global: peer memory is not cached in the local L2
+  }
+#pragma unroll
+  for (int u = 0; u < kCopyVec; ++u) {
+    const int64_t j = base + (int64_t)u * kCopyThreads;
+    if (j < elems4) stg_stream4(d + j * 4, v[u]);
+  }
+}
+
 __global__ void __launch_bounds__(1024) argmin_kernel(const float* __restrict__ costs, int n, int64_t* __restrict__ best,
                                                       float* __restrict__ best_cost) {
   __shared__ float s_v[32];
@@ -290,6 +316,20 @@ int dps_ancestors_systematic(const float* cdf, int n, const double* u0, int n_dr
 int dps_gather_particles(const float* src, const int64_t* ancestors, float* dst, int n_dst, int64_t elems,
                          dps_stream_t stream) {
   return launch_gather(src, ancestors, 0, dst, n_dst, elems, stream, "dps_gather_particles");
+}
+
+int dps_gather_particles_p2p(const float* const* peer_bases_dev, int n_per_rank, const int64_t* ancestors, float* dst,
+                             int n_dst, int64_t elems, dps_stream_t stream) {
+  DPS_REQUIRE(peer_bases_dev && ancestors && dst && n_per_rank > 0 && n_dst > 0 && n_dst <= 65535 && elems > 0,
+              DPS_ERR_INVALID, "dps_gather_particles_p2p: bad arguments");
+  DPS_REQUIRE(elems % 4 == 0, DPS_ERR_UNSUPPORTED, "dps_gather_particles_p2p: elems must be a multiple of 4");
+  DPS_REQUIRE(dps_aligned16(dst), DPS_ERR_ALIGN, "dps_gather_particles_p2p: dst must be 16-byte aligned");
+  const int64_t e4 = elems / 4;
+  const int per = kCopyThreads * kCopyVec;
+  dim3 grid((unsigned)((e4 + per - 1) / per), (unsigned)n_dst);
+  gather_p2p_kernel<<<grid, kCopyThreads, 0, (cudaStream_t)stream>>>(peer_bases_dev, n_per_rank, ancestors, dst, e4);
+  DPS_LAUNCH_CHECK("dps_gather_particles_p2p");
+  return DPS_OK;
 }
 
 int dps_argmin(const float* costs, int n, int64_t* best, float* best_cost, dps_stream_t stream) {

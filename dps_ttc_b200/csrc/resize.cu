@@ -117,8 +117,8 @@ __global__ void __launch_bounds__(kThreads) resize_fwd_kernel(const ResizeTables
     for (int k = 0; k < t.kw; ++k) acc = fmaf(__ldg(ww + k), (cs + k < W) ? vr[k] : 0.f, acc);
     float res = acc;
     const int64_t o = (int64_t)orow * oW + jc;
-    if (a.y) res = __fsub_rn(a.y[n * a.y_stride + yplane + o], res);
-    a.out[oplane + o] = res;
+    if (a.y) res = __fsub_rn(ldg_ro(a.y + n * a.y_stride + yplane + o), res);
+    stg_stream(a.out + oplane + o, res);
     sq += res * res;
     ab += fabsf(res);
   }
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(kThreads) resize_adj_kernel(const ResizeTables
           }
           float res = coef * s + xt[b];
           if (masked) res *= clamp_pass(x0_pre(xv[b], ev[b], a.mask_src.c1, a.mask_src.c2));
-          a.g[n * a.g_stride + plane + (int64_t)row * W + m] = res;
+          stg_stream(a.g + n * a.g_stride + plane + (int64_t)row * W + m, res);
         }
       }
     }

@@ -303,6 +303,17 @@ def gather_particles(src, ancestors_idx, out=None):
     return out
 
 
+def gather_particles_p2p(peer_ptrs_dev: int, n_per_rank: int, ancestors_idx, like, out=None):
+    """out[i] = particle ancestors[i] read from its owner rank's symmetric buffer over NVLink.
+    peer_ptrs_dev: device address of the array of per-rank buffer pointers (symmetric memory `buffer_ptrs_dev`)."""
+    n_dst = ancestors_idx.numel()
+    elems = like[0].numel()
+    out = torch.empty((n_dst,) + tuple(like.shape[1:]), device=like.device, dtype=torch.float32) if out is None else out
+    check(lib().dps_gather_particles_p2p(peer_ptrs_dev, int(n_per_rank), ancestors_idx.data_ptr(), out.data_ptr(), n_dst,
+                                         elems, stream_ptr(like.device)), "dps_gather_particles_p2p")
+    return out
+
+
 def argmin(costs):
     costs = _lib.dense(costs, "costs")
     best = torch.empty(1, device=costs.device, dtype=torch.int64)

@@ -412,6 +412,7 @@ class TTC_DDIM(DDIM):
     scheme = "multinomial"
     lse_weights = False      # True: w = exp(logw − max) instead of the reference's exp(logw)
     sync_free = True         # False: host check of w.max() != w.min() like the reference (:693)
+    resample_seed = 0        # sharded runs: seed of the uniforms all ranks draw identically
 
     def p_sample_loop(self, model, x_start, measurement, measurement_cond_fn, record=False, save_root=None, **kwargs):
         img, y, method, bound, fused = self._prepare(x_start, measurement, measurement_cond_fn)
@@ -439,7 +440,12 @@ class TTC_DDIM(DDIM):
                 w, cdf, _, degenerate = kernels.weights_cdf(logw_all, linear_mode=not self.lse_weights)
                 if not self.sync_free and bool(degenerate.item()):
                     continue
-                u = self.noise.uniforms(idx, 1 if self.scheme == "systematic" else n_total, img.device)
+                n_u = 1 if self.scheme == "systematic" else n_total
+                if shards is None:
+                    u = self.noise.uniforms(idx, n_u, img.device)
+                else:  # every rank must see the same uniforms: a CPU generator keyed by (seed, step)
+                    from .dist import shared_uniforms
+                    u = shared_uniforms(self.resample_seed, idx, n_u, img.device)
                 ids = kernels.ancestors(cdf, u, n_total, systematic=(self.scheme == "systematic"), degenerate=degenerate)
                 self.last_stats["ancestors"][idx] = ids
                 if shards is None:

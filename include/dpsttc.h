@@ -205,6 +205,14 @@ int dps_ancestors_systematic(const float* cdf, int n, const double* u0, int n_dr
  * ancestors are indices into src (particle stride = elems).                                     */
 int dps_gather_particles(const float* src, const int64_t* ancestors, float* dst, int n_dst,
                          int64_t elems, dps_stream_t stream);
+/* Multi-GPU form (new: the reference is single-GPU): particle a = ancestors[i] lives on rank a / n_per_rank
+ * at slot a % n_per_rank of that rank's particle buffer; peer_bases_dev[r] is a device pointer, valid in
+ * THIS process, to rank r's buffer (CUDA IPC / symmetric memory).  The kernel reads the needed particles
+ * straight from their owners over NVLink/NVSwitch — the exchange and the gather are one kernel, and only
+ * n_dst·elems floats cross the fabric instead of the W·n_dst·elems of an all-gather.  The caller provides the
+ * cross-rank ordering (a barrier before: buffers written; after: buffers free to be overwritten).           */
+int dps_gather_particles_p2p(const float* const* peer_bases_dev, int n_per_rank, const int64_t* ancestors,
+                             float* dst, int n_dst, int64_t elems, dps_stream_t stream);
 /* Greedy search (SearchDDPM.p_sample_loop, :630-633): best = argmin costs (first minimum).      */
 int dps_argmin(const float* costs, int n, int64_t* best, float* best_cost, dps_stream_t stream);
 /* dst[i] = src[*index] for all i in [0, n_dst)  (img[best_path.repeat(n_paths)], :633)          */
