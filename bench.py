@@ -58,6 +58,8 @@ def parse():
     ap.add_argument("--model", default="auto", choices=["auto", "ffhq", "imagenet", "tiny"])
     ap.add_argument("--cpu-particles", type=int, default=1, help="particles per step of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--channels-last", action="store_true", help="run the UNet module in NHWC memory format")
+    ap.add_argument("--cudnn-benchmark", action="store_true", help="let cuDNN autotune its convolution algorithms")
     return ap.parse_args()
 
 
@@ -237,6 +239,12 @@ def run_b200(args, rank, world, local_rank):
     n, K, W = args.particles, args.steps, args.warmup
     op_name, op_cfg, method, params, m_bytes, desc = WORKLOADS[args.workload]
     model, model_name = load_model(args.model, device)
+    if args.channels_last:
+        model = model.to(memory_format=torch.channels_last)
+        model_name += " [channels_last]"
+    if args.cudnn_benchmark:
+        torch.backends.cudnn.benchmark = True
+        model_name += " [cudnn.benchmark]"
     op, cond, sampler, kw = build_b200(args.workload, device)
     import functools
     cond_fn = functools.partial(cond.conditioning, **kw) if kw else cond.conditioning

@@ -364,19 +364,6 @@ constexpr int kT3 = 128;  // threads = column pairs of a 256-wide image
 #endif
 constexpr int kLB = SEP3_LB;  // rows per load batch = outputs per compute batch
 
-DPS_DEV float2 ldg_stream2(const float2* p) {
-  float2 r;
-  asm("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
-  return r;
-}
-// x̂₀ of a column pair, bit-identical to the scalar path (mul, mul, sub, clamp)
-DPS_DEV float2 x0_pair(float2 x, float2 e, float c1, float c2, int clip) {
-  const float2 a = __fmul2_rn(make_float2(c1, c1), x);
-  const float2 b = __fmul2_rn(make_float2(c2, c2), e);
-  float2 v = __fadd2_rn(a, make_float2(-b.x, -b.y));
-  if (clip) { v.x = clamp1(v.x); v.y = clamp1(v.y); }
-  return v;
-}
 // Mirrored-tap correction of output row `o` of a border strip (all indices compile-time after unrolling).
 // a / b = distance of the input / output row from the border, a = κ − R + b with κ the window position counted
 // from the border side; forward: a ≥ 1, b ≥ 0; adjoint: a ≥ 0, b ≥ 1; a + b ≤ R;

@@ -76,6 +76,21 @@ DPS_DEV float4 mask_load4(const dps_source& s, int has_mask, int n, int64_t i) {
                      clamp_pass(x0_pre(xv.z, ev.z, s.c1, s.c2)), clamp_pass(x0_pre(xv.w, ev.w, s.c1, s.c2)));
 }
 
+// 64-bit streaming load of a column pair
+DPS_DEV float2 ldg_stream2(const float2* p) {
+  float2 r;
+  asm("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+  return r;
+}
+// x̂₀ of a column pair, bit-identical to the scalar path (mul, mul, sub, clamp)
+DPS_DEV float2 x0_pair(float2 x, float2 e, float c1, float c2, int clip) {
+  const float2 a = __fmul2_rn(make_float2(c1, c1), x);
+  const float2 b = __fmul2_rn(make_float2(c2, c2), e);
+  float2 v = __fadd2_rn(a, make_float2(-b.x, -b.y));
+  if (clip) { v.x = clamp1(v.x); v.y = clamp1(v.y); }
+  return v;
+}
+
 // per-operator launchers (each returns DPS_OK / error)
 int inpaint_forward(const dps_operator* op, const FwdArgs& a, cudaStream_t st);
 int inpaint_adjoint(const dps_operator* op, const AdjArgs& a, cudaStream_t st);

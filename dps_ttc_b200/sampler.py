@@ -150,6 +150,8 @@ class SpacedSampler:
     def _model_out(self, model, x, k):
         t = torch.full((1,), k.model_t, device=x.device, dtype=torch.float32)
         out = model(x, t)
+        if not out.is_contiguous():  # e.g. a channels_last module: the kernels read dense NCHW particle planes
+            out = out.contiguous()
         C = x.shape[1]
         if out.shape[1] == 2 * C:
             return out, out[:, :C], out[:, C:]
