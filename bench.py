@@ -330,8 +330,13 @@ def run_b200(args, rank, world, local_rank):
                       "gbs": round(b / (mean_ms * 1e-3) / 1e9, 1) if mean_ms > 0 else None}
     dom = max((k for k in ktab if alg_bytes.get(k, 0) > 0), key=lambda k: ktab[k]["mean_us"] * ktab[k]["launches"])
     achieved = ktab[dom]["gbs"]
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch from one `ncu --set full` capture of the same kernels at
+    # the same size (N=8, SR x4; profiles/r1_ncu_bench_kernels_n8.csv).  Reads equal the algorithmic input bytes; the
+    # outputs were still in L2 when the kernel ended (no write-back yet), hence traffic < algorithmic bytes.
+    ncu_traffic = {"resize_forward": 12673536 + 0, "resize_adjoint": 13036288 + 0, "posterior_update_ddpm": 37760512 + 5888}
+    traffic = ncu_traffic.get(dom) if (n == 8 and args.workload == "c2") else None
     roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                 "note": f"N={n} particles/launch: working set {alg_bytes[dom] / 1e6:.0f} MB is L2-sized and the kernel lasts "
                         f"{ktab[dom]['mean_us']} us, so launch latency weighs in; HBM-regime numbers (N>=128) are in profiles/",
                 "kernels": ktab}

@@ -304,6 +304,7 @@ class SpacedSampler:
     # -- base loop (GaussianDiffusion.p_sample_loop, :175-303) --------------------------------------
     def p_sample_loop(self, model, x_start, measurement, measurement_cond_fn, record=False, save_root=None, **kwargs):
         img, y, method, bound, fused = self._prepare(x_start, measurement, measurement_cond_fn)
+        fused = fused and kwargs.get("fused", True)   # fused=False forces the generic autograd path (debugging / tests)
         anneal_kw = {k_: kwargs[k_] for k_ in ("anneal_amp", "anneal_scale", "anneal_loc") if k_ in kwargs}
         callback = kwargs.get("callback")
         meas_d = sem_d = None
