@@ -226,7 +226,53 @@ def gen_masks():
     save("masks.npz", **out)
 
 
+def gen_var_types():
+    """DDPM.p_sample with the other variance processors (posterior_mean_variance.py:159-228)."""
+    out = {}
+    g = torch.Generator().manual_seed(31)
+    x = torch.randn(2, 3, 16, 16, generator=g)
+    out["x"] = x
+    model = TinyEps(seed=31)
+    for var_type in ("fixed_small", "fixed_large", "learned", "learned_range"):
+        with _ref.quiet():
+            s = create_sampler(sampler="ddpm", timestep_respacing="", **{**DIFF, "model_var_type": var_type})
+        for idx in (999, 500, 1, 0):
+            with Recorder() as rec, _ref.quiet(), torch.no_grad():
+                o = s.p_sample(model=model, x=x, t=torch.tensor([idx]))
+            out[f"{var_type}_{idx}_sample"] = o["sample"]
+            out[f"{var_type}_{idx}_x0"] = o["pred_xstart"]
+            out[f"{var_type}_{idx}_z"] = rec.randn[0]
+    save("var_types.npz", **out)
+
+
+def gen_resample_update():
+    """SearchDDPM.resample_update (gaussian_diffusion.py:516-587) for every potential type."""
+    out = {}
+    torch.manual_seed(41)
+    with _ref.quiet():
+        s = create_sampler(sampler="search_ddpm", timestep_respacing="", **DIFF)
+        op = get_operator("gaussian_blur", kernel_size=61, intensity=3.0, device="cpu")
+    cand = torch.randn(6, 3, 64, 64)
+    den = torch.rand(6, 3, 64, 64) * 2 - 1
+    y = op.forward(torch.rand(1, 3, 64, 64) * 2 - 1).detach()
+    prev = torch.rand(6) * 5 + 20
+    out.update(cand=cand, den=den, y=y, prev=prev)
+    for pt in ("min", "mean", "diff", "curr"):
+        with Recorder() as rec, _ref.quiet():
+            c2, net = s.resample_update(cand.clone(), den.clone(), op, y, resample=True, rs_temp=0.05,
+                                        prev_costs=prev.clone(), potential_type=pt, steps_done=3)
+        out[f"{pt}_cand"], out[f"{pt}_net"] = c2, net
+        if rec.multinomial:
+            out[f"{pt}_ids"], out[f"{pt}_u"] = rec.multinomial[0][1], rec.multinomial[0][2]
+    with _ref.quiet():
+        c2, net = s.resample_update(cand.clone(), den.clone(), op, y, prev_costs=None, potential_type="min")
+    out["first_net"] = net
+    save("resample_update.npz", **out)
+
+
 if __name__ == "__main__":
+    gen_var_types()
+    gen_resample_update()
     gen_schedule()
     gen_resizer()
     gen_operators()

@@ -1,0 +1,56 @@
+"""GPU parity for the remaining §8 rows: the other variance processors (A3 siblings), SearchDDPM.resample_update
+(A11) and best-of-N selection (E1), against fixtures recorded from the reference."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import CpuBridge, TinyEps, golden
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+DIFF = dict(steps=1000, noise_schedule="linear", model_mean_type="epsilon", dynamic_threshold=False,
+            clip_denoised=True, rescale_timesteps=True)
+
+
+@pytest.mark.parametrize("var_type", ["learned_range", "fixed_small", "fixed_large", "learned"])
+def test_variance_processors(var_type):
+    from dps_ttc_b200.sampler import NoiseTape, create_sampler
+    g = golden("var_types.npz")
+    s = create_sampler(sampler="ddpm", model_var_type=var_type, **DIFF)
+    model = CpuBridge(TinyEps(seed=31))
+    x = torch.from_numpy(g["x"]).to(DEV)
+    for idx in (999, 500, 1, 0):
+        s.noise = NoiseTape(z={idx: torch.from_numpy(g[f"{var_type}_{idx}_z"])})
+        with torch.no_grad():
+            out = s.p_sample(model=model, x=x, t=torch.tensor([idx]))
+        ref_s, ref_x0 = g[f"{var_type}_{idx}_sample"], g[f"{var_type}_{idx}_x0"]
+        assert np.abs(out["pred_xstart"].cpu().numpy() - ref_x0).max() == 0.0, (var_type, idx)
+        assert np.abs(out["sample"].cpu().numpy() - ref_s).max() <= 2e-6 * max(1.0, np.abs(ref_s).max()), (var_type, idx)
+
+
+@pytest.mark.parametrize("pt", ["min", "mean", "diff", "curr"])
+def test_resample_update(pt):
+    from dps_ttc_b200.registry import get_operator
+    from dps_ttc_b200.sampler import create_sampler
+    g = golden("resample_update.npz")
+    s = create_sampler(sampler="search_ddpm", model_var_type="learned_range", **DIFF)
+    op = get_operator("gaussian_blur", kernel_size=61, intensity=3.0, device=DEV)
+    T = lambda k: torch.from_numpy(g[k]).to(DEV)  # noqa: E731
+    u = torch.from_numpy(g[f"{pt}_u"]).to(DEV) if f"{pt}_u" in g.files else None
+    cand, net = s.resample_update(T("cand"), T("den"), op, T("y"), resample=True, rs_temp=0.05, prev_costs=T("prev"),
+                                  potential_type=pt, steps_done=3, uniforms=u)
+    assert np.array_equal(cand.cpu().numpy(), g[f"{pt}_cand"])                 # bit-exact ancestors → identical gather
+    assert np.abs(net.cpu().numpy() - g[f"{pt}_net"]).max() <= 1e-4 * np.abs(g[f"{pt}_net"]).max()   # fp32 L1² sum order
+    cand0, net0 = s.resample_update(T("cand"), T("den"), op, T("y"), prev_costs=None, potential_type="min")
+    assert np.abs(net0.cpu().numpy() - g["first_net"]).max() <= 1e-4 * g["first_net"].max()
+
+
+def test_best_of_n_selection():
+    from dps_ttc_b200.best_of_n import best_of_n_curves, best_paths, select_best
+    d = np.array([[3.0, 1.0, 2.0, 0.5], [1.0, 1.0, 0.2, 0.9]])
+    assert np.array_equal(best_paths(d), np.array([[0, 1, 1, 3], [0, 0, 2, 2]]))
+    curves = best_of_n_curves(d, psnr=np.arange(8.0).reshape(2, 4))
+    assert np.allclose(curves["distances"], [2.0, 1.0, 0.6, 0.35]) and np.allclose(curves["psnr"], [2.0, 2.5, 3.5, 4.5])
+    imgs = torch.randn(4, 3, 256, 256, device=DEV)
+    best, idx, cost = select_best(imgs, torch.tensor([3.0, 0.5, 2.0, 0.5], device=DEV))
+    assert int(idx.item()) == 1 and float(cost.item()) == 0.5 and torch.equal(best[0], imgs[1])
