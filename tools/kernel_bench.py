@@ -31,10 +31,27 @@ def peak_gbs():
 WARM = 3
 
 
+BRACKET = False
+
+
 def time_it(fn, n_sets, iters, warm=None):
     for i in range(WARM if warm is None else warm):
         fn(i % n_sets)
     torch.cuda.synchronize()
+    if BRACKET:
+        # per-launch event brackets with the GPU kept busy first, so that the CPU-side launch cost (tens of µs of
+        # Python/ctypes per call) never shows up between the two events: what bench.py measures at N = 8
+        torch.cuda._sleep(int(2e7))
+        pairs = []
+        for i in range(iters):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn(i % n_sets)
+            e1.record()
+            pairs.append((e0, e1))
+        torch.cuda.synchronize()
+        ts = sorted(a.elapsed_time(b) for a, b in pairs)
+        return ts[len(ts) // 2] * 1e3  # median µs
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(iters):
@@ -51,9 +68,10 @@ def main():
     ap.add_argument("--sets", type=int, default=3, help="rotating buffer sets (each ≥ L2)")
     ap.add_argument("--only", default="")
     ap.add_argument("--warm", type=int, default=3)
+    ap.add_argument("--bracket", action="store_true", help="median of per-launch CUDA-event brackets (small N)")
     a = ap.parse_args()
-    global WARM
-    WARM = a.warm
+    global WARM, BRACKET
+    WARM, BRACKET = a.warm, a.bracket
     dev = torch.device("cuda:0")
     n, S = a.n, a.sets
     only = set(filter(None, a.only.split(",")))
