@@ -125,6 +125,31 @@ DPS_DEV void block_sum2(float& a, float& b, float* red) {
   __syncthreads();
 }
 
+// ---- asynchronous table staging (global -> shared, no registers, every request in flight at once) ------------
+// A plain "for (i = tid; …) smem[i] = table[i]" loop serialises one L2 round trip per iteration (the compiler cannot
+// hoist a generic-pointer load above the previous shared store); with N ≈ 8 particles and ≈1 CTA per SM those round
+// trips ARE the kernel time.  cp.async issues them all, one wait at the end.
+DPS_DEV void cp_async16(float* dst_smem, const float* src) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(dst_smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(src) : "memory");
+}
+DPS_DEV void cp_async4(float* dst_smem, const float* src) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(dst_smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(src) : "memory");
+}
+DPS_DEV void stage_async(float* dst_smem, const float* src, int count, int tid, int nthreads) {
+  if (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst_smem)) & 15) == 0) {
+    const int n4 = count >> 2;
+    for (int i = tid; i < n4; i += nthreads) cp_async16(dst_smem + 4 * i, src + 4 * i);
+    for (int i = 4 * n4 + tid; i < count; i += nthreads) cp_async4(dst_smem + i, src + i);
+  } else {
+    for (int i = tid; i < count; i += nthreads) cp_async4(dst_smem + i, src + i);
+  }
+}
+DPS_DEV void stage_wait() {  // the caller still needs __syncthreads() before other threads' data is read
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
 DPS_DEV int reflect_idx(int i, int n) {  // ReflectionPad2d semantics (no edge repeat), |excursion| < n
   if (i < 0) i = -i;
   if (i >= n) i = 2 * (n - 1) - i;

@@ -17,6 +17,7 @@
 //           registers (one thread per input column), then out = A_hᵀ·E, fused with coef/extra/clamp mask.
 // Roofline: HBM-bound.  forward 2T + M, adjoint M + 3T per particle (T = particle, M = measurement).
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "operator.cuh"
@@ -26,50 +27,138 @@ constexpr int kThreads = 256;
 constexpr int kRO = 8;     // forward: output rows per CTA
 constexpr int kRA = 32;    // adjoint: input-space rows per CTA
 constexpr int kJMax = 16;  // adjoint: measurement rows a strip may touch
+constexpr int kRAs = 8;    // adjoint, small-grid variant: rows per CTA
+constexpr int kJs = 8;     //   and the measurement rows such a strip may touch
 constexpr int kKTMax = 12; // adjoint: measurement columns touching one input column
 }  // namespace
 
-struct ResizeTables {
-  // forward
+// Strip windows travel in the kernel parameters (constant bank): a CTA knows its window without a dependent
+// global load in front of its first data load.
+constexpr int kMaxStrips = 128;
+struct StripMeta {
+  short lo[kMaxStrips];
+  short cnt[kMaxStrips];
+};
+
+struct FwdTables {
   int fstrips = 0;        // ceil(out_h / kRO)
   int span = 0;           // max input-row window of a strip
-  int* f_rmin = nullptr;  // (fstrips)
-  int* f_rcnt = nullptr;  // (fstrips)
-  float* f_dh = nullptr;  // (fstrips, span, kRO): A_h[strip*kRO + j][rmin + rr]
   int kw = 0;             // max column window of an output column
-  int* f_cstart = nullptr;  // (out_w)
-  float* f_ww = nullptr;    // (out_w, kw): A_w[j][cstart[j] + k]
-  // adjoint
-  int astrips = 0;        // ceil(H / kRA)
-  int* a_jmin = nullptr;  // (astrips)
-  int* a_jcnt = nullptr;  // (astrips)
-  float* a_dht = nullptr; // (astrips, kRA, kJMax): A_h[jmin + jj][strip*kRA + i]
+  StripMeta rows;         // input-row window of every strip
+  float* dh = nullptr;    // (fstrips, span, kRO): A_h[strip*kRO + j][lo + rr]
+  int* cstart = nullptr;  // (out_w)
+  float* wwt = nullptr;   // (kw, out_w) tap-major: A_w[j][cstart[j] + k]
+};
+
+struct AdjStrips {
+  int strips = 0;         // ceil(H / RA); 0: variant not available
+  StripMeta rows;         // measurement-row window of every strip
+  float* dht = nullptr;   // (strips, RA, KJ): A_h[lo + jj][strip*RA + i]
+};
+
+struct AdjCols {
   int kt = 0;             // max measurement-column window of an input column
-  int* a_jstart = nullptr;  // (W)
-  float* a_wt = nullptr;    // (W, kt): A_w[jstart[m] + k][m]
+  int* jstart = nullptr;  // (W)
+  float* wtt = nullptr;   // (kt, W) tap-major: A_w[jstart[m] + k][m]
+};
+
+struct ResizeTables {
+  FwdTables f;
+  AdjStrips big;    // strips of kRA rows, ≤ kJMax measurement rows each
+  AdjStrips small;  // strips of kRAs rows, ≤ kJs measurement rows each
+  AdjCols cols;
 };
 
 namespace {
 
-__global__ void __launch_bounds__(kThreads) resize_fwd_kernel(const ResizeTables t, int C, int H, int W,
-                                                              int oH, int oW, const FwdArgs a) {
+// shared-memory carve-up of the forward kernels
+struct FwdSmem {
+  float* dh;   // (span, kRO)
+  float* V;    // (parts, kRO, W)
+  float* red;  // 64
+  float* wws;  // (kw, oW)
+  int* css;    // (oW)
+};
+DPS_DEV FwdSmem fwd_carve(float* smem, const FwdTables& t, int parts, int W, int oW) {
+  FwdSmem m;
+  m.dh = smem;
+  m.V = m.dh + t.span * kRO;
+  m.red = m.V + parts * kRO * W;
+  m.wws = m.red + 64;
+  m.css = reinterpret_cast<int*>(m.wws + ((t.kw * oW + 3) & ~3));
+  return m;
+}
+DPS_DEV void fwd_stage(const FwdSmem& m, const FwdTables& t, int strip, int rcnt, int oW, int tid, int nt) {
+  stage_async(m.dh, t.dh + (int64_t)strip * t.span * kRO, rcnt * kRO, tid, nt);
+  stage_async(m.wws, t.wwt, t.kw * oW, tid, nt);
+  stage_async(reinterpret_cast<float*>(m.css), reinterpret_cast<const float*>(t.cstart), oW, tid, nt);
+}
+
+// The measurement values a thread needs in the W pass are fetched early (before the H-pass barrier) so that their
+// DRAM latency is not a serial step at the end of the CTA: the first kYPre outputs of every thread.
+constexpr int kYPre = 2;
+struct YPre {
+  float v[kYPre];
+};
+DPS_DEV YPre fwd_y_prefetch(int oH, int oW, int strip, int c, int n, int tid, int nt, const FwdArgs& a) {
+  YPre y;
+  const float* yp = a.y ? a.y + n * a.y_stride + (int64_t)c * oH * oW : nullptr;
+#pragma unroll
+  for (int u = 0; u < kYPre; ++u) {
+    const int i = tid + u * nt;
+    const int orow = strip * kRO + i / oW;
+    y.v[u] = (yp && i < kRO * oW && orow < oH) ? ldg_ro(yp + (int64_t)strip * kRO * oW + i) : 0.f;
+  }
+  return y;
+}
+
+// W pass + residual + Σr², Σ|r| from the (kRO, W) tile V
+DPS_DEV void fwd_wpass(const FwdSmem& m, const FwdTables& t, int C, int W, int oH, int oW, int strip, int c, int n,
+                       int tid, int nt, const FwdArgs& a, const YPre& ypre) {
+  float sq = 0.f, ab = 0.f;
+  const int64_t oplane = ((int64_t)n * C + c) * oH * oW;
+  const float* yp = a.y ? a.y + n * a.y_stride + (int64_t)c * oH * oW : nullptr;
+  auto one = [&](int i, bool have, float yv) {
+    const int j = i / oW, jc = i - j * oW;
+    const int orow = strip * kRO + j;
+    if (orow >= oH) return;
+    const int64_t o = (int64_t)orow * oW + jc;
+    if (!have) yv = yp ? ldg_ro(yp + o) : 0.f;
+    const int cs = m.css[jc];
+    const float* vr = m.V + j * W + cs;
+    float s = 0.f;
+    for (int k = 0; k < t.kw; ++k) s = fmaf(m.wws[k * oW + jc], (cs + k < W) ? vr[k] : 0.f, s);
+    const float res = yp ? __fsub_rn(yv, s) : s;
+    stg_stream(a.out + oplane + o, res);
+    sq += res * res;
+    ab += fabsf(res);
+  };
+#pragma unroll
+  for (int u = 0; u < kYPre; ++u)
+    if (tid + u * nt < kRO * oW) one(tid + u * nt, true, ypre.v[u]);
+  for (int i = tid + kYPre * nt; i < kRO * oW; i += nt) one(i, false, 0.f);
+  if (a.partials) {
+    block_sum2(sq, ab, m.red);
+    if (tid == 0) {
+      float* pp = a.partials + ((int64_t)n * (C * t.fstrips) + blockIdx.x) * 2;
+      pp[0] = sq;
+      pp[1] = ab;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) resize_fwd_kernel(const FwdTables t, int C, int H, int W, int oH, int oW,
+                                                              const FwdArgs a) {
   extern __shared__ __align__(16) float smem[];
-  float* dh = smem;                  // (span, kRO)
-  float* V = dh + t.span * kRO;      // (kRO, W)
-  float* red = V + kRO * W;          // 64
-  float* wws = red + 64;             // (kw, oW): W-pass weights, tap-major so that a warp reads consecutive words
-  int* css = reinterpret_cast<int*>(wws + t.kw * oW);  // (oW)
+  const FwdSmem m = fwd_carve(smem, t, 1, W, oW);
   const int strip = blockIdx.x % t.fstrips;
   const int c = blockIdx.x / t.fstrips;
   const int n = blockIdx.y;
   const int tid = threadIdx.x;
-  const int rmin = t.f_rmin[strip], rcnt = t.f_rcnt[strip];
-  for (int i = tid; i < rcnt * kRO; i += kThreads) dh[i] = t.f_dh[(int64_t)strip * t.span * kRO + i];
-  for (int i = tid; i < t.kw * oW; i += kThreads) {  // coalesced read of (oW, kw), transposed store
-    const int jc = i / t.kw, k = i - jc * t.kw;
-    wws[k * oW + jc] = t.f_ww[i];
-  }
-  for (int i = tid; i < oW; i += kThreads) css[i] = t.f_cstart[i];
+  const int rmin = t.rows.lo[strip], rcnt = t.rows.cnt[strip];
+  fwd_stage(m, t, strip, rcnt, oW, tid, kThreads);
+  const YPre ypre = fwd_y_prefetch(oH, oW, strip, c, n, tid, kThreads, a);
+  stage_wait();
   __syncthreads();
 
   const int64_t plane = (int64_t)c * H * W;
@@ -96,8 +185,8 @@ __global__ void __launch_bounds__(kThreads) resize_fwd_kernel(const ResizeTables
       for (int b = 0; b < kBatch; ++b) {
         if (rr0 + b < rcnt) {
           const float v = eps ? x0_of(xv[b], ev[b], a.src.c1, a.src.c2, a.src.clip) : xv[b];
-          const float4 w0 = *reinterpret_cast<const float4*>(dh + (rr0 + b) * kRO);
-          const float4 w1 = *reinterpret_cast<const float4*>(dh + (rr0 + b) * kRO + 4);
+          const float4 w0 = *reinterpret_cast<const float4*>(m.dh + (rr0 + b) * kRO);
+          const float4 w1 = *reinterpret_cast<const float4*>(m.dh + (rr0 + b) * kRO + 4);
           acc[0] = fmaf(w0.x, v, acc[0]); acc[1] = fmaf(w0.y, v, acc[1]);
           acc[2] = fmaf(w0.z, v, acc[2]); acc[3] = fmaf(w0.w, v, acc[3]);
           acc[4] = fmaf(w1.x, v, acc[4]); acc[5] = fmaf(w1.y, v, acc[5]);
@@ -106,87 +195,64 @@ __global__ void __launch_bounds__(kThreads) resize_fwd_kernel(const ResizeTables
       }
     }
 #pragma unroll
-    for (int j = 0; j < kRO; ++j) V[j * W + col] = acc[j];
+    for (int j = 0; j < kRO; ++j) m.V[j * W + col] = acc[j];
   }
   __syncthreads();
-  // ---- W pass + epilogue -----------------------------------------------------------------------
-  float sq = 0.f, ab = 0.f;
-  const int64_t oplane = ((int64_t)n * C + c) * oH * oW;
-  const int64_t yplane = (int64_t)c * oH * oW;
-  for (int i = tid; i < kRO * oW; i += kThreads) {
-    const int j = i / oW, jc = i - j * oW;
-    const int orow = strip * kRO + j;
-    if (orow >= oH) continue;
-    const int cs = css[jc];
-    const float* vr = V + j * W + cs;
-    float acc = 0.f;
-    for (int k = 0; k < t.kw; ++k) acc = fmaf(wws[k * oW + jc], (cs + k < W) ? vr[k] : 0.f, acc);
-    float res = acc;
-    const int64_t o = (int64_t)orow * oW + jc;
-    if (a.y) res = __fsub_rn(ldg_ro(a.y + n * a.y_stride + yplane + o), res);
-    stg_stream(a.out + oplane + o, res);
-    sq += res * res;
-    ab += fabsf(res);
-  }
-  if (a.partials) {
-    block_sum2(sq, ab, red);
-    if (tid == 0) {
-      float* pp = a.partials + ((int64_t)n * (C * t.fstrips) + blockIdx.x) * 2;
-      pp[0] = sq;
-      pp[1] = ab;
-    }
-  }
+  fwd_wpass(m, t, C, W, oH, oW, strip, c, n, tid, kThreads, a, ypre);
 }
 
-// Pair variant for W = 256: 256 threads = 128 column pairs × 2 row halves.  64-bit loads, x̂₀ and the accumulation on
-// packed FFMA2 — half the load and FMA instructions of the scalar kernel at the same occupancy.  The two row-half
-// partial sums are combined through shared memory in a fixed order.
-__global__ void __launch_bounds__(kThreads) resize_fwd_pair_kernel(const ResizeTables t, int C, int H, int oH, int oW,
-                                                                   const FwdArgs a) {
-  constexpr int W = 256, W2 = 128, kBatch = 12;
+// Pair variant for W = 256: 128 column pairs × kParts row groups.  64-bit loads, x̂₀ and the accumulation on
+// packed FFMA2 — half the load and FMA instructions of the scalar kernel.  The row-group partial sums are combined
+// through shared memory in a fixed order.  kParts = 2 (256 threads, two load batches per thread, 3 CTAs per SM) was
+// the fastest split at every particle count measured (a 4-way split with one batch per thread lost 15-25 %).
+template <int kParts>
+__global__ void __launch_bounds__(128 * kParts, 3) resize_fwd_pair_kernel(const FwdTables t, int C, int H, int oH, int oW,
+                                                                       const FwdArgs a) {
+  constexpr int W = 256, W2 = 128, kBatch = 12, kT = 128 * kParts;
   extern __shared__ __align__(16) float smem[];
-  float* dh = smem;                    // (span, kRO)
-  float* V = dh + t.span * kRO;        // (kRO, W)   half 0 partial, then the sum
-  float* V1 = V + kRO * W;             // (kRO, W)   half 1 partial
-  float* red = V1 + kRO * W;           // 64
-  float* wws = red + 64;               // (kw, oW)
-  int* css = reinterpret_cast<int*>(wws + t.kw * oW);
+  const FwdSmem m = fwd_carve(smem, t, kParts, W, oW);
   const int strip = blockIdx.x % t.fstrips;
   const int c = blockIdx.x / t.fstrips;
   const int n = blockIdx.y;
   const int tid = threadIdx.x;
-  const int rmin = t.f_rmin[strip], rcnt = t.f_rcnt[strip];
-  for (int i = tid; i < rcnt * kRO; i += kThreads) dh[i] = t.f_dh[(int64_t)strip * t.span * kRO + i];
-  for (int i = tid; i < t.kw * oW; i += kThreads) {
-    const int jc = i / t.kw, k = i - jc * t.kw;
-    wws[k * oW + jc] = t.f_ww[i];
-  }
-  for (int i = tid; i < oW; i += kThreads) css[i] = t.f_cstart[i];
-  __syncthreads();
-  const int half = tid >> 7, cp = tid & 127;
-  const int hrows = (rcnt + 1) >> 1;             // rows per half
-  const int rr_lo = half * hrows, rr_hi = min(rcnt, rr_lo + hrows);
+  const int rmin = t.rows.lo[strip], rcnt = t.rows.cnt[strip];
+  const int part = tid >> 7, cp = tid & 127;
+  const int hrows = (rcnt + kParts - 1) / kParts;  // rows per group
+  const int rr_lo = part * hrows, rr_hi = min(rcnt, rr_lo + hrows);
   const int64_t plane = (int64_t)c * H * W;
   const float2* x2 = reinterpret_cast<const float2*>(a.src.x + n * a.src.x_stride + plane);
   const float2* e2 = a.src.eps ? reinterpret_cast<const float2*>(a.src.eps + n * a.src.eps_stride + plane) : nullptr;
+  // the first batch of loads goes out before the tables are staged
+  float2 xv[kBatch], ev[kBatch];
+#pragma unroll
+  for (int b = 0; b < kBatch; ++b) {
+    const int rr = max(0, min(rr_lo + b, rr_hi - 1));
+    xv[b] = ldg_stream2(x2 + (rmin + rr) * W2 + cp);
+    ev[b] = e2 ? ldg_stream2(e2 + (rmin + rr) * W2 + cp) : make_float2(0.f, 0.f);
+  }
+  fwd_stage(m, t, strip, rcnt, oW, tid, kT);
+  const YPre ypre = fwd_y_prefetch(oH, oW, strip, c, n, tid, kT, a);
+  stage_wait();
+  __syncthreads();
   float2 acc[kRO];
 #pragma unroll
   for (int j = 0; j < kRO; ++j) acc[j] = make_float2(0.f, 0.f);
 #pragma unroll 1
   for (int rr0 = rr_lo; rr0 < rr_hi; rr0 += kBatch) {
-    float2 xv[kBatch], ev[kBatch];
+    if (rr0 != rr_lo) {
 #pragma unroll
-    for (int b = 0; b < kBatch; ++b) {
-      const int rr = rr0 + b < rr_hi ? rr0 + b : rr_hi - 1;
-      xv[b] = ldg_stream2(x2 + (rmin + rr) * W2 + cp);
-      ev[b] = e2 ? ldg_stream2(e2 + (rmin + rr) * W2 + cp) : make_float2(0.f, 0.f);
+      for (int b = 0; b < kBatch; ++b) {
+        const int rr = rr0 + b < rr_hi ? rr0 + b : rr_hi - 1;
+        xv[b] = ldg_stream2(x2 + (rmin + rr) * W2 + cp);
+        ev[b] = e2 ? ldg_stream2(e2 + (rmin + rr) * W2 + cp) : make_float2(0.f, 0.f);
+      }
     }
 #pragma unroll
     for (int b = 0; b < kBatch; ++b) {
       if (rr0 + b < rr_hi) {
         const float2 v = e2 ? x0_pair(xv[b], ev[b], a.src.c1, a.src.c2, a.src.clip) : xv[b];
-        const float4 w0 = *reinterpret_cast<const float4*>(dh + (rr0 + b) * kRO);
-        const float4 w1 = *reinterpret_cast<const float4*>(dh + (rr0 + b) * kRO + 4);
+        const float4 w0 = *reinterpret_cast<const float4*>(m.dh + (rr0 + b) * kRO);
+        const float4 w1 = *reinterpret_cast<const float4*>(m.dh + (rr0 + b) * kRO + 4);
         acc[0] = __ffma2_rn(make_float2(w0.x, w0.x), v, acc[0]); acc[1] = __ffma2_rn(make_float2(w0.y, w0.y), v, acc[1]);
         acc[2] = __ffma2_rn(make_float2(w0.z, w0.z), v, acc[2]); acc[3] = __ffma2_rn(make_float2(w0.w, w0.w), v, acc[3]);
         acc[4] = __ffma2_rn(make_float2(w1.x, w1.x), v, acc[4]); acc[5] = __ffma2_rn(make_float2(w1.y, w1.y), v, acc[5]);
@@ -195,112 +261,97 @@ __global__ void __launch_bounds__(kThreads) resize_fwd_pair_kernel(const ResizeT
     }
   }
   {
-    float* dstp = half ? V1 : V;
+    float* dstp = m.V + part * kRO * W;
 #pragma unroll
     for (int j = 0; j < kRO; ++j) *reinterpret_cast<float2*>(dstp + j * W + 2 * cp) = acc[j];
   }
   __syncthreads();
-  for (int i = tid; i < kRO * W / 4; i += kThreads) {  // V += V1 (fixed order)
-    float4 s0 = *reinterpret_cast<const float4*>(V + i * 4);
-    const float4 s1 = *reinterpret_cast<const float4*>(V1 + i * 4);
-    s0.x += s1.x; s0.y += s1.y; s0.z += s1.z; s0.w += s1.w;
-    *reinterpret_cast<float4*>(V + i * 4) = s0;
+  for (int i = tid; i < kRO * W / 4; i += kT) {  // V[0] += V[1] (+ V[2] + V[3]), fixed order
+    float4 s0 = *reinterpret_cast<const float4*>(m.V + i * 4);
+#pragma unroll
+    for (int q = 1; q < kParts; ++q) {
+      const float4 s1 = *reinterpret_cast<const float4*>(m.V + q * kRO * W + i * 4);
+      s0.x += s1.x; s0.y += s1.y; s0.z += s1.z; s0.w += s1.w;
+    }
+    *reinterpret_cast<float4*>(m.V + i * 4) = s0;
   }
   __syncthreads();
-  float sq = 0.f, ab = 0.f;
-  const int64_t oplane = ((int64_t)n * C + c) * oH * oW;
-  const int64_t yplane = (int64_t)c * oH * oW;
-  for (int i = tid; i < kRO * oW; i += kThreads) {
-    const int j = i / oW, jc = i - j * oW;
-    const int orow = strip * kRO + j;
-    if (orow >= oH) continue;
-    const int64_t o = (int64_t)orow * oW + jc;
-    const float yv = a.y ? ldg_ro(a.y + n * a.y_stride + yplane + o) : 0.f;
-    const int cs = css[jc];
-    const float* vr = V + j * W + cs;
-    float s = 0.f;
-    for (int k = 0; k < t.kw; ++k) s = fmaf(wws[k * oW + jc], (cs + k < W) ? vr[k] : 0.f, s);
-    const float res = a.y ? __fsub_rn(yv, s) : s;
-    stg_stream(a.out + oplane + o, res);
-    sq += res * res;
-    ab += fabsf(res);
-  }
-  if (a.partials) {
-    block_sum2(sq, ab, red);
-    if (tid == 0) {
-      float* pp = a.partials + ((int64_t)n * (C * t.fstrips) + blockIdx.x) * 2;
-      pp[0] = sq;
-      pp[1] = ab;
-    }
-  }
+  fwd_wpass(m, t, C, W, oH, oW, strip, c, n, tid, kT, a, ypre);
 }
 
-__global__ void __launch_bounds__(kThreads) resize_adj_kernel(const ResizeTables t, int C, int H, int W,
+// Adjoint.  RA input rows per CTA, KJ = the most measurement rows such a strip may touch.  Only the measurement
+// rows the strip touches are staged.  The clamp-mask / extra loads of the first row batch are issued before the
+// tiles are staged, so a CTA's dependent chain is one round trip.
+template <int RA, int KJ, int KT>
+__global__ void __launch_bounds__(kThreads, RA == kRAs ? 4 : 3) resize_adj_kernel(const AdjStrips at, const AdjCols ac, int C, int H, int W,
                                                               int oH, int oW, const AdjArgs a) {
   extern __shared__ __align__(16) float smem[];
-  float* G = smem;               // (oH, oW) whole residual plane of this (n, c)
-  float* dht = G + ((oH * oW + 3) & ~3);  // (kRA, kJMax), 16-byte aligned
-  const int strip = blockIdx.x % t.astrips;
-  const int c = blockIdx.x / t.astrips;
+  float* G = smem;                          // (KJ, oW): the measurement rows this strip touches
+  float* dht = G + ((KJ * oW + 3) & ~3);    // (RA, KJ), 16-byte aligned
+  float* wts = dht + RA * KJ;               // (kt, W): column weights, tap-major
+  const int strip = blockIdx.x % at.strips;
+  const int c = blockIdx.x / at.strips;
   const int n = blockIdx.y;
   const int tid = threadIdx.x;
-  const int jmin = t.a_jmin[strip], jcnt = t.a_jcnt[strip];
-  const float* r = a.r + ((int64_t)n * C + c) * oH * oW;
-  for (int i = tid; i < oH * oW; i += kThreads) G[i] = ldg_stream(r + i);
-  for (int i = tid; i < kRA * kJMax; i += kThreads) dht[i] = t.a_dht[(int64_t)strip * kRA * kJMax + i];
-  float* wts = dht + kRA * kJMax;  // (kt, W): column weights, tap-major (coalesced global read, conflict-free use)
-  for (int i = tid; i < t.kt * W; i += kThreads) {
-    const int m = i / t.kt, k = i - m * t.kt;
-    wts[k * W + m] = t.a_wt[i];
-  }
+  const int jmin = at.rows.lo[strip], jcnt = at.rows.cnt[strip];
+  constexpr int kB = 8;
+  const bool masked = a.has_mask && a.mask_src.eps && a.mask_src.clip;
+  const int64_t plane = (int64_t)c * H * W;
+  const float* mx = masked ? a.mask_src.x + n * a.mask_src.x_stride + plane : nullptr;
+  const float* me = masked ? a.mask_src.eps + n * a.mask_src.eps_stride + plane : nullptr;
+  const float* ex = a.extra ? a.extra + n * a.extra_stride + plane : nullptr;
+  float xv[kB], ev[kB], xt[kB];
+  auto load_batch = [&](int m, int i0) {
+#pragma unroll
+    for (int b = 0; b < kB; ++b) {
+      const int row = min(strip * RA + i0 + b, H - 1);
+      const int64_t off = (int64_t)row * W + m;
+      xv[b] = masked ? ldg_stream(mx + off) : 0.f;
+      ev[b] = masked ? ldg_stream(me + off) : 0.f;
+      xt[b] = ex ? ldg_stream(ex + off) : 0.f;
+    }
+  };
+  if (tid < W) load_batch(tid, 0);  // in flight while the tiles are staged
+  stage_async(G, a.r + ((int64_t)n * C + c) * oH * oW + (int64_t)jmin * oW, jcnt * oW, tid, kThreads);
+  stage_async(dht, at.dht + (int64_t)strip * RA * KJ, RA * KJ, tid, kThreads);
+  stage_async(wts, ac.wtt, ac.kt * W, tid, kThreads);
+  const float coef = a.coef ? a.coef[n] : 1.0f;
+  int js_next = tid < W ? ac.jstart[tid] : 0;
+  stage_wait();
   __syncthreads();
 
-  const float coef = a.coef ? a.coef[n] : 1.0f;
-  const int64_t plane = (int64_t)c * H * W;
   for (int m = tid; m < W; m += kThreads) {
     // E[jj] = Σ_k A_w[jstart+k][m]·G[jmin+jj][jstart+k]
-    const int js = t.a_jstart[m];
-    float wt[kKTMax];
+    const int js = js_next;
+    if (m + kThreads < W) js_next = ac.jstart[m + kThreads];
+    float wt[KT];
 #pragma unroll
-    for (int k = 0; k < kKTMax; ++k) wt[k] = k < t.kt ? wts[k * W + m] : 0.f;
-    float e[kJMax];
+    for (int k = 0; k < KT; ++k) wt[k] = k < ac.kt ? wts[k * W + m] : 0.f;
+    float e[KJ];
 #pragma unroll
-    for (int jj = 0; jj < kJMax; ++jj) {
+    for (int jj = 0; jj < KJ; ++jj) {
       float s = 0.f;
       if (jj < jcnt) {
-        const float* gr = G + (jmin + jj) * oW + js;
+        const float* gr = G + jj * oW + js;
 #pragma unroll
-        for (int k = 0; k < kKTMax; ++k)
-          if (k < t.kt && js + k < oW) s = fmaf(wt[k], gr[k], s);
+        for (int k = 0; k < KT; ++k)
+          if (k < ac.kt && js + k < oW) s = fmaf(wt[k], gr[k], s);
       }
       e[jj] = s;
     }
-    // out[i][m] = Σ_jj A_h[jmin+jj][i]·E[jj]
-    // rows in batches of 8: the clamp-mask sources (x, ε) and `extra` of a batch are loaded before any use
-    constexpr int kB = 8;
-    const bool masked = a.has_mask && a.mask_src.eps && a.mask_src.clip;
-    const float* mx = masked ? a.mask_src.x + n * a.mask_src.x_stride : nullptr;
-    const float* me = masked ? a.mask_src.eps + n * a.mask_src.eps_stride : nullptr;
-    const float* ex = a.extra ? a.extra + n * a.extra_stride : nullptr;
+    // out[i][m] = Σ_jj A_h[jmin+jj][i]·E[jj]; rows in batches of 8, the clamp-mask sources (x, ε) and `extra` of a
+    // batch are loaded before any use
 #pragma unroll 1
-    for (int i0 = 0; i0 < kRA; i0 += kB) {
-      float xv[kB], ev[kB], xt[kB];
+    for (int i0 = 0; i0 < RA; i0 += kB) {
+      if (i0 != 0 || m != tid) load_batch(m, i0);
 #pragma unroll
       for (int b = 0; b < kB; ++b) {
-        const int row = min(strip * kRA + i0 + b, H - 1);
-        const int64_t off = plane + (int64_t)row * W + m;
-        xv[b] = masked ? ldg_stream(mx + off) : 0.f;
-        ev[b] = masked ? ldg_stream(me + off) : 0.f;
-        xt[b] = ex ? ldg_stream(ex + off) : 0.f;
-      }
-#pragma unroll
-      for (int b = 0; b < kB; ++b) {
-        const int row = strip * kRA + i0 + b;
+        const int row = strip * RA + i0 + b;
         if (row < H) {
-          const float4* dr = reinterpret_cast<const float4*>(dht + (i0 + b) * kJMax);
+          const float4* dr = reinterpret_cast<const float4*>(dht + (i0 + b) * KJ);
           float s = 0.f;
 #pragma unroll
-          for (int q = 0; q < kJMax / 4; ++q) {
+          for (int q = 0; q < KJ / 4; ++q) {
             const float4 w = dr[q];
             s = fmaf(w.x, e[4 * q + 0], s); s = fmaf(w.y, e[4 * q + 1], s);
             s = fmaf(w.z, e[4 * q + 2], s); s = fmaf(w.w, e[4 * q + 3], s);
@@ -335,11 +386,42 @@ std::vector<double> dense_from_tables(const int32_t* fov, const float* w, int ta
   return A;
 }
 
-size_t fwd_smem(const ResizeTables& t, int W, int oW) {
-  return sizeof(float) * ((size_t)t.span * kRO + (size_t)kRO * W + 64 + (size_t)t.kw * oW + oW);
+size_t fwd_smem(const FwdTables& t, int parts, int W, int oW) {
+  return sizeof(float) * ((size_t)t.span * kRO + (size_t)parts * kRO * W + 64 + (size_t)((t.kw * oW + 3) & ~3) + oW);
 }
-size_t adj_smem(int oH, int oW, int kt, int W) {
-  return sizeof(float) * ((size_t)((oH * oW + 3) & ~3) + (size_t)kRA * kJMax + (size_t)kt * W);
+size_t adj_smem(int ra, int kj, int oW, int kt, int W) {
+  return sizeof(float) * ((size_t)((kj * oW + 3) & ~3) + (size_t)ra * kj + (size_t)kt * W);
+}
+
+// strip tables of A_hᵀ for strips of `ra` input rows; DPS_ERR_UNSUPPORTED when a strip touches more than `kj` rows
+int build_adj_strips(const std::vector<double>& Ah, int H, int out_h, int ra, int kj, AdjStrips* out) {
+  const int strips = (H + ra - 1) / ra;
+  if (strips > kMaxStrips) return DPS_ERR_UNSUPPORTED;
+  std::vector<int> jmin(strips), jcnt(strips);
+  for (int s = 0; s < strips; ++s) {
+    int lo = out_h, hi = -1;
+    for (int i = s * ra; i < std::min(H, (s + 1) * ra); ++i)
+      for (int j = 0; j < out_h; ++j)
+        if (Ah[(size_t)j * H + i] != 0.0) { lo = std::min(lo, j); hi = std::max(hi, j); }
+    if (hi < lo) { lo = 0; hi = 0; }
+    jmin[s] = lo;
+    jcnt[s] = hi - lo + 1;
+    if (jcnt[s] > kj) return DPS_ERR_UNSUPPORTED;
+  }
+  std::vector<float> dht((size_t)strips * ra * kj, 0.f);
+  for (int s = 0; s < strips; ++s)
+    for (int ii = 0; ii < ra; ++ii)
+      for (int jj = 0; jj < jcnt[s]; ++jj) {
+        const int i = s * ra + ii;
+        if (i < H) dht[((size_t)s * ra + ii) * kj + jj] = (float)Ah[(size_t)(jmin[s] + jj) * H + i];
+      }
+  for (int s = 0; s < strips; ++s) {
+    out->rows.lo[s] = (short)jmin[s];
+    out->rows.cnt[s] = (short)jcnt[s];
+  }
+  if (int rc = upload(dht, &out->dht)) return rc;
+  out->strips = strips;
+  return DPS_OK;
 }
 
 }  // namespace
@@ -349,35 +431,37 @@ int resize_create(dps_operator* op, const int32_t* fov_h, const float* w_h, int 
   const int H = op->H, W = op->W;
   DPS_REQUIRE(out_h > 0 && out_w > 0 && out_h <= H && out_w <= W, DPS_ERR_UNSUPPORTED,
               "resize: only down-scaling is supported (%dx%d -> %dx%d)", H, W, out_h, out_w);
+  DPS_REQUIRE(H < 32768 && (out_h + kRO - 1) / kRO <= kMaxStrips, DPS_ERR_UNSUPPORTED,
+              "resize: at most %d measurement rows are supported (got %d)", kMaxStrips * kRO, out_h);
   bool ok_h, ok_w;
   std::vector<double> Ah = dense_from_tables(fov_h, w_h, taps_h, out_h, H, &ok_h);
   std::vector<double> Aw = dense_from_tables(fov_w, w_w, taps_w, out_w, W, &ok_w);
   DPS_REQUIRE(ok_h && ok_w, DPS_ERR_INVALID, "resize: field-of-view index out of range");
   ResizeTables* t = new ResizeTables();
   op->resize = t;
+  FwdTables& f = t->f;
   // ---- forward H-pass blocks ----
-  t->fstrips = (out_h + kRO - 1) / kRO;
-  std::vector<int> rmin(t->fstrips), rcnt(t->fstrips);
+  f.fstrips = (out_h + kRO - 1) / kRO;
   int span = 1;
-  for (int s = 0; s < t->fstrips; ++s) {
+  for (int s = 0; s < f.fstrips; ++s) {
     int lo = H, hi = -1;
     for (int j = s * kRO; j < std::min(out_h, (s + 1) * kRO); ++j)
       for (int m = 0; m < H; ++m)
         if (Ah[(size_t)j * H + m] != 0.0) { lo = std::min(lo, m); hi = std::max(hi, m); }
     if (hi < lo) { lo = 0; hi = 0; }
-    rmin[s] = lo;
-    rcnt[s] = hi - lo + 1;
-    span = std::max(span, rcnt[s]);
+    f.rows.lo[s] = (short)lo;
+    f.rows.cnt[s] = (short)(hi - lo + 1);
+    span = std::max(span, hi - lo + 1);
   }
-  t->span = span;
-  std::vector<float> dh((size_t)t->fstrips * span * kRO, 0.f);
-  for (int s = 0; s < t->fstrips; ++s)
-    for (int rr = 0; rr < rcnt[s]; ++rr)
+  f.span = span;
+  std::vector<float> dh((size_t)f.fstrips * span * kRO, 0.f);
+  for (int s = 0; s < f.fstrips; ++s)
+    for (int rr = 0; rr < f.rows.cnt[s]; ++rr)
       for (int j = 0; j < kRO; ++j) {
         const int jo = s * kRO + j;
-        if (jo < out_h) dh[((size_t)s * span + rr) * kRO + j] = (float)Ah[(size_t)jo * H + rmin[s] + rr];
+        if (jo < out_h) dh[((size_t)s * span + rr) * kRO + j] = (float)Ah[(size_t)jo * H + f.rows.lo[s] + rr];
       }
-  // ---- forward W-pass windows ----
+  // ---- forward W-pass windows (tap-major so that a warp reads consecutive words) ----
   std::vector<int> cstart(out_w);
   int kw = 1;
   for (int j = 0; j < out_w; ++j) {
@@ -388,33 +472,16 @@ int resize_create(dps_operator* op, const int32_t* fov_h, const float* w_h, int 
     cstart[j] = lo;
     kw = std::max(kw, hi - lo + 1);
   }
-  t->kw = kw;
-  std::vector<float> ww((size_t)out_w * kw, 0.f);
+  f.kw = kw;
+  std::vector<float> wwt((size_t)kw * out_w, 0.f);
   for (int j = 0; j < out_w; ++j)
     for (int k = 0; k < kw; ++k)
-      if (cstart[j] + k < W) ww[(size_t)j * kw + k] = (float)Aw[(size_t)j * W + cstart[j] + k];
-  // ---- adjoint: A_hᵀ blocks per input-row strip ----
-  t->astrips = (H + kRA - 1) / kRA;
-  std::vector<int> jmin(t->astrips), jcnt(t->astrips);
-  for (int s = 0; s < t->astrips; ++s) {
-    int lo = out_h, hi = -1;
-    for (int i = s * kRA; i < std::min(H, (s + 1) * kRA); ++i)
-      for (int j = 0; j < out_h; ++j)
-        if (Ah[(size_t)j * H + i] != 0.0) { lo = std::min(lo, j); hi = std::max(hi, j); }
-    if (hi < lo) { lo = 0; hi = 0; }
-    jmin[s] = lo;
-    jcnt[s] = hi - lo + 1;
-    DPS_REQUIRE(jcnt[s] <= kJMax, DPS_ERR_UNSUPPORTED, "resize: a %d-row strip touches %d measurement rows (> %d)",
-                kRA, jcnt[s], kJMax);
-  }
-  std::vector<float> dht((size_t)t->astrips * kRA * kJMax, 0.f);
-  for (int s = 0; s < t->astrips; ++s)
-    for (int ii = 0; ii < kRA; ++ii)
-      for (int jj = 0; jj < jcnt[s]; ++jj) {
-        const int i = s * kRA + ii;
-        if (i < H) dht[((size_t)s * kRA + ii) * kJMax + jj] = (float)Ah[(size_t)(jmin[s] + jj) * H + i];
-      }
-  // ---- adjoint: A_w column windows ----
+      if (cstart[j] + k < W) wwt[(size_t)k * out_w + j] = (float)Aw[(size_t)j * W + cstart[j] + k];
+  // ---- adjoint: A_hᵀ blocks per input-row strip, two strip heights ----
+  DPS_REQUIRE(build_adj_strips(Ah, H, out_h, kRA, kJMax, &t->big) == DPS_OK, DPS_ERR_UNSUPPORTED,
+              "resize: a %d-row strip touches more than %d measurement rows", kRA, kJMax);
+  if (build_adj_strips(Ah, H, out_h, kRAs, kJs, &t->small) != DPS_OK) t->small.strips = 0;  // optional variant
+  // ---- adjoint: A_w column windows (tap-major) ----
   std::vector<int> jstart(W);
   int kt = 1;
   for (int m = 0; m < W; ++m) {
@@ -427,28 +494,23 @@ int resize_create(dps_operator* op, const int32_t* fov_h, const float* w_h, int 
   }
   DPS_REQUIRE(kt <= kKTMax, DPS_ERR_UNSUPPORTED, "resize: an input column feeds %d measurement columns (> %d)", kt,
               kKTMax);
-  t->kt = kt;
-  std::vector<float> wt((size_t)W * kt, 0.f);
+  t->cols.kt = kt;
+  std::vector<float> wtt((size_t)kt * W, 0.f);
   for (int m = 0; m < W; ++m)
     for (int k = 0; k < kt; ++k)
-      if (jstart[m] + k < out_w) wt[(size_t)m * kt + k] = (float)Aw[(size_t)(jstart[m] + k) * W + m];
+      if (jstart[m] + k < out_w) wtt[(size_t)k * W + m] = (float)Aw[(size_t)(jstart[m] + k) * W + m];
 
-  DPS_REQUIRE(fwd_smem(*t, W, out_w) <= 227 * 1024 && adj_smem(out_h, out_w, kt, W) <= 227 * 1024, DPS_ERR_UNSUPPORTED,
-              "resize: tiles exceed shared memory");
-  if (int rc = upload(rmin, &t->f_rmin)) return rc;
-  if (int rc = upload(rcnt, &t->f_rcnt)) return rc;
-  if (int rc = upload(dh, &t->f_dh)) return rc;
-  if (int rc = upload(cstart, &t->f_cstart)) return rc;
-  if (int rc = upload(ww, &t->f_ww)) return rc;
-  if (int rc = upload(jmin, &t->a_jmin)) return rc;
-  if (int rc = upload(jcnt, &t->a_jcnt)) return rc;
-  if (int rc = upload(dht, &t->a_dht)) return rc;
-  if (int rc = upload(jstart, &t->a_jstart)) return rc;
-  if (int rc = upload(wt, &t->a_wt)) return rc;
+  DPS_REQUIRE(fwd_smem(f, 2, W, out_w) <= 227 * 1024 && adj_smem(kRA, kJMax, out_w, kt, W) <= 227 * 1024,
+              DPS_ERR_UNSUPPORTED, "resize: tiles exceed shared memory");
+  if (int rc = upload(dh, &f.dh)) return rc;
+  if (int rc = upload(cstart, &f.cstart)) return rc;
+  if (int rc = upload(wwt, &f.wwt)) return rc;
+  if (int rc = upload(jstart, &t->cols.jstart)) return rc;
+  if (int rc = upload(wtt, &t->cols.wtt)) return rc;
   op->oC = op->C;
   op->oH = out_h;
   op->oW = out_w;
-  op->P = op->C * t->fstrips;
+  op->P = op->C * f.fstrips;
   op->taps = taps_h;
   return DPS_OK;
 }
@@ -456,42 +518,65 @@ int resize_create(dps_operator* op, const int32_t* fov_h, const float* w_h, int 
 void resize_destroy(dps_operator* op) {
   ResizeTables* t = op->resize;
   if (!t) return;
-  cudaFree(t->f_rmin); cudaFree(t->f_rcnt); cudaFree(t->f_dh); cudaFree(t->f_cstart); cudaFree(t->f_ww);
-  cudaFree(t->a_jmin); cudaFree(t->a_jcnt); cudaFree(t->a_dht); cudaFree(t->a_jstart); cudaFree(t->a_wt);
+  cudaFree(t->f.dh); cudaFree(t->f.cstart); cudaFree(t->f.wwt);
+  cudaFree(t->big.dht); cudaFree(t->small.dht);
+  cudaFree(t->cols.jstart); cudaFree(t->cols.wtt);
   delete t;
   op->resize = nullptr;
 }
 
+// The short-strip adjoint wins only while its own grid is about one wave (measured: 10.3 vs 12.2 µs at N = 8, but
+// 17.6 vs 15.8 µs at N = 16 and 120 vs 96 µs at N = 128 for 256² → 64²).
+static int variant_override() {  // DPSTTC_RESIZE_VARIANT=big|small pins the choice (profiling aid)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DPSTTC_RESIZE_VARIANT");
+    v = !e ? 0 : (e[0] == 'b' ? 1 : (e[0] == 's' ? 2 : 0));
+  }
+  return v;
+}
+static bool small_grid(int64_t ctas) {
+  const int v = variant_override();
+  return v ? v == 2 : ctas <= 148 * 2;
+}
+
 int resize_forward(const dps_operator* op, const FwdArgs& a, cudaStream_t st) {
-  const ResizeTables& t = *op->resize;
-  const size_t smem = fwd_smem(t, op->W, op->oW);
+  const FwdTables& f = op->resize->f;
   static bool attr_set = false;
   if (!attr_set) {
     DPS_CUDA(cudaFuncSetAttribute(resize_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    DPS_CUDA(cudaFuncSetAttribute(resize_fwd_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DPS_CUDA(cudaFuncSetAttribute(resize_fwd_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  dim3 grid((unsigned)(op->C * t.fstrips), (unsigned)a.n);
+  dim3 grid((unsigned)(op->C * f.fstrips), (unsigned)a.n);
   if (op->W == 256) {
-    resize_fwd_pair_kernel<<<grid, kThreads, smem + sizeof(float) * kRO * 256, st>>>(t, op->C, op->H, op->oH, op->oW, a);
-    DPS_LAUNCH_CHECK("resize_forward");
-    return DPS_OK;
+    resize_fwd_pair_kernel<2><<<grid, 256, fwd_smem(f, 2, 256, op->oW), st>>>(f, op->C, op->H, op->oH, op->oW, a);
+  } else {
+    resize_fwd_kernel<<<grid, kThreads, fwd_smem(f, 1, op->W, op->oW), st>>>(f, op->C, op->H, op->W, op->oH, op->oW, a);
   }
-  resize_fwd_kernel<<<grid, kThreads, smem, st>>>(t, op->C, op->H, op->W, op->oH, op->oW, a);
   DPS_LAUNCH_CHECK("resize_forward");
+  return DPS_OK;
+}
+
+template <int RA, int KJ, int KT>
+static int launch_adj(const dps_operator* op, const AdjStrips& strips, const AdjArgs& a, cudaStream_t st) {
+  const ResizeTables& t = *op->resize;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DPS_CUDA(cudaFuncSetAttribute(resize_adj_kernel<RA, KJ, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)(op->C * strips.strips), (unsigned)a.n);
+  resize_adj_kernel<RA, KJ, KT><<<grid, kThreads, adj_smem(RA, KJ, op->oW, t.cols.kt, op->W), st>>>(
+      strips, t.cols, op->C, op->H, op->W, op->oH, op->oW, a);
+  DPS_LAUNCH_CHECK("resize_adjoint");
   return DPS_OK;
 }
 
 int resize_adjoint(const dps_operator* op, const AdjArgs& a, cudaStream_t st) {
   const ResizeTables& t = *op->resize;
-  const size_t smem = adj_smem(op->oH, op->oW, t.kt, op->W);
-  static bool attr_set = false;
-  if (!attr_set) {
-    DPS_CUDA(cudaFuncSetAttribute(resize_adj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
-  dim3 grid((unsigned)(op->C * t.astrips), (unsigned)a.n);
-  resize_adj_kernel<<<grid, kThreads, smem, st>>>(t, op->C, op->H, op->W, op->oH, op->oW, a);
-  DPS_LAUNCH_CHECK("resize_adjoint");
-  return DPS_OK;
+  const bool narrow = t.cols.kt <= 4;  // KT: compile-time bound of the column window (4 covers bicubic x4 and x8)
+  if (t.small.strips && small_grid((int64_t)op->C * t.big.strips * a.n))
+    return narrow ? launch_adj<kRAs, kJs, 4>(op, t.small, a, st) : launch_adj<kRAs, kJs, kKTMax>(op, t.small, a, st);
+  return narrow ? launch_adj<kRA, kJMax, 4>(op, t.big, a, st) : launch_adj<kRA, kJMax, kKTMax>(op, t.big, a, st);
 }

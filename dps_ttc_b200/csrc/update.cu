@@ -11,9 +11,7 @@
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kVecPerThread = 2;  // float4 per thread per stream -> 12-14 independent 16 B loads in flight (x0 / q kernels)
-// The update kernel picks its vector count per launch: 2 for large grids (more CTAs per SM), 4 when the whole
-// problem fits in one wave of CTAs anyway (N ≈ 8 particles): fewer, fatter CTAs finish in a single wave, no tail.
+constexpr int kVecPerThread = 2;  // float4 per thread per stream -> 12-14 independent 16 B loads in flight
 
 struct UpdateArgs {
   const float* x;
@@ -64,7 +62,7 @@ DPS_DEV float ddim_sample(float x, float x0, float z, float c1, float c2, const 
     body(x) body(y) body(z) body(w) \
   }
 
-template <bool kDdim, int kVecPerThread>
+template <bool kDdim>
 __global__ void __launch_bounds__(kThreads) posterior_update_kernel(const UpdateArgs a) {
   const int n = blockIdx.y;
   const int64_t base4 = (int64_t)blockIdx.x * (kThreads * kVecPerThread) + threadIdx.x;
@@ -211,14 +209,9 @@ int launch_update(const dps_source* src, const float* v, int64_t v_stride, const
   a.c2 = src->c2;
   a.clip = src->clip;
   a.k = *k;
-  const int64_t blocks2 = (a.chw4 + kThreads * 2 - 1) / (kThreads * 2) * n;
-  if (blocks2 <= 148 * 8) {  // small problem: one wave of fat CTAs
-    dim3 grid((unsigned)((a.chw4 + kThreads * 4 - 1) / (kThreads * 4)), (unsigned)n);
-    posterior_update_kernel<kDdim, 4><<<grid, kThreads, 0, (cudaStream_t)stream>>>(a);
-  } else {
-    dim3 grid((unsigned)((a.chw4 + kThreads * 2 - 1) / (kThreads * 2)), (unsigned)n);
-    posterior_update_kernel<kDdim, 2><<<grid, kThreads, 0, (cudaStream_t)stream>>>(a);
-  }
+  const int per_block = kThreads * kVecPerThread;
+  dim3 grid((unsigned)((a.chw4 + per_block - 1) / per_block), (unsigned)n);
+  posterior_update_kernel<kDdim><<<grid, kThreads, 0, (cudaStream_t)stream>>>(a);
   DPS_LAUNCH_CHECK(who);
   return DPS_OK;
 }

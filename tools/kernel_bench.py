@@ -32,6 +32,7 @@ WARM = 3
 
 
 BRACKET = False
+GRAPH = False
 
 
 def time_it(fn, n_sets, iters, warm=None):
@@ -50,8 +51,31 @@ def time_it(fn, n_sets, iters, warm=None):
             e1.record()
             pairs.append((e0, e1))
         torch.cuda.synchronize()
+        # event timestamps tick every ≈2 µs on this part: the MEAN of many brackets resolves below the tick, a
+        # median cannot.  The slowest tenth (stragglers behind a clock ramp) is dropped.
         ts = sorted(a.elapsed_time(b) for a, b in pairs)
-        return ts[len(ts) // 2] * 1e3  # median µs
+        ts = ts[: max(1, len(ts) - len(ts) // 10)]
+        return sum(ts) / len(ts) * 1e3  # µs
+    if GRAPH:
+        # `iters` launches captured into one CUDA graph and replayed: GPU-side back-to-back time with no CPU launch
+        # cost in between (the other way to time small-N launches)
+        g = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(g, stream=side):
+                for i in range(iters):
+                    fn(i % n_sets)
+        torch.cuda.current_stream().wait_stream(side)
+        g.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / (5 * iters) * 1e3
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(iters):
@@ -69,11 +93,14 @@ def main():
     ap.add_argument("--only", default="")
     ap.add_argument("--warm", type=int, default=3)
     ap.add_argument("--bracket", action="store_true", help="median of per-launch CUDA-event brackets (small N)")
+    ap.add_argument("--graph", action="store_true", help="replay `iters` launches from one CUDA graph (small N)")
     a = ap.parse_args()
-    global WARM, BRACKET
-    WARM, BRACKET = a.warm, a.bracket
+    global WARM, BRACKET, GRAPH
+    WARM, BRACKET, GRAPH = a.warm, a.bracket, a.graph
     dev = torch.device("cuda:0")
-    n, S = a.n, a.sets
+    n = a.n
+    # enough rotating sets that one tensor stream alone cycles through ≥ 2x the 126 MB L2 before it is reused
+    S = max(a.sets, -(-256 * 2**20 // (2 * n * T)))
     only = set(filter(None, a.only.split(",")))
     peak = peak_gbs()
     k = Schedule(named_beta_schedule("linear", 1000)).consts(500)
