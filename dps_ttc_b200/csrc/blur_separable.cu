@@ -208,15 +208,14 @@ __global__ void __launch_bounds__(kThreads, 2) sep2_kernel(const SepParams<R> p,
   const int64_t plane = (int64_t)c * H * W;
   const int64_t nchw = (int64_t)p.C * H * W;
 
-  for (int i = tid; i < kBorder; i += kThreads) {
-    bvs[i] = p.bv[i];
-    bhs[i] = p.bh[i];
-  }
+  stage_async(bvs, p.bv, kBorder, tid, kThreads);  // border tables: asynchronous, awaited with the tile
+  stage_async(bhs, p.bh, kBorder, tid, kThreads);
   sep_stage<R, kAdjoint>(tile, W, 0, r0, n, plane, p.C, H, W, fa, aa);
   for (int i = tid; i < (kRows / 2) * 2 * R; i += kThreads) {  // zero the column halos of V2
     const int rp = i / (2 * R), q = i - rp * (2 * R);
     V2[rp * VW + (q < R ? q : W + q)] = make_float2(0.f, 0.f);
   }
+  stage_wait();
   __syncthreads();
 
   // ---- phase 1: vertical pass, two columns per thread, 16 rows per thread ------------------------
@@ -421,7 +420,7 @@ __global__ void __launch_bounds__(kT3, SEP3_MINB) sep3_kernel(const SepParams<R>
   const int64_t nchw = (int64_t)p.C * H * W;
   const bool is_top = strip == 0, is_bot = strip == p.strips - 1;
 
-  for (int i = tid; i < kBorder; i += kT3) bhs[i] = p.bh[i];
+  stage_async(bhs, p.bh, kBorder, tid, kT3);  // horizontal border table: lands while the vertical pass streams
   for (int i = tid; i < (kRows / 2) * 2 * R; i += kT3) {
     const int rp = i / (2 * R), q = i - rp * (2 * R);
     V2[rp * VW + (q < R ? q : W + q)] = make_float2(0.f, 0.f);
@@ -484,6 +483,7 @@ __global__ void __launch_bounds__(kT3, SEP3_MINB) sep3_kernel(const SepParams<R>
       }
     }
   }
+  stage_wait();
   __syncthreads();
 
   // ---- phase 2: horizontal pass, a row pair × 4 columns per item (as sep2_kernel) -----------------
@@ -580,15 +580,14 @@ __global__ void __launch_bounds__(kThreads) sep1_kernel(const SepParams<R> p, co
   const int tid = threadIdx.x;
   const int64_t plane = (int64_t)c * H * W;
   const int64_t nchw = (int64_t)p.C * H * W;
-  for (int i = tid; i < kBorder; i += kThreads) {
-    bvs[i] = p.bv[i];
-    bhs[i] = p.bh[i];
-  }
+  stage_async(bvs, p.bv, kBorder, tid, kThreads);  // border tables: asynchronous, awaited with the tile
+  stage_async(bhs, p.bh, kBorder, tid, kThreads);
   sep_stage<R, kAdjoint>(tile, SW, R, r0, n, plane, p.C, H, W, fa, aa);
   for (int i = tid; i < (kRows + 2 * R) * 2 * R; i += kThreads) {
     const int tr = i / (2 * R), q = i - tr * (2 * R);
     tile[tr * SW + (q < R ? q : W + q)] = 0.f;
   }
+  stage_wait();
   __syncthreads();
   for (int col = tid; col < W; col += kThreads) {  // vertical, in place (a column is touched by one thread)
     float* colp = tile + R + col;

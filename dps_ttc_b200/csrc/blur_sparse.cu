@@ -5,30 +5,39 @@
 // keeps only the non-zero taps (dy, dx, w).
 //
 // forward : one CTA stages a strip of x̂₀ with its halo in shared memory, reflect-filled, and every thread
-//           accumulates 8 vertically adjacent outputs of one column: one LDS + one FFMA per (tap, output),
-//           the tap's tile offset precomputed once per CTA.
+//           accumulates 8 vertically adjacent outputs of one column.  The non-zero taps are covered by vertical
+//           CHUNKS of 4 (same dx, dy0 … dy0+3, absent taps weigh 0): a chunk loads the 11 tile values under it once
+//           and feeds 32 FFMA from registers — 0.34 LDS per FFMA instead of 1.1 with one tap at a time (a motion
+//           path is 2-5 taps thick in every column, so a chunk is rarely more than half empty).
 // adjoint : A = C·P (P = reflect pad, C = valid correlation) ⇒ Aᵀ = Pᵀ·Cᵀ, done literally in two kernels:
 //           (1) t = Cᵀu on the PADDED domain (H+2Ry, W+2Rx) — the same gather kernel with negated offsets over
 //               a zero-filled tile, no border cases at all — into the operator's workspace (stays in L2);
 //           (2) fold: g[m] = Σ_{p : reflect(p) = m} t[p]  (1, 2 or 4 terms per pixel), fused with
 //               coef / extra / clamp mask.
-// Roofline: T_nz taps → 2·T_nz flop per pixel per direction against 8-16 B, one LDS per FMA: LDS/issue-bound,
-// NOT HBM-bound, for T_nz ≳ 20 — stated as such in DESIGN.md.
+// Roofline: T_nz taps → 2·T_nz flop per pixel per direction against 12-16 B: for T_nz ≳ 20 this is bound by the
+// shared-memory / fp32 issue rate of the SM, NOT by HBM — stated as such in DESIGN.md.
+#include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "operator.cuh"
 
 namespace {
 constexpr int kRows = 32;
-constexpr int kGroup = 8;
+constexpr int kGroup = 16;  // vertically adjacent outputs per thread and pass
+constexpr int kSWFixed = 384;   // compile-time tile row strides of the 256-wide fast path: halo ≤ 64 columns per side,
+constexpr int kSWFixedS = 320;  // or ≤ 32 (smaller tile, one more CTA per SM)
 
-struct Tap {
-  int dydx;  // (dy << 16) | (dx & 0xffff)
-  float w;
+constexpr int kChunk = 4;  // taps per vertical chunk
+
+struct Tap {    // global: one chunk
+  int dydx;     // (dy0 << 16) | (dx & 0xffff)
+  float w[kChunk];
 };
-struct TapOff {
-  int off;  // signed offset in the staged tile
-  float w;
+struct __align__(16) TapOff {  // shared: the same with the tile offset resolved
+  float w[kChunk];
+  int off;      // signed offset in the staged tile of the chunk's first row
+  int pad[3];
 };
 }  // namespace
 
@@ -46,7 +55,9 @@ DPS_DEV int tap_dx(int v) { return (int)(short)(v & 0xffff); }
 // kAdjoint = false: out rows/cols = image;   tile = rows [r0−Ry, r0+32+Ry) × cols [−Rx, W+Rx), reflect fill
 // kAdjoint = true : out rows/cols = padded t; tile = u rows [p0−2Ry, p0+32) (image coords p0−Ry …) zero fill,
 //                   cols [−2Rx, W+2Rx).  blockDim.x ≥ number of output columns is NOT required (columns loop).
-template <bool kAdjoint>
+// kSW > 0: the tile row stride is the compile-time constant kSW (every LDS of the tap loop gets an immediate offset,
+// no address arithmetic); kSW = 0: stride W + 2·halo computed at run time.
+template <bool kAdjoint, int kSW>
 __global__ void __launch_bounds__(320) sparse_kernel(const Tap* __restrict__ taps_g, int ntaps, int Ry, int Rx, int C,
                                                      int H, int W, int strips, const FwdArgs fa, const AdjArgs aa,
                                                      float* __restrict__ t_out) {
@@ -54,10 +65,10 @@ __global__ void __launch_bounds__(320) sparse_kernel(const Tap* __restrict__ tap
   const int OW = kAdjoint ? W + 2 * Rx : W;      // output columns
   const int OH = kAdjoint ? H + 2 * Ry : H;      // output rows
   const int halo_x = kAdjoint ? 2 * Rx : Rx;     // tile columns left of image column 0
-  const int SW = W + 2 * halo_x;
+  const int SW = kSW > 0 ? kSW : W + 2 * halo_x;
   const int tile_rows = kRows + 2 * Ry;
   float* tile = smem;
-  TapOff* taps = reinterpret_cast<TapOff*>(tile + tile_rows * SW);
+  TapOff* taps = reinterpret_cast<TapOff*>(tile + ((tile_rows * SW + 3) & ~3));
   float* red = reinterpret_cast<float*>(taps + ntaps);
 
   const int strip = blockIdx.x % strips;
@@ -70,9 +81,11 @@ __global__ void __launch_bounds__(320) sparse_kernel(const Tap* __restrict__ tap
 
   for (int i = tid; i < ntaps; i += nthreads) {
     const Tap tp = taps_g[i];
-    const int off = tap_dy(tp.dydx) * SW + tap_dx(tp.dydx);
-    taps[i].off = kAdjoint ? -off : off;
-    taps[i].w = tp.w;
+    const int dy0 = tap_dy(tp.dydx), dx = tap_dx(tp.dydx);
+    // adjoint: t[p] = Σ w_i·u[p − d_i]; the run p − (dy0+3) … p − dy0 read top-down carries the weights reversed
+    taps[i].off = kAdjoint ? -((dy0 + kChunk - 1) * SW + dx) : dy0 * SW + dx;
+#pragma unroll
+    for (int k = 0; k < kChunk; ++k) taps[i].w[k] = tp.w[kAdjoint ? kChunk - 1 - k : k];
   }
   {
     const float* x;
@@ -87,17 +100,31 @@ __global__ void __launch_bounds__(320) sparse_kernel(const Tap* __restrict__ tap
       c1 = fa.src.c1; c2 = fa.src.c2; clip = fa.src.clip;
     }
     const int w4 = W / 4;
-    for (int i = tid; i < tile_rows * w4; i += nthreads) {
-      const int tr = i / w4, q = i - tr * w4;
-      int row = img_row0 + tr;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (kAdjoint) {
-        if (row >= 0 && row < H) v = ldg_stream4(x + (int64_t)row * W + q * 4);
-      } else {
-        row = reflect_idx(row, H);
-        v = src_load4(x, eps, (int64_t)row * W + q * 4, c1, c2, clip);
+    // four independent 16-byte requests (eight with ε) per thread in flight before the first shared store
+    constexpr int kSB = 4;
+    for (int i0 = tid; i0 < tile_rows * w4; i0 += kSB * nthreads) {
+      float4 v[kSB];
+#pragma unroll
+      for (int b = 0; b < kSB; ++b) {
+        const int i = i0 + b * nthreads;
+        const int tr = i / w4, q = i - tr * w4;
+        int row = img_row0 + tr;
+        v[b] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < tile_rows * w4) {
+          if (kAdjoint) {
+            if (row >= 0 && row < H) v[b] = ldg_stream4(x + (int64_t)row * W + q * 4);
+          } else {
+            row = reflect_idx(row, H);
+            v[b] = src_load4(x, eps, (int64_t)row * W + q * 4, c1, c2, clip);
+          }
+        }
       }
-      *reinterpret_cast<float4*>(tile + tr * SW + halo_x + q * 4) = v;
+#pragma unroll
+      for (int b = 0; b < kSB; ++b) {
+        const int i = i0 + b * nthreads;
+        const int tr = i / w4, q = i - tr * w4;
+        if (i < tile_rows * w4) *reinterpret_cast<float4*>(tile + tr * SW + halo_x + q * 4) = v[b];
+      }
     }
     __syncthreads();
     // column halos: reflect (forward) from the staged interior, zero (adjoint)
@@ -123,12 +150,20 @@ __global__ void __launch_bounds__(320) sparse_kernel(const Tap* __restrict__ tap
 #pragma unroll
       for (int j = 0; j < kGroup; ++j) acc[j] = 0.f;
       const float* base = base0 + g0 * SW;
-#pragma unroll 4
+#pragma unroll 2
       for (int t = 0; t < ntaps; ++t) {
-        const TapOff tp = taps[t];
-        const float* p = base + tp.off;
+        const float4 w = *reinterpret_cast<const float4*>(taps[t].w);
+        const float* p = base + taps[t].off;
+        float v[kGroup + kChunk - 1];
 #pragma unroll
-        for (int j = 0; j < kGroup; ++j) acc[j] = fmaf(tp.w, p[j * SW], acc[j]);
+        for (int i = 0; i < kGroup + kChunk - 1; ++i) v[i] = p[i * SW];
+#pragma unroll
+        for (int j = 0; j < kGroup; ++j) {
+          acc[j] = fmaf(w.x, v[j], acc[j]);
+          acc[j] = fmaf(w.y, v[j + 1], acc[j]);
+          acc[j] = fmaf(w.z, v[j + 2], acc[j]);
+          acc[j] = fmaf(w.w, v[j + 3], acc[j]);
+        }
       }
 #pragma unroll
       for (int j = 0; j < kGroup; ++j) {
@@ -183,27 +218,64 @@ __global__ void __launch_bounds__(256) sparse_fold_kernel(const float* __restric
   stg_stream(aa.g + n * aa.g_stride + off, res);
 }
 
-size_t sparse_smem(const dps_operator* op, bool adjoint) {
+// tile row stride: the compile-time kSWFixed when the image is 256 wide and the halo fits, else W + 2·halo
+int sparse_stride(const dps_operator* op, bool adjoint, bool* fixed) {
   const SparseTables* t = op->sparse;
   const int halo_x = adjoint ? 2 * t->Rx : t->Rx;
-  return sizeof(float) * ((size_t)(kRows + 2 * t->Ry) * (op->W + 2 * halo_x) + 64) + sizeof(TapOff) * (size_t)t->ntaps;
+  *fixed = op->W == 256 && op->W + 2 * halo_x <= kSWFixed;
+  return !*fixed ? op->W + 2 * halo_x : (op->W + 2 * halo_x <= kSWFixedS ? kSWFixedS : kSWFixed);
+}
+
+size_t sparse_smem(const dps_operator* op, bool adjoint) {
+  const SparseTables* t = op->sparse;
+  bool fixed;
+  const int SW = sparse_stride(op, adjoint, &fixed);
+  size_t bytes = sizeof(float) * ((((size_t)(kRows + 2 * t->Ry) * SW + 3) & ~(size_t)3) + 64) + sizeof(TapOff) * (size_t)t->ntaps;
+  if (fixed && bytes > 227 * 1024) {  // tall kernels: fall back to the tight run-time stride
+    bytes = sizeof(float) * ((((size_t)(kRows + 2 * t->Ry) * (op->W + 2 * (adjoint ? 2 * t->Rx : t->Rx)) + 3) & ~(size_t)3) + 64) +
+            sizeof(TapOff) * (size_t)t->ntaps;
+  }
+  return bytes;
+}
+bool sparse_fixed(const dps_operator* op, bool adjoint) {
+  const SparseTables* t = op->sparse;
+  bool fixed;
+  const int SW = sparse_stride(op, adjoint, &fixed);
+  const size_t bytes = sizeof(float) * ((((size_t)(kRows + 2 * t->Ry) * SW + 3) & ~(size_t)3) + 64) + sizeof(TapOff) * (size_t)t->ntaps;
+  return fixed && bytes <= 227 * 1024;
 }
 
 }  // namespace
 
 int sparse_create(dps_operator* op, const float* kernel, int ksize) {
   const int r0 = ksize / 2;
-  std::vector<Tap> taps;
-  int Ry = 0, Rx = 0;
+  int Ry = 0, Rx = 0, nnz = 0;
   for (int a = 0; a < ksize; ++a)
     for (int b = 0; b < ksize; ++b) {
-      const float w = kernel[a * ksize + b];
-      if (w == 0.0f) continue;
-      const int dy = a - r0, dx = b - r0;
-      taps.push_back({(int)(((unsigned)dy << 16) | ((unsigned)dx & 0xffffu)), w});
-      Ry = abs(dy) > Ry ? abs(dy) : Ry;
-      Rx = abs(dx) > Rx ? abs(dx) : Rx;
+      if (kernel[a * ksize + b] == 0.0f) continue;
+      ++nnz;
+      Ry = std::max(Ry, abs(a - r0));
+      Rx = std::max(Rx, abs(b - r0));
     }
+  Ry = std::max(Ry, 2);  // a chunk of 4 rows must fit inside the halo window [−Ry, Ry]
+  // cover the non-zero taps of every column with chunks of kChunk rows; a chunk never leaves [−Ry, Ry]
+  std::vector<Tap> taps;
+  for (int b = 0; b < ksize; ++b) {
+    int a = 0;
+    while (a < ksize) {
+      if (kernel[a * ksize + b] == 0.0f) { ++a; continue; }
+      const int dy_first = a - r0;
+      const int dy0 = std::min(dy_first, Ry - (kChunk - 1));
+      Tap tp;
+      tp.dydx = (int)(((unsigned)dy0 << 16) | ((unsigned)(b - r0) & 0xffffu));
+      for (int k = 0; k < kChunk; ++k) {
+        const int aa = dy0 + k + r0;  // rows before dy_first belong to an earlier chunk (or are zero)
+        tp.w[k] = (aa >= a && aa < ksize) ? kernel[aa * ksize + b] : 0.0f;
+      }
+      taps.push_back(tp);
+      a = dy0 + kChunk + r0;
+    }
+  }
   DPS_REQUIRE(!taps.empty(), DPS_ERR_INVALID, "blur: kernel is all zero");
   DPS_REQUIRE(Ry < op->H && Rx < op->W, DPS_ERR_UNSUPPORTED, "sparse blur: kernel radius (%d,%d) reaches the image size", Ry, Rx);
   Rx = (Rx + 3) / 4 * 4;
@@ -217,10 +289,14 @@ int sparse_create(dps_operator* op, const float* kernel, int ksize) {
   DPS_REQUIRE(sparse_smem(op, true) <= 227 * 1024, DPS_ERR_UNSUPPORTED, "sparse blur: tile exceeds shared memory");
   DPS_CUDA(cudaMalloc(&t->taps_dev, taps.size() * sizeof(Tap)));
   DPS_CUDA(cudaMemcpy(t->taps_dev, taps.data(), taps.size() * sizeof(Tap), cudaMemcpyHostToDevice));
-  DPS_CUDA(cudaFuncSetAttribute(sparse_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  DPS_CUDA(cudaFuncSetAttribute(sparse_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  DPS_CUDA(cudaFuncSetAttribute(sparse_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  DPS_CUDA(cudaFuncSetAttribute(sparse_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  DPS_CUDA(cudaFuncSetAttribute(sparse_kernel<false, kSWFixed>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  DPS_CUDA(cudaFuncSetAttribute(sparse_kernel<true, kSWFixed>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  DPS_CUDA(cudaFuncSetAttribute(sparse_kernel<false, kSWFixedS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  DPS_CUDA(cudaFuncSetAttribute(sparse_kernel<true, kSWFixedS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   op->P = op->C * ((op->H + kRows - 1) / kRows);
-  op->taps = t->ntaps;
+  op->taps = nnz;
   op->aux_floats = (int64_t)op->C * (op->H + 2 * Ry) * (op->W + 2 * Rx);  // padded t of the adjoint
   return DPS_OK;
 }
@@ -237,8 +313,17 @@ int sparse_forward(const dps_operator* op, const FwdArgs& a, cudaStream_t st) {
   AdjArgs dummy = {};
   const int strips = (op->H + kRows - 1) / kRows;
   dim3 grid((unsigned)(op->C * strips), (unsigned)a.n);
-  sparse_kernel<false><<<grid, 256, sparse_smem(op, false), st>>>(t->taps_dev, t->ntaps, t->Ry, t->Rx, op->C, op->H,
-                                                                  op->W, strips, a, dummy, nullptr);
+  bool fx;
+  const int SW = sparse_stride(op, false, &fx);
+  if (sparse_fixed(op, false) && SW == kSWFixedS)
+    sparse_kernel<false, kSWFixedS><<<grid, 256, sparse_smem(op, false), st>>>(t->taps_dev, t->ntaps, t->Ry, t->Rx, op->C,
+                                                                               op->H, op->W, strips, a, dummy, nullptr);
+  else if (sparse_fixed(op, false))
+    sparse_kernel<false, kSWFixed><<<grid, 256, sparse_smem(op, false), st>>>(t->taps_dev, t->ntaps, t->Ry, t->Rx, op->C,
+                                                                              op->H, op->W, strips, a, dummy, nullptr);
+  else
+    sparse_kernel<false, 0><<<grid, 256, sparse_smem(op, false), st>>>(t->taps_dev, t->ntaps, t->Ry, t->Rx, op->C, op->H,
+                                                                       op->W, strips, a, dummy, nullptr);
   DPS_LAUNCH_CHECK("sparse_blur_forward");
   return DPS_OK;
 }
@@ -253,8 +338,17 @@ int sparse_adjoint(const dps_operator* op, const AdjArgs& a, cudaStream_t st) {
   const int strips = (OH + kRows - 1) / kRows;
   const int threads = OW >= 320 ? 320 : ((OW + 31) / 32) * 32;
   dim3 grid((unsigned)(op->C * strips), (unsigned)a.n);
-  sparse_kernel<true><<<grid, threads, sparse_smem(op, true), st>>>(t->taps_dev, t->ntaps, t->Ry, t->Rx, op->C, op->H,
-                                                                    op->W, strips, dummy, a, scratch);
+  bool fx;
+  const int SW = sparse_stride(op, true, &fx);
+  if (sparse_fixed(op, true) && SW == kSWFixedS)
+    sparse_kernel<true, kSWFixedS><<<grid, threads, sparse_smem(op, true), st>>>(t->taps_dev, t->ntaps, t->Ry, t->Rx, op->C,
+                                                                                 op->H, op->W, strips, dummy, a, scratch);
+  else if (sparse_fixed(op, true))
+    sparse_kernel<true, kSWFixed><<<grid, threads, sparse_smem(op, true), st>>>(t->taps_dev, t->ntaps, t->Ry, t->Rx, op->C,
+                                                                                op->H, op->W, strips, dummy, a, scratch);
+  else
+    sparse_kernel<true, 0><<<grid, threads, sparse_smem(op, true), st>>>(t->taps_dev, t->ntaps, t->Ry, t->Rx, op->C, op->H,
+                                                                         op->W, strips, dummy, a, scratch);
   DPS_LAUNCH_CHECK("sparse_blur_adjoint_t");
   dim3 fgrid((unsigned)((op->H * op->W + 255) / 256), (unsigned)op->C, (unsigned)a.n);
   sparse_fold_kernel<<<fgrid, 256, 0, st>>>(scratch, t->Ry, t->Rx, op->C, op->H, op->W, a);

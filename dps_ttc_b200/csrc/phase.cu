@@ -26,7 +26,9 @@
 namespace {
 constexpr int kL = 384;
 constexpr int kHalf = kL / 2 + 1;  // 193
-constexpr int kLP = kL + kL / 8;     // padded length of a sequence in shared memory (432)
+constexpr int kLP = kL + kL / 8 + 1;  // padded length of a sequence in shared memory: 433, ODD so that the same element of
+                                      // consecutive sequences falls into different banks (loops that run over the sequence index)
+constexpr int kLF = kL + 1;           // row stride of the float planes staged per sequence (same reason)
 constexpr int kImg = 256;
 constexpr int kPad = 64;
 constexpr int kThreads = 256;
@@ -48,6 +50,26 @@ namespace {
 // Shared-memory sequences are padded by one element every 8: element i lives at i + (i >> 3).  With 8-byte
 // elements this makes the stride-8 / stride-64 scatter of the Stockham stages conflict-free (stride 9 / 72).
 DPS_DEV int P(int i) { return i + (i >> 3); }
+
+// for (i = tid; i < kItems; i += kThreads) store(i, load(i)) with the loads of kBatch iterations issued before the
+// first store: a "load, then store to shared" loop otherwise serialises one global round trip per iteration.
+template <int kItems, int kBatch, class Load, class Store>
+DPS_DEV void batched_copy(int tid, Load load, Store store) {
+#pragma unroll 1
+  for (int i0 = tid; i0 < kItems; i0 += kBatch * kThreads) {
+    decltype(load(0)) v[kBatch];
+#pragma unroll
+    for (int b = 0; b < kBatch; ++b) {
+      const int i = i0 + b * kThreads;
+      if (i < kItems) v[b] = load(i);
+    }
+#pragma unroll
+    for (int b = 0; b < kBatch; ++b) {
+      const int i = i0 + b * kThreads;
+      if (i < kItems) store(i, v[b]);
+    }
+  }
+}
 
 DPS_DEV float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 DPS_DEV float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
@@ -191,7 +213,7 @@ __global__ void __launch_bounds__(kThreads) phase_rows_fwd(const FwdArgs fa, con
   const int groups = kImg / kRowsPerCta;
   const int grp = blockIdx.x % groups, c = blockIdx.x / groups, n = blockIdx.y;
   const int r0 = grp * kRowsPerCta;
-  for (int i = tid; i < kL; i += kThreads) s.tw[i] = tw_g[i];
+  stage_async(reinterpret_cast<float*>(s.tw), reinterpret_cast<const float*>(tw_g), 2 * kL, tid, kThreads);
   // zero the padding columns [0,64) and [320,384) of every sequence
   for (int i = tid; i < nfft * 2 * kPad; i += kThreads) {
     const int f = i / (2 * kPad), q = i - f * (2 * kPad);
@@ -200,15 +222,24 @@ __global__ void __launch_bounds__(kThreads) phase_rows_fwd(const FwdArgs fa, con
   const int64_t plane = (int64_t)c * kImg * kImg;
   const float* x = fa.src.x + n * fa.src.x_stride + plane;
   const float* eps = fa.src.eps ? fa.src.eps + n * fa.src.eps_stride + plane : nullptr;
-  for (int i = tid; i < nfft * (kImg / 4); i += kThreads) {
-    const int f = i / (kImg / 4), q = i - f * (kImg / 4);
-    const float4 re = src_load4(x, eps, (int64_t)(r0 + 2 * f) * kImg + q * 4, fa.src.c1, fa.src.c2, fa.src.clip);
-    const float4 im = src_load4(x, eps, (int64_t)(r0 + 2 * f + 1) * kImg + q * 4, fa.src.c1, fa.src.c2, fa.src.clip);
-    float2* d = s.a + f * kLP;
-    const int i0 = kPad + q * 4;
-    d[P(i0)] = make_float2(re.x, im.x); d[P(i0 + 1)] = make_float2(re.y, im.y);
-    d[P(i0 + 2)] = make_float2(re.z, im.z); d[P(i0 + 3)] = make_float2(re.w, im.w);
-  }
+  struct RowPair { float4 re, im; };
+  batched_copy<nfft * (kImg / 4), 2>(
+      tid,
+      [&](int i) {
+        const int f = i / (kImg / 4), q = i - f * (kImg / 4);
+        RowPair v;
+        v.re = src_load4(x, eps, (int64_t)(r0 + 2 * f) * kImg + q * 4, fa.src.c1, fa.src.c2, fa.src.clip);
+        v.im = src_load4(x, eps, (int64_t)(r0 + 2 * f + 1) * kImg + q * 4, fa.src.c1, fa.src.c2, fa.src.clip);
+        return v;
+      },
+      [&](int i, const RowPair& v) {
+        const int f = i / (kImg / 4), q = i - f * (kImg / 4);
+        float2* d = s.a + f * kLP;
+        const int i0 = kPad + q * 4;
+        d[P(i0)] = make_float2(v.re.x, v.im.x); d[P(i0 + 1)] = make_float2(v.re.y, v.im.y);
+        d[P(i0 + 2)] = make_float2(v.re.z, v.im.z); d[P(i0 + 3)] = make_float2(v.re.w, v.im.w);
+      });
+  stage_wait();
   __syncthreads();
   fft384_batch(s.a, s.b, s.tw, nfft);
   // split Z = A + iB (A, B spectra of the even / odd row) and store Rt[k2][row] for k2 ∈ [0,192]
@@ -235,25 +266,31 @@ __global__ void __launch_bounds__(kThreads) phase_cols_fwd(const FwdArgs fa, con
   const int grp = blockIdx.x % kColGroups, c = blockIdx.x / kColGroups, n = blockIdx.y;
   const int k20 = grp * kColsPerCta;
   const int ncols = min(kColsPerCta, kHalf - k20);
-  for (int i = tid; i < kL; i += kThreads) s.tw[i] = tw_g[i];
+  stage_async(reinterpret_cast<float*>(s.tw), reinterpret_cast<const float*>(tw_g), 2 * kL, tid, kThreads);
   for (int i = tid; i < nfft * 2 * kPad; i += kThreads) {
     const int f = i / (2 * kPad), q = i - f * (2 * kPad);
     s.a[f * kLP + P(q < kPad ? q : kImg + q)] = make_float2(0.f, 0.f);
   }
   const float2* rt = aux_scratch(fa.aux, n, C, c);
-  for (int i = tid; i < nfft * (kImg / 2); i += kThreads) {
-    const int f = i / (kImg / 2), q = i - f * (kImg / 2);
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (f < ncols) v = *reinterpret_cast<const float4*>(rt + (int64_t)(k20 + f) * kImg + q * 2);
-    float2* d = s.a + f * kLP;
-    d[P(kPad + q * 2)] = make_float2(v.x, v.y);
-    d[P(kPad + q * 2 + 1)] = make_float2(v.z, v.w);
-  }
+  batched_copy<nfft * (kImg / 2), 4>(
+      tid,
+      [&](int i) {
+        const int f = i / (kImg / 2), q = i - f * (kImg / 2);
+        return f < ncols ? *reinterpret_cast<const float4*>(rt + (int64_t)(k20 + f) * kImg + q * 2)
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
+      },
+      [&](int i, const float4& v) {
+        const int f = i / (kImg / 2), q = i - f * (kImg / 2);
+        float2* d = s.a + f * kLP;
+        d[P(kPad + q * 2)] = make_float2(v.x, v.y);
+        d[P(kPad + q * 2 + 1)] = make_float2(v.z, v.w);
+      });
+  stage_wait();
   __syncthreads();
   fft384_batch(s.a, s.b, s.tw, nfft);
   // unit phase conj(F)/|F| → aux[k2][k1] (contiguous in k1), magnitude → s.a reused as float storage
   float2* ph = aux_phase(fa.aux, n, C, c);
-  float* amp = reinterpret_cast<float*>(s.a);  // (nfft, 384)
+  float* amp = reinterpret_cast<float*>(s.a);  // (nfft, kLF)
   const float inv_l = 1.0f / (float)kL;
   for (int i = tid; i < ncols * kL; i += kThreads) {
     const int f = i / kL, k1 = i - f * kL;
@@ -261,30 +298,54 @@ __global__ void __launch_bounds__(kThreads) phase_cols_fwd(const FwdArgs fa, con
     const float mag = sqrtf(F.x * F.x + F.y * F.y);
     const float inv = mag > 0.f ? 1.0f / mag : 0.f;
     ph[(int64_t)(k20 + f) * kL + k1] = make_float2(F.x * inv, -F.y * inv);
-    amp[f * kL + k1] = mag * inv_l;
+    amp[f * kLF + k1] = mag * inv_l;
   }
   __syncthreads();
   // outputs: direct position (u, v) = shift(k1, k2) and, for 0 < k2 < 192, the mirror shift(−k1, −k2)
   float sq = 0.f, ab = 0.f;
   const int64_t oplane = ((int64_t)n * C + c) * kL * kL;
   const float* y = fa.y ? fa.y + n * fa.y_stride + (int64_t)c * kL * kL : nullptr;
-  for (int i = tid; i < kL * ncols; i += kThreads) {
-    const int k1 = i / ncols, f = i - k1 * ncols;
+  // the measurement values of kYB output pairs are fetched before any is used (one round trip per batch, not per value)
+  constexpr int kYB = 6;
+  auto out_pos = [&](int i, int64_t& o1, int64_t& o2, int& f, int& k1) -> int {  // 0: none, 1: direct, 2: direct + mirror
+    k1 = i / kColsPerCta;
+    f = i - k1 * kColsPerCta;
     const int k2 = k20 + f;
-    const float a = amp[f * kL + k1];
-    {
-      const int64_t o = (int64_t)shift_idx(k1) * kL + shift_idx(k2);
-      const float res = y ? __fsub_rn(ldg_ro(y + o), a) : a;
-      if (fa.out) stg_stream(fa.out + oplane + o, res);
-      sq += res * res;
-      ab += fabsf(res);
+    if (i >= kL * kColsPerCta || f >= ncols) return 0;
+    o1 = (int64_t)shift_idx(k1) * kL + shift_idx(k2);
+    o2 = (int64_t)shift_idx(k1 ? kL - k1 : 0) * kL + shift_idx(kL - k2);
+    return (k2 > 0 && k2 < kL / 2) ? 2 : 1;
+  };
+#pragma unroll 1
+  for (int i0 = tid; i0 < kL * kColsPerCta; i0 += kYB * kThreads) {
+    float y1[kYB], y2[kYB];
+#pragma unroll
+    for (int b = 0; b < kYB; ++b) {
+      int64_t o1, o2;
+      int f, k1;
+      const int m = out_pos(i0 + b * kThreads, o1, o2, f, k1);
+      y1[b] = (y && m >= 1) ? ldg_ro(y + o1) : 0.f;
+      y2[b] = (y && m == 2) ? ldg_ro(y + o2) : 0.f;
     }
-    if (k2 > 0 && k2 < kL / 2) {
-      const int64_t o = (int64_t)shift_idx(k1 ? kL - k1 : 0) * kL + shift_idx(kL - k2);
-      const float res = y ? __fsub_rn(ldg_ro(y + o), a) : a;
-      if (fa.out) stg_stream(fa.out + oplane + o, res);
-      sq += res * res;
-      ab += fabsf(res);
+#pragma unroll
+    for (int b = 0; b < kYB; ++b) {
+      int64_t o1, o2;
+      int f, k1;
+      const int m = out_pos(i0 + b * kThreads, o1, o2, f, k1);
+      if (m == 0) continue;
+      const float a = amp[f * kLF + k1];
+      {
+        const float res = y ? __fsub_rn(y1[b], a) : a;
+        if (fa.out) stg_stream(fa.out + oplane + o1, res);
+        sq += res * res;
+        ab += fabsf(res);
+      }
+      if (m == 2) {
+        const float res = y ? __fsub_rn(y2[b], a) : a;
+        if (fa.out) stg_stream(fa.out + oplane + o2, res);
+        sq += res * res;
+        ab += fabsf(res);
+      }
     }
   }
   if (fa.partials) {
@@ -307,29 +368,37 @@ __global__ void __launch_bounds__(kThreads) phase_cols_adj(const AdjArgs aa, flo
   const int grp = blockIdx.x % kColGroupsAdj, c = blockIdx.x / kColGroupsAdj, n = blockIdx.y;
   const int k20 = grp * kColsAdj;
   const int ncols = min(kColsAdj, kHalf - k20);
-  for (int i = tid; i < kL; i += kThreads) s.tw[i] = tw_g[i];
+  stage_async(reinterpret_cast<float*>(s.tw), reinterpret_cast<const float*>(tw_g), 2 * kL, tid, kThreads);
   const float* r = aa.r + ((int64_t)n * C + c) * kL * kL;
   const float2* ph = aux_phase(aux_rw, n, C, c);
   // symmetrised cotangent (coalesced over the CTA's columns), staged as floats in s.b
   float* gs = reinterpret_cast<float*>(s.b);
-  for (int i = tid; i < kL * ncols; i += kThreads) {
-    const int k1 = i / ncols, f = i - k1 * ncols;
-    const int k2 = k20 + f;
-    const float g1 = ldg_stream(r + (int64_t)shift_idx(k1) * kL + shift_idx(k2));
-    const float g2 = ldg_stream(r + (int64_t)shift_idx(k1 ? kL - k1 : 0) * kL + shift_idx(k2 ? kL - k2 : 0));
-    gs[f * kL + k1] = 0.5f * (g1 + g2);
-  }
+  batched_copy<kL * kColsAdj, 6>(
+      tid,
+      [&](int i) {
+        const int k1 = i / kColsAdj, f = i - k1 * kColsAdj;
+        const int k2 = k20 + f;
+        if (f >= ncols) return make_float2(0.f, 0.f);
+        return make_float2(ldg_stream(r + (int64_t)shift_idx(k1) * kL + shift_idx(k2)),
+                           ldg_stream(r + (int64_t)shift_idx(k1 ? kL - k1 : 0) * kL + shift_idx(k2 ? kL - k2 : 0)));
+      },
+      [&](int i, const float2& g) {
+        const int k1 = i / kColsAdj, f = i - k1 * kColsAdj;
+        gs[f * kLF + k1] = 0.5f * (g.x + g.y);
+      });
   __syncthreads();
-  for (int i = tid; i < nfft * kL; i += kThreads) {
-    const int f = i / kL, k1 = i - f * kL;
-    float2 v = make_float2(0.f, 0.f);
-    if (f < ncols) {
-      const float2 p = ph[(int64_t)(k20 + f) * kL + k1];
-      const float g = gs[f * kL + k1];
-      v = make_float2(g * p.x, g * p.y);
-    }
-    s.a[f * kLP + P(k1)] = v;
-  }
+  batched_copy<nfft * kL, 6>(
+      tid,
+      [&](int i) {
+        const int f = i / kL, k1 = i - f * kL;
+        return f < ncols ? ph[(int64_t)(k20 + f) * kL + k1] : make_float2(0.f, 0.f);
+      },
+      [&](int i, const float2& pv) {
+        const int f = i / kL, k1 = i - f * kL;
+        const float g = gs[f * kLF + k1];
+        s.a[f * kLP + P(k1)] = make_float2(g * pv.x, g * pv.y);
+      });
+  stage_wait();
   __syncthreads();
   fft384_batch(s.a, s.b, s.tw, nfft);
   // T[row][k2] for padded rows 64..319 → image rows 0..255; row stride 193 complex
@@ -350,41 +419,52 @@ __global__ void __launch_bounds__(kThreads) phase_rows_adj(const AdjArgs aa, con
   const int groups = kImg / kRowsAdj;
   const int grp = blockIdx.x % groups, c = blockIdx.x / groups, n = blockIdx.y;
   const int r0 = grp * kRowsAdj;
-  for (int i = tid; i < kL; i += kThreads) s.tw[i] = tw_g[i];
+  stage_async(reinterpret_cast<float*>(s.tw), reinterpret_cast<const float*>(tw_g), 2 * kL, tid, kThreads);
   const float2* t = aux_scratch(const_cast<float*>(aux_r), n, C, c);
   // X[k] = T1[k] + i·T2[k] with T[384−k] = conj(T[k]) for k > 192
-  for (int i = tid; i < nfft * kL; i += kThreads) {
-    const int f = i / kL, k = i - f * kL;
-    const int kk = k < kHalf ? k : kL - k;
-    float2 t1 = t[(int64_t)(r0 + 2 * f) * kHalf + kk];
-    float2 t2 = t[(int64_t)(r0 + 2 * f + 1) * kHalf + kk];
-    if (k >= kHalf) { t1.y = -t1.y; t2.y = -t2.y; }
-    s.a[f * kLP + P(k)] = make_float2(t1.x - t2.y, t1.y + t2.x);
-  }
+  batched_copy<nfft * kL, 6>(
+      tid,
+      [&](int i) {
+        const int f = i / kL, k = i - f * kL;
+        const int kk = k < kHalf ? k : kL - k;
+        const float2 t1 = t[(int64_t)(r0 + 2 * f) * kHalf + kk];
+        const float2 t2 = t[(int64_t)(r0 + 2 * f + 1) * kHalf + kk];
+        return make_float4(t1.x, t1.y, t2.x, t2.y);
+      },
+      [&](int i, const float4& v) {
+        const int f = i / kL, k = i - f * kL;
+        const float sg = k >= kHalf ? -1.f : 1.f;  // conj for the mirrored half
+        s.a[f * kLP + P(k)] = make_float2(v.x - sg * v.w, sg * v.y + v.z);
+      });
+  stage_wait();
   __syncthreads();
   fft384_batch(s.a, s.b, s.tw, nfft);
   const float coef = (aa.coef ? aa.coef[n] : 1.0f) * (1.0f / (float)kL);
   const int64_t plane = (int64_t)c * kImg * kImg;
-  for (int i = tid; i < kRowsAdj * (kImg / 4); i += kThreads) {
-    const int rr = i / (kImg / 4), q = i - rr * (kImg / 4);
-    const int f = rr >> 1, odd = rr & 1;
-    const float2* zb = s.b + f * kLP;
-    const int i0 = kPad + q * 4;
-    const float2 z0 = zb[P(i0)], z1 = zb[P(i0 + 1)], z2 = zb[P(i0 + 2)], z3 = zb[P(i0 + 3)];
-    float4 res;
-    res.x = coef * (odd ? z0.y : z0.x);
-    res.y = coef * (odd ? z1.y : z1.x);
-    res.z = coef * (odd ? z2.y : z2.x);
-    res.w = coef * (odd ? z3.y : z3.x);
-    const int64_t off = plane + (int64_t)(r0 + rr) * kImg + q * 4;
-    if (aa.extra) {
-      const float4 e = ldg_stream4(aa.extra + n * aa.extra_stride + off);
-      res.x += e.x; res.y += e.y; res.z += e.z; res.w += e.w;
-    }
-    const float4 pass = mask_load4(aa.mask_src, aa.has_mask, n, off);
-    res.x *= pass.x; res.y *= pass.y; res.z *= pass.z; res.w *= pass.w;
-    stg_stream4(aa.g + n * aa.g_stride + off, res);
-  }
+  struct Epi { float4 e, pass; };
+  batched_copy<kRowsAdj * (kImg / 4), 4>(
+      tid,
+      [&](int i) {
+        const int rr = i / (kImg / 4), q = i - rr * (kImg / 4);
+        const int64_t off = plane + (int64_t)(r0 + rr) * kImg + q * 4;
+        Epi v;
+        v.e = aa.extra ? ldg_stream4(aa.extra + n * aa.extra_stride + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v.pass = mask_load4(aa.mask_src, aa.has_mask, n, off);
+        return v;
+      },
+      [&](int i, const Epi& v) {
+        const int rr = i / (kImg / 4), q = i - rr * (kImg / 4);
+        const int f = rr >> 1, odd = rr & 1;
+        const float2* zb = s.b + f * kLP;
+        const int i0 = kPad + q * 4;
+        const float2 z0 = zb[P(i0)], z1 = zb[P(i0 + 1)], z2 = zb[P(i0 + 2)], z3 = zb[P(i0 + 3)];
+        float4 res;
+        res.x = (coef * (odd ? z0.y : z0.x) + v.e.x) * v.pass.x;
+        res.y = (coef * (odd ? z1.y : z1.x) + v.e.y) * v.pass.y;
+        res.z = (coef * (odd ? z2.y : z2.x) + v.e.z) * v.pass.z;
+        res.w = (coef * (odd ? z3.y : z3.x) + v.e.w) * v.pass.w;
+        stg_stream4(aa.g + n * aa.g_stride + plane + (int64_t)(r0 + rr) * kImg + q * 4, res);
+      });
 }
 
 int set_smem(const void* fn, size_t bytes) {
