@@ -32,7 +32,7 @@ class Source(C.Structure):
 class StepConstsC(C.Structure):
     _fields_ = [("p1", C.c_float), ("p2", C.c_float), ("max_log", C.c_float), ("min_log", C.c_float),
                 ("ddim_sa", C.c_float), ("ddim_sb", C.c_float), ("ddim_sigma", C.c_float),
-                ("noise_on", C.c_int32), ("var_mode", C.c_int32)]
+                ("noise_on", C.c_int32), ("var_mode", C.c_int32), ("mean_mode", C.c_int32)]
 
 
 class OperatorInfo(C.Structure):
@@ -182,6 +182,7 @@ def make_consts(k, var_mode: int = 0, max_log=None) -> StepConstsC:
     c.min_log = k.min_log
     c.ddim_sa, c.ddim_sb, c.ddim_sigma = k.ddim_sa, k.ddim_sb, k.ddim_sigma
     c.noise_on, c.var_mode = int(k.noise_on), int(var_mode)
+    c.mean_mode = int(getattr(k, "mean_mode", 0))
     return c
 
 

@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(kThreads) phase_rows_fwd(const FwdArgs fa, con
 DPS_DEV int shift_idx(int k) { return k + kL / 2 >= kL ? k - kL / 2 : k + kL / 2; }  // fftshift position of bin k
 
 // ---- K2: column transforms, magnitude, residual, partial sums, unit phase -----------------------
-__global__ void __launch_bounds__(kThreads) phase_cols_fwd(const FwdArgs fa, const float2* __restrict__ tw_g, int C) {
+__global__ void __launch_bounds__(kThreads, 3) phase_cols_fwd(const FwdArgs fa, const float2* __restrict__ tw_g, int C) {
   extern __shared__ __align__(16) float smem[];
   constexpr int nfft = kColsPerCta;
   PhaseSmem s = carve(smem, nfft);
@@ -292,6 +292,7 @@ __global__ void __launch_bounds__(kThreads) phase_cols_fwd(const FwdArgs fa, con
   float2* ph = aux_phase(fa.aux, n, C, c);
   float* amp = reinterpret_cast<float*>(s.a);  // (nfft, kLF)
   const float inv_l = 1.0f / (float)kL;
+#pragma unroll 4
   for (int i = tid; i < ncols * kL; i += kThreads) {
     const int f = i / kL, k1 = i - f * kL;
     const float2 F = s.b[f * kLP + P(k1)];
@@ -305,46 +306,45 @@ __global__ void __launch_bounds__(kThreads) phase_cols_fwd(const FwdArgs fa, con
   float sq = 0.f, ab = 0.f;
   const int64_t oplane = ((int64_t)n * C + c) * kL * kL;
   const float* y = fa.y ? fa.y + n * fa.y_stride + (int64_t)c * kL * kL : nullptr;
-  // the measurement values of kYB output pairs are fetched before any is used (one round trip per batch, not per value)
-  constexpr int kYB = 6;
-  auto out_pos = [&](int i, int64_t& o1, int64_t& o2, int& f, int& k1) -> int {  // 0: none, 1: direct, 2: direct + mirror
-    k1 = i / kColsPerCta;
-    f = i - k1 * kColsPerCta;
+  // A thread keeps ONE spectrum column f (so the column part of both output positions is loop-invariant) and walks
+  // k1 = kk, kk + 32, …: after unrolling every row index is kk plus a constant.  The measurement values of a batch of
+  // kYB output pairs are fetched before any is used (one round trip per batch, not per value).
+  static_assert(kColsPerCta == 8 && kThreads == 256 && kL % 32 == 0, "epilogue mapping");
+  constexpr int kIters = kL / 32, kYB = 4;
+  static_assert(kIters % kYB == 0, "batches");
+  {
+    const int f = tid & 7, kk = tid >> 3;
     const int k2 = k20 + f;
-    if (i >= kL * kColsPerCta || f >= ncols) return 0;
-    o1 = (int64_t)shift_idx(k1) * kL + shift_idx(k2);
-    o2 = (int64_t)shift_idx(k1 ? kL - k1 : 0) * kL + shift_idx(kL - k2);
-    return (k2 > 0 && k2 < kL / 2) ? 2 : 1;
-  };
-#pragma unroll 1
-  for (int i0 = tid; i0 < kL * kColsPerCta; i0 += kYB * kThreads) {
-    float y1[kYB], y2[kYB];
+    const bool act = f < ncols, mir = act && k2 > 0 && k2 < kL / 2;
+    const int c1 = shift_idx(k2), c2 = mir ? shift_idx(kL - k2) : 0;
+    const float* ampf = amp + f * kLF;
 #pragma unroll
-    for (int b = 0; b < kYB; ++b) {
-      int64_t o1, o2;
-      int f, k1;
-      const int m = out_pos(i0 + b * kThreads, o1, o2, f, k1);
-      y1[b] = (y && m >= 1) ? ldg_ro(y + o1) : 0.f;
-      y2[b] = (y && m == 2) ? ldg_ro(y + o2) : 0.f;
-    }
+    for (int it0 = 0; it0 < kIters; it0 += kYB) {
+      float y1[kYB], y2[kYB];
+      int o1[kYB], o2[kYB];
 #pragma unroll
-    for (int b = 0; b < kYB; ++b) {
-      int64_t o1, o2;
-      int f, k1;
-      const int m = out_pos(i0 + b * kThreads, o1, o2, f, k1);
-      if (m == 0) continue;
-      const float a = amp[f * kLF + k1];
-      {
-        const float res = y ? __fsub_rn(y1[b], a) : a;
-        if (fa.out) stg_stream(fa.out + oplane + o1, res);
-        sq += res * res;
-        ab += fabsf(res);
+      for (int b = 0; b < kYB; ++b) {
+        const int k1 = kk + 32 * (it0 + b);
+        o1[b] = shift_idx(k1) * kL + c1;
+        o2[b] = shift_idx(k1 ? kL - k1 : 0) * kL + c2;
+        y1[b] = (y && act) ? ldg_ro(y + o1[b]) : 0.f;
+        y2[b] = (y && mir) ? ldg_ro(y + o2[b]) : 0.f;
       }
-      if (m == 2) {
-        const float res = y ? __fsub_rn(y2[b], a) : a;
-        if (fa.out) stg_stream(fa.out + oplane + o2, res);
-        sq += res * res;
-        ab += fabsf(res);
+#pragma unroll
+      for (int b = 0; b < kYB; ++b) {
+        const float a = ampf[kk + 32 * (it0 + b)];
+        if (act) {
+          const float res = y ? __fsub_rn(y1[b], a) : a;
+          if (fa.out) stg_stream(fa.out + oplane + o1[b], res);
+          sq += res * res;
+          ab += fabsf(res);
+        }
+        if (mir) {
+          const float res = y ? __fsub_rn(y2[b], a) : a;
+          if (fa.out) stg_stream(fa.out + oplane + o2[b], res);
+          sq += res * res;
+          ab += fabsf(res);
+        }
       }
     }
   }
@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(kThreads) phase_cols_adj(const AdjArgs aa, flo
   const float2* ph = aux_phase(aux_rw, n, C, c);
   // symmetrised cotangent (coalesced over the CTA's columns), staged as floats in s.b
   float* gs = reinterpret_cast<float*>(s.b);
-  batched_copy<kL * kColsAdj, 6>(
+  batched_copy<kL * kColsAdj, 12>(
       tid,
       [&](int i) {
         const int k1 = i / kColsAdj, f = i - k1 * kColsAdj;
@@ -387,7 +387,7 @@ __global__ void __launch_bounds__(kThreads) phase_cols_adj(const AdjArgs aa, flo
         gs[f * kLF + k1] = 0.5f * (g.x + g.y);
       });
   __syncthreads();
-  batched_copy<nfft * kL, 6>(
+  batched_copy<nfft * kL, 12>(
       tid,
       [&](int i) {
         const int f = i / kL, k1 = i - f * kL;
@@ -403,9 +403,10 @@ __global__ void __launch_bounds__(kThreads) phase_cols_adj(const AdjArgs aa, flo
   fft384_batch(s.a, s.b, s.tw, nfft);
   // T[row][k2] for padded rows 64..319 → image rows 0..255; row stride 193 complex
   float2* t = aux_scratch(aux_rw, n, C, c);
-  for (int i = tid; i < kImg * ncols; i += kThreads) {
-    const int row = i / ncols, f = i - row * ncols;
-    t[(int64_t)row * kHalf + k20 + f] = s.b[f * kLP + P(kPad + row)];
+#pragma unroll 4
+  for (int i = tid; i < kImg * kColsAdj; i += kThreads) {
+    const int row = i / kColsAdj, f = i - row * kColsAdj;
+    if (f < ncols) t[(int64_t)row * kHalf + k20 + f] = s.b[f * kLP + P(kPad + row)];
   }
 }
 
@@ -422,7 +423,7 @@ __global__ void __launch_bounds__(kThreads) phase_rows_adj(const AdjArgs aa, con
   stage_async(reinterpret_cast<float*>(s.tw), reinterpret_cast<const float*>(tw_g), 2 * kL, tid, kThreads);
   const float2* t = aux_scratch(const_cast<float*>(aux_r), n, C, c);
   // X[k] = T1[k] + i·T2[k] with T[384−k] = conj(T[k]) for k > 192
-  batched_copy<nfft * kL, 6>(
+  batched_copy<nfft * kL, 12>(
       tid,
       [&](int i) {
         const int f = i / kL, k = i - f * kL;
@@ -442,7 +443,7 @@ __global__ void __launch_bounds__(kThreads) phase_rows_adj(const AdjArgs aa, con
   const float coef = (aa.coef ? aa.coef[n] : 1.0f) * (1.0f / (float)kL);
   const int64_t plane = (int64_t)c * kImg * kImg;
   struct Epi { float4 e, pass; };
-  batched_copy<kRowsAdj * (kImg / 4), 4>(
+  batched_copy<kRowsAdj * (kImg / 4), 8>(
       tid,
       [&](int i) {
         const int rr = i / (kImg / 4), q = i - rr * (kImg / 4);

@@ -30,9 +30,10 @@ struct UpdateArgs {
   dps_step_consts k;
 };
 
-DPS_DEV float ddpm_sample(float x, float x0, float v, float z, const dps_step_consts& k) {
+DPS_DEV float ddpm_sample(float x, float e, float x0, float v, float z, const dps_step_consts& k) {
   // μ = p1·x̂₀ + p2·x                                       posterior_mean_variance.py:110-118
-  float mean = __fadd_rn(__fmul_rn(k.p1, x0), __fmul_rn(k.p2, x));
+  // μ = model output (previous_x processor)                 :62-65
+  float mean = k.mean_mode ? e : __fadd_rn(__fmul_rn(k.p1, x0), __fmul_rn(k.p2, x));
   if (!k.noise_on) return mean;  // gaussian_diffusion.py:473
   float logvar;
   if (k.var_mode == 0) {
@@ -98,7 +99,7 @@ __global__ void __launch_bounds__(kThreads) posterior_update_kernel(const Update
   {                                                                                   \
     const float x0 = x0_of(vx[u].c, ve[u].c, a.c1, a.c2, a.clip);                     \
     const float s = kDdim ? ddim_sample(vx[u].c, x0, vz[u].c, a.c1, a.c2, a.k)        \
-                          : ddpm_sample(vx[u].c, x0, vv[u].c, vz[u].c, a.k);          \
+                          : ddpm_sample(vx[u].c, ve[u].c, x0, vv[u].c, vz[u].c, a.k);          \
     /* ∇ₓ = c1·g − c2·VJP_ε(g)  (chain rule through c1·x − c2·ε(x), App. A.4) */      \
     const float grad = __fsub_rn(__fmul_rn(a.c1, vg[u].c), __fmul_rn(a.c2, vj[u].c)); \
     x0v.c = x0;                                                                       \

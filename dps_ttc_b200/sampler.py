@@ -113,9 +113,12 @@ class SpacedSampler:
 
     def __init__(self, use_timesteps, betas, model_mean_type, model_var_type, dynamic_threshold, clip_denoised,
                  rescale_timesteps):
-        if model_mean_type != "epsilon":
-            raise NotImplementedError(f"model_mean_type={model_mean_type!r}: the fused kernels cover the 'epsilon' "
-                                      "processor that configs/diffusion_config.yaml selects (SURVEY §8f row 4)")
+        if model_mean_type not in ("epsilon", "start_x", "previous_x"):
+            raise NameError(f"Name {model_mean_type} is not defined.")      # get_mean_processor's error
+        if model_mean_type != "epsilon" and self.kind == "ddim":
+            raise NotImplementedError("DDIM recovers ε with the epsilon processor's tables (gaussian_diffusion.py:506-509); "
+                                      f"model_mean_type={model_mean_type!r} is covered for the DDPM family only")
+        self.model_mean_type = model_mean_type
         if model_var_type not in self._VAR_MODES:
             raise NameError(f"Name {model_var_type} is not defined.")
         if dynamic_threshold:
@@ -139,6 +142,9 @@ class SpacedSampler:
     # -- helpers ----------------------------------------------------------------------------------
     def _idx(self, t) -> int:
         return int(t.reshape(-1)[0]) if torch.is_tensor(t) else int(t)
+
+    def _consts(self, idx: int):
+        return self.schedule.consts(idx, self.eta, self.model_mean_type)
 
     def _max_log(self, k):
         if self.model_var_type == "fixed_small":
@@ -171,7 +177,7 @@ class SpacedSampler:
     # -- reference API ----------------------------------------------------------------------------
     def q_sample(self, x_start, t):
         """gaussian_diffusion.py:134-151 (draws randn_like(x_start))."""
-        k = self.schedule.consts(self._idx(t))
+        k = self._consts(self._idx(t))
         noise = torch.randn_like(x_start)
         if x_start.is_cuda:
             return kernels.q_sample(x_start, noise, k.sqrt_acp, k.sqrt_1macp)
@@ -179,11 +185,11 @@ class SpacedSampler:
 
     def p_mean_variance(self, model, x, t):
         """gaussian_diffusion.py:308-330 — differentiable w.r.t. x through the model like the original."""
-        k = self.schedule.consts(self._idx(t))
+        k = self._consts(self._idx(t))
         _, eps, v = self._model_out(model, x, k)
         pre = k.c1 * x - k.c2 * eps
         x0 = pre.clamp(-1, 1) if self.clip_denoised else pre
-        mean = k.p1 * x0 + k.p2 * x
+        mean = eps if k.mean_mode else k.p1 * x0 + k.p2 * x      # previous_x: the model predicts the mean itself
         if self.var_mode == 0:
             frac = (v + 1.0) / 2.0
             logvar = frac * k.max_log + (1 - frac) * k.min_log
@@ -197,7 +203,7 @@ class SpacedSampler:
         """DDPM.p_sample / DDIM.p_sample (:468-509): returns {'sample', 'pred_xstart'}; pred_xstart stays
         connected to x for autograd-based conditioning, the sample comes from the fused kernel."""
         idx = self._idx(t)
-        k = self.schedule.consts(idx, self.eta)
+        k = self._consts(idx)
         out, eps, v = self._model_out(model, x, k)
         pre = k.c1 * x - k.c2 * eps
         x0 = pre.clamp(-1, 1) if self.clip_denoised else pre
@@ -221,7 +227,7 @@ class SpacedSampler:
     def guided_step(self, model, x, idx, measurement, method, spec: GuidanceSpec, cond_kwargs, noisy_measurement=None,
                     z=None):
         """One reverse step with measurement guidance.  Returns (x_next, meas_dist (N,), sem_dist or None)."""
-        k = self.schedule.consts(idx, self.eta)
+        k = self._consts(idx)
         op = method.operator
         x = x.detach().requires_grad_(True)
         with torch.enable_grad():
@@ -267,7 +273,7 @@ class SpacedSampler:
         img = img.detach().requires_grad_(True)
         with torch.enable_grad():
             out = self.p_sample(model=model, x=img, t=idx)   # draws z
-            k = self.schedule.consts(idx, self.eta)
+            k = self._consts(idx)
             q_noise = self.noise.q(idx, measurement)            # then the q_sample draw
             noisy_measurement = None if q_noise is None else kernels.q_sample(measurement, q_noise, k.sqrt_acp, k.sqrt_1macp)
             sample = out["sample"].clone()
@@ -309,7 +315,7 @@ class SpacedSampler:
         callback = kwargs.get("callback")
         meas_d = sem_d = None
         for idx in self._step_indices(kwargs):
-            k = self.schedule.consts(idx, self.eta)
+            k = self._consts(idx)
             t = idx / self.num_timesteps
             if fused:
                 anneal = anneal_factor(t, kwargs.get("anneal_amp", 1.0), kwargs.get("anneal_scale", 10.0),
@@ -338,7 +344,7 @@ class DDIM(SpacedSampler):
     kind = "ddim"
 
     def predict_eps_from_x_start(self, x_t, t, pred_xstart):
-        k = self.schedule.consts(self._idx(t))
+        k = self._consts(self._idx(t))
         return (k.c1 * x_t - pred_xstart) / k.c2
 
 
@@ -389,7 +395,7 @@ class SearchDDPM(DDPM):
         n = img.shape[0]
         self.last_stats = {"best": []}
         for idx in self._step_indices(kwargs):
-            k = self.schedule.consts(idx)
+            k = self._consts(idx)
             with torch.no_grad():
                 _, eps, v = self._model_out(model, img, k)
                 z = self.noise.z(idx, img)
@@ -424,7 +430,7 @@ class TTC_DDIM(DDIM):
         distance = None
         self.last_stats = {"ancestors": {}}
         for idx in self._step_indices(kwargs):
-            k = self.schedule.consts(idx, self.eta)
+            k = self._consts(idx)
             t = idx / self.num_timesteps
             sem_d = None
             if fused:

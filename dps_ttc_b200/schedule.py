@@ -12,6 +12,7 @@ so a step uploads nothing.
 """
 from __future__ import annotations
 
+import dataclasses
 import math
 from dataclasses import dataclass
 
@@ -80,6 +81,9 @@ class StepConsts:
     beta: float        # betas[idx] as python float (the loop's `beta_scale`, :225)
     model_t: float     # what the UNet receives: timestep_map[idx] * 1000/original_steps (:455-463)
     noise_on: int
+    mean_mode: int = 0  # 1: the model output IS the posterior mean (previous_x processor)
+    inv_p1: float = 0.0     # f32(1/posterior_mean_coef1[idx])      previous_x predict_xstart (:57-60)
+    p2_over_p1: float = 0.0  # f32(coef2[idx]/coef1[idx])
 
 
 class Schedule:
@@ -126,10 +130,26 @@ class Schedule:
         respacing = timestep_respacing if timestep_respacing else [steps]
         return cls(betas, space_timesteps(steps, respacing), rescale_timesteps)
 
-    def consts(self, idx: int, eta: float = 0.0) -> StepConsts:
-        key = (idx, eta)
+    def consts(self, idx: int, eta: float = 0.0, mean_type: str = "epsilon") -> StepConsts:
+        """Scalars of step `idx`.  `mean_type` selects the reference's mean processor
+        (posterior_mean_variance.py:45-129): every processor's x̂₀ is  c1·x − c2·out  with its own (c1, c2) —
+        epsilon: (√(1/ᾱ), √(1/ᾱ−1)); start_x: (0, −1), i.e. x̂₀ = out; previous_x: (−f32(p2/p1), −f32(1/p1)), and
+        there the posterior mean is the model output itself (mean_mode 1)."""
+        key = (idx, eta, mean_type)
         if key in self._cache:
             return self._cache[key]
+        if mean_type != "epsilon":
+            base = self.consts(idx, eta)
+            c1_64, c2_64 = self.posterior_mean_coef1[idx], self.posterior_mean_coef2[idx]
+            if mean_type == "start_x":
+                k = dataclasses.replace(base, c1=0.0, c2=-1.0)
+            elif mean_type == "previous_x":
+                inv_p1, ratio = float(np.float32(1.0 / c1_64)), float(np.float32(c2_64 / c1_64))
+                k = dataclasses.replace(base, c1=-ratio, c2=-inv_p1, mean_mode=1, inv_p1=inv_p1, p2_over_p1=ratio)
+            else:
+                raise NameError(f"Name {mean_type} is not defined.")
+            self._cache[key] = k
+            return k
         f32 = np.float32
         acp, acp_prev = f32(self.alphas_cumprod[idx]), f32(self.alphas_cumprod_prev[idx])
         # DDIM scalars in fp32, same operation order as gaussian_diffusion.py:488-498

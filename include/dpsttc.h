@@ -74,10 +74,16 @@ typedef struct dps_step_consts {
   float ddim_sigma; /* η·sqrt((1−ᾱ_prev)/(1−ᾱ))·sqrt(1−ᾱ/ᾱ_prev)   :488-492                     */
   int32_t noise_on; /* 0 at idx == 0 ("no noise when t == 0", :473, :501)                       */
   int32_t var_mode; /* 0 learned_range (:230-242)  1 fixed: log σ² = max_log  2 learned: log σ² = v */
+  int32_t mean_mode; /* 0: μ = p1·x̂₀ + p2·x (epsilon / start_x processors, :110-118, :86-92)
+                        1: μ = the model output itself (previous_x processor, :62-65)             */
 } dps_step_consts;
 
 /* x̂₀ alone (for callers that need the tensor: semantic embedder, pred_xstart output).
- * Replaces EpsilonXMeanProcessor.predict_xstart + process_xstart.                              */
+ * Replaces EpsilonXMeanProcessor.predict_xstart + process_xstart.  The other mean processors are the
+ * same expression with other scalars in dps_source, bit for bit:
+ *   start_x    (:86-92)  x̂₀ = out                         c1 = 0,              c2 = −1
+ *   previous_x (:57-65)  x̂₀ = out/p1 − (p2/p1)·x          c1 = −f32(p2/p1),    c2 = −f32(1/p1)
+ * (out = the model's first C channels, passed as `eps`); the guidance chain rule c1·g − c2·vjp holds as is. */
 int dps_x0_from_eps(const dps_source* src, float* x0, int n_particles, int64_t chw,
                     dps_stream_t stream);
 

@@ -87,9 +87,26 @@ def x0_from_eps(x, eps, k, clip=True):
     return (np.clip(pre, f32(-1), f32(1)) if clip else pre), pre
 
 
+def mean_consts(tables, idx, mean_type="epsilon"):
+    """Per-step scalars of the reference's three mean processors (posterior_mean_variance.py:45-129), all written
+    as x̂₀ = c1·x − c2·out:  epsilon (c1, c2) = (√(1/ᾱ), √(1/ᾱ−1));  start_x x̂₀ = out (:86-92);  previous_x
+    x̂₀ = f32(1/coef1)·out − f32(coef2/coef1)·x and the posterior mean is the model output (:57-65)."""
+    k = dict(tables.at(idx))
+    k["mean_is_output"] = False
+    if mean_type == "start_x":
+        k["c1"], k["c2"] = f32(0.0), f32(-1.0)
+    elif mean_type == "previous_x":
+        k["c1"] = -f32(tables.coef2[idx] / tables.coef1[idx])
+        k["c2"] = -f32(1.0 / tables.coef1[idx])
+        k["mean_is_output"] = True
+    elif mean_type != "epsilon":
+        raise NameError(mean_type)
+    return k
+
+
 def ddpm_sample(x, eps, v, z, k, idx, clip=True):
     x0, _ = x0_from_eps(x, eps, k, clip)
-    mean = k["p1"] * x0 + k["p2"] * x                     # q_posterior_mean :110-118
+    mean = eps if k.get("mean_is_output") else k["p1"] * x0 + k["p2"] * x   # q_posterior_mean :110-118 / :62-65
     if idx == 0:
         return mean, x0                                   # no noise when t == 0, gaussian_diffusion.py:473
     frac = (v + f32(1.0)) / f32(2.0)                      # learned_range :239

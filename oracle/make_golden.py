@@ -245,6 +245,42 @@ def gen_var_types():
     save("var_types.npz", **out)
 
 
+def gen_mean_types():
+    """DDPM.p_sample + the `ps` conditioning step with every mean processor (posterior_mean_variance.py:45-129):
+    sample, pred_xstart, the guided x_{t-1} and the distance, through the reference's own autograd chain."""
+    out = {}
+    g = torch.Generator().manual_seed(53)
+    x = torch.randn(2, 3, 32, 32, generator=g)
+    with _ref.quiet():
+        op = get_operator("gaussian_blur", kernel_size=61, intensity=3.0, device="cpu")
+        noiser = get_noise("gaussian", sigma=0.05)
+        cond = get_conditioning_method("ps", op, noiser, scale=0.3)
+    y = op.forward(torch.rand(1, 3, 32, 32, generator=g) * 2 - 1).detach()
+    out.update(x=x, y=y)
+    model = TinyEps(seed=53)
+    for mean_type in ("epsilon", "start_x", "previous_x"):
+        with _ref.quiet():
+            s = create_sampler(sampler="ddpm", timestep_respacing="", **{**DIFF, "model_mean_type": mean_type})
+        for idx in (999, 500, 1, 0):
+            tag = f"{mean_type}_{idx}"
+            if mean_type == "previous_x":
+                # the reference cannot differentiate this processor (p_sample's in-place `sample +=` hits a view of
+                # torch.split, gaussian_diffusion.py:474): only the unguided step exists upstream
+                with Recorder() as rec, _ref.quiet(), torch.no_grad():
+                    o = s.p_sample(model=model, x=x.clone(), t=torch.tensor([idx]))
+                out[f"{tag}_sample"], out[f"{tag}_x0"], out[f"{tag}_z"] = o["sample"], o["pred_xstart"], rec.randn[0]
+                continue
+            xi = x.clone().requires_grad_(True)
+            with Recorder() as rec, _ref.quiet():
+                o = s.p_sample(model=model, x=xi, t=torch.tensor([idx]))
+                sample = o["sample"].detach().clone()        # `ps` updates x_t in place (condition_methods.py:103)
+                res = cond.conditioning(x_t=o["sample"], measurement=y, noisy_measurement=None, x_prev=xi,
+                                        x_0_hat=o["pred_xstart"])
+            out[f"{tag}_sample"], out[f"{tag}_x0"], out[f"{tag}_z"] = sample, o["pred_xstart"], rec.randn[0]
+            out[f"{tag}_next"], out[f"{tag}_dist"] = res[0], res[1]
+    save("mean_types.npz", **out)
+
+
 def gen_resample_update():
     """SearchDDPM.resample_update (gaussian_diffusion.py:516-587) for every potential type."""
     out = {}
@@ -272,6 +308,7 @@ def gen_resample_update():
 
 if __name__ == "__main__":
     gen_var_types()
+    gen_mean_types()
     gen_resample_update()
     gen_schedule()
     gen_resizer()

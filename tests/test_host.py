@@ -108,8 +108,18 @@ def test_sampler_construction_and_errors():
                dynamic_threshold=False, clip_denoised=True, rescale_timesteps=True)
     s = create_sampler(sampler="ddpm", timestep_respacing="50", **cfg)
     assert s.num_timesteps == 50 and s.timestep_map[:3] == [0, 20, 41] and s.timestep_map[-1] == 999
+    sx = create_sampler(sampler="ddpm", **{**cfg, "model_mean_type": "start_x"})
+    k = sx._consts(500)
+    assert (k.c1, k.c2, k.mean_mode) == (0.0, -1.0, 0)                 # x̂₀ = model output
+    px = create_sampler(sampler="ddpm", **{**cfg, "model_mean_type": "previous_x"})
+    k, base = px._consts(500), px.schedule.consts(500)
+    assert k.mean_mode == 1 and k.c2 == -np.float32(1.0 / px.posterior_mean_coef1[500]) and k.p1 == base.p1
+    with pytest.raises(NameError):
+        create_sampler(sampler="ddpm", **{**cfg, "model_mean_type": "nope"})
     with pytest.raises(NotImplementedError):
-        create_sampler(sampler="ddpm", **{**cfg, "model_mean_type": "start_x"})
+        create_sampler(sampler="ddim", **{**cfg, "model_mean_type": "previous_x"})
+    with pytest.raises(NotImplementedError):
+        create_sampler(sampler="ddpm", **{**cfg, "dynamic_threshold": True})
     with pytest.raises(NameError):
         create_sampler(sampler="nope", **cfg)
     with pytest.raises(ValueError):

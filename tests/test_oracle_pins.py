@@ -141,6 +141,33 @@ def test_trace_ddpm_ps_semantic_gaussian_blur():
     assert np.abs(img - g["final"]).max() <= 1e-4
 
 
+@pytest.mark.parametrize("mean_type", ["epsilon", "start_x", "previous_x"])
+def test_mean_processors_restatement(mean_type):
+    """posterior_mean_variance.py:45-129: every mean processor as x̂₀ = c1·x − c2·out with its own scalars; the
+    guided x_{t-1} of `ps` through the chain rule c1·g − c2·VJP(g) (the reference's autograd)."""
+    g = golden("mean_types.npz")
+    T = O.Tables(1000)
+    model = TinyEps(seed=53)
+    from dps_ttc_b200.tables import gaussian_kernel
+    kern = gaussian_kernel(61, 3.0).astype(np.float32)
+    x, y = g["x"], g["y"]
+    for idx in (999, 500, 1, 0):
+        k = O.mean_consts(T, idx, mean_type)
+        out6, vjp = model_and_vjp(model, x, k["model_t"])
+        tag = f"{mean_type}_{idx}"
+        sample, x0 = O.ddpm_sample(x, out6[:, :3], out6[:, 3:], g[f"{tag}_z"], k, idx)
+        assert np.abs(x0 - g[f"{tag}_x0"]).max() == 0.0, tag                               # bit-exact
+        assert np.abs(sample - g[f"{tag}_sample"]).max() <= 2e-6 * max(1.0, np.abs(sample).max()), tag
+        if f"{tag}_next" not in g.files:
+            continue                       # previous_x: the reference cannot run its guided step (see make_golden.py)
+        _, pre = O.x0_from_eps(x, out6[:, :3], k)
+        r = y - O.blur_forward(x0, kern)
+        gpre, norm = O.guidance_cotangent(r, lambda u: O.blur_adjoint(u, kern), pre, "norm", 0.3)
+        nxt = O.guided_update(sample, gpre, vjp(gpre), k)
+        assert np.abs(norm - g[f"{tag}_dist"]).max() / norm.max() <= 1e-6, tag
+        assert np.abs(nxt - g[f"{tag}_next"]).max() <= 1e-5 * max(1.0, np.abs(nxt).max()), tag
+
+
 def test_trace_ttc_ddim_resampling_indices():
     g = golden("trace_ttc_ddim_mcg_sr.npz")
     i = 0
