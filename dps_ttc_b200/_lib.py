@@ -57,6 +57,8 @@ SIGNATURES = {
                                        _I, _L, _P]),
     "dps_posterior_update_ddim": (_I, [C.POINTER(Source), _P, _P, _L, _P, C.POINTER(StepConstsC), _P, _P, _P, _I, _L,
                                        _P]),
+    "dps_guidance_grad": (_I, [_P, _L, _P, _F, _F, _P, _I, _L, _P]),
+    "dps_apply_gradient": (_I, [_P, _P, _L, _P, _I, _L, _P]),
     "dps_q_sample": (_I, [_P, _P, _F, _F, _P, _L, _P]),
     "dps_operator_create_inpainting": (_I, [_P, _I, _I, _I, C.POINTER(_P)]),
     "dps_operator_create_blur": (_I, [_P, _I, _I, _I, _I, _I, C.POINTER(_P)]),

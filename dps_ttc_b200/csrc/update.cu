@@ -219,6 +219,63 @@ int launch_update(const dps_source* src, const float* v, int64_t v_stride, const
 
 }  // namespace
 
+namespace {
+// grad = c1·g − c2·vjp (kApply = false)   |   x' = sample − grad (kApply = true); b may be particle-broadcast
+template <bool kApply>
+__global__ void __launch_bounds__(kThreads) grad_kernel(const float* __restrict__ a, int64_t a_stride,
+                                                        const float* __restrict__ b, int64_t b_stride, float c1,
+                                                        float c2, float* __restrict__ out, int64_t chw4) {
+  const int n = blockIdx.y;
+  const float* ap = a + n * a_stride;
+  const float* bp = b ? b + n * b_stride : nullptr;
+  float* op = out + n * chw4 * 4;
+  const int64_t base4 = (int64_t)blockIdx.x * (kThreads * kVecPerThread) + threadIdx.x;
+  float4 va[kVecPerThread], vb[kVecPerThread];
+#pragma unroll
+  for (int u = 0; u < kVecPerThread; ++u) {
+    const int64_t i4 = base4 + (int64_t)u * kThreads;
+    va[u] = vb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i4 < chw4) {
+      va[u] = ldg_stream4(ap + i4 * 4);
+      if (bp) vb[u] = b_stride ? ldg_stream4(bp + i4 * 4) : ldg_ro4(bp + i4 * 4);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < kVecPerThread; ++u) {
+    const int64_t i4 = base4 + (int64_t)u * kThreads;
+    if (i4 >= chw4) continue;
+    float4 r;
+    if (kApply) {
+      r.x = __fsub_rn(va[u].x, vb[u].x); r.y = __fsub_rn(va[u].y, vb[u].y);
+      r.z = __fsub_rn(va[u].z, vb[u].z); r.w = __fsub_rn(va[u].w, vb[u].w);
+    } else {
+      r.x = __fsub_rn(__fmul_rn(c1, va[u].x), __fmul_rn(c2, vb[u].x));
+      r.y = __fsub_rn(__fmul_rn(c1, va[u].y), __fmul_rn(c2, vb[u].y));
+      r.z = __fsub_rn(__fmul_rn(c1, va[u].z), __fmul_rn(c2, vb[u].z));
+      r.w = __fsub_rn(__fmul_rn(c1, va[u].w), __fmul_rn(c2, vb[u].w));
+    }
+    stg_stream4(op + i4 * 4, r);
+  }
+}
+
+template <bool kApply>
+int launch_grad(const float* a, int64_t a_stride, const float* b, int64_t b_stride, float c1, float c2, float* out,
+                int n, int64_t chw, dps_stream_t stream, const char* who) {
+  DPS_REQUIRE(a && out && (b || !kApply), DPS_ERR_INVALID, "%s: null tensor", who);
+  DPS_REQUIRE(n > 0 && n <= 65535 && chw > 0 && chw % 4 == 0, DPS_ERR_INVALID, "%s: bad sizes", who);
+  DPS_REQUIRE(a_stride >= chw && a_stride % 4 == 0 && (b_stride == 0 || (b_stride >= chw && b_stride % 4 == 0)),
+              DPS_ERR_INVALID, "%s: bad particle strides", who);
+  DPS_REQUIRE(dps_aligned16(a) && dps_aligned16(out) && (!b || dps_aligned16(b)), DPS_ERR_ALIGN,
+              "%s: tensors must be 16-byte aligned", who);
+  const int64_t chw4 = chw / 4;
+  const int per_block = kThreads * kVecPerThread;
+  dim3 grid((unsigned)((chw4 + per_block - 1) / per_block), (unsigned)n);
+  grad_kernel<kApply><<<grid, kThreads, 0, (cudaStream_t)stream>>>(a, a_stride, b, b_stride, c1, c2, out, chw4);
+  DPS_LAUNCH_CHECK(who);
+  return DPS_OK;
+}
+}  // namespace
+
 extern "C" {
 
 int dps_x0_from_eps(const dps_source* src, float* x0, int n, int64_t chw, dps_stream_t stream) {
@@ -234,6 +291,17 @@ int dps_x0_from_eps(const dps_source* src, float* x0, int n, int64_t chw, dps_st
       src->x, src->eps, x0, src->x_stride, src->eps_stride, chw4, src->c1, src->c2, src->clip);
   DPS_LAUNCH_CHECK("dps_x0_from_eps");
   return DPS_OK;
+}
+
+
+int dps_guidance_grad(const float* g, int64_t g_stride, const float* vjp, float c1, float c2, float* grad, int n,
+                      int64_t chw, dps_stream_t stream) {
+  return launch_grad<false>(g, g_stride, vjp, chw, c1, c2, grad, n, chw, stream, "dps_guidance_grad");
+}
+
+int dps_apply_gradient(const float* sample, const float* grad, int64_t grad_stride, float* x_next, int n, int64_t chw,
+                       dps_stream_t stream) {
+  return launch_grad<true>(sample, chw, grad, grad_stride, 0.f, 0.f, x_next, n, chw, stream, "dps_apply_gradient");
 }
 
 int dps_posterior_update_ddpm(const dps_source* src, const float* v, int64_t v_stride,

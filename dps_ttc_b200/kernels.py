@@ -90,6 +90,33 @@ def posterior_update(sampler: str, x, eps, v, z, k, *, clip=True, g=None, vjp=No
     return x_next, sample, x0
 
 
+def guidance_grad(g, vjp, k, out=None):
+    """grad = c1·g − c2·vjp as a tensor (the chain rule the update kernel applies internally); `g` may be a
+    channel-slice view.  Used on DiffStateGrad projection steps (gaussian_diffusion.py:240-253)."""
+    n, chw = g.shape[0], _chw(g)
+    gp, gs = particle_view(g, "g")
+    if vjp is not None:
+        vjp = _lib.dense(vjp, "vjp")
+    out = torch.empty((n,) + tuple(g.shape[1:]), device=g.device, dtype=torch.float32) if out is None else out
+    check(lib().dps_guidance_grad(gp, gs, ptr(vjp), k.c1, k.c2, out.data_ptr(), n, chw, stream_ptr(g.device)),
+          "dps_guidance_grad")
+    return out
+
+
+def apply_gradient(sample, grad, out=None):
+    """x' = sample − grad; a gradient of batch 1 is applied to every particle (what the reference's projected
+    gradient does, gaussian_diffusion.py:255)."""
+    sample, grad = _lib.dense(sample, "sample"), _lib.dense(grad, "grad")
+    n, chw = sample.shape[0], _chw(sample)
+    if grad.shape[0] not in (1, n) or _chw(grad) != chw:
+        raise DpsError(f"grad {tuple(grad.shape)} does not match sample {tuple(sample.shape)}")
+    out = torch.empty_like(sample) if out is None else out
+    stride = 0 if (grad.shape[0] == 1 and n > 1) else chw
+    check(lib().dps_apply_gradient(sample.data_ptr(), grad.data_ptr(), stride, out.data_ptr(), n, chw,
+                                   stream_ptr(sample.device)), "dps_apply_gradient")
+    return out
+
+
 def q_sample(y, noise, a: float, b: float, out=None):
     y = _lib.dense(y, "y")
     noise = _lib.dense(noise, "noise")

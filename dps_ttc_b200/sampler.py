@@ -23,7 +23,7 @@ import functools
 
 import torch
 
-from . import kernels
+from . import diffstategrad, kernels
 from ._lib import DpsError
 from .conditioning import ConditioningMethod, GuidanceSpec
 from .operators import B200Operator
@@ -225,8 +225,10 @@ class SpacedSampler:
         return self._g6, self._g3
 
     def guided_step(self, model, x, idx, measurement, method, spec: GuidanceSpec, cond_kwargs, noisy_measurement=None,
-                    z=None):
-        """One reverse step with measurement guidance.  Returns (x_next, meas_dist (N,), sem_dist or None)."""
+                    z=None, dsg=False):
+        """One reverse step with measurement guidance.  Returns (x_next, meas_dist (N,), sem_dist or None).
+        `dsg`: DiffStateGrad projection step (gaussian_diffusion.py:240-255) — the gradient is materialised,
+        projected onto the sample's leading singular subspaces and applied to every particle."""
         k = self._consts(idx)
         op = method.operator
         x = x.detach().requires_grad_(True)
@@ -261,13 +263,18 @@ class SpacedSampler:
         # kernel 4: fused posterior update
         if z is None and self._needs_z(k):
             z = self.noise.z(idx, xd)
-        x_next, _, _ = kernels.posterior_update(self.kind, xd, eps_d, v_d, z, k, clip=self.clip_denoised, g=g, vjp=vjp,
-                                                var_mode=self.var_mode, max_log=self._max_log(k))
+        if dsg:
+            sample, _, _ = kernels.posterior_update(self.kind, xd, eps_d, v_d, z, k, clip=self.clip_denoised,
+                                                    var_mode=self.var_mode, max_log=self._max_log(k))
+            x_next = diffstategrad.projected_update(sample, kernels.guidance_grad(g, vjp, k))
+        else:
+            x_next, _, _ = kernels.posterior_update(self.kind, xd, eps_d, v_d, z, k, clip=self.clip_denoised, g=g,
+                                                    vjp=vjp, var_mode=self.var_mode, max_log=self._max_log(k))
         if spec.project:  # mcg: x_t = operator.project(x_t, noisy_measurement)
             x_next = method.project(data=x_next, noisy_measurement=noisy_measurement, **cond_kwargs)
         return x_next, dist, sem_dist
 
-    def _generic_step(self, model, img, idx, measurement, cond_fn, extra_kw):
+    def _generic_step(self, model, img, idx, measurement, cond_fn, extra_kw, dsg=False):
         """Foreign conditioning function (e.g. the reference's own class): autograd end to end, the
         x̂₀/sample arithmetic still fused.  Handles every return arity of HEAD."""
         img = img.detach().requires_grad_(True)
@@ -285,7 +292,10 @@ class SpacedSampler:
         third = res[2] if len(res) > 2 else None
         obj = getattr(getattr(cond_fn, "func", cond_fn), "__self__", None)
         returns_grad = type(obj).__name__ == "PosteriorSamplingSemanticGuid"
-        x_next = out["sample"] - first if returns_grad else first
+        if returns_grad and dsg:
+            x_next = diffstategrad.projected_update(out["sample"].detach(), first.detach().contiguous())
+        else:
+            x_next = out["sample"] - first if returns_grad else first
         return x_next.detach(), (dist.detach() if torch.is_tensor(dist) else dist), (third if returns_grad else None)
 
     def _step_indices(self, kwargs):
@@ -313,20 +323,23 @@ class SpacedSampler:
         fused = fused and kwargs.get("fused", True)   # fused=False forces the generic autograd path (debugging / tests)
         anneal_kw = {k_: kwargs[k_] for k_ in ("anneal_amp", "anneal_scale", "anneal_loc") if k_ in kwargs}
         callback = kwargs.get("callback")
+        # DiffStateGrad (gaussian_diffusion.py:203-204, :240-253): `project`, `period` as upstream
+        dsg_on, period = bool(kwargs.get("project", False)), int(kwargs.get("period", 20))
         meas_d = sem_d = None
         for idx in self._step_indices(kwargs):
             k = self._consts(idx)
             t = idx / self.num_timesteps
+            dsg = dsg_on and period != 0 and idx % period == 0
             if fused:
                 anneal = anneal_factor(t, kwargs.get("anneal_amp", 1.0), kwargs.get("anneal_scale", 10.0),
                                        kwargs.get("anneal_loc", 0.5)) if anneal_kw else 1.0
                 spec = method.guidance(beta_scale=k.beta, t=t, anneal=anneal)
                 z, q_noise = self._draws(idx, img, y, k, need_q=spec.project)
                 noisy = kernels.q_sample(y, q_noise, k.sqrt_acp, k.sqrt_1macp) if spec.project else None
-                img, meas_d, sem_d = self.guided_step(model, img, idx, y, method, spec, bound, noisy, z)
+                img, meas_d, sem_d = self.guided_step(model, img, idx, y, method, spec, bound, noisy, z, dsg=dsg)
             else:
                 img, meas_d, sem_d = self._generic_step(model, img, idx, y, measurement_cond_fn,
-                                                        {"beta_scale": k.beta, "t": t})
+                                                        {"beta_scale": k.beta, "t": t}, dsg=dsg)
             if callback is not None:
                 callback(idx, img, meas_d, sem_d)
         if sem_d is None:

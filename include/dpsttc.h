@@ -108,6 +108,16 @@ int dps_posterior_update_ddim(const dps_source* src, const float* z, const float
                               float* x_next, float* sample_out, float* x0_out, int n_particles,
                               int64_t chw, dps_stream_t stream);
 
+/* DiffStateGrad hook (gaussian_diffusion.py:240-255, diffstategrad_utils.py:46-78): on a projection step the loop
+ * needs the guidance gradient as a tensor, projects it (SVD of the sample: cuSOLVER/cuBLAS on the host side) and
+ * applies the projected gradient — which has batch 1 upstream — to every particle.
+ *   grad   = c1·g − c2·vjp                       the chain rule inside dps_posterior_update_*, materialised
+ *   x_next = sample − grad[n·grad_stride]         grad_stride = 0 broadcasts one gradient over all particles (:255) */
+int dps_guidance_grad(const float* g, int64_t g_stride, const float* vjp, float c1, float c2,
+                      float* grad, int n_particles, int64_t chw, dps_stream_t stream);
+int dps_apply_gradient(const float* sample, const float* grad, int64_t grad_stride, float* x_next,
+                       int n_particles, int64_t chw, dps_stream_t stream);
+
 /* q_sample (gaussian_diffusion.py:134-151): out = a·y + b·noise                                 */
 int dps_q_sample(const float* y, const float* noise, float a, float b, float* out, int64_t n_elems,
                  dps_stream_t stream);

@@ -329,6 +329,26 @@ def ancestors_systematic(cdf, u0, n, degenerate=False):
     return search(cdf, (np.arange(n, dtype=np.float64) + np.float64(u0)) / np.float64(n))
 
 
+# ------------------------------------------------------------------------------------------------
+# DiffStateGrad projection  (guided_diffusion/diffstategrad_utils.py; hook gaussian_diffusion.py:240-255)
+# ------------------------------------------------------------------------------------------------
+def diffstategrad_rank(singular_values, cutoff):
+    """compute_rank_for_explained_variance as called (:41): ONE (C, r) array in the list → flattened cumsum, then /3."""
+    sq = np.asarray(singular_values) ** 2
+    cum = np.cumsum(sq) / np.sum(sq)
+    return int((int(np.searchsorted(cum, cutoff)) + 1) / 3)
+
+
+def diffstategrad_update(sample, grad, cutoff=0.99):
+    """x' = sample − U_r U_rᵀ grad[0] V_r V_rᵀ per channel, SVD of sample[0]; the batch-1 result broadcasts (:255)."""
+    U, sv, Vh = np.linalg.svd(sample[0].astype(np.float32), full_matrices=False)
+    r = diffstategrad_rank(sv, cutoff)
+    A, B = U[:, :, :r], Vh[:, :r, :]
+    low = np.matmul(np.matmul(A.transpose(0, 2, 1), grad[0]), B.transpose(0, 2, 1))
+    proj = np.matmul(np.matmul(A, low), B).astype(np.float32)
+    return (sample - proj[None]).astype(np.float32), r
+
+
 def greedy_best(costs):
     return int(np.argmin(costs))                            # torch.argmin: first minimum (:631)
 

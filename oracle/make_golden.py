@@ -141,7 +141,7 @@ def gen_operators():
 
 
 def run_trace(tag, sampler_name, respacing, method, params, op_name, op_cfg, n, size, seed, use_loop=True, mask=None,
-              noise_sigma=0.05, anneal=False):
+              noise_sigma=0.05, anneal=False, loop_kwargs=None):
     """Run the reference's own loop (or an upstream-arity loop assembled from its classes) and record."""
     torch.manual_seed(seed)
     np.random.seed(seed)
@@ -171,6 +171,7 @@ def run_trace(tag, sampler_name, respacing, method, params, op_name, op_cfg, n, 
     with Recorder() as rec, _ref.quiet():
         if use_loop:
             extra = {"operator": op} if sampler_name == "search_ddpm" else {}
+            extra.update(loop_kwargs or {})
             result = s.p_sample_loop(model=model, x_start=x_start.clone(), measurement=y, measurement_cond_fn=cond_fn,
                                      record=False, save_root=None, **extra)
         else:
@@ -318,6 +319,10 @@ if __name__ == "__main__":
     # the combinations that run at HEAD …
     run_trace("ddpm_ps_semantic_gblur", "ddpm", "4", "ps_semantic", dict(scale=0.3, sem_guid_scale=0.0),
               "gaussian_blur", dict(kernel_size=61, intensity=3.0), n=2, size=32, seed=11)
+    # DiffStateGrad: projection at idx 2 and 0 of a 4-step chain (the loop prints; it is silenced by _ref.quiet)
+    run_trace("ddpm_ps_semantic_gblur_dsg", "ddpm", "4", "ps_semantic", dict(scale=0.3, sem_guid_scale=0.0),
+              "gaussian_blur", dict(kernel_size=61, intensity=3.0), n=2, size=32, seed=17,
+              loop_kwargs=dict(project=True, period=2))
     run_trace("ttc_ddim_mcg_sr", "ttc_ddim", "12", "mcg", dict(scale=0.5),
               "super_resolution", dict(in_shape=(1, 3, 32, 32), scale_factor=4), n=4, size=32, seed=12)
     run_trace("search_ddpm_gblur", "search_ddpm", "4", "ps", dict(scale=0.3),

@@ -69,6 +69,28 @@ def test_trace_ddpm_ps_semantic_gaussian_blur():
     assert close(img.cpu().numpy(), g["final"], 1e-4)
 
 
+@pytest.mark.parametrize("fused", [True, False])
+def test_trace_diffstategrad_projection(fused):
+    """§8f row 1: the reference loop with project=True, period=2 (projection at idx 2 and 0, particle 0's projected
+    gradient applied to both particles)."""
+    g = golden("trace_ddpm_ps_semantic_gblur_dsg.npz")
+    s, op, cond, dev = build("ddpm", "4", "ps_semantic", dict(scale=0.3, sem_guid_scale=0.0), "gaussian_blur",
+                             dict(kernel_size=61, intensity=3.0))
+    s.noise = tape_from(g, 4)
+    model = CpuBridge(TinyEps(seed=17))
+    seen = {}
+    img, dist, sem = s.p_sample_loop(model=model, x_start=torch.from_numpy(g["x_start"]).to(dev),
+                                     measurement=torch.from_numpy(g["y"]).to(dev),
+                                     measurement_cond_fn=cond.conditioning, record=False, save_root=None,
+                                     project=True, period=2, fused=fused,
+                                     callback=lambda idx, im, d, sd: seen.__setitem__(idx, (im.cpu().numpy(), d.cpu().numpy())))
+    for i, idx in enumerate(reversed(range(4))):
+        assert close(seen[idx][1], g[f"step{i}_dist"], 1e-5), f"distance at step {idx}"
+        if i < 3:
+            assert close(seen[idx][0], g[f"step{i + 1}_x_prev"], 1e-4), f"x after step {idx}"
+    assert close(img.cpu().numpy(), g["final"], 1e-4)
+
+
 def test_trace_ddpm_ps_inpainting_upstream_arity():
     g = golden("trace_ddpm_ps_inpaint.npz")
     s, op, cond, dev = build("ddpm", "4", "ps", dict(scale=0.5), "inpainting", {})

@@ -168,6 +168,23 @@ def test_mean_processors_restatement(mean_type):
         assert np.abs(nxt - g[f"{tag}_next"]).max() <= 1e-5 * max(1.0, np.abs(nxt).max()), tag
 
 
+def test_trace_diffstategrad_projection():
+    """Reference loop with project=True, period=2 on a 4-step chain: idx 2 and 0 subtract the projected gradient of
+    particle 0 from every particle, idx 3 and 1 the plain per-particle gradient."""
+    g = golden("trace_ddpm_ps_semantic_gblur_dsg.npz")
+    n_steps = int(g["n_steps"])
+    for i, idx in enumerate(reversed(range(n_steps))):
+        sample, grad = g[f"step{i}_sample"], g[f"step{i}_grad"]
+        nxt = g[f"step{i + 1}_x_prev"] if i + 1 < n_steps else g["final"]
+        if idx % 2 == 0:
+            mine, r = O.diffstategrad_update(sample, grad)
+            assert 1 <= r <= 32
+            assert np.abs(mine[1] - (sample[1] - (sample[0] - nxt[0]))).max() <= 1e-5     # particle 0's projection on particle 1
+        else:
+            mine = sample - grad
+        assert np.abs(mine - nxt).max() <= 1e-5 * max(1.0, np.abs(nxt).max()), idx
+
+
 def test_trace_ttc_ddim_resampling_indices():
     g = golden("trace_ttc_ddim_mcg_sr.npz")
     i = 0
