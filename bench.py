@@ -60,6 +60,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--channels-last", action="store_true", help="run the UNet module in NHWC memory format")
     ap.add_argument("--cudnn-benchmark", action="store_true", help="let cuDNN autotune its convolution algorithms")
+    ap.add_argument("--eager-unet", action="store_true",
+                    help="launch the UNet forward/VJP kernel by kernel instead of replaying them from CUDA graphs")
     return ap.parse_args()
 
 
@@ -307,7 +309,8 @@ def run_b200(args, rank, world, local_rank):
 
     def loop(x0, y, start, steps, **extra):
         return sampler.p_sample_loop(model=model, x_start=x0, measurement=y, measurement_cond_fn=cond_fn, record=False,
-                                     save_root=None, start_idx=start, num_steps=steps, **extra)
+                                     save_root=None, start_idx=start, num_steps=steps, graph_model=not args.eager_unet,
+                                     **extra)
 
     # ---------------- device-resident throughput (`value`) ----------------
     sampler.noise, sampler.parity_rng = TorchNoise(), False
@@ -411,7 +414,11 @@ def run_b200(args, rank, world, local_rank):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {desc}", "particles_per_gpu": n, "global_particles": n * world,
                        "image": "3x256x256", "chain": "ddpm 1000 steps, timed window idx %d..%d" % (999 - W, 999 - W - K + 1),
-                       "unet": model_name, "unet_math": "fp32 weights/activations; cuDNN conv TF32 = torch default "
+                       "unet": model_name,
+                       "unet_launch": "eager (kernel by kernel)" if args.eager_unet else
+                                      "the module's own forward and input-VJP kernels replayed from two CUDA graphs "
+                                      "(dps_ttc_b200/graphed.py; same kernels, same order)",
+                       "unet_math": "fp32 weights/activations; cuDNN conv TF32 = torch default "
                        f"({torch.backends.cudnn.allow_tf32}), matmul TF32 {torch.backends.cuda.matmul.allow_tf32}",
                        "parallelism": f"particle-sharded dp{world}, no data-path collective (best-of-N selects after the loop)",
                        "l2_policy": "inputs larger than L2: between two launches of any graft kernel the UNet forward+VJP "

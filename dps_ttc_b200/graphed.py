@@ -1,0 +1,93 @@
+"""CUDA-graph replay of the ε-model's forward and input-VJP for one fixed particle batch.
+
+The guided step runs the UNet forward, three graft kernels, the UNet VJP and the fused update.  At
+N = 8 particles the reference module issues ≈2 600 small kernels per step and the GPU idles between them; replaying
+the SAME kernels from two captured graphs (forward; backward w.r.t. the input only) removes those gaps (−7 % step time
+on a B200 at N = 8, `tools/graph_probe.py`) without touching the model: no kernel is replaced, skipped or reordered.
+
+    g = GraphedEps(model, x.shape, device)      # captures on first use
+    out = g.forward(x, model_t)                 # (N, C_out, H, W) static buffer: valid until the next forward()
+    ...kernels write the cotangent into g.cotangent[:, :C]...
+    vjp = g.vjp()                               # (N, C, H, W) static buffer
+
+The reference's `timestep_embedding` (guided_diffusion/nn.py:103-121) builds its frequency table on the CPU and copies
+it to the device on every call, which cannot be captured; `capturable_timestep_embedding` is the same arithmetic with
+the table cached on the device (bit-identical values) and is installed over the reference's module attribute.
+"""
+from __future__ import annotations
+
+import math
+import sys
+
+import torch
+
+from ._lib import DpsError
+
+_FREQS = {}
+
+
+def capturable_timestep_embedding(timesteps, dim, max_period=10000):
+    """guided_diffusion/nn.py:103-121 with the frequency table cached per device."""
+    key = (dim, max_period, timesteps.device)
+    if key not in _FREQS:
+        half = dim // 2
+        _FREQS[key] = torch.exp(-math.log(max_period) * torch.arange(start=0, end=half, dtype=torch.float32) / half
+                                ).to(device=timesteps.device)
+    args = timesteps[:, None].float() * _FREQS[key][None]
+    emb = torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
+    if dim % 2:
+        emb = torch.cat([emb, torch.zeros_like(emb[:, :1])], dim=-1)
+    return emb
+
+
+def make_reference_capturable():
+    """Re-bind the reference's timestep_embedding (if its modules are imported) to the capturable spelling."""
+    for name in ("guided_diffusion.nn", "guided_diffusion.unet"):
+        mod = sys.modules.get(name)
+        if mod is not None and hasattr(mod, "timestep_embedding"):
+            mod.timestep_embedding = capturable_timestep_embedding
+
+
+class GraphedEps:
+    def __init__(self, model, x_shape, device, warmup: int = 3):
+        if torch.device(device).type != "cuda":
+            raise DpsError("GraphedEps needs a CUDA device")
+        make_reference_capturable()
+        self.model = model
+        self.x = torch.zeros(x_shape, device=device, dtype=torch.float32).requires_grad_(True)
+        self.t = torch.zeros((1,), device=device, dtype=torch.float32)
+        side = torch.cuda.Stream(device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side), torch.enable_grad():
+            for _ in range(warmup):                                    # cuDNN plans, allocator warm-up
+                out = model(self.x, self.t)
+                cot = torch.zeros_like(out)
+                torch.autograd.grad(out, self.x, cot)
+        torch.cuda.current_stream(device).wait_stream(side)
+        torch.cuda.synchronize(device)
+        self.cotangent = torch.zeros(out.shape, device=device, dtype=torch.float32)   # [ε | v] cotangent, v half stays 0
+        del out, cot
+        self._fwd, self._bwd = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        pool = torch.cuda.graph_pool_handle()
+        try:
+            with torch.enable_grad():
+                with torch.cuda.graph(self._fwd, pool=pool):
+                    out = model(self.x, self.t)
+                    if not out.is_contiguous():
+                        out = out.contiguous()
+                with torch.cuda.graph(self._bwd, pool=pool):
+                    (vjp,) = torch.autograd.grad(out, self.x, self.cotangent)
+        except RuntimeError as e:
+            raise DpsError(f"the model's forward/backward cannot be captured in a CUDA graph: {e}") from e
+        self.out, self._vjp = out.detach(), vjp
+
+    def forward(self, x, model_t: float):
+        with torch.no_grad():
+            self.x.copy_(x)
+            self.t.fill_(model_t)
+        self._fwd.replay()
+        return self.out
+
+    def vjp(self):
+        self._bwd.replay()
+        return self._vjp

@@ -26,6 +26,7 @@ import torch
 from . import diffstategrad, kernels
 from ._lib import DpsError
 from .conditioning import ConditioningMethod, GuidanceSpec
+from .graphed import GraphedEps
 from .operators import B200Operator
 from .registry import get_sampler, register_sampler
 from .schedule import Schedule, anneal_factor, named_beta_schedule, space_timesteps
@@ -224,17 +225,31 @@ class SpacedSampler:
             self._g3 = torch.zeros((n, C, H, W), device=x.device, dtype=torch.float32)
         return self._g6, self._g3
 
+    def _graphed(self, model, x):
+        """The model's forward + input-VJP captured in CUDA graphs for this particle batch (graphed.GraphedEps)."""
+        key = (id(model), tuple(x.shape), x.device)
+        if getattr(self, "_graph_key", None) != key:
+            self._graph_key, self._graph = key, GraphedEps(model, tuple(x.shape), x.device)
+        return self._graph
+
     def guided_step(self, model, x, idx, measurement, method, spec: GuidanceSpec, cond_kwargs, noisy_measurement=None,
-                    z=None, dsg=False):
+                    z=None, dsg=False, graph_model=False):
         """One reverse step with measurement guidance.  Returns (x_next, meas_dist (N,), sem_dist or None).
         `dsg`: DiffStateGrad projection step (gaussian_diffusion.py:240-255) — the gradient is materialised,
         projected onto the sample's leading singular subspaces and applied to every particle."""
         k = self._consts(idx)
         op = method.operator
-        x = x.detach().requires_grad_(True)
-        with torch.enable_grad():
-            out, eps, v = self._model_out(model, x, k)
-        xd = x.detach()
+        gm = self._graphed(model, x) if graph_model else None
+        if gm is not None:
+            xd = x.detach()
+            out = gm.forward(xd, k.model_t)              # replayed forward graph; out is a static buffer
+            if out.shape[1] != 2 * x.shape[1] and self.var_mode in (0, 2):
+                raise DpsError(f"model_var_type={self.model_var_type} needs a model with 2·C output channels")
+        else:
+            x = x.detach().requires_grad_(True)
+            with torch.enable_grad():
+                out, eps, v = self._model_out(model, x, k)
+            xd = x.detach()
         out_d = out.detach()
         C = x.shape[1]
         eps_d = out_d[:, :C] if out_d.shape[1] == 2 * C else out_d
@@ -252,13 +267,18 @@ class SpacedSampler:
                 extra = torch.autograd.grad(sem_loss.sum(), x0)[0].contiguous()
             sem_dist = sem_dist.detach()
         # kernel 3: cotangent w.r.t. the pre-clamp x̂₀ written into the ε-channels of the cotangent buffer
-        g6, g3 = self._buffers(xd)
         two_c = out.shape[1] == 2 * C
-        g = g6[:, :C] if two_c else g3
+        if gm is not None:
+            g = gm.cotangent[:, :C] if two_c else gm.cotangent
+        else:
+            g6, g3 = self._buffers(xd)
+            g = g6[:, :C] if two_c else g3
         op.cotangent(r, coef, xd, eps_d, k, self.clip_denoised, extra, out=g, aux=aux, **cond_kwargs)
         # UNet VJP
         vjp = None
-        if out.requires_grad:
+        if gm is not None:
+            vjp = gm.vjp()                               # replayed backward graph (input gradient only)
+        elif out.requires_grad:
             vjp = torch.autograd.grad(out, x, grad_outputs=g6 if two_c else g3)[0]
         # kernel 4: fused posterior update
         if z is None and self._needs_z(k):
@@ -336,7 +356,8 @@ class SpacedSampler:
                 spec = method.guidance(beta_scale=k.beta, t=t, anneal=anneal)
                 z, q_noise = self._draws(idx, img, y, k, need_q=spec.project)
                 noisy = kernels.q_sample(y, q_noise, k.sqrt_acp, k.sqrt_1macp) if spec.project else None
-                img, meas_d, sem_d = self.guided_step(model, img, idx, y, method, spec, bound, noisy, z, dsg=dsg)
+                img, meas_d, sem_d = self.guided_step(model, img, idx, y, method, spec, bound, noisy, z, dsg=dsg,
+                                                      graph_model=bool(kwargs.get("graph_model", False)))
             else:
                 img, meas_d, sem_d = self._generic_step(model, img, idx, y, measurement_cond_fn,
                                                         {"beta_scale": k.beta, "t": t}, dsg=dsg)
@@ -450,7 +471,8 @@ class TTC_DDIM(DDIM):
                 spec = method.guidance(beta_scale=k.beta, t=t)
                 z, q_noise = self._draws(idx, img, y, k, need_q=spec.project)
                 noisy = kernels.q_sample(y, q_noise, k.sqrt_acp, k.sqrt_1macp) if spec.project else None
-                img, distance, sem_d = self.guided_step(model, img, idx, y, method, spec, bound, noisy, z)
+                img, distance, sem_d = self.guided_step(model, img, idx, y, method, spec, bound, noisy, z,
+                                                        graph_model=bool(kwargs.get("graph_model", False)))
             else:
                 img, distance, _ = self._generic_step(model, img, idx, y, measurement_cond_fn, {})
             n_local = img.shape[0]

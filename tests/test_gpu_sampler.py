@@ -91,6 +91,27 @@ def test_trace_diffstategrad_projection(fused):
     assert close(img.cpu().numpy(), g["final"], 1e-4)
 
 
+def test_graphed_model_equals_eager():
+    """graph_model=True replays the model's own forward / input-VJP kernels from CUDA graphs: same results."""
+    s, op, cond, dev = build("ddpm", "", "ps", dict(scale=0.3), "super_resolution",
+                             dict(in_shape=(1, 3, 256, 256), scale_factor=4))
+    model = TinyEps(seed=3).to(dev)
+    gen = torch.Generator().manual_seed(5)
+    x = torch.randn(3, 3, 256, 256, generator=gen).to(dev)
+    y = torch.randn(1, 3, 64, 64, generator=gen).to(dev)
+    z = {i: torch.randn(3, 3, 256, 256, generator=gen) for i in (999, 998, 997)}
+    outs = []
+    for graphed in (False, True):
+        from dps_ttc_b200.sampler import NoiseTape
+        s.noise, s.parity_rng = NoiseTape(z=z), False
+        img, dist, _ = s.p_sample_loop(model=model, x_start=x, measurement=y, measurement_cond_fn=cond.conditioning,
+                                       record=False, save_root=None, num_steps=3, graph_model=graphed)
+        outs.append((img.clone(), dist.clone()))
+    (a, da), (b, db) = outs
+    assert float((a - b).abs().max()) <= 1e-5 * max(1.0, float(a.abs().max()))
+    assert float((da - db).abs().max()) <= 1e-5 * float(da.abs().max())
+
+
 def test_trace_ddpm_ps_inpainting_upstream_arity():
     g = golden("trace_ddpm_ps_inpaint.npz")
     s, op, cond, dev = build("ddpm", "4", "ps", dict(scale=0.5), "inpainting", {})
