@@ -150,6 +150,37 @@ DPS_DEV void stage_wait() {  // the caller still needs __syncthreads() before ot
   asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
+// ---- bulk asynchronous copies (TMA engine, 1-D): global -> shared, completion on an mbarrier -------------------
+// One thread arms the barrier with the byte count and issues the copy; the bytes land without occupying registers or
+// LSU issue slots, so a CTA can have its whole input window in flight from its first instruction.
+DPS_DEV unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+DPS_DEV void mbar_init(uint64_t* bar, unsigned arrivals) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(arrivals) : "memory");
+}
+DPS_DEV void mbar_init_fence() {  // make the initialised barriers visible to the async proxy
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+DPS_DEV void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// dst, src 16-byte aligned, bytes a multiple of 16
+DPS_DEV void bulk_load(void* dst_smem, const void* src, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+DPS_DEV void mbar_wait(uint64_t* bar, unsigned parity) {
+  unsigned done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+
 DPS_DEV int reflect_idx(int i, int n) {  // ReflectionPad2d semantics (no edge repeat), |excursion| < n
   if (i < 0) i = -i;
   if (i >= n) i = 2 * (n - 1) - i;

@@ -279,6 +279,97 @@ __global__ void __launch_bounds__(128 * kParts, 3) resize_fwd_pair_kernel(const 
   fwd_wpass(m, t, C, W, oH, oW, strip, c, n, tid, kT, a, ypre);
 }
 
+// Bulk-copy variant for W = 256 (the default): the strip's input window is fetched by the TMA engine — 1-D bulk copies
+// of 8 image rows (8 KB per tensor, contiguous in a plane) into a 3-stage shared-memory ring, completion on mbarriers —
+// so 48 KB per CTA (144 KB per SM at 3 CTAs) are in flight without holding a register, and the threads only ever wait
+// on shared memory.  Compute is the pair kernel's: 128 column pairs × 2 row groups on packed FFMA2, then the W pass.
+constexpr int kCR = 8;      // rows per chunk
+constexpr int kStages = 3;  // chunks in flight
+
+__global__ void __launch_bounds__(256, 4) resize_fwd_bulk_kernel(const FwdTables t, int C, int H, int oH, int oW,
+                                                                 const FwdArgs a) {
+  constexpr int W = 256, W2 = 128, kT = 256, kParts = 2;
+  extern __shared__ __align__(128) float smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);  // kStages mbarriers in the first 128 bytes
+  float* ring = smem + 32;                             // (kStages, 2, kCR, W): x rows then ε rows of a chunk
+  FwdSmem m = fwd_carve(ring + kStages * 2 * kCR * W, t, 0, W, oW);
+  m.V = ring;  // the H-pass result (2, kRO, W) reuses the ring once every chunk has been consumed → 55 KB, 4 CTAs per SM
+  static_assert(kStages * 2 * kCR >= kParts * kRO, "V must fit in the ring");
+  const int strip = blockIdx.x % t.fstrips;
+  const int c = blockIdx.x / t.fstrips;
+  const int n = blockIdx.y;
+  const int tid = threadIdx.x;
+  const int rmin = t.rows.lo[strip], rcnt = t.rows.cnt[strip];
+  const int nchunks = (rcnt + kCR - 1) / kCR;
+  const int64_t plane = (int64_t)c * H * W;
+  const float* x = a.src.x + n * a.src.x_stride + plane + (int64_t)rmin * W;
+  const float* eps = a.src.eps ? a.src.eps + n * a.src.eps_stride + plane + (int64_t)rmin * W : nullptr;
+  auto issue = [&](int k) {  // one thread: arm the stage's barrier, start the copies of chunk k
+    const int stage = k % kStages;
+    const unsigned bytes = (unsigned)(min(kCR, rcnt - k * kCR) * W * sizeof(float));
+    float* dst = ring + stage * 2 * kCR * W;
+    mbar_expect_tx(&bars[stage], eps ? 2 * bytes : bytes);
+    bulk_load(dst, x + (int64_t)k * kCR * W, bytes, &bars[stage]);
+    if (eps) bulk_load(dst + kCR * W, eps + (int64_t)k * kCR * W, bytes, &bars[stage]);
+  };
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) mbar_init(&bars[s], 1);
+    mbar_init_fence();
+    for (int k = 0; k < min(kStages, nchunks); ++k) issue(k);
+  }
+  fwd_stage(m, t, strip, rcnt, oW, tid, kT);
+  const YPre ypre = fwd_y_prefetch(oH, oW, strip, c, n, tid, kT, a);
+  stage_wait();
+  __syncthreads();  // tables staged, barriers initialised
+  const int part = tid >> 7, cp = tid & 127;
+  float2 acc[kRO];
+#pragma unroll
+  for (int j = 0; j < kRO; ++j) acc[j] = make_float2(0.f, 0.f);
+#pragma unroll 1
+  for (int k = 0; k < nchunks; ++k) {
+    const int stage = k % kStages;
+    mbar_wait(&bars[stage], (unsigned)((k / kStages) & 1));
+    const float2* xs = reinterpret_cast<const float2*>(ring + stage * 2 * kCR * W);
+    const float2* es = xs + kCR * W2;
+    const int rows = min(kCR, rcnt - k * kCR);
+#pragma unroll
+    for (int q = 0; q < kCR / kParts; ++q) {  // row group `part` takes rows part·4 … part·4+3 of the chunk
+      const int rl = part * (kCR / kParts) + q;
+      if (rl < rows) {
+        const float2 xv = xs[rl * W2 + cp];
+        const float2 v = eps ? x0_pair(xv, es[rl * W2 + cp], a.src.c1, a.src.c2, a.src.clip) : xv;
+        const float* wr = m.dh + (k * kCR + rl) * kRO;
+        const float4 w0 = *reinterpret_cast<const float4*>(wr);
+        const float4 w1 = *reinterpret_cast<const float4*>(wr + 4);
+        acc[0] = __ffma2_rn(make_float2(w0.x, w0.x), v, acc[0]); acc[1] = __ffma2_rn(make_float2(w0.y, w0.y), v, acc[1]);
+        acc[2] = __ffma2_rn(make_float2(w0.z, w0.z), v, acc[2]); acc[3] = __ffma2_rn(make_float2(w0.w, w0.w), v, acc[3]);
+        acc[4] = __ffma2_rn(make_float2(w1.x, w1.x), v, acc[4]); acc[5] = __ffma2_rn(make_float2(w1.y, w1.y), v, acc[5]);
+        acc[6] = __ffma2_rn(make_float2(w1.z, w1.z), v, acc[6]); acc[7] = __ffma2_rn(make_float2(w1.w, w1.w), v, acc[7]);
+      }
+    }
+    if (k + kStages < nchunks) {  // recycle the stage: every thread has read it, then one thread refills it
+      __syncthreads();
+      if (tid == 0) issue(k + kStages);
+    }
+  }
+  __syncthreads();  // every chunk consumed: the ring becomes V
+  {
+    float* dstp = m.V + part * kRO * W;
+#pragma unroll
+    for (int j = 0; j < kRO; ++j) *reinterpret_cast<float2*>(dstp + j * W + 2 * cp) = acc[j];
+  }
+  __syncthreads();
+  for (int i = tid; i < kRO * W / 4; i += kT) {  // V[0] += V[1], fixed order
+    float4 s0 = *reinterpret_cast<const float4*>(m.V + i * 4);
+    const float4 s1 = *reinterpret_cast<const float4*>(m.V + kRO * W + i * 4);
+    s0.x += s1.x; s0.y += s1.y; s0.z += s1.z; s0.w += s1.w;
+    *reinterpret_cast<float4*>(m.V + i * 4) = s0;
+  }
+  __syncthreads();
+  fwd_wpass(m, t, C, W, oH, oW, strip, c, n, tid, kT, a, ypre);
+}
+
 // Adjoint.  RA input rows per CTA, KJ = the most measurement rows such a strip may touch.  Only the measurement
 // rows the strip touches are staged.  The clamp-mask / extra loads of the first row batch are issued before the
 // tiles are staged, so a CTA's dependent chain is one round trip.
@@ -546,11 +637,17 @@ int resize_forward(const dps_operator* op, const FwdArgs& a, cudaStream_t st) {
   if (!attr_set) {
     DPS_CUDA(cudaFuncSetAttribute(resize_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     DPS_CUDA(cudaFuncSetAttribute(resize_fwd_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DPS_CUDA(cudaFuncSetAttribute(resize_fwd_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   dim3 grid((unsigned)(op->C * f.fstrips), (unsigned)a.n);
   if (op->W == 256) {
-    resize_fwd_pair_kernel<2><<<grid, 256, fwd_smem(f, 2, 256, op->oW), st>>>(f, op->C, op->H, op->oH, op->oW, a);
+    static const bool pair_path = getenv("DPSTTC_RESIZE_FWD") && getenv("DPSTTC_RESIZE_FWD")[0] == 'p';  // A/B aid
+    if (pair_path)
+      resize_fwd_pair_kernel<2><<<grid, 256, fwd_smem(f, 2, 256, op->oW), st>>>(f, op->C, op->H, op->oH, op->oW, a);
+    else
+      resize_fwd_bulk_kernel<<<grid, 256, fwd_smem(f, 0, 256, op->oW) + sizeof(float) * (32 + kStages * 2 * kCR * 256), st>>>(
+          f, op->C, op->H, op->oH, op->oW, a);
   } else {
     resize_fwd_kernel<<<grid, kThreads, fwd_smem(f, 1, op->W, op->oW), st>>>(f, op->C, op->H, op->W, op->oH, op->oW, a);
   }
