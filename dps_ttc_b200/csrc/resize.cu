@@ -373,13 +373,19 @@ __global__ void __launch_bounds__(256, 4) resize_fwd_bulk_kernel(const FwdTables
 // Adjoint.  RA input rows per CTA, KJ = the most measurement rows such a strip may touch.  Only the measurement
 // rows the strip touches are staged.  The clamp-mask / extra loads of the first row batch are issued before the
 // tiles are staged, so a CTA's dependent chain is one round trip.
-template <int RA, int KJ, int KT>
+// kBulk: the clamp-mask sources (x, ε rows of the strip, contiguous in a plane) are fetched by the TMA engine into shared
+// memory in chunks of 8 rows, one mbarrier per chunk, all issued by one thread at kernel start — nothing is held in
+// registers and no load is on a thread's dependent path.
+template <int RA, int KJ, int KT, bool kBulk>
 __global__ void __launch_bounds__(kThreads, RA == kRAs ? 4 : 3) resize_adj_kernel(const AdjStrips at, const AdjCols ac, int C, int H, int W,
                                                               int oH, int oW, const AdjArgs a) {
-  extern __shared__ __align__(16) float smem[];
-  float* G = smem;                          // (KJ, oW): the measurement rows this strip touches
-  float* dht = G + ((KJ * oW + 3) & ~3);    // (RA, KJ), 16-byte aligned
-  float* wts = dht + RA * KJ;               // (kt, W): column weights, tap-major
+  extern __shared__ __align__(128) float smem[];
+  constexpr int kChunks = RA / 8;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);  // kBulk: kChunks mbarriers in the first 128 bytes
+  float* xs = smem + (kBulk ? 32 : 0);                  // kBulk: (RA, W) x rows, then (RA, W) ε rows
+  float* G = xs + (kBulk ? 2 * RA * W : 0);             // (KJ, oW): the measurement rows this strip touches
+  float* dht = G + ((KJ * oW + 3) & ~3);                // (RA, KJ), 16-byte aligned
+  float* wts = dht + RA * KJ;                           // (kt, W): column weights, tap-major
   const int strip = blockIdx.x % at.strips;
   const int c = blockIdx.x / at.strips;
   const int n = blockIdx.y;
@@ -392,7 +398,34 @@ __global__ void __launch_bounds__(kThreads, RA == kRAs ? 4 : 3) resize_adj_kerne
   const float* me = masked ? a.mask_src.eps + n * a.mask_src.eps_stride + plane : nullptr;
   const float* ex = a.extra ? a.extra + n * a.extra_stride + plane : nullptr;
   float xv[kB], ev[kB], xt[kB];
+  static_assert(kB == 8 && RA % 8 == 0 && kChunks <= 16, "one mbarrier per 8-row chunk");
+  if (kBulk && tid == 0) {
+#pragma unroll
+    for (int q = 0; q < kChunks; ++q) mbar_init(&bars[q], 1);
+    mbar_init_fence();
+    if (masked) {
+      for (int q = 0; q < kChunks; ++q) {
+        const int row0 = strip * RA + q * 8;
+        const int rows = min(8, H - row0);
+        if (rows <= 0) break;
+        const unsigned bytes = (unsigned)(rows * W * sizeof(float));
+        mbar_expect_tx(&bars[q], 2 * bytes);
+        bulk_load(xs + q * 8 * W, mx + (int64_t)row0 * W, bytes, &bars[q]);
+        bulk_load(xs + (RA + q * 8) * W, me + (int64_t)row0 * W, bytes, &bars[q]);
+      }
+    }
+  }
   auto load_batch = [&](int m, int i0) {
+    if (kBulk) {
+      if (masked && strip * RA + i0 < H) mbar_wait(&bars[i0 / 8], 0);
+#pragma unroll
+      for (int b = 0; b < kB; ++b) {
+        xv[b] = masked ? xs[(i0 + b) * W + m] : 0.f;  // rows past H hold stale shared memory; they are never stored
+        ev[b] = masked ? xs[(RA + i0 + b) * W + m] : 0.f;
+        xt[b] = ex ? ldg_stream(ex + (int64_t)min(strip * RA + i0 + b, H - 1) * W + m) : 0.f;
+      }
+      return;
+    }
 #pragma unroll
     for (int b = 0; b < kB; ++b) {
       const int row = min(strip * RA + i0 + b, H - 1);
@@ -402,7 +435,7 @@ __global__ void __launch_bounds__(kThreads, RA == kRAs ? 4 : 3) resize_adj_kerne
       xt[b] = ex ? ldg_stream(ex + off) : 0.f;
     }
   };
-  if (tid < W) load_batch(tid, 0);  // in flight while the tiles are staged
+  if (!kBulk && tid < W) load_batch(tid, 0);  // in flight while the tiles are staged
   stage_async(G, a.r + ((int64_t)n * C + c) * oH * oW + (int64_t)jmin * oW, jcnt * oW, tid, kThreads);
   stage_async(dht, at.dht + (int64_t)strip * RA * KJ, RA * KJ, tid, kThreads);
   stage_async(wts, ac.wtt, ac.kt * W, tid, kThreads);
@@ -434,7 +467,7 @@ __global__ void __launch_bounds__(kThreads, RA == kRAs ? 4 : 3) resize_adj_kerne
     // batch are loaded before any use
 #pragma unroll 1
     for (int i0 = 0; i0 < RA; i0 += kB) {
-      if (i0 != 0 || m != tid) load_batch(m, i0);
+      if (kBulk || i0 != 0 || m != tid) load_batch(m, i0);
 #pragma unroll
       for (int b = 0; b < kB; ++b) {
         const int row = strip * RA + i0 + b;
@@ -616,8 +649,9 @@ void resize_destroy(dps_operator* op) {
   op->resize = nullptr;
 }
 
-// The short-strip adjoint wins only while its own grid is about one wave (measured: 10.3 vs 12.2 µs at N = 8, but
-// 17.6 vs 15.8 µs at N = 16 and 120 vs 96 µs at N = 128 for 256² → 64²).
+// The short-strip adjoint (4x the CTAs, one 8-row chunk each) wins while the machine is not yet full of long strips —
+// measured with the bulk-copy kernels, 256² → 64²: 7.7 vs 10.1 µs at N = 8, 11.9 vs 15.0 at N = 16, 21.4 vs 25.2 at
+// N = 32, but 80.8 vs 75.5 µs at N = 128.
 static int variant_override() {  // DPSTTC_RESIZE_VARIANT=big|small pins the choice (profiling aid)
   static int v = -1;
   if (v < 0) {
@@ -628,7 +662,7 @@ static int variant_override() {  // DPSTTC_RESIZE_VARIANT=big|small pins the cho
 }
 static bool small_grid(int64_t ctas) {
   const int v = variant_override();
-  return v ? v == 2 : ctas <= 148 * 2;
+  return v ? v == 2 : ctas <= 148 * 10;
 }
 
 int resize_forward(const dps_operator* op, const FwdArgs& a, cudaStream_t st) {
@@ -660,12 +694,21 @@ static int launch_adj(const dps_operator* op, const AdjStrips& strips, const Adj
   const ResizeTables& t = *op->resize;
   static bool attr_set = false;
   if (!attr_set) {
-    DPS_CUDA(cudaFuncSetAttribute(resize_adj_kernel<RA, KJ, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DPS_CUDA(cudaFuncSetAttribute(resize_adj_kernel<RA, KJ, KT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DPS_CUDA(cudaFuncSetAttribute(resize_adj_kernel<RA, KJ, KT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   dim3 grid((unsigned)(op->C * strips.strips), (unsigned)a.n);
-  resize_adj_kernel<RA, KJ, KT><<<grid, kThreads, adj_smem(RA, KJ, op->oW, t.cols.kt, op->W), st>>>(
-      strips, t.cols, op->C, op->H, op->W, op->oH, op->oW, a);
+  const size_t base = adj_smem(RA, KJ, op->oW, t.cols.kt, op->W);
+  const size_t bulk = base + sizeof(float) * (32 + (size_t)2 * RA * op->W);
+  static const bool no_bulk = getenv("DPSTTC_RESIZE_ADJ") && getenv("DPSTTC_RESIZE_ADJ")[0] == 'r';  // A/B aid: "regs"
+  // bulk copies need 16-byte rows and a tile that still leaves 3 CTAs per SM
+  if (!no_bulk && op->W % 4 == 0 && bulk <= 75 * 1024)
+    resize_adj_kernel<RA, KJ, KT, true><<<grid, kThreads, bulk, st>>>(strips, t.cols, op->C, op->H, op->W, op->oH,
+                                                                      op->oW, a);
+  else
+    resize_adj_kernel<RA, KJ, KT, false><<<grid, kThreads, base, st>>>(strips, t.cols, op->C, op->H, op->W, op->oH,
+                                                                       op->oW, a);
   DPS_LAUNCH_CHECK("resize_adjoint");
   return DPS_OK;
 }
