@@ -67,15 +67,16 @@ class GraphedEps:
         torch.cuda.synchronize(device)
         self.cotangent = torch.zeros(out.shape, device=device, dtype=torch.float32)   # [ε | v] cotangent, v half stays 0
         del out, cot
+        # thread_local: other threads of the process (NCCL's watchdog polling its events) may call the CUDA API while we capture
         self._fwd, self._bwd = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
         pool = torch.cuda.graph_pool_handle()
         try:
             with torch.enable_grad():
-                with torch.cuda.graph(self._fwd, pool=pool):
+                with torch.cuda.graph(self._fwd, pool=pool, capture_error_mode="thread_local"):
                     out = model(self.x, self.t)
                     if not out.is_contiguous():
                         out = out.contiguous()
-                with torch.cuda.graph(self._bwd, pool=pool):
+                with torch.cuda.graph(self._bwd, pool=pool, capture_error_mode="thread_local"):
                     (vjp,) = torch.autograd.grad(out, self.x, self.cotangent)
         except RuntimeError as e:
             raise DpsError(f"the model's forward/backward cannot be captured in a CUDA graph: {e}") from e
