@@ -125,6 +125,26 @@ DPS_DEV void block_sum2(float& a, float& b, float* red) {
   __syncthreads();
 }
 
+// The same tree for `nw` warps that synchronise on named barrier `bar_id` (a subset of a CTA whose other warps do
+// something else, e.g. a TMA producer): bit-identical to block_sum2 of a CTA of nw warps.
+DPS_DEV void group_sum2(float& a, float& b, float* red, int nw, int bar_id) {
+  a = warp_sum(a);
+  b = warp_sum(b);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) {
+    red[warp] = a;
+    red[32 + warp] = b;
+  }
+  asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nw * 32) : "memory");
+  if (warp == 0) {
+    a = lane < nw ? red[lane] : 0.0f;
+    b = lane < nw ? red[32 + lane] : 0.0f;
+    a = warp_sum(a);
+    b = warp_sum(b);
+  }
+  asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nw * 32) : "memory");
+}
+
 // ---- asynchronous table staging (global -> shared, no registers, every request in flight at once) ------------
 // A plain "for (i = tid; …) smem[i] = table[i]" loop serialises one L2 round trip per iteration (the compiler cannot
 // hoist a generic-pointer load above the previous shared store); with N ≈ 8 particles and ≈1 CTA per SM those round
@@ -179,6 +199,27 @@ DPS_DEV void mbar_wait(uint64_t* bar, unsigned parity) {
         : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
   } while (!done);
+}
+
+// mbar_wait for producer/consumer pipelines: a protocol error traps (launch failure) instead of hanging the GPU
+DPS_DEV void mbar_wait_guarded(uint64_t* bar, unsigned parity) {
+  unsigned done, spins = 0;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (!done && ++spins > (1u << 22)) __trap();
+  } while (!done);
+}
+DPS_DEV void mbar_arrive(uint64_t* bar) {  // one plain arrival (consumer releasing a pipeline stage)
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// barrier among a subset of the CTA's warps (id 1..15; id 0 is __syncthreads), `count` threads, multiple of 32
+DPS_DEV void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+DPS_DEV void stg_stream2(float* p, const float2& v) {
+  asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(v.x), "f"(v.y));
 }
 
 DPS_DEV int reflect_idx(int i, int n) {  // ReflectionPad2d semantics (no edge repeat), |excursion| < n

@@ -50,6 +50,18 @@ struct FwdTables {
   float* wwt = nullptr;   // (kw, out_w) tap-major: A_w[j][cstart[j] + k]
 };
 
+// Streaming forward (resize_fwd_stream_kernel): input rows arrive in absolute 8-row chunks; chunk Q feeds the output rows
+// jb(Q) … jb(Q)+kWO−1 with jb(Q) = D·Q − B, and the rows jb(Q) … jb(Q)+D−1 are complete once chunk Q has been added.
+constexpr int kWO = 6;              // sliding window of output-row accumulators
+constexpr int kStripsPerUnit = 4;   // a work unit = 4 output strips (32 measurement rows) of one plane
+struct FwdStream {
+  int ok = 0;
+  int D = 0, B = 0;
+  int upp = 0;              // units per plane
+  short q_lo[8], q_hi[8];   // chunk range of every unit of a plane (q_hi may be a virtual chunk past the image: flush only)
+  float* wq = nullptr;      // (H, kWO): weight of input row r for output row jb(r/8)+t
+};
+
 struct AdjStrips {
   int strips = 0;         // ceil(H / RA); 0: variant not available
   StripMeta rows;         // measurement-row window of every strip
@@ -64,6 +76,7 @@ struct AdjCols {
 
 struct ResizeTables {
   FwdTables f;
+  FwdStream fs;
   AdjStrips big;    // strips of kRA rows, ≤ kJMax measurement rows each
   AdjStrips small;  // strips of kRAs rows, ≤ kJs measurement rows each
   AdjCols cols;
@@ -113,8 +126,10 @@ DPS_DEV YPre fwd_y_prefetch(int oH, int oW, int strip, int c, int n, int tid, in
 }
 
 // W pass + residual + Σr², Σ|r| from the (kRO, W) tile V
+// `slot`: the strip's partial-sum slot c·fstrips + strip.  `bar_id` 0: the whole CTA takes part (block_sum2); else the
+// nt threads of named barrier `bar_id` (the consumers of the streaming kernel) — same tree, same bits.
 DPS_DEV void fwd_wpass(const FwdSmem& m, const FwdTables& t, int C, int W, int oH, int oW, int strip, int c, int n,
-                       int tid, int nt, const FwdArgs& a, const YPre& ypre) {
+                       int tid, int nt, const FwdArgs& a, const YPre& ypre, int slot, int bar_id) {
   float sq = 0.f, ab = 0.f;
   const int64_t oplane = ((int64_t)n * C + c) * oH * oW;
   const float* yp = a.y ? a.y + n * a.y_stride + (int64_t)c * oH * oW : nullptr;
@@ -138,12 +153,15 @@ DPS_DEV void fwd_wpass(const FwdSmem& m, const FwdTables& t, int C, int W, int o
     if (tid + u * nt < kRO * oW) one(tid + u * nt, true, ypre.v[u]);
   for (int i = tid + kYPre * nt; i < kRO * oW; i += nt) one(i, false, 0.f);
   if (a.partials) {
-    block_sum2(sq, ab, m.red);
+    if (bar_id == 0) block_sum2(sq, ab, m.red);
+    else group_sum2(sq, ab, m.red, nt / 32, bar_id);
     if (tid == 0) {
-      float* pp = a.partials + ((int64_t)n * (C * t.fstrips) + blockIdx.x) * 2;
+      float* pp = a.partials + ((int64_t)n * (C * t.fstrips) + slot) * 2;
       pp[0] = sq;
       pp[1] = ab;
     }
+  } else if (bar_id != 0) {
+    named_bar_sync(bar_id, nt);
   }
 }
 
@@ -198,7 +216,7 @@ __global__ void __launch_bounds__(kThreads) resize_fwd_kernel(const FwdTables t,
     for (int j = 0; j < kRO; ++j) m.V[j * W + col] = acc[j];
   }
   __syncthreads();
-  fwd_wpass(m, t, C, W, oH, oW, strip, c, n, tid, kThreads, a, ypre);
+  fwd_wpass(m, t, C, W, oH, oW, strip, c, n, tid, kThreads, a, ypre, blockIdx.x, 0);
 }
 
 // Pair variant for W = 256: 128 column pairs × kParts row groups.  64-bit loads, x̂₀ and the accumulation on
@@ -276,13 +294,15 @@ __global__ void __launch_bounds__(128 * kParts, 3) resize_fwd_pair_kernel(const 
     *reinterpret_cast<float4*>(m.V + i * 4) = s0;
   }
   __syncthreads();
-  fwd_wpass(m, t, C, W, oH, oW, strip, c, n, tid, kT, a, ypre);
+  fwd_wpass(m, t, C, W, oH, oW, strip, c, n, tid, kT, a, ypre, blockIdx.x, 0);
 }
 
 // Bulk-copy variant for W = 256 (the default): the strip's input window is fetched by the TMA engine — 1-D bulk copies
 // of 8 image rows (8 KB per tensor, contiguous in a plane) into a 3-stage shared-memory ring, completion on mbarriers —
 // so 48 KB per CTA (144 KB per SM at 3 CTAs) are in flight without holding a register, and the threads only ever wait
 // on shared memory.  Compute is the pair kernel's: 128 column pairs × 2 row groups on packed FFMA2, then the W pass.
+constexpr int kSaStages = 6;          // streaming adjoint: ring stages
+constexpr int kSaThreads = 256 + 32;  // streaming kernels: 256 consumers + one producer warp
 constexpr int kCR = 8;      // rows per chunk
 constexpr int kStages = 3;  // chunks in flight
 
@@ -367,7 +387,129 @@ __global__ void __launch_bounds__(256, 4) resize_fwd_bulk_kernel(const FwdTables
     *reinterpret_cast<float4*>(m.V + i * 4) = s0;
   }
   __syncthreads();
-  fwd_wpass(m, t, C, W, oH, oW, strip, c, n, tid, kT, a, ypre);
+  fwd_wpass(m, t, C, W, oH, oW, strip, c, n, tid, kT, a, ypre, blockIdx.x, 0);
+}
+
+// Streaming forward for full machines (W = 256; ×4 and ×8 bicubic): persistent CTAs, one producer warp + 256 consumers.
+// A work unit is 4 consecutive output strips of one plane; its input rows are streamed ONCE, in absolute 8-row chunks,
+// through a ring of kSfStages TMA stages (x rows | ε rows), so the 1.5× halo re-read of the strip kernels disappears and
+// loads never pause for a W pass.  Consumers (128 column pairs × 2 row halves) keep a sliding window of kWO output-row
+// accumulators: chunk Q adds to rows jb(Q)…jb(Q)+5, after which the first D of them are complete and go to the V tile;
+// every 8 completed rows the strip's W pass, residual and partial sums run exactly as in the strip kernels.
+// Bit-identity with resize_fwd_bulk_kernel: both split the rows of a chunk into the same halves (chunks are aligned to
+// absolute multiples of 8 in both), add them in ascending order, and share fwd_wpass and the reduction tree.
+constexpr int kSfStages = 5;
+
+template <int D>
+__global__ void __launch_bounds__(kSaThreads, 2) resize_fwd_stream_kernel(const FwdTables t, const FwdStream fs, int C, int H,
+                                                                            int oH, int oW, int units, const FwdArgs a) {
+  constexpr int W = 256, W2 = 128, kStageFloats = 2 * 8 * W;
+  extern __shared__ __align__(128) float smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* empty = full + kSfStages;
+  static_assert(2 * kSfStages <= 16, "barriers must fit in the first 128 bytes");
+  float* ring = smem + 32;
+  FwdSmem m;
+  m.dh = nullptr;
+  m.V = ring + kSfStages * kStageFloats;  // (2, kRO, W)
+  float* wq = m.V + 2 * kRO * W;          // (H, kWO)
+  m.red = wq + H * kWO;
+  m.wws = m.red + 64;
+  m.css = reinterpret_cast<int*>(m.wws + ((t.kw * oW + 3) & ~3));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kSfStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 8); }
+    mbar_init_fence();
+  }
+  stage_async(wq, fs.wq, H * kWO, tid, kSaThreads);
+  stage_async(m.wws, t.wwt, t.kw * oW, tid, kSaThreads);
+  stage_async(reinterpret_cast<float*>(m.css), reinterpret_cast<const float*>(t.cstart), oW, tid, kSaThreads);
+  stage_wait();
+  __syncthreads();
+  const int upp = fs.upp, nchunks = H / 8;
+  const bool has_eps = a.src.eps != nullptr;
+
+  if (warp == 8) {  // ---------------- producer ----------------
+    if (lane != 0) return;
+    int it = 0;
+    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+      const int k = u % upp, c = (u / upp) % C, n = u / (upp * C);
+      const int64_t plane = (int64_t)c * H * W;
+      const float* x = a.src.x + n * a.src.x_stride + plane;
+      const float* eps = has_eps ? a.src.eps + n * a.src.eps_stride + plane : nullptr;
+      const int q1 = min((int)fs.q_hi[k], nchunks - 1);
+#pragma unroll 1
+      for (int Q = fs.q_lo[k]; Q <= q1; ++Q, ++it) {
+        const int s = it % kSfStages;
+        mbar_wait_guarded(&empty[s], (unsigned)(((it / kSfStages) & 1) ^ 1));
+        float* dst = ring + s * kStageFloats;
+        const unsigned bytes = 8 * W * sizeof(float);
+        mbar_expect_tx(&full[s], has_eps ? 2 * bytes : bytes);
+        bulk_load(dst, x + (int64_t)Q * 8 * W, bytes, &full[s]);
+        if (has_eps) bulk_load(dst + 8 * W, eps + (int64_t)Q * 8 * W, bytes, &full[s]);
+      }
+    }
+    return;
+  }
+
+  // ---------------- consumers ----------------
+  const int half = tid >> 7, cp = tid & 127;
+  int it = 0;
+  for (int u = blockIdx.x; u < units; u += gridDim.x) {
+    const int k = u % upp, c = (u / upp) % C, n = u / (upp * C);
+    const int j_lo = k * kStripsPerUnit * kRO, j_hi = min(oH, j_lo + kStripsPerUnit * kRO);
+    float2 acc[kWO];
+#pragma unroll
+    for (int tt = 0; tt < kWO; ++tt) acc[tt] = make_float2(0.f, 0.f);
+    YPre ypre = fwd_y_prefetch(oH, oW, j_lo / kRO, c, n, tid, 256, a);
+#pragma unroll 1
+    for (int Q = fs.q_lo[k]; Q <= fs.q_hi[k]; ++Q) {
+      if (Q < nchunks) {
+        const int s = it % kSfStages;
+        mbar_wait_guarded(&full[s], (unsigned)((it / kSfStages) & 1));
+        const float2* xs = reinterpret_cast<const float2*>(ring + s * kStageFloats);
+        const float2* es = xs + 8 * W2;
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+          const int rl = half * 4 + rr;
+          const float2 xv = xs[rl * W2 + cp];
+          const float2 v = has_eps ? x0_pair(xv, es[rl * W2 + cp], a.src.c1, a.src.c2, a.src.clip) : xv;
+          const float2* wr = reinterpret_cast<const float2*>(wq + (Q * 8 + rl) * kWO);
+          const float2 wa = wr[0], wb = wr[1], wc = wr[2];
+          acc[0] = __ffma2_rn(make_float2(wa.x, wa.x), v, acc[0]); acc[1] = __ffma2_rn(make_float2(wa.y, wa.y), v, acc[1]);
+          acc[2] = __ffma2_rn(make_float2(wb.x, wb.x), v, acc[2]); acc[3] = __ffma2_rn(make_float2(wb.y, wb.y), v, acc[3]);
+          acc[4] = __ffma2_rn(make_float2(wc.x, wc.x), v, acc[4]); acc[5] = __ffma2_rn(make_float2(wc.y, wc.y), v, acc[5]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+        ++it;
+      }
+      // rows jb … jb+D−1 are complete: into the V tile of their strip (row-half `half` of the sum)
+      const int jb = D * Q - fs.B;
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        const int j = jb + d;
+        if (j >= j_lo && j < j_hi) *reinterpret_cast<float2*>(m.V + (half * kRO + (j & (kRO - 1))) * W + 2 * cp) = acc[d];
+      }
+#pragma unroll
+      for (int tt = 0; tt < kWO; ++tt) acc[tt] = tt + D < kWO ? acc[tt + D] : make_float2(0.f, 0.f);
+      const int j_last = jb + D - 1;
+      if (j_last >= j_lo && j_last < j_hi && (j_last & (kRO - 1)) == kRO - 1) {  // a strip is complete
+        const int strip = j_last / kRO;
+        named_bar_sync(1, 256);
+        for (int i = tid; i < kRO * W / 4; i += 256) {  // V[0] += V[1], fixed order
+          float4 s0 = *reinterpret_cast<const float4*>(m.V + i * 4);
+          const float4 s1 = *reinterpret_cast<const float4*>(m.V + kRO * W + i * 4);
+          s0.x += s1.x; s0.y += s1.y; s0.z += s1.z; s0.w += s1.w;
+          *reinterpret_cast<float4*>(m.V + i * 4) = s0;
+        }
+        named_bar_sync(1, 256);
+        fwd_wpass(m, t, C, W, oH, oW, strip, c, n, tid, 256, a, ypre, c * t.fstrips + strip, 1);
+        if (strip + 1 < (j_hi + kRO - 1) / kRO) ypre = fwd_y_prefetch(oH, oW, strip + 1, c, n, tid, 256, a);
+      }
+    }
+  }
 }
 
 // Adjoint.  RA input rows per CTA, KJ = the most measurement rows such a strip may touch.  Only the measurement
@@ -489,6 +631,149 @@ __global__ void __launch_bounds__(kThreads, RA == kRAs ? 4 : 3) resize_adj_kerne
   }
 }
 
+// Streaming adjoint for full machines (W = 256, H a multiple of 32, clamp mask on): persistent CTAs, one producer warp
+// and 256 consumer threads.  The producer walks the CTA's work list — units (particle, channel, 32-row strip), round
+// robin over the grid — and keeps a ring of kSaStages 8-row chunks of the clamp-mask sources (x rows | ε rows, 16 KB per
+// stage) plus the NEXT unit's header (its measurement rows and its A_hᵀ block) in flight through the TMA engine, gated by
+// full/empty mbarriers, so loads never stop for a CTA's compute or store phase.  Consumers: 128 column pairs × 2 row
+// halves; E = G·A_w in registers per unit, then 12-16 packed FFMA2 per output row pair element, the clamp mask from the
+// ring, one 64-bit streaming store per row.  Arithmetic (order of every fma chain) is that of resize_adj_kernel:
+// the result is bit-identical to the strip kernels', whichever variant a launch picks.
+template <int KJ, int KT>
+__global__ void __launch_bounds__(kSaThreads, 2) resize_adj_stream_kernel(const AdjStrips at, const AdjCols ac, int C, int H,
+                                                                            int oH, int oW, int units, const AdjArgs a) {
+  constexpr int W = 256, W2 = 128, RA = kRA, kChunks = RA / 8;
+  constexpr int kStageFloats = 2 * 8 * W;
+  extern __shared__ __align__(128) float smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);  // [kSaStages]
+  uint64_t* empty = full + kSaStages;                  // [kSaStages]
+  uint64_t* hfull = empty + kSaStages;                 // [2]
+  uint64_t* hempty = hfull + 2;                        // [2]   → 2·kSaStages + 4 ≤ 16 barriers = 128 bytes
+  static_assert(2 * kSaStages + 4 <= 16, "barriers must fit in the first 128 bytes");
+  float* ring = smem + 32;
+  const int hdr_floats = KJ * oW + RA * KJ;  // [G: (KJ, oW) | dht: (RA, KJ)], both multiples of 4 floats
+  float* hdr = ring + kSaStages * kStageFloats;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kSaStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 8); }
+    mbar_init(&hfull[0], 1); mbar_init(&hfull[1], 1);
+    mbar_init(&hempty[0], 8); mbar_init(&hempty[1], 8);
+    mbar_init_fence();
+  }
+  __syncthreads();
+  const int strips = at.strips;
+  const int64_t chw = (int64_t)C * H * W;
+
+  if (warp == 8) {  // ---------------- producer ----------------
+    if (lane != 0) return;
+    int it = 0, hu = 0;
+    for (int u = blockIdx.x; u < units; u += gridDim.x, ++hu) {
+      const int strip = u % strips, c = (u / strips) % C, n = u / (strips * C);
+      const int hs = hu & 1;
+      const int jmin = at.rows.lo[strip], jcnt = at.rows.cnt[strip];
+      mbar_wait_guarded(&hempty[hs], (unsigned)(((hu >> 1) & 1) ^ 1));
+      float* hb = hdr + hs * hdr_floats;
+      const unsigned bytes_g = (unsigned)(jcnt * oW * sizeof(float)), bytes_d = (unsigned)(RA * KJ * sizeof(float));
+      mbar_expect_tx(&hfull[hs], bytes_g + bytes_d);
+      bulk_load(hb, a.r + (((int64_t)n * C + c) * oH + jmin) * oW, bytes_g, &hfull[hs]);
+      bulk_load(hb + KJ * oW, at.dht + (int64_t)strip * RA * KJ, bytes_d, &hfull[hs]);
+      const int64_t base = (int64_t)c * H * W + (int64_t)strip * RA * W;
+      const float* mx = a.mask_src.x + n * a.mask_src.x_stride + base;
+      const float* me = a.mask_src.eps + n * a.mask_src.eps_stride + base;
+#pragma unroll 1
+      for (int q = 0; q < kChunks; ++q, ++it) {
+        const int s = it % kSaStages;
+        mbar_wait_guarded(&empty[s], (unsigned)(((it / kSaStages) & 1) ^ 1));
+        float* dst = ring + s * kStageFloats;
+        mbar_expect_tx(&full[s], (unsigned)(kStageFloats * sizeof(float)));
+        bulk_load(dst, mx + q * 8 * W, 8 * W * sizeof(float), &full[s]);
+        bulk_load(dst + 8 * W, me + q * 8 * W, 8 * W * sizeof(float), &full[s]);
+      }
+    }
+    return;
+  }
+
+  // ---------------- consumers ----------------
+  const int half = tid >> 7, cp = tid & 127;
+  float w0[KT], w1[KT];
+  int i0[KT], i1[KT];
+  {
+    const int js0 = ac.jstart[2 * cp], js1 = ac.jstart[2 * cp + 1];
+#pragma unroll
+    for (int k = 0; k < KT; ++k) {
+      const bool v0 = k < ac.kt && js0 + k < oW, v1 = k < ac.kt && js1 + k < oW;
+      w0[k] = v0 ? ac.wtt[k * W + 2 * cp] : 0.f;
+      w1[k] = v1 ? ac.wtt[k * W + 2 * cp + 1] : 0.f;
+      i0[k] = min(js0 + k, oW - 1);
+      i1[k] = min(js1 + k, oW - 1);
+    }
+  }
+  const float c1 = a.mask_src.c1, c2 = a.mask_src.c2;
+  int it = 0, hu = 0;
+  for (int u = blockIdx.x; u < units; u += gridDim.x, ++hu) {
+    const int strip = u % strips, c = (u / strips) % C, n = u / (strips * C);
+    const int hs = hu & 1;
+    const int jcnt = at.rows.cnt[strip];
+    const float coef = a.coef ? a.coef[n] : 1.0f;
+    const int64_t plane = (int64_t)c * H * W;
+    const float* ex = a.extra ? a.extra + n * a.extra_stride + plane : nullptr;
+    float* gout = a.g + n * a.g_stride + plane;
+    mbar_wait_guarded(&hfull[hs], (unsigned)((hu >> 1) & 1));
+    const float* G = hdr + hs * hdr_floats;
+    const float* D = G + KJ * oW;
+    // E[jj] = Σ_k A_w[jstart+k][m]·G[jmin+jj][jstart+k] for the thread's two columns
+    float2 e[KJ];
+#pragma unroll
+    for (int jj = 0; jj < KJ; ++jj) {
+      float s0 = 0.f, s1 = 0.f;
+      if (jj < jcnt) {
+        const float* gr = G + jj * oW;
+#pragma unroll
+        for (int k = 0; k < KT; ++k) {
+          s0 = fmaf(w0[k], gr[i0[k]], s0);
+          s1 = fmaf(w1[k], gr[i1[k]], s1);
+        }
+      }
+      e[jj] = make_float2(s0, s1);
+    }
+#pragma unroll 1
+    for (int q = 0; q < kChunks; ++q, ++it) {
+      const int s = it % kSaStages;
+      mbar_wait_guarded(&full[s], (unsigned)((it / kSaStages) & 1));
+      const float2* xs = reinterpret_cast<const float2*>(ring + s * kStageFloats);
+      const float2* es = xs + 8 * W2;
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) {
+        const int rl = half * 4 + rr;   // row inside the chunk
+        const int i = q * 8 + rl;       // row inside the strip
+        const float4* dr = reinterpret_cast<const float4*>(D + i * KJ);
+        float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int qq = 0; qq < KJ / 4; ++qq) {
+          const float4 w = dr[qq];
+          acc = __ffma2_rn(make_float2(w.x, w.x), e[4 * qq + 0], acc);
+          acc = __ffma2_rn(make_float2(w.y, w.y), e[4 * qq + 1], acc);
+          acc = __ffma2_rn(make_float2(w.z, w.z), e[4 * qq + 2], acc);
+          acc = __ffma2_rn(make_float2(w.w, w.w), e[4 * qq + 3], acc);
+        }
+        const int64_t off = (int64_t)(strip * RA + i) * W + 2 * cp;
+        float2 xt = make_float2(0.f, 0.f);
+        if (ex) xt = ldg_stream2(reinterpret_cast<const float2*>(ex + off));
+        float2 res = __ffma2_rn(make_float2(coef, coef), acc, xt);
+        const float2 pre = x0_pair(xs[rl * W2 + cp], es[rl * W2 + cp], c1, c2, 0);
+        res.x *= clamp_pass(pre.x);
+        res.y *= clamp_pass(pre.y);
+        stg_stream2(gout + off, res);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&hempty[hs]);
+  }
+}
+
 template <typename T>
 int upload(const std::vector<T>& h, T** d) {
   DPS_CUDA(cudaMalloc(d, std::max<size_t>(1, h.size()) * sizeof(T)));
@@ -573,6 +858,9 @@ int resize_create(dps_operator* op, const int32_t* fov_h, const float* w_h, int 
       for (int m = 0; m < H; ++m)
         if (Ah[(size_t)j * H + m] != 0.0) { lo = std::min(lo, m); hi = std::max(hi, m); }
     if (hi < lo) { lo = 0; hi = 0; }
+    // windows start on absolute multiples of 8 rows: the bulk kernel's chunks (and its split of a chunk's rows into two
+    // partial sums) then coincide with the streaming kernel's, which makes the two bit-identical
+    if (H % 8 == 0) lo &= ~7;
     f.rows.lo[s] = (short)lo;
     f.rows.cnt[s] = (short)(hi - lo + 1);
     span = std::max(span, hi - lo + 1);
@@ -601,6 +889,55 @@ int resize_create(dps_operator* op, const int32_t* fov_h, const float* w_h, int 
   for (int j = 0; j < out_w; ++j)
     for (int k = 0; k < kw; ++k)
       if (cstart[j] + k < W) wwt[(size_t)k * out_w + j] = (float)Aw[(size_t)j * W + cstart[j] + k];
+  // ---- streaming forward: sliding-window tables (×4 / ×8 style operators on 256-wide images only) ----
+  {
+    FwdStream& fs = t->fs;
+    const int nchunks = H / 8;
+    const bool shape_ok = W == 256 && H % 8 == 0 && out_h % kRO == 0 && (H == 4 * out_h || H == 8 * out_h) &&
+                          (f.fstrips + kStripsPerUnit - 1) / kStripsPerUnit <= 8;
+    if (shape_ok) {
+      const int D = 8 * out_h / H;
+      int B = -(1 << 30);
+      std::vector<int> first(out_h, nchunks), last(out_h, -1);
+      for (int j = 0; j < out_h; ++j)
+        for (int m = 0; m < H; ++m)
+          if (Ah[(size_t)j * H + m] != 0.0) {
+            const int Q = m / 8;
+            first[j] = std::min(first[j], Q);
+            last[j] = std::max(last[j], Q);
+            B = std::max(B, D * Q - j);  // jb(Q) = D·Q − B ≤ j for every contribution
+          }
+      bool ok = B > -(1 << 30);
+      for (int j = 0; ok && j < out_h; ++j) {
+        if (last[j] < 0) continue;
+        if (j >= D * first[j] - B + kWO) ok = false;  // inside the window of its first chunk (later chunks: larger base)
+        if (last[j] > (j + B) / D) ok = false;        // complete when it is emitted
+        if (j + B < 0) ok = false;
+      }
+      if (ok) {
+        std::vector<float> wq((size_t)H * kWO, 0.f);
+        for (int m = 0; m < H; ++m)
+          for (int tt = 0; tt < kWO; ++tt) {
+            const int j = D * (m / 8) - B + tt;
+            if (j >= 0 && j < out_h) wq[(size_t)m * kWO + tt] = (float)Ah[(size_t)j * H + m];
+          }
+        fs.upp = (f.fstrips + kStripsPerUnit - 1) / kStripsPerUnit;
+        for (int k = 0; k < fs.upp; ++k) {
+          const int j_lo = k * kStripsPerUnit * kRO, j_hi = std::min(out_h, j_lo + kStripsPerUnit * kRO);
+          int q_lo = nchunks;
+          for (int j = j_lo; j < j_hi; ++j) q_lo = std::min(q_lo, first[j]);
+          // the window base of the first chunk must not lie beyond the unit's first row
+          q_lo = std::min(q_lo, (j_lo + B) / D);
+          fs.q_lo[k] = (short)std::max(0, q_lo);
+          fs.q_hi[k] = (short)((j_hi - 1 + B) / D);
+        }
+        if (int rc = upload(wq, &fs.wq)) return rc;
+        fs.D = D;
+        fs.B = B;
+        fs.ok = 1;
+      }
+    }
+  }
   // ---- adjoint: A_hᵀ blocks per input-row strip, two strip heights ----
   DPS_REQUIRE(build_adj_strips(Ah, H, out_h, kRA, kJMax, &t->big) == DPS_OK, DPS_ERR_UNSUPPORTED,
               "resize: a %d-row strip touches more than %d measurement rows", kRA, kJMax);
@@ -642,7 +979,7 @@ int resize_create(dps_operator* op, const int32_t* fov_h, const float* w_h, int 
 void resize_destroy(dps_operator* op) {
   ResizeTables* t = op->resize;
   if (!t) return;
-  cudaFree(t->f.dh); cudaFree(t->f.cstart); cudaFree(t->f.wwt);
+  cudaFree(t->f.dh); cudaFree(t->f.cstart); cudaFree(t->f.wwt); cudaFree(t->fs.wq);
   cudaFree(t->big.dht); cudaFree(t->small.dht);
   cudaFree(t->cols.jstart); cudaFree(t->cols.wtt);
   delete t;
@@ -652,11 +989,11 @@ void resize_destroy(dps_operator* op) {
 // The short-strip adjoint (4x the CTAs, one 8-row chunk each) wins while the machine is not yet full of long strips —
 // measured with the bulk-copy kernels, 256² → 64²: 7.7 vs 10.1 µs at N = 8, 11.9 vs 15.0 at N = 16, 21.4 vs 25.2 at
 // N = 32, but 80.8 vs 75.5 µs at N = 128.
-static int variant_override() {  // DPSTTC_RESIZE_VARIANT=big|small pins the choice (profiling aid)
+static int variant_override() {  // DPSTTC_RESIZE_VARIANT=big|small|stream pins the choice (profiling / test aid)
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("DPSTTC_RESIZE_VARIANT");
-    v = !e ? 0 : (e[0] == 'b' ? 1 : (e[0] == 's' ? 2 : 0));
+    v = !e ? 0 : (e[0] == 'b' ? 1 : (e[0] == 's' ? (e[1] == 't' ? 3 : 2) : 0));  // "stream" = 3
   }
   return v;
 }
@@ -673,6 +1010,31 @@ int resize_forward(const dps_operator* op, const FwdArgs& a, cudaStream_t st) {
     DPS_CUDA(cudaFuncSetAttribute(resize_fwd_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     DPS_CUDA(cudaFuncSetAttribute(resize_fwd_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
+  }
+  {  // streaming variant once the strip grid would fill the machine several times over
+    const FwdStream& fs = op->resize->fs;
+    const int64_t units = (int64_t)op->C * fs.upp * a.n;
+    const int v = variant_override();
+    const size_t smem = sizeof(float) * (32 + (size_t)kSfStages * 2 * 8 * 256 + 2 * kRO * 256 + (size_t)op->H * kWO + 64 +
+                                         (size_t)((f.kw * op->oW + 3) & ~3) + op->oW);
+    if (fs.ok && smem <= 113 * 1024 && units < (1 << 30) && (v == 3 || (v == 0 && (int64_t)op->C * f.fstrips * a.n >= 148 * 12))) {
+      static bool sattr = false;
+      if (!sattr) {
+        DPS_CUDA(cudaFuncSetAttribute(resize_fwd_stream_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        DPS_CUDA(cudaFuncSetAttribute(resize_fwd_stream_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        sattr = true;
+      }
+      int sms = 148;
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, op->device);
+      const int rounds = (int)((units + 2 * sms - 1) / (2 * sms));
+      const int grid = (int)((units + rounds - 1) / rounds);  // every CTA gets `rounds` units (±1): no ragged tail
+      if (fs.D == 2)
+        resize_fwd_stream_kernel<2><<<grid, kSaThreads, smem, st>>>(f, fs, op->C, op->H, op->oH, op->oW, (int)units, a);
+      else
+        resize_fwd_stream_kernel<1><<<grid, kSaThreads, smem, st>>>(f, fs, op->C, op->H, op->oH, op->oW, (int)units, a);
+      DPS_LAUNCH_CHECK("resize_forward");
+      return DPS_OK;
+    }
   }
   dim3 grid((unsigned)(op->C * f.fstrips), (unsigned)a.n);
   if (op->W == 256) {
@@ -713,9 +1075,38 @@ static int launch_adj(const dps_operator* op, const AdjStrips& strips, const Adj
   return DPS_OK;
 }
 
+// The streaming (persistent, TMA-pipelined) adjoint once the strip grid fills the machine several times over.
+template <int KT>
+static int launch_adj_stream(const dps_operator* op, const AdjArgs& a, cudaStream_t st) {
+  const ResizeTables& t = *op->resize;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DPS_CUDA(cudaFuncSetAttribute(resize_adj_stream_kernel<kJMax, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  const int units = op->C * t.big.strips * a.n;
+  const size_t smem = sizeof(float) * (32 + (size_t)kSaStages * 2 * 8 * 256 + 2 * ((size_t)kJMax * op->oW + kRA * kJMax));
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, op->device);
+  const int rounds = (units + 2 * sms - 1) / (2 * sms);
+  const int grid = (units + rounds - 1) / rounds;  // every CTA gets `rounds` units (±1): no ragged tail
+  resize_adj_stream_kernel<kJMax, KT><<<grid, kSaThreads, smem, st>>>(t.big, t.cols, op->C, op->H, op->oH, op->oW, units, a);
+  DPS_LAUNCH_CHECK("resize_adjoint");
+  return DPS_OK;
+}
+
 int resize_adjoint(const dps_operator* op, const AdjArgs& a, cudaStream_t st) {
   const ResizeTables& t = *op->resize;
   const bool narrow = t.cols.kt <= 4;  // KT: compile-time bound of the column window (4 covers bicubic x4 and x8)
+  {
+    const bool masked = a.has_mask && a.mask_src.eps && a.mask_src.clip;
+    const int64_t units = (int64_t)op->C * t.big.strips * a.n;
+    const int v = variant_override();
+    const bool eligible = masked && op->W == 256 && op->H % kRA == 0 && op->oW % 4 == 0 && units < (1 << 30) &&
+                          sizeof(float) * (32 + (size_t)kSaStages * 2 * 8 * 256 + 2 * ((size_t)kJMax * op->oW + kRA * kJMax)) <= 113 * 1024;
+    if (eligible && (v == 3 || (v == 0 && units >= 148 * 12)))
+      return narrow ? launch_adj_stream<4>(op, a, st) : launch_adj_stream<kKTMax>(op, a, st);
+  }
   if (t.small.strips && small_grid((int64_t)op->C * t.big.strips * a.n))
     return narrow ? launch_adj<kRAs, kJs, 4>(op, t.small, a, st) : launch_adj<kRAs, kJs, kKTMax>(op, t.small, a, st);
   return narrow ? launch_adj<kRA, kJMax, 4>(op, t.big, a, st) : launch_adj<kRA, kJMax, kKTMax>(op, t.big, a, st);
