@@ -82,12 +82,27 @@ DPS_DEV float2 ldg_stream2(const float2* p) {
   asm("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
   return r;
 }
-// x̂₀ of a column pair, bit-identical to the scalar path (mul, mul, sub, clamp)
-DPS_DEV float2 x0_pair(float2 x, float2 e, float c1, float c2, int clip) {
+// x̂₀ of a column pair, bit-identical to the scalar path (mul, mul, sub, clamp).  ptxas contracts mul.rn.f32x2 +
+// add.rn.f32x2 into ONE FFMA2 (seen in SASS, CUDA 12.9), which would round c1·x only once and break the bit-identity
+// with x0_pre / the reference.  The subtraction is therefore written as fma(a, 1, −b) with the 1 read from constant
+// memory, a value ptxas cannot see: FMUL2, FMUL2, FFMA2 — three packed instructions, every product rounded on its own.
+static __constant__ float dps_opaque_one = 1.0f;
+DPS_DEV float2 x0_pair_pre(float2 x, float2 e, float c1, float c2) {
   const float2 a = __fmul2_rn(make_float2(c1, c1), x);
   const float2 b = __fmul2_rn(make_float2(c2, c2), e);
-  float2 v = __fadd2_rn(a, make_float2(-b.x, -b.y));
+  const float one = dps_opaque_one;
+  return __ffma2_rn(a, make_float2(one, one), make_float2(-b.x, -b.y));
+}
+DPS_DEV float2 x0_pair(float2 x, float2 e, float c1, float c2, int clip) {
+  float2 v = x0_pair_pre(x, e, c1, c2);
   if (clip) { v.x = clamp1(v.x); v.y = clamp1(v.y); }
+  return v;
+}
+// the same with the clamp bounds as data (±1 or ±inf): no branch in an unrolled row loop
+DPS_DEV float2 x0_pair_bounds(float2 x, float2 e, float c1, float c2, float lo, float hi) {
+  float2 v = x0_pair_pre(x, e, c1, c2);
+  v.x = fminf(fmaxf(v.x, lo), hi);
+  v.y = fminf(fmaxf(v.y, lo), hi);
   return v;
 }
 

@@ -125,43 +125,43 @@ DPS_DEV YPre fwd_y_prefetch(int oH, int oW, int strip, int c, int n, int tid, in
   return y;
 }
 
+// One output of the W pass: Σ_k A_w[jc][cs+k]·V[j][cs+k], residual, store, Σr², Σ|r|.  i = j·oW + jc inside the strip.
+DPS_DEV void wpass_one(const FwdSmem& m, const FwdTables& t, int W, int oH, int oW, int strip, int i, const float* yp,
+                       bool have, float yv, float* outp, float& sq, float& ab) {
+  const int j = i / oW, jc = i - j * oW;
+  const int orow = strip * kRO + j;
+  if (orow >= oH) return;
+  const int64_t o = (int64_t)orow * oW + jc;
+  if (!have) yv = yp ? ldg_ro(yp + o) : 0.f;
+  const int cs = m.css[jc];
+  const float* vr = m.V + j * W + cs;
+  float s = 0.f;
+#pragma unroll 8
+  for (int k = 0; k < t.kw; ++k) s = fmaf(m.wws[k * oW + jc], (cs + k < W) ? vr[k] : 0.f, s);
+  const float res = yp ? __fsub_rn(yv, s) : s;
+  stg_stream(outp + o, res);
+  sq += res * res;
+  ab += fabsf(res);
+}
+
 // W pass + residual + Σr², Σ|r| from the (kRO, W) tile V
-// `slot`: the strip's partial-sum slot c·fstrips + strip.  `bar_id` 0: the whole CTA takes part (block_sum2); else the
-// nt threads of named barrier `bar_id` (the consumers of the streaming kernel) — same tree, same bits.
+// `slot`: the strip's partial-sum slot c·fstrips + strip.
 DPS_DEV void fwd_wpass(const FwdSmem& m, const FwdTables& t, int C, int W, int oH, int oW, int strip, int c, int n,
-                       int tid, int nt, const FwdArgs& a, const YPre& ypre, int slot, int bar_id) {
+                       int tid, int nt, const FwdArgs& a, const YPre& ypre, int slot) {
   float sq = 0.f, ab = 0.f;
-  const int64_t oplane = ((int64_t)n * C + c) * oH * oW;
+  float* outp = a.out + ((int64_t)n * C + c) * oH * oW;
   const float* yp = a.y ? a.y + n * a.y_stride + (int64_t)c * oH * oW : nullptr;
-  auto one = [&](int i, bool have, float yv) {
-    const int j = i / oW, jc = i - j * oW;
-    const int orow = strip * kRO + j;
-    if (orow >= oH) return;
-    const int64_t o = (int64_t)orow * oW + jc;
-    if (!have) yv = yp ? ldg_ro(yp + o) : 0.f;
-    const int cs = m.css[jc];
-    const float* vr = m.V + j * W + cs;
-    float s = 0.f;
-    for (int k = 0; k < t.kw; ++k) s = fmaf(m.wws[k * oW + jc], (cs + k < W) ? vr[k] : 0.f, s);
-    const float res = yp ? __fsub_rn(yv, s) : s;
-    stg_stream(a.out + oplane + o, res);
-    sq += res * res;
-    ab += fabsf(res);
-  };
 #pragma unroll
   for (int u = 0; u < kYPre; ++u)
-    if (tid + u * nt < kRO * oW) one(tid + u * nt, true, ypre.v[u]);
-  for (int i = tid + kYPre * nt; i < kRO * oW; i += nt) one(i, false, 0.f);
+    if (tid + u * nt < kRO * oW) wpass_one(m, t, W, oH, oW, strip, tid + u * nt, yp, true, ypre.v[u], outp, sq, ab);
+  for (int i = tid + kYPre * nt; i < kRO * oW; i += nt) wpass_one(m, t, W, oH, oW, strip, i, yp, false, 0.f, outp, sq, ab);
   if (a.partials) {
-    if (bar_id == 0) block_sum2(sq, ab, m.red);
-    else group_sum2(sq, ab, m.red, nt / 32, bar_id);
+    block_sum2(sq, ab, m.red);
     if (tid == 0) {
       float* pp = a.partials + ((int64_t)n * (C * t.fstrips) + slot) * 2;
       pp[0] = sq;
       pp[1] = ab;
     }
-  } else if (bar_id != 0) {
-    named_bar_sync(bar_id, nt);
   }
 }
 
@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(kThreads) resize_fwd_kernel(const FwdTables t,
     for (int j = 0; j < kRO; ++j) m.V[j * W + col] = acc[j];
   }
   __syncthreads();
-  fwd_wpass(m, t, C, W, oH, oW, strip, c, n, tid, kThreads, a, ypre, blockIdx.x, 0);
+  fwd_wpass(m, t, C, W, oH, oW, strip, c, n, tid, kThreads, a, ypre, blockIdx.x);
 }
 
 // Pair variant for W = 256: 128 column pairs × kParts row groups.  64-bit loads, x̂₀ and the accumulation on
@@ -294,14 +294,18 @@ __global__ void __launch_bounds__(128 * kParts, 3) resize_fwd_pair_kernel(const 
     *reinterpret_cast<float4*>(m.V + i * 4) = s0;
   }
   __syncthreads();
-  fwd_wpass(m, t, C, W, oH, oW, strip, c, n, tid, kT, a, ypre, blockIdx.x, 0);
+  fwd_wpass(m, t, C, W, oH, oW, strip, c, n, tid, kT, a, ypre, blockIdx.x);
 }
 
 // Bulk-copy variant for W = 256 (the default): the strip's input window is fetched by the TMA engine — 1-D bulk copies
 // of 8 image rows (8 KB per tensor, contiguous in a plane) into a 3-stage shared-memory ring, completion on mbarriers —
 // so 48 KB per CTA (144 KB per SM at 3 CTAs) are in flight without holding a register, and the threads only ever wait
 // on shared memory.  Compute is the pair kernel's: 128 column pairs × 2 row groups on packed FFMA2, then the W pass.
-constexpr int kSaStages = 6;          // streaming adjoint: ring stages
+// Stage geometry of the streaming kernels.  tools/tma_stream_probe.cu (B200): persistent CTAs that each stream their own
+// region reach 4.0-4.2 TB/s with 8 KB bulk copies, 5.5 TB/s with 16 KB and 6.0 TB/s with 32 KB (a grid-wide linear sweep:
+// 6.0 TB/s at any size) — DRAM row locality wants large contiguous requests, so a stage holds 16 / 32 rows per tensor.
+constexpr int kSaStages = 3;          // streaming adjoint: ring stages
+constexpr int kSaRows = 16;           //   rows per stage and tensor (16 KB per bulk copy)
 constexpr int kSaThreads = 256 + 32;  // streaming kernels: 256 consumers + one producer warp
 constexpr int kCR = 8;      // rows per chunk
 constexpr int kStages = 3;  // chunks in flight
@@ -387,17 +391,23 @@ __global__ void __launch_bounds__(256, 4) resize_fwd_bulk_kernel(const FwdTables
     *reinterpret_cast<float4*>(m.V + i * 4) = s0;
   }
   __syncthreads();
-  fwd_wpass(m, t, C, W, oH, oW, strip, c, n, tid, kT, a, ypre, blockIdx.x, 0);
+  fwd_wpass(m, t, C, W, oH, oW, strip, c, n, tid, kT, a, ypre, blockIdx.x);
 }
 
-// Streaming forward for full machines (W = 256; ×4 and ×8 bicubic): persistent CTAs, one producer warp + 256 consumers.
-// A work unit is 4 consecutive output strips of one plane; its input rows are streamed ONCE, in absolute 8-row chunks,
-// through a ring of kSfStages TMA stages (x rows | ε rows), so the 1.5× halo re-read of the strip kernels disappears and
-// loads never pause for a W pass.  Consumers (128 column pairs × 2 row halves) keep a sliding window of kWO output-row
-// accumulators: chunk Q adds to rows jb(Q)…jb(Q)+5, after which the first D of them are complete and go to the V tile;
-// every 8 completed rows the strip's W pass, residual and partial sums run exactly as in the strip kernels.
-// Bit-identity with resize_fwd_bulk_kernel: both split the rows of a chunk into the same halves (chunks are aligned to
-// absolute multiples of 8 in both), add them in ascending order, and share fwd_wpass and the reduction tree.
+// Streaming forward for full machines (W = 256; ×4 and ×8 bicubic): persistent CTAs of three roles.
+//   producer (1 warp) : a work unit is 4 consecutive output strips of one plane; its input rows are streamed ONCE, in
+//                       absolute 8-row chunks, through a ring of kSfStages TMA stages (x rows | ε rows) — the 1.5× halo
+//                       re-read of the strip kernels disappears and loads never pause;
+//   H warps (4)       : a thread owns a column pair and keeps a sliding window of kWO output-row accumulators (two partial
+//                       sums: rows 0-3 and rows 4-7 of every chunk).  Chunk Q adds to rows jb(Q)…jb(Q)+5, after which the
+//                       first D of them are complete and go to the V tile of their strip (double-buffered);
+//   W warps (4)       : per completed strip the W pass, residual, store and partial sums — concurrently with the H warps'
+//                       next strip.  The 128 threads play the 256 threads of the strip kernels (two virtual threads each,
+//                       two virtual warps per warp), so the reduction tree and therefore the partial sums are bit-identical.
+// Bit-identity with resize_fwd_bulk_kernel: chunks are aligned to absolute multiples of 8 rows in both, each partial sum
+// adds its rows in ascending order, V = part0 + part1, and both use wpass_one.
+// Variants that were measured and lost (N = 128, this kernel 50.7 µs): 16-row stages × 3 with a single V tile 64 µs,
+// 32-row stages × 3 at one CTA per SM 66 µs, 8 H warps (one row half each) + W pass on the split tile 63 µs.
 constexpr int kSfStages = 5;
 
 template <int D>
@@ -407,19 +417,24 @@ __global__ void __launch_bounds__(kSaThreads, 2) resize_fwd_stream_kernel(const 
   extern __shared__ __align__(128) float smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);
   uint64_t* empty = full + kSfStages;
-  static_assert(2 * kSfStages <= 16, "barriers must fit in the first 128 bytes");
+  uint64_t* vfull = empty + kSfStages;  // [2]
+  uint64_t* vempty = vfull + 2;         // [2]
+  static_assert(2 * kSfStages + 4 <= 16, "barriers must fit in the first 128 bytes");
   float* ring = smem + 32;
+  float* Vbuf = ring + kSfStages * kStageFloats;  // (2, kRO, W)
+  float* wq = Vbuf + 2 * kRO * W;                 // (H, kWO)
   FwdSmem m;
   m.dh = nullptr;
-  m.V = ring + kSfStages * kStageFloats;  // (2, kRO, W)
-  float* wq = m.V + 2 * kRO * W;          // (H, kWO)
-  m.red = wq + H * kWO;
-  m.wws = m.red + 64;
+  m.V = Vbuf;
+  m.red = wq + H * kWO;                           // (2, 64)
+  m.wws = m.red + 128;
   m.css = reinterpret_cast<int*>(m.wws + ((t.kw * oW + 3) & ~3));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < kSfStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 8); }
+    for (int s = 0; s < kSfStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 4); }
+    mbar_init(&vfull[0], 4); mbar_init(&vfull[1], 4);
+    mbar_init(&vempty[0], 4); mbar_init(&vempty[1], 4);
     mbar_init_fence();
   }
   stage_async(wq, fs.wq, H * kWO, tid, kSaThreads);
@@ -453,60 +468,130 @@ __global__ void __launch_bounds__(kSaThreads, 2) resize_fwd_stream_kernel(const 
     return;
   }
 
-  // ---------------- consumers ----------------
-  const int half = tid >> 7, cp = tid & 127;
-  int it = 0;
+  if (warp < 4) {  // ---------------- H warps ----------------
+    const int cp = tid;
+    const float c1 = a.src.c1, c2 = a.src.c2;
+    const float clamp_hi = a.src.clip ? 1.0f : __int_as_float(0x7f800000), clamp_lo = -clamp_hi;
+    int it = 0, sc = 0;  // chunks consumed, strips produced
+    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+      const int k = u % upp;
+      const int j_lo = k * kStripsPerUnit * kRO, j_hi = min(oH, j_lo + kStripsPerUnit * kRO);
+      float2 acc0[kWO], acc1[kWO];
+#pragma unroll
+      for (int tt = 0; tt < kWO; ++tt) acc0[tt] = acc1[tt] = make_float2(0.f, 0.f);
+#pragma unroll 1
+      for (int Q = fs.q_lo[k]; Q <= fs.q_hi[k]; ++Q) {
+        if (Q < nchunks) {
+          const int s = it % kSfStages;
+          mbar_wait_guarded(&full[s], (unsigned)((it / kSfStages) & 1));
+          const float2* xs = reinterpret_cast<const float2*>(ring + s * kStageFloats) + cp;
+          const float2* es = xs + 8 * W2;
+          const float2* wr = reinterpret_cast<const float2*>(wq + Q * 8 * kWO);
+          float2 v[8];
+          if (has_eps) {
+#pragma unroll
+            for (int rl = 0; rl < 8; ++rl) v[rl] = x0_pair_bounds(xs[rl * W2], es[rl * W2], c1, c2, clamp_lo, clamp_hi);
+          } else {
+#pragma unroll
+            for (int rl = 0; rl < 8; ++rl) v[rl] = xs[rl * W2];
+          }
+#pragma unroll
+          for (int rl = 0; rl < 8; ++rl) {
+            const float2 wa = wr[rl * 3], wb = wr[rl * 3 + 1], wc = wr[rl * 3 + 2];
+            float2* acc = rl < 4 ? acc0 : acc1;
+            acc[0] = __ffma2_rn(make_float2(wa.x, wa.x), v[rl], acc[0]); acc[1] = __ffma2_rn(make_float2(wa.y, wa.y), v[rl], acc[1]);
+            acc[2] = __ffma2_rn(make_float2(wb.x, wb.x), v[rl], acc[2]); acc[3] = __ffma2_rn(make_float2(wb.y, wb.y), v[rl], acc[3]);
+            acc[4] = __ffma2_rn(make_float2(wc.x, wc.x), v[rl], acc[4]); acc[5] = __ffma2_rn(make_float2(wc.y, wc.y), v[rl], acc[5]);
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty[s]);
+          ++it;
+        }
+        // rows jb … jb+D−1 are complete: V[row] = part0 + part1 into the strip's tile
+        const int jb = D * Q - fs.B;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          const int j = jb + d;
+          if (j >= j_lo && j < j_hi) {
+            const int buf = sc & 1;
+            if ((j & (kRO - 1)) == 0) mbar_wait_guarded(&vempty[buf], (unsigned)(((sc >> 1) & 1) ^ 1));  // tile free?
+            float2 sum = acc0[d];
+            sum.x += acc1[d].x;
+            sum.y += acc1[d].y;
+            *reinterpret_cast<float2*>(Vbuf + (buf * kRO + (j & (kRO - 1))) * W + 2 * cp) = sum;
+            if ((j & (kRO - 1)) == kRO - 1) {  // strip complete: hand the tile to the W warps
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&vfull[buf]);
+              ++sc;
+            }
+          }
+        }
+#pragma unroll
+        for (int tt = 0; tt < kWO; ++tt) {
+          acc0[tt] = tt + D < kWO ? acc0[tt + D] : make_float2(0.f, 0.f);
+          acc1[tt] = tt + D < kWO ? acc1[tt + D] : make_float2(0.f, 0.f);
+        }
+      }
+    }
+    return;
+  }
+
+  // ---------------- W warps: thread wt plays the strip kernels' threads wt and wt + 128 ----------------
+  const int wt = tid - 128, ww = wt >> 5;
+  int sc = 0;
   for (int u = blockIdx.x; u < units; u += gridDim.x) {
     const int k = u % upp, c = (u / upp) % C, n = u / (upp * C);
     const int j_lo = k * kStripsPerUnit * kRO, j_hi = min(oH, j_lo + kStripsPerUnit * kRO);
-    float2 acc[kWO];
-#pragma unroll
-    for (int tt = 0; tt < kWO; ++tt) acc[tt] = make_float2(0.f, 0.f);
-    YPre ypre = fwd_y_prefetch(oH, oW, j_lo / kRO, c, n, tid, 256, a);
+    float* outp = a.out + ((int64_t)n * C + c) * oH * oW;
+    const float* yp = a.y ? a.y + n * a.y_stride + (int64_t)c * oH * oW : nullptr;
 #pragma unroll 1
-    for (int Q = fs.q_lo[k]; Q <= fs.q_hi[k]; ++Q) {
-      if (Q < nchunks) {
-        const int s = it % kSfStages;
-        mbar_wait_guarded(&full[s], (unsigned)((it / kSfStages) & 1));
-        const float2* xs = reinterpret_cast<const float2*>(ring + s * kStageFloats);
-        const float2* es = xs + 8 * W2;
+    for (int strip = j_lo / kRO; strip < j_hi / kRO; ++strip, ++sc) {
+      const int buf = sc & 1;
+      // measurement values first: their latency hides behind the wait for the tile
+      float yv[2][kYPre];
 #pragma unroll
-        for (int rr = 0; rr < 4; ++rr) {
-          const int rl = half * 4 + rr;
-          const float2 xv = xs[rl * W2 + cp];
-          const float2 v = has_eps ? x0_pair(xv, es[rl * W2 + cp], a.src.c1, a.src.c2, a.src.clip) : xv;
-          const float2* wr = reinterpret_cast<const float2*>(wq + (Q * 8 + rl) * kWO);
-          const float2 wa = wr[0], wb = wr[1], wc = wr[2];
-          acc[0] = __ffma2_rn(make_float2(wa.x, wa.x), v, acc[0]); acc[1] = __ffma2_rn(make_float2(wa.y, wa.y), v, acc[1]);
-          acc[2] = __ffma2_rn(make_float2(wb.x, wb.x), v, acc[2]); acc[3] = __ffma2_rn(make_float2(wb.y, wb.y), v, acc[3]);
-          acc[4] = __ffma2_rn(make_float2(wc.x, wc.x), v, acc[4]); acc[5] = __ffma2_rn(make_float2(wc.y, wc.y), v, acc[5]);
+      for (int vtt = 0; vtt < 2; ++vtt)
+#pragma unroll
+        for (int uu = 0; uu < kYPre; ++uu) {
+          const int i = wt + vtt * 128 + uu * 256;
+          yv[vtt][uu] = (yp && i < kRO * oW) ? ldg_ro(yp + (int64_t)strip * kRO * oW + i) : 0.f;
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[s]);
-        ++it;
-      }
-      // rows jb … jb+D−1 are complete: into the V tile of their strip (row-half `half` of the sum)
-      const int jb = D * Q - fs.B;
+      mbar_wait_guarded(&vfull[buf], (unsigned)((sc >> 1) & 1));
+      m.V = Vbuf + buf * kRO * W;
+      float sq[2] = {0.f, 0.f}, ab[2] = {0.f, 0.f};
 #pragma unroll
-      for (int d = 0; d < D; ++d) {
-        const int j = jb + d;
-        if (j >= j_lo && j < j_hi) *reinterpret_cast<float2*>(m.V + (half * kRO + (j & (kRO - 1))) * W + 2 * cp) = acc[d];
-      }
+      for (int vtt = 0; vtt < 2; ++vtt) {
+        const int vt = wt + vtt * 128;
 #pragma unroll
-      for (int tt = 0; tt < kWO; ++tt) acc[tt] = tt + D < kWO ? acc[tt + D] : make_float2(0.f, 0.f);
-      const int j_last = jb + D - 1;
-      if (j_last >= j_lo && j_last < j_hi && (j_last & (kRO - 1)) == kRO - 1) {  // a strip is complete
-        const int strip = j_last / kRO;
-        named_bar_sync(1, 256);
-        for (int i = tid; i < kRO * W / 4; i += 256) {  // V[0] += V[1], fixed order
-          float4 s0 = *reinterpret_cast<const float4*>(m.V + i * 4);
-          const float4 s1 = *reinterpret_cast<const float4*>(m.V + kRO * W + i * 4);
-          s0.x += s1.x; s0.y += s1.y; s0.z += s1.z; s0.w += s1.w;
-          *reinterpret_cast<float4*>(m.V + i * 4) = s0;
+        for (int uu = 0; uu < kYPre; ++uu)
+          if (vt + uu * 256 < kRO * oW)
+            wpass_one(m, t, W, oH, oW, strip, vt + uu * 256, yp, true, yv[vtt][uu], outp, sq[vtt], ab[vtt]);
+        for (int i = vt + kYPre * 256; i < kRO * oW; i += 256) wpass_one(m, t, W, oH, oW, strip, i, yp, false, 0.f, outp, sq[vtt], ab[vtt]);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&vempty[buf]);  // the tile has been read
+      if (a.partials) {  // block_sum2's tree for 8 (virtual) warps: virtual warp of (ww, vtt) = ww + 4·vtt
+        float* red = m.red + buf * 64;
+#pragma unroll
+        for (int vtt = 0; vtt < 2; ++vtt) {
+          const float s2 = warp_sum(sq[vtt]), a2 = warp_sum(ab[vtt]);
+          if (lane == 0) {
+            red[ww + 4 * vtt] = s2;
+            red[32 + ww + 4 * vtt] = a2;
+          }
         }
-        named_bar_sync(1, 256);
-        fwd_wpass(m, t, C, W, oH, oW, strip, c, n, tid, 256, a, ypre, c * t.fstrips + strip, 1);
-        if (strip + 1 < (j_hi + kRO - 1) / kRO) ypre = fwd_y_prefetch(oH, oW, strip + 1, c, n, tid, 256, a);
+        named_bar_sync(2, 128);
+        if (ww == 0) {
+          float s2 = lane < 8 ? red[lane] : 0.0f;
+          float a2 = lane < 8 ? red[32 + lane] : 0.0f;
+          s2 = warp_sum(s2);
+          a2 = warp_sum(a2);
+          if (lane == 0) {
+            float* pp = a.partials + ((int64_t)n * (C * t.fstrips) + c * t.fstrips + strip) * 2;
+            pp[0] = s2;
+            pp[1] = a2;
+          }
+        }
       }
     }
   }
@@ -633,7 +718,7 @@ __global__ void __launch_bounds__(kThreads, RA == kRAs ? 4 : 3) resize_adj_kerne
 
 // Streaming adjoint for full machines (W = 256, H a multiple of 32, clamp mask on): persistent CTAs, one producer warp
 // and 256 consumer threads.  The producer walks the CTA's work list — units (particle, channel, 32-row strip), round
-// robin over the grid — and keeps a ring of kSaStages 8-row chunks of the clamp-mask sources (x rows | ε rows, 16 KB per
+// robin over the grid — and keeps a ring of kSaStages 16-row chunks of the clamp-mask sources (x rows | ε rows, 32 KB per
 // stage) plus the NEXT unit's header (its measurement rows and its A_hᵀ block) in flight through the TMA engine, gated by
 // full/empty mbarriers, so loads never stop for a CTA's compute or store phase.  Consumers: 128 column pairs × 2 row
 // halves; E = G·A_w in registers per unit, then 12-16 packed FFMA2 per output row pair element, the clamp mask from the
@@ -642,8 +727,8 @@ __global__ void __launch_bounds__(kThreads, RA == kRAs ? 4 : 3) resize_adj_kerne
 template <int KJ, int KT>
 __global__ void __launch_bounds__(kSaThreads, 2) resize_adj_stream_kernel(const AdjStrips at, const AdjCols ac, int C, int H,
                                                                             int oH, int oW, int units, const AdjArgs a) {
-  constexpr int W = 256, W2 = 128, RA = kRA, kChunks = RA / 8;
-  constexpr int kStageFloats = 2 * 8 * W;
+  constexpr int W = 256, W2 = 128, RA = kRA, kChunks = RA / kSaRows, kHalfRows = kSaRows / 2;
+  constexpr int kStageFloats = 2 * kSaRows * W;
   extern __shared__ __align__(128) float smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);  // [kSaStages]
   uint64_t* empty = full + kSaStages;                  // [kSaStages]
@@ -687,8 +772,8 @@ __global__ void __launch_bounds__(kSaThreads, 2) resize_adj_stream_kernel(const 
         mbar_wait_guarded(&empty[s], (unsigned)(((it / kSaStages) & 1) ^ 1));
         float* dst = ring + s * kStageFloats;
         mbar_expect_tx(&full[s], (unsigned)(kStageFloats * sizeof(float)));
-        bulk_load(dst, mx + q * 8 * W, 8 * W * sizeof(float), &full[s]);
-        bulk_load(dst + 8 * W, me + q * 8 * W, 8 * W * sizeof(float), &full[s]);
+        bulk_load(dst, mx + q * kSaRows * W, kSaRows * W * sizeof(float), &full[s]);
+        bulk_load(dst + kSaRows * W, me + q * kSaRows * W, kSaRows * W * sizeof(float), &full[s]);
       }
     }
     return;
@@ -737,17 +822,21 @@ __global__ void __launch_bounds__(kSaThreads, 2) resize_adj_stream_kernel(const 
       }
       e[jj] = make_float2(s0, s1);
     }
-#pragma unroll 1
+    // per-unit bases: every per-row offset below is a compile-time immediate
+    const int64_t off0 = (int64_t)(strip * RA + half * kHalfRows) * W + 2 * cp;
+    float* gp = gout + off0;
+    const float* exp_ = ex ? ex + off0 : nullptr;
+    const float4* dbase = reinterpret_cast<const float4*>(D + half * kHalfRows * KJ);
+#pragma unroll
     for (int q = 0; q < kChunks; ++q, ++it) {
       const int s = it % kSaStages;
       mbar_wait_guarded(&full[s], (unsigned)((it / kSaStages) & 1));
-      const float2* xs = reinterpret_cast<const float2*>(ring + s * kStageFloats);
-      const float2* es = xs + 8 * W2;
+      const float2* xs = reinterpret_cast<const float2*>(ring + s * kStageFloats) + half * kHalfRows * W2 + cp;
+      const float2* es = xs + kSaRows * W2;
 #pragma unroll
-      for (int rr = 0; rr < 4; ++rr) {
-        const int rl = half * 4 + rr;   // row inside the chunk
-        const int i = q * 8 + rl;       // row inside the strip
-        const float4* dr = reinterpret_cast<const float4*>(D + i * KJ);
+      for (int rr = 0; rr < kHalfRows; ++rr) {
+        const int i = q * kSaRows + rr;  // row inside the strip, relative to the half's first row
+        const float4* dr = dbase + i * (KJ / 4);
         float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
         for (int qq = 0; qq < KJ / 4; ++qq) {
@@ -757,14 +846,13 @@ __global__ void __launch_bounds__(kSaThreads, 2) resize_adj_stream_kernel(const 
           acc = __ffma2_rn(make_float2(w.z, w.z), e[4 * qq + 2], acc);
           acc = __ffma2_rn(make_float2(w.w, w.w), e[4 * qq + 3], acc);
         }
-        const int64_t off = (int64_t)(strip * RA + i) * W + 2 * cp;
         float2 xt = make_float2(0.f, 0.f);
-        if (ex) xt = ldg_stream2(reinterpret_cast<const float2*>(ex + off));
+        if (exp_) xt = ldg_stream2(reinterpret_cast<const float2*>(exp_ + i * W));
         float2 res = __ffma2_rn(make_float2(coef, coef), acc, xt);
-        const float2 pre = x0_pair(xs[rl * W2 + cp], es[rl * W2 + cp], c1, c2, 0);
+        const float2 pre = x0_pair_pre(xs[rr * W2], es[rr * W2], c1, c2);
         res.x *= clamp_pass(pre.x);
         res.y *= clamp_pass(pre.y);
-        stg_stream2(gout + off, res);
+        stg_stream2(gp + i * W, res);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[s]);
@@ -1015,9 +1103,9 @@ int resize_forward(const dps_operator* op, const FwdArgs& a, cudaStream_t st) {
     const FwdStream& fs = op->resize->fs;
     const int64_t units = (int64_t)op->C * fs.upp * a.n;
     const int v = variant_override();
-    const size_t smem = sizeof(float) * (32 + (size_t)kSfStages * 2 * 8 * 256 + 2 * kRO * 256 + (size_t)op->H * kWO + 64 +
+    const size_t smem = sizeof(float) * (32 + (size_t)kSfStages * 2 * 8 * 256 + 2 * kRO * 256 + (size_t)op->H * kWO + 128 +
                                          (size_t)((f.kw * op->oW + 3) & ~3) + op->oW);
-    if (fs.ok && smem <= 113 * 1024 && units < (1 << 30) && (v == 3 || (v == 0 && (int64_t)op->C * f.fstrips * a.n >= 148 * 12))) {
+    if (fs.ok && smem <= 113 * 1024 && units < (1 << 30) && (v == 3 || (v == 0 && (int64_t)op->C * f.fstrips * a.n >= 80 * 24))) {  // N ≥ 80: 41.1 vs 44.5 µs at 96, 50.7 vs 56.6 at 128
       static bool sattr = false;
       if (!sattr) {
         DPS_CUDA(cudaFuncSetAttribute(resize_fwd_stream_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -1085,7 +1173,7 @@ static int launch_adj_stream(const dps_operator* op, const AdjArgs& a, cudaStrea
     attr_set = true;
   }
   const int units = op->C * t.big.strips * a.n;
-  const size_t smem = sizeof(float) * (32 + (size_t)kSaStages * 2 * 8 * 256 + 2 * ((size_t)kJMax * op->oW + kRA * kJMax));
+  const size_t smem = sizeof(float) * (32 + (size_t)kSaStages * 2 * kSaRows * 256 + 2 * ((size_t)kJMax * op->oW + kRA * kJMax));
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, op->device);
   const int rounds = (units + 2 * sms - 1) / (2 * sms);
@@ -1103,8 +1191,10 @@ int resize_adjoint(const dps_operator* op, const AdjArgs& a, cudaStream_t st) {
     const int64_t units = (int64_t)op->C * t.big.strips * a.n;
     const int v = variant_override();
     const bool eligible = masked && op->W == 256 && op->H % kRA == 0 && op->oW % 4 == 0 && units < (1 << 30) &&
-                          sizeof(float) * (32 + (size_t)kSaStages * 2 * 8 * 256 + 2 * ((size_t)kJMax * op->oW + kRA * kJMax)) <= 113 * 1024;
-    if (eligible && (v == 3 || (v == 0 && units >= 148 * 12)))
+                          sizeof(float) * (32 + (size_t)kSaStages * 2 * kSaRows * 256 + 2 * ((size_t)kJMax * op->oW + kRA * kJMax)) <= 113 * 1024;
+    // measured (N: small / big / stream µs): 32: 28.3 / 28.4 / 27.1, 48: 34.4 / 36.4 / 27.2, 64: 44.4 / 45.0 / 34.3,
+    // 96: 63.2 / 60.4 / 44.1, 128: 81.4 / 76.5 / 56.7
+    if (eligible && (v == 3 || (v == 0 && units >= 40 * 24)))
       return narrow ? launch_adj_stream<4>(op, a, st) : launch_adj_stream<kKTMax>(op, a, st);
   }
   if (t.small.strips && small_grid((int64_t)op->C * t.big.strips * a.n))

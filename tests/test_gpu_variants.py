@@ -1,0 +1,20 @@
+"""Kernel variants that a launch picks by grid size must agree bit for bit: the sharded and the unsharded run of a
+resampling sampler launch different variants (8 particles per rank vs 64 on one GPU) and still have to produce the same
+per-particle norms, hence the same ancestor indices.  tools/variant_check.py runs one process per variant."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("op,n", [("sr4", 12), ("sr8", 5)])
+def test_resize_variants_bit_identical(op, n):
+    cmd = [sys.executable, os.path.join(REPO, "tools", "variant_check.py"), "--op", op, "--n", str(n),
+           "--env", "DPSTTC_RESIZE_VARIANT=big", "--env", "DPSTTC_RESIZE_VARIANT=small", "--env", "DPSTTC_RESIZE_VARIANT=stream"]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert "PASS" in res.stdout
