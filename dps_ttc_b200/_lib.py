@@ -17,6 +17,7 @@ CSRC_DIR = os.path.join(_HERE, "csrc")
 
 DPS_COEF_NORM = 1
 DPS_COEF_NORM_SQ = 2
+DPS_COEF_GLOBAL_NORM = 3
 OP_KINDS = {1: "inpainting", 2: "blur_separable", 3: "blur_sparse", 4: "resize", 5: "phase"}
 
 
@@ -60,6 +61,7 @@ SIGNATURES = {
     "dps_guidance_grad": (_I, [_P, _L, _P, _F, _F, _P, _I, _L, _P]),
     "dps_apply_gradient": (_I, [_P, _P, _L, _P, _I, _L, _P]),
     "dps_q_sample": (_I, [_P, _P, _F, _F, _P, _L, _P]),
+    "dps_particle_sqdiff": (_I, [_P, _L, _P, _L, _I, _L, _P, _I, _P]),
     "dps_operator_create_inpainting": (_I, [_P, _I, _I, _I, C.POINTER(_P)]),
     "dps_operator_create_blur": (_I, [_P, _I, _I, _I, _I, _I, C.POINTER(_P)]),
     "dps_operator_create_resize": (_I, [_P, _P, _I, _I, _P, _P, _I, _I, _I, _I, _I, C.POINTER(_P)]),

@@ -41,6 +41,32 @@ __global__ void particle_norms_kernel(const float* __restrict__ partials, int P,
   }
 }
 
+// Poisson-likelihood guidance (condition_methods.py:50-55): the loss is the Frobenius norm over ALL particles times
+// mean(1/|y|), so every particle gets the same coefficient −scale/‖r‖_all (scale = ζ·mean(1/|y|), folded by the host).
+// One CTA: per-particle norms like particle_norms_kernel, then the global sum in a fixed order.
+__global__ void __launch_bounds__(256) global_norm_coef_kernel(const float* __restrict__ partials, int P, int n, float scale,
+                                                               float* __restrict__ l2, float* __restrict__ coef) {
+  __shared__ double red[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double tot = 0.0;
+  for (int i = warp; i < n; i += 8) {  // a warp per particle
+    const float* p = partials + (int64_t)i * P * 2;
+    double sq = 0.0;
+    for (int j = lane; j < P; j += 32) sq += (double)p[2 * j];
+    sq = warp_sum(sq);
+    if (lane == 0 && l2) l2[i] = (float)sqrt(sq);
+    tot += sq;
+  }
+  if (lane == 0) red[warp] = tot;
+  __syncthreads();
+  double all = 0.0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) all += red[w];
+  const float nrm = (float)sqrt(all);
+  const float c = nrm > 0.f ? -scale / nrm : 0.f;
+  for (int i = threadIdx.x; i < n; i += 256) coef[i] = c;
+}
+
 __global__ void logweights_kernel(const float* __restrict__ meas, const float* __restrict__ sem, int n, float tau,
                                   float meas_scale, int meas_pow, float sem_scale, int sem_pow,
                                   float* __restrict__ logw) {
@@ -265,7 +291,13 @@ int dps_particle_norms(const float* partials, int P, int n, float* l2, float* l1
 int dps_guidance_coef(const float* partials, int P, int n, int mode, float scale, float* l2, float* coef,
                       dps_stream_t stream) {
   DPS_REQUIRE(partials && P > 0 && n > 0 && coef, DPS_ERR_INVALID, "dps_guidance_coef: bad arguments");
-  DPS_REQUIRE(mode == DPS_COEF_NORM || mode == DPS_COEF_NORM_SQ, DPS_ERR_INVALID, "dps_guidance_coef: bad mode %d", mode);
+  DPS_REQUIRE(mode == DPS_COEF_NORM || mode == DPS_COEF_NORM_SQ || mode == DPS_COEF_GLOBAL_NORM, DPS_ERR_INVALID,
+              "dps_guidance_coef: bad mode %d", mode);
+  if (mode == DPS_COEF_GLOBAL_NORM) {
+    global_norm_coef_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(partials, P, n, scale, l2, coef);
+    DPS_LAUNCH_CHECK("dps_guidance_coef");
+    return DPS_OK;
+  }
   const int threads = 128, warps_per_block = threads / 32;
   particle_norms_kernel<<<(n + warps_per_block - 1) / warps_per_block, threads, 0, (cudaStream_t)stream>>>(
       partials, P, n, mode, scale, l2, nullptr, coef);

@@ -276,6 +276,31 @@ int launch_grad(const float* a, int64_t a_stride, const float* b, int64_t b_stri
 }
 }  // namespace
 
+// Per-particle Σ(a − ref)² and Σ|a − ref| as P partial sums per particle (finished by dps_particle_norms): the PSNR /
+// distance bookkeeping of the drivers (compute_metrics.py:93-98).  CTA p of particle n takes the float4 items
+// p, p + P, … of the particle in steps of 256·P — a fixed assignment and a fixed tree, so the sums are reproducible.
+__global__ void __launch_bounds__(256) sqdiff_kernel(const float* __restrict__ a, int64_t a_stride, const float* __restrict__ ref,
+                                                     int64_t ref_stride, int64_t chw, float* __restrict__ partials) {
+  __shared__ float red[64];
+  const int n = blockIdx.y, P = gridDim.x;
+  const float* ap = a + n * a_stride;
+  const float* rp = ref + n * ref_stride;
+  float sq = 0.f, ab = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < chw / 4; i += (int64_t)256 * P) {
+    const float4 u = ldg_stream4(ap + 4 * i);
+    const float4 v = ldg_ro4(rp + 4 * i);
+    const float dx = u.x - v.x, dy = u.y - v.y, dz = u.z - v.z, dw = u.w - v.w;
+    sq += dx * dx + dy * dy + dz * dz + dw * dw;
+    ab += fabsf(dx) + fabsf(dy) + fabsf(dz) + fabsf(dw);
+  }
+  block_sum2(sq, ab, red);
+  if (threadIdx.x == 0) {
+    float* pp = partials + ((int64_t)n * P + blockIdx.x) * 2;
+    pp[0] = sq;
+    pp[1] = ab;
+  }
+}
+
 extern "C" {
 
 int dps_x0_from_eps(const dps_source* src, float* x0, int n, int64_t chw, dps_stream_t stream) {
@@ -318,6 +343,18 @@ int dps_posterior_update_ddim(const dps_source* src, const float* z, const float
                               dps_stream_t stream) {
   return launch_update<true>(src, nullptr, 0, z, g, g_stride, vjp, k, x_next, sample_out, x0_out, n,
                              chw, stream, "dps_posterior_update_ddim");
+}
+
+int dps_particle_sqdiff(const float* a, int64_t a_stride, const float* ref, int64_t ref_stride, int n_particles,
+                        int64_t chw, float* partials, int P, dps_stream_t stream) {
+  DPS_REQUIRE(a && ref && partials && n_particles > 0 && chw > 0 && chw % 4 == 0 && P > 0 && P <= 65535, DPS_ERR_INVALID,
+              "dps_particle_sqdiff: bad arguments (chw must be a multiple of 4)");
+  DPS_REQUIRE(dps_aligned16(a) && dps_aligned16(ref) && a_stride % 4 == 0 && ref_stride % 4 == 0, DPS_ERR_INVALID,
+              "dps_particle_sqdiff: pointers and strides must be 16-byte aligned");
+  sqdiff_kernel<<<dim3((unsigned)P, (unsigned)n_particles), 256, 0, (cudaStream_t)stream>>>(a, a_stride, ref, ref_stride,
+                                                                                             chw, partials);
+  DPS_LAUNCH_CHECK("dps_particle_sqdiff");
+  return DPS_OK;
 }
 
 int dps_q_sample(const float* y, const float* noise, float a, float b, float* out, int64_t n,

@@ -268,6 +268,21 @@ def particle_norms(partials, want_l1=False):
     return (l2, l1) if want_l1 else l2
 
 
+def particle_sqdiff(a, ref, P: int = 32):
+    """Per-particle (‖a − ref‖₂, ‖a − ref‖₁); ref is (1, …) (broadcast) or (n, …).  Two launches: partial sums, finish."""
+    a = _lib.dense(a, "a")
+    ref = _lib.dense(ref, "ref")
+    n = a.shape[0]
+    chw = a[0].numel()
+    if ref.numel() not in (chw, n * chw):
+        raise DpsError(f"reference of {ref.numel()} elements does not match particles of {chw}")
+    ref_stride = 0 if ref.numel() == chw else chw
+    partials = torch.empty((n, P, 2), device=a.device, dtype=torch.float32)
+    check(lib().dps_particle_sqdiff(a.data_ptr(), chw, ref.data_ptr(), ref_stride, n, chw, partials.data_ptr(), P,
+                                    stream_ptr(a.device)), "dps_particle_sqdiff")
+    return particle_norms(partials, want_l1=True)
+
+
 def guidance_coef(partials, mode: int, scale: float):
     """(‖r‖ per particle, coefficient folded into the adjoint): −scale/‖r‖ (mode 1) or −2·scale (mode 2)."""
     n, P, _ = partials.shape

@@ -24,7 +24,7 @@ import functools
 import torch
 
 from . import diffstategrad, kernels
-from ._lib import DpsError
+from ._lib import DPS_COEF_GLOBAL_NORM, DpsError
 from .conditioning import ConditioningMethod, GuidanceSpec
 from .graphed import GraphedEps
 from .operators import B200Operator
@@ -225,6 +225,13 @@ class SpacedSampler:
             self._g3 = torch.zeros((n, C, H, W), device=x.device, dtype=torch.float32)
         return self._g6, self._g3
 
+    def _inv_abs_mean(self, y) -> float:
+        """mean(1/|y|) of the measurement (Poisson likelihood): y is fixed during a run, so it is computed once."""
+        key = (y.data_ptr(), tuple(y.shape))
+        if getattr(self, "_inv_key", None) != key:
+            self._inv_key, self._inv_val = key, float((1.0 / y.abs()).mean())
+        return self._inv_val
+
     def _graphed(self, model, x):
         """The model's forward + input-VJP captured in CUDA graphs for this particle batch (graphed.GraphedEps)."""
         key = (id(model), tuple(x.shape), x.device)
@@ -257,7 +264,14 @@ class SpacedSampler:
         # kernel 1: residual + partial sums, x̂₀ formed on the fly
         r, partials, aux = op.residual(xd, eps_d, k, self.clip_denoised, measurement, **cond_kwargs)
         # kernel 2: ‖r‖ and the per-particle coefficient
-        dist, coef = kernels.guidance_coef(partials, spec.coef_mode, spec.scale)
+        if getattr(method.noiser, "__name__", "gaussian") == "poisson" and spec.kind != "ps_semantic":
+            # Poisson branch of grad_and_value (condition_methods.py:50-55): loss = ‖r‖_F(all particles)·mean(1/|y|);
+            # norm_exp is ignored there, so ps_anneal's ζ_t multiplies the same gradient
+            inv = self._inv_abs_mean(measurement)
+            l2, coef = kernels.guidance_coef(partials, DPS_COEF_GLOBAL_NORM, spec.scale * inv)
+            dist = torch.linalg.norm(l2) * inv            # the scalar the reference returns as `norm`
+        else:
+            dist, coef = kernels.guidance_coef(partials, spec.coef_mode, spec.scale)
         # optional semantic term: gradient w.r.t. x̂₀ of s_t·ℓ_sem (external embedder stays PyTorch)
         extra, sem_dist = None, None
         if spec.semantic is not None:
@@ -333,7 +347,7 @@ class SpacedSampler:
         y = measurement.detach().to(img.device, torch.float32).contiguous()
         method, fn, bound = _resolve_cond_fn(measurement_cond_fn)
         fused = isinstance(method, ConditioningMethod) and isinstance(method.operator, B200Operator) \
-            and getattr(method.noiser, "__name__", "gaussian") == "gaussian" \
+            and getattr(method.noiser, "__name__", "gaussian") in ("gaussian", "poisson") \
             and method.guidance().kind != "none"
         return img, y, method, bound, fused
 

@@ -118,6 +118,13 @@ int dps_guidance_grad(const float* g, int64_t g_stride, const float* vjp, float 
 int dps_apply_gradient(const float* sample, const float* grad, int64_t grad_stride, float* x_next,
                        int n_particles, int64_t chw, dps_stream_t stream);
 
+/* Per-particle partial sums of (a − ref)² and |a − ref| (P per particle, layout (n, P, 2) like the
+ * operators' partials; finish with dps_particle_norms).  ref_stride 0 broadcasts one reference.
+ * Replaces compute_psnr_manual's mean((real − fake)²) (compute_metrics.py:93-98) and the drivers'
+ * per-path distance bookkeeping (sample_condition_batched_ttc.py:183-196).                        */
+int dps_particle_sqdiff(const float* a, int64_t a_stride, const float* ref, int64_t ref_stride,
+                        int n_particles, int64_t chw, float* partials, int P, dps_stream_t stream);
+
 /* q_sample (gaussian_diffusion.py:134-151): out = a·y + b·noise                                 */
 int dps_q_sample(const float* y, const float* noise, float a, float b, float* out, int64_t n_elems,
                  dps_stream_t stream);
@@ -192,6 +199,9 @@ int dps_particle_norms(const float* partials, int P, int n_particles, float* l2,
  *   mode 2: coef = −2·scale        (∇‖r‖², ps_anneal, norm_exp == 2)                            */
 #define DPS_COEF_NORM 1
 #define DPS_COEF_NORM_SQ 2
+/*   mode 3: coef = −scale/‖r‖_F over ALL particles (the Poisson-noise branch of grad_and_value,
+ *           condition_methods.py:50-55; scale = ζ·mean(1/|y|) folded by the caller)              */
+#define DPS_COEF_GLOBAL_NORM 3
 int dps_guidance_coef(const float* partials, int P, int n_particles, int mode, float scale,
                       float* l2, float* coef, dps_stream_t stream);
 

@@ -357,3 +357,19 @@ def best_of_n(distances):
     """best_of_n_simple.py:32-41: per image, argmin over the first n+1 paths, for every n."""
     d = np.asarray(distances)
     return np.stack([np.argmin(d[:, :n + 1], axis=1) for n in range(d.shape[1])], axis=1)
+
+
+def psnr(real, fake):
+    """compute_psnr_manual (compute_metrics.py:93-98): 20·log10(1/√mean((real − fake)²)), one value per particle of
+    `fake` (the drivers call it with one path at a time, sample_condition_batched_ttc.py:191)."""
+    real = np.asarray(real, dtype=np.float32)
+    fake = np.asarray(fake, dtype=np.float32)
+    d = (fake - real).reshape(fake.shape[0], -1).astype(np.float64)
+    mse = (d * d).mean(axis=1)
+    return (20.0 * np.log10(1.0 / np.sqrt(mse))).astype(np.float32)
+
+
+def measurement_distance(y, forward, samples):
+    """‖y − A(sample)‖₂ per particle (the drivers' y_space / the loops' measurement distance, gaussian_diffusion.py:303)."""
+    r = y - forward(samples)
+    return particle_norms(r)[0]

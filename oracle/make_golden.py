@@ -141,14 +141,14 @@ def gen_operators():
 
 
 def run_trace(tag, sampler_name, respacing, method, params, op_name, op_cfg, n, size, seed, use_loop=True, mask=None,
-              noise_sigma=0.05, anneal=False, loop_kwargs=None):
+              noise_sigma=0.05, anneal=False, loop_kwargs=None, noise=None):
     """Run the reference's own loop (or an upstream-arity loop assembled from its classes) and record."""
     torch.manual_seed(seed)
     np.random.seed(seed)
     model = TinyEps(seed=seed)
     with _ref.quiet():
         op = get_operator(op_name, device="cpu", **op_cfg)
-        noiser = get_noise("gaussian", sigma=noise_sigma)
+        noiser = get_noise(**noise) if noise else get_noise("gaussian", sigma=noise_sigma)
         cond = get_conditioning_method(method, op, noiser, **params)
     s = sampler(sampler_name, respacing)
     kw = {"mask": mask} if mask is not None else {}
@@ -307,7 +307,23 @@ def gen_resample_update():
     save("resample_update.npz", **out)
 
 
+def gen_psnr():
+    """compute_psnr_manual of the reference (compute_metrics.py:93-98).  The module imports torchmetrics / lpips
+    (absent here) at the top, so only that function's source is compiled."""
+    import ast
+    src = open("/root/reference/compute_metrics.py").read()
+    fn = [n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "compute_psnr_manual"][0]
+    ns = {"torch": torch}
+    exec(compile(ast.Module([fn], []), "compute_metrics.py", "exec"), ns)
+    g = torch.Generator().manual_seed(3)
+    real = torch.rand(1, 3, 32, 32, generator=g) * 2 - 1
+    fake = real + 0.1 * torch.randn(5, 3, 32, 32, generator=g)
+    vals = np.array([float(ns["compute_psnr_manual"](real, fake[i:i + 1])) for i in range(5)], dtype=np.float32)
+    save("psnr_manual.npz", real=real.numpy(), fake=fake.numpy(), psnr=vals)
+
+
 if __name__ == "__main__":
+    gen_psnr()
     gen_var_types()
     gen_mean_types()
     gen_resample_update()
@@ -337,3 +353,7 @@ if __name__ == "__main__":
               dict(oversample=2.0), n=2, size=64, seed=15, use_loop=False, anneal=True)
     run_trace("ddim_ps_motion", "ddim", "3", "ps", dict(scale=0.3), "motion_blur", dict(kernel_size=61, intensity=0.5),
               n=2, size=64, seed=16, use_loop=False)
+    # Poisson noise model: the other branch of grad_and_value (condition_methods.py:50-55)
+    run_trace("ddpm_ps_poisson_gblur", "ddpm", "4", "ps", dict(scale=0.3), "gaussian_blur",
+              dict(kernel_size=61, intensity=3.0), n=3, size=32, seed=18, use_loop=False,
+              noise=dict(name="poisson", rate=1.0))

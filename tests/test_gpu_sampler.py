@@ -24,12 +24,12 @@ def _exact_fp32():
     yield
 
 
-def build(sampler_name, respacing, method, params, op_name, op_cfg, noise_sigma=0.05):
+def build(sampler_name, respacing, method, params, op_name, op_cfg, noise_sigma=0.05, noise=None):
     from dps_ttc_b200.registry import get_conditioning_method, get_noise, get_operator
     from dps_ttc_b200.sampler import create_sampler
     dev = torch.device("cuda:0")
     op = get_operator(op_name, device=dev, **op_cfg)
-    noiser = get_noise("gaussian", sigma=noise_sigma)
+    noiser = get_noise(**noise) if noise else get_noise("gaussian", sigma=noise_sigma)
     cond = get_conditioning_method(method, op, noiser, **params)
     s = create_sampler(sampler=sampler_name, timestep_respacing=respacing, **DIFF)
     return s, op, cond, dev
@@ -125,6 +125,28 @@ def test_trace_ddpm_ps_inpainting_upstream_arity():
                                    record=False, save_root=None)
     assert close(img.cpu().numpy(), g["final"], 1e-4)
     assert close(dist.cpu().numpy(), g["final_dist"], 1e-5)
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_trace_ddpm_ps_poisson_likelihood(fused):
+    """§8f row 4: the Poisson branch of grad_and_value (condition_methods.py:50-55) — one global norm over all particles
+    times mean(1/|y|) — through the fused kernels (coefficient mode 3) and through the generic autograd path."""
+    g = golden("trace_ddpm_ps_poisson_gblur.npz")
+    s, op, cond, dev = build("ddpm", "4", "ps", dict(scale=0.3), "gaussian_blur", dict(kernel_size=61, intensity=3.0),
+                             noise=dict(name="poisson", rate=1.0))
+    s.noise = tape_from(g, 4, stride=1)
+    s.parity_rng = False
+    model = CpuBridge(TinyEps(seed=18))
+    seen = {}
+    img, dist, _ = s.p_sample_loop(model=model, x_start=torch.from_numpy(g["x_start"]).to(dev),
+                                   measurement=torch.from_numpy(g["y"]).float().to(dev),
+                                   measurement_cond_fn=cond.conditioning, record=False, save_root=None, fused=fused,
+                                   callback=lambda idx, im, d, sd: seen.__setitem__(idx, (im.cpu().numpy(), float(d))))
+    for i, idx in enumerate(reversed(range(4))):
+        assert abs(seen[idx][1] - float(g[f"step{i}_dist"])) <= 1e-4 * float(g[f"step{i}_dist"]), f"norm at step {idx}"
+        if i < 3:
+            assert close(seen[idx][0], g[f"step{i + 1}_x_prev"], 1e-4), f"x after step {idx}"
+    assert close(img.cpu().numpy(), g["final"], 1e-4)
 
 
 def test_trace_ddim_ps_motion_blur():

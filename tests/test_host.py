@@ -156,3 +156,32 @@ def test_semantic_and_anneal_schedules():
     from dps_ttc_b200.schedule import anneal_factor, semantic_scale
     assert semantic_scale(0.7, 0.5, 1.0) == 0.5
     assert abs(anneal_factor(0.5) - 0.5) < 1e-12 and anneal_factor(1.0, amp=2.0) > 1.98
+
+
+def test_pathwise_log_and_best_of_n_curves(tmp_path):
+    """PathwiseLog writes what best_of_n_simple.py loads; its curves equal that script's loop (:32-41) restated literally."""
+    from dps_ttc_b200.driver import PathwiseLog
+    rng = np.random.default_rng(0)
+    n_data, n_max = 3, 6
+    dist, ps = rng.random((n_data, n_max)), rng.random((n_data, n_max)) * 30
+    log = PathwiseLog(n_data, n_max)
+    for i in range(n_data):
+        log.record(i, 0, distances=torch.from_numpy(dist[i, :4]), psnr=ps[i, :4])
+        log.record(i, 4, distances=dist[i, 4:], psnr=torch.from_numpy(ps[i, 4:]))
+    log.save(str(tmp_path))
+    d2 = np.load(os.path.join(tmp_path, "pathwise_distances.npy"))
+    p2 = np.load(os.path.join(tmp_path, "pathwise_psnr.npy"))
+    assert np.array_equal(d2, dist) and np.array_equal(p2, ps)
+    psnr_best = np.zeros((n_data, n_max))
+    for n in range(n_max):                                   # best_of_n_simple.py:32-41
+        best = np.argmin(d2[:, :n + 1], axis=1)
+        for img in range(n_data):
+            psnr_best[img, n] += p2[img, best[img]]
+    assert np.allclose(log.best_of_n()["psnr"], psnr_best.mean(axis=0))
+
+
+def test_driver_refuses_cpu_tensors():
+    from dps_ttc_b200._lib import DpsError
+    from dps_ttc_b200.driver import psnr
+    with pytest.raises(DpsError):
+        psnr(torch.zeros(1, 3, 8, 8), torch.zeros(2, 3, 8, 8))

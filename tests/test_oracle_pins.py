@@ -206,3 +206,9 @@ def test_trace_search_ddpm_greedy():
 def test_best_of_n_rule():
     d = np.array([[3.0, 1.0, 2.0, 0.5], [1.0, 1.0, 0.2, 0.9]])
     assert np.array_equal(O.best_of_n(d), np.array([[0, 1, 1, 3], [0, 0, 2, 2]]))
+
+
+def test_psnr_matches_reference_function():
+    """oracle.psnr against compute_psnr_manual of the reference (compute_metrics.py:93-98), fixture by make_golden.gen_psnr."""
+    g = golden("psnr_manual.npz")
+    assert np.abs(O.psnr(g["real"], g["fake"]) - g["psnr"]).max() <= 5e-6
