@@ -5,10 +5,12 @@
 // keeps only the non-zero taps (dy, dx, w).
 //
 // forward : one CTA stages a strip of x̂₀ with its halo in shared memory, reflect-filled, and every thread
-//           accumulates 8 vertically adjacent outputs of one column.  The non-zero taps are covered by vertical
-//           CHUNKS of 4 (same dx, dy0 … dy0+3, absent taps weigh 0): a chunk loads the 11 tile values under it once
-//           and feeds 32 FFMA from registers — 0.34 LDS per FFMA instead of 1.1 with one tap at a time (a motion
-//           path is 2-5 taps thick in every column, so a chunk is rarely more than half empty).
+//           accumulates 16 vertically adjacent outputs of a column PAIR on packed FFMA2.  The non-zero taps are
+//           covered by vertical CHUNKS of 4 (same dx, dy0 … dy0+3, absent taps weigh 0): a chunk loads the 19 tile
+//           value pairs under it once and feeds 64 FFMA2 (128 FMAs) from registers (a motion path is 2-5 taps thick
+//           in every column, so a chunk is rarely more than half empty).  Chunks with an even dx read their pairs with
+//           one aligned 64-bit load, chunks with an odd dx with two 32-bit loads; the plan sorts the even ones first so
+//           that neither loop branches.  (One column and scalar FFMA per thread before: 409 → see DESIGN.md.)
 // adjoint : A = C·P (P = reflect pad, C = valid correlation) ⇒ Aᵀ = Pᵀ·Cᵀ, done literally in two kernels:
 //           (1) t = Cᵀu on the PADDED domain (H+2Ry, W+2Rx) — the same gather kernel with negated offsets over
 //               a zero-filled tile, no border cases at all — into the operator's workspace (stays in L2);
@@ -43,6 +45,7 @@ struct __align__(16) TapOff {  // shared: the same with the tile offset resolved
 
 struct SparseTables {
   int ntaps = 0;
+  int n_even = 0;  // chunks [0, n_even) have an even dx
   int Ry = 0, Rx = 0;  // halo (Rx rounded up to a multiple of 4)
   Tap* taps_dev = nullptr;
 };
@@ -58,7 +61,7 @@ DPS_DEV int tap_dx(int v) { return (int)(short)(v & 0xffff); }
 // kSW > 0: the tile row stride is the compile-time constant kSW (every LDS of the tap loop gets an immediate offset,
 // no address arithmetic); kSW = 0: stride W + 2·halo computed at run time.
 template <bool kAdjoint, int kSW>
-__global__ void __launch_bounds__(320) sparse_kernel(const Tap* __restrict__ taps_g, int ntaps, int Ry, int Rx, int C,
+__global__ void __launch_bounds__(320) sparse_kernel(const Tap* __restrict__ taps_g, int ntaps, int n_even, int Ry, int Rx, int C,
                                                      int H, int W, int strips, const FwdArgs fa, const AdjArgs aa,
                                                      float* __restrict__ t_out) {
   extern __shared__ __align__(16) float smem[];
@@ -139,46 +142,66 @@ __global__ void __launch_bounds__(320) sparse_kernel(const Tap* __restrict__ tap
   __syncthreads();
 
   float sq = 0.f, ab = 0.f;
-  for (int col = tid; col < OW; col += nthreads) {
+  // items = (column pair, group of kGroup rows); consecutive threads take consecutive pairs of one group
+  const int OW2 = OW / 2;
+  constexpr int kGroups = kRows / kGroup;
+  for (int item = tid; item < OW2 * kGroups; item += nthreads) {
+    const int grp = item / OW2, cp = item - grp * OW2;
+    const int col = 2 * cp, g0 = grp * kGroup;
     // tile element under output (o0+g0, col) with zero tap offset:
     //   forward: image (o0+g0, col)            → tile row g0+Ry,      tile col halo_x+col
     //   adjoint: padded (p, q) = image (p−Ry, q−Rx) → tile row g0+Ry, tile col halo_x+col−Rx
-    const float* base0 = tile + Ry * SW + halo_x + col - (kAdjoint ? Rx : 0);
-#pragma unroll 1
-    for (int g0 = 0; g0 < kRows; g0 += kGroup) {
-      float acc[kGroup];
+    // SW, halo_x, Rx and col are even: the pair under a chunk is 8-byte aligned exactly when the chunk's dx is even
+    const float* base = tile + (Ry + g0) * SW + halo_x + col - (kAdjoint ? Rx : 0);
+    float2 acc[kGroup];
 #pragma unroll
-      for (int j = 0; j < kGroup; ++j) acc[j] = 0.f;
-      const float* base = base0 + g0 * SW;
+    for (int j = 0; j < kGroup; ++j) acc[j] = make_float2(0.f, 0.f);
 #pragma unroll 2
-      for (int t = 0; t < ntaps; ++t) {
-        const float4 w = *reinterpret_cast<const float4*>(taps[t].w);
-        const float* p = base + taps[t].off;
-        float v[kGroup + kChunk - 1];
+    for (int t = 0; t < n_even; ++t) {
+      const float4 w = *reinterpret_cast<const float4*>(taps[t].w);
+      const float2* p = reinterpret_cast<const float2*>(base + taps[t].off);
+      float2 v[kGroup + kChunk - 1];
 #pragma unroll
-        for (int i = 0; i < kGroup + kChunk - 1; ++i) v[i] = p[i * SW];
-#pragma unroll
-        for (int j = 0; j < kGroup; ++j) {
-          acc[j] = fmaf(w.x, v[j], acc[j]);
-          acc[j] = fmaf(w.y, v[j + 1], acc[j]);
-          acc[j] = fmaf(w.z, v[j + 2], acc[j]);
-          acc[j] = fmaf(w.w, v[j + 3], acc[j]);
-        }
-      }
+      for (int i = 0; i < kGroup + kChunk - 1; ++i) v[i] = p[i * (SW / 2)];
 #pragma unroll
       for (int j = 0; j < kGroup; ++j) {
-        const int row = o0 + g0 + j;
-        if (row >= OH) continue;
-        if (!kAdjoint) {
-          const int64_t off = plane + (int64_t)row * W + col;
-          float res = acc[j];
-          if (fa.y) res = __fsub_rn(ldg_ro(fa.y + n * fa.y_stride + off), res);
-          stg_stream(fa.out + (int64_t)n * C * H * W + off, res);
-          sq += res * res;
-          ab += fabsf(res);
-        } else {
-          stg_stream(t_out + (((int64_t)n * C + c) * OH + row) * OW + col, acc[j]);
+        acc[j] = __ffma2_rn(make_float2(w.x, w.x), v[j], acc[j]);
+        acc[j] = __ffma2_rn(make_float2(w.y, w.y), v[j + 1], acc[j]);
+        acc[j] = __ffma2_rn(make_float2(w.z, w.z), v[j + 2], acc[j]);
+        acc[j] = __ffma2_rn(make_float2(w.w, w.w), v[j + 3], acc[j]);
+      }
+    }
+#pragma unroll 2
+    for (int t = n_even; t < ntaps; ++t) {
+      const float4 w = *reinterpret_cast<const float4*>(taps[t].w);
+      const float* p = base + taps[t].off;
+      float2 v[kGroup + kChunk - 1];
+#pragma unroll
+      for (int i = 0; i < kGroup + kChunk - 1; ++i) v[i] = make_float2(p[i * SW], p[i * SW + 1]);
+#pragma unroll
+      for (int j = 0; j < kGroup; ++j) {
+        acc[j] = __ffma2_rn(make_float2(w.x, w.x), v[j], acc[j]);
+        acc[j] = __ffma2_rn(make_float2(w.y, w.y), v[j + 1], acc[j]);
+        acc[j] = __ffma2_rn(make_float2(w.z, w.z), v[j + 2], acc[j]);
+        acc[j] = __ffma2_rn(make_float2(w.w, w.w), v[j + 3], acc[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kGroup; ++j) {
+      const int row = o0 + g0 + j;
+      if (row >= OH) continue;
+      if (!kAdjoint) {
+        const int64_t off = plane + (int64_t)row * W + col;
+        float2 res = acc[j];
+        if (fa.y) {
+          const float2 yv = __ldg(reinterpret_cast<const float2*>(fa.y + n * fa.y_stride + off));
+          res = make_float2(__fsub_rn(yv.x, res.x), __fsub_rn(yv.y, res.y));
         }
+        stg_stream2(fa.out + (int64_t)n * C * H * W + off, res);
+        sq += res.x * res.x + res.y * res.y;
+        ab += fabsf(res.x) + fabsf(res.y);
+      } else {
+        stg_stream2(t_out + (((int64_t)n * C + c) * OH + row) * OW + col, acc[j]);
       }
     }
   }
@@ -277,12 +300,17 @@ int sparse_create(dps_operator* op, const float* kernel, int ksize) {
     }
   }
   DPS_REQUIRE(!taps.empty(), DPS_ERR_INVALID, "blur: kernel is all zero");
+  // even-dx chunks first (aligned 64-bit pair loads), odd-dx chunks after them
+  std::stable_partition(taps.begin(), taps.end(), [](const Tap& tp) { return ((tp.dydx & 0xffff) & 1) == 0; });
+  int n_even = 0;
+  for (const Tap& tp : taps) n_even += ((tp.dydx & 0xffff) & 1) == 0;
   DPS_REQUIRE(Ry < op->H && Rx < op->W, DPS_ERR_UNSUPPORTED, "sparse blur: kernel radius (%d,%d) reaches the image size", Ry, Rx);
   Rx = (Rx + 3) / 4 * 4;
   if (Rx == 0) Rx = 4;
   DPS_REQUIRE(op->W % 4 == 0, DPS_ERR_UNSUPPORTED, "sparse blur: W must be a multiple of 4");
   SparseTables* t = new SparseTables();
   t->ntaps = (int)taps.size();
+  t->n_even = n_even;
   t->Ry = Ry;
   t->Rx = Rx;
   op->sparse = t;
@@ -316,13 +344,13 @@ int sparse_forward(const dps_operator* op, const FwdArgs& a, cudaStream_t st) {
   bool fx;
   const int SW = sparse_stride(op, false, &fx);
   if (sparse_fixed(op, false) && SW == kSWFixedS)
-    sparse_kernel<false, kSWFixedS><<<grid, 256, sparse_smem(op, false), st>>>(t->taps_dev, t->ntaps, t->Ry, t->Rx, op->C,
+    sparse_kernel<false, kSWFixedS><<<grid, 256, sparse_smem(op, false), st>>>(t->taps_dev, t->ntaps, t->n_even, t->Ry, t->Rx, op->C,
                                                                                op->H, op->W, strips, a, dummy, nullptr);
   else if (sparse_fixed(op, false))
-    sparse_kernel<false, kSWFixed><<<grid, 256, sparse_smem(op, false), st>>>(t->taps_dev, t->ntaps, t->Ry, t->Rx, op->C,
+    sparse_kernel<false, kSWFixed><<<grid, 256, sparse_smem(op, false), st>>>(t->taps_dev, t->ntaps, t->n_even, t->Ry, t->Rx, op->C,
                                                                               op->H, op->W, strips, a, dummy, nullptr);
   else
-    sparse_kernel<false, 0><<<grid, 256, sparse_smem(op, false), st>>>(t->taps_dev, t->ntaps, t->Ry, t->Rx, op->C, op->H,
+    sparse_kernel<false, 0><<<grid, 256, sparse_smem(op, false), st>>>(t->taps_dev, t->ntaps, t->n_even, t->Ry, t->Rx, op->C, op->H,
                                                                        op->W, strips, a, dummy, nullptr);
   DPS_LAUNCH_CHECK("sparse_blur_forward");
   return DPS_OK;
@@ -341,13 +369,13 @@ int sparse_adjoint(const dps_operator* op, const AdjArgs& a, cudaStream_t st) {
   bool fx;
   const int SW = sparse_stride(op, true, &fx);
   if (sparse_fixed(op, true) && SW == kSWFixedS)
-    sparse_kernel<true, kSWFixedS><<<grid, threads, sparse_smem(op, true), st>>>(t->taps_dev, t->ntaps, t->Ry, t->Rx, op->C,
+    sparse_kernel<true, kSWFixedS><<<grid, threads, sparse_smem(op, true), st>>>(t->taps_dev, t->ntaps, t->n_even, t->Ry, t->Rx, op->C,
                                                                                  op->H, op->W, strips, dummy, a, scratch);
   else if (sparse_fixed(op, true))
-    sparse_kernel<true, kSWFixed><<<grid, threads, sparse_smem(op, true), st>>>(t->taps_dev, t->ntaps, t->Ry, t->Rx, op->C,
+    sparse_kernel<true, kSWFixed><<<grid, threads, sparse_smem(op, true), st>>>(t->taps_dev, t->ntaps, t->n_even, t->Ry, t->Rx, op->C,
                                                                                 op->H, op->W, strips, dummy, a, scratch);
   else
-    sparse_kernel<true, 0><<<grid, threads, sparse_smem(op, true), st>>>(t->taps_dev, t->ntaps, t->Ry, t->Rx, op->C, op->H,
+    sparse_kernel<true, 0><<<grid, threads, sparse_smem(op, true), st>>>(t->taps_dev, t->ntaps, t->n_even, t->Ry, t->Rx, op->C, op->H,
                                                                          op->W, strips, dummy, a, scratch);
   DPS_LAUNCH_CHECK("sparse_blur_adjoint_t");
   dim3 fgrid((unsigned)((op->H * op->W + 255) / 256), (unsigned)op->C, (unsigned)a.n);
