@@ -32,7 +32,7 @@ constexpr int kLF = kL + 1;           // row stride of the float planes staged p
 constexpr int kImg = 256;
 constexpr int kPad = 64;
 constexpr int kThreads = 256;
-constexpr int kRowsPerCta = 16;  // K1 / A2: image rows per CTA → 8 packed FFTs (56 KB of shared memory → 4 CTAs per SM)
+constexpr int kRowsPerCta = 16;  // K1 / A2: image rows per CTA → 8 packed FFTs (55.9 KB of shared memory → 4 CTAs per SM)
 constexpr int kColsPerCta = 8;   // K2 / A1: spectrum columns per CTA
 constexpr int kColGroups = (kHalf + kColsPerCta - 1) / kColsPerCta;  // 25
 // the adjoint prefers wider CTAs: its scattered reads of r coalesce into 64-byte runs with 16 columns
@@ -127,6 +127,15 @@ DPS_DEV void dft6(float2* v) {
   v[2] = cadd(e2, t2); v[5] = csub(e2, t2);   // W6^5 = −W6^2
 }
 
+// Twiddle exp(−2πi j/384), j ∈ [0,384), from the half table in shared memory: tw[j+192] = −tw[j].  Halving the table
+// (1.5 KB instead of 3 KB) is what lets FOUR 8-sequence CTAs (57 KB each) share an SM instead of three.
+constexpr int kTW = kL / 2;
+DPS_DEV float2 twid(const float2* tw, int j) {
+  const bool hi = j >= kTW;
+  const float2 t = tw[hi ? j - kTW : j];
+  return hi ? make_float2(-t.x, -t.y) : t;
+}
+
 // `nfft` independent forward FFTs of length 384, sequence f at a[f*384 ...]; the result lands in b.
 // Stockham autosort, radices 8·8·6 (natural order in, natural order out).  All threads must call it.
 __device__ void fft384_batch(float2* a, float2* b, const float2* tw, int nfft) {
@@ -154,7 +163,7 @@ __device__ void fft384_batch(float2* a, float2* b, const float2* tw, int nfft) {
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
       v[r] = src[54 * r];
-      if (r) v[r] = cmul(v[r], tw[6 * k * r]);
+      if (r) v[r] = cmul(v[r], twid(tw, 6 * k * r));
     }
     dft8(v);
 #pragma unroll
@@ -170,7 +179,7 @@ __device__ void fft384_batch(float2* a, float2* b, const float2* tw, int nfft) {
 #pragma unroll
     for (int r = 0; r < 6; ++r) {
       v[r] = src[72 * r];
-      if (r) v[r] = cmul(v[r], tw[j * r]);
+      if (r) v[r] = cmul(v[r], twid(tw, j * r));
     }
     dft6(v);
 #pragma unroll
@@ -190,10 +199,10 @@ DPS_DEV PhaseSmem carve(float* smem, int nfft) {
   s.a = reinterpret_cast<float2*>(smem);
   s.b = s.a + nfft * kLP;
   s.tw = s.b + nfft * kLP;
-  s.red = reinterpret_cast<float*>(s.tw + kL);
+  s.red = reinterpret_cast<float*>(s.tw + kTW);
   return s;
 }
-size_t smem_bytes(int nfft) { return sizeof(float2) * ((size_t)2 * nfft * kLP + kL) + 64 * sizeof(float); }
+size_t smem_bytes(int nfft) { return sizeof(float2) * ((size_t)2 * nfft * kLP + kTW) + 64 * sizeof(float); }
 
 // aux layout per particle (floats): [phase: C·193·384·2][scratch: C·193·256·2]
 DPS_DEV float2* aux_phase(float* aux, int n, int C, int c) {
@@ -205,7 +214,7 @@ DPS_DEV float2* aux_scratch(float* aux, int n, int C, int c) {
 }
 
 // ---- K1: row transforms of the 256 image rows, two real rows per complex FFT ---------------------
-__global__ void __launch_bounds__(kThreads) phase_rows_fwd(const FwdArgs fa, const float2* __restrict__ tw_g, int C) {
+__global__ void __launch_bounds__(kThreads, 4) phase_rows_fwd(const FwdArgs fa, const float2* __restrict__ tw_g, int C) {
   extern __shared__ __align__(16) float smem[];
   constexpr int nfft = kRowsPerCta / 2;
   PhaseSmem s = carve(smem, nfft);
@@ -213,7 +222,7 @@ __global__ void __launch_bounds__(kThreads) phase_rows_fwd(const FwdArgs fa, con
   const int groups = kImg / kRowsPerCta;
   const int grp = blockIdx.x % groups, c = blockIdx.x / groups, n = blockIdx.y;
   const int r0 = grp * kRowsPerCta;
-  stage_async(reinterpret_cast<float*>(s.tw), reinterpret_cast<const float*>(tw_g), 2 * kL, tid, kThreads);
+  stage_async(reinterpret_cast<float*>(s.tw), reinterpret_cast<const float*>(tw_g), 2 * kTW, tid, kThreads);
   // zero the padding columns [0,64) and [320,384) of every sequence
   for (int i = tid; i < nfft * 2 * kPad; i += kThreads) {
     const int f = i / (2 * kPad), q = i - f * (2 * kPad);
@@ -258,7 +267,7 @@ __global__ void __launch_bounds__(kThreads) phase_rows_fwd(const FwdArgs fa, con
 DPS_DEV int shift_idx(int k) { return k + kL / 2 >= kL ? k - kL / 2 : k + kL / 2; }  // fftshift position of bin k
 
 // ---- K2: column transforms, magnitude, residual, partial sums, unit phase -----------------------
-__global__ void __launch_bounds__(kThreads, 3) phase_cols_fwd(const FwdArgs fa, const float2* __restrict__ tw_g, int C) {
+__global__ void __launch_bounds__(kThreads, 4) phase_cols_fwd(const FwdArgs fa, const float2* __restrict__ tw_g, int C) {
   extern __shared__ __align__(16) float smem[];
   constexpr int nfft = kColsPerCta;
   PhaseSmem s = carve(smem, nfft);
@@ -266,7 +275,7 @@ __global__ void __launch_bounds__(kThreads, 3) phase_cols_fwd(const FwdArgs fa, 
   const int grp = blockIdx.x % kColGroups, c = blockIdx.x / kColGroups, n = blockIdx.y;
   const int k20 = grp * kColsPerCta;
   const int ncols = min(kColsPerCta, kHalf - k20);
-  stage_async(reinterpret_cast<float*>(s.tw), reinterpret_cast<const float*>(tw_g), 2 * kL, tid, kThreads);
+  stage_async(reinterpret_cast<float*>(s.tw), reinterpret_cast<const float*>(tw_g), 2 * kTW, tid, kThreads);
   for (int i = tid; i < nfft * 2 * kPad; i += kThreads) {
     const int f = i / (2 * kPad), q = i - f * (2 * kPad);
     s.a[f * kLP + P(q < kPad ? q : kImg + q)] = make_float2(0.f, 0.f);
@@ -368,7 +377,7 @@ __global__ void __launch_bounds__(kThreads) phase_cols_adj(const AdjArgs aa, flo
   const int grp = blockIdx.x % kColGroupsAdj, c = blockIdx.x / kColGroupsAdj, n = blockIdx.y;
   const int k20 = grp * kColsAdj;
   const int ncols = min(kColsAdj, kHalf - k20);
-  stage_async(reinterpret_cast<float*>(s.tw), reinterpret_cast<const float*>(tw_g), 2 * kL, tid, kThreads);
+  stage_async(reinterpret_cast<float*>(s.tw), reinterpret_cast<const float*>(tw_g), 2 * kTW, tid, kThreads);
   const float* r = aa.r + ((int64_t)n * C + c) * kL * kL;
   const float2* ph = aux_phase(aux_rw, n, C, c);
   // symmetrised cotangent (coalesced over the CTA's columns), staged as floats in s.b
@@ -420,7 +429,7 @@ __global__ void __launch_bounds__(kThreads) phase_rows_adj(const AdjArgs aa, con
   const int groups = kImg / kRowsAdj;
   const int grp = blockIdx.x % groups, c = blockIdx.x / groups, n = blockIdx.y;
   const int r0 = grp * kRowsAdj;
-  stage_async(reinterpret_cast<float*>(s.tw), reinterpret_cast<const float*>(tw_g), 2 * kL, tid, kThreads);
+  stage_async(reinterpret_cast<float*>(s.tw), reinterpret_cast<const float*>(tw_g), 2 * kTW, tid, kThreads);
   const float2* t = aux_scratch(const_cast<float*>(aux_r), n, C, c);
   // X[k] = T1[k] + i·T2[k] with T[384−k] = conj(T[k]) for k > 192
   batched_copy<nfft * kL, 12>(
