@@ -398,11 +398,11 @@ def run_b200(args, rank, world, local_rank):
     dom = max((k for k in ktab if alg_bytes.get(k, 0) > 0 and ktab[k]["mean_us"]),
               key=lambda k: ktab[k]["mean_us"] * ktab[k]["launches"])
     achieved = ktab[dom]["gbs"]
-    # dram__bytes_read.sum + dram__bytes_write.sum per launch of the same kernels at the same size (N=8, SR x4), from
-    # ncu passes over this very command (profiles/r1d_bench_graft_launches.csv.gz, r1d_ncu_bench_kernels_n8.csv).  Reads
-    # equal the algorithmic input bytes; the outputs were still in L2 when the kernel ended (no write-back yet), hence
-    # traffic < algorithmic bytes.
-    ncu_traffic = {"resize_forward": 12657082 + 0, "resize_adjoint": 13019507 + 0, "posterior_update_ddpm": 37760922 + 256}
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch of the same kernels at the same size (N=8, SR x4), mean over
+    # the launches of an ncu pass over this very command (profiles/r1f_bench_graft_launches.csv.gz,
+    # r1f_ncu_bench_kernels_n8.csv).  Reads equal the algorithmic input bytes; the outputs were still in L2 when the kernel
+    # ended (no write-back yet), hence traffic < algorithmic bytes.
+    ncu_traffic = {"resize_forward": 12650227 + 0, "resize_adjoint": 13016415 + 0, "posterior_update_ddpm": 37760968 + 2151}
     traffic = ncu_traffic.get(dom) if (n == 8 and args.workload == "c2") else None
     roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
