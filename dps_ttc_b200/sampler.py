@@ -122,8 +122,9 @@ class SpacedSampler:
         self.model_mean_type = model_mean_type
         if model_var_type not in self._VAR_MODES:
             raise NameError(f"Name {model_var_type} is not defined.")
-        if dynamic_threshold:
-            raise NotImplementedError("dynamic_threshold (quantile clipping) is not covered (SURVEY §8f row 4)")
+        if dynamic_threshold and model_mean_type != "epsilon":
+            raise NotImplementedError("dynamic_threshold is covered for model_mean_type='epsilon' (the configured processor)")
+        self.dynamic_threshold = bool(dynamic_threshold)
         self.schedule = Schedule(betas, use_timesteps, rescale_timesteps)
         s = self.schedule
         self.betas, self.num_timesteps, self.timestep_map = s.betas, s.num_timesteps, s.timestep_map
@@ -166,6 +167,18 @@ class SpacedSampler:
             raise DpsError(f"model_var_type={self.model_var_type} needs a model with 2·C output channels")
         return out, out, None
 
+    # -- dynamic thresholding (process_xstart, posterior_mean_variance.py:40-45; util/img_utils.py:237-249) -----------
+    # x̂₀ = clip(pre·quantile(|pre|, 0.95)) over the WHOLE particle batch, differentiated through the quantile.  At t ≈ T the
+    # product pre·s is ~10⁴ before clipping, so x̂₀ only matches the reference to 1e-4 if it is rounded exactly where the
+    # reference rounds it (folding s into c1, c2 — which the fused kernels would need — is off by ~3e-3).  Samplers with
+    # dynamic_threshold=True therefore take the generic autograd path: this torch restatement for x̂₀ / mean / sample, the
+    # B200 operator kernels (forward + adjoint through autograd) for the guidance.
+    def _process_xstart(self, pre):
+        """torch restatement (differentiable, like the reference: autograd flows through the quantile too)."""
+        if self.dynamic_threshold:
+            pre = torch.clip(pre * torch.quantile(pre.abs(), 0.95), -1.0, 1.0)
+        return pre.clamp(-1, 1) if self.clip_denoised else pre
+
     def _needs_z(self, k):
         return bool(k.noise_on and (self.kind == "ddpm" or k.ddim_sigma != 0.0))
 
@@ -189,7 +202,7 @@ class SpacedSampler:
         k = self._consts(self._idx(t))
         _, eps, v = self._model_out(model, x, k)
         pre = k.c1 * x - k.c2 * eps
-        x0 = pre.clamp(-1, 1) if self.clip_denoised else pre
+        x0 = self._process_xstart(pre)
         mean = eps if k.mean_mode else k.p1 * x0 + k.p2 * x      # previous_x: the model predicts the mean itself
         if self.var_mode == 0:
             frac = (v + 1.0) / 2.0
@@ -207,13 +220,32 @@ class SpacedSampler:
         k = self._consts(idx)
         out, eps, v = self._model_out(model, x, k)
         pre = k.c1 * x - k.c2 * eps
-        x0 = pre.clamp(-1, 1) if self.clip_denoised else pre
+        x0 = self._process_xstart(pre)
         z = self.noise.z(idx, x)
         xd, ed = x.detach(), eps.detach()
+        if self.dynamic_threshold:
+            return {"sample": self._torch_sample(x, eps, v, x0, z, k), "pred_xstart": x0}
         sample, _, _ = kernels.posterior_update(self.kind, xd, ed, None if v is None else v.detach(), z, k,
                                                 clip=self.clip_denoised, var_mode=self.var_mode,
                                                 max_log=self._max_log(k))
         return {"sample": sample, "pred_xstart": x0}
+
+    def _torch_sample(self, x, eps, v, x0, z, k):
+        """DDPM.p_sample / DDIM.p_sample (:468-509) in torch, for the dynamic-threshold path (x̂₀ comes from
+        _process_xstart and cannot be recomputed inside a kernel)."""
+        if self.kind == "ddim":
+            eps2 = (k.c1 * x - x0) / k.c2
+            sample = x0 * k.ddim_sa + k.ddim_sb * eps2
+            return sample + k.ddim_sigma * z if (k.noise_on and k.ddim_sigma != 0.0) else sample
+        mean = k.p1 * x0 + k.p2 * x
+        if self.var_mode == 0:
+            frac = (v + 1.0) / 2.0
+            logvar = frac * k.max_log + (1 - frac) * k.min_log
+        elif self.var_mode == 1:
+            logvar = torch.full_like(x, self._max_log(k))
+        else:
+            logvar = v
+        return mean + torch.exp(0.5 * logvar) * z if k.noise_on else mean
 
     # -- the fused guided step --------------------------------------------------------------------
     def _buffers(self, x):
@@ -261,8 +293,9 @@ class SpacedSampler:
         C = x.shape[1]
         eps_d = out_d[:, :C] if out_d.shape[1] == 2 * C else out_d
         v_d = out_d[:, C:] if out_d.shape[1] == 2 * C else None
+        clip = self.clip_denoised
         # kernel 1: residual + partial sums, x̂₀ formed on the fly
-        r, partials, aux = op.residual(xd, eps_d, k, self.clip_denoised, measurement, **cond_kwargs)
+        r, partials, aux = op.residual(xd, eps_d, k, clip, measurement, **cond_kwargs)
         # kernel 2: ‖r‖ and the per-particle coefficient
         if getattr(method.noiser, "__name__", "gaussian") == "poisson" and spec.kind != "ps_semantic":
             # Poisson branch of grad_and_value (condition_methods.py:50-55): loss = ‖r‖_F(all particles)·mean(1/|y|);
@@ -275,7 +308,7 @@ class SpacedSampler:
         # optional semantic term: gradient w.r.t. x̂₀ of s_t·ℓ_sem (external embedder stays PyTorch)
         extra, sem_dist = None, None
         if spec.semantic is not None:
-            x0 = kernels.x0_from_eps(xd, eps_d, k, self.clip_denoised).requires_grad_(True)
+            x0 = kernels.x0_from_eps(xd, eps_d, k, clip).requires_grad_(True)
             with torch.enable_grad():
                 sem_loss, sem_dist = spec.semantic(x0)
                 extra = torch.autograd.grad(sem_loss.sum(), x0)[0].contiguous()
@@ -287,7 +320,7 @@ class SpacedSampler:
         else:
             g6, g3 = self._buffers(xd)
             g = g6[:, :C] if two_c else g3
-        op.cotangent(r, coef, xd, eps_d, k, self.clip_denoised, extra, out=g, aux=aux, **cond_kwargs)
+        op.cotangent(r, coef, xd, eps_d, k, clip, extra, out=g, aux=aux, **cond_kwargs)
         # UNet VJP
         vjp = None
         if gm is not None:
@@ -298,11 +331,11 @@ class SpacedSampler:
         if z is None and self._needs_z(k):
             z = self.noise.z(idx, xd)
         if dsg:
-            sample, _, _ = kernels.posterior_update(self.kind, xd, eps_d, v_d, z, k, clip=self.clip_denoised,
+            sample, _, _ = kernels.posterior_update(self.kind, xd, eps_d, v_d, z, k, clip=clip,
                                                     var_mode=self.var_mode, max_log=self._max_log(k))
             x_next = diffstategrad.projected_update(sample, kernels.guidance_grad(g, vjp, k))
         else:
-            x_next, _, _ = kernels.posterior_update(self.kind, xd, eps_d, v_d, z, k, clip=self.clip_denoised, g=g,
+            x_next, _, _ = kernels.posterior_update(self.kind, xd, eps_d, v_d, z, k, clip=clip, g=g,
                                                     vjp=vjp, var_mode=self.var_mode, max_log=self._max_log(k))
         if spec.project:  # mcg: x_t = operator.project(x_t, noisy_measurement)
             x_next = method.project(data=x_next, noisy_measurement=noisy_measurement, **cond_kwargs)
@@ -348,7 +381,7 @@ class SpacedSampler:
         method, fn, bound = _resolve_cond_fn(measurement_cond_fn)
         fused = isinstance(method, ConditioningMethod) and isinstance(method.operator, B200Operator) \
             and getattr(method.noiser, "__name__", "gaussian") in ("gaussian", "poisson") \
-            and method.guidance().kind != "none"
+            and method.guidance().kind != "none" and not self.dynamic_threshold
         return img, y, method, bound, fused
 
     # -- base loop (GaussianDiffusion.p_sample_loop, :175-303) --------------------------------------
@@ -447,8 +480,11 @@ class SearchDDPM(DDPM):
             with torch.no_grad():
                 _, eps, v = self._model_out(model, img, k)
                 z = self.noise.z(idx, img)
-                img, _, _ = kernels.posterior_update("ddpm", img, eps, v, z, k, clip=self.clip_denoised,
-                                                     var_mode=self.var_mode, max_log=self._max_log(k))
+                if self.dynamic_threshold:
+                    img = self._torch_sample(img, eps, v, self._process_xstart(k.c1 * img - k.c2 * eps), z, k)
+                else:
+                    img, _, _ = kernels.posterior_update("ddpm", img, eps, v, z, k, clip=self.clip_denoised,
+                                                         var_mode=self.var_mode, max_log=self._max_log(k))
                 _, partials, _ = operator.residual(img, y=y, **bound)      # ‖y − A(x_{t−1})‖₂, :626-630
                 costs = kernels.particle_norms(partials)
                 if shards is None:

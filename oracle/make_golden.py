@@ -78,9 +78,9 @@ class Recorder:
         torch.randn_like, torch.multinomial = self._randn_like, self._multinomial
 
 
-def sampler(name, respacing):
+def sampler(name, respacing, **overrides):
     with _ref.quiet():
-        return create_sampler(sampler=name, timestep_respacing=respacing, **DIFF)
+        return create_sampler(sampler=name, timestep_respacing=respacing, **{**DIFF, **overrides})
 
 
 # ---------------------------------------------------------------------------------------------
@@ -141,7 +141,7 @@ def gen_operators():
 
 
 def run_trace(tag, sampler_name, respacing, method, params, op_name, op_cfg, n, size, seed, use_loop=True, mask=None,
-              noise_sigma=0.05, anneal=False, loop_kwargs=None, noise=None):
+              noise_sigma=0.05, anneal=False, loop_kwargs=None, noise=None, diffusion=None):
     """Run the reference's own loop (or an upstream-arity loop assembled from its classes) and record."""
     torch.manual_seed(seed)
     np.random.seed(seed)
@@ -150,7 +150,7 @@ def run_trace(tag, sampler_name, respacing, method, params, op_name, op_cfg, n, 
         op = get_operator(op_name, device="cpu", **op_cfg)
         noiser = get_noise(**noise) if noise else get_noise("gaussian", sigma=noise_sigma)
         cond = get_conditioning_method(method, op, noiser, **params)
-    s = sampler(sampler_name, respacing)
+    s = sampler(sampler_name, respacing, **(diffusion or {}))
     kw = {"mask": mask} if mask is not None else {}
     x_true = torch.rand(1, 3, size, size) * 2 - 1
     y = noiser(op.forward(x_true, **kw)).detach()
@@ -357,3 +357,7 @@ if __name__ == "__main__":
     run_trace("ddpm_ps_poisson_gblur", "ddpm", "4", "ps", dict(scale=0.3), "gaussian_blur",
               dict(kernel_size=61, intensity=3.0), n=3, size=32, seed=18, use_loop=False,
               noise=dict(name="poisson", rate=1.0))
+    # dynamic thresholding: x̂₀ = clip(pre·quantile(|pre|, 0.95)) over the whole batch, differentiated through the quantile
+    run_trace("ddpm_ps_dynthresh_sr", "ddpm", "4", "ps", dict(scale=0.3), "super_resolution",
+              dict(in_shape=(1, 3, 32, 32), scale_factor=4), n=3, size=32, seed=19, use_loop=False,
+              diffusion=dict(dynamic_threshold=True))

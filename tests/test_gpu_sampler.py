@@ -149,6 +149,32 @@ def test_trace_ddpm_ps_poisson_likelihood(fused):
     assert close(img.cpu().numpy(), g["final"], 1e-4)
 
 
+@pytest.mark.parametrize("fused", [True, False])
+def test_trace_ddpm_ps_dynamic_threshold(fused):
+    """§8f row 4: dynamic_threshold=True — x̂₀ = clip(pre·quantile(|pre|, 0.95)) over the whole batch, the gradient flowing
+    through the quantile's two order statistics — against the reference's own classes (upstream-arity loop)."""
+    g = golden("trace_ddpm_ps_dynthresh_sr.npz")
+    from dps_ttc_b200.registry import get_conditioning_method, get_noise, get_operator
+    from dps_ttc_b200.sampler import create_sampler
+    dev = torch.device("cuda:0")
+    op = get_operator("super_resolution", device=dev, in_shape=(1, 3, 32, 32), scale_factor=4)
+    cond = get_conditioning_method("ps", op, get_noise("gaussian", sigma=0.05), scale=0.3)
+    s = create_sampler(sampler="ddpm", timestep_respacing="4", **{**DIFF, "dynamic_threshold": True})
+    s.noise = tape_from(g, 4, stride=1)
+    s.parity_rng = False
+    model = CpuBridge(TinyEps(seed=19))
+    seen = {}
+    img, dist, _ = s.p_sample_loop(model=model, x_start=torch.from_numpy(g["x_start"]).to(dev),
+                                   measurement=torch.from_numpy(g["y"]).to(dev),
+                                   measurement_cond_fn=cond.conditioning, record=False, save_root=None, fused=fused,
+                                   callback=lambda idx, im, d, sd: seen.__setitem__(idx, (im.cpu().numpy(), d.cpu().numpy())))
+    for i, idx in enumerate(reversed(range(4))):
+        assert close(seen[idx][1], g[f"step{i}_dist"], 1e-5), f"distance at step {idx}"
+        if i < 3:
+            assert close(seen[idx][0], g[f"step{i + 1}_x_prev"], 1e-4), f"x after step {idx}"
+    assert close(img.cpu().numpy(), g["final"], 1e-4)
+
+
 def test_trace_ddim_ps_motion_blur():
     g = golden("trace_ddim_ps_motion.npz")
     s, op, cond, dev = build("ddim", "3", "ps", dict(scale=0.3), "motion_blur", dict(kernel_size=61, intensity=0.5))

@@ -118,8 +118,9 @@ def test_sampler_construction_and_errors():
         create_sampler(sampler="ddpm", **{**cfg, "model_mean_type": "nope"})
     with pytest.raises(NotImplementedError):
         create_sampler(sampler="ddim", **{**cfg, "model_mean_type": "previous_x"})
+    assert create_sampler(sampler="ddpm", **{**cfg, "dynamic_threshold": True}).dynamic_threshold is True
     with pytest.raises(NotImplementedError):
-        create_sampler(sampler="ddpm", **{**cfg, "dynamic_threshold": True})
+        create_sampler(sampler="ddpm", **{**cfg, "dynamic_threshold": True, "model_mean_type": "start_x"})
     with pytest.raises(NameError):
         create_sampler(sampler="nope", **cfg)
     with pytest.raises(ValueError):
@@ -185,3 +186,15 @@ def test_driver_refuses_cpu_tensors():
     from dps_ttc_b200.driver import psnr
     with pytest.raises(DpsError):
         psnr(torch.zeros(1, 3, 8, 8), torch.zeros(2, 3, 8, 8))
+
+
+def test_dynamic_threshold_torch_restatement_matches_reference():
+    """_process_xstart (used by the generic autograd path) against the reference's dynamic_thresholding + clamp
+    (posterior_mean_variance.py:40-45, util/img_utils.py:237-249), recorded in the dynamic-threshold trace."""
+    from dps_ttc_b200.sampler import create_sampler
+    cfg = dict(steps=1000, noise_schedule="linear", model_mean_type="epsilon", model_var_type="learned_range",
+               dynamic_threshold=True, clip_denoised=True, rescale_timesteps=True)
+    s = create_sampler(sampler="ddpm", timestep_respacing="4", **cfg)
+    pre = torch.randn(3, 3, 16, 16, generator=torch.Generator().manual_seed(0)) * 2
+    want = torch.clip(pre * torch.quantile(pre.abs(), 0.95), -1.0, 1.0).clamp(-1, 1)
+    assert torch.equal(s._process_xstart(pre), want)
