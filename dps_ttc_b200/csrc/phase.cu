@@ -301,14 +301,31 @@ __global__ void __launch_bounds__(kThreads, 4) phase_cols_fwd(const FwdArgs fa, 
   float2* ph = aux_phase(fa.aux, n, C, c);
   float* amp = reinterpret_cast<float*>(s.a);  // (nfft, kLF)
   const float inv_l = 1.0f / (float)kL;
-#pragma unroll 4
-  for (int i = tid; i < ncols * kL; i += kThreads) {
-    const int f = i / kL, k1 = i - f * kL;
-    const float2 F = s.b[f * kLP + P(k1)];
-    const float mag = sqrtf(F.x * F.x + F.y * F.y);
-    const float inv = mag > 0.f ? 1.0f / mag : 0.f;
-    ph[(int64_t)(k20 + f) * kL + k1] = make_float2(F.x * inv, -F.y * inv);
-    amp[f * kLF + k1] = mag * inv_l;
+  {
+    // one spectrum column per warp, bins k1 = lane + 32·j: P(k1) = lane + (lane >> 3) + 36·j, so every address below is a
+    // per-thread base plus a compile-time offset; the unit phase goes out in 256-byte runs.
+    static_assert(kColsPerCta * 32 == kThreads && kL % 32 == 0, "one warp per spectrum column");
+    const int f = tid >> 5, lane = tid & 31;
+    if (f < ncols) {
+      const float2* fb = s.b + f * kLP + lane + (lane >> 3);
+      float2* php = ph + (int64_t)(k20 + f) * kL + lane;
+      float* ampp = amp + f * kLF + lane;
+#pragma unroll
+      for (int j = 0; j < kL / 32; ++j) {
+        const float2 F = fb[36 * j];
+        // |F| and 1/|F| without the slow paths of sqrtf and the division: rsqrt.approx (2 ulp) refined by one Newton
+        // step, then |F| = m·r corrected by its residual — both within 1 ulp of the correctly rounded values.
+        const float m2 = fmaf(F.x, F.x, F.y * F.y);
+        float r = rsqrtf(m2);
+        r = fmaf(r, fmaf(-0.5f * m2 * r, r, 0.5f), r);
+        float mag = m2 * r;
+        mag = fmaf(fmaf(-mag, mag, m2), 0.5f * r, mag);
+        const bool nz = m2 > 0.f;
+        const float inv = nz ? r : 0.f;
+        php[32 * j] = make_float2(F.x * inv, -F.y * inv);
+        ampp[32 * j] = nz ? mag * inv_l : 0.f;
+      }
+    }
   }
   __syncthreads();
   // outputs: direct position (u, v) = shift(k1, k2) and, for 0 < k2 < 192, the mirror shift(−k1, −k2)
