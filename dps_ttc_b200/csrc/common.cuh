@@ -125,26 +125,6 @@ DPS_DEV void block_sum2(float& a, float& b, float* red) {
   __syncthreads();
 }
 
-// The same tree for `nw` warps that synchronise on named barrier `bar_id` (a subset of a CTA whose other warps do
-// something else, e.g. a TMA producer): bit-identical to block_sum2 of a CTA of nw warps.
-DPS_DEV void group_sum2(float& a, float& b, float* red, int nw, int bar_id) {
-  a = warp_sum(a);
-  b = warp_sum(b);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane == 0) {
-    red[warp] = a;
-    red[32 + warp] = b;
-  }
-  asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nw * 32) : "memory");
-  if (warp == 0) {
-    a = lane < nw ? red[lane] : 0.0f;
-    b = lane < nw ? red[32 + lane] : 0.0f;
-    a = warp_sum(a);
-    b = warp_sum(b);
-  }
-  asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nw * 32) : "memory");
-}
-
 // ---- asynchronous table staging (global -> shared, no registers, every request in flight at once) ------------
 // A plain "for (i = tid; …) smem[i] = table[i]" loop serialises one L2 round trip per iteration (the compiler cannot
 // hoist a generic-pointer load above the previous shared store); with N ≈ 8 particles and ≈1 CTA per SM those round

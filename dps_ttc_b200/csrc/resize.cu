@@ -407,7 +407,8 @@ __global__ void __launch_bounds__(256, 4) resize_fwd_bulk_kernel(const FwdTables
 // Bit-identity with resize_fwd_bulk_kernel: chunks are aligned to absolute multiples of 8 rows in both, each partial sum
 // adds its rows in ascending order, V = part0 + part1, and both use wpass_one.
 // Variants that were measured and lost (N = 128, this kernel 50.7 µs): 16-row stages × 3 with a single V tile 64 µs,
-// 32-row stages × 3 at one CTA per SM 66 µs, 8 H warps (one row half each) + W pass on the split tile 63 µs.
+// 32-row stages × 3 at one CTA per SM 66 µs, 8 H warps (one row half each) + W pass on the split tile 63 µs, 8 H warps
+// with one column per thread (scalar FFMA) 56.8 µs, chunks issued in pairs 50.9 µs, in triples 53.1 µs.
 constexpr int kSfStages = 5;
 
 template <int D>
@@ -748,7 +749,6 @@ __global__ void __launch_bounds__(kSaThreads, 2) resize_adj_stream_kernel(const 
   }
   __syncthreads();
   const int strips = at.strips;
-  const int64_t chw = (int64_t)C * H * W;
 
   if (warp == 8) {  // ---------------- producer ----------------
     if (lane != 0) return;
