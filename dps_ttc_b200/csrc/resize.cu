@@ -167,7 +167,7 @@ DPS_DEV void fwd_wpass(const FwdSmem& m, const FwdTables& t, int C, int W, int o
 
 __global__ void __launch_bounds__(kThreads) resize_fwd_kernel(const FwdTables t, int C, int H, int W, int oH, int oW,
                                                               const FwdArgs a) {
-  extern __shared__ __align__(16) float smem[];
+  extern __shared__ __align__(128) float smem[];
   const FwdSmem m = fwd_carve(smem, t, 1, W, oW);
   const int strip = blockIdx.x % t.fstrips;
   const int c = blockIdx.x / t.fstrips;
@@ -227,7 +227,7 @@ template <int kParts>
 __global__ void __launch_bounds__(128 * kParts, 3) resize_fwd_pair_kernel(const FwdTables t, int C, int H, int oH, int oW,
                                                                        const FwdArgs a) {
   constexpr int W = 256, W2 = 128, kBatch = 12, kT = 128 * kParts;
-  extern __shared__ __align__(16) float smem[];
+  extern __shared__ __align__(128) float smem[];
   const FwdSmem m = fwd_carve(smem, t, kParts, W, oW);
   const int strip = blockIdx.x % t.fstrips;
   const int c = blockIdx.x / t.fstrips;
