@@ -53,8 +53,14 @@ def child(op, n, out_path):
     extra = rnd(n, 3, 256, 256) * 1e-3
     g2 = torch.zeros(n, 3, 256, 256, device=dev)
     plan.adjoint(r, coef, x, o6[:, :3], k, True, extra, out=g2, aux=aux)
+    # the other argument shapes a launch can have: x̂₀ = x (no ε), no measurement, no partial sums, no clamp mask
+    ax, _, _ = plan.forward(x * 0.01)
+    r_plain, p_plain, _ = plan.forward(x * 0.01, None, None, False, y, want_partials=True, aux=plan.new_aux(n))
+    g3 = torch.zeros(n, 3, 256, 256, device=dev)
+    plan.adjoint(r, None, None, None, None, False, None, out=g3, aux=aux)
     torch.cuda.synchronize()
-    torch.save({"r": r.cpu(), "partials": partials.cpu(), "g": gbuf[:, :3].cpu(), "g_extra": g2.cpu()}, out_path)
+    torch.save({"r": r.cpu(), "partials": partials.cpu(), "g": gbuf[:, :3].cpu(), "g_extra": g2.cpu(), "Ax": ax.cpu(),
+                "r_plain": r_plain.cpu(), "partials_plain": p_plain.cpu(), "g_nomask": g3.cpu()}, out_path)
 
 
 def main():
