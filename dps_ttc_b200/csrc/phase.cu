@@ -188,6 +188,92 @@ __device__ void fft384_batch(float2* a, float2* b, const float2* tw, int nfft) {
   __syncthreads();
 }
 
+// The same transform IN PLACE (one buffer): a stage first pulls all of a thread's butterfly inputs into registers, the
+// CTA synchronises, then the outputs go back into the same buffer (the last stage reads and writes the same words, so
+// it needs no extra barrier).  Half the shared memory of the ping-pong version — what decides how many 16-sequence CTAs
+// (the adjoint kernels) fit on an SM — for two more barriers and 48 live registers.
+template <int NFFT>
+__device__ void fft384_inplace(float2* a, const float2* tw) {
+  constexpr int N12 = NFFT * 48, I12 = (N12 + kThreads - 1) / kThreads;
+  constexpr int N3 = NFFT * 64, I3 = (N3 + kThreads - 1) / kThreads;
+  const int tid = threadIdx.x;
+  {  // stage 1: R = 8, Ns = 1: out[8j + r] = DFT8(in[j + 48r])
+    float2 v[I12][8];
+#pragma unroll
+    for (int q = 0; q < I12; ++q) {
+      const int it = tid + q * kThreads;
+      if (it < N12) {
+        const int f = it / 48, j = it - f * 48;
+        const float2* src = a + f * kLP + P(j);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) v[q][r] = src[54 * r];
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < I12; ++q) {
+      const int it = tid + q * kThreads;
+      if (it < N12) {
+        const int f = it / 48, j = it - f * 48;
+        dft8(v[q]);
+        float2* dst = a + f * kLP + 9 * j;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) dst[r] = v[q][r];
+      }
+    }
+    __syncthreads();
+  }
+  {  // stage 2: R = 8, Ns = 8
+    float2 v[I12][8];
+#pragma unroll
+    for (int q = 0; q < I12; ++q) {
+      const int it = tid + q * kThreads;
+      if (it < N12) {
+        const int f = it / 48, j = it - f * 48;
+        const int k = j & 7;
+        const float2* src = a + f * kLP + P(j);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          v[q][r] = src[54 * r];
+          if (r) v[q][r] = cmul(v[q][r], twid(tw, 6 * k * r));
+        }
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < I12; ++q) {
+      const int it = tid + q * kThreads;
+      if (it < N12) {
+        const int f = it / 48, j = it - f * 48;
+        dft8(v[q]);
+        float2* dst = a + f * kLP + 72 * (j >> 3) + (j & 7);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) dst[9 * r] = v[q][r];
+      }
+    }
+    __syncthreads();
+  }
+  // stage 3: R = 6, Ns = 64: a butterfly reads and writes the same six words
+#pragma unroll
+  for (int q = 0; q < I3; ++q) {
+    const int it = tid + q * kThreads;
+    if (it < N3) {
+      const int f = it >> 6, j = it & 63;
+      float2* p = a + f * kLP + P(j);
+      float2 v[6];
+#pragma unroll
+      for (int r = 0; r < 6; ++r) {
+        v[r] = p[72 * r];
+        if (r) v[r] = cmul(v[r], twid(tw, j * r));
+      }
+      dft6(v);
+#pragma unroll
+      for (int r = 0; r < 6; ++r) p[72 * r] = v[r];
+    }
+  }
+  __syncthreads();
+}
+
 struct PhaseSmem {
   float2* a;
   float2* b;
@@ -202,6 +288,15 @@ DPS_DEV PhaseSmem carve(float* smem, int nfft) {
   s.red = reinterpret_cast<float*>(s.tw + kTW);
   return s;
 }
+DPS_DEV PhaseSmem carve1(float* smem, int nfft) {  // one sequence buffer (in-place FFT)
+  PhaseSmem s;
+  s.a = reinterpret_cast<float2*>(smem);
+  s.b = s.a;
+  s.tw = s.a + nfft * kLP;
+  s.red = reinterpret_cast<float*>(s.tw + kTW);
+  return s;
+}
+size_t smem_bytes1(int nfft) { return sizeof(float2) * ((size_t)nfft * kLP + kTW) + 64 * sizeof(float); }
 size_t smem_bytes(int nfft) { return sizeof(float2) * ((size_t)2 * nfft * kLP + kTW) + 64 * sizeof(float); }
 
 // aux layout per particle (floats): [phase: C·193·384·2][scratch: C·193·256·2]
@@ -385,11 +480,11 @@ __global__ void __launch_bounds__(kThreads, 4) phase_cols_fwd(const FwdArgs fa, 
 }
 
 // ---- A1: H_s[k1][k2] = ½(g[k]+g[−k])·conj(F)/|F|, column transform, keep rows 64..319 ------------
-__global__ void __launch_bounds__(kThreads) phase_cols_adj(const AdjArgs aa, float* __restrict__ aux_rw,
-                                                           const float2* __restrict__ tw_g, int C) {
+__global__ void __launch_bounds__(kThreads, 3) phase_cols_adj(const AdjArgs aa, float* __restrict__ aux_rw,
+                                                              const float2* __restrict__ tw_g, int C) {
   extern __shared__ __align__(16) float smem[];
   constexpr int nfft = kColsAdj;
-  PhaseSmem s = carve(smem, nfft);
+  PhaseSmem s = carve1(smem, nfft);
   const int tid = threadIdx.x;
   const int grp = blockIdx.x % kColGroupsAdj, c = blockIdx.x / kColGroupsAdj, n = blockIdx.y;
   const int k20 = grp * kColsAdj;
@@ -397,9 +492,8 @@ __global__ void __launch_bounds__(kThreads) phase_cols_adj(const AdjArgs aa, flo
   stage_async(reinterpret_cast<float*>(s.tw), reinterpret_cast<const float*>(tw_g), 2 * kTW, tid, kThreads);
   const float* r = aa.r + ((int64_t)n * C + c) * kL * kL;
   const float2* ph = aux_phase(aux_rw, n, C, c);
-  // symmetrised cotangent (coalesced over the CTA's columns), staged as floats in s.b
-  float* gs = reinterpret_cast<float*>(s.b);
-  batched_copy<kL * kColsAdj, 12>(
+  // symmetrised cotangent (coalesced over the CTA's columns), parked in the real parts of the sequence buffer
+  batched_copy<kL * kColsAdj, 8>(
       tid,
       [&](int i) {
         const int k1 = i / kColsAdj, f = i - k1 * kColsAdj;
@@ -410,10 +504,10 @@ __global__ void __launch_bounds__(kThreads) phase_cols_adj(const AdjArgs aa, flo
       },
       [&](int i, const float2& g) {
         const int k1 = i / kColsAdj, f = i - k1 * kColsAdj;
-        gs[f * kLF + k1] = 0.5f * (g.x + g.y);
+        s.a[f * kLP + P(k1)].x = 0.5f * (g.x + g.y);
       });
   __syncthreads();
-  batched_copy<nfft * kL, 12>(
+  batched_copy<nfft * kL, 8>(
       tid,
       [&](int i) {
         const int f = i / kL, k1 = i - f * kL;
@@ -421,12 +515,13 @@ __global__ void __launch_bounds__(kThreads) phase_cols_adj(const AdjArgs aa, flo
       },
       [&](int i, const float2& pv) {
         const int f = i / kL, k1 = i - f * kL;
-        const float g = gs[f * kLF + k1];
-        s.a[f * kLP + P(k1)] = make_float2(g * pv.x, g * pv.y);
+        float2* w = s.a + f * kLP + P(k1);  // the thread that multiplies is the only one touching this word
+        const float g = w->x;
+        *w = make_float2(g * pv.x, g * pv.y);
       });
   stage_wait();
   __syncthreads();
-  fft384_batch(s.a, s.b, s.tw, nfft);
+  fft384_inplace<nfft>(s.a, s.tw);
   // T[row][k2] for padded rows 64..319 → image rows 0..255; row stride 193 complex
   float2* t = aux_scratch(aux_rw, n, C, c);
 #pragma unroll 4
@@ -437,11 +532,11 @@ __global__ void __launch_bounds__(kThreads) phase_cols_adj(const AdjArgs aa, flo
 }
 
 // ---- A2: Hermitian row back-transform, two real rows per complex FFT, crop + epilogue ------------
-__global__ void __launch_bounds__(kThreads) phase_rows_adj(const AdjArgs aa, const float* __restrict__ aux_r,
-                                                           const float2* __restrict__ tw_g, int C) {
+__global__ void __launch_bounds__(kThreads, 3) phase_rows_adj(const AdjArgs aa, const float* __restrict__ aux_r,
+                                                              const float2* __restrict__ tw_g, int C) {
   extern __shared__ __align__(16) float smem[];
   constexpr int nfft = kRowsAdj / 2;
-  PhaseSmem s = carve(smem, nfft);
+  PhaseSmem s = carve1(smem, nfft);
   const int tid = threadIdx.x;
   const int groups = kImg / kRowsAdj;
   const int grp = blockIdx.x % groups, c = blockIdx.x / groups, n = blockIdx.y;
@@ -449,7 +544,7 @@ __global__ void __launch_bounds__(kThreads) phase_rows_adj(const AdjArgs aa, con
   stage_async(reinterpret_cast<float*>(s.tw), reinterpret_cast<const float*>(tw_g), 2 * kTW, tid, kThreads);
   const float2* t = aux_scratch(const_cast<float*>(aux_r), n, C, c);
   // X[k] = T1[k] + i·T2[k] with T[384−k] = conj(T[k]) for k > 192
-  batched_copy<nfft * kL, 12>(
+  batched_copy<nfft * kL, 8>(
       tid,
       [&](int i) {
         const int f = i / kL, k = i - f * kL;
@@ -465,11 +560,11 @@ __global__ void __launch_bounds__(kThreads) phase_rows_adj(const AdjArgs aa, con
       });
   stage_wait();
   __syncthreads();
-  fft384_batch(s.a, s.b, s.tw, nfft);
+  fft384_inplace<nfft>(s.a, s.tw);
   const float coef = (aa.coef ? aa.coef[n] : 1.0f) * (1.0f / (float)kL);
   const int64_t plane = (int64_t)c * kImg * kImg;
   struct Epi { float4 e, pass; };
-  batched_copy<kRowsAdj * (kImg / 4), 8>(
+  batched_copy<kRowsAdj * (kImg / 4), 4>(
       tid,
       [&](int i) {
         const int rr = i / (kImg / 4), q = i - rr * (kImg / 4);
@@ -516,8 +611,8 @@ int phase_create(dps_operator* op, int pad) {
   DPS_CUDA(cudaMemcpy(t->tw, tw.data(), sizeof(float2) * kL, cudaMemcpyHostToDevice));
   if (int rc = set_smem((const void*)phase_rows_fwd, smem_bytes(kRowsPerCta / 2))) return rc;
   if (int rc = set_smem((const void*)phase_cols_fwd, smem_bytes(kColsPerCta))) return rc;
-  if (int rc = set_smem((const void*)phase_cols_adj, smem_bytes(kColsAdj))) return rc;
-  if (int rc = set_smem((const void*)phase_rows_adj, smem_bytes(kRowsAdj / 2))) return rc;
+  if (int rc = set_smem((const void*)phase_cols_adj, smem_bytes1(kColsAdj))) return rc;
+  if (int rc = set_smem((const void*)phase_rows_adj, smem_bytes1(kRowsAdj / 2))) return rc;
   op->oC = op->C;
   op->oH = op->oW = kL;
   op->P = op->C * kColGroups;
@@ -549,10 +644,10 @@ int phase_adjoint(const dps_operator* op, const AdjArgs& a, cudaStream_t st) {
   DPS_REQUIRE(a.aux && a.r, DPS_ERR_INVALID, "phase retrieval adjoint needs r and the aux workspace of the forward pass");
   float* aux = const_cast<float*>(a.aux);
   dim3 g1((unsigned)(op->C * kColGroupsAdj), (unsigned)a.n);
-  phase_cols_adj<<<g1, kThreads, smem_bytes(kColsAdj), st>>>(a, aux, op->phase->tw, op->C);
+  phase_cols_adj<<<g1, kThreads, smem_bytes1(kColsAdj), st>>>(a, aux, op->phase->tw, op->C);
   DPS_LAUNCH_CHECK("phase_cols_adj");
   dim3 g2((unsigned)(op->C * (kImg / kRowsAdj)), (unsigned)a.n);
-  phase_rows_adj<<<g2, kThreads, smem_bytes(kRowsAdj / 2), st>>>(a, aux, op->phase->tw, op->C);
+  phase_rows_adj<<<g2, kThreads, smem_bytes1(kRowsAdj / 2), st>>>(a, aux, op->phase->tw, op->C);
   DPS_LAUNCH_CHECK("phase_rows_adj");
   return DPS_OK;
 }
