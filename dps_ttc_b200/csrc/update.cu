@@ -10,8 +10,17 @@
 
 namespace {
 
-constexpr int kThreads = 256;
-constexpr int kVecPerThread = 2;  // float4 per thread per stream -> 12-14 independent 16 B loads in flight
+#ifndef UPD_THREADS
+#define UPD_THREADS 256
+#endif
+#ifndef UPD_VEC
+#define UPD_VEC 1
+#endif
+constexpr int kThreads = UPD_THREADS;
+// float4 per thread and stream.  Measured (tools/build_variant.sh + kernel_bench, DDPM update): one vector per thread —
+// 6-7 independent 16 B loads in flight per thread, twice the CTAs — beats two at every particle count: 8.98 → 8.32 µs at
+// N = 8 (75 → 81 % of the HBM peak), 15.0 → 14.4 at 16, 27.2 → 26.7 at 32, 104.1 → 103.3 at 128; three or four lose.
+constexpr int kVecPerThread = UPD_VEC;
 
 struct UpdateArgs {
   const float* x;
