@@ -5,8 +5,13 @@
 
 namespace {
 constexpr int kThreads = 256;
-constexpr int kVec = 2;
+constexpr int kVec = 2;                      // forward: float4 per thread (also fixes the partial-sum split)
 constexpr int kPerBlock4 = kThreads * kVec;  // float4 per CTA
+// adjoint: ONE float4 per thread and stream (4 loads in flight per thread, twice the CTAs) — measured against 2:
+// 63.1 vs 65.0 µs at N = 128, 16.6 vs 17.4 µs at N = 32, 5.70 vs 6.05 µs at N = 8 (profiles/r1j_variants.md).  The
+// forward keeps 2 (54.1 vs 58.7 µs): its block reduction amortises over twice the data.
+constexpr int kVecAdj = 1;
+constexpr int kPerBlockAdj4 = kThreads * kVecAdj;
 
 __global__ void __launch_bounds__(kThreads) inpaint_fwd_kernel(const FwdArgs a, const float* __restrict__ mask,
                                                                int64_t chw4, int hw4, int P) {
@@ -52,8 +57,8 @@ __global__ void __launch_bounds__(kThreads) inpaint_adj_kernel(const AdjArgs a, 
   const float* extra = a.extra ? a.extra + n * a.extra_stride : nullptr;
   float* g = a.g + n * a.g_stride;
 #pragma unroll
-  for (int u = 0; u < kVec; ++u) {
-    const int64_t i4 = (int64_t)blockIdx.x * kPerBlock4 + u * kThreads + threadIdx.x;
+  for (int u = 0; u < kVecAdj; ++u) {
+    const int64_t i4 = (int64_t)blockIdx.x * kPerBlockAdj4 + u * kThreads + threadIdx.x;
     if (i4 >= chw4) continue;
     const float4 rv = ldg_stream4(r + i4 * 4);
     const float4 m = *reinterpret_cast<const float4*>(mask + (i4 % hw4) * 4);
@@ -85,7 +90,7 @@ int inpaint_forward(const dps_operator* op, const FwdArgs& a, cudaStream_t st) {
 
 int inpaint_adjoint(const dps_operator* op, const AdjArgs& a, cudaStream_t st) {
   const int64_t chw4 = (int64_t)op->C * op->H * op->W / 4;
-  dim3 grid((unsigned)op->P, (unsigned)a.n);
+  dim3 grid((unsigned)((chw4 + kPerBlockAdj4 - 1) / kPerBlockAdj4), (unsigned)a.n);
   inpaint_adj_kernel<<<grid, kThreads, 0, st>>>(a, op->mask_dev, chw4, op->H * op->W / 4);
   DPS_LAUNCH_CHECK("inpaint_adjoint");
   return DPS_OK;
