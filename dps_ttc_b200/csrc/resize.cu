@@ -307,11 +307,14 @@ __global__ void __launch_bounds__(128 * kParts, 3) resize_fwd_pair_kernel(const 
 constexpr int kSaStages = 3;          // streaming adjoint: ring stages
 constexpr int kSaRows = 16;           //   rows per stage and tensor (16 KB per bulk copy)
 constexpr int kSaThreads = 256 + 32;  // streaming kernels: 256 consumers + one producer warp
-constexpr int kCR = 8;      // rows per chunk
-constexpr int kStages = 3;  // chunks in flight
+constexpr int kCR = 8;          // rows per chunk
+constexpr int kStagesStd = 3;   // chunks in flight (4 CTAs per SM)
+constexpr int kStagesDeep = 6;  // very small grids: the whole ×4 window (≤ 6 chunks) in flight at once — one DRAM round
+                                // trip per CTA instead of two, no recycle barrier; same arithmetic, same bits
 
-__global__ void __launch_bounds__(256, 4) resize_fwd_bulk_kernel(const FwdTables t, int C, int H, int oH, int oW,
-                                                                 const FwdArgs a) {
+template <int kStages>
+__global__ void __launch_bounds__(256, kStages == kStagesStd ? 4 : 2) resize_fwd_bulk_kernel(const FwdTables t, int C, int H, int oH,
+                                                                                    int oW, const FwdArgs a) {
   constexpr int W = 256, W2 = 128, kT = 256, kParts = 2;
   extern __shared__ __align__(128) float smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);  // kStages mbarriers in the first 128 bytes
@@ -1090,13 +1093,30 @@ static bool small_grid(int64_t ctas) {
   return v ? v == 2 : ctas <= 148 * 10;
 }
 
+// Deep ring (6 stages, 104 KB) only while the strip grid leaves a third of the SMs empty: measured ×4, deep vs 3 stages
+// (profiles/r1k_ring.md): 6.40 vs 6.66 µs at N = 4 (96 CTAs), but 8.53 vs 8.31 µs at N = 8 (192) and 9.77 vs 9.14 µs at
+// N = 12 — once every SM hosts a CTA the launch is paced by its 13-19 MB crossing HBM, not by a CTA's second round trip.
+// DPSTTC_RESIZE_FWD_STAGES=3|6 pins the choice (A/B and tests/test_gpu_variants.py).
+static bool fwd_deep_ring(int64_t ctas, int device) {
+  static int pin = -1;
+  if (pin < 0) {
+    const char* e = getenv("DPSTTC_RESIZE_FWD_STAGES");
+    pin = !e ? 0 : (e[0] == '6' ? 6 : 3);
+  }
+  if (pin) return pin == 6;
+  static int sms = 0;
+  if (!sms) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  return 3 * ctas <= 2 * (int64_t)sms;
+}
+
 int resize_forward(const dps_operator* op, const FwdArgs& a, cudaStream_t st) {
   const FwdTables& f = op->resize->f;
   static bool attr_set = false;
   if (!attr_set) {
     DPS_CUDA(cudaFuncSetAttribute(resize_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     DPS_CUDA(cudaFuncSetAttribute(resize_fwd_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    DPS_CUDA(cudaFuncSetAttribute(resize_fwd_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DPS_CUDA(cudaFuncSetAttribute(resize_fwd_bulk_kernel<kStagesStd>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DPS_CUDA(cudaFuncSetAttribute(resize_fwd_bulk_kernel<kStagesDeep>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   {  // streaming variant once the strip grid would fill the machine several times over
@@ -1129,8 +1149,11 @@ int resize_forward(const dps_operator* op, const FwdArgs& a, cudaStream_t st) {
     static const bool pair_path = getenv("DPSTTC_RESIZE_FWD") && getenv("DPSTTC_RESIZE_FWD")[0] == 'p';  // A/B aid
     if (pair_path)
       resize_fwd_pair_kernel<2><<<grid, 256, fwd_smem(f, 2, 256, op->oW), st>>>(f, op->C, op->H, op->oH, op->oW, a);
+    else if (fwd_deep_ring((int64_t)grid.x * grid.y, op->device))
+      resize_fwd_bulk_kernel<kStagesDeep><<<grid, 256, fwd_smem(f, 0, 256, op->oW) + sizeof(float) * (32 + kStagesDeep * 2 * kCR * 256), st>>>(
+          f, op->C, op->H, op->oH, op->oW, a);
     else
-      resize_fwd_bulk_kernel<<<grid, 256, fwd_smem(f, 0, 256, op->oW) + sizeof(float) * (32 + kStages * 2 * kCR * 256), st>>>(
+      resize_fwd_bulk_kernel<kStagesStd><<<grid, 256, fwd_smem(f, 0, 256, op->oW) + sizeof(float) * (32 + kStagesStd * 2 * kCR * 256), st>>>(
           f, op->C, op->H, op->oH, op->oW, a);
   } else {
     resize_fwd_kernel<<<grid, kThreads, fwd_smem(f, 1, op->W, op->oW), st>>>(f, op->C, op->H, op->W, op->oH, op->oW, a);

@@ -18,3 +18,15 @@ def test_resize_variants_bit_identical(op, n):
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert "PASS" in res.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("op,n", [("sr4", 8), ("sr8", 3)])
+def test_resize_forward_ring_depths_bit_identical(op, n):
+    """3-stage (4 CTAs/SM) and 6-stage (2 CTAs/SM, small grids) TMA rings of the strip forward: same chunks, same order."""
+    cmd = [sys.executable, os.path.join(REPO, "tools", "variant_check.py"), "--op", op, "--n", str(n),
+           "--env", "DPSTTC_RESIZE_VARIANT=big,DPSTTC_RESIZE_FWD_STAGES=3",
+           "--env", "DPSTTC_RESIZE_VARIANT=big,DPSTTC_RESIZE_FWD_STAGES=6"]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert "PASS" in res.stdout
