@@ -403,10 +403,10 @@ def run_b200(args, rank, world, local_rank):
     dom = max((k for k in cands if t_of(k) >= 0.95 * t_max), key=lambda k: alg_bytes[k])
     achieved = ktab[dom]["gbs"]
     # dram__bytes_read.sum + dram__bytes_write.sum per launch of the same kernels at the same size (N=8, SR x4), mean over
-    # the launches of an ncu pass over this very command (profiles/r1f_bench_graft_launches.csv.gz,
-    # r1f_ncu_bench_kernels_n8.csv).  Reads equal the algorithmic input bytes; the outputs were still in L2 when the kernel
+    # the launches of an ncu pass over this very command (profiles/r1l_bench_graft_launches.csv.gz,
+    # r1l_ncu_bench_kernels_n8.csv).  Reads equal the algorithmic input bytes; the outputs were still in L2 when the kernel
     # ended (no write-back yet), hence traffic < algorithmic bytes.
-    ncu_traffic = {"resize_forward": 12650227 + 0, "resize_adjoint": 13016415 + 0, "posterior_update_ddpm": 37760968 + 2151}
+    ncu_traffic = {"resize_forward": 12682907 + 17, "resize_adjoint": 13016227 + 0, "posterior_update_ddpm": 37756835 + 0}
     traffic = ncu_traffic.get(dom) if (n == 8 and args.workload == "c2") else None
     roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
