@@ -397,6 +397,138 @@ __global__ void __launch_bounds__(256, kStages == kStagesStd ? 4 : 2) resize_fwd
   fwd_wpass(m, t, C, W, oH, oW, strip, c, n, tid, kT, a, ypre, blockIdx.x);
 }
 
+// Lean strip forward — OPT-IN (DPSTTC_RESIZE_FWD_LEAN=1), prepared from the N = 8 ncu capture of the bulk kernel
+// (profiles/r1l_resize_fwd_n8_sass.md): at bench size the kernel is bound by each warp's own instruction stream (2.7 warps
+// per scheduler, one issue every 8.9 cycles, 12 % of the stall samples on instruction fetch), and only 12 % of its 2.46 M
+// warp instructions are FFMA2 — the rest is per-row control flow (a BSSY/BSYNC-guarded `rl < rows` block and a uniform
+// `eps` branch per row), runtime index arithmetic, and a W pass that divides by a runtime oW and walks a runtime tap count.
+// Same arithmetic in the same order as resize_fwd_bulk_kernel (hence the same bits), with the control flow folded away:
+//   * specialised for the DPS path proper: x̂₀ source with clipping, W = 256, oW = 64, KW taps at compile time;
+//   * H pass: rows past the window's end contribute v = 0 through a select instead of a branch (acc + w·0 = acc exactly:
+//     the weights row index is clamped into the staged block, so w is finite; acc is never −0), so the four rows of a
+//     thread's chunk share one straight-line block and their shared-memory loads issue together;
+//   * W pass: i → (j, jc) by shifts, taps fully unrolled.
+// Not launched unless the environment variable is set; bit-identity with the default kernel is checked by
+//   python tools/variant_check.py --op sr4 --n 8 --env DPSTTC_RESIZE_FWD_LEAN=0 --env DPSTTC_RESIZE_FWD_LEAN=1
+template <int kStages, int KW>
+__global__ void __launch_bounds__(256, kStages == kStagesStd ? 4 : 2) resize_fwd_lean_kernel(const FwdTables t, int C, int H, int oH,
+                                                                                    const FwdArgs a) {
+  constexpr int W = 256, W2 = 128, kT = 256, kParts = 2, oW = 64;
+  static_assert(kYPre * kT == kRO * oW, "every W-pass output of a thread has its measurement value prefetched");
+  extern __shared__ __align__(128) float smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  float* ring = smem + 32;
+  FwdSmem m = fwd_carve(ring + kStages * 2 * kCR * W, t, 0, W, oW);
+  m.V = ring;
+  static_assert(kStages * 2 * kCR >= kParts * kRO, "V must fit in the ring");
+  const int strip = blockIdx.x % t.fstrips;
+  const int c = blockIdx.x / t.fstrips;
+  const int n = blockIdx.y;
+  const int tid = threadIdx.x;
+  const int rmin = t.rows.lo[strip], rcnt = t.rows.cnt[strip];
+  const int nchunks = (rcnt + kCR - 1) / kCR;
+  const int64_t plane = (int64_t)c * H * W;
+  const float* x = a.src.x + n * a.src.x_stride + plane + (int64_t)rmin * W;
+  const float* eps = a.src.eps + n * a.src.eps_stride + plane + (int64_t)rmin * W;
+  auto issue = [&](int k) {
+    const int stage = k % kStages;
+    const unsigned bytes = (unsigned)(min(kCR, rcnt - k * kCR) * W * sizeof(float));
+    float* dst = ring + stage * 2 * kCR * W;
+    mbar_expect_tx(&bars[stage], 2 * bytes);
+    bulk_load(dst, x + (int64_t)k * kCR * W, bytes, &bars[stage]);
+    bulk_load(dst + kCR * W, eps + (int64_t)k * kCR * W, bytes, &bars[stage]);
+  };
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) mbar_init(&bars[s], 1);
+    mbar_init_fence();
+    for (int k = 0; k < min(kStages, nchunks); ++k) issue(k);
+  }
+  fwd_stage(m, t, strip, rcnt, oW, tid, kT);
+  const YPre ypre = fwd_y_prefetch(oH, oW, strip, c, n, tid, kT, a);
+  stage_wait();
+  __syncthreads();
+  const int part = tid >> 7, cp = tid & 127;
+  const float c1 = a.src.c1, c2 = a.src.c2;
+  float2 acc[kRO];
+#pragma unroll
+  for (int j = 0; j < kRO; ++j) acc[j] = make_float2(0.f, 0.f);
+#pragma unroll 1
+  for (int k = 0; k < nchunks; ++k) {
+    const int stage = k % kStages;
+    mbar_wait(&bars[stage], (unsigned)((k / kStages) & 1));
+    const float2* xs = reinterpret_cast<const float2*>(ring + stage * 2 * kCR * W) + part * (kCR / kParts) * W2 + cp;
+    const float2* es = xs + kCR * W2;
+    const int left = rcnt - k * kCR - part * (kCR / kParts);  // rows of this thread's group that exist in the chunk
+    float2 v[kCR / kParts];
+#pragma unroll
+    for (int q = 0; q < kCR / kParts; ++q) {
+      const float2 p = x0_pair_bounds(xs[q * W2], es[q * W2], c1, c2, -1.0f, 1.0f);
+      v[q] = make_float2(q < left ? p.x : 0.f, q < left ? p.y : 0.f);  // a select: stale rows (even NaN) never reach an FMA
+    }
+    const int wrow0 = k * kCR + part * (kCR / kParts);
+#pragma unroll
+    for (int q = 0; q < kCR / kParts; ++q) {
+      const float* wr = m.dh + min(wrow0 + q, rcnt - 1) * kRO;
+      const float4 w0 = *reinterpret_cast<const float4*>(wr);
+      const float4 w1 = *reinterpret_cast<const float4*>(wr + 4);
+      acc[0] = __ffma2_rn(make_float2(w0.x, w0.x), v[q], acc[0]); acc[1] = __ffma2_rn(make_float2(w0.y, w0.y), v[q], acc[1]);
+      acc[2] = __ffma2_rn(make_float2(w0.z, w0.z), v[q], acc[2]); acc[3] = __ffma2_rn(make_float2(w0.w, w0.w), v[q], acc[3]);
+      acc[4] = __ffma2_rn(make_float2(w1.x, w1.x), v[q], acc[4]); acc[5] = __ffma2_rn(make_float2(w1.y, w1.y), v[q], acc[5]);
+      acc[6] = __ffma2_rn(make_float2(w1.z, w1.z), v[q], acc[6]); acc[7] = __ffma2_rn(make_float2(w1.w, w1.w), v[q], acc[7]);
+    }
+    if (k + kStages < nchunks) {
+      __syncthreads();
+      if (tid == 0) issue(k + kStages);
+    }
+  }
+  __syncthreads();
+  {
+    float* dstp = m.V + part * kRO * W;
+#pragma unroll
+    for (int j = 0; j < kRO; ++j) *reinterpret_cast<float2*>(dstp + j * W + 2 * cp) = acc[j];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int u = 0; u < kRO * W / 4 / kT; ++u) {  // V[0] += V[1], fixed order
+    const int i = tid + u * kT;
+    float4 s0 = *reinterpret_cast<const float4*>(m.V + i * 4);
+    const float4 s1 = *reinterpret_cast<const float4*>(m.V + kRO * W + i * 4);
+    s0.x += s1.x; s0.y += s1.y; s0.z += s1.z; s0.w += s1.w;
+    *reinterpret_cast<float4*>(m.V + i * 4) = s0;
+  }
+  __syncthreads();
+  // ---- W pass: the thread → output mapping, tap order and partial-sum order of fwd_wpass / wpass_one ----
+  float sq = 0.f, ab = 0.f;
+  float* outp = a.out + ((int64_t)n * C + c) * oH * oW;
+  const bool has_y = a.y != nullptr;
+#pragma unroll
+  for (int u = 0; u < kYPre; ++u) {
+    const int i = tid + u * kT;
+    const int j = i >> 6, jc = i & (oW - 1);
+    const int orow = strip * kRO + j;
+    if (orow < oH) {
+      const int cs = m.css[jc];
+      const float* vr = m.V + j * W + cs;
+      float s = 0.f;
+#pragma unroll
+      for (int k = 0; k < KW; ++k) s = fmaf(m.wws[k * oW + jc], (cs + k < W) ? vr[k] : 0.f, s);
+      const float res = has_y ? __fsub_rn(ypre.v[u], s) : s;
+      stg_stream(outp + (int64_t)orow * oW + jc, res);
+      sq += res * res;
+      ab += fabsf(res);
+    }
+  }
+  if (a.partials) {
+    block_sum2(sq, ab, m.red);
+    if (tid == 0) {
+      float* pp = a.partials + ((int64_t)n * (C * t.fstrips) + blockIdx.x) * 2;
+      pp[0] = sq;
+      pp[1] = ab;
+    }
+  }
+}
+
 // Streaming forward for full machines (W = 256; ×4 and ×8 bicubic): persistent CTAs of three roles.
 //   producer (1 warp) : a work unit is 4 consecutive output strips of one plane; its input rows are streamed ONCE, in
 //                       absolute 8-row chunks, through a ring of kSfStages TMA stages (x rows | ε rows) — the 1.5× halo
@@ -1109,6 +1241,16 @@ static bool fwd_deep_ring(int64_t ctas, int device) {
   return 3 * ctas <= 2 * (int64_t)sms;
 }
 
+// DPSTTC_RESIZE_FWD_LEAN=1: the lean strip forward (opt-in until it has been validated on a B200, see its header).
+static bool fwd_lean() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DPSTTC_RESIZE_FWD_LEAN");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 int resize_forward(const dps_operator* op, const FwdArgs& a, cudaStream_t st) {
   const FwdTables& f = op->resize->f;
   static bool attr_set = false;
@@ -1149,7 +1291,20 @@ int resize_forward(const dps_operator* op, const FwdArgs& a, cudaStream_t st) {
     static const bool pair_path = getenv("DPSTTC_RESIZE_FWD") && getenv("DPSTTC_RESIZE_FWD")[0] == 'p';  // A/B aid
     if (pair_path)
       resize_fwd_pair_kernel<2><<<grid, 256, fwd_smem(f, 2, 256, op->oW), st>>>(f, op->C, op->H, op->oH, op->oW, a);
-    else if (fwd_deep_ring((int64_t)grid.x * grid.y, op->device))
+    else if (fwd_lean() && a.src.eps && a.src.clip && op->oW == 64 && f.kw == 16 && a.n > 0) {
+      static bool lattr = false;
+      if (!lattr) {
+        DPS_CUDA(cudaFuncSetAttribute(resize_fwd_lean_kernel<kStagesStd, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        DPS_CUDA(cudaFuncSetAttribute(resize_fwd_lean_kernel<kStagesDeep, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        lattr = true;
+      }
+      if (fwd_deep_ring((int64_t)grid.x * grid.y, op->device))
+        resize_fwd_lean_kernel<kStagesDeep, 16><<<grid, 256, fwd_smem(f, 0, 256, op->oW) + sizeof(float) * (32 + kStagesDeep * 2 * kCR * 256), st>>>(
+            f, op->C, op->H, op->oH, a);
+      else
+        resize_fwd_lean_kernel<kStagesStd, 16><<<grid, 256, fwd_smem(f, 0, 256, op->oW) + sizeof(float) * (32 + kStagesStd * 2 * kCR * 256), st>>>(
+            f, op->C, op->H, op->oH, a);
+    } else if (fwd_deep_ring((int64_t)grid.x * grid.y, op->device))
       resize_fwd_bulk_kernel<kStagesDeep><<<grid, 256, fwd_smem(f, 0, 256, op->oW) + sizeof(float) * (32 + kStagesDeep * 2 * kCR * 256), st>>>(
           f, op->C, op->H, op->oH, op->oW, a);
     else
