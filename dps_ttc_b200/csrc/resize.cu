@@ -852,6 +852,83 @@ __global__ void __launch_bounds__(kThreads, RA == kRAs ? 4 : 3) resize_adj_kerne
   }
 }
 
+// Lean short-strip adjoint — OPT-IN (DPSTTC_RESIZE_ADJ_LEAN=1), the adjoint's counterpart of resize_fwd_lean_kernel, prepared
+// from the same N = 8 ncu capture (profiles/r1l_resize_n8_sass.md): resize_adj_kernel<8, 8, 4, true> executes ≈780 instructions
+// per thread for 8 outputs, 12 % of them FFMA, at 60 % issue-slot utilisation — guards (`row < H`, `masked`, `extra`, `jj < jcnt`,
+// `k < kt`), the generic column loop and runtime shapes make up the rest.  This variant is the guided step's case only — clamp
+// mask on, no `extra`, W = 256 = one column per thread, H a multiple of 8, oW = 64, at most 4 column taps — with the guards
+// turned into selects on the operand (fma(w, 0, s) = s exactly: w is finite and s is never −0) or removed where the shape
+// makes them constant.  Same fma chains in the same order as resize_adj_kernel, hence the same bits; gate:
+//   python tools/variant_check.py --op sr4 --n 8 --env DPSTTC_RESIZE_ADJ_LEAN=0 --env DPSTTC_RESIZE_ADJ_LEAN=1
+__global__ void __launch_bounds__(kThreads, 4) resize_adj_lean_kernel(const AdjStrips at, const AdjCols ac, int C, int H, int oH,
+                                                                      const AdjArgs a) {
+  constexpr int RA = kRAs, KJ = kJs, KT = 4, W = 256, oW = 64;
+  static_assert(kThreads == W && RA == 8 && KJ == 8, "one column per thread, one 8-row chunk per CTA");
+  extern __shared__ __align__(128) float smem[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem);  // same carve-up as resize_adj_kernel<…, kBulk = true>
+  float* xs = smem + 32;                               // (RA, W) x rows, then (RA, W) ε rows
+  float* G = xs + 2 * RA * W;                          // (KJ, oW)
+  float* dht = G + ((KJ * oW + 3) & ~3);               // (RA, KJ)
+  float* wts = dht + RA * KJ;                          // (kt, W)
+  const int strip = blockIdx.x % at.strips;
+  const int c = blockIdx.x / at.strips;
+  const int n = blockIdx.y;
+  const int m = threadIdx.x;
+  const int jmin = at.rows.lo[strip], jcnt = at.rows.cnt[strip];
+  const int64_t plane = (int64_t)c * H * W;
+  const int64_t row0 = (int64_t)strip * RA * W;
+  if (m == 0) {
+    mbar_init(bar, 1);
+    mbar_init_fence();
+    constexpr unsigned bytes = RA * W * sizeof(float);
+    mbar_expect_tx(bar, 2 * bytes);
+    bulk_load(xs, a.mask_src.x + n * a.mask_src.x_stride + plane + row0, bytes, bar);
+    bulk_load(xs + RA * W, a.mask_src.eps + n * a.mask_src.eps_stride + plane + row0, bytes, bar);
+  }
+  stage_async(G, a.r + ((int64_t)n * C + c) * oH * oW + (int64_t)jmin * oW, jcnt * oW, m, kThreads);
+  stage_async(dht, at.dht + (int64_t)strip * RA * KJ, RA * KJ, m, kThreads);
+  stage_async(wts, ac.wtt, ac.kt * W, m, kThreads);
+  const float coef = a.coef ? a.coef[n] : 1.0f;
+  const int js = ac.jstart[m];
+  stage_wait();
+  __syncthreads();
+
+  // E[jj] = Σ_k A_w[jstart+k][m]·G[jmin+jj][jstart+k]
+  float wt[KT];
+#pragma unroll
+  for (int k = 0; k < KT; ++k) wt[k] = k < ac.kt ? wts[k * W + m] : 0.f;
+  float e[KJ];
+#pragma unroll
+  for (int jj = 0; jj < KJ; ++jj) {
+    const float* gr = G + jj * oW + js;
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < KT; ++k) {
+      const bool on = jj < jcnt && k < ac.kt && js + k < oW;
+      s = fmaf(wt[k], on ? gr[k] : 0.f, s);  // off: s + (±0) = s; the unstaged value never reaches the fma
+    }
+    e[jj] = s;
+  }
+  // out[i][m] = Σ_jj A_h[jmin+jj][i]·E[jj], clamp mask from the bulk-copied x / ε rows
+  mbar_wait(bar, 0);
+  const float c1 = a.mask_src.c1, c2 = a.mask_src.c2;
+  float* gp = a.g + n * a.g_stride + plane + row0 + m;
+#pragma unroll
+  for (int b = 0; b < RA; ++b) {
+    const float4* dr = reinterpret_cast<const float4*>(dht + b * KJ);
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < KJ / 4; ++q) {
+      const float4 w = dr[q];
+      s = fmaf(w.x, e[4 * q + 0], s); s = fmaf(w.y, e[4 * q + 1], s);
+      s = fmaf(w.z, e[4 * q + 2], s); s = fmaf(w.w, e[4 * q + 3], s);
+    }
+    float res = coef * s + 0.f;  // resize_adj_kernel: coef·s + extra with extra = 0
+    res *= clamp_pass(x0_pre(xs[b * W + m], xs[(RA + b) * W + m], c1, c2));
+    stg_stream(gp + b * W, res);
+  }
+}
+
 // Streaming adjoint for full machines (W = 256, H a multiple of 32, clamp mask on): persistent CTAs, one producer warp
 // and 256 consumer threads.  The producer walks the CTA's work list — units (particle, channel, 32-row strip), round
 // robin over the grid — and keeps a ring of kSaStages 16-row chunks of the clamp-mask sources (x rows | ε rows, 32 KB per
@@ -1375,7 +1452,22 @@ int resize_adjoint(const dps_operator* op, const AdjArgs& a, cudaStream_t st) {
     if (eligible && (v == 3 || (v == 0 && units >= 40 * 24)))
       return narrow ? launch_adj_stream<4>(op, a, st) : launch_adj_stream<kKTMax>(op, a, st);
   }
-  if (t.small.strips && small_grid((int64_t)op->C * t.big.strips * a.n))
+  if (t.small.strips && small_grid((int64_t)op->C * t.big.strips * a.n)) {
+    static const bool lean = getenv("DPSTTC_RESIZE_ADJ_LEAN") && getenv("DPSTTC_RESIZE_ADJ_LEAN")[0] == '1';  // opt-in, see its header
+    const bool masked = a.has_mask && a.mask_src.eps && a.mask_src.clip;
+    if (lean && narrow && masked && !a.extra && op->W == 256 && op->H % kRAs == 0 && op->oW == 64 && a.r) {
+      static bool lattr = false;
+      if (!lattr) {
+        DPS_CUDA(cudaFuncSetAttribute(resize_adj_lean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        lattr = true;
+      }
+      dim3 grid((unsigned)(op->C * t.small.strips), (unsigned)a.n);
+      const size_t smem = adj_smem(kRAs, kJs, op->oW, t.cols.kt, op->W) + sizeof(float) * (32 + (size_t)2 * kRAs * op->W);
+      resize_adj_lean_kernel<<<grid, kThreads, smem, st>>>(t.small, t.cols, op->C, op->H, op->oH, a);
+      DPS_LAUNCH_CHECK("resize_adjoint");
+      return DPS_OK;
+    }
     return narrow ? launch_adj<kRAs, kJs, 4>(op, t.small, a, st) : launch_adj<kRAs, kJs, kKTMax>(op, t.small, a, st);
+  }
   return narrow ? launch_adj<kRA, kJMax, 4>(op, t.big, a, st) : launch_adj<kRA, kJMax, kKTMax>(op, t.big, a, st);
 }

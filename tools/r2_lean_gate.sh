@@ -1,0 +1,17 @@
+#!/bin/bash
+# Gate + A/B of the opt-in lean SR kernels (written after round 1's last GPU call; see profiles/r1l_resize_n8_sass.md).
+#   gpurun --timeout 420 -- 'bash tools/r2_lean_gate.sh r2a'   →  gpurun_out/<tag>_lean_*
+# 1. bit-identity against the default kernels (must print PASS twice per op), 2. µs per launch at N = 4 / 8 / 12 / 32.
+tag=${1:-r2a}
+mkdir -p gpurun_out
+for n in 3 8; do
+  timeout 200 python tools/variant_check.py --op sr4 --n $n \
+    --env DPSTTC_RESIZE_FWD_LEAN=0,DPSTTC_RESIZE_ADJ_LEAN=0 --env DPSTTC_RESIZE_FWD_LEAN=1,DPSTTC_RESIZE_ADJ_LEAN=1 \
+    --env DPSTTC_RESIZE_FWD_LEAN=1,DPSTTC_RESIZE_FWD_STAGES=6,DPSTTC_RESIZE_ADJ_LEAN=1 > gpurun_out/${tag}_lean_gate_n$n.log 2>&1
+  echo "gate n=$n rc=$?" >> gpurun_out/${tag}_lean_gate_n$n.log
+done
+for v in 0 1; do for n in 4 8 12 32; do
+  DPSTTC_RESIZE_FWD_LEAN=$v DPSTTC_RESIZE_ADJ_LEAN=$v timeout 90 python tools/kernel_bench.py --n $n --iters 50 --graph --only sr4 \
+    > gpurun_out/${tag}_lean${v}_n$n.jsonl 2> gpurun_out/${tag}_lean${v}_n$n.err
+done; done
+tail -n 3 gpurun_out/${tag}_lean_gate_n*.log; cat gpurun_out/${tag}_lean*_n*.jsonl | cut -c1-150
