@@ -362,6 +362,13 @@ __global__ void __launch_bounds__(kThreads, 4) phase_rows_fwd(const FwdArgs fa, 
 DPS_DEV int shift_idx(int k) { return k + kL / 2 >= kL ? k - kL / 2 : k + kL / 2; }  // fftshift position of bin k
 
 // ---- K2: column transforms, magnitude, residual, partial sums, unit phase -----------------------
+// kLean (opt-in, DPSTTC_PHASE_LEAN=1, not launched by default): the output epilogue with its addressing hoisted.  Under the
+// 64-register cap of 4 CTAs/SM the compiler rematerialises, for EVERY one of a thread's 24 stores, the 64-bit product
+// (n·C + c)·384² + o, the `fa.out` / `y` null tests and a BSSY/BSYNC pair (≈20 instructions per output, 36 % of the kernel's
+// instructions in the ncu source page).  Here the plane pointers are formed once, the null tests become two CTA-uniform flags and
+// each output is: LDS, FSUB, STG [base + 4·o], FFMA, FADD.  Same values in the same order
+// (gate: tools/variant_check.py --op phase --n 4 --env DPSTTC_PHASE_LEAN=0 --env DPSTTC_PHASE_LEAN=1).
+template <bool kLean>
 __global__ void __launch_bounds__(kThreads, 4) phase_cols_fwd(const FwdArgs fa, const float2* __restrict__ tw_g, int C) {
   extern __shared__ __align__(16) float smem[];
   constexpr int nfft = kColsPerCta;
@@ -450,6 +457,21 @@ __global__ void __launch_bounds__(kThreads, 4) phase_cols_fwd(const FwdArgs fa, 
         o2[b] = shift_idx(k1 ? kL - k1 : 0) * kL + c2;
         y1[b] = (y && act) ? ldg_ro(y + o1[b]) : 0.f;
         y2[b] = (y && mir) ? ldg_ro(y + o2[b]) : 0.f;
+      }
+      if constexpr (kLean) {
+        float* const outp = fa.out ? fa.out + oplane : nullptr;
+        const bool st1 = act && outp != nullptr, st2 = mir && outp != nullptr, has_y = y != nullptr;
+#pragma unroll
+        for (int b = 0; b < kYB; ++b) {
+          const float a = ampf[kk + 32 * (it0 + b)];
+          const float r1 = has_y ? __fsub_rn(y1[b], a) : a;
+          const float r2 = has_y ? __fsub_rn(y2[b], a) : a;
+          if (st1) stg_stream(outp + o1[b], r1);
+          if (act) { sq += r1 * r1; ab += fabsf(r1); }
+          if (st2) stg_stream(outp + o2[b], r2);
+          if (mir) { sq += r2 * r2; ab += fabsf(r2); }
+        }
+        continue;
       }
 #pragma unroll
       for (int b = 0; b < kYB; ++b) {
@@ -610,7 +632,8 @@ int phase_create(dps_operator* op, int pad) {
   DPS_CUDA(cudaMalloc(&t->tw, sizeof(float2) * kL));
   DPS_CUDA(cudaMemcpy(t->tw, tw.data(), sizeof(float2) * kL, cudaMemcpyHostToDevice));
   if (int rc = set_smem((const void*)phase_rows_fwd, smem_bytes(kRowsPerCta / 2))) return rc;
-  if (int rc = set_smem((const void*)phase_cols_fwd, smem_bytes(kColsPerCta))) return rc;
+  if (int rc = set_smem((const void*)phase_cols_fwd<false>, smem_bytes(kColsPerCta))) return rc;
+  if (int rc = set_smem((const void*)phase_cols_fwd<true>, smem_bytes(kColsPerCta))) return rc;
   if (int rc = set_smem((const void*)phase_cols_adj, smem_bytes1(kColsAdj))) return rc;
   if (int rc = set_smem((const void*)phase_rows_adj, smem_bytes1(kRowsAdj / 2))) return rc;
   op->oC = op->C;
@@ -635,7 +658,11 @@ int phase_forward(const dps_operator* op, const FwdArgs& a, cudaStream_t st) {
   phase_rows_fwd<<<g1, kThreads, smem_bytes(kRowsPerCta / 2), st>>>(a, op->phase->tw, op->C);
   DPS_LAUNCH_CHECK("phase_rows_fwd");
   dim3 g2((unsigned)(op->C * kColGroups), (unsigned)a.n);
-  phase_cols_fwd<<<g2, kThreads, smem_bytes(kColsPerCta), st>>>(a, op->phase->tw, op->C);
+  static const bool lean = getenv("DPSTTC_PHASE_LEAN") && getenv("DPSTTC_PHASE_LEAN")[0] == '1';  // opt-in, see phase_cols_fwd
+  if (lean)
+    phase_cols_fwd<true><<<g2, kThreads, smem_bytes(kColsPerCta), st>>>(a, op->phase->tw, op->C);
+  else
+    phase_cols_fwd<false><<<g2, kThreads, smem_bytes(kColsPerCta), st>>>(a, op->phase->tw, op->C);
   DPS_LAUNCH_CHECK("phase_cols_fwd");
   return DPS_OK;
 }

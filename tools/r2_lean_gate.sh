@@ -1,5 +1,5 @@
 #!/bin/bash
-# Gate + A/B of the opt-in lean SR kernels (written after round 1's last GPU call; see profiles/r1l_resize_n8_sass.md).
+# Gate + A/B of the opt-in lean kernels (SR strip forward / short-strip adjoint, phase column epilogue) (written after round 1's last GPU call; see profiles/r1l_resize_n8_sass.md).
 #   gpurun --timeout 420 -- 'bash tools/r2_lean_gate.sh r2a'   →  gpurun_out/<tag>_lean_*
 # 1. bit-identity against the default kernels (must print PASS twice per op), 2. µs per launch at N = 4 / 8 / 12 / 32.
 tag=${1:-r2a}
@@ -14,4 +14,10 @@ for v in 0 1; do for n in 4 8 12 32; do
   DPSTTC_RESIZE_FWD_LEAN=$v DPSTTC_RESIZE_ADJ_LEAN=$v timeout 90 python tools/kernel_bench.py --n $n --iters 50 --graph --only sr4 \
     > gpurun_out/${tag}_lean${v}_n$n.jsonl 2> gpurun_out/${tag}_lean${v}_n$n.err
 done; done
-tail -n 3 gpurun_out/${tag}_lean_gate_n*.log; cat gpurun_out/${tag}_lean*_n*.jsonl | cut -c1-150
+# phase retrieval: lean output epilogue of the column kernel (DPSTTC_PHASE_LEAN=1)
+timeout 200 python tools/variant_check.py --op phase --n 4 --env DPSTTC_PHASE_LEAN=0 --env DPSTTC_PHASE_LEAN=1 > gpurun_out/${tag}_lean_gate_phase.log 2>&1
+echo "gate phase rc=$?" >> gpurun_out/${tag}_lean_gate_phase.log
+for v in 0 1; do for n in 8 32; do
+  DPSTTC_PHASE_LEAN=$v timeout 90 python tools/kernel_bench.py --n $n --iters 50 --graph --only phase > gpurun_out/${tag}_phase_lean${v}_n$n.jsonl 2> gpurun_out/${tag}_phase_lean${v}_n$n.err
+done; done
+tail -n 3 gpurun_out/${tag}_lean_gate_n*.log gpurun_out/${tag}_lean_gate_phase.log; cat gpurun_out/${tag}_lean*_n*.jsonl | cut -c1-150
