@@ -544,9 +544,29 @@ __global__ void __launch_bounds__(256, kStages == kStagesStd ? 4 : 2) resize_fwd
 // Variants that were measured and lost (N = 128, this kernel 50.7 µs): 16-row stages × 3 with a single V tile 64 µs,
 // 32-row stages × 3 at one CTA per SM 66 µs, 8 H warps (one row half each) + W pass on the split tile 63 µs, 8 H warps
 // with one column per thread (scalar FFMA) 56.8 µs, chunks issued in pairs 50.9 µs, in triples 53.1 µs.
+// wpass_one for oW = 64 and KW taps at compile time (the form validated bit-identical in resize_fwd_lean_kernel): i → (j, jc) by
+// shifts, taps unrolled.  Used by the streaming forward's W warps under DPSTTC_RESIZE_FWD_LEAN=1: with the generic wpass_one
+// (≈180 instructions per output, 4 outputs per thread and strip) the four W warps, not the H warps, pace a CTA.
+template <int KW>
+DPS_DEV void wpass_one_lean(const FwdSmem& m, int oH, int strip, int i, bool has_y, float yv, float* outp, float& sq, float& ab) {
+  constexpr int W = 256, oW = 64;
+  const int j = i >> 6, jc = i & (oW - 1);
+  const int orow = strip * kRO + j;
+  if (orow >= oH) return;
+  const int cs = m.css[jc];
+  const float* vr = m.V + j * W + cs;
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < KW; ++k) s = fmaf(m.wws[k * oW + jc], (cs + k < W) ? vr[k] : 0.f, s);
+  const float res = has_y ? __fsub_rn(yv, s) : s;
+  stg_stream(outp + (int64_t)orow * oW + jc, res);
+  sq += res * res;
+  ab += fabsf(res);
+}
+
 constexpr int kSfStages = 5;
 
-template <int D>
+template <int D, bool kLeanW = false>  // kLeanW: opt-in (oW = 64, 16 taps), see wpass_one_lean
 __global__ void __launch_bounds__(kSaThreads, 2) resize_fwd_stream_kernel(const FwdTables t, const FwdStream fs, int C, int H,
                                                                             int oH, int oW, int units, const FwdArgs a) {
   constexpr int W = 256, W2 = 128, kStageFloats = 2 * 8 * W;
@@ -699,10 +719,16 @@ __global__ void __launch_bounds__(kSaThreads, 2) resize_fwd_stream_kernel(const 
       for (int vtt = 0; vtt < 2; ++vtt) {
         const int vt = wt + vtt * 128;
 #pragma unroll
-        for (int uu = 0; uu < kYPre; ++uu)
-          if (vt + uu * 256 < kRO * oW)
-            wpass_one(m, t, W, oH, oW, strip, vt + uu * 256, yp, true, yv[vtt][uu], outp, sq[vtt], ab[vtt]);
-        for (int i = vt + kYPre * 256; i < kRO * oW; i += 256) wpass_one(m, t, W, oH, oW, strip, i, yp, false, 0.f, outp, sq[vtt], ab[vtt]);
+        for (int uu = 0; uu < kYPre; ++uu) {
+          if constexpr (kLeanW) {  // kRO·oW = 512 = kYPre·256: every output of a thread has its measurement value prefetched
+            wpass_one_lean<16>(m, oH, strip, vt + uu * 256, yp != nullptr, yv[vtt][uu], outp, sq[vtt], ab[vtt]);
+          } else {
+            if (vt + uu * 256 < kRO * oW)
+              wpass_one(m, t, W, oH, oW, strip, vt + uu * 256, yp, true, yv[vtt][uu], outp, sq[vtt], ab[vtt]);
+          }
+        }
+        if constexpr (!kLeanW)
+          for (int i = vt + kYPre * 256; i < kRO * oW; i += 256) wpass_one(m, t, W, oH, oW, strip, i, yp, false, 0.f, outp, sq[vtt], ab[vtt]);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&vempty[buf]);  // the tile has been read
@@ -1355,7 +1381,18 @@ int resize_forward(const dps_operator* op, const FwdArgs& a, cudaStream_t st) {
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, op->device);
       const int rounds = (int)((units + 2 * sms - 1) / (2 * sms));
       const int grid = (int)((units + rounds - 1) / rounds);  // every CTA gets `rounds` units (±1): no ragged tail
-      if (fs.D == 2)
+      if (fwd_lean() && op->oW == 64 && f.kw == 16) {  // opt-in: lean W pass (wpass_one_lean)
+        static bool lsattr = false;
+        if (!lsattr) {
+          DPS_CUDA(cudaFuncSetAttribute(resize_fwd_stream_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+          DPS_CUDA(cudaFuncSetAttribute(resize_fwd_stream_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+          lsattr = true;
+        }
+        if (fs.D == 2)
+          resize_fwd_stream_kernel<2, true><<<grid, kSaThreads, smem, st>>>(f, fs, op->C, op->H, op->oH, op->oW, (int)units, a);
+        else
+          resize_fwd_stream_kernel<1, true><<<grid, kSaThreads, smem, st>>>(f, fs, op->C, op->H, op->oH, op->oW, (int)units, a);
+      } else if (fs.D == 2)
         resize_fwd_stream_kernel<2><<<grid, kSaThreads, smem, st>>>(f, fs, op->C, op->H, op->oH, op->oW, (int)units, a);
       else
         resize_fwd_stream_kernel<1><<<grid, kSaThreads, smem, st>>>(f, fs, op->C, op->H, op->oH, op->oW, (int)units, a);
