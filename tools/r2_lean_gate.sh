@@ -1,5 +1,5 @@
 #!/bin/bash
-# Gate + A/B of the opt-in lean kernels (SR strip forward / short-strip adjoint, phase column epilogue) (written after round 1's last GPU call; see profiles/r1l_resize_n8_sass.md).
+# Gate + A/B of the opt-in lean kernels (SR strip forward, short-strip adjoint, streaming forward W pass, phase column epilogue) (written after round 1's last GPU call; see profiles/r1l_resize_n8_sass.md).
 #   gpurun --timeout 420 -- 'bash tools/r2_lean_gate.sh r2a'   →  gpurun_out/<tag>_lean_*
 # 1. bit-identity against the default kernels (must print PASS twice per op), 2. µs per launch at N = 4 / 8 / 12 / 32.
 tag=${1:-r2a}
