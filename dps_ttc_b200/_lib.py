@@ -78,6 +78,7 @@ SIGNATURES = {
     "dps_ancestors_systematic": (_I, [_P, _I, _P, _I, _P, _P, _P]),
     "dps_gather_particles": (_I, [_P, _P, _P, _I, _L, _P]),
     "dps_gather_particles_p2p": (_I, [_P, _I, _P, _P, _I, _L, _P]),
+    "dps_exchange_particles_p2p": (_I, [_P, _P, _I, _I, C.c_uint32, _L, _I, _P, _P, _I, _L, _P]),
     "dps_argmin": (_I, [_P, _I, _P, _P, _P]),
     "dps_broadcast_particle": (_I, [_P, _P, _P, _I, _L, _P]),
 }

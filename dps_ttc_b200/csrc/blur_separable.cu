@@ -677,31 +677,19 @@ int sep_launch(const dps_operator* op, const SepSet& set, const FwdArgs& fa, con
   p.C = op->C; p.H = op->H; p.W = op->W;
   p.strips = (op->H + kRows - 1) / kRows;
   const size_t smem = sep_smem_for(R, op->W);
-  static bool attr_set = false;  // per template instantiation
   dim3 grid((unsigned)(p.C * p.strips), (unsigned)n);
   if constexpr (R <= 16) {
-    if (!attr_set) {
-      DPS_CUDA(cudaFuncSetAttribute(sep2_kernel<R, 256, kAdjoint>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      DPS_CUDA(cudaFuncSetAttribute(sep2_kernel<R, 0, kAdjoint>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      attr_set = true;
-    }
+    DPS_SMEM_OPTIN((sep2_kernel<R, 256, kAdjoint>), 227 * 1024, op->device);
+    DPS_SMEM_OPTIN((sep2_kernel<R, 0, kAdjoint>), 227 * 1024, op->device);
     if (op->W == 256 && op->H % kRows == 0) {
-      static bool attr3_set = false;
-      if (!attr3_set) {
-        DPS_CUDA(cudaFuncSetAttribute(sep3_kernel<R, kAdjoint>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)sep3_smem_bytes<R>()));
-        attr3_set = true;
-      }
+      DPS_SMEM_OPTIN((sep3_kernel<R, kAdjoint>), sep3_smem_bytes<R>(), op->device);
       sep3_kernel<R, kAdjoint><<<grid, kT3, sep3_smem_bytes<R>(), st>>>(p, fa, aa);
     } else if (op->W == 256)
       sep2_kernel<R, 256, kAdjoint><<<grid, kThreads, smem, st>>>(p, fa, aa);
     else
       sep2_kernel<R, 0, kAdjoint><<<grid, kThreads, smem, st>>>(p, fa, aa);
   } else {
-    if (!attr_set) {
-      DPS_CUDA(cudaFuncSetAttribute(sep1_kernel<R, kAdjoint>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      attr_set = true;
-    }
+    DPS_SMEM_OPTIN((sep1_kernel<R, kAdjoint>), 227 * 1024, op->device);
     sep1_kernel<R, kAdjoint><<<grid, kThreads, smem, st>>>(p, fa, aa);
   }
   DPS_LAUNCH_CHECK(kAdjoint ? "sep_blur_adjoint" : "sep_blur_forward");

@@ -4,6 +4,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "../../include/dpsttc.h"
 
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
@@ -42,6 +44,18 @@ void dps_count_launch(int n = 1);
       return DPS_ERR_CUDA;                                                              \
     }                                                                                   \
     dps_count_launch();                                                                 \
+  } while (0)
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute of a kernel: remember per device (bit d of a mask that
+// is static per call site, i.e. per kernel instantiation) that the opt-in has been made.  Thread-safe; setting twice is harmless.
+#define DPS_SMEM_OPTIN(fn, bytes, device)                                                               \
+  do {                                                                                                  \
+    static std::atomic<uint64_t> done_{0};                                                              \
+    const uint64_t bit_ = 1ull << ((device) & 63);                                                      \
+    if (!(done_.load(std::memory_order_acquire) & bit_)) {                                              \
+      DPS_CUDA(cudaFuncSetAttribute((fn), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));  \
+      done_.fetch_or(bit_, std::memory_order_release);                                                  \
+    }                                                                                                   \
   } while (0)
 
 static inline bool dps_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

@@ -28,6 +28,15 @@ int new_op(int kind, int C, int H, int W, dps_operator** out, const char* who) {
   return DPS_OK;
 }
 
+// The plan's tables live on op->device and the launch goes to the CALLER's current device: they must be the same one.
+int check_device(const dps_operator* op, const char* who) {
+  int cur = -1;
+  DPS_CUDA(cudaGetDevice(&cur));
+  DPS_REQUIRE(cur == op->device, DPS_ERR_INVALID, "%s: the operator was created on device %d but the current device is %d", who,
+              op->device, cur);
+  return DPS_OK;
+}
+
 int fail(dps_operator** out, int rc) {
   if (out && *out) {
     dps_operator_destroy(*out);
@@ -148,6 +157,7 @@ int dps_operator_forward(const dps_operator* op, const dps_source* src, const fl
                          float* partials, float* aux, int n, dps_stream_t stream) {
   DPS_REQUIRE(op && src && src->x, DPS_ERR_INVALID, "dps_operator_forward: null operator/source");
   DPS_REQUIRE(n > 0 && n <= 65535, DPS_ERR_INVALID, "dps_operator_forward: bad particle count %d", n);
+  if (int rc = check_device(op, "dps_operator_forward")) return rc;
   DPS_REQUIRE(out || (op->kind == DPS_OP_PHASE && aux), DPS_ERR_INVALID, "dps_operator_forward: null output");
   DPS_REQUIRE(dps_aligned16(src->x) && dps_aligned16(src->eps) && dps_aligned16(y) && dps_aligned16(out) &&
                   dps_aligned16(aux) && src->x_stride % 4 == 0 && (!src->eps || src->eps_stride % 4 == 0) &&
@@ -181,6 +191,7 @@ int dps_operator_adjoint(const dps_operator* op, const float* r, const float* co
   DPS_REQUIRE(op && g, DPS_ERR_INVALID, "dps_operator_adjoint: null operator/output");
   DPS_REQUIRE(r || (op->kind == DPS_OP_PHASE && aux), DPS_ERR_INVALID, "dps_operator_adjoint: null residual");
   DPS_REQUIRE(n > 0 && n <= 65535, DPS_ERR_INVALID, "dps_operator_adjoint: bad particle count %d", n);
+  if (int rc = check_device(op, "dps_operator_adjoint")) return rc;
   DPS_REQUIRE(dps_aligned16(r) && dps_aligned16(extra) && dps_aligned16(g) && dps_aligned16(aux) && g_stride % 4 == 0 &&
                   extra_stride % 4 == 0,
               DPS_ERR_ALIGN, "dps_operator_adjoint: tensors must be 16-byte aligned, strides multiples of 4");

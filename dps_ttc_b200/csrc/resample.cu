@@ -221,6 +221,70 @@ __global__ void __launch_bounds__(kCopyThreads) gather_p2p_kernel(const float* c
   }
 }
 
+// ---- the same with the inter-GPU rendezvous INSIDE the kernel (no barrier launches around it) -------------------------
+// signal_pads[r] points (in this process) at rank r's pad of `world` uint32 words; rank q announces "my particle buffer of
+// exchange `epoch` is complete" by storing `epoch` into word q of EVERY rank's pad (release, system scope: the stores of the
+// kernel that produced the particles — an earlier kernel of the same stream — are ordered before it).  A CTA then only
+// waits for the OWNER of the particle it copies, so copies from ranks that are ready start while others are still arriving.
+// CTA (0,0) additionally waits for every peer: when this kernel has finished on rank A, all ranks have started exchange
+// `epoch`, hence finished exchange `epoch − 1` (stream order).  With the particle buffers double-buffered by epoch parity
+// (slot_elems selects the half) a buffer is therefore never overwritten while a peer still reads it, and no trailing
+// barrier is needed.  Epochs only grow (wrap-safe signed comparison); a peer that never arrives traps instead of hanging.
+DPS_DEV unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+DPS_DEV void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+DPS_DEV float4 ld_relaxed_sys4(const float4* p) {
+  float4 r;
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+DPS_DEV void wait_epoch(const unsigned* word, unsigned epoch) {
+  unsigned spins = 0;
+  while ((int)(ld_acquire_sys(word) - epoch) < 0) {
+    if (++spins > (1u << 26)) __trap();  // a peer never announced this exchange: fail the launch instead of hanging the GPU
+    __nanosleep(64);
+  }
+}
+
+__global__ void __launch_bounds__(kCopyThreads) gather_p2p_sync_kernel(const float* const* __restrict__ peer_bases,
+                                                                       unsigned* const* __restrict__ signal_pads, int rank,
+                                                                       int world, unsigned epoch, int64_t slot_elems,
+                                                                       int n_per_rank,
+                                                                       const int64_t* __restrict__ ancestors,
+                                                                       float* __restrict__ dst, int64_t elems4) {
+  const int i = blockIdx.y;
+  const bool lead = blockIdx.x == 0 && blockIdx.y == 0;
+  if (lead && threadIdx.x < world) {
+    __threadfence_system();
+    st_release_sys(signal_pads[threadIdx.x] + rank, epoch);
+  }
+  const int64_t a = ancestors[i];
+  const int owner = (int)(a / n_per_rank);
+  const unsigned* mine = signal_pads[rank];
+  if (threadIdx.x == 0) wait_epoch(mine + owner, epoch);
+  __syncthreads();
+  const float4* s = reinterpret_cast<const float4*>(peer_bases[owner] + slot_elems) + (a - (int64_t)owner * n_per_rank) * elems4;
+  float* d = dst + (int64_t)i * elems4 * 4;
+  const int64_t base = (int64_t)blockIdx.x * (kCopyThreads * kCopyVec) + threadIdx.x;
+  float4 v[kCopyVec];
+#pragma unroll
+  for (int u = 0; u < kCopyVec; ++u) {
+    const int64_t j = base + (int64_t)u * kCopyThreads;
+    if (j < elems4) v[u] = ld_relaxed_sys4(s + j);
+  }
+#pragma unroll
+  for (int u = 0; u < kCopyVec; ++u) {
+    const int64_t j = base + (int64_t)u * kCopyThreads;
+    if (j < elems4) stg_stream4(d + j * 4, v[u]);
+  }
+  if (lead && threadIdx.x < world) wait_epoch(mine + threadIdx.x, epoch);
+}
+
 __global__ void __launch_bounds__(1024) argmin_kernel(const float* __restrict__ costs, int n, int64_t* __restrict__ best,
                                                       float* __restrict__ best_cost) {
   __shared__ float s_v[32];
@@ -361,6 +425,26 @@ int dps_gather_particles_p2p(const float* const* peer_bases_dev, int n_per_rank,
   dim3 grid((unsigned)((e4 + per - 1) / per), (unsigned)n_dst);
   gather_p2p_kernel<<<grid, kCopyThreads, 0, (cudaStream_t)stream>>>(peer_bases_dev, n_per_rank, ancestors, dst, e4);
   DPS_LAUNCH_CHECK("dps_gather_particles_p2p");
+  return DPS_OK;
+}
+
+int dps_exchange_particles_p2p(const float* const* peer_bases_dev, uint32_t* const* signal_pads_dev, int rank, int world,
+                               uint32_t epoch, int64_t slot_elems, int n_per_rank, const int64_t* ancestors, float* dst,
+                               int n_dst, int64_t elems, dps_stream_t stream) {
+  DPS_REQUIRE(peer_bases_dev && signal_pads_dev && ancestors && dst && n_per_rank > 0 && n_dst > 0 && n_dst <= 65535 &&
+                  elems > 0,
+              DPS_ERR_INVALID, "dps_exchange_particles_p2p: bad arguments");
+  DPS_REQUIRE(world > 0 && world <= kCopyThreads && rank >= 0 && rank < world, DPS_ERR_INVALID,
+              "dps_exchange_particles_p2p: bad rank %d of %d", rank, world);
+  DPS_REQUIRE(elems % 4 == 0 && slot_elems % 4 == 0 && slot_elems >= 0, DPS_ERR_UNSUPPORTED,
+              "dps_exchange_particles_p2p: elems and slot_elems must be multiples of 4");
+  DPS_REQUIRE(dps_aligned16(dst), DPS_ERR_ALIGN, "dps_exchange_particles_p2p: dst must be 16-byte aligned");
+  const int64_t e4 = elems / 4;
+  const int per = kCopyThreads * kCopyVec;
+  dim3 grid((unsigned)((e4 + per - 1) / per), (unsigned)n_dst);
+  gather_p2p_sync_kernel<<<grid, kCopyThreads, 0, (cudaStream_t)stream>>>(peer_bases_dev, signal_pads_dev, rank, world, epoch,
+                                                                          slot_elems, n_per_rank, ancestors, dst, e4);
+  DPS_LAUNCH_CHECK("dps_exchange_particles_p2p");
   return DPS_OK;
 }
 

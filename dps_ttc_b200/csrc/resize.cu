@@ -1339,8 +1339,8 @@ static bool fwd_deep_ring(int64_t ctas, int device) {
     pin = !e ? 0 : (e[0] == '6' ? 6 : 3);
   }
   if (pin) return pin == 6;
-  static int sms = 0;
-  if (!sms) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
   return 3 * ctas <= 2 * (int64_t)sms;
 }
 
@@ -1356,14 +1356,10 @@ static bool fwd_lean() {
 
 int resize_forward(const dps_operator* op, const FwdArgs& a, cudaStream_t st) {
   const FwdTables& f = op->resize->f;
-  static bool attr_set = false;
-  if (!attr_set) {
-    DPS_CUDA(cudaFuncSetAttribute(resize_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    DPS_CUDA(cudaFuncSetAttribute(resize_fwd_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    DPS_CUDA(cudaFuncSetAttribute(resize_fwd_bulk_kernel<kStagesStd>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    DPS_CUDA(cudaFuncSetAttribute(resize_fwd_bulk_kernel<kStagesDeep>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
+  DPS_SMEM_OPTIN((resize_fwd_kernel), 227 * 1024, op->device);
+  DPS_SMEM_OPTIN((resize_fwd_pair_kernel<2>), 227 * 1024, op->device);
+  DPS_SMEM_OPTIN((resize_fwd_bulk_kernel<kStagesStd>), 227 * 1024, op->device);
+  DPS_SMEM_OPTIN((resize_fwd_bulk_kernel<kStagesDeep>), 227 * 1024, op->device);
   {  // streaming variant once the strip grid would fill the machine several times over
     const FwdStream& fs = op->resize->fs;
     const int64_t units = (int64_t)op->C * fs.upp * a.n;
@@ -1371,23 +1367,15 @@ int resize_forward(const dps_operator* op, const FwdArgs& a, cudaStream_t st) {
     const size_t smem = sizeof(float) * (32 + (size_t)kSfStages * 2 * 8 * 256 + 2 * kRO * 256 + (size_t)op->H * kWO + 128 +
                                          (size_t)((f.kw * op->oW + 3) & ~3) + op->oW);
     if (fs.ok && smem <= 113 * 1024 && units < (1 << 30) && (v == 3 || (v == 0 && (int64_t)op->C * f.fstrips * a.n >= 80 * 24))) {  // N ≥ 80: 41.1 vs 44.5 µs at 96, 50.7 vs 56.6 at 128
-      static bool sattr = false;
-      if (!sattr) {
-        DPS_CUDA(cudaFuncSetAttribute(resize_fwd_stream_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        DPS_CUDA(cudaFuncSetAttribute(resize_fwd_stream_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        sattr = true;
-      }
+      DPS_SMEM_OPTIN((resize_fwd_stream_kernel<1>), 227 * 1024, op->device);
+      DPS_SMEM_OPTIN((resize_fwd_stream_kernel<2>), 227 * 1024, op->device);
       int sms = 148;
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, op->device);
       const int rounds = (int)((units + 2 * sms - 1) / (2 * sms));
       const int grid = (int)((units + rounds - 1) / rounds);  // every CTA gets `rounds` units (±1): no ragged tail
       if (fwd_lean() && op->oW == 64 && f.kw == 16) {  // opt-in: lean W pass (wpass_one_lean)
-        static bool lsattr = false;
-        if (!lsattr) {
-          DPS_CUDA(cudaFuncSetAttribute(resize_fwd_stream_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-          DPS_CUDA(cudaFuncSetAttribute(resize_fwd_stream_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-          lsattr = true;
-        }
+        DPS_SMEM_OPTIN((resize_fwd_stream_kernel<1, true>), 227 * 1024, op->device);
+        DPS_SMEM_OPTIN((resize_fwd_stream_kernel<2, true>), 227 * 1024, op->device);
         if (fs.D == 2)
           resize_fwd_stream_kernel<2, true><<<grid, kSaThreads, smem, st>>>(f, fs, op->C, op->H, op->oH, op->oW, (int)units, a);
         else
@@ -1406,12 +1394,8 @@ int resize_forward(const dps_operator* op, const FwdArgs& a, cudaStream_t st) {
     if (pair_path)
       resize_fwd_pair_kernel<2><<<grid, 256, fwd_smem(f, 2, 256, op->oW), st>>>(f, op->C, op->H, op->oH, op->oW, a);
     else if (fwd_lean() && a.src.eps && a.src.clip && op->oW == 64 && f.kw == 16 && a.n > 0) {
-      static bool lattr = false;
-      if (!lattr) {
-        DPS_CUDA(cudaFuncSetAttribute(resize_fwd_lean_kernel<kStagesStd, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        DPS_CUDA(cudaFuncSetAttribute(resize_fwd_lean_kernel<kStagesDeep, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        lattr = true;
-      }
+      DPS_SMEM_OPTIN((resize_fwd_lean_kernel<kStagesStd, 16>), 227 * 1024, op->device);
+      DPS_SMEM_OPTIN((resize_fwd_lean_kernel<kStagesDeep, 16>), 227 * 1024, op->device);
       if (fwd_deep_ring((int64_t)grid.x * grid.y, op->device))
         resize_fwd_lean_kernel<kStagesDeep, 16><<<grid, 256, fwd_smem(f, 0, 256, op->oW) + sizeof(float) * (32 + kStagesDeep * 2 * kCR * 256), st>>>(
             f, op->C, op->H, op->oH, a);
@@ -1434,12 +1418,8 @@ int resize_forward(const dps_operator* op, const FwdArgs& a, cudaStream_t st) {
 template <int RA, int KJ, int KT>
 static int launch_adj(const dps_operator* op, const AdjStrips& strips, const AdjArgs& a, cudaStream_t st) {
   const ResizeTables& t = *op->resize;
-  static bool attr_set = false;
-  if (!attr_set) {
-    DPS_CUDA(cudaFuncSetAttribute(resize_adj_kernel<RA, KJ, KT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    DPS_CUDA(cudaFuncSetAttribute(resize_adj_kernel<RA, KJ, KT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
+  DPS_SMEM_OPTIN((resize_adj_kernel<RA, KJ, KT, false>), 227 * 1024, op->device);
+  DPS_SMEM_OPTIN((resize_adj_kernel<RA, KJ, KT, true>), 227 * 1024, op->device);
   dim3 grid((unsigned)(op->C * strips.strips), (unsigned)a.n);
   const size_t base = adj_smem(RA, KJ, op->oW, t.cols.kt, op->W);
   const size_t bulk = base + sizeof(float) * (32 + (size_t)2 * RA * op->W);
@@ -1459,11 +1439,7 @@ static int launch_adj(const dps_operator* op, const AdjStrips& strips, const Adj
 template <int KT>
 static int launch_adj_stream(const dps_operator* op, const AdjArgs& a, cudaStream_t st) {
   const ResizeTables& t = *op->resize;
-  static bool attr_set = false;
-  if (!attr_set) {
-    DPS_CUDA(cudaFuncSetAttribute(resize_adj_stream_kernel<kJMax, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
+  DPS_SMEM_OPTIN((resize_adj_stream_kernel<kJMax, KT>), 227 * 1024, op->device);
   const int units = op->C * t.big.strips * a.n;
   const size_t smem = sizeof(float) * (32 + (size_t)kSaStages * 2 * kSaRows * 256 + 2 * ((size_t)kJMax * op->oW + kRA * kJMax));
   int sms = 148;
@@ -1493,11 +1469,7 @@ int resize_adjoint(const dps_operator* op, const AdjArgs& a, cudaStream_t st) {
     static const bool lean = getenv("DPSTTC_RESIZE_ADJ_LEAN") && getenv("DPSTTC_RESIZE_ADJ_LEAN")[0] == '1';  // opt-in, see its header
     const bool masked = a.has_mask && a.mask_src.eps && a.mask_src.clip;
     if (lean && narrow && masked && !a.extra && op->W == 256 && op->H % kRAs == 0 && op->oW == 64 && a.r) {
-      static bool lattr = false;
-      if (!lattr) {
-        DPS_CUDA(cudaFuncSetAttribute(resize_adj_lean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        lattr = true;
-      }
+      DPS_SMEM_OPTIN((resize_adj_lean_kernel), 227 * 1024, op->device);
       dim3 grid((unsigned)(op->C * t.small.strips), (unsigned)a.n);
       const size_t smem = adj_smem(kRAs, kJs, op->oW, t.cols.kt, op->W) + sizeof(float) * (32 + (size_t)2 * kRAs * op->W);
       resize_adj_lean_kernel<<<grid, kThreads, smem, st>>>(t.small, t.cols, op->C, op->H, op->oH, a);

@@ -4,6 +4,7 @@ allocates in a launch); all launches go to torch's current stream.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 
 import numpy as np
@@ -36,6 +37,13 @@ class KernelTimer:
 
 
 TIMER = None
+_NULL = contextlib.nullcontext()
+
+
+def _on(device):
+    """Context that makes `device` the current CUDA device when it is not already (a launch goes to the current device;
+    the operator tables and the per-device shared-memory opt-in belong to the plan's device)."""
+    return _NULL if torch.cuda.current_device() == device.index else torch.cuda.device(device)
 
 
 def _chw(x: torch.Tensor) -> int:
@@ -158,6 +166,8 @@ class OperatorPlan:
         device = torch.device(device)
         if device.type != "cuda":
             raise DpsError("dps_ttc_b200 operators need a CUDA device (no CPU path)")
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
         handle = C.c_void_p()
         with torch.cuda.device(device):
             check(getattr(lib(), fn_name)(*args, C.byref(handle)), fn_name)
@@ -193,6 +203,8 @@ class OperatorPlan:
     # -- launches ---------------------------------------------------------------------------------
     def _check_in(self, x, name):
         require_cuda_f32(x, name)
+        if x.device != self.device:
+            raise DpsError(f"{name} is on {x.device} but this operator plan's tables live on {self.device}")
         if tuple(x.shape[1:]) != self.in_shape:
             raise DpsError(f"{name}: expected (N,{self.in_shape}), got {tuple(x.shape)}")
 
@@ -221,8 +233,9 @@ class OperatorPlan:
         if self.aux_floats and aux is None:
             aux = self.new_aux(n)
         tok = TIMER.start(f"{self.kind}_forward") if TIMER else None
-        check(lib().dps_operator_forward(self._h, C.byref(src), yp, ys, out.data_ptr(), ptr(partials), ptr(aux), n,
-                                         stream_ptr(x.device)), f"dps_operator_forward[{self.kind}]")
+        with _on(self.device):
+            check(lib().dps_operator_forward(self._h, C.byref(src), yp, ys, out.data_ptr(), ptr(partials), ptr(aux), n,
+                                             stream_ptr(x.device)), f"dps_operator_forward[{self.kind}]")
         if tok:
             TIMER.stop(tok)
         return out, partials, aux
@@ -231,6 +244,8 @@ class OperatorPlan:
         """g = 1[−1 ≤ c1·x − c2·ε ≤ 1] ⊙ (coef_n·Aᵀr + extra); mask only when mask_x/mask_eps given.
         `out` may be a channel-slice view of a larger buffer."""
         require_cuda_f32(r, "r")
+        if r.device != self.device:
+            raise DpsError(f"r is on {r.device} but this operator plan's tables live on {self.device}")
         n = r.shape[0]
         if tuple(r.shape[1:]) != self.out_shape:
             raise DpsError(f"r: expected (N,{self.out_shape}), got {tuple(r.shape)}")
@@ -249,8 +264,9 @@ class OperatorPlan:
                 raise DpsError("phase retrieval adjoint needs the aux tensor its forward pass returned (the phase)")
             aux = self.new_aux(n)  # pure scratch (padded t of the sparse-blur adjoint)
         tok = TIMER.start(f"{self.kind}_adjoint") if TIMER else None
-        check(lib().dps_operator_adjoint(self._h, r.data_ptr(), ptr(coef), msrc, ep, es, gp, gs, ptr(aux), n,
-                                         stream_ptr(r.device)), f"dps_operator_adjoint[{self.kind}]")
+        with _on(self.device):
+            check(lib().dps_operator_adjoint(self._h, r.data_ptr(), ptr(coef), msrc, ep, es, gp, gs, ptr(aux), n,
+                                             stream_ptr(r.device)), f"dps_operator_adjoint[{self.kind}]")
         if tok:
             TIMER.stop(tok)
         return out
@@ -353,6 +369,19 @@ def gather_particles_p2p(peer_ptrs_dev: int, n_per_rank: int, ancestors_idx, lik
     out = torch.empty((n_dst,) + tuple(like.shape[1:]), device=like.device, dtype=torch.float32) if out is None else out
     check(lib().dps_gather_particles_p2p(peer_ptrs_dev, int(n_per_rank), ancestors_idx.data_ptr(), out.data_ptr(), n_dst,
                                          elems, stream_ptr(like.device)), "dps_gather_particles_p2p")
+    return out
+
+
+def exchange_particles_p2p(peer_ptrs_dev: int, signal_pads_dev: int, rank: int, world: int, epoch: int, slot_elems: int,
+                           n_per_rank: int, ancestors_idx, like, out=None):
+    """gather_particles_p2p with the inter-GPU rendezvous inside the kernel (dps_exchange_particles_p2p): no barrier
+    launches around it; reads the half of the double-buffered symmetric particle buffers that starts at `slot_elems`."""
+    n_dst = ancestors_idx.numel()
+    elems = like[0].numel()
+    out = torch.empty((n_dst,) + tuple(like.shape[1:]), device=like.device, dtype=torch.float32) if out is None else out
+    check(lib().dps_exchange_particles_p2p(peer_ptrs_dev, signal_pads_dev, int(rank), int(world), int(epoch) & 0xFFFFFFFF,
+                                           int(slot_elems), int(n_per_rank), ancestors_idx.data_ptr(), out.data_ptr(),
+                                           n_dst, elems, stream_ptr(like.device)), "dps_exchange_particles_p2p")
     return out
 
 

@@ -10,6 +10,8 @@ Two ways in:
 """
 from __future__ import annotations
 
+import zlib
+
 import numpy as np
 import torch
 
@@ -71,7 +73,7 @@ class B200Operator:
     def plan_for(self, data, **kwargs) -> OperatorPlan:
         if not data.is_cuda:
             raise DpsError(f"{type(self).__name__}: data is on {data.device}; the B200 operators have no CPU path")
-        key = self._plan_key(data.shape, kwargs)
+        key = (data.device.index, self._plan_key(data.shape, kwargs))    # plans own device tables: one per device
         plan = self._plans.get(key)
         if plan is None:
             _, C, H, W = data.shape
@@ -218,25 +220,47 @@ class MotionBlurOperator(_BlurOperator):
 class InpaintingOperator(B200Operator):
     """measurements.py:151-168: data * mask; the mask arrives as a kwarg on every call."""
 
+    _MAX_MASKS = 4     # plans kept alive (one cudaMalloc'd mask each); the drivers use one mask per image
+
     def __init__(self, device):
         super().__init__(device)
         self.name = "inpainting"
-        self._mask_cache = {}
+        self._mask_cache = {}   # key -> (strong reference to the caller's mask, its _version / content hash, host copy)
 
     def _mask_host(self, mask, H, W):
+        """(cache key, host fp32 (H, W) copy) of a mask.  A cache entry keeps a STRONG reference to the caller's mask
+        object, so its id / address cannot be recycled for another mask while the entry lives (the drivers build a new
+        mask per image: partial(cond.conditioning, mask=mask), sample_condition_*.py); a hit additionally requires the
+        same object and an unchanged tensor version (numpy: an unchanged crc32 of the bytes).  The cache is a small LRU —
+        evicted entries drop their plan and its device mask."""
         if mask is None:
             raise ValueError("Require mask")
-        key = (mask.data_ptr(), getattr(mask, "_version", 0), tuple(mask.shape)) if torch.is_tensor(mask) else id(mask)
+        is_t = torch.is_tensor(mask)
+        key = (id(mask), tuple(mask.shape), H, W)
+        stamp = mask._version if is_t else zlib.crc32(np.ascontiguousarray(mask).view(np.uint8).reshape(-1))
         hit = self._mask_cache.get(key)
-        if hit is None:
-            m = mask.detach().to("cpu", torch.float32).numpy() if torch.is_tensor(mask) else np.asarray(mask, np.float32)
-            if m.size != H * W:
-                m = np.broadcast_to(m, (1, m.shape[-3] if m.ndim >= 3 else 1, H, W))
-                if not (m == m[:, :1]).all():
-                    raise DpsError("inpainting: per-channel / per-particle masks are not supported by the kernel")
-                m = m[0, 0]
-            hit = self._mask_cache[key] = np.ascontiguousarray(m.reshape(H, W))
-        return key, hit
+        if hit is not None and hit[0] is mask and hit[1] == stamp:
+            self._mask_cache[key] = self._mask_cache.pop(key)          # most recently used last
+            return key, hit[2]
+        m = mask.detach().to("cpu", torch.float32).numpy() if is_t else np.asarray(mask, np.float32)
+        if m.size != H * W:
+            m = np.broadcast_to(m, (1, m.shape[-3] if m.ndim >= 3 else 1, H, W))
+            if not (m == m[:, :1]).all():
+                raise DpsError("inpainting: per-channel / per-particle masks are not supported by the kernel")
+            m = m[0, 0]
+        host = np.ascontiguousarray(m.reshape(H, W)).copy()
+        self._mask_cache.pop(key, None)
+        self._drop_plans(key)                                            # same object, new contents: its plan is stale
+        self._mask_cache[key] = (mask, stamp, host)
+        while len(self._mask_cache) > self._MAX_MASKS:
+            old = next(iter(self._mask_cache))
+            del self._mask_cache[old]
+            self._drop_plans(old)
+        return key, host
+
+    def _drop_plans(self, mask_key):
+        for k in [k for k in self._plans if k[1][-1] == mask_key]:
+            del self._plans[k]
 
     def _plan_key(self, shape, kwargs):
         mask = kwargs.get("mask")

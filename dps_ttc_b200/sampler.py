@@ -95,6 +95,20 @@ class NoiseTape:
         return self._get(self._u, idx, (n,), device, torch.float64)
 
 
+def _returns_gradient(method) -> bool:
+    """Does this conditioning object's conditioning() return the GRADIENT first (HEAD's ps_semantic, condition_methods.py:
+    145-195) rather than the updated x_t?  Ours say so in their GuidanceSpec; the reference's class is recognised by
+    identity when its module is loaded (by name only as a last resort, e.g. a subclass defined by a driver)."""
+    import sys
+    if isinstance(method, ConditioningMethod):
+        return method.guidance().returns == "grad"
+    ref = sys.modules.get("guided_diffusion.condition_methods")
+    ref_cls = getattr(ref, "PosteriorSamplingSemanticGuid", None) if ref is not None else None
+    if ref_cls is not None and isinstance(method, ref_cls):
+        return True
+    return any(c.__name__ == "PosteriorSamplingSemanticGuid" for c in type(method).__mro__)
+
+
 def _resolve_cond_fn(fn):
     """Unwrap functools.partial layers (the drivers bind mask=…/l1=… this way) down to the bound method."""
     bound = {}
@@ -257,39 +271,114 @@ class SpacedSampler:
             self._g3 = torch.zeros((n, C, H, W), device=x.device, dtype=torch.float32)
         return self._g6, self._g3
 
-    def _inv_abs_mean(self, y) -> float:
-        """mean(1/|y|) of the measurement (Poisson likelihood): y is fixed during a run, so it is computed once."""
-        key = (y.data_ptr(), tuple(y.shape))
-        if getattr(self, "_inv_key", None) != key:
-            self._inv_key, self._inv_val = key, float((1.0 / y.abs()).mean())
-        return self._inv_val
+    @staticmethod
+    def _inv_abs_mean(y) -> float:
+        """mean(1/|y|) of the measurement (Poisson likelihood, condition_methods.py:52).  y is fixed during a run: the loops
+        compute it ONCE per p_sample_loop call (in _prepare) and hand the value down — never cached by address, a sampler
+        object outlives its measurements."""
+        return float((1.0 / y.abs()).mean())
 
     def _graphed(self, model, x):
         """The model's forward + input-VJP captured in CUDA graphs for this particle batch (graphed.GraphedEps)."""
-        key = (id(model), tuple(x.shape), x.device)
-        if getattr(self, "_graph_key", None) != key:
-            self._graph_key, self._graph = key, GraphedEps(model, tuple(x.shape), x.device)
-        return self._graph
+        cache = self.__dict__.setdefault("_graphs", {})
+        key = (tuple(x.shape), x.device)
+        hit = cache.get(key)
+        if hit is None or hit.model is not model:       # GraphedEps holds the module: its id cannot be recycled while cached
+            if len(cache) >= 4:
+                cache.pop(next(iter(cache)))
+            hit = cache[key] = GraphedEps(model, tuple(x.shape), x.device)
+        return hit
+
+    # -- micro-batching of the ε-model ---------------------------------------------------------------
+    # The UNet's saved activations, not the graft, bound the particles per GPU (1.9 GB / particle for the FFHQ model,
+    # 5.5 GB for ImageNet-256: SURVEY §7.2).  Every quantity of a guided step is per particle (residual, its norm, the
+    # cotangent, the VJP, the update), so a step over n particles can run as ⌈n/chunk⌉ passes of "forward → residual →
+    # cotangent → VJP → update" over slices: the graph of a slice is freed before the next one is built, the results are
+    # those of the one-pass step bit for bit (kernels are particle-major: no value depends on which particles share a
+    # launch) and nothing is recomputed.  `unet_chunk`: None (one pass), an int, or "auto" (sized from free memory).
+    unet_chunk = None
+
+    def _chunk_size(self, model, x) -> int:
+        n = x.shape[0]
+        c = self.unet_chunk
+        if c is None:
+            return n
+        if c == "auto":
+            key = (id(model), tuple(x.shape[1:]), x.device)
+            if getattr(self, "_auto_chunk_key", None) != key:
+                self._auto_chunk_key, self._auto_chunk = key, self._probe_chunk(model, x)
+            c = self._auto_chunk
+        c = max(1, min(int(c), n))
+        while n % c:             # equal slices: one CUDA-graph shape, no ragged tail
+            c -= 1
+        return c
+
+    @staticmethod
+    def _probe_chunk(model, x, reserve=0.15):
+        """Particles per pass that fit: peak bytes of a ONE-particle forward + input-VJP, against the free memory."""
+        dev = x.device
+        torch.cuda.synchronize(dev)
+        torch.cuda.reset_peak_memory_stats(dev)
+        base = torch.cuda.memory_allocated(dev)
+        xi = x[:1].detach().clone().requires_grad_(True)
+        with torch.enable_grad():
+            out = model(xi, torch.zeros((1,), device=dev, dtype=torch.float32))
+            torch.autograd.grad(out, xi, torch.zeros_like(out))
+        torch.cuda.synchronize(dev)
+        per = max(1, torch.cuda.max_memory_allocated(dev) - base)
+        del out, xi
+        torch.cuda.empty_cache()
+        free, _ = torch.cuda.mem_get_info(dev)
+        return max(1, int(free * (1.0 - reserve)) // per)
 
     def guided_step(self, model, x, idx, measurement, method, spec: GuidanceSpec, cond_kwargs, noisy_measurement=None,
-                    z=None, dsg=False, graph_model=False):
+                    z=None, dsg=False, graph_model=False, inv_abs_mean=None, out=None):
         """One reverse step with measurement guidance.  Returns (x_next, meas_dist (N,), sem_dist or None).
         `dsg`: DiffStateGrad projection step (gaussian_diffusion.py:240-255) — the gradient is materialised,
-        projected onto the sample's leading singular subspaces and applied to every particle."""
+        projected onto the sample's leading singular subspaces and applied to every particle.
+        `out`: optional destination of x_next (e.g. a symmetric-memory buffer other GPUs read from)."""
+        n = x.shape[0]
+        poisson = getattr(method.noiser, "__name__", "gaussian") == "poisson" and spec.kind != "ps_semantic"
+        chunk = self._chunk_size(model, x)
+        if chunk >= n or dsg or poisson:
+            # DiffStateGrad applies particle 0's projected gradient to all particles and the Poisson likelihood has ONE norm
+            # over all particles: both need the whole batch in one pass
+            if chunk < n:
+                raise DpsError("unet_chunk: DiffStateGrad steps and the Poisson likelihood couple the particles of a step; "
+                               "run them with unet_chunk=None")
+            return self._guided_pass(model, x, idx, measurement, method, spec, cond_kwargs, noisy_measurement, z, dsg,
+                                     graph_model, inv_abs_mean, out)
+        if z is None and self._needs_z(self._consts(idx)):
+            z = self.noise.z(idx, x)                         # one draw for the whole batch: the RNG stream does not see the slicing
+        x_next = torch.empty_like(x) if out is None else out
+        dists, sems = [], []
+        for a in range(0, n, chunk):
+            sl = slice(a, a + chunk)
+            _, d, sd = self._guided_pass(model, x[sl], idx, measurement, method, spec, cond_kwargs,
+                                         None if noisy_measurement is None else noisy_measurement, None if z is None else z[sl],
+                                         False, graph_model, inv_abs_mean, x_next[sl])
+            dists.append(d)
+            sems.append(sd)
+        dist = torch.cat(dists)
+        sem = None if sems[0] is None else torch.cat([t.reshape(-1) for t in sems])
+        return x_next, dist, sem
+
+    def _guided_pass(self, model, x, idx, measurement, method, spec, cond_kwargs, noisy_measurement, z, dsg, graph_model,
+                     inv_abs_mean, out):
         k = self._consts(idx)
         op = method.operator
         gm = self._graphed(model, x) if graph_model else None
         if gm is not None:
             xd = x.detach()
-            out = gm.forward(xd, k.model_t)              # replayed forward graph; out is a static buffer
-            if out.shape[1] != 2 * x.shape[1] and self.var_mode in (0, 2):
+            mo = gm.forward(xd, k.model_t)               # replayed forward graph; mo is a static buffer
+            if mo.shape[1] != 2 * x.shape[1] and self.var_mode in (0, 2):
                 raise DpsError(f"model_var_type={self.model_var_type} needs a model with 2·C output channels")
         else:
             x = x.detach().requires_grad_(True)
             with torch.enable_grad():
-                out, eps, v = self._model_out(model, x, k)
+                mo, eps, v = self._model_out(model, x, k)
             xd = x.detach()
-        out_d = out.detach()
+        out_d = mo.detach()
         C = x.shape[1]
         eps_d = out_d[:, :C] if out_d.shape[1] == 2 * C else out_d
         v_d = out_d[:, C:] if out_d.shape[1] == 2 * C else None
@@ -300,7 +389,7 @@ class SpacedSampler:
         if getattr(method.noiser, "__name__", "gaussian") == "poisson" and spec.kind != "ps_semantic":
             # Poisson branch of grad_and_value (condition_methods.py:50-55): loss = ‖r‖_F(all particles)·mean(1/|y|);
             # norm_exp is ignored there, so ps_anneal's ζ_t multiplies the same gradient
-            inv = self._inv_abs_mean(measurement)
+            inv = self._inv_abs_mean(measurement) if inv_abs_mean is None else inv_abs_mean
             l2, coef = kernels.guidance_coef(partials, DPS_COEF_GLOBAL_NORM, spec.scale * inv)
             dist = torch.linalg.norm(l2) * inv            # the scalar the reference returns as `norm`
         else:
@@ -314,7 +403,7 @@ class SpacedSampler:
                 extra = torch.autograd.grad(sem_loss.sum(), x0)[0].contiguous()
             sem_dist = sem_dist.detach()
         # kernel 3: cotangent w.r.t. the pre-clamp x̂₀ written into the ε-channels of the cotangent buffer
-        two_c = out.shape[1] == 2 * C
+        two_c = mo.shape[1] == 2 * C
         if gm is not None:
             g = gm.cotangent[:, :C] if two_c else gm.cotangent
         else:
@@ -325,8 +414,8 @@ class SpacedSampler:
         vjp = None
         if gm is not None:
             vjp = gm.vjp()                               # replayed backward graph (input gradient only)
-        elif out.requires_grad:
-            vjp = torch.autograd.grad(out, x, grad_outputs=g6 if two_c else g3)[0]
+        elif mo.requires_grad:
+            vjp = torch.autograd.grad(mo, x, grad_outputs=g6 if two_c else g3)[0]
         # kernel 4: fused posterior update
         if z is None and self._needs_z(k):
             z = self.noise.z(idx, xd)
@@ -334,11 +423,15 @@ class SpacedSampler:
             sample, _, _ = kernels.posterior_update(self.kind, xd, eps_d, v_d, z, k, clip=clip,
                                                     var_mode=self.var_mode, max_log=self._max_log(k))
             x_next = diffstategrad.projected_update(sample, kernels.guidance_grad(g, vjp, k))
+            if out is not None:
+                x_next = out.copy_(x_next)
         else:
             x_next, _, _ = kernels.posterior_update(self.kind, xd, eps_d, v_d, z, k, clip=clip, g=g,
-                                                    vjp=vjp, var_mode=self.var_mode, max_log=self._max_log(k))
+                                                    vjp=vjp, var_mode=self.var_mode, max_log=self._max_log(k), out=out)
         if spec.project:  # mcg: x_t = operator.project(x_t, noisy_measurement)
             x_next = method.project(data=x_next, noisy_measurement=noisy_measurement, **cond_kwargs)
+            if out is not None and x_next.data_ptr() != out.data_ptr():
+                x_next = out.copy_(x_next)
         return x_next, dist, sem_dist
 
     def _generic_step(self, model, img, idx, measurement, cond_fn, extra_kw, dsg=False):
@@ -357,8 +450,7 @@ class SpacedSampler:
             return res.detach(), None, None
         first, dist = res[0], (res[1] if len(res) > 1 else None)
         third = res[2] if len(res) > 2 else None
-        obj = getattr(getattr(cond_fn, "func", cond_fn), "__self__", None)
-        returns_grad = type(obj).__name__ == "PosteriorSamplingSemanticGuid"
+        returns_grad = _returns_gradient(_resolve_cond_fn(cond_fn)[0])
         if returns_grad and dsg:
             x_next = diffstategrad.projected_update(out["sample"].detach(), first.detach().contiguous())
         else:
@@ -382,6 +474,8 @@ class SpacedSampler:
         fused = isinstance(method, ConditioningMethod) and isinstance(method.operator, B200Operator) \
             and getattr(method.noiser, "__name__", "gaussian") in ("gaussian", "poisson") \
             and method.guidance().kind != "none" and not self.dynamic_threshold
+        # Poisson likelihood: mean(1/|y|) once per loop call (one host sync here instead of one per step)
+        self._loop_inv = self._inv_abs_mean(y) if (fused and getattr(method.noiser, "__name__", "") == "poisson") else None
         return img, y, method, bound, fused
 
     # -- base loop (GaussianDiffusion.p_sample_loop, :175-303) --------------------------------------
@@ -404,7 +498,8 @@ class SpacedSampler:
                 z, q_noise = self._draws(idx, img, y, k, need_q=spec.project)
                 noisy = kernels.q_sample(y, q_noise, k.sqrt_acp, k.sqrt_1macp) if spec.project else None
                 img, meas_d, sem_d = self.guided_step(model, img, idx, y, method, spec, bound, noisy, z, dsg=dsg,
-                                                      graph_model=bool(kwargs.get("graph_model", False)))
+                                                      graph_model=bool(kwargs.get("graph_model", False)),
+                                                      inv_abs_mean=self._loop_inv)
             else:
                 img, meas_d, sem_d = self._generic_step(model, img, idx, y, measurement_cond_fn,
                                                         {"beta_scale": k.beta, "t": t}, dsg=dsg)
@@ -437,6 +532,10 @@ class SearchDDPM(DDPM):
     """Greedy best-of-N inside the loop (gaussian_diffusion.py:592-641) and the resample_update
     potentials (:516-587)."""
 
+    sync_free = False   # False: host check of max(w) != min(w) before drawing, like the reference (:545) — keeps its RNG stream.
+                        # True: no host sync; the ancestors kernel returns the identity when the weights are degenerate
+                        # (the uniforms are drawn either way, so the RNG stream differs from the reference's in that case)
+
     @torch.no_grad()
     def resample_update(self, candidates, denoised_candidates, operator, measurement, resample=True, rs_temp=0.01,
                         prev_costs=None, potential_type="min", steps_done=1, uniforms=None, **op_kwargs):
@@ -445,9 +544,9 @@ class SearchDDPM(DDPM):
             tau = rs_temp / steps_done if potential_type == "mean" else rs_temp
             logw = kernels.particle_logweights(prev_costs.float().contiguous(), tau=tau)
             w, cdf, _, degenerate = kernels.weights_cdf(logw, linear_mode=True)
-            if bool(degenerate.item()) is False:  # the reference also syncs here (:545)
+            if self.sync_free or not bool(degenerate.item()):
                 u = self.noise.uniforms(-1, n, candidates.device) if uniforms is None else uniforms
-                ids = kernels.ancestors(cdf, u, n)
+                ids = kernels.ancestors(cdf, u, n, degenerate=degenerate if self.sync_free else None)
                 candidates = kernels.gather_particles(candidates, ids)
                 denoised_candidates = kernels.gather_particles(denoised_candidates, ids)
                 prev_costs = prev_costs[ids]
@@ -509,31 +608,46 @@ class TTC_DDIM(DDIM):
 
     def p_sample_loop(self, model, x_start, measurement, measurement_cond_fn, record=False, save_root=None, **kwargs):
         img, y, method, bound, fused = self._prepare(x_start, measurement, measurement_cond_fn)
+        fused = fused and kwargs.get("fused", True)
         shards = kwargs.get("shards")
         sem_weight = kwargs.get("semantic_weight", 0.0)  # config 5: semantic term in the reweighting
+        callback = kwargs.get("callback")
+        graph_model = bool(kwargs.get("graph_model", False))
         distance = None
         self.last_stats = {"ancestors": {}}
         for idx in self._step_indices(kwargs):
             k = self._consts(idx)
-            t = idx / self.num_timesteps
             sem_d = None
+            n_total = img.shape[0] if shards is None else shards.total
+            resampling = n_total > 1 and idx % self.resample_every_steps == 0
             if fused:
-                spec = method.guidance(beta_scale=k.beta, t=t)
+                # the reference's TTC loop hands the conditioning function neither beta_scale nor t (:672-676), so
+                # ps_anneal runs with its constructor scale and ps_semantic with t = 1 — as the generic path below does
+                spec = method.guidance()
                 z, q_noise = self._draws(idx, img, y, k, need_q=spec.project)
                 noisy = kernels.q_sample(y, q_noise, k.sqrt_acp, k.sqrt_1macp) if spec.project else None
+                # sharded resampling step: the update kernel writes x_{t-1} straight into the symmetric buffer the
+                # other GPUs read from (no staging copy)
+                tgt = shards.publish_target(img) if (resampling and shards is not None and img.is_cuda) else None
+                if tgt is not None and tgt.data_ptr() == img.data_ptr():
+                    tgt = None
                 img, distance, sem_d = self.guided_step(model, img, idx, y, method, spec, bound, noisy, z,
-                                                        graph_model=bool(kwargs.get("graph_model", False)))
+                                                        graph_model=graph_model, inv_abs_mean=self._loop_inv, out=tgt)
             else:
                 img, distance, _ = self._generic_step(model, img, idx, y, measurement_cond_fn, {})
-            n_local = img.shape[0]
-            n_total = n_local if shards is None else shards.total
-            if n_total > 1 and idx % self.resample_every_steps == 0:
+            if resampling:
                 logw = kernels.particle_logweights(distance.contiguous(), sem_d if sem_weight else None,
                                                    tau=1.0 / self.resample_scale, sem_scale=sem_weight)
-                logw_all = logw if shards is None else shards.all_gather_scalars(logw)
+                if shards is None:
+                    logw_all, dist_all = logw, None
+                else:   # ONE all-gather carries the log-weights and the distances that travel with the particles
+                    both = shards.all_gather_scalars(torch.stack((logw, distance.reshape(-1)), dim=1))
+                    logw_all, dist_all = both[:, 0].contiguous(), both[:, 1]
                 w, cdf, _, degenerate = kernels.weights_cdf(logw_all, linear_mode=not self.lse_weights)
                 if not self.sync_free and bool(degenerate.item()):
-                    continue
+                    if callback is not None:
+                        callback(idx, img, distance, sem_d)
+                    continue            # the reference draws nothing when max(w) == min(w) (:693)
                 n_u = 1 if self.scheme == "systematic" else n_total
                 if shards is None:
                     u = self.noise.uniforms(idx, n_u, img.device)
@@ -546,5 +660,7 @@ class TTC_DDIM(DDIM):
                     img = kernels.gather_particles(img, ids)
                     distance = distance[ids]
                 else:
-                    img, distance = shards.exchange(img, distance, ids)
+                    img, distance = shards.exchange(img, distance, ids, dist_all=dist_all)
+            if callback is not None:
+                callback(idx, img, distance, sem_d)
         return img, distance

@@ -239,6 +239,17 @@ int dps_gather_particles(const float* src, const int64_t* ancestors, float* dst,
  * cross-rank ordering (a barrier before: buffers written; after: buffers free to be overwritten).           */
 int dps_gather_particles_p2p(const float* const* peer_bases_dev, int n_per_rank, const int64_t* ancestors,
                              float* dst, int n_dst, int64_t elems, dps_stream_t stream);
+/* The same exchange with the inter-GPU rendezvous inside the kernel (no barrier launches around it).
+ * signal_pads_dev[r]: device pointer, valid in THIS process, to rank r's pad of `world` uint32 words (zeroed once);
+ * `epoch` = 1, 2, 3, … counts the exchanges (identical on every rank).  Rank q announces that its particle buffer of
+ * this exchange is complete by writing `epoch` into word q of every rank's pad; a CTA waits only for the owner of
+ * the particle it copies.  The particle buffers are double-buffered by the caller: this exchange reads
+ * peer_bases_dev[r] + slot_elems.  When the kernel has completed, every rank has finished exchange epoch − 1, so the
+ * other half of the buffers may be overwritten (see resample.cu).  A missing peer traps (launch failure), never hangs. */
+int dps_exchange_particles_p2p(const float* const* peer_bases_dev, uint32_t* const* signal_pads_dev, int rank,
+                               int world, uint32_t epoch, int64_t slot_elems, int n_per_rank,
+                               const int64_t* ancestors, float* dst, int n_dst, int64_t elems,
+                               dps_stream_t stream);
 /* Greedy search (SearchDDPM.p_sample_loop, :630-633): best = argmin costs (first minimum).      */
 int dps_argmin(const float* costs, int n, int64_t* best, float* best_cost, dps_stream_t stream);
 /* dst[i] = src[*index] for all i in [0, n_dst)  (img[best_path.repeat(n_paths)], :633)          */

@@ -212,3 +212,32 @@ def test_psnr_matches_reference_function():
     """oracle.psnr against compute_psnr_manual of the reference (compute_metrics.py:93-98), fixture by make_golden.gen_psnr."""
     g = golden("psnr_manual.npz")
     assert np.abs(O.psnr(g["real"], g["fake"]) - g["psnr"]).max() <= 5e-6
+
+
+def test_trace_ddpm_ps_anneal_phase_retrieval():
+    """Pins the oracle's `norm_sq` guidance mode and its phase-retrieval forward / VJP to the reference:
+    ps_anneal (condition_methods.py:198-212: x_t −= β_t/σ² · ∇‖y − A(x̂₀)‖²) over the nonlinear |FFT| operator
+    (measurements.py:179-189), 3 respaced steps of DDPM.p_sample + PosterorSamplingAnnealing.conditioning as recorded by
+    oracle/make_golden.py (upstream-arity loop: beta_scale = betas[idx], anneal = 1)."""
+    from helpers import oracle_guided_step
+    g = golden("trace_ddpm_ps_anneal_phase.npz")
+    T = O.Tables(1000, "3")
+    model = TinyEps(seed=15)
+    y = g["y"]
+    pad = (y.shape[-1] - g["x_start"].shape[-1]) // 2
+    n_steps = int(g["n_steps"])
+    sigma = 0.05                                           # max(noiser.sigma, 0.05), :203
+    img = g["x_start"]
+    for i, idx in enumerate(reversed(range(n_steps))):
+        assert np.abs(img - g[f"step{i}_x_prev"]).max() <= 1e-4 * max(1.0, np.abs(img).max())   # chained parity
+        img = g[f"step{i}_x_prev"]                       # re-anchor: per-step parity
+        scale = float(T.betas[idx]) / sigma ** 2
+        nxt, norm, dbg = oracle_guided_step(O, model, T, img, idx, y, lambda a: O.phase_forward(a, pad), None,
+                                            g[f"randn_{i}"], "norm_sq", scale,
+                                            nonlinear_vjp=lambda x0, u: O.phase_vjp(x0, u, pad))
+        assert np.abs(dbg["x0"] - g[f"step{i}_x0"]).max() == 0.0                               # bit-exact
+        assert np.abs(norm - g[f"step{i}_dist"]).max() / norm.max() <= 2e-6
+        assert np.abs(nxt - g[f"step{i}_x_t_out"]).max() <= 1e-4 * max(1.0, np.abs(nxt).max()), idx
+        img = nxt
+    assert np.abs(img - g["final"]).max() <= 1e-4 * max(1.0, np.abs(g["final"]).max())
+    assert np.abs(norm - g["final_dist"]).max() / norm.max() <= 2e-6
