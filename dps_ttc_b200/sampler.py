@@ -613,6 +613,7 @@ class TTC_DDIM(DDIM):
         sem_weight = kwargs.get("semantic_weight", 0.0)  # config 5: semantic term in the reweighting
         callback = kwargs.get("callback")
         graph_model = bool(kwargs.get("graph_model", False))
+        anneal_kw = any(k_ in kwargs for k_ in ("anneal_amp", "anneal_scale", "anneal_loc"))
         distance = None
         self.last_stats = {"ancestors": {}}
         for idx in self._step_indices(kwargs):
@@ -623,7 +624,10 @@ class TTC_DDIM(DDIM):
             if fused:
                 # the reference's TTC loop hands the conditioning function neither beta_scale nor t (:672-676), so
                 # ps_anneal runs with its constructor scale and ps_semantic with t = 1 — as the generic path below does
-                spec = method.guidance()
+                # (extension: the annealing-schedule kwargs of the base loop, when given, scale the guidance here too)
+                spec = method.guidance(anneal=anneal_factor(idx / self.num_timesteps, kwargs.get("anneal_amp", 1.0),
+                                                            kwargs.get("anneal_scale", 10.0), kwargs.get("anneal_loc", 0.5))) \
+                    if anneal_kw else method.guidance()
                 z, q_noise = self._draws(idx, img, y, k, need_q=spec.project)
                 noisy = kernels.q_sample(y, q_noise, k.sqrt_acp, k.sqrt_1macp) if spec.project else None
                 # sharded resampling step: the update kernel writes x_{t-1} straight into the symmetric buffer the

@@ -31,6 +31,15 @@ def _worker(rank, world, port, out_dir):
     u = shared_uniforms(123, 10, N, "cpu").numpy()
     ids = torch.from_numpy(O.ancestors_multinomial(cdf, u, deg))
     new_img, new_d = sh.exchange(img, d, ids)
+    # the samplers' form: ONE all-gather of (log-weight, distance) pairs, distances handed to exchange()
+    both = sh.all_gather_scalars(torch.stack((logw, d), dim=1))
+    new_img2, new_d2 = sh.exchange(img, d, ids, dist_all=both[:, 1])
+    assert torch.equal(new_img2, new_img) and torch.equal(new_d2, new_d) and torch.equal(both[:, 0], logw_all)
+    # NCCL/gloo all_to_all_single of exactly the needed particles
+    sh_a2a = ParticleShards(n_local, transport="all_to_all")
+    img_a2a, d_a2a = sh_a2a.exchange(img, d, ids)
+    assert sh_a2a.transport == "all_to_all" and torch.equal(img_a2a, new_img) and torch.equal(d_a2a, new_d)
+    assert sh_a2a.bytes_exchanged <= sh.bytes_exchanged
     best = sh.greedy_broadcast(img, d)
     torch.save({"ids": ids, "img": new_img, "d": new_d, "best": best, "logw_all": logw_all},
                os.path.join(out_dir, f"rank{rank}.pt"))

@@ -4,9 +4,10 @@
 
 1. ttc_ddim + ps (Gaussian deblur, 64×64, N = 4 per rank, CPU-bridged stand-in model): the sharded run must
    reproduce the unsharded N-particle run — ancestor indices bit-identical on every rank and at every resampling
-   step, particles equal — for both transports (NCCL all-gather + gather kernel, and the fused P2P gather kernel).
+   step, particles equal — for every transport (fused P2P exchange kernel with in-kernel rendezvous; P2P gather between
+   symmetric-memory barriers; NCCL all-gather + gather kernel; NCCL all_to_all_single).
 2. search_ddpm greedy broadcast, same comparison.
-3. Timing of the particle exchange at 256×256, 8 particles per rank: all-gather + gather vs fused P2P gather."""
+3. Timing of the particle exchange at 256×256, 8 particles per rank, per transport."""
 from __future__ import annotations
 
 import os
@@ -22,7 +23,7 @@ sys.path.insert(0, os.path.join(REPO, "tests"))
 
 from helpers import CpuBridge, TinyEps  # noqa: E402
 from dps_ttc_b200 import kernels  # noqa: E402
-from dps_ttc_b200.dist import ParticleShards, shared_uniforms  # noqa: E402
+from dps_ttc_b200.dist import TRANSPORTS, ParticleShards, shared_uniforms  # noqa: E402
 from dps_ttc_b200.registry import get_conditioning_method, get_noise, get_operator  # noqa: E402
 from dps_ttc_b200.sampler import NoiseTape, create_sampler  # noqa: E402
 
@@ -62,8 +63,8 @@ def main():
 
     for sampler_name in ("ttc_ddim", "search_ddpm"):
         full_img, full_d, s_full = run(sampler_name, None, 0, N)          # unsharded, every rank computes it
-        for p2p in (False, True):
-            shards = ParticleShards(n_local, p2p=p2p)
+        for transport in TRANSPORTS:
+            shards = ParticleShards(n_local, transport=transport)
             img, d, s = run(sampler_name, shards, shards.offset, shards.offset + n_local)
             want = full_img[shards.offset:shards.offset + n_local]
             err = float((img - want).abs().max())
@@ -83,8 +84,8 @@ def main():
     x = torch.randn(n_local, 3, 256, 256, device=dev)
     d = torch.rand(n_local, device=dev)
     ids = torch.randint(0, n_local * world, (n_local * world,), generator=torch.Generator().manual_seed(3)).to(dev)
-    for p2p in (False, True):
-        sh = ParticleShards(n_local, p2p=p2p)
+    for transport in TRANSPORTS:
+        sh = ParticleShards(n_local, transport=transport)
         for _ in range(3):
             sh.exchange(x, d, ids)
         torch.cuda.synchronize(); dist.barrier()
@@ -99,7 +100,7 @@ def main():
         good = torch.equal(out, ref)
         ok &= good
         if rank == 0:
-            print(f"exchange of {n_local} particles/rank (256x256) transport={sh.transport:9s}: {float(t) * 1e3:8.1f} us  "
+            print(f"exchange of {n_local} particles/rank (256x256) transport={sh.transport:11s}: {float(t) * 1e3:8.1f} us  "
                   f"bit-equal to all-gather reference: {good}", flush=True)
     flag = torch.tensor([int(ok)], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
