@@ -241,6 +241,28 @@ def phase_vjp(x, g_out, pad):
     return np.real(back)[..., pad:pad + H, pad:pad + W].astype(f32)
 
 
+# ---- projections (measurements.py:48-54, :90-91, :167-168; condition_methods.py:72-82 `projection`) ---------------
+def ortho_project(x, forward, transpose=lambda u: u):
+    """LinearOperator.ortho_project: (I − AᵀA)x with the reference's `transpose` — the IDENTITY for the blur and
+    inpainting operators (measurements.py:115-116, :147-148, :164-165), nearest up-sampling for super-resolution."""
+    return (x - transpose(forward(x))).astype(f32)
+
+
+def project(x, measurement, forward, transpose=lambda u: u):
+    """LinearOperator.project: ortho_project(measurement) − A(x)."""
+    return (ortho_project(measurement, forward, transpose) - forward(x)).astype(f32)
+
+
+def nearest_upsample(u, s):
+    return np.repeat(np.repeat(u, s, axis=-2), s, axis=-1)   # F.interpolate(scale_factor=s), default mode 'nearest'
+
+
+def sr_project(x, measurement, scale_factor):
+    """SuperResolutionOperator.project (measurements.py:90-91): x − up(A x) + up(y)."""
+    ax = resize_forward(x, 1.0 / scale_factor)
+    return (x - nearest_upsample(ax, scale_factor) + nearest_upsample(measurement, scale_factor)).astype(f32)
+
+
 # ------------------------------------------------------------------------------------------------
 # guidance  (guided_diffusion/condition_methods.py:33-60, :101-106, :145-195, :206-212)
 # ------------------------------------------------------------------------------------------------

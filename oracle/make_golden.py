@@ -22,7 +22,7 @@ sys.path.insert(0, REPO)
 sys.path.insert(0, os.path.join(REPO, "tests"))
 
 from dps_ttc_b200 import _ref  # noqa: E402  (only for locating the reference + import stubs)
-from helpers import GOLDEN, TinyEps  # noqa: E402
+from helpers import GOLDEN, SemEmbedder, TinyEps, seeded_randn, seeded_unet, tensor_checksum  # noqa: E402
 
 _ref.ensure_reference()
 with _ref.quiet():
@@ -322,7 +322,172 @@ def gen_psnr():
     save("psnr_manual.npz", real=real.numpy(), fake=fake.numpy(), psnr=vals)
 
 
+class SeededDraws:
+    """Replaces torch.randn_like while active: the i-th call returns seeded_randn(base, i, shape) — a tape both the
+    reference run here and the GPU test can regenerate, so multi-MB noise tensors need not be committed."""
+
+    def __init__(self, base):
+        self.base, self.calls = base, 0
+
+    def __enter__(self):
+        self._orig = torch.randn_like
+
+        def randn_like(t, *a, **k):
+            out = seeded_randn(self.base, self.calls, t.shape).to(t.device, t.dtype)
+            self.calls += 1
+            return out
+        torch.randn_like = randn_like
+        return self
+
+    def __exit__(self, *exc):
+        torch.randn_like = self._orig
+
+
+def gen_phase256():
+    """Phase retrieval at the size the CUDA kernels are built for (256² → 384²): operator output, ‖r‖, its gradient and a
+    2-step ps_anneal trace from the REFERENCE; inputs are regenerated from seeds (checksums stored), outputs stored."""
+    g = torch.Generator().manual_seed(2560)
+    x = torch.rand(1, 3, 256, 256, generator=g) * 2 - 1
+    y = torch.rand(1, 3, 384, 384, generator=g) * 1.5           # any non-negative array is a valid |FFT| measurement here
+    with _ref.quiet():
+        op = get_operator("phase_retrieval", oversample=2.0, device="cpu")
+        noiser = get_noise("gaussian", sigma=0.05)
+        cond = get_conditioning_method("ps_anneal", op, noiser, scale=1.0)
+    with torch.no_grad():
+        ax = op.forward(x)
+    norm, grad = norm_grad(op, x, y)
+    out = {"x_sum": tensor_checksum(x), "y_sum": tensor_checksum(y), "Ax_sub": ax[..., ::3, ::3], "norm": norm, "grad": grad}
+    # trace: DDPM.p_sample + PosterorSamplingAnnealing.conditioning, respacing "2", one particle, upstream-arity loop
+    s = sampler("ddpm", "2")
+    model = TinyEps(seed=25)
+    x_start = seeded_randn(2600, 0, (1, 3, 256, 256))
+    img = x_start.clone()
+    with SeededDraws(2700) as draws, _ref.quiet():
+        for i, idx in enumerate(reversed(range(s.num_timesteps))):
+            img = img.requires_grad_()
+            o = s.p_sample(x=img, t=torch.tensor([idx]), model=model)
+            res = cond.conditioning(x_t=o["sample"], measurement=y, x_prev=img, x_0_hat=o["pred_xstart"],
+                                    beta_scale=s.betas[idx], anneal=1.0)
+            img = res[0].detach()
+            out[f"step{i}_dist"] = res[1].detach()
+            if i == 0:
+                out["step0_x_t_out_sub"] = img[..., ::2, ::2].clone()
+    out["final"], out["n_draws"] = img, np.array(draws.calls)
+    save("phase256.npz", **out)
+
+
+def gen_project():
+    """§8f row 2: LinearOperator.ortho_project / project (measurements.py:48-54), the SR and inpainting overrides (:90-91,
+    :167-168) and the `projection` conditioning method (condition_methods.py:72-82) from the reference's classes.
+    (NonLinearOperator.project adds data and measurement, which have different shapes for phase retrieval: unusable at HEAD.)"""
+    g = torch.Generator().manual_seed(4321)
+    x = torch.rand(2, 3, 64, 64, generator=g) * 2 - 1
+    out = {"x": x}
+    with _ref.quiet():
+        ops = {"gaussian_blur": (get_operator("gaussian_blur", kernel_size=61, intensity=3.0, device="cpu"), {}),
+               "super_resolution": (get_operator("super_resolution", in_shape=(1, 3, 64, 64), scale_factor=4, device="cpu"), {})}
+        np.random.seed(8)
+        ops["motion_blur"] = (get_operator("motion_blur", kernel_size=61, intensity=0.5, device="cpu"), {})
+        out["motion_kernel"] = ops["motion_blur"][0].kernel.kernelMatrix
+        np.random.seed(8)
+        mask = mask_generator("box", mask_len_range=(16, 17), image_size=64)(x[:1])[:, 0].unsqueeze(0)
+        out["mask"] = mask
+        ops["inpainting"] = (get_operator("inpainting", device="cpu"), {"mask": mask})
+        noiser = get_noise("gaussian", sigma=0.05)
+    for name, (op, kw) in ops.items():
+        with torch.no_grad():
+            m = op.forward(torch.rand(1, 3, 64, 64, generator=g) * 2 - 1, **kw)
+            m = m + 0.05 * torch.randn(m.shape, generator=g)
+            out[f"{name}_measurement"] = m
+            out[f"{name}_ortho"] = op.ortho_project(x, **kw)
+            out[f"{name}_project"] = op.project(x, m, **kw)
+            if not kw:   # Projection.conditioning forwards no kwargs (no mask)
+                with _ref.quiet():
+                    cond = get_conditioning_method("projection", op, noiser)
+                out[f"{name}_projection_cond"] = cond.conditioning(x_t=x.clone(), noisy_measurement=m)
+    save("project.npz", **out)
+
+
+def gen_semantic_on():
+    """ps_semantic WITH the semantic term inside the reference's base loop (condition_methods.py:145-195): the
+    embedder / guidance embeddings are injected as attributes of the reference's own object (its constructor would load
+    facenet, which is external) — nothing else of the reference is touched.  anneal_factor ≠ 1 exercises s_t(t)."""
+    torch.manual_seed(23)
+    np.random.seed(23)
+    model = TinyEps(seed=23)
+    emb = SemEmbedder(seed=9)
+    guid = torch.randn(1, 2, 16, generator=torch.Generator().manual_seed(1))
+    with _ref.quiet():
+        op = get_operator("gaussian_blur", kernel_size=61, intensity=3.0, device="cpu")
+        noiser = get_noise("gaussian", sigma=0.05)
+        cond = get_conditioning_method("ps_semantic", op, noiser, scale=0.3, sem_guid_scale=0.5, anneal_factor=2.0)
+    cond.resnet, cond.guid_image_emb, cond.n_guid_images = emb, guid, guid.shape[1]
+    s = sampler("ddpm", "4")
+    x_true = torch.rand(1, 3, 32, 32) * 2 - 1
+    y = noiser(op.forward(x_true)).detach()
+    x_start = torch.randn(3, 3, 32, 32)
+    steps = []
+
+    def cond_fn(**k):
+        res = cond.conditioning(**k)
+        steps.append({"x_prev": k["x_prev"].detach().clone(), "grad": res[0].detach().clone(), "dist": res[1].detach().clone(),
+                      "sem": res[2].detach().clone()})
+        return res
+    with Recorder() as rec, _ref.quiet():
+        final, md, sd = s.p_sample_loop(model=model, x_start=x_start.clone(), measurement=y, measurement_cond_fn=cond_fn,
+                                        record=False, save_root=None)
+    out = {"x_start": x_start, "y": y, "final": final.detach(), "final_dist": md.detach(), "final_sem": sd.detach(),
+           "guid": guid, "n_steps": np.array(s.num_timesteps)}
+    for i, r in enumerate(rec.randn):
+        out[f"randn_{i}"] = r
+    for i, st in enumerate(steps):
+        for k2, v in st.items():
+            out[f"step{i}_{k2}"] = v
+    save("trace_ddpm_ps_semantic_on_gblur.npz", **out)
+
+
+def gen_full_chain():
+    """BASELINE config 1 end to end: Gaussian deblur, FFHQ-256 UNet (seeded random weights), ONE image, the full 50-step
+    respaced chain through the reference's own p_sample_loop on the CPU.  Noise draws come from a seeded tape
+    (regenerated by the test); stored: the final reconstruction, the per-step distances and a few sub-sampled states."""
+    torch.set_num_threads(os.cpu_count() or 4)
+    model = seeded_unet("model_config.yaml", seed=1234, device="cpu")
+    with _ref.quiet():
+        op = get_operator("gaussian_blur", kernel_size=61, intensity=3.0, device="cpu")
+        noiser = get_noise("gaussian", sigma=0.05)
+        cond = get_conditioning_method("ps_semantic", op, noiser, scale=0.3, sem_guid_scale=0.0)   # = ps at HEAD (App. B)
+    g = torch.Generator().manual_seed(501)
+    x_true = torch.rand(1, 3, 256, 256, generator=g) * 2 - 1
+    y = (op.forward(x_true) + 0.05 * torch.randn(1, 3, 256, 256, generator=g)).detach()
+    x_start = seeded_randn(5100, 0, (1, 3, 256, 256))
+    s = sampler("ddpm", "50")
+    dists, states = [], {}
+
+    def cond_fn(**k):
+        res = cond.conditioning(**k)
+        dists.append(float(res[1]))
+        n = len(dists)
+        if n in (1, 10, 25, 40):
+            states[n] = k["x_prev"].detach()[..., ::4, ::4].clone()
+        return res
+    with SeededDraws(5200) as draws, _ref.quiet():
+        final, md, _ = s.p_sample_loop(model=model, x_start=x_start.clone(), measurement=y, measurement_cond_fn=cond_fn,
+                                       record=False, save_root=None)
+    out = {"y": y, "final": final.detach(), "dists": np.array(dists, np.float32), "n_draws": np.array(draws.calls),
+           "x_start_sum": tensor_checksum(x_start), "weights_sum": tensor_checksum(torch.cat([p.detach().reshape(-1)[:4096]
+                                                                                            for p in model.parameters()])),
+           "eps_probe": model(x_start, torch.tensor([999.0])).detach()[..., ::8, ::8]}
+    for n, v in states.items():
+        out[f"x_prev_at_call{n}_sub"] = v
+    save("full_chain_c1.npz", **out)
+
+
 if __name__ == "__main__":
+    only = sys.argv[1:]
+    if only:                     # e.g. `python oracle/make_golden.py gen_phase256 gen_full_chain`
+        for fn_name in only:
+            globals()[fn_name]()
+        sys.exit(0)
     gen_psnr()
     gen_var_types()
     gen_mean_types()

@@ -33,6 +33,47 @@ class TinyEps(torch.nn.Module):
         return self.c2(h) * gain
 
 
+class SemEmbedder(torch.nn.Module):
+    """Seeded stand-in for the face-embedding network of ps_semantic (the reference's is facenet_pytorch's
+    InceptionResnetV1 with downloaded weights: external).  (N,3,H,W) → (N,16).  Shared by
+    oracle/make_golden.py (injected into the REFERENCE's PosteriorSamplingSemanticGuid) and the tests."""
+
+    def __init__(self, seed=9):
+        super().__init__()
+        g = torch.Generator().manual_seed(seed)
+        self.c = torch.nn.Conv2d(3, 4, 5, stride=4)
+        self.l = torch.nn.Linear(4, 16)
+        with torch.no_grad():
+            for p in self.parameters():
+                p.copy_(torch.randn(p.shape, generator=g) * 0.3)
+
+    def forward(self, x):
+        return self.l(torch.tanh(self.c(x)).mean(dim=(2, 3)))
+
+
+def seeded_randn(base, i, shape):
+    """The i-th normal draw of a reproducible tape (regenerated from seeds on both sides instead of being stored)."""
+    return torch.randn(tuple(shape), generator=torch.Generator().manual_seed(int(base) + int(i)))
+
+
+def seeded_unet(config="model_config.yaml", seed=1234, device="cpu"):
+    """The reference's UNet with reproducible random weights: torch's global generator is seeded before the module's
+    default init, then the zero-initialised output convs are re-drawn under `seed` (dps_ttc_b200._ref.create_unet)."""
+    from dps_ttc_b200 import _ref
+    state = torch.get_rng_state()
+    torch.manual_seed(seed)
+    try:
+        return _ref.create_unet(config, reinit_zero_seed=seed, device=device)
+    finally:
+        torch.set_rng_state(state)
+
+
+def tensor_checksum(t):
+    """(float64 sum, float64 sum of squares) — detects a drifted RNG / weight init between fixture and test."""
+    t = torch.as_tensor(t).double()
+    return np.array([float(t.sum()), float((t * t).sum())])
+
+
 def golden(name):
     path = os.path.join(GOLDEN, name)
     return np.load(path, allow_pickle=False)

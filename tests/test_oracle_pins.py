@@ -241,3 +241,76 @@ def test_trace_ddpm_ps_anneal_phase_retrieval():
         img = nxt
     assert np.abs(img - g["final"]).max() <= 1e-4 * max(1.0, np.abs(g["final"]).max())
     assert np.abs(norm - g["final_dist"]).max() / norm.max() <= 2e-6
+
+
+def test_phase256_oracle_vs_reference():
+    """The oracle's phase operator and VJP at 256² → 384² (the size the CUDA kernels are built for) against the reference
+    (fixture inputs are regenerated from seeds; checksums guard the RNG)."""
+    from helpers import tensor_checksum
+    g = golden("phase256.npz")
+    gen = torch.Generator().manual_seed(2560)
+    x = torch.rand(1, 3, 256, 256, generator=gen) * 2 - 1
+    y = torch.rand(1, 3, 384, 384, generator=gen) * 1.5
+    assert np.allclose(tensor_checksum(x), g["x_sum"], rtol=1e-12) and np.allclose(tensor_checksum(y), g["y_sum"], rtol=1e-12)
+    x, y = x.numpy(), y.numpy()
+    amp = O.phase_forward(x, 64)
+    assert np.abs(amp[..., ::3, ::3] - g["Ax_sub"]).max() <= 2e-5
+    r = y - amp
+    norm, _ = O.particle_norms(r)
+    assert np.abs(norm - g["norm"]).max() / g["norm"].max() <= 1e-5      # the reference's norm is fp32 over a complex64 FFT
+    grad = -O.phase_vjp(x, r / norm[:, None, None, None], 64)
+    assert np.abs(grad - g["grad"]).max() <= 2e-5 * max(1.0, np.abs(g["grad"]).max())
+
+
+@pytest.mark.parametrize("name", ["gaussian_blur", "motion_blur", "super_resolution", "inpainting"])
+def test_projection_restatements_vs_reference(name):
+    """§8f row 2: ortho_project / project / `projection` conditioning of the reference's classes (fixture: gen_project)."""
+    g = golden("project.npz")
+    x, m = g["x"], g[f"{name}_measurement"]
+    if name == "super_resolution":
+        fwd = lambda a: O.resize_forward(a, 0.25)  # noqa: E731
+        ortho = O.ortho_project(x, fwd, lambda u: O.nearest_upsample(u, 4))
+        proj = O.sr_project(x, m, 4)
+    else:
+        if name == "inpainting":
+            fwd = lambda a: O.inpaint_forward(a, g["mask"])  # noqa: E731
+        else:
+            from dps_ttc_b200.tables import gaussian_kernel
+            kern = (gaussian_kernel(61, 3.0) if name == "gaussian_blur" else g["motion_kernel"]).astype(np.float32)
+            fwd = lambda a: O.blur_forward(a, kern)  # noqa: E731
+        ortho = O.ortho_project(x, fwd)
+        proj = O.project(x, m, fwd)
+    assert np.abs(ortho - g[f"{name}_ortho"]).max() <= 2e-6
+    assert np.abs(proj - g[f"{name}_project"]).max() <= 2e-6
+    if f"{name}_projection_cond" in g.files:
+        assert np.abs(proj - g[f"{name}_projection_cond"]).max() <= 2e-6     # Projection.conditioning = operator.project
+
+
+def test_trace_ps_semantic_on_oracle():
+    """ps_semantic with the semantic term on: the oracle's cotangent with the embedder's gradient as `extra`
+    (g_pre = mask ⊙ (−ζ/‖r‖·Aᵀr + s_t·∂ℓ_sem/∂x̂₀)) against the reference's recorded gradient, step by step."""
+    import math
+    from helpers import SemEmbedder
+    from dps_ttc_b200.tables import gaussian_kernel
+    g = golden("trace_ddpm_ps_semantic_on_gblur.npz")
+    T = O.Tables(1000, "4")
+    model, emb = TinyEps(seed=23), SemEmbedder(seed=9)
+    guid = torch.from_numpy(g["guid"])
+    kern = gaussian_kernel(61, 3.0).astype(np.float32)
+    y = g["y"]
+    for i, idx in enumerate(reversed(range(4))):
+        k = T.at(idx)
+        img = g[f"step{i}_x_prev"]
+        out6, vjp = model_and_vjp(model, img, k["model_t"])
+        x0, pre = O.x0_from_eps(img, out6[:, :3], k)
+        t = idx / 4
+        s_t = 0.5 * (1 + (2.0 - 1) / (1 + math.exp(-10 * (0.3 - t))))            # condition_methods.py:155
+        x0t = torch.from_numpy(x0).requires_grad_(True)
+        d = torch.norm((emb(x0t).unsqueeze(1) - guid).reshape(x0.shape[0], -1), dim=-1) / guid.shape[1]
+        (extra,) = torch.autograd.grad((s_t * d).sum(), x0t)
+        assert np.abs(d.detach().numpy() - g[f"step{i}_sem"]).max() <= 1e-5
+        r = y - O.blur_forward(x0, kern)
+        gpre, norm = O.guidance_cotangent(r, lambda u: O.blur_adjoint(u, kern), pre, "norm", 0.3, extra=extra.numpy())
+        grad = k["c1"] * gpre - k["c2"] * vjp(gpre)
+        assert np.abs(norm - g[f"step{i}_dist"]).max() / norm.max() <= 1e-6
+        assert np.abs(grad - g[f"step{i}_grad"]).max() <= 1e-5 * max(1.0, np.abs(g[f"step{i}_grad"]).max())

@@ -228,21 +228,24 @@ def _():
             report(f"cdf n={n} linear={linear}", np.abs(N(cdf) - cdf_ref).max(), 2e-7)
             ids_sys = kernels.ancestors(cdf, T(u[:1]), n, systematic=True, degenerate=deg)
             report(f"ancestors systematic n={n} linear={linear}", float(np.abs(N(ids_sys) - O.ancestors_systematic(N(cdf), u[0], n)).max()), 0.0)
-    # bit-exactness against torch.multinomial (CPU) given identical weights and uniforms
+    # against torch.multinomial (CPU) given identical distances and uniforms: CUDA expf vs torch's CPU exp agree to an ulp,
+    # so an ancestor may differ only when a uniform falls into an ulp-wide gap of the CDF — at most 1 of 40 trials
     import torch as th
-    for trial in range(20):
+    mism = 0
+    for trial in range(40):
         n = (4, 8, 64, 256)[trial % 4]
         g = th.Generator().manual_seed(trial)
-        w = th.exp(-(th.rand(n, generator=g) * 40 + 60) / 100)
+        d = th.rand(n, generator=g) * 40 + 60
+        w = th.exp(-d / 100)
         th.manual_seed(1000 + trial)
         ids_t = th.multinomial(w, n, replacement=True).numpy()
         th.manual_seed(1000 + trial)
         u = th.rand(n, dtype=th.float64)
-        _, cdf, _, deg = kernels.weights_cdf(th.log(w).to(dev), linear_mode=True)
-        # weights via exp(log w) may differ by an ulp from w: use the linear weights path directly too
+        logw = kernels.particle_logweights(d.to(dev), tau=0.01)
+        _, cdf, _, deg = kernels.weights_cdf(logw, linear_mode=True)
         ids = kernels.ancestors(cdf, u.to(dev), n, degenerate=deg)
-        results.append(True)
-        print(f"INFO  multinomial vs torch trial {trial} n={n}: equal={np.array_equal(N(ids), ids_t)}")
+        mism += int(not np.array_equal(N(ids), ids_t))
+    report("multinomial vs torch.multinomial (CPU): trials with a differing ancestor (<= 1 of 40)", float(max(0, mism - 1)), 0.0)
     # degenerate weights → identity
     w, cdf, lse, deg = kernels.weights_cdf(T(np.full(16, -1.0, np.float32)), linear_mode=True)
     ids = kernels.ancestors(cdf, T(rng.random(16)), 16, degenerate=deg)
