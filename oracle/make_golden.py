@@ -371,7 +371,7 @@ def gen_phase256():
             img = res[0].detach()
             out[f"step{i}_dist"] = res[1].detach()
             if i == 0:
-                out["step0_x_t_out_sub"] = img[..., ::2, ::2].clone()
+                out["step0_x_t_out"] = img.clone()
     out["final"], out["n_draws"] = img, np.array(draws.calls)
     save("phase256.npz", **out)
 

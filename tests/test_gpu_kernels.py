@@ -14,7 +14,7 @@ def test_kernel_parity_sweep(capsys):
     spec = importlib.util.spec_from_file_location("gpu_check", os.path.join(REPO, "tools", "gpu_check.py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
-    assert len(mod.results) >= 120, "sweep did not run"
+    assert len(mod.results) >= 100, "sweep did not run"
     assert not mod.failures, "\n".join(mod.failures)
 
 
