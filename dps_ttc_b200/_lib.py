@@ -36,11 +36,17 @@ class StepConstsC(C.Structure):
                 ("noise_on", C.c_int32), ("var_mode", C.c_int32), ("mean_mode", C.c_int32)]
 
 
+class UpdateExt(C.Structure):
+    _fields_ = [("partials", C.c_void_p), ("P", C.c_int32), ("coef_mode", C.c_int32), ("scale", C.c_float),
+                ("use_philox", C.c_int32), ("l2_out", C.c_void_p), ("philox_seed", C.c_uint64), ("philox_step", C.c_uint64),
+                ("particle_offset", C.c_int64)]
+
+
 class OperatorInfo(C.Structure):
     _fields_ = [("kind", C.c_int32), ("C", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
                 ("out_C", C.c_int32), ("out_H", C.c_int32), ("out_W", C.c_int32),
                 ("partials_per_particle", C.c_int32), ("aux_floats_per_particle", C.c_int64),
-                ("taps", C.c_int32), ("pad_", C.c_int32)]
+                ("taps", C.c_int32), ("guidance_partials", C.c_int32)]
 
 
 _P = C.c_void_p
@@ -58,6 +64,10 @@ SIGNATURES = {
                                        _I, _L, _P]),
     "dps_posterior_update_ddim": (_I, [C.POINTER(Source), _P, _P, _L, _P, C.POINTER(StepConstsC), _P, _P, _P, _I, _L,
                                        _P]),
+    "dps_posterior_update_ddpm_ext": (_I, [C.POINTER(Source), _P, _L, _P, _P, _L, _P, C.POINTER(StepConstsC),
+                                           C.POINTER(UpdateExt), _P, _I, _L, _P]),
+    "dps_posterior_update_ddim_ext": (_I, [C.POINTER(Source), _P, _P, _L, _P, C.POINTER(StepConstsC), C.POINTER(UpdateExt), _P,
+                                           _I, _L, _P]),
     "dps_guidance_grad": (_I, [_P, _L, _P, _F, _F, _P, _I, _L, _P]),
     "dps_apply_gradient": (_I, [_P, _P, _L, _P, _I, _L, _P]),
     "dps_q_sample": (_I, [_P, _P, _F, _F, _P, _L, _P]),
@@ -70,6 +80,7 @@ SIGNATURES = {
     "dps_operator_get_info": (_I, [_P, C.POINTER(OperatorInfo)]),
     "dps_operator_forward": (_I, [_P, C.POINTER(Source), _P, _L, _P, _P, _P, _I, _P]),
     "dps_operator_adjoint": (_I, [_P, _P, _P, C.POINTER(Source), _P, _L, _P, _L, _P, _I, _P]),
+    "dps_operator_guidance": (_I, [_P, C.POINTER(Source), _P, _L, _P, _P, _L, _P, _P, _I, _P]),
     "dps_particle_norms": (_I, [_P, _I, _I, _P, _P, _P]),
     "dps_guidance_coef": (_I, [_P, _I, _I, _I, _F, _P, _P, _P]),
     "dps_particle_logweights": (_I, [_P, _P, _I, _F, _F, _I, _F, _I, _P, _P]),

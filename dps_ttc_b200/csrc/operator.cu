@@ -136,6 +136,7 @@ void dps_operator_destroy(dps_operator* op) {
   sep_destroy(op);
   sparse_destroy(op);
   resize_destroy(op);
+  resize_fused_destroy(op);
   phase_destroy(op);
   if (cur != op->device) cudaSetDevice(cur);
   delete op;
@@ -149,7 +150,7 @@ int dps_operator_get_info(const dps_operator* op, dps_operator_info* info) {
   info->partials_per_particle = op->P;
   info->aux_floats_per_particle = op->aux_floats;
   info->taps = op->taps;
-  info->pad_ = 0;
+  info->guidance_partials = op->guidance_P;
   return DPS_OK;
 }
 
@@ -183,6 +184,23 @@ int dps_operator_forward(const dps_operator* op, const dps_source* src, const fl
   }
   dps_set_error("dps_operator_forward: unknown operator kind %d", op->kind);
   return DPS_ERR_INVALID;
+}
+
+int dps_operator_guidance(const dps_operator* op, const dps_source* src, const float* y, int64_t y_stride, float* r_out,
+                          float* g, int64_t g_stride, float* partials, float* aux, int n, dps_stream_t stream) {
+  DPS_REQUIRE(op && src && src->x && g, DPS_ERR_INVALID, "dps_operator_guidance: null operator/source/output");
+  DPS_REQUIRE(n > 0 && n <= 65535, DPS_ERR_INVALID, "dps_operator_guidance: bad particle count %d", n);
+  if (int rc = check_device(op, "dps_operator_guidance")) return rc;
+  if (op->guidance_P > 0) {
+    DPS_REQUIRE(dps_aligned16(src->x) && dps_aligned16(src->eps) && dps_aligned16(y) && dps_aligned16(g) && dps_aligned16(r_out) &&
+                    src->x_stride % 4 == 0 && (!src->eps || src->eps_stride % 4 == 0) && y_stride % 4 == 0 && g_stride % 4 == 0,
+                DPS_ERR_ALIGN, "dps_operator_guidance: tensors must be 16-byte aligned, strides multiples of 4");
+    if (op->kind == DPS_OP_RESIZE) return resize_fused_guidance(op, *src, y, y_stride, r_out, g, g_stride, partials, n, (cudaStream_t)stream);
+  }
+  // no fused kernel for this operator / shape: the residual kernel, then the adjoint kernel without a coefficient
+  DPS_REQUIRE(r_out, DPS_ERR_INVALID, "dps_operator_guidance: this operator has no fused kernel and needs the residual buffer r_out");
+  if (int rc = dps_operator_forward(op, src, y, y_stride, r_out, partials, aux, n, stream)) return rc;
+  return dps_operator_adjoint(op, r_out, nullptr, src->eps ? src : nullptr, nullptr, 0, g, g_stride, aux, n, stream);
 }
 
 int dps_operator_adjoint(const dps_operator* op, const float* r, const float* coef, const dps_source* mask_src,

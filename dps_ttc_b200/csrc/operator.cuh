@@ -6,6 +6,7 @@ struct SepTables;     // blur_separable.cu
 struct SparseTables;  // blur_sparse.cu
 struct ResizeTables;  // resize.cu
 struct PhaseTables;   // phase.cu
+struct ResizeFused;   // resize_fused.cu
 
 struct dps_operator {
   int kind = 0;
@@ -20,6 +21,8 @@ struct dps_operator {
   SparseTables* sparse = nullptr;
   ResizeTables* resize = nullptr;
   PhaseTables* phase = nullptr;
+  ResizeFused* rfused = nullptr;  // fused residual + cotangent kernel (resize_fused.cu), null when the shape is not covered
+  int guidance_P = 0;             // partial sums per particle written by the fused guidance kernel (0: none)
 };
 
 // Arguments common to every forward / adjoint launch (already validated by operator.cu).
@@ -125,6 +128,10 @@ int resize_create(dps_operator* op, const int32_t* fov_h, const float* w_h, int 
 void resize_destroy(dps_operator* op);
 int resize_forward(const dps_operator* op, const FwdArgs& a, cudaStream_t st);
 int resize_adjoint(const dps_operator* op, const AdjArgs& a, cudaStream_t st);
+
+void resize_fused_destroy(dps_operator* op);
+int resize_fused_guidance(const dps_operator* op, const dps_source& src, const float* y, int64_t y_stride, float* r_out, float* g,
+                          int64_t g_stride, float* partials, int n, cudaStream_t st);
 
 int phase_create(dps_operator* op, int pad);
 void phase_destroy(dps_operator* op);

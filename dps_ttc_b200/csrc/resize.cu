@@ -74,6 +74,8 @@ struct AdjCols {
   float* wtt = nullptr;   // (kt, W) tap-major: A_w[jstart[m] + k][m]
 };
 
+int resize_fused_create(dps_operator* op, const std::vector<double>& Ah, const std::vector<double>& Aw, int out_h, int out_w);
+
 struct ResizeTables {
   FwdTables f;
   FwdStream fs;
@@ -1299,7 +1301,7 @@ int resize_create(dps_operator* op, const int32_t* fov_h, const float* w_h, int 
   op->oW = out_w;
   op->P = op->C * f.fstrips;
   op->taps = taps_h;
-  return DPS_OK;
+  return resize_fused_create(op, Ah, Aw, out_h, out_w);   // fused residual + cotangent kernel where the shape allows
 }
 
 void resize_destroy(dps_operator* op) {

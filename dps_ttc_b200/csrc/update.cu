@@ -37,7 +37,38 @@ struct UpdateArgs {
   float c1, c2;
   int clip;
   dps_step_consts k;
+  dps_update_ext ext;  // used by the kExt instantiations only
 };
+
+// ---- Philox4x32-10 (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3"; the Random123 constants) + Box–Muller ----
+DPS_DEV uint4 philox4x32_10(uint4 c, uint2 key) {
+  constexpr unsigned M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const unsigned hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
+    const unsigned hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
+    c = make_uint4(hi1 ^ c.y ^ key.x, lo1, hi0 ^ c.w ^ key.y, lo0);
+    key.x += W0;
+    key.y += W1;
+  }
+  return c;
+}
+DPS_DEV float u01(unsigned r) { return fmaf((float)r, 2.3283064365386963e-10f, 1.1641532182693481e-10f); }  // (r + ½)·2⁻³² ∈ (0,1)
+DPS_DEV float4 philox_normal4(int64_t i4, int64_t particle, const dps_update_ext& e) {
+  const uint4 r = philox4x32_10(make_uint4((unsigned)i4, (unsigned)((uint64_t)i4 >> 32), (unsigned)particle, (unsigned)e.philox_step),
+                                make_uint2((unsigned)e.philox_seed, (unsigned)(e.philox_seed >> 32)));
+  float4 z;
+  float s, c;
+  const float m0 = sqrtf(-2.0f * logf(u01(r.x)));
+  sincospif(2.0f * u01(r.y), &s, &c);
+  z.x = m0 * c;
+  z.y = m0 * s;
+  const float m1 = sqrtf(-2.0f * logf(u01(r.z)));
+  sincospif(2.0f * u01(r.w), &s, &c);
+  z.z = m1 * c;
+  z.w = m1 * s;
+  return z;
+}
 
 DPS_DEV float ddpm_sample(float x, float e, float x0, float v, float z, const dps_step_consts& k) {
   // μ = p1·x̂₀ + p2·x                                       posterior_mean_variance.py:110-118
@@ -72,9 +103,10 @@ DPS_DEV float ddim_sample(float x, float x0, float z, float c1, float c2, const 
     body(x) body(y) body(z) body(w) \
   }
 
-template <bool kDdim>
+template <bool kDdim, bool kExt>
 __global__ void __launch_bounds__(kThreads) posterior_update_kernel(const UpdateArgs a) {
   const int n = blockIdx.y;
+  __shared__ float s_coef;
   const int64_t base4 = (int64_t)blockIdx.x * (kThreads * kVecPerThread) + threadIdx.x;
   const float* x = a.x + n * a.x_stride;
   const float* eps = a.eps + n * a.eps_stride;
@@ -99,6 +131,31 @@ __global__ void __launch_bounds__(kThreads) posterior_update_kernel(const Update
     vg[u] = (ok && g) ? ldg_stream4(g + i4 * 4) : zero4;
     vj[u] = (ok && vjp) ? ldg_stream4(vjp + i4 * 4) : zero4;
   }
+  float coef = 1.0f;
+  if constexpr (kExt) {
+    if (a.ext.partials) {
+      // while the loads are in flight: ‖r_n‖ from the residual kernel's partial sums — the reduction order of
+      // particle_norms_kernel (lane-strided fp64 sums, xor-shuffle tree), so the value is bit-identical to it
+      if (threadIdx.x < 32) {
+        const float* p = a.ext.partials + (int64_t)n * a.ext.P * 2;
+        double sq = 0.0;
+        for (int i = threadIdx.x; i < a.ext.P; i += 32) sq += (double)p[2 * i];
+        sq = warp_sum(sq);
+        if (threadIdx.x == 0) {
+          const float nrm = (float)sqrt(sq);
+          s_coef = a.ext.coef_mode == DPS_COEF_NORM ? (nrm > 0.f ? -a.ext.scale / nrm : 0.f) : -2.0f * a.ext.scale;
+          if (a.ext.l2_out && blockIdx.x == 0) a.ext.l2_out[n] = nrm;
+        }
+      }
+      __syncthreads();
+      coef = s_coef;
+    }
+    if (a.ext.use_philox && !z && a.k.noise_on) {
+#pragma unroll
+      for (int u = 0; u < kVecPerThread; ++u)
+        vz[u] = philox_normal4(base4 + (int64_t)u * kThreads, a.ext.particle_offset + n, a.ext);
+    }
+  }
 #pragma unroll
   for (int u = 0; u < kVecPerThread; ++u) {
     const int64_t i4 = base4 + (int64_t)u * kThreads;
@@ -113,7 +170,7 @@ __global__ void __launch_bounds__(kThreads) posterior_update_kernel(const Update
     const float grad = __fsub_rn(__fmul_rn(a.c1, vg[u].c), __fmul_rn(a.c2, vj[u].c)); \
     x0v.c = x0;                                                                       \
     sv.c = s;                                                                         \
-    nv.c = g ? __fsub_rn(s, grad) : s;                                                \
+    nv.c = g ? __fsub_rn(s, (kExt && a.ext.partials) ? __fmul_rn(coef, grad) : grad) : s; \
   }
     DPS_FOR4(DPS_ELEM)
 #undef DPS_ELEM
@@ -180,7 +237,7 @@ template <bool kDdim>
 int launch_update(const dps_source* src, const float* v, int64_t v_stride, const float* z,
                   const float* g, int64_t g_stride, const float* vjp, const dps_step_consts* k,
                   float* x_next, float* sample_out, float* x0_out, int n, int64_t chw,
-                  dps_stream_t stream, const char* who) {
+                  dps_stream_t stream, const char* who, const dps_update_ext* ext = nullptr) {
   if (int rc = check_source(src, who)) return rc;
   DPS_REQUIRE(src->eps, DPS_ERR_INVALID, "%s: eps is required", who);
   DPS_REQUIRE(k && x_next, DPS_ERR_INVALID, "%s: null consts/output", who);
@@ -191,13 +248,19 @@ int launch_update(const dps_source* src, const float* v, int64_t v_stride, const
                   dps_aligned16(vjp) && dps_aligned16(sample_out) && dps_aligned16(x0_out) &&
                   v_stride % 4 == 0 && g_stride % 4 == 0,
               DPS_ERR_ALIGN, "%s: tensors must be 16-byte aligned", who);
+  const bool device_noise = ext && ext->use_philox;
+  if (ext && ext->partials) {
+    DPS_REQUIRE(ext->P > 0 && (ext->coef_mode == DPS_COEF_NORM || ext->coef_mode == DPS_COEF_NORM_SQ), DPS_ERR_INVALID,
+                "%s: deferred coefficient needs P > 0 and coef_mode NORM or NORM_SQ", who);
+    DPS_REQUIRE(g, DPS_ERR_INVALID, "%s: deferred coefficient without a cotangent g", who);
+  }
   if (!kDdim) {
     DPS_REQUIRE(k->var_mode >= 0 && k->var_mode <= 2, DPS_ERR_INVALID, "%s: bad var_mode", who);
     DPS_REQUIRE(v || k->var_mode == 1 || !k->noise_on, DPS_ERR_INVALID,
                 "%s: variance channels required", who);
-    DPS_REQUIRE(z || !k->noise_on, DPS_ERR_INVALID, "%s: noise z required when noise_on", who);
+    DPS_REQUIRE(z || device_noise || !k->noise_on, DPS_ERR_INVALID, "%s: noise z required when noise_on", who);
   } else {
-    DPS_REQUIRE(z || !k->noise_on || k->ddim_sigma == 0.0f, DPS_ERR_INVALID,
+    DPS_REQUIRE(z || device_noise || !k->noise_on || k->ddim_sigma == 0.0f, DPS_ERR_INVALID,
                 "%s: noise z required when sigma != 0", who);
   }
   UpdateArgs a;
@@ -219,9 +282,13 @@ int launch_update(const dps_source* src, const float* v, int64_t v_stride, const
   a.c2 = src->c2;
   a.clip = src->clip;
   a.k = *k;
+  a.ext = ext ? *ext : dps_update_ext{};
   const int per_block = kThreads * kVecPerThread;
   dim3 grid((unsigned)((a.chw4 + per_block - 1) / per_block), (unsigned)n);
-  posterior_update_kernel<kDdim><<<grid, kThreads, 0, (cudaStream_t)stream>>>(a);
+  if (ext)
+    posterior_update_kernel<kDdim, true><<<grid, kThreads, 0, (cudaStream_t)stream>>>(a);
+  else
+    posterior_update_kernel<kDdim, false><<<grid, kThreads, 0, (cudaStream_t)stream>>>(a);
   DPS_LAUNCH_CHECK(who);
   return DPS_OK;
 }
@@ -352,6 +419,22 @@ int dps_posterior_update_ddim(const dps_source* src, const float* z, const float
                               dps_stream_t stream) {
   return launch_update<true>(src, nullptr, 0, z, g, g_stride, vjp, k, x_next, sample_out, x0_out, n,
                              chw, stream, "dps_posterior_update_ddim");
+}
+
+int dps_posterior_update_ddpm_ext(const dps_source* src, const float* v, int64_t v_stride, const float* z, const float* g,
+                                  int64_t g_stride, const float* vjp, const dps_step_consts* k, const dps_update_ext* ext,
+                                  float* x_next, int n, int64_t chw, dps_stream_t stream) {
+  DPS_REQUIRE(ext, DPS_ERR_INVALID, "dps_posterior_update_ddpm_ext: null ext");
+  return launch_update<false>(src, v, v_stride, z, g, g_stride, vjp, k, x_next, nullptr, nullptr, n, chw, stream,
+                              "dps_posterior_update_ddpm_ext", ext);
+}
+
+int dps_posterior_update_ddim_ext(const dps_source* src, const float* z, const float* g, int64_t g_stride, const float* vjp,
+                                  const dps_step_consts* k, const dps_update_ext* ext, float* x_next, int n, int64_t chw,
+                                  dps_stream_t stream) {
+  DPS_REQUIRE(ext, DPS_ERR_INVALID, "dps_posterior_update_ddim_ext: null ext");
+  return launch_update<true>(src, nullptr, 0, z, g, g_stride, vjp, k, x_next, nullptr, nullptr, n, chw, stream,
+                             "dps_posterior_update_ddim_ext", ext);
 }
 
 int dps_particle_sqdiff(const float* a, int64_t a_stride, const float* ref, int64_t ref_stride, int n_particles,

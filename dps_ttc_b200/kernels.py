@@ -66,10 +66,17 @@ def x0_from_eps(x, eps, k, clip=True, out=None):
 
 
 def posterior_update(sampler: str, x, eps, v, z, k, *, clip=True, g=None, vjp=None, var_mode=0, max_log=None,
-                     want_sample=False, want_x0=False, out=None):
+                     want_sample=False, want_x0=False, out=None, deferred=None, philox=None):
     """Fused x̂₀ / posterior mean / log-variance / σ·z / guidance step.  Returns (x_next, sample, x0);
     the last two are None unless requested.  `g` may be a channel-slice view (e.g. of an (N,6,H,W)
-    cotangent buffer)."""
+    cotangent buffer).
+    deferred=(partials, coef_mode, scale[, l2_out]): g and vjp are UNSCALED (g = mask ⊙ Aᵀr); the kernel derives the
+    per-particle coefficient from the residual kernel's partial sums (and writes ‖r‖ to l2_out) — see dps_update_ext.
+    philox=(seed, step, particle_offset): with z=None the noise is generated in the kernel (Philox4x32-10 + Box–Muller)."""
+    if deferred is not None or philox is not None:
+        if want_sample or want_x0:
+            raise DpsError("the extended update writes x_next only")
+        return _posterior_update_ext(sampler, x, eps, v, z, k, clip, g, vjp, var_mode, max_log, out, deferred, philox), None, None
     n, chw = x.shape[0], _chw(x)
     src = make_source(x, eps, k.c1, k.c2, clip)
     kc = make_consts(k, var_mode, max_log)
@@ -96,6 +103,47 @@ def posterior_update(sampler: str, x, eps, v, z, k, *, clip=True, g=None, vjp=No
     if tok:
         TIMER.stop(tok)
     return x_next, sample, x0
+
+
+def _posterior_update_ext(sampler, x, eps, v, z, k, clip, g, vjp, var_mode, max_log, out, deferred, philox):
+    n, chw = x.shape[0], _chw(x)
+    src = make_source(x, eps, k.c1, k.c2, clip)
+    kc = make_consts(k, var_mode, max_log)
+    dev = x.device
+    x_next = torch.empty(x.shape, device=dev, dtype=torch.float32) if out is None else out
+    ext = _lib.UpdateExt()
+    keep = []
+    if deferred is not None:
+        partials, mode, scale = deferred[:3]
+        l2_out = deferred[3] if len(deferred) > 3 else None
+        require_cuda_f32(partials, "partials")
+        if partials.shape[0] != n or partials.shape[-1] != 2 or not partials.is_contiguous():
+            raise DpsError(f"partials must be a contiguous (N, P, 2) tensor, got {tuple(partials.shape)}")
+        ext.partials, ext.P, ext.coef_mode, ext.scale = partials.data_ptr(), partials.shape[1], int(mode), float(scale)
+        ext.l2_out = ptr(l2_out)
+        keep.append(partials)
+    if philox is not None:
+        seed, step, offset = philox
+        ext.use_philox, ext.philox_seed, ext.philox_step, ext.particle_offset = 1, int(seed) & (2**64 - 1), int(step), int(offset)
+    gp, gs = (None, 0) if g is None else particle_view(g, "g")
+    if vjp is not None:
+        vjp = _lib.dense(vjp, "vjp")
+    if z is not None:
+        z = _lib.dense(z, "z")
+    tok = TIMER.start(f"posterior_update_{sampler}") if TIMER else None
+    if sampler == "ddpm":
+        vp, vs = (None, 0) if v is None else particle_view(v, "v")
+        rc = lib().dps_posterior_update_ddpm_ext(C.byref(src), vp, vs, ptr(z), gp, gs, ptr(vjp), C.byref(kc), C.byref(ext),
+                                                 x_next.data_ptr(), n, chw, stream_ptr(dev))
+    elif sampler == "ddim":
+        rc = lib().dps_posterior_update_ddim_ext(C.byref(src), ptr(z), gp, gs, ptr(vjp), C.byref(kc), C.byref(ext),
+                                                 x_next.data_ptr(), n, chw, stream_ptr(dev))
+    else:
+        raise DpsError(f"unknown sampler kind {sampler!r}")
+    check(rc, f"dps_posterior_update_{sampler}_ext")
+    if tok:
+        TIMER.stop(tok)
+    return x_next
 
 
 def guidance_grad(g, vjp, k, out=None):
@@ -151,6 +199,7 @@ class OperatorPlan:
         self.partials_per_particle = info.partials_per_particle
         self.aux_floats = info.aux_floats_per_particle
         self.taps = info.taps
+        self.guidance_partials = info.guidance_partials      # > 0: dps_operator_guidance is ONE fused kernel
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
@@ -239,6 +288,39 @@ class OperatorPlan:
         if tok:
             TIMER.stop(tok)
         return out, partials, aux
+
+    def guidance(self, x, eps, k, clip, y, out, aux=None, want_r=False):
+        """The operator part of a guided step with the per-particle coefficient DEFERRED to the update kernel:
+        out ← 1[|pre| ≤ 1] ⊙ Aᵀ(y − A x̂₀) (unscaled), returns (partials, r or None, aux).  One fused cluster kernel where
+        the plan has one (`guidance_partials` > 0: r stays on chip unless want_r), else forward + adjoint launches."""
+        self._check_in(x, "x")
+        if eps is None or k is None:
+            raise DpsError("guidance(): x̂₀ is formed from x and ε — pass eps and the step constants")
+        n = x.shape[0]
+        src = make_source(x, eps, k.c1, k.c2, clip)
+        require_cuda_f32(y, "y")
+        if tuple(y.shape[-3:]) != self.out_shape:
+            raise DpsError(f"measurement shape {tuple(y.shape)} does not match operator output {self.out_shape}")
+        y = _lib.dense(y.reshape((-1,) + self.out_shape), "y")
+        if y.shape[0] not in (1, n):
+            raise DpsError(f"measurement batch {y.shape[0]} must be 1 or {n}")
+        ys = 0 if y.shape[0] == 1 else y[0].numel()
+        fused = self.guidance_partials > 0
+        P = self.guidance_partials if fused else self.partials_per_particle
+        partials = torch.empty((n, P, 2), device=x.device, dtype=torch.float32)
+        r = None
+        if want_r or not fused:
+            r = torch.empty((n,) + self.out_shape, device=x.device, dtype=torch.float32)
+        if self.aux_floats and aux is None:
+            aux = self.new_aux(n)
+        gp, gs = particle_view(out, "g")
+        tok = TIMER.start(f"{self.kind}_guidance" if fused else f"{self.kind}_forward+adjoint") if TIMER else None
+        with _on(self.device):
+            check(lib().dps_operator_guidance(self._h, C.byref(src), y.data_ptr(), ys, ptr(r), gp, gs, partials.data_ptr(),
+                                              ptr(aux), n, stream_ptr(x.device)), f"dps_operator_guidance[{self.kind}]")
+        if tok:
+            TIMER.stop(tok)
+        return partials, r, aux
 
     def adjoint(self, r, coef=None, mask_x=None, mask_eps=None, k=None, clip=True, extra=None, out=None, aux=None):
         """g = 1[−1 ≤ c1·x − c2·ε ≤ 1] ⊙ (coef_n·Aᵀr + extra); mask only when mask_x/mask_eps given.

@@ -108,6 +108,11 @@ class B200Operator:
         """(r = y − A(x̂₀), partials, aux); x̂₀ = clamp(c1·x − c2·ε) on the fly (x̂₀ = x when eps is None)."""
         return self.plan_for(x, **kwargs).forward(x, eps, k, clip, y, want_partials, aux, out)
 
+    def guidance(self, x, eps, k, clip, y, out, want_r=False, **kwargs):
+        """(partials, r or None, aux) with out ← clamp-mask ⊙ Aᵀ(y − A x̂₀), UNSCALED: the per-particle coefficient is applied
+        by the posterior-update kernel (kernels.posterior_update(deferred=…)).  One fused kernel where the plan has one."""
+        return self.plan_for(x, **kwargs).guidance(x, eps, k, clip, y, out, want_r=want_r)
+
     def cotangent(self, r, coef, x, eps=None, k=None, clip=True, extra=None, out=None, aux=None, **kwargs):
         """clamp-mask ⊙ (coef_n·Aᵀ r + extra) — the cotangent w.r.t. the pre-clamp x̂₀ (App. A.4)."""
         if x is None:

@@ -24,7 +24,7 @@ import functools
 import torch
 
 from . import diffstategrad, kernels
-from ._lib import DPS_COEF_GLOBAL_NORM, DpsError
+from ._lib import DPS_COEF_GLOBAL_NORM, DPS_COEF_NORM, DPS_COEF_NORM_SQ, DpsError
 from .conditioning import ConditioningMethod, GuidanceSpec
 from .graphed import GraphedEps
 from .operators import B200Operator
@@ -58,6 +58,34 @@ class TorchNoise:
     def uniforms(self, idx, n, device):
         # torch.multinomial on CPU consumes n fp64 uniforms of the global CPU generator (pinned in tests)
         return torch.rand(n, dtype=torch.float64).to(device, non_blocking=True)
+
+
+class PhiloxNoise:
+    """Throughput mode: σ·z is generated INSIDE the posterior-update kernel from the counter-based Philox4x32-10 generator
+    keyed by (seed, step, global particle index, element) — no z tensor is written or read (7T → 6T bytes for the DDPM
+    update) and a sharded run draws the same noise as an unsharded one.  It does not reproduce torch's RNG stream: parity
+    runs use TorchNoise or a NoiseTape.  Draws that are not the update's own z (q_sample, resampling uniforms) come from
+    torch generators seeded with the same seed."""
+
+    def __init__(self, seed=0):
+        self.seed = int(seed)
+        self._gen = {}
+
+    def _g(self, device):
+        key = str(device)
+        if key not in self._gen:
+            self._gen[key] = torch.Generator(device).manual_seed(self.seed)
+        return self._gen[key]
+
+    def z(self, idx, like):
+        return None                      # made in the kernel
+
+    def q(self, idx, like):
+        return torch.randn(like.shape, device=like.device, dtype=like.dtype, generator=self._g(like.device))
+
+    def uniforms(self, idx, n, device):
+        g = torch.Generator().manual_seed((self.seed * 1_000_003 + int(idx)) & 0x7FFFFFFFFFFF)
+        return torch.rand(n, dtype=torch.float64, generator=g).to(device, non_blocking=True)
 
 
 class NoiseTape:
@@ -332,7 +360,7 @@ class SpacedSampler:
         return max(1, int(free * (1.0 - reserve)) // per)
 
     def guided_step(self, model, x, idx, measurement, method, spec: GuidanceSpec, cond_kwargs, noisy_measurement=None,
-                    z=None, dsg=False, graph_model=False, inv_abs_mean=None, out=None):
+                    z=None, dsg=False, graph_model=False, inv_abs_mean=None, out=None, particle_offset=0):
         """One reverse step with measurement guidance.  Returns (x_next, meas_dist (N,), sem_dist or None).
         `dsg`: DiffStateGrad projection step (gaussian_diffusion.py:240-255) — the gradient is materialised,
         projected onto the sample's leading singular subspaces and applied to every particle.
@@ -347,7 +375,7 @@ class SpacedSampler:
                 raise DpsError("unet_chunk: DiffStateGrad steps and the Poisson likelihood couple the particles of a step; "
                                "run them with unet_chunk=None")
             return self._guided_pass(model, x, idx, measurement, method, spec, cond_kwargs, noisy_measurement, z, dsg,
-                                     graph_model, inv_abs_mean, out)
+                                     graph_model, inv_abs_mean, out, particle_offset)
         if z is None and self._needs_z(self._consts(idx)):
             z = self.noise.z(idx, x)                         # one draw for the whole batch: the RNG stream does not see the slicing
         x_next = torch.empty_like(x) if out is None else out
@@ -356,15 +384,27 @@ class SpacedSampler:
             sl = slice(a, a + chunk)
             _, d, sd = self._guided_pass(model, x[sl], idx, measurement, method, spec, cond_kwargs,
                                          None if noisy_measurement is None else noisy_measurement, None if z is None else z[sl],
-                                         False, graph_model, inv_abs_mean, x_next[sl])
+                                         False, graph_model, inv_abs_mean, x_next[sl], particle_offset + a)
             dists.append(d)
             sems.append(sd)
         dist = torch.cat(dists)
         sem = None if sems[0] is None else torch.cat([t.reshape(-1) for t in sems])
         return x_next, dist, sem
 
+    # The per-particle factor of the guidance gradient (−ζ/‖r‖ or −2ζ) commutes with Aᵀ, the clamp mask and the UNet VJP,
+    # so by default it is applied by the update kernel (dps_update_ext) to the UNSCALED cotangent: the coefficient launch
+    # disappears and operators with a fused residual+cotangent kernel (super-resolution) run ONE launch before the VJP.
+    # False restores the round-1 sequence residual → coefficient → cotangent (A/B aid; also taken whenever a step needs the
+    # scaled cotangent itself: semantic term, Poisson likelihood, DiffStateGrad).
+    deferred_coef = True
+
+    def _philox(self, k, particle_offset, idx):
+        if isinstance(self.noise, PhiloxNoise) and self._needs_z(k):
+            return (self.noise.seed, idx, particle_offset)
+        return None
+
     def _guided_pass(self, model, x, idx, measurement, method, spec, cond_kwargs, noisy_measurement, z, dsg, graph_model,
-                     inv_abs_mean, out):
+                     inv_abs_mean, out, particle_offset=0):
         k = self._consts(idx)
         op = method.operator
         gm = self._graphed(model, x) if graph_model else None
@@ -383,33 +423,43 @@ class SpacedSampler:
         eps_d = out_d[:, :C] if out_d.shape[1] == 2 * C else out_d
         v_d = out_d[:, C:] if out_d.shape[1] == 2 * C else None
         clip = self.clip_denoised
-        # kernel 1: residual + partial sums, x̂₀ formed on the fly
-        r, partials, aux = op.residual(xd, eps_d, k, clip, measurement, **cond_kwargs)
-        # kernel 2: ‖r‖ and the per-particle coefficient
-        if getattr(method.noiser, "__name__", "gaussian") == "poisson" and spec.kind != "ps_semantic":
-            # Poisson branch of grad_and_value (condition_methods.py:50-55): loss = ‖r‖_F(all particles)·mean(1/|y|);
-            # norm_exp is ignored there, so ps_anneal's ζ_t multiplies the same gradient
-            inv = self._inv_abs_mean(measurement) if inv_abs_mean is None else inv_abs_mean
-            l2, coef = kernels.guidance_coef(partials, DPS_COEF_GLOBAL_NORM, spec.scale * inv)
-            dist = torch.linalg.norm(l2) * inv            # the scalar the reference returns as `norm`
-        else:
-            dist, coef = kernels.guidance_coef(partials, spec.coef_mode, spec.scale)
-        # optional semantic term: gradient w.r.t. x̂₀ of s_t·ℓ_sem (external embedder stays PyTorch)
-        extra, sem_dist = None, None
-        if spec.semantic is not None:
-            x0 = kernels.x0_from_eps(xd, eps_d, k, clip).requires_grad_(True)
-            with torch.enable_grad():
-                sem_loss, sem_dist = spec.semantic(x0)
-                extra = torch.autograd.grad(sem_loss.sum(), x0)[0].contiguous()
-            sem_dist = sem_dist.detach()
-        # kernel 3: cotangent w.r.t. the pre-clamp x̂₀ written into the ε-channels of the cotangent buffer
         two_c = mo.shape[1] == 2 * C
         if gm is not None:
             g = gm.cotangent[:, :C] if two_c else gm.cotangent
         else:
             g6, g3 = self._buffers(xd)
             g = g6[:, :C] if two_c else g3
-        op.cotangent(r, coef, xd, eps_d, k, clip, extra, out=g, aux=aux, **cond_kwargs)
+        poisson = getattr(method.noiser, "__name__", "gaussian") == "poisson" and spec.kind != "ps_semantic"
+        deferred = None
+        extra, sem_dist = None, None
+        if self.deferred_coef and not dsg and not poisson and spec.semantic is None \
+                and spec.coef_mode in (DPS_COEF_NORM, DPS_COEF_NORM_SQ):
+            # kernels 1-3 as ONE call: residual, partial sums and the unscaled masked cotangent (fused where the operator
+            # has such a kernel); the coefficient is applied by the update kernel below
+            partials, _, aux = op.guidance(xd, eps_d, k, clip, measurement, out=g, **cond_kwargs)
+            dist = torch.empty((x.shape[0],), device=x.device, dtype=torch.float32)
+            deferred = (partials, spec.coef_mode, spec.scale, dist)
+        else:
+            # kernel 1: residual + partial sums, x̂₀ formed on the fly
+            r, partials, aux = op.residual(xd, eps_d, k, clip, measurement, **cond_kwargs)
+            # kernel 2: ‖r‖ and the per-particle coefficient
+            if poisson:
+                # Poisson branch of grad_and_value (condition_methods.py:50-55): loss = ‖r‖_F(all particles)·mean(1/|y|);
+                # norm_exp is ignored there, so ps_anneal's ζ_t multiplies the same gradient
+                inv = self._inv_abs_mean(measurement) if inv_abs_mean is None else inv_abs_mean
+                l2, coef = kernels.guidance_coef(partials, DPS_COEF_GLOBAL_NORM, spec.scale * inv)
+                dist = torch.linalg.norm(l2) * inv            # the scalar the reference returns as `norm`
+            else:
+                dist, coef = kernels.guidance_coef(partials, spec.coef_mode, spec.scale)
+            # optional semantic term: gradient w.r.t. x̂₀ of s_t·ℓ_sem (external embedder stays PyTorch)
+            if spec.semantic is not None:
+                x0 = kernels.x0_from_eps(xd, eps_d, k, clip).requires_grad_(True)
+                with torch.enable_grad():
+                    sem_loss, sem_dist = spec.semantic(x0)
+                    extra = torch.autograd.grad(sem_loss.sum(), x0)[0].contiguous()
+                sem_dist = sem_dist.detach()
+            # kernel 3: cotangent w.r.t. the pre-clamp x̂₀ written into the ε-channels of the cotangent buffer
+            op.cotangent(r, coef, xd, eps_d, k, clip, extra, out=g, aux=aux, **cond_kwargs)
         # UNet VJP
         vjp = None
         if gm is not None:
@@ -421,13 +471,15 @@ class SpacedSampler:
             z = self.noise.z(idx, xd)
         if dsg:
             sample, _, _ = kernels.posterior_update(self.kind, xd, eps_d, v_d, z, k, clip=clip,
-                                                    var_mode=self.var_mode, max_log=self._max_log(k))
+                                                    var_mode=self.var_mode, max_log=self._max_log(k),
+                                                    philox=self._philox(k, particle_offset, idx))
             x_next = diffstategrad.projected_update(sample, kernels.guidance_grad(g, vjp, k))
             if out is not None:
                 x_next = out.copy_(x_next)
         else:
             x_next, _, _ = kernels.posterior_update(self.kind, xd, eps_d, v_d, z, k, clip=clip, g=g,
-                                                    vjp=vjp, var_mode=self.var_mode, max_log=self._max_log(k), out=out)
+                                                    vjp=vjp, var_mode=self.var_mode, max_log=self._max_log(k), out=out,
+                                                    deferred=deferred, philox=self._philox(k, particle_offset, idx))
         if spec.project:  # mcg: x_t = operator.project(x_t, noisy_measurement)
             x_next = method.project(data=x_next, noisy_measurement=noisy_measurement, **cond_kwargs)
             if out is not None and x_next.data_ptr() != out.data_ptr():
@@ -455,7 +507,8 @@ class SpacedSampler:
             x_next = diffstategrad.projected_update(out["sample"].detach(), first.detach().contiguous())
         else:
             x_next = out["sample"] - first if returns_grad else first
-        return x_next.detach(), (dist.detach() if torch.is_tensor(dist) else dist), (third if returns_grad else None)
+        third = third.detach() if (returns_grad and torch.is_tensor(third)) else (third if returns_grad else None)
+        return x_next.detach(), (dist.detach() if torch.is_tensor(dist) else dist), third
 
     def _step_indices(self, kwargs):
         """All steps T−1 … 0 like the reference, or a window of the chain: `start_idx` (default T−1) and
@@ -583,7 +636,8 @@ class SearchDDPM(DDPM):
                     img = self._torch_sample(img, eps, v, self._process_xstart(k.c1 * img - k.c2 * eps), z, k)
                 else:
                     img, _, _ = kernels.posterior_update("ddpm", img, eps, v, z, k, clip=self.clip_denoised,
-                                                         var_mode=self.var_mode, max_log=self._max_log(k))
+                                                         var_mode=self.var_mode, max_log=self._max_log(k),
+                                                         philox=self._philox(k, 0 if shards is None else shards.offset, idx))
                 _, partials, _ = operator.residual(img, y=y, **bound)      # ‖y − A(x_{t−1})‖₂, :626-630
                 costs = kernels.particle_norms(partials)
                 if shards is None:
@@ -636,7 +690,8 @@ class TTC_DDIM(DDIM):
                 if tgt is not None and tgt.data_ptr() == img.data_ptr():
                     tgt = None
                 img, distance, sem_d = self.guided_step(model, img, idx, y, method, spec, bound, noisy, z,
-                                                        graph_model=graph_model, inv_abs_mean=self._loop_inv, out=tgt)
+                                                        graph_model=graph_model, inv_abs_mean=self._loop_inv, out=tgt,
+                                                        particle_offset=0 if shards is None else shards.offset)
             else:
                 img, distance, _ = self._generic_step(model, img, idx, y, measurement_cond_fn, {})
             if resampling:

@@ -108,6 +108,39 @@ int dps_posterior_update_ddim(const dps_source* src, const float* z, const float
                               float* x_next, float* sample_out, float* x0_out, int n_particles,
                               int64_t chw, dps_stream_t stream);
 
+/* Extended form of the two updates (round 2).  Two independent options, selected by `ext`:
+ *  (1) DEFERRED GUIDANCE COEFFICIENT (ext->partials != NULL).  The per-particle factor of the guidance gradient
+ *      (∇‖r‖ = −Aᵀr/‖r‖, condition_methods.py:36-39; ∇‖r‖² = −2Aᵀr, :206-212) commutes with the adjoint operator, the
+ *      clamp mask and the UNet VJP, which are all linear in the cotangent.  So g and vjp may be computed from the UNSCALED
+ *      cotangent g = mask ⊙ Aᵀr (dps_operator_adjoint with coef = NULL, or dps_operator_guidance) and the factor applied
+ *      here:  coef_n = −scale/‖r_n‖ (DPS_COEF_NORM; 0 where ‖r_n‖ = 0) or −2·scale (DPS_COEF_NORM_SQ), with ‖r_n‖² the
+ *      fixed-order fp64 sum of the P partial sums the residual kernel wrote — the arithmetic of dps_guidance_coef, which
+ *      this replaces (one launch and one N-vector round trip less per step);  x' = s − coef_n·(c1·g − c2·vjp).
+ *      l2_out (nullable, N floats) receives ‖r_n‖.
+ *  (2) DEVICE NOISE (ext->use_philox != 0, z == NULL): z ~ N(0,1) is generated in the kernel from the counter-based
+ *      Philox4x32-10 generator — counter (element/4 lo, element/4 hi, particle_offset + n, step), key (seed lo, seed hi),
+ *      Box–Muller on the four outputs — so the z tensor is neither written nor read (7T → 6T for DDPM) and a sharded
+ *      run draws the same noise as an unsharded one.  Throughput mode: it does not reproduce torch's RNG stream; parity
+ *      runs pass z (recorded draws) instead.                                                                          */
+typedef struct dps_update_ext {
+  const float* partials;   /* (N, P, 2) or NULL */
+  int32_t P;
+  int32_t coef_mode;       /* DPS_COEF_NORM | DPS_COEF_NORM_SQ */
+  float scale;             /* ζ at this step (annealing folded in) */
+  int32_t use_philox;
+  float* l2_out;           /* nullable */
+  uint64_t philox_seed;
+  uint64_t philox_step;
+  int64_t particle_offset; /* global index of particle 0 of this launch */
+} dps_update_ext;
+int dps_posterior_update_ddpm_ext(const dps_source* src, const float* v, int64_t v_stride, const float* z,
+                                  const float* g, int64_t g_stride, const float* vjp, const dps_step_consts* k,
+                                  const dps_update_ext* ext, float* x_next, int n_particles, int64_t chw,
+                                  dps_stream_t stream);
+int dps_posterior_update_ddim_ext(const dps_source* src, const float* z, const float* g, int64_t g_stride,
+                                  const float* vjp, const dps_step_consts* k, const dps_update_ext* ext,
+                                  float* x_next, int n_particles, int64_t chw, dps_stream_t stream);
+
 /* DiffStateGrad hook (gaussian_diffusion.py:240-255, diffstategrad_utils.py:46-78): on a projection step the loop
  * needs the guidance gradient as a tensor, projects it (SVD of the sample: cuSOLVER/cuBLAS on the host side) and
  * applies the projected gradient — which has batch 1 upstream — to every particle.
@@ -167,7 +200,8 @@ typedef struct dps_operator_info {
   int32_t partials_per_particle;  /* P: residual-norm partial sums written per particle         */
   int64_t aux_floats_per_particle;/* workspace the forward pass leaves for the adjoint (phase)  */
   int32_t taps;                   /* blur: non-zero taps (sparse) or 1-D support (separable)    */
-  int32_t pad_;
+  int32_t guidance_partials;      /* > 0: dps_operator_guidance runs ONE fused kernel for this operator and writes this many
+                                     partial sums per particle; 0: it runs the forward and the adjoint kernel (P partials)   */
 } dps_operator_info;
 int dps_operator_get_info(const dps_operator* op, dps_operator_info* info);
 
@@ -180,6 +214,18 @@ int dps_operator_get_info(const dps_operator* op, dps_operator_info* info);
 int dps_operator_forward(const dps_operator* op, const dps_source* src, const float* y,
                          int64_t y_stride, float* out, float* partials, float* aux,
                          int n_particles, dps_stream_t stream);
+
+/* Residual AND unscaled cotangent in one call — the whole operator part of a guided step (condition_methods.py:33-39
+ * differentiated through A and the clamp):
+ *   r = y − A(x̂₀)   (kept on chip where a fused kernel exists; written to r_out if given),  partials: Σr², Σ|r| pieces,
+ *   g = 1[−1 ≤ pre ≤ 1] ⊙ Aᵀ r        — WITHOUT the per-particle factor −ζ/‖r‖ (or −2ζ): the caller applies it in the
+ *                                         posterior update (dps_update_ext), after the UNet VJP of g.
+ * Operators with guidance_partials > 0 (super-resolution ×4/×8 at 256²) run one thread-block-cluster kernel: x, ε read once,
+ * g written once, r never leaves shared memory (3T + M bytes instead of 5T + 2M and three launches).  The others run
+ * dps_operator_forward + dps_operator_adjoint(coef = NULL) and need r_out (and aux where the operator has one).            */
+int dps_operator_guidance(const dps_operator* op, const dps_source* src, const float* y, int64_t y_stride,
+                          float* r_out, float* g, int64_t g_stride, float* partials, float* aux,
+                          int n_particles, dps_stream_t stream);
 
 /* Adjoint / Jacobian-transpose, fused with the gradient scaling and the clamp backward
  * (SURVEY.md App. A.4):  g = 1[−1 ≤ c1·x−c2·ε ≤ 1] ⊙ (coef_n · Aᵀ r + extra)

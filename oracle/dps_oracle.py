@@ -293,6 +293,39 @@ def guided_update(sample, g_pre, vjp, k):
 
 
 # ------------------------------------------------------------------------------------------------
+# device noise of the throughput mode (no reference counterpart: the reference calls torch.randn_like, :472).  Restated
+# from the published algorithm: Philox4x32-10 (Salmon, Moraes, Dror, Shaw: "Parallel random numbers: as easy as 1, 2, 3",
+# SC'11; Random123 constants) and the Box–Muller transform, with the counter/key layout of include/dpsttc.h.
+# ------------------------------------------------------------------------------------------------
+def philox4x32_10(counter, key):
+    """counter: (n,4) uint32, key: (2,) uint32 → (n,4) uint32."""
+    M0, M1, W0, W1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), 0x9E3779B9, 0xBB67AE85
+    c = counter.astype(np.uint64)
+    k0, k1 = int(key[0]), int(key[1])
+    mask = np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0, p1 = M0 * c[:, 0], M1 * c[:, 2]
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & mask, p1 >> np.uint64(32), p1 & mask
+        c = np.stack([hi1 ^ c[:, 1] ^ np.uint64(k0), lo1, hi0 ^ c[:, 3] ^ np.uint64(k1), lo0], axis=1)
+        k0, k1 = (k0 + W0) & 0xFFFFFFFF, (k1 + W1) & 0xFFFFFFFF
+    return c.astype(np.uint32)
+
+
+def philox_normal(seed, step, particle, n_elems):
+    """The z of one particle (n_elems values, a multiple of 4): element group i4 ↦ Philox(counter = (i4 lo, i4 hi, particle,
+    step), key = (seed lo, seed hi)) → u = (r + ½)·2⁻³² → Box–Muller pairs (√(−2 ln u₀)·cos 2πu₁, ·sin 2πu₁, …)."""
+    i4 = np.arange(n_elems // 4, dtype=np.uint64)
+    ctr = np.stack([i4 & np.uint64(0xFFFFFFFF), i4 >> np.uint64(32), np.full_like(i4, particle & 0xFFFFFFFF),
+                    np.full_like(i4, step & 0xFFFFFFFF)], axis=1).astype(np.uint32)
+    r = philox4x32_10(ctr, np.array([seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF], dtype=np.uint32))
+    u = (r.astype(np.float32) * f32(2.3283064365386963e-10) + f32(1.1641532182693481e-10)).astype(np.float64)
+    m0, m1 = np.sqrt(-2.0 * np.log(u[:, 0])), np.sqrt(-2.0 * np.log(u[:, 2]))
+    z = np.stack([m0 * np.cos(2 * np.pi * u[:, 1]), m0 * np.sin(2 * np.pi * u[:, 1]),
+                  m1 * np.cos(2 * np.pi * u[:, 3]), m1 * np.sin(2 * np.pi * u[:, 3])], axis=1)
+    return z.reshape(-1).astype(f32)
+
+
+# ------------------------------------------------------------------------------------------------
 # reweighting / resampling  (gaussian_diffusion.py:537-552, :685-698; torch CPU multinomial kernel)
 # ------------------------------------------------------------------------------------------------
 def logweights(meas, sem=None, tau=0.01, meas_scale=1.0, meas_pow=1, sem_scale=0.0, sem_pow=1):

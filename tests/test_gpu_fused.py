@@ -1,0 +1,165 @@
+"""Round-2 kernels: the fused super-resolution guidance kernel (thread-block cluster, DSMEM halos), the posterior update
+with the deferred guidance coefficient, and the in-kernel Philox noise — against the oracle and against the two-kernel
+path they replace.  All through the C ABI."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import CpuBridge, TinyEps, oracle_guided_step, psnr
+from oracle import dps_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda:0")
+DIFF = dict(steps=1000, noise_schedule="linear", model_mean_type="epsilon", model_var_type="learned_range",
+            dynamic_threshold=False, clip_denoised=True, rescale_timesteps=True)
+
+
+@pytest.fixture(autouse=True)
+def _exact_fp32():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.deterministic = True
+    yield
+
+
+def _consts(idx):
+    from dps_ttc_b200.schedule import Schedule, named_beta_schedule
+    return Schedule(named_beta_schedule("linear", 1000)).consts(idx)
+
+
+@pytest.mark.parametrize("factor,n,idx,clip", [(4, 1, 999, True), (4, 5, 500, True), (8, 3, 999, True), (4, 2, 10, False)])
+def test_fused_sr_guidance_vs_two_kernels_and_oracle(factor, n, idx, clip):
+    from dps_ttc_b200 import kernels, tables
+    from dps_ttc_b200.kernels import OperatorPlan
+    (fh, wh), (fw, ww), _ = tables.resizer_tables((1, 3, 256, 256), 1.0 / factor)
+    plan = OperatorPlan.resize(fh, wh, fw, ww, 3, 256, 256, DEV)
+    assert plan.guidance_partials == 3 * 8
+    k = _consts(idx)
+    gen = torch.Generator(DEV).manual_seed(100 * factor + n)
+    x = torch.randn(n, 3, 256, 256, device=DEV, generator=gen) / k.c1
+    o6 = torch.randn(n, 6, 256, 256, device=DEV, generator=gen) * 0.3 / max(k.c2, 1e-3)
+    eps = o6[:, :3]
+    m = 256 // factor
+    y = torch.randn(1, 3, m, m, device=DEV, generator=gen)
+    # two-kernel path
+    r2, p2, _ = plan.forward(x, eps, k, clip, y, want_partials=True)
+    g2 = torch.zeros(n, 6, 256, 256, device=DEV)
+    plan.adjoint(r2, None, x, eps, k, clip, None, out=g2[:, :3])
+    # fused path (into a channel-slice view like the sampler's cotangent buffer)
+    g1 = torch.full((n, 6, 256, 256), float("nan"), device=DEV)
+    g1[:, 3:] = 0
+    p1, r1, _ = plan.guidance(x, eps, k, clip, y, out=g1[:, :3], want_r=True)
+    assert torch.isfinite(g1).all()
+    scale_r, scale_g = float(r2.abs().max()), float(g2.abs().max())
+    assert float((r1 - r2).abs().max()) <= 2e-6 * max(1.0, scale_r)
+    assert float((g1[:, :3] - g2[:, :3]).abs().max()) <= 5e-6 * max(1.0, scale_g)
+    n1, n2 = kernels.particle_norms(p1, want_l1=True), kernels.particle_norms(p2, want_l1=True)
+    assert float((n1[0] - n2[0]).abs().max()) <= 1e-5 * float(n2[0].max())
+    assert float((n1[1] - n2[1]).abs().max()) <= 1e-5 * float(n2[1].max())
+    # oracle
+    xn, en = x.cpu().numpy(), eps.cpu().numpy()
+    x0, pre = O.x0_from_eps(xn, en, dict(c1=np.float32(k.c1), c2=np.float32(k.c2)), clip)
+    r_ref = y.cpu().numpy() - O.resize_forward(x0, 1.0 / factor)
+    g_ref = O.resize_adjoint(r_ref, 1.0 / factor, 256, 256)
+    if clip:
+        g_ref = g_ref * ((pre >= -1) & (pre <= 1))
+    assert np.abs(r1.cpu().numpy() - r_ref).max() <= 5e-6 * max(1.0, np.abs(r_ref).max())
+    assert np.abs(g1[:, :3].cpu().numpy() - g_ref).max() <= 1e-5 * max(1.0, np.abs(g_ref).max())
+    # without r_out the residual never leaves the chip; same cotangent and partial sums, bit for bit
+    g3 = torch.zeros(n, 3, 256, 256, device=DEV)
+    p3, r3, _ = plan.guidance(x, eps, k, clip, y, out=g3)
+    assert r3 is None and torch.equal(g3, g1[:, :3]) and torch.equal(p3, p1)
+
+
+@pytest.mark.parametrize("sampler,mode", [("ddpm", 1), ("ddpm", 2), ("ddim", 1)])
+def test_update_with_deferred_coefficient_equals_scaled_path(sampler, mode):
+    from dps_ttc_b200 import kernels
+    k = _consts(700)
+    gen = torch.Generator(DEV).manual_seed(5)
+    n = 5
+    x = torch.randn(n, 3, 256, 256, device=DEV, generator=gen)
+    o6 = torch.randn(n, 6, 256, 256, device=DEV, generator=gen) * 0.3
+    z = torch.randn(n, 3, 256, 256, device=DEV, generator=gen)
+    g_un = torch.randn(n, 3, 256, 256, device=DEV, generator=gen)
+    vjp_un = torch.randn(n, 3, 256, 256, device=DEV, generator=gen) * 0.1
+    partials = torch.rand(n, 24, 2, device=DEV, generator=gen) * 50
+    scale = 0.37
+    l2, coef = kernels.guidance_coef(partials, mode, scale)
+    v = o6[:, 3:] if sampler == "ddpm" else None
+    want, _, _ = kernels.posterior_update(sampler, x, o6[:, :3], v, z, k, g=(g_un * coef.view(-1, 1, 1, 1)).contiguous(),
+                                          vjp=(vjp_un * coef.view(-1, 1, 1, 1)).contiguous())
+    dist = torch.empty(n, device=DEV)
+    got, _, _ = kernels.posterior_update(sampler, x, o6[:, :3], v, z, k, g=g_un, vjp=vjp_un, deferred=(partials, mode, scale, dist))
+    assert torch.equal(dist, l2)                                             # same reduction order as dps_guidance_coef
+    assert float((got - want).abs().max()) <= 2e-6 * max(1.0, float(want.abs().max()))
+    # a particle with r = 0 gets a zero coefficient (torch's norm backward at 0), not a NaN
+    partials[2] = 0
+    got, _, _ = kernels.posterior_update(sampler, x, o6[:, :3], v, z, k, g=g_un, vjp=vjp_un, deferred=(partials, 1, scale, dist))
+    plain, _, _ = kernels.posterior_update(sampler, x, o6[:, :3], v, z, k)
+    assert torch.equal(got[2], plain[2]) and float(dist[2]) == 0.0 and torch.isfinite(got).all()
+
+
+def test_philox_noise_in_the_update_kernel():
+    from dps_ttc_b200 import kernels
+    k = _consts(400)
+    gen = torch.Generator(DEV).manual_seed(9)
+    n = 4
+    x = torch.randn(n, 3, 256, 256, device=DEV, generator=gen)
+    o6 = torch.randn(n, 6, 256, 256, device=DEV, generator=gen) * 0.3
+    seed, step, offset = (1 << 40) + 12345, 400, 6
+    got, _, _ = kernels.posterior_update("ddpm", x, o6[:, :3], o6[:, 3:], None, k, philox=(seed, step, offset))
+    # the same update with the oracle's restatement of the generator as an explicit z tensor
+    z = np.stack([O.philox_normal(seed, step, offset + i, 3 * 256 * 256).reshape(3, 256, 256) for i in range(n)])
+    want, _, _ = kernels.posterior_update("ddpm", x, o6[:, :3], o6[:, 3:], torch.from_numpy(z).to(DEV), k)
+    assert float((got - want).abs().max()) <= 2e-5 * max(1.0, float(want.abs().max()))     # logf / sincospif vs libm
+    # sharded == unsharded: particles 2..3 of the launch above = a launch of two particles at offset + 2
+    part, _, _ = kernels.posterior_update("ddpm", x[2:], o6[2:, :3], o6[2:, 3:], None, k, philox=(seed, step, offset + 2))
+    assert torch.equal(part, got[2:])
+    # idx 0 adds no noise (gaussian_diffusion.py:473)
+    k0 = _consts(0)
+    a, _, _ = kernels.posterior_update("ddpm", x, o6[:, :3], o6[:, 3:], None, k0, philox=(seed, 0, 0))
+    b, _, _ = kernels.posterior_update("ddpm", x, o6[:, :3], o6[:, 3:], None, k0)
+    assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("op_name,op_cfg,method,params,mode,scale_of", [
+    ("super_resolution", dict(in_shape=(1, 3, 256, 256), scale_factor=4), "ps", dict(scale=0.01), "norm", lambda t, i: 0.01),
+    ("gaussian_blur", dict(kernel_size=61, intensity=3.0), "ps", dict(scale=0.3), "norm", lambda t, i: 0.3),
+    ("phase_retrieval", dict(oversample=2.0), "ps_anneal", dict(scale=1.0), "norm_sq", lambda t, i: t.at(i)["beta"] / 0.05 ** 2),
+])
+def test_deferred_step_vs_oracle_and_vs_round1_sequence(op_name, op_cfg, method, params, mode, scale_of):
+    """The guided step with the deferred coefficient (default) against the oracle (per step, 1e-4) and against the
+    residual → coefficient → cotangent sequence of round 1 (deferred_coef=False)."""
+    from dps_ttc_b200.registry import get_conditioning_method, get_noise, get_operator
+    from dps_ttc_b200.sampler import NoiseTape, create_sampler
+    from dps_ttc_b200.tables import gaussian_kernel
+    kern = gaussian_kernel(61, 3.0).astype(np.float32)
+    fwd = {"super_resolution": lambda a: O.resize_forward(a, 0.25), "gaussian_blur": lambda a: O.blur_forward(a, kern),
+           "phase_retrieval": lambda a: O.phase_forward(a, 64)}[op_name]
+    adj = {"super_resolution": lambda u: O.resize_adjoint(u, 0.25, 256, 256), "gaussian_blur": lambda u: O.blur_adjoint(u, kern),
+           "phase_retrieval": None}[op_name]
+    nl = (lambda x0, u: O.phase_vjp(x0, u, 64)) if op_name == "phase_retrieval" else None
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((2, 3, 256, 256)).astype(np.float32)
+    y = fwd((rng.random((1, 3, 256, 256)) * 2 - 1).astype(np.float32))
+    y = (y + 0.05 * rng.standard_normal(y.shape)).astype(np.float32)
+    z = rng.standard_normal(x.shape).astype(np.float32)
+    idx = 999
+    model_cpu = TinyEps(seed=3)
+    outs = {}
+    for deferred in (True, False):
+        op = get_operator(op_name, device=DEV, **op_cfg)
+        cond = get_conditioning_method(method, op, get_noise("gaussian", sigma=0.05), **params)
+        s = create_sampler(sampler="ddpm", **DIFF)
+        s.deferred_coef, s.parity_rng = deferred, False
+        s.noise = NoiseTape(z={idx: torch.from_numpy(z)})
+        img, dist, _ = s.p_sample_loop(model=CpuBridge(model_cpu), x_start=torch.from_numpy(x).to(DEV),
+                                       measurement=torch.from_numpy(y).to(DEV), measurement_cond_fn=cond.conditioning,
+                                       record=False, save_root=None, start_idx=idx, num_steps=1)
+        outs[deferred] = (img.cpu().numpy(), dist.cpu().numpy())
+    tab = O.Tables(1000)
+    ref, norm, _ = oracle_guided_step(O, model_cpu, tab, x, idx, y, fwd, adj, z, mode, scale_of(tab, idx), nonlinear_vjp=nl)
+    for deferred, (img, dist) in outs.items():
+        assert np.abs(img - ref).max() <= 1e-4 * max(1.0, np.abs(ref).max()), f"deferred={deferred}"
+        assert np.abs(dist - norm).max() <= 1e-5 * norm.max(), f"deferred={deferred}"
+    assert psnr(outs[True][0], outs[False][0]) >= 100.0

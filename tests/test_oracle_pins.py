@@ -314,3 +314,18 @@ def test_trace_ps_semantic_on_oracle():
         grad = k["c1"] * gpre - k["c2"] * vjp(gpre)
         assert np.abs(norm - g[f"step{i}_dist"]).max() / norm.max() <= 1e-6
         assert np.abs(grad - g[f"step{i}_grad"]).max() <= 1e-5 * max(1.0, np.abs(g[f"step{i}_grad"]).max())
+
+
+def test_philox_restatement_known_answers():
+    """The oracle's Philox4x32-10 (device noise of the throughput mode) against the published Random123 known-answer vectors
+    (kat_vectors: philox4x32 10 rounds)."""
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0), (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        got = O.philox4x32_10(np.array([ctr], dtype=np.uint32), np.array(key, dtype=np.uint32))[0]
+        assert tuple(int(v) for v in got) == want
+    z = O.philox_normal(7, 999, 3, 3 * 256 * 256)
+    assert abs(float(z.mean())) < 0.01 and abs(float(z.std()) - 1) < 0.01 and np.isfinite(z).all()
+    assert not np.array_equal(z, O.philox_normal(7, 998, 3, 3 * 256 * 256))       # keyed by step …
+    assert not np.array_equal(z, O.philox_normal(7, 999, 4, 3 * 256 * 256))       # … and by particle
