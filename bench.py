@@ -351,7 +351,7 @@ def run_reference(args, rank, world):
 
 
 # ------------------------------------------------------------------------------------------------
-def graph_durations(plan, sampler_kind, k, n, y, device, want_gather, reps=4):
+def graph_durations(plan, sampler_kind, k, n, y, device, want_gather, philox, reps=4):
     """µs per launch of the operator forward / adjoint, the posterior update (and the resampling gather) at N = n particles:
     `reps` passes over S rotating argument sets captured in ONE CUDA graph per kernel and replayed, CUDA events around
     the replays on the launching stream."""
@@ -372,12 +372,17 @@ def graph_durations(plan, sampler_kind, k, n, y, device, want_gather, reps=4):
     upd = f"posterior_update_{sampler_kind}"
     fns = {f"{plan.kind}_forward": lambda i: plan.forward(X[i], O6[i][:, :3], k, True, y, want_partials=True, aux=AUX[i], out=R[i]),
            f"{plan.kind}_adjoint": lambda i: plan.adjoint(R[i], coef, X[i], O6[i][:, :3], k, True, None, out=G6[i][:, :3], aux=AUX[i])}
+    PART = torch.rand(n, max(plan.guidance_partials, plan.partials_per_particle), 2, device=device) * 10
+    dfr = (PART, 1, 0.01, torch.empty(n, device=device))
     if sampler_kind == "ddpm":
-        fns[upd] = lambda i: kernels.posterior_update("ddpm", X[i], O6[i][:, :3], O6[i][:, 3:], Z[i], k, g=G6[i][:, :3],
-                                                      vjp=VJ[i], out=OUT[i])
+        fns[upd] = lambda i: kernels.posterior_update("ddpm", X[i], O6[i][:, :3], O6[i][:, 3:], None if philox else Z[i], k,
+                                                      g=G6[i][:, :3], vjp=VJ[i], out=OUT[i], deferred=dfr,
+                                                      philox=(1, 5, 0) if philox else None)
     else:
         fns[upd] = lambda i: kernels.posterior_update("ddim", X[i], O6[i][:, :3], None, None, k, g=G6[i][:, :3], vjp=VJ[i],
-                                                      out=OUT[i])
+                                                      out=OUT[i], deferred=dfr)
+    if plan.guidance_partials > 0:
+        fns[f"{plan.kind}_guidance"] = lambda i: plan.guidance(X[i], O6[i][:, :3], k, True, y, out=G6[i][:, :3])
     if want_gather:
         fns["gather_particles"] = lambda i: kernels.gather_particles(X[i], ids, out=OUT[i])
     out = {}
@@ -408,7 +413,7 @@ def run_b200(args, rank, world, local_rank):
     import torch.distributed as dist
     from dps_ttc_b200 import _lib, kernels
     from dps_ttc_b200.dist import ParticleShards, shared_uniforms
-    from dps_ttc_b200.sampler import NoiseTape, TorchNoise
+    from dps_ttc_b200.sampler import NoiseTape, PhiloxNoise, TorchNoise
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py --impl b200 needs a GPU: dps_ttc_b200 has no CPU fallback")
     device = torch.device(f"cuda:{local_rank}")
@@ -454,7 +459,9 @@ def run_b200(args, rank, world, local_rank):
         return res[0], res[1]
 
     # ---------------- device-resident throughput (`value`) ----------------
-    sampler.noise, sampler.parity_rng = TorchNoise(), False
+    # device-resident leg: the update kernel generates its own noise (Philox, keyed by seed/step/particle) — the throughput
+    # mode; the e2e leg below feeds recorded host noise through a NoiseTape instead
+    sampler.noise, sampler.parity_rng = PhiloxNoise(seed=1000 + rank), False
     shards = new_shards(timing=True)
     x_dev = x_start_h.to(device)
     img, _ = loop(sampler, x_dev, y_dev, 999, W, shards)       # warm-up steps (untimed)
@@ -540,7 +547,7 @@ def run_b200(args, rank, world, local_rank):
         if rank == 0 and wl["scaling"] == "weak":
             from dps_ttc_b200.sampler import create_sampler
             s1 = create_sampler(sampler=wl["sampler"], **DIFF)
-            s1.unet_chunk, s1.noise, s1.parity_rng = wl.get("chunk"), TorchNoise(), False
+            s1.unet_chunk, s1.noise, s1.parity_rng = wl.get("chunk"), PhiloxNoise(seed=1000), False
             im1, _ = loop(s1, x_dev, y_dev, 999, W)
             torch.cuda.synchronize()
             a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -573,7 +580,14 @@ def run_b200(args, rank, world, local_rank):
     alg_bytes = {f"{kind}_forward": n * (2 * T_BYTES + m_bytes), f"{kind}_adjoint": n * (3 * T_BYTES + m_bytes),
                  upd: n * (7 if sampler.kind == "ddpm" else 5) * T_BYTES, "gather_particles": n * 2 * T_BYTES, "guidance_coef": 0}
     peak, peak_src = peaks()
-    live = graph_durations(plan, sampler.kind, sampler.schedule.consts(500), n, y_dev, device, want_gather=searching)
+    philox = sampler.kind == "ddpm"
+    alg_bytes[f"{kind}_guidance"] = n * (3 * T_BYTES + m_bytes)
+    alg_bytes[f"{kind}_forward+adjoint"] = alg_bytes[f"{kind}_forward"] + alg_bytes[f"{kind}_adjoint"]
+    if philox:
+        alg_bytes[upd] = n * 6 * T_BYTES                        # no z tensor: the noise is generated in the kernel
+    live = graph_durations(plan, sampler.kind, sampler.schedule.consts(500), n, y_dev, device, want_gather=searching, philox=philox)
+    if f"{kind}_forward" in live and f"{kind}_adjoint" in live:
+        live[f"{kind}_forward+adjoint"] = live[f"{kind}_forward"] + live[f"{kind}_adjoint"]
     ktab = {}
     for kname, (cnt, mean_ms) in spans.items():
         b = alg_bytes.get(kname, 0)
@@ -638,6 +652,10 @@ def run_b200(args, rank, world, local_rank):
             "config": {"workload": f"{name}: {desc}", "particles_per_gpu": n, "global_particles": n_global,
                        "image": "3x256x256", "sampler": wl["sampler"],
                        "chain": "1000 steps, timed window idx %d..%d" % (999 - W, 999 - W - K + 1),
+                       "noise": "value: Philox4x32-10 inside the update kernel (no z tensor); e2e: z copied from pinned host memory every step",
+                       "guidance_coefficient": "deferred to the update kernel (dps_update_ext): residual+cotangent = " +
+                                               ("ONE fused cluster kernel" if plan.guidance_partials > 0 else "forward + adjoint launches") +
+                                               ", no coefficient launch",
                        "unet": model_name, "unet_chunk": sampler._chunk_size(None, x_dev) if sampler.unet_chunk != "auto"
                        else getattr(sampler, "_auto_chunk", None),
                        "unet_launch": "eager (kernel by kernel)" if args.eager_unet else
@@ -735,7 +753,7 @@ def single_gpu_extras(args, wl, name, model, sampler, loop, x_dev, y_dev, device
     """Driver-recorded context for the N=1 line: (1) the reference's OWN loop in torch eager on cuda:0 with the same UNet, same
     window, same particle count — what the graft replaces, like for like; (2) the B200 arm again with TF32 switched off in
     cuDNN and cuBLAS (every parity test runs that way)."""
-    from dps_ttc_b200.sampler import TorchNoise, create_sampler
+    from dps_ttc_b200.sampler import PhiloxNoise, create_sampler
     out = {}
     sampler.__dict__.pop("_graphs", None)                      # release the main arm's CUDA-graph pools
     torch.cuda.empty_cache()
@@ -752,7 +770,7 @@ def single_gpu_extras(args, wl, name, model, sampler, loop, x_dev, y_dev, device
     torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
     try:
         s2 = create_sampler(sampler=wl["sampler"], **DIFF)     # fresh sampler: its CUDA graphs are captured without TF32
-        s2.unet_chunk, s2.noise, s2.parity_rng = wl.get("chunk"), TorchNoise(), False
+        s2.unet_chunk, s2.noise, s2.parity_rng = wl.get("chunk"), PhiloxNoise(seed=1000), False
         im, _ = loop(s2, x_dev, y_dev, 999, W)
         torch.cuda.synchronize()
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -7,15 +7,22 @@
 // mask and the UNet VJP (all linear in the cotangent), so it is applied by the posterior-update kernel instead
 // (dps_update_ext), and nothing global stands between A and Aᵀ any more: 3T + M bytes, one launch.
 //
+// The Resizer with an integer factor is a strided convolution with ONE weight vector w[4F] over the symmetrically padded
+// image (field_of_view = mirror[...], weights independent of the output position; checked at plan creation, else no fused
+// kernel).  So the weights travel as kernel parameters (constant bank: no shared-memory table, no bank conflicts) and the
+// borders are handled by mirrored reads of rows / columns the CTA already holds.
+//
 // Mapping: a thread-block CLUSTER of 8 CTAs owns one (particle, channel) plane; CTA q owns image rows [32q, 32q+32) and
 // residual rows [RJ·q, RJ·(q+1)), RJ = 32/F.
-//   0. x, ε rows → shared memory by two 32 KB TMA bulk copies; x̂₀ (clamped) and the pre-clamp value replace them in place.
-//   1. cluster barrier; H pass: a thread owns a column and walks the 32 + 2·HALO rows its RJ residual rows need — the halo
-//      rows are read from the neighbour CTAs' shared memory (DSMEM), not from HBM.
-//   2. W pass from the RJ×256 tile; r = y − (·), Σr², Σ|r| → one partial-sum pair per CTA; r stays in shared memory.
-//   3. cluster barrier; Aᵀ: u = r·A_w for the RJ+4 residual rows that touch this CTA's image rows (2+2 of them from the
-//      neighbours' shared memory), then g = A_hᵀ u, masked with the pre-clamp value still in shared memory; one coalesced
-//      store per image row.
+//   0. x, ε rows → shared memory by TMA bulk copies in four 8-row chunks; each chunk becomes x̂₀ (clamped) in place as it
+//      lands; the clamp mask of a thread's column is one 32-bit register.  The ε buffer is dead afterwards and is reused
+//      for the H-pass tile and the residual rows (3 CTAs per SM).
+//   1. cluster barrier; H pass: a thread owns a column and walks the 32 + 2·HALO rows its RJ residual rows need — halo
+//      rows come from the neighbour CTAs' shared memory (DSMEM), mirrored own rows at the image border.
+//   2. W pass from the column-padded RJ×(256+2·HALO) tile with 128-bit shared loads; r = y − (·), Σr², Σ|r| → one
+//      partial-sum pair per CTA; r stays in shared memory.
+//   3. cluster barrier (arrive early, wait late); Aᵀ: u = r·A_w for the RJ+4 residual rows that touch this CTA's image
+//      rows (2+2 of them from the neighbours), then g = A_hᵀ u, masked, one coalesced store per image row.
 // HBM traffic = the algorithmic minimum: x, ε read once, g written once, y read once.
 #include <cooperative_groups.h>
 
@@ -26,94 +33,112 @@
 namespace cg = cooperative_groups;
 
 struct ResizeFused {
-  int F = 0;            // 4 or 8
-  float* wf_h = nullptr;  // (oH, TAPS) folded forward weights along H: row j uses image rows F·j − HALO + k
-  float* wf_w = nullptr;  // (oW, TAPS) the same along W
+  int F = 0;              // 4 or 8
+  float w[32] = {};       // the convolution weights (4F of them)
   float* at_h = nullptr;  // (H, 4) transposed band along H: image row i receives from residual rows j0(i) + d, d < 4
   float* at_w = nullptr;  // (W, 4) the same along W
 };
 
 namespace {
-constexpr int kW = 256, kRI = 32, kCluster = 8, kT = 256;
+constexpr int kW = 256, kRI = 32, kCluster = 8, kT = 256, kChunks = 4, kChunkRows = kRI / kChunks;
+
+struct FusedArgs {
+  float w[32];
+  const float* at_h;
+  const float* at_w;
+  int C;
+  dps_source src;
+  const float* y;
+  int64_t y_stride;
+  float* r_out;
+  float* g;
+  int64_t g_stride;
+  float* partials;
+};
 
 template <int F>
 struct Geo {
-  static constexpr int TAPS = 4 * F, HALO = (TAPS - F) / 2, RJ = kRI / F, OW = kW / F, RU = RJ + 4;
+  static constexpr int TAPS = 4 * F, HALO = (TAPS - F) / 2, RJ = kRI / F, OW = kW / F, RU = RJ + 4, PADW = kW + 2 * HALO;
   // first residual row/col (relative, may be negative) that touches image row/col p:  ceil((p + HALO − TAPS + 1) / F)
   static constexpr int j0(int p) { return (p + HALO - TAPS + 1 + 1024 * F + F - 1) / F - 1024; }
 };
 
 template <int F>
 size_t fused_smem() {
-  using G = Geo<F>;
-  return sizeof(float) * ((size_t)2 * kRI * kW + (size_t)G::RJ * kW + (size_t)G::RJ * G::OW + (size_t)G::RJ * G::TAPS +
-                          (size_t)G::OW * G::TAPS + (size_t)kRI * 4 + 64) + 16;
+  return sizeof(float) * ((size_t)2 * kRI * kW + (size_t)kRI * 4 + 64) + 8 * kChunks;
 }
 
+DPS_DEV void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+DPS_DEV void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
 template <int F>
-__global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kT, 2)
-    resize_guidance_kernel(const ResizeFused t, int C, const dps_source src, const float* __restrict__ y, int64_t y_stride,
-                           float* __restrict__ r_out, float* __restrict__ g, int64_t g_stride, float* __restrict__ partials) {
+__global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kT, 3) resize_guidance_kernel(const __grid_constant__ FusedArgs a) {
   using G = Geo<F>;
-  constexpr int TAPS = G::TAPS, HALO = G::HALO, RJ = G::RJ, OW = G::OW, RU = G::RU, H = kRI * kCluster;
+  constexpr int TAPS = G::TAPS, HALO = G::HALO, RJ = G::RJ, OW = G::OW, RU = G::RU, PADW = G::PADW, H = kRI * kCluster;
+  static_assert((size_t)RJ * PADW + (size_t)RJ * OW <= (size_t)kRI * kW, "tile + residual rows fit into the dead ε buffer");
   extern __shared__ __align__(16) float smem[];
   float* Sx = smem;                       // (32, 256)  x → x̂₀ (clamped)
-  float* Se = Sx + kRI * kW;              // (32, 256)  ε → pre-clamp value
-  float* St = Se + kRI * kW;              // (RJ, 256)  H-pass result
-  float* Sr = St + RJ * kW;               // (RJ, OW)   residual rows of this CTA
-  float* Wh = Sr + RJ * OW;               // (RJ, TAPS) folded H weights of my residual rows
-  float* Ww = Wh + RJ * TAPS;             // (OW, TAPS) folded W weights
-  float* Ah = Ww + OW * TAPS;             // (32, 4)    transposed H band of my image rows
+  float* Se = Sx + kRI * kW;              // (32, 256)  ε; dead after step 0 → St, Sr
+  float* St = Se;                         // (RJ, PADW) H-pass result, column-padded by mirroring
+  float* Sr = St + RJ * PADW;             // (RJ, OW)   residual rows of this CTA
+  float* Ah = Se + kRI * kW;              // (32, 4)    transposed H band of my image rows
   float* red = Ah + kRI * 4;              // 64
-  uint64_t* bar = reinterpret_cast<uint64_t*>(red + 64);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(red + 64);  // kChunks barriers
 
   cg::cluster_group cluster = cg::this_cluster();
   const int q = (int)cluster.block_rank();
-  const int plane = blockIdx.x / kCluster, c = plane % C, n = plane / C;
+  const int plane = blockIdx.x / kCluster, c = plane % a.C, n = plane / a.C;
   const int tid = threadIdx.x;
   const int64_t poff = (int64_t)c * H * kW + (int64_t)q * kRI * kW;
-  const float* xg = src.x + n * src.x_stride + poff;
-  const float* eg = src.eps + n * src.eps_stride + poff;
+  const float* xg = a.src.x + n * a.src.x_stride + poff;
+  const float* eg = a.src.eps + n * a.src.eps_stride + poff;
 
   if (tid == 0) {
-    mbar_init(bar, 1);
+#pragma unroll
+    for (int ch = 0; ch < kChunks; ++ch) mbar_init(bar + ch, 1);
     mbar_init_fence();
   }
   __syncthreads();
   if (tid == 0) {
-    mbar_expect_tx(bar, 2u * kRI * kW * sizeof(float));
-    bulk_load(Sx, xg, kRI * kW * sizeof(float), bar);
-    bulk_load(Se, eg, kRI * kW * sizeof(float), bar);
+    constexpr unsigned bytes = kChunkRows * kW * sizeof(float);
+#pragma unroll
+    for (int ch = 0; ch < kChunks; ++ch) {
+      mbar_expect_tx(bar + ch, 2u * bytes);
+      bulk_load(Sx + ch * kChunkRows * kW, xg + ch * kChunkRows * kW, bytes, bar + ch);
+      bulk_load(Se + ch * kChunkRows * kW, eg + ch * kChunkRows * kW, bytes, bar + ch);
+    }
   }
   // tables and measurement values while the rows are in flight
-  stage_async(Wh, t.wf_h + (size_t)q * RJ * TAPS, RJ * TAPS, tid, kT);
-  stage_async(Ww, t.wf_w, OW * TAPS, tid, kT);
-  stage_async(Ah, t.at_h + (size_t)q * kRI * 4, kRI * 4, tid, kT);
-  const float4 aw = __ldg(reinterpret_cast<const float4*>(t.at_w) + tid);  // my column's transposed W band
-  constexpr int kRPerThread = RJ * OW / kT;  // residual values per thread in the W pass: 2 (F=4) or … ≥ 1
-  static_assert(RJ * OW % kT == 0 || RJ * OW < kT, "W-pass mapping");
-  float yv[kRPerThread > 0 ? kRPerThread : 1];
-  const float* yp = y ? y + n * y_stride + (int64_t)c * (H / F) * OW + (int64_t)q * RJ * OW : nullptr;
+  stage_async(Ah, a.at_h + (size_t)q * kRI * 4, kRI * 4, tid, kT);
+  const float4 aw = __ldg(reinterpret_cast<const float4*>(a.at_w) + tid);  // my column's transposed W band
+  constexpr int kRP = (RJ * OW + kT - 1) / kT;  // residual values per thread in the W pass
+  float yv[kRP];
+  const float* yp = a.y ? a.y + n * a.y_stride + (int64_t)c * (H / F) * OW + (int64_t)q * RJ * OW : nullptr;
 #pragma unroll
-  for (int u = 0; u < (kRPerThread > 0 ? kRPerThread : 1); ++u) {
+  for (int u = 0; u < kRP; ++u) {
     const int o = tid + u * kT;
     yv[u] = (yp && o < RJ * OW) ? ldg_ro(yp + o) : 0.f;
   }
   stage_wait();
-  mbar_wait(bar, 0);
-  // x̂₀ and the pre-clamp value in place (column = thread: conflict-free)
+  // ---- 0. x̂₀ in place, chunk by chunk as the copies land; clamp mask of my column → one register ----
+  unsigned pass_bits = 0;
   {
-    const float lo = src.clip ? -1.0f : -INFINITY, hi = src.clip ? 1.0f : INFINITY;
-#pragma unroll 8
-    for (int r = 0; r < kRI; ++r) {
-      const float pre = x0_pre(Sx[r * kW + tid], Se[r * kW + tid], src.c1, src.c2);
-      Sx[r * kW + tid] = fminf(fmaxf(pre, lo), hi);
-      Se[r * kW + tid] = pre;
+    const float lo = a.src.clip ? -1.0f : -INFINITY, hi = a.src.clip ? 1.0f : INFINITY;
+#pragma unroll
+    for (int ch = 0; ch < kChunks; ++ch) {
+      mbar_wait(bar + ch, 0);
+#pragma unroll
+      for (int rr = 0; rr < kChunkRows; ++rr) {
+        const int r = ch * kChunkRows + rr;
+        const float pre = x0_pre(Sx[r * kW + tid], Se[r * kW + tid], a.src.c1, a.src.c2);
+        Sx[r * kW + tid] = fminf(fmaxf(pre, lo), hi);
+        pass_bits |= (pre >= lo && pre <= hi) ? (1u << r) : 0u;
+      }
     }
   }
-  cluster.sync();  // every CTA's x̂₀ rows are in place
+  cluster.sync();  // every CTA's x̂₀ rows are in place (and nobody reads the ε buffer any more)
 
-  // ---- 1. H pass: t[jj][col] = Σ_k Wh[jj][k] · x̂₀[F·(RJ·q + jj) − HALO + k][col] ----
+  // ---- 1. H pass: t[jj][col] = Σ_k w[k] · x̂₀[sym(F·(RJ·q + jj) − HALO + k)][col] ----
   {
     const float* up = q > 0 ? cluster.map_shared_rank(Sx, q - 1) : Sx;
     const float* dn = q < kCluster - 1 ? cluster.map_shared_rank(Sx, q + 1) : Sx;
@@ -121,120 +146,128 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kT, 2)
 #pragma unroll
     for (int jj = 0; jj < RJ; ++jj) acc[jj] = 0.f;
 #pragma unroll
-    for (int w = 0; w < kRI + 2 * HALO; ++w) {
-      const int lr = w - HALO;  // row relative to my first image row
+    for (int wdx = 0; wdx < kRI + 2 * HALO; ++wdx) {
+      const int lr = wdx - HALO;  // row relative to my first image row
       float v;
-      if (lr < 0) {
-        if (q == 0) continue;  // above the image: its folded weights are zero
-        v = up[(kRI + lr) * kW + tid];
-      } else if (lr >= kRI) {
-        if (q == kCluster - 1) continue;
-        v = dn[(lr - kRI) * kW + tid];
-      } else {
+      if (lr < 0)  // above my rows: the neighbour's last rows, or (top of the image) my own rows mirrored: −1 ↦ 0, −2 ↦ 1 …
+        v = q > 0 ? up[(kRI + lr) * kW + tid] : Sx[(-lr - 1) * kW + tid];
+      else if (lr >= kRI)
+        v = q < kCluster - 1 ? dn[(lr - kRI) * kW + tid] : Sx[(2 * kRI - 1 - lr) * kW + tid];
+      else
         v = Sx[lr * kW + tid];
-      }
 #pragma unroll
       for (int jj = 0; jj < RJ; ++jj) {
-        const int k = w - F * jj;  // compile-time after unrolling
-        if (k >= 0 && k < TAPS) acc[jj] = fmaf(Wh[jj * TAPS + k], v, acc[jj]);
+        const int k = wdx - F * jj;  // compile-time after unrolling
+        if (k >= 0 && k < TAPS) acc[jj] = fmaf(a.w[k], v, acc[jj]);
       }
     }
 #pragma unroll
-    for (int jj = 0; jj < RJ; ++jj) St[jj * kW + tid] = acc[jj];
+    for (int jj = 0; jj < RJ; ++jj) {
+      float* row = St + jj * PADW + HALO;
+      row[tid] = acc[jj];
+      if (tid < HALO) row[-1 - tid] = acc[jj];                   // columns −1, −2, … mirror columns 0, 1, …
+      if (tid >= kW - HALO) row[2 * kW - 1 - tid] = acc[jj];     // columns 256, 257, … mirror 255, 254, …
+    }
   }
   __syncthreads();
 
   // ---- 2. W pass, residual, partial sums ----
   float sq = 0.f, ab = 0.f;
 #pragma unroll
-  for (int u = 0; u < (kRPerThread > 0 ? kRPerThread : 1); ++u) {
+  for (int u = 0; u < kRP; ++u) {
     const int o = tid + u * kT;
     if (o < RJ * OW) {
       const int jj = o / OW, l = o - jj * OW;
-      const float* tr = St + jj * kW;
-      const float* wl = Ww + l * TAPS;
-      float a = 0.f;
+      const float4* tr = reinterpret_cast<const float4*>(St + jj * PADW + F * l);  // padded column F·l = image column F·l − HALO
+      float acc = 0.f;
 #pragma unroll
-      for (int k = 0; k < TAPS; ++k) {
-        const int col = F * l - HALO + k;
-        if (col >= 0 && col < kW) a = fmaf(wl[k], tr[col], a);
+      for (int m = 0; m < TAPS / 4; ++m) {
+        const float4 t4 = tr[m];
+        acc = fmaf(a.w[4 * m + 0], t4.x, acc);
+        acc = fmaf(a.w[4 * m + 1], t4.y, acc);
+        acc = fmaf(a.w[4 * m + 2], t4.z, acc);
+        acc = fmaf(a.w[4 * m + 3], t4.w, acc);
       }
-      const float res = yp ? yv[u] - a : a;
+      const float res = yp ? yv[u] - acc : acc;
       Sr[o] = res;
-      if (r_out) r_out[((int64_t)n * C + c) * (H / F) * OW + (int64_t)q * RJ * OW + o] = res;
+      if (a.r_out) a.r_out[((int64_t)n * a.C + c) * (H / F) * OW + (int64_t)q * RJ * OW + o] = res;
       sq = fmaf(res, res, sq);
       ab += fabsf(res);
     }
   }
-  if (partials) {
+  __syncthreads();  // my residual rows are complete …
+  cluster_arrive();  // … and announced; the partial sums below overlap the other CTAs' arrival
+  if (a.partials) {
     block_sum2(sq, ab, red);
     if (tid == 0) {
-      float* pp = partials + ((int64_t)n * (C * kCluster) + c * kCluster + q) * 2;
+      float* pp = a.partials + ((int64_t)n * (a.C * kCluster) + c * kCluster + q) * 2;
       pp[0] = sq;
       pp[1] = ab;
     }
   }
-  cluster.sync();  // every CTA's residual rows are in place
-
   // ---- 3. Aᵀ: u[m][col] = Σ_d aw[d] · r[RJ·q − 2 + m][l0(col) + d],  then g[ii][col] = mask · Σ_d Ah[ii][d] · u[m0(ii) + d] ----
   {
-    const float* rup = q > 0 ? cluster.map_shared_rank(Sr, q - 1) : Sr;
-    const float* rdn = q < kCluster - 1 ? cluster.map_shared_rank(Sr, q + 1) : Sr;
     // first residual column that touches image column `tid`:  ceil((tid + HALO − TAPS + 1)/F)
     const int num = tid + HALO - TAPS + 1;
     const int lfirst = num >= 0 ? (num + F - 1) / F : -((-num) / F);
     const float awv[4] = {aw.x, aw.y, aw.z, aw.w};
     float uu[RU];
-#pragma unroll
-    for (int m = 0; m < RU; ++m) {
-      const int jr = m - 2;  // residual row relative to my first one
-      const float* rr;
-      if (jr < 0) {
-        if (q == 0) { uu[m] = 0.f; continue; }
-        rr = rup + (RJ + jr) * OW;
-      } else if (jr >= RJ) {
-        if (q == kCluster - 1) { uu[m] = 0.f; continue; }
-        rr = rdn + (jr - RJ) * OW;
-      } else {
-        rr = Sr + jr * OW;
-      }
-      float a = 0.f;
+    auto urow = [&](const float* rr) {
+      float s = 0.f;
 #pragma unroll
       for (int d = 0; d < 4; ++d) {
         const int l = lfirst + d;
-        if (l >= 0 && l < OW) a = fmaf(awv[d], rr[l], a);
+        if (l >= 0 && l < OW) s = fmaf(awv[d], rr[l], s);
       }
-      uu[m] = a;
+      return s;
+    };
+#pragma unroll
+    for (int m = 2; m < RJ + 2; ++m) uu[m] = urow(Sr + (m - 2) * OW);  // my own rows first
+    cluster_wait();                                                       // every CTA's residual rows are in place
+    const float* rup = q > 0 ? cluster.map_shared_rank(Sr, q - 1) : Sr;
+    const float* rdn = q < kCluster - 1 ? cluster.map_shared_rank(Sr, q + 1) : Sr;
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+      uu[m] = q > 0 ? urow(rup + (RJ - 2 + m) * OW) : 0.f;                       // residual rows above the image do not exist
+      uu[RJ + 2 + m] = q < kCluster - 1 ? urow(rdn + m * OW) : 0.f;
     }
-    float* gp = g + n * g_stride + poff;
+    cluster_arrive();  // my remote reads are done: the neighbours may exit once everybody has said so
+    float* gp = a.g + n * a.g_stride + poff;
 #pragma unroll
     for (int ii = 0; ii < kRI; ++ii) {
-      // first residual row (relative to RJ·q − 2) that touches image row ii:  ceil((ii + HALO − TAPS + 1)/F) + 2
-      const int m0 = G::j0(ii) + 2;  // compile-time after unrolling
-      float a = 0.f;
+      const int m0 = G::j0(ii) + 2;  // first residual row, relative to RJ·q − 2, that touches image row ii (compile-time)
+      float s = 0.f;
 #pragma unroll
       for (int d = 0; d < 4; ++d)
-        if (m0 + d >= 0 && m0 + d < RU) a = fmaf(Ah[ii * 4 + d], uu[m0 + d], a);
-      const float pre = Se[ii * kW + tid];
-      const float pass = (!src.clip || (pre >= -1.0f && pre <= 1.0f)) ? 1.0f : 0.f;
-      stg_stream(gp + ii * kW + tid, a * pass);
+        if (m0 + d >= 0 && m0 + d < RU) s = fmaf(Ah[ii * 4 + d], uu[m0 + d], s);
+      stg_stream(gp + ii * kW + tid, ((pass_bits >> ii) & 1u) ? s : 0.f);
     }
+    cluster_wait();
   }
-  cluster.sync();  // neighbours may still be reading my shared memory
 }
 
-// folded forward band: wf[j][k] = Σ A[j][F·j − HALO + k]  (dense A already carries the reflected taps merged)
-std::vector<float> folded(const std::vector<double>& A, int out_len, int in_len, int F, int TAPS, int HALO, bool* ok) {
-  std::vector<float> wf((size_t)out_len * TAPS, 0.f);
-  for (int j = 0; j < out_len; ++j)
-    for (int m = 0; m < in_len; ++m) {
-      const double v = A[(size_t)j * in_len + m];
-      if (v == 0.0) continue;
-      const int k = m - (F * j - HALO);
-      if (k < 0 || k >= TAPS) { *ok = false; continue; }
-      wf[(size_t)j * TAPS + k] = (float)v;
-    }
-  return wf;
+int sym_idx(int p, int n) { return p < 0 ? -p - 1 : (p >= n ? 2 * n - 1 - p : p); }
+
+// Is A (out_len × in_len, dense) the stride-F convolution with weights w[k] = A[mid][F·mid − HALO + k] over the symmetrically
+// padded signal?  (True for the Resizer with an integer factor: util/resizer.py:104-167 builds every row from the same kernel
+// samples and mirrors the field of view.)
+bool is_symmetric_conv(const std::vector<double>& A, int out_len, int in_len, int F, int TAPS, int HALO, float* w) {
+  const int mid = out_len / 2;
+  double wmax = 0.0;
+  for (int k = 0; k < TAPS; ++k) {
+    const int p = F * mid - HALO + k;
+    if (p < 0 || p >= in_len) return false;
+    w[k] = (float)A[(size_t)mid * in_len + p];
+    wmax = std::max(wmax, fabs((double)w[k]));
+  }
+  std::vector<double> row(in_len);
+  for (int j = 0; j < out_len; ++j) {
+    std::fill(row.begin(), row.end(), 0.0);
+    for (int k = 0; k < TAPS; ++k) row[sym_idx(F * j - HALO + k, in_len)] += (double)w[k];
+    for (int m = 0; m < in_len; ++m)
+      if (fabs(row[m] - A[(size_t)j * in_len + m]) > 1e-6 * wmax) return false;
+  }
+  return true;
 }
 // transposed band: at[p][d] = A[j0(p) + d][p]
 std::vector<float> transposed(const std::vector<double>& A, int out_len, int in_len, int F, int TAPS, int HALO, bool* ok) {
@@ -264,15 +297,17 @@ int upload(float** dst, const std::vector<float>& v) {
 int resize_fused_create(dps_operator* op, const std::vector<double>& Ah, const std::vector<double>& Aw, int out_h, int out_w) {
   if (op->H != kRI * kCluster || op->W != kW || out_h != out_w || (op->H != 4 * out_h && op->H != 8 * out_h)) return DPS_OK;
   const int F = op->H / out_h, TAPS = 4 * F, HALO = (TAPS - F) / 2;
+  float wh[32] = {}, ww[32] = {};
+  if (!is_symmetric_conv(Ah, out_h, op->H, F, TAPS, HALO, wh) || !is_symmetric_conv(Aw, out_w, op->W, F, TAPS, HALO, ww)) return DPS_OK;
+  for (int k = 0; k < TAPS; ++k)
+    if (wh[k] != ww[k]) return DPS_OK;  // one weight vector serves both axes (square images, same factor)
   bool ok = true;
-  std::vector<float> wfh = folded(Ah, out_h, op->H, F, TAPS, HALO, &ok), wfw = folded(Aw, out_w, op->W, F, TAPS, HALO, &ok);
   std::vector<float> ath = transposed(Ah, out_h, op->H, F, TAPS, HALO, &ok), atw = transposed(Aw, out_w, op->W, F, TAPS, HALO, &ok);
-  if (!ok) return DPS_OK;  // a band wider than the bicubic ×F one (other kernels / antialiasing off): not covered
+  if (!ok) return DPS_OK;
   ResizeFused* t = new ResizeFused();
   t->F = F;
+  for (int k = 0; k < TAPS; ++k) t->w[k] = wh[k];
   op->rfused = t;
-  if (int rc = upload(&t->wf_h, wfh)) return rc;
-  if (int rc = upload(&t->wf_w, wfw)) return rc;
   if (int rc = upload(&t->at_h, ath)) return rc;
   if (int rc = upload(&t->at_w, atw)) return rc;
   if (F == 4)
@@ -286,7 +321,7 @@ int resize_fused_create(dps_operator* op, const std::vector<double>& Ah, const s
 void resize_fused_destroy(dps_operator* op) {
   ResizeFused* t = op->rfused;
   if (!t) return;
-  cudaFree(t->wf_h); cudaFree(t->wf_w); cudaFree(t->at_h); cudaFree(t->at_w);
+  cudaFree(t->at_h); cudaFree(t->at_w);
   delete t;
   op->rfused = nullptr;
 }
@@ -295,11 +330,23 @@ int resize_fused_guidance(const dps_operator* op, const dps_source& src, const f
                           float* g, int64_t g_stride, float* partials, int n, cudaStream_t st) {
   const ResizeFused& t = *op->rfused;
   DPS_REQUIRE(src.eps, DPS_ERR_INVALID, "resize guidance: the fused kernel forms x̂₀ from x and ε (eps is required)");
+  FusedArgs a;
+  for (int k = 0; k < 32; ++k) a.w[k] = t.w[k];
+  a.at_h = t.at_h;
+  a.at_w = t.at_w;
+  a.C = op->C;
+  a.src = src;
+  a.y = y;
+  a.y_stride = y_stride;
+  a.r_out = r_out;
+  a.g = g;
+  a.g_stride = g_stride;
+  a.partials = partials;
   dim3 grid((unsigned)((int64_t)op->C * n * kCluster));
   if (t.F == 4)
-    resize_guidance_kernel<4><<<grid, kT, fused_smem<4>(), st>>>(t, op->C, src, y, y_stride, r_out, g, g_stride, partials);
+    resize_guidance_kernel<4><<<grid, kT, fused_smem<4>(), st>>>(a);
   else
-    resize_guidance_kernel<8><<<grid, kT, fused_smem<8>(), st>>>(t, op->C, src, y, y_stride, r_out, g, g_stride, partials);
+    resize_guidance_kernel<8><<<grid, kT, fused_smem<8>(), st>>>(a);
   DPS_LAUNCH_CHECK("resize_guidance");
   return DPS_OK;
 }

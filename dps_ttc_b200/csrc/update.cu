@@ -53,18 +53,23 @@ DPS_DEV uint4 philox4x32_10(uint4 c, uint2 key) {
   }
   return c;
 }
-DPS_DEV float u01(unsigned r) { return fmaf((float)r, 2.3283064365386963e-10f, 1.1641532182693481e-10f); }  // (r + ½)·2⁻³² ∈ (0,1)
+// 24 random bits → u = (k + ½)·2⁻²⁴ ∈ [2⁻²⁵, 1 − 2⁻²⁵]: exact in fp32, never 0 or 1 (ln u finite, −2 ln u > 0)
+DPS_DEV float u01(unsigned r) { return ((float)(r >> 8) + 0.5f) * 5.9604644775390625e-08f; }
+// Box–Muller with the SFU forms (lg2 / rsq / sin / cos): the generator must not cost more than the HBM read of a z tensor
+// it replaces.  Angle 2π(u − ½) ∈ (−π, π), the range where __sincosf is accurate to 2⁻²¹.
 DPS_DEV float4 philox_normal4(int64_t i4, int64_t particle, const dps_update_ext& e) {
   const uint4 r = philox4x32_10(make_uint4((unsigned)i4, (unsigned)((uint64_t)i4 >> 32), (unsigned)particle, (unsigned)e.philox_step),
                                 make_uint2((unsigned)e.philox_seed, (unsigned)(e.philox_seed >> 32)));
   float4 z;
   float s, c;
-  const float m0 = sqrtf(-2.0f * logf(u01(r.x)));
-  sincospif(2.0f * u01(r.y), &s, &c);
+  const float t0 = -2.0f * __logf(u01(r.x));
+  const float m0 = t0 * rsqrtf(t0);
+  __sincosf(6.283185307179586f * (u01(r.y) - 0.5f), &s, &c);
   z.x = m0 * c;
   z.y = m0 * s;
-  const float m1 = sqrtf(-2.0f * logf(u01(r.z)));
-  sincospif(2.0f * u01(r.w), &s, &c);
+  const float t1 = -2.0f * __logf(u01(r.z));
+  const float m1 = t1 * rsqrtf(t1);
+  __sincosf(6.283185307179586f * (u01(r.w) - 0.5f), &s, &c);
   z.z = m1 * c;
   z.w = m1 * s;
   return z;
@@ -106,7 +111,6 @@ DPS_DEV float ddim_sample(float x, float x0, float z, float c1, float c2, const 
 template <bool kDdim, bool kExt>
 __global__ void __launch_bounds__(kThreads) posterior_update_kernel(const UpdateArgs a) {
   const int n = blockIdx.y;
-  __shared__ float s_coef;
   const int64_t base4 = (int64_t)blockIdx.x * (kThreads * kVecPerThread) + threadIdx.x;
   const float* x = a.x + n * a.x_stride;
   const float* eps = a.eps + n * a.eps_stride;
@@ -135,20 +139,15 @@ __global__ void __launch_bounds__(kThreads) posterior_update_kernel(const Update
   if constexpr (kExt) {
     if (a.ext.partials) {
       // while the loads are in flight: ‖r_n‖ from the residual kernel's partial sums — the reduction order of
-      // particle_norms_kernel (lane-strided fp64 sums, xor-shuffle tree), so the value is bit-identical to it
-      if (threadIdx.x < 32) {
-        const float* p = a.ext.partials + (int64_t)n * a.ext.P * 2;
-        double sq = 0.0;
-        for (int i = threadIdx.x; i < a.ext.P; i += 32) sq += (double)p[2 * i];
-        sq = warp_sum(sq);
-        if (threadIdx.x == 0) {
-          const float nrm = (float)sqrt(sq);
-          s_coef = a.ext.coef_mode == DPS_COEF_NORM ? (nrm > 0.f ? -a.ext.scale / nrm : 0.f) : -2.0f * a.ext.scale;
-          if (a.ext.l2_out && blockIdx.x == 0) a.ext.l2_out[n] = nrm;
-        }
-      }
-      __syncthreads();
-      coef = s_coef;
+      // particle_norms_kernel (lane-strided fp64 sums, xor-shuffle tree), so the value is bit-identical to it.  Every
+      // warp does it for itself (P is a few dozen L2-resident floats): no shared memory, no CTA barrier in the prologue.
+      const float* p = a.ext.partials + (int64_t)n * a.ext.P * 2;
+      double sq = 0.0;
+      for (int i = threadIdx.x & 31; i < a.ext.P; i += 32) sq += (double)__ldg(p + 2 * i);
+      sq = warp_sum(sq);
+      const float nrm = (float)sqrt(sq);
+      coef = a.ext.coef_mode == DPS_COEF_NORM ? (nrm > 0.f ? -a.ext.scale / nrm : 0.f) : -2.0f * a.ext.scale;
+      if (a.ext.l2_out && blockIdx.x == 0 && threadIdx.x == 0) a.ext.l2_out[n] = nrm;
     }
     if (a.ext.use_philox && !z && a.k.noise_on) {
 #pragma unroll

@@ -313,15 +313,16 @@ def philox4x32_10(counter, key):
 
 def philox_normal(seed, step, particle, n_elems):
     """The z of one particle (n_elems values, a multiple of 4): element group i4 ↦ Philox(counter = (i4 lo, i4 hi, particle,
-    step), key = (seed lo, seed hi)) → u = (r + ½)·2⁻³² → Box–Muller pairs (√(−2 ln u₀)·cos 2πu₁, ·sin 2πu₁, …)."""
+    step), key = (seed lo, seed hi)) → u = ((r >> 8) + ½)·2⁻²⁴ → Box–Muller pairs (√(−2 ln u₀)·cos θ, ·sin θ, …) with
+    θ = 2π(u₁ − ½)."""
     i4 = np.arange(n_elems // 4, dtype=np.uint64)
     ctr = np.stack([i4 & np.uint64(0xFFFFFFFF), i4 >> np.uint64(32), np.full_like(i4, particle & 0xFFFFFFFF),
                     np.full_like(i4, step & 0xFFFFFFFF)], axis=1).astype(np.uint32)
     r = philox4x32_10(ctr, np.array([seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF], dtype=np.uint32))
-    u = (r.astype(np.float32) * f32(2.3283064365386963e-10) + f32(1.1641532182693481e-10)).astype(np.float64)
+    u = ((r >> np.uint32(8)).astype(np.float64) + 0.5) * 2.0 ** -24
     m0, m1 = np.sqrt(-2.0 * np.log(u[:, 0])), np.sqrt(-2.0 * np.log(u[:, 2]))
-    z = np.stack([m0 * np.cos(2 * np.pi * u[:, 1]), m0 * np.sin(2 * np.pi * u[:, 1]),
-                  m1 * np.cos(2 * np.pi * u[:, 3]), m1 * np.sin(2 * np.pi * u[:, 3])], axis=1)
+    t0, t1 = 2 * np.pi * (u[:, 1] - 0.5), 2 * np.pi * (u[:, 3] - 0.5)
+    z = np.stack([m0 * np.cos(t0), m0 * np.sin(t0), m1 * np.cos(t1), m1 * np.sin(t1)], axis=1)
     return z.reshape(-1).astype(f32)
 
 

@@ -111,7 +111,7 @@ def test_philox_noise_in_the_update_kernel():
     # the same update with the oracle's restatement of the generator as an explicit z tensor
     z = np.stack([O.philox_normal(seed, step, offset + i, 3 * 256 * 256).reshape(3, 256, 256) for i in range(n)])
     want, _, _ = kernels.posterior_update("ddpm", x, o6[:, :3], o6[:, 3:], torch.from_numpy(z).to(DEV), k)
-    assert float((got - want).abs().max()) <= 2e-5 * max(1.0, float(want.abs().max()))     # logf / sincospif vs libm
+    assert float((got - want).abs().max()) <= 1e-4 * max(1.0, float(want.abs().max()))     # SFU lg2 / rsq / sin / cos vs libm
     # sharded == unsharded: particles 2..3 of the launch above = a launch of two particles at offset + 2
     part, _, _ = kernels.posterior_update("ddpm", x[2:], o6[2:, :3], o6[2:, 3:], None, k, philox=(seed, step, offset + 2))
     assert torch.equal(part, got[2:])

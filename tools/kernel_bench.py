@@ -140,6 +140,24 @@ def main():
         emit("posterior_update_ddim (5T)", 5 * n * T, us)
         us = time_it(lambda i: kernels.x0_from_eps(X[i], O6[i][:, :3], k, out=OUT[i]), S, a.iters)
         emit("x0_from_eps (3T)", 3 * n * T, us)
+    if want("update_ext"):
+        us = time_it(lambda i: Z[i].normal_(), S, a.iters)
+        emit("torch normal_ into a (N,3,256,256) tensor (what the device-noise mode replaces, +1T read in the update)", n * T, us)
+        part = torch.rand(n, 24, 2, device=dev) * 10
+        dist = torch.empty(n, device=dev)
+        us = time_it(lambda i: kernels.posterior_update("ddpm", X[i], O6[i][:, :3], O6[i][:, 3:], Z[i], k, g=G6[i][:, :3],
+                                                        vjp=VJ[i], out=OUT[i], deferred=(part, 1, 0.01, dist)), S, a.iters)
+        emit("posterior_update_ddpm_ext deferred coef (7T)", 7 * n * T, us)
+        us = time_it(lambda i: kernels.posterior_update("ddpm", X[i], O6[i][:, :3], O6[i][:, 3:], None, k, g=G6[i][:, :3],
+                                                        vjp=VJ[i], out=OUT[i], philox=(1, 5, 0)), S, a.iters)
+        emit("posterior_update_ddpm_ext philox (6T)", 6 * n * T, us)
+        us = time_it(lambda i: kernels.posterior_update("ddpm", X[i], O6[i][:, :3], O6[i][:, 3:], None, k, g=G6[i][:, :3],
+                                                        vjp=VJ[i], out=OUT[i], deferred=(part, 1, 0.01, dist), philox=(1, 5, 0)),
+                     S, a.iters)
+        emit("posterior_update_ddpm_ext deferred coef + philox (6T)", 6 * n * T, us)
+        us = time_it(lambda i: kernels.posterior_update("ddim", X[i], O6[i][:, :3], None, None, k, g=G6[i][:, :3],
+                                                        vjp=VJ[i], out=OUT[i], deferred=(part, 1, 0.01, dist)), S, a.iters)
+        emit("posterior_update_ddim_ext deferred coef (5T)", 5 * n * T, us)
 
     def op_bench(tag, plan, m_bytes):
         if not want(tag):
@@ -169,6 +187,15 @@ def main():
     op_bench("gauss", OperatorPlan.blur(tables.gaussian_kernel(61, 3.0).astype(np.float32), 3, 256, 256, dev), T)
     (fh, wh), (fw, ww), _ = tables.resizer_tables((1, 3, 256, 256), 0.25)
     op_bench("sr4", OperatorPlan.resize(fh, wh, fw, ww, 3, 256, 256, dev), T // 16)
+    if want("sr4fused") or want("sr8fused"):
+        for tag, f in (("sr4fused", 4), ("sr8fused", 8)):
+            if not want(tag):
+                continue
+            (fh_, wh_), (fw_, ww_), _ = tables.resizer_tables((1, 3, 256, 256), 1.0 / f)
+            plan_f = OperatorPlan.resize(fh_, wh_, fw_, ww_, 3, 256, 256, dev)
+            yf = rnd(1, 3, 256 // f, 256 // f)
+            us = time_it(lambda i: plan_f.guidance(X[i], O6[i][:, :3], k, True, yf, out=G6[i][:, :3]), S, a.iters)
+            emit(f"{tag} guidance: residual + cotangent in one cluster kernel (3T+M)", n * (3 * T + T // (f * f)), us)
     np.random.seed(8)
     op_bench("motion", OperatorPlan.blur(tables.motion_kernel(61, 0.5).astype(np.float32), 3, 256, 256, dev), T)
     if want("phase"):
