@@ -111,6 +111,7 @@ DPS_DEV float ddim_sample(float x, float x0, float z, float c1, float c2, const 
 template <bool kDdim, bool kExt>
 __global__ void __launch_bounds__(kThreads) posterior_update_kernel(const UpdateArgs a) {
   const int n = blockIdx.y;
+  __shared__ float s_coef;
   const int64_t base4 = (int64_t)blockIdx.x * (kThreads * kVecPerThread) + threadIdx.x;
   const float* x = a.x + n * a.x_stride;
   const float* eps = a.eps + n * a.eps_stride;
@@ -139,20 +140,29 @@ __global__ void __launch_bounds__(kThreads) posterior_update_kernel(const Update
   if constexpr (kExt) {
     if (a.ext.partials) {
       // while the loads are in flight: ‖r_n‖ from the residual kernel's partial sums — the reduction order of
-      // particle_norms_kernel (lane-strided fp64 sums, xor-shuffle tree), so the value is bit-identical to it.  Every
-      // warp does it for itself (P is a few dozen L2-resident floats): no shared memory, no CTA barrier in the prologue.
-      const float* p = a.ext.partials + (int64_t)n * a.ext.P * 2;
-      double sq = 0.0;
-      for (int i = threadIdx.x & 31; i < a.ext.P; i += 32) sq += (double)__ldg(p + 2 * i);
-      sq = warp_sum(sq);
-      const float nrm = (float)sqrt(sq);
-      coef = a.ext.coef_mode == DPS_COEF_NORM ? (nrm > 0.f ? -a.ext.scale / nrm : 0.f) : -2.0f * a.ext.scale;
-      if (a.ext.l2_out && blockIdx.x == 0 && threadIdx.x == 0) a.ext.l2_out[n] = nrm;
+      // particle_norms_kernel (lane-strided fp64 sums, xor-shuffle tree), so the value is bit-identical to it.  Warp 0
+      // does it once per CTA; the barrier that publishes it comes after the noise generation below, so neither the
+      // partial-sum round trip nor the reduction sits on the other warps' critical path.
+      if (threadIdx.x < 32) {
+        const float* p = a.ext.partials + (int64_t)n * a.ext.P * 2;
+        double sq = 0.0;
+        for (int i = threadIdx.x; i < a.ext.P; i += 32) sq += (double)__ldg(p + 2 * i);
+        sq = warp_sum(sq);
+        if (threadIdx.x == 0) {
+          const float nrm = (float)sqrt(sq);
+          s_coef = a.ext.coef_mode == DPS_COEF_NORM ? (nrm > 0.f ? -a.ext.scale / nrm : 0.f) : -2.0f * a.ext.scale;
+          if (a.ext.l2_out && blockIdx.x == 0) a.ext.l2_out[n] = nrm;
+        }
+      }
     }
     if (a.ext.use_philox && !z && a.k.noise_on) {
 #pragma unroll
       for (int u = 0; u < kVecPerThread; ++u)
         vz[u] = philox_normal4(base4 + (int64_t)u * kThreads, a.ext.particle_offset + n, a.ext);
+    }
+    if (a.ext.partials) {
+      __syncthreads();
+      coef = s_coef;
     }
   }
 #pragma unroll
