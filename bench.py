@@ -53,7 +53,7 @@ WORKLOADS = {
                m_bytes=T_BYTES, sampler="ttc_ddim", n=8, scaling="weak", model="ffhq",
                desc="batched TTC: motion deblur k=61 (synthetic sparse kernel, np seed 8), ps zeta=0.3, ttc_ddim with multinomial "
                     "resampling (w = exp(-d/100)) every 10th index, particles sharded over the GPUs"),
-    "c4": dict(op="phase_retrieval", op_cfg=dict(oversample=2.0), method="ps_anneal", params=dict(scale=0.001),
+    "c4": dict(op="phase_retrieval", op_cfg=dict(oversample=2.0), method="ps_anneal", params=dict(scale=0.0001),
                m_bytes=T_BYTES * 9 // 4, sampler="ttc_ddim", n_global=32, scaling="strong", model="ffhq",
                loop=dict(anneal_amp=1.0, anneal_scale=10.0, anneal_loc=0.5),
                desc="phase retrieval (oversample 2 -> 384x384 |FFT|), ps_anneal with the annealing schedule, ttc_ddim "
@@ -452,7 +452,9 @@ def run_b200(args, rank, world, local_rank):
 
     def loop(smp, x0, y, start, steps, shards=None, **extra):
         kws = dict(model=model, x_start=x0, measurement=y, measurement_cond_fn=cond_fn, record=False, save_root=None,
-                   start_idx=start, num_steps=steps, graph_model=graph_model, **loop_kw, **extra)
+                   start_idx=start, num_steps=steps, **loop_kw)
+        kws["graph_model"] = graph_model
+        kws.update(extra)
         if shards is not None:
             kws["shards"] = shards
         res = smp.p_sample_loop(**kws)
@@ -464,6 +466,8 @@ def run_b200(args, rank, world, local_rank):
     sampler.noise, sampler.parity_rng = PhiloxNoise(seed=1000 + rank), False
     shards = new_shards(timing=True)
     x_dev = x_start_h.to(device)
+    if shards is not None:
+        shards.publish_target(x_dev)                            # symmetric-memory allocation + rendezvous happen here, untimed
     img, _ = loop(sampler, x_dev, y_dev, 999, W, shards)       # warm-up steps (untimed)
     if shards is not None:
         shards.spans.clear()
@@ -517,6 +521,8 @@ def run_b200(args, rank, world, local_rank):
         d2h["bytes"] += d.numel() * 4
 
     e2e_shards = new_shards()
+    if e2e_shards is not None:
+        e2e_shards.publish_target(x_dev)
     barrier()
     t0 = time.perf_counter()
     x_in = x_start_h.to(device, non_blocking=True)             # H2D of the particles and the measurement
@@ -539,7 +545,7 @@ def run_b200(args, rank, world, local_rank):
     # ---------------- sharded == unsharded? (all ranks take part; rank 0 re-runs the loop unsharded) ----------------
     verify = None
     if searching and world > 1 and not args.no_extras:
-        verify = verify_sharded(args, wl, model, cond_fn, y_dev, device, rank, world, n, loop, graph_model)
+        verify = verify_sharded(args, wl, model, cond_fn, y_dev, device, rank, world, n, loop)
     same_1gpu = None
     if searching and world > 1 and not args.no_extras:
         # the SAME workload on ONE GPU (rank 0 alone, the others wait): the like-for-like denominator of the scaling curve
@@ -684,10 +690,13 @@ def run_b200(args, rank, world, local_rank):
     emit(line)
 
 
-def verify_sharded(args, wl, model, cond_fn, y_dev, device, rank, world, n, loop, graph_model):
+def verify_sharded(args, wl, model, cond_fn, y_dev, device, rank, world, n, loop):
     """Sharded run vs the unsharded run of the SAME N particles on rank 0 (same noise tape, same resampling uniforms, UNet
     micro-batched in the ranks' slices so every cuDNN call has the shape it has in the sharded run): ancestors at every
-    resampling index and the final particles + distances must agree bit for bit."""
+    resampling index and the final particles + distances must agree bit for bit.  The UNet runs EAGER with
+    cudnn.deterministic=True in both runs: cuDNN's default backward-data kernels accumulate with atomics (forward+VJP of
+    the FFHQ UNet is not repeatable bit for bit without the flag — tools/determinism_probe.py), and a CUDA graph freezes
+    whatever algorithm the heuristics picked at capture time."""
     import torch.distributed as dist
     from dps_ttc_b200.dist import ParticleShards, shared_uniforms
     from dps_ttc_b200.sampler import NoiseTape, create_sampler
@@ -715,7 +724,7 @@ def verify_sharded(args, wl, model, cond_fn, y_dev, device, rank, world, n, loop
         s_sh.noise = tape_for([rank])
         x0 = make_inputs(n, rank)[1].to(device)
         sh = ParticleShards(n, transport=args.transport)
-        img, d = loop(s_sh, x0, y_dev, start, steps, sh)
+        img, d = loop(s_sh, x0, y_dev, start, steps, sh, graph_model=False)
         anc = s_sh.last_stats["ancestors"]
         anc_keys = sorted(anc, reverse=True)
         anc_mine = torch.stack([anc[i] for i in anc_keys]) if anc_keys else torch.zeros((0, N), dtype=torch.int64, device=device)
@@ -732,7 +741,7 @@ def verify_sharded(args, wl, model, cond_fn, y_dev, device, rank, world, n, loop
             if s_un.unet_chunk is None or s_un.unet_chunk == "auto" or int(s_un.unet_chunk) > n:
                 s_un.unet_chunk = n                              # UNet launches of the ranks' shape
             x_all = torch.cat([make_inputs(n, r)[1] for r in range(world)]).to(device)
-            u_img, u_d = loop(s_un, x_all, y_dev, start, steps)
+            u_img, u_d = loop(s_un, x_all, y_dev, start, steps, graph_model=False)
             u_anc = s_un.last_stats["ancestors"]
             same_anc = sorted(u_anc, reverse=True) == anc_keys and all(
                 bool((all_anc[:, j] == u_anc[i].unsqueeze(0)).all()) for j, i in enumerate(anc_keys))
@@ -742,7 +751,7 @@ def verify_sharded(args, wl, model, cond_fn, y_dev, device, rank, world, n, loop
                    "resampling_indices": anc_keys, "max_abs_particle_diff": dmax, "max_abs_distance_diff": ddist,
                    "window": f"idx {start}..{start - steps + 1}", "transport": sh.transport,
                    "what": f"{N} particles: {world} ranks x {n} sharded vs rank 0 unsharded (UNet micro-batched by {n}), "
-                           "cudnn.deterministic=True for both"}
+                           "eager UNet with cudnn.deterministic=True for both"}
         dist.barrier()
         return res
     finally:

@@ -196,6 +196,8 @@ int dps_operator_guidance(const dps_operator* op, const dps_source* src, const f
                     src->x_stride % 4 == 0 && (!src->eps || src->eps_stride % 4 == 0) && y_stride % 4 == 0 && g_stride % 4 == 0,
                 DPS_ERR_ALIGN, "dps_operator_guidance: tensors must be 16-byte aligned, strides multiples of 4");
     if (op->kind == DPS_OP_RESIZE) return resize_fused_guidance(op, *src, y, y_stride, r_out, g, g_stride, partials, n, (cudaStream_t)stream);
+    if (op->kind == DPS_OP_PHASE && src->eps)
+      return phase_guidance(op, *src, y, y_stride, r_out, g, g_stride, partials, aux, n, (cudaStream_t)stream);
   }
   // no fused kernel for this operator / shape: the residual kernel, then the adjoint kernel without a coefficient
   DPS_REQUIRE(r_out, DPS_ERR_INVALID, "dps_operator_guidance: this operator has no fused kernel and needs the residual buffer r_out");

@@ -137,3 +137,5 @@ int phase_create(dps_operator* op, int pad);
 void phase_destroy(dps_operator* op);
 int phase_forward(const dps_operator* op, const FwdArgs& a, cudaStream_t st);
 int phase_adjoint(const dps_operator* op, const AdjArgs& a, cudaStream_t st);
+int phase_guidance(const dps_operator* op, const dps_source& src, const float* y, int64_t y_stride, float* r_out, float* g,
+                   int64_t g_stride, float* partials, float* aux, int n, cudaStream_t st);

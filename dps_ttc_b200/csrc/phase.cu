@@ -307,8 +307,27 @@ DPS_DEV float2* aux_scratch(float* aux, int n, int C, int c) {
   return reinterpret_cast<float2*>(aux + (int64_t)n * C * kHalf * (kL + kImg) * 2) + (int64_t)C * kHalf * kL +
          (int64_t)c * kHalf * kImg;
 }
+// Fused guidance path: the unit phase never leaves the column kernel, so its region of the workspace holds the second
+// scratch T[row][k2] (C·256·193 complex ≤ C·193·384) and, behind it, the clamp-mask bytes (C·256·256 bytes).
+DPS_DEV float2* aux_scratch2(float* aux, int n, int C, int c) {
+  return reinterpret_cast<float2*>(aux + (int64_t)n * C * kHalf * (kL + kImg) * 2) + (int64_t)c * kHalf * kImg;
+}
+DPS_DEV unsigned char* aux_mask(float* aux, int n, int C, int c) {
+  return reinterpret_cast<unsigned char*>(reinterpret_cast<float2*>(aux + (int64_t)n * C * kHalf * (kL + kImg) * 2) +
+                                          (int64_t)C * kHalf * kImg) + (int64_t)c * kImg * kImg;
+}
+
+// clamp-mask bytes of the fused guidance path (1 = gradient passes): written by the row kernel, read by the last kernel,
+// so that x and ε are read ONCE per step (T/4 bytes each way instead of 2T)
+DPS_DEV unsigned pack_pass4(const float* x, const float* eps, int64_t i, float c1, float c2, int clip) {
+  if (!eps || !clip) return 0x01010101u;
+  const float4 xv = ldg_stream4(x + i), ev = ldg_stream4(eps + i);
+  return (clamp_pass(x0_pre(xv.x, ev.x, c1, c2)) != 0.f ? 1u : 0u) | (clamp_pass(x0_pre(xv.y, ev.y, c1, c2)) != 0.f ? 0x100u : 0u) |
+         (clamp_pass(x0_pre(xv.z, ev.z, c1, c2)) != 0.f ? 0x10000u : 0u) | (clamp_pass(x0_pre(xv.w, ev.w, c1, c2)) != 0.f ? 0x1000000u : 0u);
+}
 
 // ---- K1: row transforms of the 256 image rows, two real rows per complex FFT ---------------------
+template <bool kMaskOut>
 __global__ void __launch_bounds__(kThreads, 4) phase_rows_fwd(const FwdArgs fa, const float2* __restrict__ tw_g, int C) {
   extern __shared__ __align__(16) float smem[];
   constexpr int nfft = kRowsPerCta / 2;
@@ -327,6 +346,7 @@ __global__ void __launch_bounds__(kThreads, 4) phase_rows_fwd(const FwdArgs fa, 
   const float* x = fa.src.x + n * fa.src.x_stride + plane;
   const float* eps = fa.src.eps ? fa.src.eps + n * fa.src.eps_stride + plane : nullptr;
   struct RowPair { float4 re, im; };
+  unsigned* maskw = kMaskOut ? reinterpret_cast<unsigned*>(aux_mask(fa.aux, n, C, c)) : nullptr;
   batched_copy<nfft * (kImg / 4), 2>(
       tid,
       [&](int i) {
@@ -334,6 +354,10 @@ __global__ void __launch_bounds__(kThreads, 4) phase_rows_fwd(const FwdArgs fa, 
         RowPair v;
         v.re = src_load4(x, eps, (int64_t)(r0 + 2 * f) * kImg + q * 4, fa.src.c1, fa.src.c2, fa.src.clip);
         v.im = src_load4(x, eps, (int64_t)(r0 + 2 * f + 1) * kImg + q * 4, fa.src.c1, fa.src.c2, fa.src.clip);
+        if constexpr (kMaskOut) {  // the same loads again hit L1/L2; the mask is the clamp-backward pass bit of each element
+          maskw[((r0 + 2 * f) * kImg + q * 4) >> 2] = pack_pass4(x, eps, (int64_t)(r0 + 2 * f) * kImg + q * 4, fa.src.c1, fa.src.c2, fa.src.clip);
+          maskw[((r0 + 2 * f + 1) * kImg + q * 4) >> 2] = pack_pass4(x, eps, (int64_t)(r0 + 2 * f + 1) * kImg + q * 4, fa.src.c1, fa.src.c2, fa.src.clip);
+        }
         return v;
       },
       [&](int i, const RowPair& v) {
@@ -501,6 +525,133 @@ __global__ void __launch_bounds__(kThreads, 4) phase_cols_fwd(const FwdArgs fa, 
   }
 }
 
+// ---- K2': the column kernel of the fused guidance path -------------------------------------------------------------------
+// Everything between the two column transforms is local to a spectrum column, and with the guidance coefficient deferred
+// to the update kernel nothing global (‖r‖) is needed in between.  So one CTA does, for its 8 columns: column FFT, |F|,
+// residual r = y − |F|/L at both Hermitian-mirrored output positions (Σr², Σ|r| → partial sums; r itself only if asked
+// for), the symmetrised cotangent ½(r(k) + r(−k))·conj(F)/|F| in place, and the second column transform whose rows
+// 64..319 go to the scratch T[row][k2].  The residual (2.25T), the unit phase (2.26T) and one launch of the two-kernel
+// path never touch HBM.
+__global__ void __launch_bounds__(kThreads, 4) phase_cols_fused(const FwdArgs fa, const float2* __restrict__ tw_g, int C) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int nfft = kColsPerCta;
+  PhaseSmem s = carve(smem, nfft);
+  const int tid = threadIdx.x;
+  const int grp = blockIdx.x % kColGroups, c = blockIdx.x / kColGroups, n = blockIdx.y;
+  const int k20 = grp * kColsPerCta;
+  const int ncols = min(kColsPerCta, kHalf - k20);
+  stage_async(reinterpret_cast<float*>(s.tw), reinterpret_cast<const float*>(tw_g), 2 * kTW, tid, kThreads);
+  for (int i = tid; i < nfft * 2 * kPad; i += kThreads) {
+    const int f = i / (2 * kPad), q = i - f * (2 * kPad);
+    s.a[f * kLP + P(q < kPad ? q : kImg + q)] = make_float2(0.f, 0.f);
+  }
+  const float2* rt = aux_scratch(fa.aux, n, C, c);
+  batched_copy<nfft * (kImg / 2), 4>(
+      tid,
+      [&](int i) {
+        const int f = i / (kImg / 2), q = i - f * (kImg / 2);
+        return f < ncols ? *reinterpret_cast<const float4*>(rt + (int64_t)(k20 + f) * kImg + q * 2)
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
+      },
+      [&](int i, const float4& v) {
+        const int f = i / (kImg / 2), q = i - f * (kImg / 2);
+        float2* d = s.a + f * kLP;
+        d[P(kPad + q * 2)] = make_float2(v.x, v.y);
+        d[P(kPad + q * 2 + 1)] = make_float2(v.z, v.w);
+      });
+  stage_wait();
+  __syncthreads();
+  fft384_batch(s.a, s.b, s.tw, nfft);
+  // pass 1 (one column per warp, conflict-free): |F|/L → amp (float plane in s.a), unit phase conj(F)/|F| in place in s.b
+  float* amp = reinterpret_cast<float*>(s.a);  // (nfft, kLF)
+  const float inv_l = 1.0f / (float)kL;
+  {
+    static_assert(kColsPerCta * 32 == kThreads && kL % 32 == 0, "one warp per spectrum column");
+    const int f = tid >> 5, lane = tid & 31;
+    float2* fb = s.b + f * kLP + lane + (lane >> 3);
+    float* ampp = amp + f * kLF + lane;
+#pragma unroll
+    for (int j = 0; j < kL / 32; ++j) {
+      const float2 F = fb[36 * j];
+      const float m2 = fmaf(F.x, F.x, F.y * F.y);
+      float r = rsqrtf(m2);
+      r = fmaf(r, fmaf(-0.5f * m2 * r, r, 0.5f), r);
+      float mag = m2 * r;
+      mag = fmaf(fmaf(-mag, mag, m2), 0.5f * r, mag);
+      const bool nz = m2 > 0.f;
+      const float inv = nz ? r : 0.f;
+      fb[36 * j] = make_float2(F.x * inv, -F.y * inv);
+      ampp[32 * j] = nz ? mag * inv_l : 0.f;
+    }
+  }
+  __syncthreads();
+  // pass 2 (8 consecutive threads = 8 consecutive spectrum columns: 32-byte runs of y): residual at both mirrored output
+  // positions, partial sums, symmetrised cotangent × unit phase written back in place
+  float sq = 0.f, ab = 0.f;
+  {
+    static_assert(kColsPerCta == 8 && kThreads == 256 && kL % 32 == 0, "epilogue mapping");
+    constexpr int kIters = kL / 32, kYB = 4;
+    const int f = tid & 7, kk = tid >> 3;
+    const int k2 = k20 + f;
+    const bool act = f < ncols, mir = act && k2 > 0 && k2 < kL / 2;
+    const int c1 = shift_idx(k2), c2 = shift_idx(k2 ? kL - k2 : 0);
+    const float* y = fa.y ? fa.y + n * fa.y_stride + (int64_t)c * kL * kL : nullptr;
+    float* const outp = fa.out ? fa.out + ((int64_t)n * C + c) * kL * kL : nullptr;
+    const float* ampf = amp + f * kLF;
+    float2* ub = s.b + f * kLP;
+#pragma unroll
+    for (int it0 = 0; it0 < kIters; it0 += kYB) {
+      float y1[kYB], y2[kYB];
+      int o1[kYB], o2[kYB];
+#pragma unroll
+      for (int b = 0; b < kYB; ++b) {
+        const int k1 = kk + 32 * (it0 + b);
+        o1[b] = shift_idx(k1) * kL + c1;
+        o2[b] = shift_idx(k1 ? kL - k1 : 0) * kL + c2;
+        y1[b] = (y && act) ? ldg_ro(y + o1[b]) : 0.f;
+        y2[b] = (y && act) ? ldg_ro(y + o2[b]) : 0.f;
+      }
+#pragma unroll
+      for (int b = 0; b < kYB; ++b) {
+        const int k1 = kk + 32 * (it0 + b);
+        const float a = ampf[k1];
+        const float r1 = y ? __fsub_rn(y1[b], a) : a;
+        const float r2 = y ? __fsub_rn(y2[b], a) : a;
+        if (act) {
+          sq = fmaf(r1, r1, sq);
+          ab += fabsf(r1);
+          if (outp) stg_stream(outp + o1[b], r1);
+        }
+        if (mir) {  // for the self-conjugate columns k2 = 0, 192 the mirrored output is another element of the same column
+          sq = fmaf(r2, r2, sq);
+          ab += fabsf(r2);
+          if (outp) stg_stream(outp + o2[b], r2);
+        }
+        const float gs = act ? 0.5f * (r1 + r2) : 0.f;
+        float2* w = ub + P(k1);
+        const float2 u = *w;
+        *w = make_float2(gs * u.x, gs * u.y);
+      }
+    }
+  }
+  if (fa.partials) {
+    block_sum2(sq, ab, s.red);  // (contains the barriers that also order pass 2 against the transform below)
+    if (tid == 0) {
+      float* pp = fa.partials + ((int64_t)n * (C * kColGroups) + blockIdx.x) * 2;
+      pp[0] = sq;
+      pp[1] = ab;
+    }
+  }
+  __syncthreads();
+  fft384_batch(s.b, s.a, s.tw, nfft);  // second column transform: result in s.a
+  float2* t = aux_scratch2(fa.aux, n, C, c);
+#pragma unroll 4
+  for (int i = tid; i < kImg * kColsPerCta; i += kThreads) {
+    const int row = i / kColsPerCta, f = i - row * kColsPerCta;
+    if (f < ncols) t[(int64_t)row * kHalf + k20 + f] = s.a[f * kLP + P(kPad + row)];
+  }
+}
+
 // ---- A1: H_s[k1][k2] = ½(g[k]+g[−k])·conj(F)/|F|, column transform, keep rows 64..319 ------------
 __global__ void __launch_bounds__(kThreads, 3) phase_cols_adj(const AdjArgs aa, float* __restrict__ aux_rw,
                                                               const float2* __restrict__ tw_g, int C) {
@@ -554,6 +705,7 @@ __global__ void __launch_bounds__(kThreads, 3) phase_cols_adj(const AdjArgs aa, 
 }
 
 // ---- A2: Hermitian row back-transform, two real rows per complex FFT, crop + epilogue ------------
+template <bool kFused>
 __global__ void __launch_bounds__(kThreads, 3) phase_rows_adj(const AdjArgs aa, const float* __restrict__ aux_r,
                                                               const float2* __restrict__ tw_g, int C) {
   extern __shared__ __align__(16) float smem[];
@@ -564,7 +716,8 @@ __global__ void __launch_bounds__(kThreads, 3) phase_rows_adj(const AdjArgs aa, 
   const int grp = blockIdx.x % groups, c = blockIdx.x / groups, n = blockIdx.y;
   const int r0 = grp * kRowsAdj;
   stage_async(reinterpret_cast<float*>(s.tw), reinterpret_cast<const float*>(tw_g), 2 * kTW, tid, kThreads);
-  const float2* t = aux_scratch(const_cast<float*>(aux_r), n, C, c);
+  const float2* t = kFused ? aux_scratch2(const_cast<float*>(aux_r), n, C, c) : aux_scratch(const_cast<float*>(aux_r), n, C, c);
+  const unsigned* maskw = kFused ? reinterpret_cast<const unsigned*>(aux_mask(const_cast<float*>(aux_r), n, C, c)) : nullptr;
   // X[k] = T1[k] + i·T2[k] with T[384−k] = conj(T[k]) for k > 192
   batched_copy<nfft * kL, 8>(
       tid,
@@ -593,7 +746,12 @@ __global__ void __launch_bounds__(kThreads, 3) phase_rows_adj(const AdjArgs aa, 
         const int64_t off = plane + (int64_t)(r0 + rr) * kImg + q * 4;
         Epi v;
         v.e = aa.extra ? ldg_stream4(aa.extra + n * aa.extra_stride + off) : make_float4(0.f, 0.f, 0.f, 0.f);
-        v.pass = mask_load4(aa.mask_src, aa.has_mask, n, off);
+        if constexpr (kFused) {
+          const unsigned m = __ldg(maskw + (((r0 + rr) * kImg + q * 4) >> 2));
+          v.pass = make_float4((m & 0xffu) ? 1.f : 0.f, (m & 0xff00u) ? 1.f : 0.f, (m & 0xff0000u) ? 1.f : 0.f, (m & 0xff000000u) ? 1.f : 0.f);
+        } else {
+          v.pass = mask_load4(aa.mask_src, aa.has_mask, n, off);
+        }
         return v;
       },
       [&](int i, const Epi& v) {
@@ -631,16 +789,20 @@ int phase_create(dps_operator* op, int pad) {
   }
   DPS_CUDA(cudaMalloc(&t->tw, sizeof(float2) * kL));
   DPS_CUDA(cudaMemcpy(t->tw, tw.data(), sizeof(float2) * kL, cudaMemcpyHostToDevice));
-  if (int rc = set_smem((const void*)phase_rows_fwd, smem_bytes(kRowsPerCta / 2))) return rc;
+  if (int rc = set_smem((const void*)phase_rows_fwd<false>, smem_bytes(kRowsPerCta / 2))) return rc;
+  if (int rc = set_smem((const void*)phase_rows_fwd<true>, smem_bytes(kRowsPerCta / 2))) return rc;
+  if (int rc = set_smem((const void*)phase_cols_fused, smem_bytes(kColsPerCta))) return rc;
   if (int rc = set_smem((const void*)phase_cols_fwd<false>, smem_bytes(kColsPerCta))) return rc;
   if (int rc = set_smem((const void*)phase_cols_fwd<true>, smem_bytes(kColsPerCta))) return rc;
   if (int rc = set_smem((const void*)phase_cols_adj, smem_bytes1(kColsAdj))) return rc;
-  if (int rc = set_smem((const void*)phase_rows_adj, smem_bytes1(kRowsAdj / 2))) return rc;
+  if (int rc = set_smem((const void*)phase_rows_adj<false>, smem_bytes1(kRowsAdj / 2))) return rc;
+  if (int rc = set_smem((const void*)phase_rows_adj<true>, smem_bytes1(kRowsAdj / 2))) return rc;
   op->oC = op->C;
   op->oH = op->oW = kL;
   op->P = op->C * kColGroups;
   op->aux_floats = (int64_t)op->C * kHalf * (kL + kImg) * 2;
   op->taps = kL;
+  op->guidance_P = op->C * kColGroups;  // dps_operator_guidance: the three-kernel fused path below
   return DPS_OK;
 }
 
@@ -655,7 +817,7 @@ int phase_forward(const dps_operator* op, const FwdArgs& a, cudaStream_t st) {
   DPS_REQUIRE(a.aux, DPS_ERR_INVALID, "phase retrieval forward needs the aux workspace (%lld floats per particle)",
               (long long)op->aux_floats);
   dim3 g1((unsigned)(op->C * (kImg / kRowsPerCta)), (unsigned)a.n);
-  phase_rows_fwd<<<g1, kThreads, smem_bytes(kRowsPerCta / 2), st>>>(a, op->phase->tw, op->C);
+  phase_rows_fwd<false><<<g1, kThreads, smem_bytes(kRowsPerCta / 2), st>>>(a, op->phase->tw, op->C);
   DPS_LAUNCH_CHECK("phase_rows_fwd");
   dim3 g2((unsigned)(op->C * kColGroups), (unsigned)a.n);
   static const bool lean = getenv("DPSTTC_PHASE_LEAN") && getenv("DPSTTC_PHASE_LEAN")[0] == '1';  // opt-in, see phase_cols_fwd
@@ -674,7 +836,44 @@ int phase_adjoint(const dps_operator* op, const AdjArgs& a, cudaStream_t st) {
   phase_cols_adj<<<g1, kThreads, smem_bytes1(kColsAdj), st>>>(a, aux, op->phase->tw, op->C);
   DPS_LAUNCH_CHECK("phase_cols_adj");
   dim3 g2((unsigned)(op->C * (kImg / kRowsAdj)), (unsigned)a.n);
-  phase_rows_adj<<<g2, kThreads, smem_bytes1(kRowsAdj / 2), st>>>(a, aux, op->phase->tw, op->C);
+  phase_rows_adj<false><<<g2, kThreads, smem_bytes1(kRowsAdj / 2), st>>>(a, aux, op->phase->tw, op->C);
+  DPS_LAUNCH_CHECK("phase_rows_adj");
+  return DPS_OK;
+}
+
+// Fused guidance: residual (kept on chip unless r_out), partial sums and the UNSCALED masked cotangent g = mask ⊙ Jᵀ r in
+// three kernels — rows (+ clamp-mask bytes), columns (both transforms, see phase_cols_fused), rows back.
+int phase_guidance(const dps_operator* op, const dps_source& src, const float* y, int64_t y_stride, float* r_out, float* g,
+                   int64_t g_stride, float* partials, float* aux, int n, cudaStream_t st) {
+  DPS_REQUIRE(aux && y, DPS_ERR_INVALID, "phase retrieval guidance needs the measurement and the aux workspace (%lld floats per particle)",
+              (long long)op->aux_floats);
+  FwdArgs fa;
+  fa.src = src;
+  fa.y = y;
+  fa.y_stride = y_stride;
+  fa.out = r_out;
+  fa.partials = partials;
+  fa.aux = aux;
+  fa.n = n;
+  dim3 g1((unsigned)(op->C * (kImg / kRowsPerCta)), (unsigned)n);
+  phase_rows_fwd<true><<<g1, kThreads, smem_bytes(kRowsPerCta / 2), st>>>(fa, op->phase->tw, op->C);
+  DPS_LAUNCH_CHECK("phase_rows_fwd");
+  dim3 g2((unsigned)(op->C * kColGroups), (unsigned)n);
+  phase_cols_fused<<<g2, kThreads, smem_bytes(kColsPerCta), st>>>(fa, op->phase->tw, op->C);
+  DPS_LAUNCH_CHECK("phase_cols_fused");
+  AdjArgs aa;
+  aa.r = nullptr;
+  aa.coef = nullptr;
+  aa.mask_src = dps_source{};
+  aa.has_mask = 0;
+  aa.extra = nullptr;
+  aa.extra_stride = 0;
+  aa.g = g;
+  aa.g_stride = g_stride;
+  aa.aux = aux;
+  aa.n = n;
+  dim3 g3((unsigned)(op->C * (kImg / kRowsAdj)), (unsigned)n);
+  phase_rows_adj<true><<<g3, kThreads, smem_bytes1(kRowsAdj / 2), st>>>(aa, aux, op->phase->tw, op->C);
   DPS_LAUNCH_CHECK("phase_rows_adj");
   return DPS_OK;
 }

@@ -163,3 +163,43 @@ def test_deferred_step_vs_oracle_and_vs_round1_sequence(op_name, op_cfg, method,
         assert np.abs(img - ref).max() <= 1e-4 * max(1.0, np.abs(ref).max()), f"deferred={deferred}"
         assert np.abs(dist - norm).max() <= 1e-5 * norm.max(), f"deferred={deferred}"
     assert psnr(outs[True][0], outs[False][0]) >= 100.0
+
+
+@pytest.mark.parametrize("n,idx,clip", [(1, 999, True), (4, 500, True), (2, 10, False)])
+def test_fused_phase_guidance_vs_two_kernels_and_oracle(n, idx, clip):
+    """Phase retrieval guidance as rows → fused columns (both transforms, residual and cotangent on chip) → rows, against
+    the forward + adjoint kernels it replaces and against the oracle's |FFT| / Jᵀ restatement."""
+    from dps_ttc_b200 import kernels
+    from dps_ttc_b200.kernels import OperatorPlan
+    plan = OperatorPlan.phase(64, 3, 256, 256, DEV)
+    assert plan.guidance_partials == plan.partials_per_particle > 0
+    k = _consts(idx)
+    gen = torch.Generator(DEV).manual_seed(31 + n)
+    x = torch.randn(n, 3, 256, 256, device=DEV, generator=gen) / k.c1
+    o6 = torch.randn(n, 6, 256, 256, device=DEV, generator=gen) * 0.3 / max(k.c2, 1e-3)
+    eps = o6[:, :3]
+    y = torch.rand(1, 3, 384, 384, device=DEV, generator=gen) * 1.5
+    r2, p2, aux2 = plan.forward(x, eps, k, clip, y, want_partials=True)
+    g2 = torch.zeros(n, 6, 256, 256, device=DEV)
+    plan.adjoint(r2, None, x, eps, k, clip, None, out=g2[:, :3], aux=aux2)
+    g1 = torch.full((n, 6, 256, 256), float("nan"), device=DEV)
+    g1[:, 3:] = 0
+    p1, r1, _ = plan.guidance(x, eps, k, clip, y, out=g1[:, :3], want_r=True)
+    assert torch.isfinite(g1).all()
+    assert float((r1 - r2).abs().max()) <= 1e-6 * max(1.0, float(r2.abs().max()))
+    assert float((g1[:, :3] - g2[:, :3]).abs().max()) <= 2e-5 * max(1.0, float(g2.abs().max()))
+    n1, n2 = kernels.particle_norms(p1, want_l1=True), kernels.particle_norms(p2, want_l1=True)
+    assert float((n1[0] - n2[0]).abs().max()) <= 1e-5 * float(n2[0].max())
+    assert float((n1[1] - n2[1]).abs().max()) <= 1e-5 * float(n2[1].max())
+    if n <= 2:
+        xn, en = x.cpu().numpy(), eps.cpu().numpy()
+        x0, pre = O.x0_from_eps(xn, en, dict(c1=np.float32(k.c1), c2=np.float32(k.c2)), clip)
+        r_ref = y.cpu().numpy() - O.phase_forward(x0, 64)
+        g_ref = O.phase_vjp(x0, r_ref, 64)
+        if clip:
+            g_ref = g_ref * ((pre >= -1) & (pre <= 1))
+        assert np.abs(r1.cpu().numpy() - r_ref).max() <= 2e-5 * max(1.0, np.abs(r_ref).max())
+        assert np.abs(g1[:, :3].cpu().numpy() - g_ref).max() <= 5e-5 * max(1.0, np.abs(g_ref).max())
+    g3 = torch.zeros(n, 3, 256, 256, device=DEV)
+    p3, r3, _ = plan.guidance(x, eps, k, clip, y, out=g3)
+    assert r3 is None and torch.equal(g3, g1[:, :3]) and torch.equal(p3, p1)

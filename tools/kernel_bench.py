@@ -212,6 +212,14 @@ def main():
         us = time_it(lambda i: plan.adjoint(R[i], coef, X[i][:nn], O6[i][:nn, :3], k, True, None, out=G6[i][:nn, :3], aux=AUX[i]),
                      S, a.iters)
         emit("phase_adjoint (3T+M, 2 kernels)", nn * (3 * T + M), us, {"n_particles": nn})
+    if want("phasefused"):
+        nn = min(n, 32)
+        plan = OperatorPlan.phase(64, 3, 256, 256, dev)
+        y = rnd(1, 3, 384, 384).abs()
+        AUX = [plan.new_aux(nn) for _ in range(S)]
+        M = T * 9 // 4
+        us = time_it(lambda i: plan.guidance(X[i][:nn], O6[i][:nn, :3], k, True, y, out=G6[i][:nn, :3], aux=AUX[i]), S, a.iters)
+        emit("phase guidance: rows, fused columns, rows (3 kernels; 3T+M algorithmic)", nn * (3 * T + M), us, {"n_particles": nn})
     if want("gather"):
         ids = torch.randint(0, n, (n,), device=dev)
         us = time_it(lambda i: kernels.gather_particles(X[i], ids, out=OUT[(i + 1) % S]), S, a.iters)
