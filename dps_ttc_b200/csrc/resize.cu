@@ -1346,12 +1346,14 @@ static bool fwd_deep_ring(int64_t ctas, int device) {
   return 3 * ctas <= 2 * (int64_t)sms;
 }
 
-// DPSTTC_RESIZE_FWD_LEAN=1: the lean strip forward (opt-in until it has been validated on a B200, see its header).
+// The lean strip forward / lean W pass are the default since round 2 (gate: bit-identical to the round-1 kernels at N = 3, 8,
+// 12 — profiles/r2a_lean_gate_*.log — and 8.73 → 7.43 µs at N = 8, 19.9 → 17.9 at 32, 50.5 → 48.6 at 128).
+// DPSTTC_RESIZE_FWD_LEAN=0 selects the round-1 kernels again (A/B and tests/test_gpu_variants.py).
 static bool fwd_lean() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("DPSTTC_RESIZE_FWD_LEAN");
-    v = (e && e[0] == '1') ? 1 : 0;
+    v = (e && e[0] == '0') ? 0 : 1;
   }
   return v == 1;
 }
@@ -1468,7 +1470,8 @@ int resize_adjoint(const dps_operator* op, const AdjArgs& a, cudaStream_t st) {
       return narrow ? launch_adj_stream<4>(op, a, st) : launch_adj_stream<kKTMax>(op, a, st);
   }
   if (t.small.strips && small_grid((int64_t)op->C * t.big.strips * a.n)) {
-    static const bool lean = getenv("DPSTTC_RESIZE_ADJ_LEAN") && getenv("DPSTTC_RESIZE_ADJ_LEAN")[0] == '1';  // opt-in, see its header
+    // default since round 2 (bit-identical gate passed; 8.38 → 6.78 µs at N = 8, 22.3 → 18.0 at N = 32); =0: round-1 kernel
+    static const bool lean = !(getenv("DPSTTC_RESIZE_ADJ_LEAN") && getenv("DPSTTC_RESIZE_ADJ_LEAN")[0] == '0');
     const bool masked = a.has_mask && a.mask_src.eps && a.mask_src.clip;
     if (lean && narrow && masked && !a.extra && op->W == 256 && op->H % kRAs == 0 && op->oW == 64 && a.r) {
       DPS_SMEM_OPTIN((resize_adj_lean_kernel), 227 * 1024, op->device);

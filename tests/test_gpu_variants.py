@@ -30,3 +30,18 @@ def test_resize_forward_ring_depths_bit_identical(op, n):
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert "PASS" in res.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("op,n,envs", [
+    ("sr4", 8, ("DPSTTC_RESIZE_FWD_LEAN=0,DPSTTC_RESIZE_ADJ_LEAN=0", "DPSTTC_RESIZE_FWD_LEAN=1,DPSTTC_RESIZE_ADJ_LEAN=1")),
+    ("phase", 3, ("DPSTTC_PHASE_LEAN=0", "DPSTTC_PHASE_LEAN=1")),
+])
+def test_lean_kernels_bit_identical_to_round1_kernels(op, n, envs):
+    """The lean strip forward / short-strip adjoint / phase epilogue (default since round 2) against the round-1 kernels."""
+    cmd = [sys.executable, os.path.join(REPO, "tools", "variant_check.py"), "--op", op, "--n", str(n)]
+    for e in envs:
+        cmd += ["--env", e]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert "PASS" in res.stdout
