@@ -483,6 +483,7 @@ def run_b200(args, rank, world, local_rank):
     e1.record()
     barrier()
     launches = _lib.launch_count()
+    eff_chunk = sampler._chunk_size(model, x_dev)               # particles per UNet forward+VJP pass actually used
     ms = e0.elapsed_time(e1)
     clock_info = clocks.stop()
     spans = kernels.TIMER.summary()
@@ -662,8 +663,7 @@ def run_b200(args, rank, world, local_rank):
                        "guidance_coefficient": "deferred to the update kernel (dps_update_ext): residual+cotangent = " +
                                                ("ONE fused cluster kernel" if plan.guidance_partials > 0 else "forward + adjoint launches") +
                                                ", no coefficient launch",
-                       "unet": model_name, "unet_chunk": sampler._chunk_size(None, x_dev) if sampler.unet_chunk != "auto"
-                       else getattr(sampler, "_auto_chunk", None),
+                       "unet": model_name, "unet_chunk": eff_chunk,
                        "unet_launch": "eager (kernel by kernel)" if args.eager_unet else
                                       "the module's own forward and input-VJP kernels replayed from two CUDA graphs "
                                       "(dps_ttc_b200/graphed.py; same kernels, same order)",

@@ -60,6 +60,7 @@ int dps_operator_create_inpainting(const float* mask_host, int C, int H, int W, 
     return fail(out, DPS_ERR_CUDA);
   }
   op->P = inpaint_partials(C, H, W);
+  op->guidance_P = op->P;  // dps_operator_guidance: one streaming kernel (inpaint_guidance)
   return DPS_OK;
 }
 
@@ -196,6 +197,17 @@ int dps_operator_guidance(const dps_operator* op, const dps_source* src, const f
                     src->x_stride % 4 == 0 && (!src->eps || src->eps_stride % 4 == 0) && y_stride % 4 == 0 && g_stride % 4 == 0,
                 DPS_ERR_ALIGN, "dps_operator_guidance: tensors must be 16-byte aligned, strides multiples of 4");
     if (op->kind == DPS_OP_RESIZE) return resize_fused_guidance(op, *src, y, y_stride, r_out, g, g_stride, partials, n, (cudaStream_t)stream);
+    if (op->kind == DPS_OP_INPAINT && src->eps && y) {
+      FwdArgs fa;
+      fa.src = *src;
+      fa.y = y;
+      fa.y_stride = y_stride;
+      fa.out = r_out;
+      fa.partials = partials;
+      fa.aux = nullptr;
+      fa.n = n;
+      return inpaint_guidance(op, fa, g, g_stride, (cudaStream_t)stream);
+    }
     if (op->kind == DPS_OP_PHASE && src->eps)
       return phase_guidance(op, *src, y, y_stride, r_out, g, g_stride, partials, aux, n, (cudaStream_t)stream);
   }

@@ -112,6 +112,7 @@ DPS_DEV float2 x0_pair_bounds(float2 x, float2 e, float c1, float c2, float lo, 
 // per-operator launchers (each returns DPS_OK / error)
 int inpaint_forward(const dps_operator* op, const FwdArgs& a, cudaStream_t st);
 int inpaint_adjoint(const dps_operator* op, const AdjArgs& a, cudaStream_t st);
+int inpaint_guidance(const dps_operator* op, const FwdArgs& a, float* g, int64_t g_stride, cudaStream_t st);
 
 int sep_create(dps_operator* op, const float* taps1d_v, const float* taps1d_h, int rv, int rh);
 void sep_destroy(dps_operator* op);

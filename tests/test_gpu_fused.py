@@ -203,3 +203,29 @@ def test_fused_phase_guidance_vs_two_kernels_and_oracle(n, idx, clip):
     g3 = torch.zeros(n, 3, 256, 256, device=DEV)
     p3, r3, _ = plan.guidance(x, eps, k, clip, y, out=g3)
     assert r3 is None and torch.equal(g3, g1[:, :3]) and torch.equal(p3, p1)
+
+
+@pytest.mark.parametrize("n,idx,clip", [(1, 999, True), (5, 500, True), (3, 10, False)])
+def test_fused_inpainting_guidance_vs_two_kernels(n, idx, clip):
+    from dps_ttc_b200 import kernels
+    from dps_ttc_b200.kernels import OperatorPlan
+    rng = np.random.default_rng(5)
+    mask = (rng.random((256, 256)) > 0.4).astype(np.float32)
+    plan = OperatorPlan.inpainting(mask, 3, 256, 256, DEV)
+    assert plan.guidance_partials == plan.partials_per_particle > 0
+    k = _consts(idx)
+    gen = torch.Generator(DEV).manual_seed(77 + n)
+    x = torch.randn(n, 3, 256, 256, device=DEV, generator=gen) / k.c1
+    o6 = torch.randn(n, 6, 256, 256, device=DEV, generator=gen) * 0.3 / max(k.c2, 1e-3)
+    eps = o6[:, :3]
+    y = torch.randn(1, 3, 256, 256, device=DEV, generator=gen)
+    r2, p2, _ = plan.forward(x, eps, k, clip, y, want_partials=True)
+    g2 = torch.zeros(n, 6, 256, 256, device=DEV)
+    plan.adjoint(r2, None, x, eps, k, clip, None, out=g2[:, :3])
+    g1 = torch.full((n, 6, 256, 256), float("nan"), device=DEV)
+    p1, r1, _ = plan.guidance(x, eps, k, clip, y, out=g1[:, :3], want_r=True)
+    assert torch.equal(r1, r2) and torch.equal(p1, p2)                     # same arithmetic, same reduction tree
+    assert torch.equal(g1[:, :3], g2[:, :3])
+    g3 = torch.zeros(n, 3, 256, 256, device=DEV)
+    p3, r3, _ = plan.guidance(x, eps, k, clip, y, out=g3)
+    assert r3 is None and torch.equal(g3, g2[:, :3]) and torch.equal(p3, p2)

@@ -212,6 +212,11 @@ def main():
         us = time_it(lambda i: plan.adjoint(R[i], coef, X[i][:nn], O6[i][:nn, :3], k, True, None, out=G6[i][:nn, :3], aux=AUX[i]),
                      S, a.iters)
         emit("phase_adjoint (3T+M, 2 kernels)", nn * (3 * T + M), us, {"n_particles": nn})
+    if want("inpaintfused"):
+        plan_i = OperatorPlan.inpainting(mask, 3, 256, 256, dev)
+        yi = rnd(1, 3, 256, 256)
+        us = time_it(lambda i: plan_i.guidance(X[i], O6[i][:, :3], k, True, yi, out=G6[i][:, :3]), S, a.iters)
+        emit("inpaint guidance: residual + cotangent in one streaming kernel (3T+M)", n * (3 * T) + T, us)
     if want("phasefused"):
         nn = min(n, 32)
         plan = OperatorPlan.phase(64, 3, 256, 256, dev)
