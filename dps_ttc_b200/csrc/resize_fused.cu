@@ -65,7 +65,7 @@ struct Geo {
 
 template <int F>
 size_t fused_smem() {
-  return sizeof(float) * ((size_t)2 * kRI * kW + (size_t)kRI * 4 + 64) + 8 * kChunks;
+  return sizeof(float) * ((size_t)2 * kRI * kW + (size_t)2 * kRI * 4 + 64) + 8 * kChunks;  // x, ε | Ah2 (float2) | red | barriers
 }
 
 DPS_DEV void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
