@@ -65,7 +65,7 @@ struct Geo {
 
 template <int F>
 size_t fused_smem() {
-  return sizeof(float) * ((size_t)2 * kRI * kW + (size_t)2 * kRI * 4 + 64) + 8 * kChunks;  // x, ε | Ah2 (float2) | red | barriers
+  return sizeof(float) * ((size_t)2 * kRI * kW + (size_t)kRI * 4 + 64) + 8 * kChunks;
 }
 
 DPS_DEV void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
@@ -74,24 +74,21 @@ DPS_DEV void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned
 template <int F>
 __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kT, 3) resize_guidance_kernel(const __grid_constant__ FusedArgs a) {
   using G = Geo<F>;
-  constexpr int TAPS = G::TAPS, HALO = G::HALO, RJ = G::RJ, OW = G::OW, PADW = G::PADW, H = kRI * kCluster;
-  constexpr int RJH = RJ / 2, RIH = kRI / 2, RUH = RJH + 4;  // per row-half: residual rows, image rows, u rows
-  static_assert(RJ % 2 == 0 && HALO % 2 == 0, "column pairs / row halves");
-  static_assert((size_t)RJ * PADW + (size_t)2 * RJ * OW <= (size_t)kRI * kW, "tile + residual rows fit into the dead ε buffer");
+  constexpr int TAPS = G::TAPS, HALO = G::HALO, RJ = G::RJ, OW = G::OW, RU = G::RU, PADW = G::PADW, H = kRI * kCluster;
+  static_assert((size_t)RJ * PADW + (size_t)RJ * OW <= (size_t)kRI * kW, "tile + residual rows fit into the dead ε buffer");
   extern __shared__ __align__(16) float smem[];
   float* Sx = smem;                       // (32, 256)  x → x̂₀ (clamped)
-  float* Se = Sx + kRI * kW;              // (32, 256)  ε; dead after step 0 → St, Sr2
+  float* Se = Sx + kRI * kW;              // (32, 256)  ε; dead after step 0 → St, Sr
   float* St = Se;                         // (RJ, PADW) H-pass result, column-padded by mirroring
-  float2* Sr2 = reinterpret_cast<float2*>(St + RJ * PADW);  // (RJ, OW) residual rows of this CTA, each value duplicated (r, r)
-  float2* Ah2 = reinterpret_cast<float2*>(Se + kRI * kW);   // (32, 4)  transposed H band of my image rows, duplicated (w, w)
-  float* red = reinterpret_cast<float*>(Ah2 + kRI * 4);     // 64
-  uint64_t* bar = reinterpret_cast<uint64_t*>(red + 64);    // kChunks barriers
+  float* Sr = St + RJ * PADW;             // (RJ, OW)   residual rows of this CTA
+  float* Ah = Se + kRI * kW;              // (32, 4)    transposed H band of my image rows
+  float* red = Ah + kRI * 4;              // 64
+  uint64_t* bar = reinterpret_cast<uint64_t*>(red + 64);  // kChunks barriers
 
   cg::cluster_group cluster = cg::this_cluster();
   const int q = (int)cluster.block_rank();
   const int plane = blockIdx.x / kCluster, c = plane % a.C, n = plane / a.C;
   const int tid = threadIdx.x;
-  const int p = tid & 127, h = tid >> 7;  // column pair (columns 2p, 2p+1) and row half; a warp has one h
   const int64_t poff = (int64_t)c * H * kW + (int64_t)q * kRI * kW;
   const float* xg = a.src.x + n * a.src.x_stride + poff;
   const float* eg = a.src.eps + n * a.src.eps_stride + poff;
@@ -112,25 +109,8 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kT, 3) resize
     }
   }
   // tables and measurement values while the rows are in flight
-  if (tid < kRI * 4) {
-    const float v = __ldg(a.at_h + (size_t)q * kRI * 4 + tid);
-    Ah2[tid] = make_float2(v, v);
-  }
-  // transposed W band of my two columns as 5 weight pairs over the residual columns lmin … lmin+4
-  int lmin;
-  float2 aw2[5];
-  {
-    const float4 w0 = __ldg(reinterpret_cast<const float4*>(a.at_w) + 2 * p), w1 = __ldg(reinterpret_cast<const float4*>(a.at_w) + 2 * p + 1);
-    const int n0 = 2 * p + HALO - TAPS + 1, n1 = n0 + 1;
-    const int l0 = n0 >= 0 ? (n0 + F - 1) / F : -((-n0) / F), l1 = n1 >= 0 ? (n1 + F - 1) / F : -((-n1) / F);
-    lmin = l0;
-    const bool sh = l1 != l0;  // the odd column starts one residual column later
-    aw2[0] = make_float2(w0.x, sh ? 0.f : w1.x);
-    aw2[1] = make_float2(w0.y, sh ? w1.x : w1.y);
-    aw2[2] = make_float2(w0.z, sh ? w1.y : w1.z);
-    aw2[3] = make_float2(w0.w, sh ? w1.z : w1.w);
-    aw2[4] = make_float2(0.f, sh ? w1.w : 0.f);
-  }
+  stage_async(Ah, a.at_h + (size_t)q * kRI * 4, kRI * 4, tid, kT);
+  const float4 aw = __ldg(reinterpret_cast<const float4*>(a.at_w) + tid);  // my column's transposed W band
   constexpr int kRP = (RJ * OW + kT - 1) / kT;  // residual values per thread in the W pass
   float yv[kRP];
   const float* yp = a.y ? a.y + n * a.y_stride + (int64_t)c * (H / F) * OW + (int64_t)q * RJ * OW : nullptr;
@@ -139,56 +119,54 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kT, 3) resize
     const int o = tid + u * kT;
     yv[u] = (yp && o < RJ * OW) ? ldg_ro(yp + o) : 0.f;
   }
-  // ---- 0. x̂₀ in place for my column pair and row half, chunk by chunk as the copies land; clamp mask → one register ----
-  unsigned pass_bits = 0;  // bit 2·rr + e: row 16h + rr, column 2p + e
+  stage_wait();
+  // ---- 0. x̂₀ in place, chunk by chunk as the copies land; clamp mask of my column → one register ----
+  unsigned pass_bits = 0;
   {
     const float lo = a.src.clip ? -1.0f : -INFINITY, hi = a.src.clip ? 1.0f : INFINITY;
-    constexpr int kChunksPerHalf = kChunks / 2;
 #pragma unroll
-    for (int chh = 0; chh < kChunksPerHalf; ++chh) {
-      mbar_wait(bar + h * kChunksPerHalf + chh, 0);
+    for (int ch = 0; ch < kChunks; ++ch) {
+      mbar_wait(bar + ch, 0);
 #pragma unroll
-      for (int r8 = 0; r8 < kChunkRows; ++r8) {
-        const int rr = chh * kChunkRows + r8, r = h * RIH + rr;
-        float2* xs = reinterpret_cast<float2*>(Sx + r * kW) + p;
-        const float2 pre = x0_pair_pre(*xs, reinterpret_cast<const float2*>(Se + r * kW)[p], a.src.c1, a.src.c2);
-        *xs = make_float2(fminf(fmaxf(pre.x, lo), hi), fminf(fmaxf(pre.y, lo), hi));
-        pass_bits |= ((pre.x >= lo && pre.x <= hi) ? (1u << (2 * rr)) : 0u) | ((pre.y >= lo && pre.y <= hi) ? (2u << (2 * rr)) : 0u);
+      for (int rr = 0; rr < kChunkRows; ++rr) {
+        const int r = ch * kChunkRows + rr;
+        const float pre = x0_pre(Sx[r * kW + tid], Se[r * kW + tid], a.src.c1, a.src.c2);
+        Sx[r * kW + tid] = fminf(fmaxf(pre, lo), hi);
+        pass_bits |= (pre >= lo && pre <= hi) ? (1u << r) : 0u;
       }
     }
   }
   cluster.sync();  // every CTA's x̂₀ rows are in place (and nobody reads the ε buffer any more)
 
-  // ---- 1. H pass for my RJH residual rows: t[jj][cols] = Σ_k w[k] · x̂₀[sym(F·(RJ·q + jj) − HALO + k)][cols] ----
+  // ---- 1. H pass: t[jj][col] = Σ_k w[k] · x̂₀[sym(F·(RJ·q + jj) − HALO + k)][col] ----
   {
     const float* up = q > 0 ? cluster.map_shared_rank(Sx, q - 1) : Sx;
     const float* dn = q < kCluster - 1 ? cluster.map_shared_rank(Sx, q + 1) : Sx;
-    float2 acc[RJH];
+    float acc[RJ];
 #pragma unroll
-    for (int jl = 0; jl < RJH; ++jl) acc[jl] = make_float2(0.f, 0.f);
+    for (int jj = 0; jj < RJ; ++jj) acc[jj] = 0.f;
 #pragma unroll
-    for (int ww = 0; ww < F * (RJH - 1) + TAPS; ++ww) {
-      const int lr = F * RJH * h + ww - HALO;  // image row relative to my CTA's first row (warp-uniform)
-      const float* rowp;
+    for (int wdx = 0; wdx < kRI + 2 * HALO; ++wdx) {
+      const int lr = wdx - HALO;  // row relative to my first image row
+      float v;
       if (lr < 0)  // above my rows: the neighbour's last rows, or (top of the image) my own rows mirrored: −1 ↦ 0, −2 ↦ 1 …
-        rowp = q > 0 ? up + (kRI + lr) * kW : Sx + (-lr - 1) * kW;
+        v = q > 0 ? up[(kRI + lr) * kW + tid] : Sx[(-lr - 1) * kW + tid];
       else if (lr >= kRI)
-        rowp = q < kCluster - 1 ? dn + (lr - kRI) * kW : Sx + (2 * kRI - 1 - lr) * kW;
+        v = q < kCluster - 1 ? dn[(lr - kRI) * kW + tid] : Sx[(2 * kRI - 1 - lr) * kW + tid];
       else
-        rowp = Sx + lr * kW;
-      const float2 v = reinterpret_cast<const float2*>(rowp)[p];
+        v = Sx[lr * kW + tid];
 #pragma unroll
-      for (int jl = 0; jl < RJH; ++jl) {
-        const int k = ww - F * jl;  // compile-time after unrolling
-        if (k >= 0 && k < TAPS) acc[jl] = __ffma2_rn(make_float2(a.w[k], a.w[k]), v, acc[jl]);
+      for (int jj = 0; jj < RJ; ++jj) {
+        const int k = wdx - F * jj;  // compile-time after unrolling
+        if (k >= 0 && k < TAPS) acc[jj] = fmaf(a.w[k], v, acc[jj]);
       }
     }
 #pragma unroll
-    for (int jl = 0; jl < RJH; ++jl) {
-      float* row = St + (RJH * h + jl) * PADW + HALO;
-      reinterpret_cast<float2*>(row)[p] = acc[jl];
-      if (2 * p < HALO) { row[-1 - 2 * p] = acc[jl].x; row[-2 - 2 * p] = acc[jl].y; }             // columns −1, −2, … mirror 0, 1, …
-      if (2 * p >= kW - HALO) { row[2 * kW - 1 - 2 * p] = acc[jl].x; row[2 * kW - 2 - 2 * p] = acc[jl].y; }  // 256, 257, … mirror 255, 254, …
+    for (int jj = 0; jj < RJ; ++jj) {
+      float* row = St + jj * PADW + HALO;
+      row[tid] = acc[jj];
+      if (tid < HALO) row[-1 - tid] = acc[jj];                   // columns −1, −2, … mirror columns 0, 1, …
+      if (tid >= kW - HALO) row[2 * kW - 1 - tid] = acc[jj];     // columns 256, 257, … mirror 255, 254, …
     }
   }
   __syncthreads();
@@ -211,13 +189,13 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kT, 3) resize
         acc = fmaf(a.w[4 * m + 3], t4.w, acc);
       }
       const float res = yp ? yv[u] - acc : acc;
-      Sr2[o] = make_float2(res, res);
+      Sr[o] = res;
       if (a.r_out) a.r_out[((int64_t)n * a.C + c) * (H / F) * OW + (int64_t)q * RJ * OW + o] = res;
       sq = fmaf(res, res, sq);
       ab += fabsf(res);
     }
   }
-  __syncthreads();   // my residual rows are complete …
+  __syncthreads();  // my residual rows are complete …
   cluster_arrive();  // … and announced; the partial sums below overlap the other CTAs' arrival
   if (a.partials) {
     block_sum2(sq, ab, red);
@@ -227,47 +205,42 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kT, 3) resize
       pp[1] = ab;
     }
   }
-  // ---- 3. Aᵀ for my column pair and row half: u[m] = Σ_d aw2[d] · r[RJ·q − 2 + RJH·h + m][lmin + d],  m < RUH,
-  //         then g[16h + il] = mask · Σ_d Ah[16h + il][d] · u[m0(il) + d] ----
+  // ---- 3. Aᵀ: u[m][col] = Σ_d aw[d] · r[RJ·q − 2 + m][l0(col) + d],  then g[ii][col] = mask · Σ_d Ah[ii][d] · u[m0(ii) + d] ----
   {
-    int li[5];
+    // first residual column that touches image column `tid`:  ceil((tid + HALO − TAPS + 1)/F)
+    const int num = tid + HALO - TAPS + 1;
+    const int lfirst = num >= 0 ? (num + F - 1) / F : -((-num) / F);
+    const float awv[4] = {aw.x, aw.y, aw.z, aw.w};
+    float uu[RU];
+    auto urow = [&](const float* rr) {
+      float s = 0.f;
 #pragma unroll
-    for (int d = 0; d < 5; ++d) li[d] = min(max(lmin + d, 0), OW - 1);  // out-of-range columns carry zero weights
-    float2 uu[RUH];
-    auto urow = [&](const float2* rr) {
-      float2 s2 = make_float2(0.f, 0.f);
-#pragma unroll
-      for (int d = 0; d < 5; ++d) s2 = __ffma2_rn(aw2[d], rr[li[d]], s2);
-      return s2;
+      for (int d = 0; d < 4; ++d) {
+        const int l = lfirst + d;
+        if (l >= 0 && l < OW) s = fmaf(awv[d], rr[l], s);
+      }
+      return s;
     };
-    // residual row of u-slot m, relative to my CTA's first residual row: jr = RJH·h + m − 2 ∈ [−2, RJ + 2)
-    bool remote[RUH];
 #pragma unroll
-    for (int m = 0; m < RUH; ++m) {
-      const int jr = RJH * h + m - 2;
-      remote[m] = jr < 0 || jr >= RJ;
-      uu[m] = remote[m] ? make_float2(0.f, 0.f) : urow(Sr2 + jr * OW);  // my own rows first
-    }
-    cluster_wait();  // every CTA's residual rows are in place
-    const float2* rup = q > 0 ? cluster.map_shared_rank(Sr2, q - 1) : Sr2;
-    const float2* rdn = q < kCluster - 1 ? cluster.map_shared_rank(Sr2, q + 1) : Sr2;
+    for (int m = 2; m < RJ + 2; ++m) uu[m] = urow(Sr + (m - 2) * OW);  // my own rows first
+    cluster_wait();                                                       // every CTA's residual rows are in place
+    const float* rup = q > 0 ? cluster.map_shared_rank(Sr, q - 1) : Sr;
+    const float* rdn = q < kCluster - 1 ? cluster.map_shared_rank(Sr, q + 1) : Sr;
 #pragma unroll
-    for (int m = 0; m < RUH; ++m) {
-      const int jr = RJH * h + m - 2;
-      if (jr < 0 && q > 0) uu[m] = urow(rup + (RJ + jr) * OW);              // residual rows outside the image do not exist
-      if (jr >= RJ && q < kCluster - 1) uu[m] = urow(rdn + (jr - RJ) * OW);
+    for (int m = 0; m < 2; ++m) {
+      uu[m] = q > 0 ? urow(rup + (RJ - 2 + m) * OW) : 0.f;                       // residual rows above the image do not exist
+      uu[RJ + 2 + m] = q < kCluster - 1 ? urow(rdn + m * OW) : 0.f;
     }
     cluster_arrive();  // my remote reads are done: the neighbours may exit once everybody has said so
-    float* gp = a.g + n * a.g_stride + poff + (int64_t)h * RIH * kW;
+    float* gp = a.g + n * a.g_stride + poff;
 #pragma unroll
-    for (int il = 0; il < RIH; ++il) {
-      const int m0 = G::j0(il) + 2;  // first u-slot that touches image row 16h + il (compile-time: F·RJH = 16 rows per half)
-      float2 s2 = make_float2(0.f, 0.f);
+    for (int ii = 0; ii < kRI; ++ii) {
+      const int m0 = G::j0(ii) + 2;  // first residual row, relative to RJ·q − 2, that touches image row ii (compile-time)
+      float s = 0.f;
 #pragma unroll
       for (int d = 0; d < 4; ++d)
-        if (m0 + d >= 0 && m0 + d < RUH) s2 = __ffma2_rn(Ah2[(h * RIH + il) * 4 + d], uu[m0 + d], s2);
-      const unsigned b = pass_bits >> (2 * il);
-      stg_stream2(gp + il * kW + 2 * p, make_float2((b & 1u) ? s2.x : 0.f, (b & 2u) ? s2.y : 0.f));
+        if (m0 + d >= 0 && m0 + d < RU) s = fmaf(Ah[ii * 4 + d], uu[m0 + d], s);
+      stg_stream(gp + ii * kW + tid, ((pass_bits >> ii) & 1u) ? s : 0.f);
     }
     cluster_wait();
   }
