@@ -545,7 +545,8 @@ def run_b200(args, rank, world, local_rank):
 
     # ---------------- sharded == unsharded? (all ranks take part; rank 0 re-runs the loop unsharded) ----------------
     verify = None
-    if searching and world > 1 and not args.no_extras:
+    if searching and world > 1 and not args.no_extras and n * world <= 64:
+        # (rank 0 re-runs all N particles alone: bounded to N ≤ 64 so that the default run stays within minutes)
         verify = verify_sharded(args, wl, model, cond_fn, y_dev, device, rank, world, n, loop)
     same_1gpu = None
     if searching and world > 1 and not args.no_extras:
