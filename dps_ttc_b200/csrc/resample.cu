@@ -275,7 +275,8 @@ __global__ void __launch_bounds__(kCopyThreads) gather_p2p_sync_kernel(const flo
 #pragma unroll
   for (int u = 0; u < kCopyVec; ++u) {
     const int64_t j = base + (int64_t)u * kCopyThreads;
-    if (j < elems4) v[u] = ld_relaxed_sys4(s + j);
+    if (j < elems4) v[u] = s[j];  // plain ld.global after the acquire above: this kernel has not touched these lines before
+                                  // (L1 is empty of them) and peer memory is not cached in the local L2
   }
 #pragma unroll
   for (int u = 0; u < kCopyVec; ++u) {
