@@ -221,84 +221,6 @@ __global__ void __launch_bounds__(kThreads) resize_fwd_kernel(const FwdTables t,
   fwd_wpass(m, t, C, W, oH, oW, strip, c, n, tid, kThreads, a, ypre, blockIdx.x);
 }
 
-// Pair variant for W = 256: 128 column pairs × kParts row groups.  64-bit loads, x̂₀ and the accumulation on
-// packed FFMA2 — half the load and FMA instructions of the scalar kernel.  The row-group partial sums are combined
-// through shared memory in a fixed order.  kParts = 2 (256 threads, two load batches per thread, 3 CTAs per SM) was
-// the fastest split at every particle count measured (a 4-way split with one batch per thread lost 15-25 %).
-template <int kParts>
-__global__ void __launch_bounds__(128 * kParts, 3) resize_fwd_pair_kernel(const FwdTables t, int C, int H, int oH, int oW,
-                                                                       const FwdArgs a) {
-  constexpr int W = 256, W2 = 128, kBatch = 12, kT = 128 * kParts;
-  extern __shared__ __align__(128) float smem[];
-  const FwdSmem m = fwd_carve(smem, t, kParts, W, oW);
-  const int strip = blockIdx.x % t.fstrips;
-  const int c = blockIdx.x / t.fstrips;
-  const int n = blockIdx.y;
-  const int tid = threadIdx.x;
-  const int rmin = t.rows.lo[strip], rcnt = t.rows.cnt[strip];
-  const int part = tid >> 7, cp = tid & 127;
-  const int hrows = (rcnt + kParts - 1) / kParts;  // rows per group
-  const int rr_lo = part * hrows, rr_hi = min(rcnt, rr_lo + hrows);
-  const int64_t plane = (int64_t)c * H * W;
-  const float2* x2 = reinterpret_cast<const float2*>(a.src.x + n * a.src.x_stride + plane);
-  const float2* e2 = a.src.eps ? reinterpret_cast<const float2*>(a.src.eps + n * a.src.eps_stride + plane) : nullptr;
-  // the first batch of loads goes out before the tables are staged
-  float2 xv[kBatch], ev[kBatch];
-#pragma unroll
-  for (int b = 0; b < kBatch; ++b) {
-    const int rr = max(0, min(rr_lo + b, rr_hi - 1));
-    xv[b] = ldg_stream2(x2 + (rmin + rr) * W2 + cp);
-    ev[b] = e2 ? ldg_stream2(e2 + (rmin + rr) * W2 + cp) : make_float2(0.f, 0.f);
-  }
-  fwd_stage(m, t, strip, rcnt, oW, tid, kT);
-  const YPre ypre = fwd_y_prefetch(oH, oW, strip, c, n, tid, kT, a);
-  stage_wait();
-  __syncthreads();
-  float2 acc[kRO];
-#pragma unroll
-  for (int j = 0; j < kRO; ++j) acc[j] = make_float2(0.f, 0.f);
-#pragma unroll 1
-  for (int rr0 = rr_lo; rr0 < rr_hi; rr0 += kBatch) {
-    if (rr0 != rr_lo) {
-#pragma unroll
-      for (int b = 0; b < kBatch; ++b) {
-        const int rr = rr0 + b < rr_hi ? rr0 + b : rr_hi - 1;
-        xv[b] = ldg_stream2(x2 + (rmin + rr) * W2 + cp);
-        ev[b] = e2 ? ldg_stream2(e2 + (rmin + rr) * W2 + cp) : make_float2(0.f, 0.f);
-      }
-    }
-#pragma unroll
-    for (int b = 0; b < kBatch; ++b) {
-      if (rr0 + b < rr_hi) {
-        const float2 v = e2 ? x0_pair(xv[b], ev[b], a.src.c1, a.src.c2, a.src.clip) : xv[b];
-        const float4 w0 = *reinterpret_cast<const float4*>(m.dh + (rr0 + b) * kRO);
-        const float4 w1 = *reinterpret_cast<const float4*>(m.dh + (rr0 + b) * kRO + 4);
-        acc[0] = __ffma2_rn(make_float2(w0.x, w0.x), v, acc[0]); acc[1] = __ffma2_rn(make_float2(w0.y, w0.y), v, acc[1]);
-        acc[2] = __ffma2_rn(make_float2(w0.z, w0.z), v, acc[2]); acc[3] = __ffma2_rn(make_float2(w0.w, w0.w), v, acc[3]);
-        acc[4] = __ffma2_rn(make_float2(w1.x, w1.x), v, acc[4]); acc[5] = __ffma2_rn(make_float2(w1.y, w1.y), v, acc[5]);
-        acc[6] = __ffma2_rn(make_float2(w1.z, w1.z), v, acc[6]); acc[7] = __ffma2_rn(make_float2(w1.w, w1.w), v, acc[7]);
-      }
-    }
-  }
-  {
-    float* dstp = m.V + part * kRO * W;
-#pragma unroll
-    for (int j = 0; j < kRO; ++j) *reinterpret_cast<float2*>(dstp + j * W + 2 * cp) = acc[j];
-  }
-  __syncthreads();
-  for (int i = tid; i < kRO * W / 4; i += kT) {  // V[0] += V[1] (+ V[2] + V[3]), fixed order
-    float4 s0 = *reinterpret_cast<const float4*>(m.V + i * 4);
-#pragma unroll
-    for (int q = 1; q < kParts; ++q) {
-      const float4 s1 = *reinterpret_cast<const float4*>(m.V + q * kRO * W + i * 4);
-      s0.x += s1.x; s0.y += s1.y; s0.z += s1.z; s0.w += s1.w;
-    }
-    *reinterpret_cast<float4*>(m.V + i * 4) = s0;
-  }
-  __syncthreads();
-  fwd_wpass(m, t, C, W, oH, oW, strip, c, n, tid, kT, a, ypre, blockIdx.x);
-}
-
 // Bulk-copy variant for W = 256 (the default): the strip's input window is fetched by the TMA engine — 1-D bulk copies
 // of 8 image rows (8 KB per tensor, contiguous in a plane) into a 3-stage shared-memory ring, completion on mbarriers —
 // so 48 KB per CTA (144 KB per SM at 3 CTAs) are in flight without holding a register, and the threads only ever wait
@@ -1361,7 +1283,6 @@ static bool fwd_lean() {
 int resize_forward(const dps_operator* op, const FwdArgs& a, cudaStream_t st) {
   const FwdTables& f = op->resize->f;
   DPS_SMEM_OPTIN((resize_fwd_kernel), 227 * 1024, op->device);
-  DPS_SMEM_OPTIN((resize_fwd_pair_kernel<2>), 227 * 1024, op->device);
   DPS_SMEM_OPTIN((resize_fwd_bulk_kernel<kStagesStd>), 227 * 1024, op->device);
   DPS_SMEM_OPTIN((resize_fwd_bulk_kernel<kStagesDeep>), 227 * 1024, op->device);
   {  // streaming variant once the strip grid would fill the machine several times over
@@ -1394,10 +1315,7 @@ int resize_forward(const dps_operator* op, const FwdArgs& a, cudaStream_t st) {
   }
   dim3 grid((unsigned)(op->C * f.fstrips), (unsigned)a.n);
   if (op->W == 256) {
-    static const bool pair_path = getenv("DPSTTC_RESIZE_FWD") && getenv("DPSTTC_RESIZE_FWD")[0] == 'p';  // A/B aid
-    if (pair_path)
-      resize_fwd_pair_kernel<2><<<grid, 256, fwd_smem(f, 2, 256, op->oW), st>>>(f, op->C, op->H, op->oH, op->oW, a);
-    else if (fwd_lean() && a.src.eps && a.src.clip && op->oW == 64 && f.kw == 16 && a.n > 0) {
+    if (fwd_lean() && a.src.eps && a.src.clip && op->oW == 64 && f.kw == 16 && a.n > 0) {
       DPS_SMEM_OPTIN((resize_fwd_lean_kernel<kStagesStd, 16>), 227 * 1024, op->device);
       DPS_SMEM_OPTIN((resize_fwd_lean_kernel<kStagesDeep, 16>), 227 * 1024, op->device);
       if (fwd_deep_ring((int64_t)grid.x * grid.y, op->device))
@@ -1427,9 +1345,8 @@ static int launch_adj(const dps_operator* op, const AdjStrips& strips, const Adj
   dim3 grid((unsigned)(op->C * strips.strips), (unsigned)a.n);
   const size_t base = adj_smem(RA, KJ, op->oW, t.cols.kt, op->W);
   const size_t bulk = base + sizeof(float) * (32 + (size_t)2 * RA * op->W);
-  static const bool no_bulk = getenv("DPSTTC_RESIZE_ADJ") && getenv("DPSTTC_RESIZE_ADJ")[0] == 'r';  // A/B aid: "regs"
   // bulk copies need 16-byte rows and a tile that still leaves 3 CTAs per SM
-  if (!no_bulk && op->W % 4 == 0 && bulk <= 75 * 1024)
+  if (op->W % 4 == 0 && bulk <= 75 * 1024)
     resize_adj_kernel<RA, KJ, KT, true><<<grid, kThreads, bulk, st>>>(strips, t.cols, op->C, op->H, op->W, op->oH,
                                                                       op->oW, a);
   else
