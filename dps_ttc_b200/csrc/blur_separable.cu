@@ -772,7 +772,7 @@ int sep_create(dps_operator* op, const float* taps1d_v, const float* taps1d_h, i
   if (int rc = build_set(wv, rv, op->H, wh, rh, op->W, R, true, &t->adj)) return rc;
   op->P = op->C * ((op->H + kRows - 1) / kRows);
   op->taps = 2 * r + 1;
-  return DPS_OK;
+  return sep_fused_create(op, taps1d_v, rv, taps1d_h, rh);  // fused residual + cotangent kernel where the shape allows
 }
 
 void sep_destroy(dps_operator* op) {

@@ -135,6 +135,7 @@ void dps_operator_destroy(dps_operator* op) {
   if (cur != op->device) cudaSetDevice(op->device);
   cudaFree(op->mask_dev);
   sep_destroy(op);
+  sep_fused_destroy(op);
   sparse_destroy(op);
   resize_destroy(op);
   resize_fused_destroy(op);
@@ -197,6 +198,8 @@ int dps_operator_guidance(const dps_operator* op, const dps_source* src, const f
                     src->x_stride % 4 == 0 && (!src->eps || src->eps_stride % 4 == 0) && y_stride % 4 == 0 && g_stride % 4 == 0,
                 DPS_ERR_ALIGN, "dps_operator_guidance: tensors must be 16-byte aligned, strides multiples of 4");
     if (op->kind == DPS_OP_RESIZE) return resize_fused_guidance(op, *src, y, y_stride, r_out, g, g_stride, partials, n, (cudaStream_t)stream);
+    if (op->kind == DPS_OP_BLUR_SEPARABLE && op->sepfused && src->eps)
+      return sep_fused_guidance(op, *src, y, y_stride, r_out, g, g_stride, partials, n, (cudaStream_t)stream);
     if (op->kind == DPS_OP_INPAINT && src->eps && y) {
       FwdArgs fa;
       fa.src = *src;

@@ -7,6 +7,7 @@ struct SparseTables;  // blur_sparse.cu
 struct ResizeTables;  // resize.cu
 struct PhaseTables;   // phase.cu
 struct ResizeFused;   // resize_fused.cu
+struct SepFused;      // blur_fused.cu
 
 struct dps_operator {
   int kind = 0;
@@ -21,6 +22,7 @@ struct dps_operator {
   SparseTables* sparse = nullptr;
   ResizeTables* resize = nullptr;
   PhaseTables* phase = nullptr;
+  SepFused* sepfused = nullptr;   // fused residual + cotangent kernel of the separable blur (blur_fused.cu)
   ResizeFused* rfused = nullptr;  // fused residual + cotangent kernel (resize_fused.cu), null when the shape is not covered
   int guidance_P = 0;             // partial sums per particle written by the fused guidance kernel (0: none)
 };
@@ -130,6 +132,10 @@ void resize_destroy(dps_operator* op);
 int resize_forward(const dps_operator* op, const FwdArgs& a, cudaStream_t st);
 int resize_adjoint(const dps_operator* op, const AdjArgs& a, cudaStream_t st);
 
+int sep_fused_create(dps_operator* op, const float* taps_v, int rv, const float* taps_h, int rh);
+void sep_fused_destroy(dps_operator* op);
+int sep_fused_guidance(const dps_operator* op, const dps_source& src, const float* y, int64_t y_stride, float* r_out, float* g,
+                       int64_t g_stride, float* partials, int n, cudaStream_t st);
 void resize_fused_destroy(dps_operator* op);
 int resize_fused_guidance(const dps_operator* op, const dps_source& src, const float* y, int64_t y_stride, float* r_out, float* g,
                           int64_t g_stride, float* partials, int n, cudaStream_t st);

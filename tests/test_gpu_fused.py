@@ -230,3 +230,53 @@ def test_fused_inpainting_guidance_vs_two_kernels(n, idx, clip):
     g3 = torch.zeros(n, 3, 256, 256, device=DEV)
     p3, r3, _ = plan.guidance(x, eps, k, clip, y, out=g3)
     assert r3 is None and torch.equal(g3, g2[:, :3]) and torch.equal(p3, p1)
+
+
+def _sep_kernels():
+    from dps_ttc_b200.tables import gaussian_kernel
+    rng = np.random.default_rng(21)
+    v = rng.random(11).astype(np.float64) + 0.1          # asymmetric rank-1 kernel, radius 5: exercises the flipped taps
+    h = rng.random(11).astype(np.float64) + 0.1          # and the folded border terms of the adjoint
+    asym = np.outer(v / v.sum(), h / h.sum()).astype(np.float32)
+    return {"gauss61": gaussian_kernel(61, 3.0).astype(np.float32), "asym11": asym,
+            "gauss9": gaussian_kernel(9, 1.0).astype(np.float32)}
+
+
+@pytest.mark.parametrize("kname,n,idx,clip", [("gauss61", 1, 999, True), ("gauss61", 5, 500, True), ("asym11", 3, 999, True),
+                                               ("gauss9", 2, 10, False)])
+def test_fused_separable_blur_guidance_vs_two_kernels_and_oracle(kname, n, idx, clip):
+    from dps_ttc_b200 import kernels
+    from dps_ttc_b200.kernels import OperatorPlan
+    kern = _sep_kernels()[kname]
+    plan = OperatorPlan.blur(kern, 3, 256, 256, DEV)
+    assert plan.kind == "blur_separable" and plan.guidance_partials == 3 * 8
+    k = _consts(idx)
+    gen = torch.Generator(DEV).manual_seed(300 + n)
+    x = torch.randn(n, 3, 256, 256, device=DEV, generator=gen) / k.c1
+    o6 = torch.randn(n, 6, 256, 256, device=DEV, generator=gen) * 0.3 / max(k.c2, 1e-3)
+    eps = o6[:, :3]
+    y = torch.randn(1, 3, 256, 256, device=DEV, generator=gen)
+    r2, p2, _ = plan.forward(x, eps, k, clip, y, want_partials=True)
+    g2 = torch.zeros(n, 6, 256, 256, device=DEV)
+    plan.adjoint(r2, None, x, eps, k, clip, None, out=g2[:, :3])
+    g1 = torch.full((n, 6, 256, 256), float("nan"), device=DEV)
+    g1[:, 3:] = 0
+    p1, r1, _ = plan.guidance(x, eps, k, clip, y, out=g1[:, :3], want_r=True)
+    assert torch.isfinite(g1).all()
+    assert float((r1 - r2).abs().max()) <= 2e-6 * max(1.0, float(r2.abs().max()))
+    assert float((g1[:, :3] - g2[:, :3]).abs().max()) <= 5e-6 * max(1.0, float(g2.abs().max()))
+    n1, n2 = kernels.particle_norms(p1, want_l1=True), kernels.particle_norms(p2, want_l1=True)
+    assert float((n1[0] - n2[0]).abs().max()) <= 1e-5 * float(n2[0].max())
+    assert float((n1[1] - n2[1]).abs().max()) <= 1e-5 * float(n2[1].max())
+    if n <= 3:
+        xn, en = x.cpu().numpy(), eps.cpu().numpy()
+        x0, pre = O.x0_from_eps(xn, en, dict(c1=np.float32(k.c1), c2=np.float32(k.c2)), clip)
+        r_ref = y.cpu().numpy() - O.blur_forward(x0, kern)
+        g_ref = O.blur_adjoint(r_ref, kern)
+        if clip:
+            g_ref = g_ref * ((pre >= -1) & (pre <= 1))
+        assert np.abs(r1.cpu().numpy() - r_ref).max() <= 5e-6 * max(1.0, np.abs(r_ref).max())
+        assert np.abs(g1[:, :3].cpu().numpy() - g_ref).max() <= 1e-5 * max(1.0, np.abs(g_ref).max())
+    g3 = torch.zeros(n, 3, 256, 256, device=DEV)
+    p3, r3, _ = plan.guidance(x, eps, k, clip, y, out=g3)
+    assert r3 is None and torch.equal(g3, g1[:, :3]) and torch.equal(p3, p1)

@@ -212,6 +212,11 @@ def main():
         us = time_it(lambda i: plan.adjoint(R[i], coef, X[i][:nn], O6[i][:nn, :3], k, True, None, out=G6[i][:nn, :3], aux=AUX[i]),
                      S, a.iters)
         emit("phase_adjoint (3T+M, 2 kernels)", nn * (3 * T + M), us, {"n_particles": nn})
+    if want("gaussfused"):
+        plan_g = OperatorPlan.blur(tables.gaussian_kernel(61, 3.0).astype(np.float32), 3, 256, 256, dev)
+        yg = rnd(1, 3, 256, 256)
+        us = time_it(lambda i: plan_g.guidance(X[i], O6[i][:, :3], k, True, yg, out=G6[i][:, :3]), S, a.iters)
+        emit("gauss guidance: residual + cotangent in one cluster kernel (3T+M)", n * (3 * T) + T, us)
     if want("inpaintfused"):
         plan_i = OperatorPlan.inpainting(mask, 3, 256, 256, dev)
         yi = rnd(1, 3, 256, 256)
