@@ -32,7 +32,8 @@ struct SepFused {
 };
 
 namespace {
-constexpr int kW = 256, kRI = 32, kCluster = 8, kT = 256, kChunks = 4, kChunkRows = kRI / kChunks, kG = 8;
+constexpr int kW = 256, kRI = 32, kCluster = 8, kT = 256, kChunks = 4, kChunkRows = kRI / kChunks, kG = 16, kNB = 18, kSL = 16;
+constexpr int kRowB = kW * (int)sizeof(float);
 
 struct SepFusedArgs {
   float wv[33];
@@ -47,36 +48,71 @@ struct SepFusedArgs {
   float* partials;
 };
 
+// smallest pitch ≥ need with pitch ≡ 2 (mod 4): lanes that walk ROWS of such a tile (one lane per row / row pair) hit
+// distinct bank groups with 64-bit accesses of 4-byte elements and with 128-bit accesses of 8-byte elements
+constexpr int pitch2mod4(int need) { return need + ((2 - need % 4) + 4) % 4; }
+constexpr int cmax(int a, int b) { return a > b ? a : b; }
+
 template <int R>
-size_t sepf_smem() {
-  return sizeof(float) * ((size_t)kRI * kW + (size_t)kRI * (kW + 2 * R) + (size_t)kRI * 2 * R + 64) + 8 * kChunks;
-}
+struct SepCfg {
+  static constexpr int TAPS = 2 * R + 1;
+  static constexpr int TP = R, TPITCH = pitch2mod4(kW + 2 * R);              // T2: (16 row pairs, TPITCH) float2, image column c at TP + c
+  static constexpr int ZP = kSL + R, ZPITCH = pitch2mod4(ZP + kW + 2 * R);   // Z2: zero-padded residual, same interleaved layout
+  static constexpr int SP = R, SPITCH = pitch2mod4(kW + 2 * R);              // s: two (16, SPITCH) float tiles (even rows, odd rows)
+  static constexpr int STILE = (kRI / 2) * SPITCH;                           // floats per parity tile
+  static constexpr int A_FLOATS = cmax(kRI * kW, 2 * STILE);
+  static constexpr int B_FLOATS = cmax(cmax(kRI * kW, (kRI / 2) * TPITCH * 2), (kRI / 2) * ZPITCH * 2 + 16);
+  static constexpr size_t SMEM = sizeof(float) * (size_t)(A_FLOATS + B_FLOATS + 64) + 8 * kChunks;
+  static constexpr int CTAS = SMEM + 1024 <= 233472 / 3 ? 3 : 2;
+};
 
 DPS_DEV void cl_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 DPS_DEV void cl_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+DPS_DEV unsigned mapa_u32(unsigned addr, unsigned rank) {
+  unsigned r;
+  asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+// 64-bit load from the cluster's distributed shared memory (own or a neighbour CTA's tile); volatile: never moved across a barrier
+DPS_DEV float2 ld_cluster2(unsigned addr) {
+  float2 v;
+  asm volatile("ld.shared::cluster.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+  return v;
+}
+DPS_DEV float2 ld_cluster2_or_zero(unsigned addr, int valid) {  // predicated: rows outside the image read as zero, no branch
+  float2 v;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %3, 0;\n\tmov.f32 %0, 0f00000000;\n\tmov.f32 %1, 0f00000000;\n\t"
+      "@p ld.shared::cluster.v2.f32 {%0,%1}, [%2];\n\t}"
+      : "=f"(v.x), "=f"(v.y)
+      : "r"(addr), "r"(valid));
+  return v;
+}
+DPS_DEV float2 fma2w(float w, float2 v, float2 acc) { return __ffma2_rn(make_float2(w, w), v, acc); }  // FFMA2 R, R, UR.F32, R
 
-// Packed arithmetic: every FMA of the four passes is an FFMA2 (fma.rn.f32x2).  The vertical passes pair two adjacent
-// COLUMNS (a thread owns columns 2p, 2p+1 and half of the CTA's rows; 64-bit shared loads of the natural row-major
-// layout), the horizontal passes pair two adjacent ROWS (a thread owns 4 columns of 4 row pairs) — for that the tiles
-// between a vertical and a horizontal pass are stored row-pair interleaved: T2[row pair][column] = (row a, row b).
+// Every FMA of the four passes is an FFMA2 (fma.rn.f32x2) whose weight is a uniform-register broadcast.  The vertical passes
+// pair two adjacent COLUMNS (a thread owns columns 2p, 2p+1 and 16 rows: 16 + 2R 64-bit loads of a row-major tile, lanes along
+// the row), the horizontal passes pair two adjacent ROWS (a thread owns a row pair and a run of 16 / 18 columns: 128-bit loads
+// of a tile stored row-pair interleaved, T2[row pair][column] = (row a, row b), lanes along the row pairs).  All loops are
+// fully unrolled over compile-time offsets and free of branches, so a pass is "load, 16 FFMA2, load, …" and nothing else.
 template <int R>
-__global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kT, 3) sep_guidance_kernel(const __grid_constant__ SepFusedArgs a) {
-  constexpr int TAPS = 2 * R + 1, PADW = kW + 2 * R, H = kRI * kCluster, NV = 4 + 2 * R, RIH = kRI / 2;
+__global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kT, SepCfg<R>::CTAS) sep_guidance_kernel(const __grid_constant__ SepFusedArgs a) {
+  using Cfg = SepCfg<R>;
+  constexpr int TAPS = Cfg::TAPS, H = kRI * kCluster, TPITCH = Cfg::TPITCH, ZPITCH = Cfg::ZPITCH, SPITCH = Cfg::SPITCH;
   static_assert(R % 4 == 0 && R >= 4 && R <= 16, "radius");
   extern __shared__ __align__(16) float smem[];
-  float* Sx = smem;                                   // (32, 256)  x → x̂₀ → (pass 3) s = A_hᵀ r, row-major
-  float* TZ = Sx + kRI * kW;                          // ε (first 32·256 floats) → T2 (pass 1) → zero-padded r (pass 3)
-  float2* T2 = reinterpret_cast<float2*>(TZ);         // (16 row pairs, PADW) of (row a, row b)
-  float* E = TZ + kRI * PADW;                         // (32, 2R)   folded border terms of the horizontal adjoint
-  float* red = E + kRI * 2 * R;                       // 64
+  float* Sx = smem;                                    // region A: x → x̂₀ (32, 256) row-major → s = A_hᵀ r as two parity tiles
+  float* TZ = smem + Cfg::A_FLOATS;                    // region B: ε → T2 (vertical pass, mirrored column pads) → Z2 (zero-padded r)
+  float2* T2 = reinterpret_cast<float2*>(TZ);
+  float* red = TZ + Cfg::B_FLOATS;                     // 64
   uint64_t* bar = reinterpret_cast<uint64_t*>(red + 64);
 
   cg::cluster_group cluster = cg::this_cluster();
   const int q = (int)cluster.block_rank();
   const int plane = blockIdx.x / kCluster, c = plane % a.C, n = plane / a.C;
   const int tid = threadIdx.x;
-  const int p = tid & 127, h = tid >> 7;              // vertical passes: column pair, row half (warp-uniform)
-  const int cgi = tid & 63, rq = tid >> 6;            // horizontal passes: 4 columns, 4 row pairs
+  const int p = tid & 127, h = tid >> 7;               // vertical passes: column pair, row half
+  const int rp = tid & 15, cb = tid >> 4;              // horizontal passes: row pair, column block
   const int64_t poff = (int64_t)c * H * kW + (int64_t)q * kRI * kW;
   const float* xg = a.src.x + n * a.src.x_stride + poff;
   const float* eg = a.src.eps + n * a.src.eps_stride + poff;
@@ -105,7 +141,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kT, 3) sep_gu
       mbar_wait(bar + h * (kChunks / 2) + chh, 0);
 #pragma unroll
       for (int r8 = 0; r8 < kChunkRows; ++r8) {
-        const int rr = chh * kChunkRows + r8, r = h * RIH + rr;
+        const int rr = chh * kChunkRows + r8, r = h * kG + rr;
         float2* xs = reinterpret_cast<float2*>(Sx + r * kW) + p;
         const float2 pre = x0_pair_pre(*xs, reinterpret_cast<const float2*>(TZ + r * kW)[p], a.src.c1, a.src.c2);
         *xs = make_float2(fminf(fmaxf(pre.x, lo), hi), fminf(fmaxf(pre.y, lo), hi));
@@ -113,89 +149,109 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kT, 3) sep_gu
       }
     }
   }
+  const unsigned own_a = mapa_u32(smem_u32(Sx), (unsigned)q);  // region A of this CTA / its neighbours in the cluster window
+  const unsigned up_a = mapa_u32(smem_u32(Sx), (unsigned)(q > 0 ? q - 1 : q));
+  const unsigned dn_a = mapa_u32(smem_u32(Sx), (unsigned)(q < kCluster - 1 ? q + 1 : q));
   cluster.sync();  // #1: every CTA's x̂₀ rows are in place; the ε rows are dead
 
   // ---- 1. vertical forward for my column pair, rows 16h..16h+15 → T2 (row-pair interleaved, column-padded by mirroring) ----
   {
-    const float* up = q > 0 ? cluster.map_shared_rank(Sx, q - 1) : Sx;
-    const float* dn = q < kCluster - 1 ? cluster.map_shared_rank(Sx, q + 1) : Sx;
+    // The first R and the last R rows of the window are halo rows for one of the two halves: neighbour rows over DSMEM or, at
+    // the image border, own rows mirrored without edge repeat (−m ↦ m, 31 + m ↦ 31 − m) — one base and one signed row stride.
+    unsigned a0, a1;
+    int s0, s1;
+    if (h == 0) {
+      a0 = q > 0 ? up_a + (kRI - R) * kRowB : own_a + R * kRowB;
+      s0 = q > 0 ? kRowB : -kRowB;
+      a1 = own_a + kG * kRowB;
+      s1 = kRowB;
+    } else {
+      a0 = own_a + (kG - R) * kRowB;
+      s0 = kRowB;
+      a1 = q < kCluster - 1 ? dn_a : own_a + (kRI - 2) * kRowB;
+      s1 = q < kCluster - 1 ? kRowB : -kRowB;
+    }
+    a0 += p * 8;
+    a1 += p * 8;
+    const float2* mid = reinterpret_cast<const float2*>(Sx + h * kG * kW) + p;  // rows 16h + (rr − R), R ≤ rr < 16 + R
+    float2 acc[kG];
 #pragma unroll
-    for (int gI = 0; gI < RIH / kG; ++gI) {
-      float2 acc[kG];
+    for (int j = 0; j < kG; ++j) acc[j] = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int j = 0; j < kG; ++j) acc[j] = make_float2(0.f, 0.f);
+    for (int rr = 0; rr < kG + 2 * R; ++rr) {
+      float2 v;
+      if (rr < R) v = ld_cluster2(a0 + rr * s0);
+      else if (rr >= kG + R) v = ld_cluster2(a1 + (rr - kG - R) * s1);
+      else v = mid[(rr - R) * (kW / 2)];
 #pragma unroll
-      for (int rr = 0; rr < kG + 2 * R; ++rr) {
-        const int lr = h * RIH + gI * kG - R + rr;  // warp-uniform
-        const float* rowp;
-        if (lr < 0)  // above my rows: neighbour rows, or (image top) my own rows mirrored without edge repeat: −m ↦ m
-          rowp = q > 0 ? up + (kRI + lr) * kW : Sx + (-lr) * kW;
-        else if (lr >= kRI)  // below: neighbour rows, or (image bottom) 31 + m ↦ 31 − m
-          rowp = q < kCluster - 1 ? dn + (lr - kRI) * kW : Sx + (2 * (kRI - 1) - lr) * kW;
-        else
-          rowp = Sx + lr * kW;
-        const float2 v = reinterpret_cast<const float2*>(rowp)[p];
-#pragma unroll
-        for (int j = 0; j < kG; ++j) {
-          const int k = rr - j;
-          if (k >= 0 && k < TAPS) acc[j] = __ffma2_rn(make_float2(a.wv[k], a.wv[k]), v, acc[j]);
-        }
+      for (int j = 0; j < kG; ++j) {
+        const int k = rr - j;
+        if (k >= 0 && k < TAPS) acc[j] = fma2w(a.wv[k], v, acc[j]);
       }
+    }
+    cl_arrive();  // #2 (arrive): my reads of the neighbours' x̂₀ rows are done
+    float2* row0 = T2 + (size_t)(h * (kG / 2)) * TPITCH + Cfg::TP;
+#pragma unroll
+    for (int jp = 0; jp < kG / 2; ++jp)
+      *reinterpret_cast<float4*>(row0 + jp * TPITCH + 2 * p) = make_float4(acc[2 * jp].x, acc[2 * jp + 1].x, acc[2 * jp].y, acc[2 * jp + 1].y);
+    if (p <= R / 2 || p >= kW / 2 - 1 - R / 2) {  // the warps at the left / right edge also write the mirrored pad columns
+      const int ca = 2 * p, cc = 2 * p + 1;
 #pragma unroll
       for (int jp = 0; jp < kG / 2; ++jp) {
-        float2* row = T2 + (size_t)((h * RIH + gI * kG) / 2 + jp) * PADW + R;  // row pair (a, b) = rows 2jp, 2jp+1 of the group
+        float2* row = row0 + jp * TPITCH;
         const float2 c0 = make_float2(acc[2 * jp].x, acc[2 * jp + 1].x), c1 = make_float2(acc[2 * jp].y, acc[2 * jp + 1].y);
-        *reinterpret_cast<float4*>(row + 2 * p) = make_float4(c0.x, c0.y, c1.x, c1.y);
-        const int ca = 2 * p, cb = 2 * p + 1;
         if (ca >= 1 && ca <= R) row[-ca] = c0;                                   // column −m mirrors column m
-        if (cb <= R) row[-cb] = c1;
+        if (cc <= R) row[-cc] = c1;
         if (ca >= kW - 1 - R && ca <= kW - 2) row[2 * (kW - 1) - ca] = c0;       // column 255 + m mirrors 255 − m
-        if (cb >= kW - 1 - R && cb <= kW - 2) row[2 * (kW - 1) - cb] = c1;
+        if (cc >= kW - 1 - R && cc <= kW - 2) row[2 * (kW - 1) - cc] = c1;
       }
     }
   }
-  cl_arrive();      // #2 (arrive): my reads of the neighbours' x̂₀ rows are done
   __syncthreads();  // T2 complete
 
-  // ---- 2. horizontal forward + residual: thread = columns 4cg..4cg+3 of row pairs 4rq..4rq+3 ----
-  float2 rres[4][4];  // [row pair][column] = (row a, row b)
+  // ---- 2. horizontal forward + residual: thread = row pair rp, columns 16cb..16cb+15 ----
+  float2 o[kNB];  // (row a, row b) per column; 16 used here, 18 by the adjoint
   float sq = 0.f, ab = 0.f;
   {
-    const float* yp = a.y ? a.y + n * a.y_stride + poff : nullptr;
+    const float4* tp = reinterpret_cast<const float4*>(T2 + (size_t)rp * TPITCH + 16 * cb);  // padded column 16cb = image column 16cb − R
 #pragma unroll
-    for (int rp = 0; rp < 4; ++rp) {
-      const int rowa = (4 * rq + rp) * 2;
-      const float4 ya = yp ? ldg_ro4(yp + rowa * kW + 4 * cgi) : make_float4(0.f, 0.f, 0.f, 0.f);
-      const float4 yb = yp ? ldg_ro4(yp + (rowa + 1) * kW + 4 * cgi) : make_float4(0.f, 0.f, 0.f, 0.f);
-      const float4* tp = reinterpret_cast<const float4*>(T2 + (size_t)(4 * rq + rp) * PADW + 4 * cgi);  // padded column 4cg = image column 4cg − R
-      float2 v[NV];
+    for (int j = 0; j < 16; ++j) o[j] = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int m = 0; m < NV / 2; ++m) {
-        const float4 t4 = tp[m];
-        v[2 * m] = make_float2(t4.x, t4.y);
-        v[2 * m + 1] = make_float2(t4.z, t4.w);
+    for (int m = 0; m < (16 + 2 * R) / 2; ++m) {
+      const float4 t4 = tp[m];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const float2 v = e ? make_float2(t4.z, t4.w) : make_float2(t4.x, t4.y);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int k = 2 * m + e - j;
+          if (k >= 0 && k < TAPS) o[j] = fma2w(a.wh[k], v, o[j]);
+        }
       }
-      float2 o[4];
+    }
+    const int rowa = 2 * rp;
+    if (a.y) {
+      const float* yp = a.y + n * a.y_stride + poff + rowa * kW + 16 * cb;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) o[j] = make_float2(0.f, 0.f);
-#pragma unroll
-      for (int k = 0; k < TAPS; ++k) {
-        const float2 w2 = make_float2(a.wh[k], a.wh[k]);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) o[j] = __ffma2_rn(w2, v[j + k], o[j]);
+      for (int i = 0; i < 4; ++i) {
+        const float4 ya = ldg_ro4(yp + 4 * i), yb = ldg_ro4(yp + kW + 4 * i);
+        o[4 * i + 0] = make_float2(__fsub_rn(ya.x, o[4 * i + 0].x), __fsub_rn(yb.x, o[4 * i + 0].y));
+        o[4 * i + 1] = make_float2(__fsub_rn(ya.y, o[4 * i + 1].x), __fsub_rn(yb.y, o[4 * i + 1].y));
+        o[4 * i + 2] = make_float2(__fsub_rn(ya.z, o[4 * i + 2].x), __fsub_rn(yb.z, o[4 * i + 2].y));
+        o[4 * i + 3] = make_float2(__fsub_rn(ya.w, o[4 * i + 3].x), __fsub_rn(yb.w, o[4 * i + 3].y));
       }
-      const float yav[4] = {ya.x, ya.y, ya.z, ya.w}, ybv[4] = {yb.x, yb.y, yb.z, yb.w};
+    }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float ra = yp ? __fsub_rn(yav[j], o[j].x) : o[j].x, rb = yp ? __fsub_rn(ybv[j], o[j].y) : o[j].y;
-        rres[rp][j] = make_float2(ra, rb);
-        sq = fmaf(ra, ra, fmaf(rb, rb, sq));
-        ab += fabsf(ra) + fabsf(rb);
-      }
-      if (a.r_out) {
-        float* ro = a.r_out + ((int64_t)n * a.C + c) * H * kW + (int64_t)(q * kRI + rowa) * kW + 4 * cgi;
-        stg_stream4(ro, make_float4(rres[rp][0].x, rres[rp][1].x, rres[rp][2].x, rres[rp][3].x));
-        stg_stream4(ro + kW, make_float4(rres[rp][0].y, rres[rp][1].y, rres[rp][2].y, rres[rp][3].y));
+    for (int j = 0; j < 16; ++j) {
+      sq = fmaf(o[j].x, o[j].x, fmaf(o[j].y, o[j].y, sq));
+      ab += fabsf(o[j].x) + fabsf(o[j].y);
+    }
+    if (a.r_out) {
+      float* ro = a.r_out + ((int64_t)n * a.C + c) * H * kW + (int64_t)(q * kRI + rowa) * kW + 16 * cb;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        stg_stream4(ro + 4 * i, make_float4(o[4 * i].x, o[4 * i + 1].x, o[4 * i + 2].x, o[4 * i + 3].x));
+        stg_stream4(ro + kW + 4 * i, make_float4(o[4 * i].y, o[4 * i + 1].y, o[4 * i + 2].y, o[4 * i + 3].y));
       }
     }
   }
@@ -206,133 +262,110 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kT, 3) sep_gu
       pp[0] = sq;
       pp[1] = ab;
     }
+  } else {
+    __syncthreads();
   }
-  __syncthreads();  // everybody is done reading T2
-  // ---- 3. horizontal adjoint: zero-padded r (same interleaved layout) → plain flipped-tap correlation + folded border terms ----
+  // (a barrier has passed: everybody is done reading T2)
+  // ---- 3. horizontal adjoint on the PADDED domain: Z2 = zero-padded r, t[P] = Σ_d wh[R − d]·r[P + d] for P ∈ [−R, 256 + R),
+  //         thread = row pair rp, 18 columns from −16 + 18cb; the pad outputs are folded onto their mirror columns afterwards
+  //         (Aᵀ = Pᵀ Cᵀ: what the mirrored padding read twice comes back twice). ----
+  {
+    float2* zrow = T2 + (size_t)rp * ZPITCH;
 #pragma unroll
-  for (int rp = 0; rp < 4; ++rp) {
-    float2* row = T2 + (size_t)(4 * rq + rp) * PADW;
-    *reinterpret_cast<float4*>(row + R + 4 * cgi) = make_float4(rres[rp][0].x, rres[rp][0].y, rres[rp][1].x, rres[rp][1].y);
-    *reinterpret_cast<float4*>(row + R + 4 * cgi + 2) = make_float4(rres[rp][2].x, rres[rp][2].y, rres[rp][3].x, rres[rp][3].y);
+    for (int i = 0; i < 8; ++i)
+      *reinterpret_cast<float4*>(zrow + Cfg::ZP + 16 * cb + 2 * i) = make_float4(o[2 * i].x, o[2 * i].y, o[2 * i + 1].x, o[2 * i + 1].y);
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (cgi < R / 4) { *reinterpret_cast<float4*>(row + 4 * cgi) = z4; *reinterpret_cast<float4*>(row + 4 * cgi + 2) = z4; }
-    if (cgi >= 64 - R / 4) { *reinterpret_cast<float4*>(row + 2 * R + 4 * cgi) = z4; *reinterpret_cast<float4*>(row + 2 * R + 4 * cgi + 2) = z4; }
+    for (int i = cb; i < Cfg::ZP / 2; i += 16) *reinterpret_cast<float4*>(zrow + 2 * i) = z4;
+    for (int i = cb; i < (ZPITCH - Cfg::ZP - kW) / 2; i += 16) *reinterpret_cast<float4*>(zrow + Cfg::ZP + kW + 2 * i) = z4;
   }
   __syncthreads();
-  for (int id = tid; id < kRI * 2 * R; id += kT) {  // folded terms: (row, side, m)
-    const int row = id / (2 * R), rem = id - row * (2 * R), side = rem / R, m = rem - side * R + 1;
-    const float* rrow = reinterpret_cast<const float*>(T2 + (size_t)(row >> 1) * PADW + R) + (row & 1);  // element i at rrow[2i]
-    float s = 0.f;
-    if (side == 0) {
-      for (int i = 0; i <= R - m; ++i) s = fmaf(a.wh[R - m - i], rrow[2 * i], s);
-    } else {
-      for (int b = 0; b <= R - m; ++b) s = fmaf(a.wh[R + m + b], rrow[2 * (kW - 1 - b)], s);
-    }
-    E[row * 2 * R + side * R + (m - 1)] = s;
-  }
+  {
+    const float4* tp = reinterpret_cast<const float4*>(T2 + (size_t)rp * ZPITCH + kNB * cb);  // Z2 index ZP + (−16 + 18cb) − R
 #pragma unroll
-  for (int rp = 0; rp < 4; ++rp) {  // plain part (rres is re-used for s)
-    const float4* tp = reinterpret_cast<const float4*>(T2 + (size_t)(4 * rq + rp) * PADW + 4 * cgi);
-    float2 v[NV];
+    for (int j = 0; j < kNB; ++j) o[j] = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int m = 0; m < NV / 2; ++m) {
+    for (int m = 0; m < (kNB + 2 * R) / 2; ++m) {
       const float4 t4 = tp[m];
-      v[2 * m] = make_float2(t4.x, t4.y);
-      v[2 * m + 1] = make_float2(t4.z, t4.w);
-    }
-    float2 o[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) o[j] = make_float2(0.f, 0.f);
+      for (int e = 0; e < 2; ++e) {
+        const float2 v = e ? make_float2(t4.z, t4.w) : make_float2(t4.x, t4.y);
 #pragma unroll
-    for (int k = 0; k < TAPS; ++k) {
-      const float2 w2 = make_float2(a.wh[2 * R - k], a.wh[2 * R - k]);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) o[j] = __ffma2_rn(w2, v[j + k], o[j]);
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) rres[rp][j] = o[j];
-  }
-  __syncthreads();  // E complete
-  cl_wait();        // #2 (wait): the neighbours are done reading my x̂₀ rows → the buffer may take s
-#pragma unroll
-  for (int rp = 0; rp < 4; ++rp) {
-    const int rowa = (4 * rq + rp) * 2;
-    float sa[4], sb[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { sa[j] = rres[rp][j].x; sb[j] = rres[rp][j].y; }
-    if (cgi <= R / 4 || cgi >= 63 - R / 4) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int m = 4 * cgi + j;
-        if (m >= 1 && m <= R) { sa[j] += E[rowa * 2 * R + (m - 1)]; sb[j] += E[(rowa + 1) * 2 * R + (m - 1)]; }
-        if (m >= kW - 1 - R && m <= kW - 2) {
-          sa[j] += E[rowa * 2 * R + R + (kW - 1 - m) - 1];
-          sb[j] += E[(rowa + 1) * 2 * R + R + (kW - 1 - m) - 1];
+        for (int j = 0; j < kNB; ++j) {
+          const int k = 2 * m + e - j;
+          if (k >= 0 && k < TAPS) o[j] = fma2w(a.wh[2 * R - k], v, o[j]);
         }
       }
     }
-    *reinterpret_cast<float4*>(Sx + rowa * kW + 4 * cgi) = make_float4(sa[0], sa[1], sa[2], sa[3]);
-    *reinterpret_cast<float4*>(Sx + (rowa + 1) * kW + 4 * cgi) = make_float4(sb[0], sb[1], sb[2], sb[3]);
+  }
+  cl_wait();  // #2 (wait): the neighbours are done reading my x̂₀ rows → region A may take s
+  {
+    float* se = Sx + (size_t)rp * SPITCH + Cfg::SP - kSL + kNB * cb;  // row 2rp (even tile); the odd tile follows at STILE
+#pragma unroll
+    for (int i = 0; i < kNB / 2; ++i) {
+      const int P = -kSL + kNB * cb + 2 * i;
+      if (P >= -R && P < kW + R) {
+        *reinterpret_cast<float2*>(se + 2 * i) = make_float2(o[2 * i].x, o[2 * i + 1].x);
+        *reinterpret_cast<float2*>(se + Cfg::STILE + 2 * i) = make_float2(o[2 * i].y, o[2 * i + 1].y);
+      }
+    }
+  }
+  __syncthreads();
+  for (int id = tid; id < kRI * 2 * R; id += kT) {  // fold: (row, side, m)
+    const int row = id / (2 * R), rem = id - row * (2 * R), side = rem / R, m = rem - side * R + 1;
+    float* srow = Sx + (row & 1) * Cfg::STILE + (size_t)(row >> 1) * SPITCH + Cfg::SP;
+    if (side == 0) srow[m] += srow[-m];
+    else srow[kW - 1 - m] += srow[kW - 1 + m];
   }
   cluster.sync();  // #3: every CTA's s rows are in place
 
   // ---- 4. vertical adjoint for my column pair, rows 16h..16h+15, + border folds + clamp mask ----
   {
-    const float* up = q > 0 ? cluster.map_shared_rank(Sx, q - 1) : Sx;
-    const float* dn = q < kCluster - 1 ? cluster.map_shared_rank(Sx, q + 1) : Sx;
-    float* gp = a.g + n * a.g_stride + poff;
-    const float2* sx2 = reinterpret_cast<const float2*>(Sx);
+    // window row lr = 16h − R + rr lives in parity tile (rr & 1) at tile row (lr >> 1): compile-time offsets from three bases
+    constexpr int kRowPB = SPITCH * (int)sizeof(float), kTileB = Cfg::STILE * (int)sizeof(float);
+    const unsigned colb = (Cfg::SP + 2 * p) * (unsigned)sizeof(float);
+    const unsigned b0 = (h == 0 ? up_a + (kRI / 2) * kRowPB : own_a + (kG / 2) * kRowPB) + colb;   // rr < R: tile row (h ? 8 : 16 of the upper CTA) + (rr − R)/2
+    const unsigned b1 = (h == 0 ? own_a + (kG / 2) * kRowPB : dn_a) + colb;                        // rr ≥ 16 + R: tile row (h ? 0 of the lower CTA : 8) + (rr − 16 − R)/2
+    const int v0 = (h == 1 || q > 0) ? 1 : 0, v1 = (h == 0 || q < kCluster - 1) ? 1 : 0;           // rows outside the image contribute nothing to the plain part
+    const float* mid = Sx + (size_t)(h * (kG / 2)) * SPITCH + Cfg::SP + 2 * p;
+    float2 acc[kG];
 #pragma unroll
-    for (int gI = 0; gI < RIH / kG; ++gI) {
-      float2 acc[kG];
+    for (int j = 0; j < kG; ++j) acc[j] = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int j = 0; j < kG; ++j) acc[j] = make_float2(0.f, 0.f);
-#pragma unroll
-      for (int rr = 0; rr < kG + 2 * R; ++rr) {
-        const int lr = h * RIH + gI * kG - R + rr;  // warp-uniform
-        float2 v = make_float2(0.f, 0.f);            // rows outside the image contribute nothing to the plain part
-        if (lr < 0) {
-          if (q > 0) v = reinterpret_cast<const float2*>(up + (kRI + lr) * kW)[p];
-        } else if (lr >= kRI) {
-          if (q < kCluster - 1) v = reinterpret_cast<const float2*>(dn + (lr - kRI) * kW)[p];
-        } else {
-          v = sx2[lr * (kW / 2) + p];
-        }
-#pragma unroll
-        for (int j = 0; j < kG; ++j) {
-          const int k = rr - j;
-          if (k >= 0 && k < TAPS) acc[j] = __ffma2_rn(make_float2(a.wv[2 * R - k], a.wv[2 * R - k]), v, acc[j]);
-        }
-      }
-      if (q == 0) {  // image top: g[m] += Σ_{i=0}^{R−m} wv[R − m − i]·s[i],  1 ≤ m ≤ R   (m is warp-uniform)
-#pragma unroll
-        for (int j = 0; j < kG; ++j) {
-          const int m = h * RIH + gI * kG + j;
-          if (m >= 1 && m <= R) {
-#pragma unroll
-            for (int i = 0; i < R; ++i)
-              if (i <= R - m) acc[j] = __ffma2_rn(make_float2(a.wv[R - m - i], a.wv[R - m - i]), sx2[i * (kW / 2) + p], acc[j]);
-          }
-        }
-      }
-      if (q == kCluster - 1) {  // image bottom: g[31 − a'] += Σ_{b=0}^{R−a'} wv[R + a' + b]·s[31 − b],  1 ≤ a' ≤ R
-#pragma unroll
-        for (int j = 0; j < kG; ++j) {
-          const int ap = kRI - 1 - (h * RIH + gI * kG + j);
-          if (ap >= 1 && ap <= R) {
-#pragma unroll
-            for (int b = 0; b < R; ++b)
-              if (b <= R - ap)
-                acc[j] = __ffma2_rn(make_float2(a.wv[R + ap + b], a.wv[R + ap + b]), sx2[(kRI - 1 - b) * (kW / 2) + p], acc[j]);
-          }
-        }
-      }
+    for (int rr = 0; rr < kG + 2 * R; ++rr) {
+      float2 v;
+      if (rr < R) v = ld_cluster2_or_zero(b0 + (rr & 1) * kTileB + ((rr - R - (rr & 1)) / 2) * kRowPB, v0);
+      else if (rr >= kG + R) v = ld_cluster2_or_zero(b1 + (rr & 1) * kTileB + ((rr - kG - R) / 2) * kRowPB, v1);
+      else v = *reinterpret_cast<const float2*>(mid + (rr & 1) * Cfg::STILE + ((rr - R) / 2) * SPITCH);
 #pragma unroll
       for (int j = 0; j < kG; ++j) {
-        const int il = gI * kG + j;  // row within my half
-        const unsigned bts = pass_bits >> (2 * il);
-        stg_stream2(gp + (h * RIH + il) * kW + 2 * p, make_float2((bts & 1u) ? acc[j].x : 0.f, (bts & 2u) ? acc[j].y : 0.f));
+        const int k = rr - j;
+        if (k >= 0 && k < TAPS) acc[j] = fma2w(a.wv[2 * R - k], v, acc[j]);
       }
+    }
+    if (q == 0 && h == 0) {  // image top: g[m] += Σ_{i=0}^{R−m} wv[R − m − i]·s[i],  1 ≤ m ≤ R
+#pragma unroll
+      for (int i = 0; i < R; ++i) {
+        const float2 v = *reinterpret_cast<const float2*>(Sx + (i & 1) * Cfg::STILE + (size_t)(i >> 1) * SPITCH + Cfg::SP + 2 * p);
+#pragma unroll
+        for (int m = 1; m <= R && m < kG; ++m)
+          if (i <= R - m) acc[m] = fma2w(a.wv[R - m - i], v, acc[m]);
+      }
+    }
+    if (q == kCluster - 1 && h == 1) {  // image bottom: g[31 − a'] += Σ_{b=0}^{R−a'} wv[R + a' + b]·s[31 − b],  1 ≤ a' ≤ R
+#pragma unroll
+      for (int b = 0; b < R; ++b) {
+        const int lr = kRI - 1 - b;
+        const float2 v = *reinterpret_cast<const float2*>(Sx + (lr & 1) * Cfg::STILE + (size_t)(lr >> 1) * SPITCH + Cfg::SP + 2 * p);
+#pragma unroll
+        for (int ap = 1; ap <= R && ap < kG; ++ap)
+          if (b <= R - ap) acc[kG - 1 - ap] = fma2w(a.wv[R + ap + b], v, acc[kG - 1 - ap]);
+      }
+    }
+    float* gp = a.g + n * a.g_stride + poff + (size_t)(h * kG) * kW + 2 * p;
+#pragma unroll
+    for (int j = 0; j < kG; ++j) {
+      const unsigned bts = pass_bits >> (2 * j);
+      stg_stream2(gp + j * kW, make_float2((bts & 1u) ? acc[j].x : 0.f, (bts & 2u) ? acc[j].y : 0.f));
     }
   }
   cluster.sync();  // #4: the neighbours may still be reading my s rows
@@ -340,9 +373,9 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kT, 3) sep_gu
 
 template <int R>
 int launch_sepf(const dps_operator* op, const SepFusedArgs& a, int n, cudaStream_t st) {
-  DPS_SMEM_OPTIN((sep_guidance_kernel<R>), sepf_smem<R>(), op->device);
+  DPS_SMEM_OPTIN((sep_guidance_kernel<R>), SepCfg<R>::SMEM, op->device);
   dim3 grid((unsigned)((int64_t)op->C * n * kCluster));
-  sep_guidance_kernel<R><<<grid, kT, sepf_smem<R>(), st>>>(a);
+  sep_guidance_kernel<R><<<grid, kT, SepCfg<R>::SMEM, st>>>(a);
   DPS_LAUNCH_CHECK("sep_guidance");
   return DPS_OK;
 }
