@@ -66,11 +66,54 @@ struct SepCfg {
   static constexpr int CTAS = SMEM + 1024 <= 233472 / 3 ? 3 : 2;
 };
 
-DPS_DEV void cl_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+#ifdef DPS_SEPF_TRACE  // experiment builds only (tools/build_variant.sh): per-CTA phase timestamps of the first 4096 CTAs
+__device__ long long sepf_trace[4096 * 16];
+#define SEPF_T(i) do { if (threadIdx.x == 0 && blockIdx.x < 4096) sepf_trace[blockIdx.x * 16 + (i)] = clock64(); } while (0)
+#else
+#define SEPF_T(i) do { } while (0)
+#endif
+
+// Cluster barrier halves (arrive early, wait late).  What an arrive has to guarantee, and how (A/B switches for experiment
+// builds; see the stress test tools/sepf_stress.py):
+//   publish   — my CTA's shared-memory stores are visible to the neighbours that read them over DSMEM after their wait:
+//               DPS_SEPF_PUB 0: barrier.cluster.arrive.release by every thread (ptxas: MEMBAR.ALL.GPU per warp, ≈2.5 k cycles);
+//                            1: bar.sync, ONE warp executes fence.acq_rel.cluster (cumulative), every thread arrives relaxed.
+//   done      — my loads from the neighbours' tiles have completed (they may overwrite the tile, or exit):
+//               DPS_SEPF_DONE 0: arrive.release by every thread;
+//                             1: relaxed arrive predicated on a value that depends on every halo load (acc[0] and acc[15] of the
+//                                window cover all 2R halo rows): ptxas cannot schedule it above the FMAs that consume the loads.
+#ifndef DPS_SEPF_PUB
+#define DPS_SEPF_PUB 1
+#endif
+#ifndef DPS_SEPF_DONE
+#define DPS_SEPF_DONE 1
+#endif
+DPS_DEV void cl_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+DPS_DEV void cl_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
+// `synced`: a bar.sync after the last store has already been executed by the caller
+DPS_DEV void cl_arrive_publish(bool synced) {
+#if DPS_SEPF_PUB == 0
+  cl_arrive_release();
+#else
+  if (!synced) __syncthreads();
+  if (threadIdx.x < 32) asm volatile("fence.acq_rel.cluster;" ::: "memory");
+  cl_arrive_relaxed();
+#endif
+}
+DPS_DEV void cl_arrive_done_reading(float dep0, float dep1) {
+#if DPS_SEPF_DONE == 0
+  cl_arrive_release();
+#else
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .f32 t;\n\tadd.rn.f32 t, %0, %1;\n\tsetp.neu.f32 p, t, t;\n\t"
+      "@p barrier.cluster.arrive.relaxed;\n\t@!p barrier.cluster.arrive.relaxed;\n\t}" ::"f"(dep0), "f"(dep1)
+      : "memory");
+#endif
+}
 DPS_DEV void cl_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
-DPS_DEV unsigned mapa_u32(unsigned addr, unsigned rank) {
+DPS_DEV unsigned mapa_u32(unsigned addr, unsigned rank) {  // volatile: computed where it is written, not hoisted (and spilled)
   unsigned r;
-  asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
 // 64-bit load from the cluster's distributed shared memory (own or a neighbour CTA's tile); volatile: never moved across a barrier
@@ -88,6 +131,12 @@ DPS_DEV float2 ld_cluster2_or_zero(unsigned addr, int valid) {  // predicated: r
       : "r"(addr), "r"(valid));
   return v;
 }
+// volatile read-only load: issued where it is written (ptxas otherwise sinks the y loads below the barrier that follows them)
+DPS_DEV float4 ldg_ro4_pinned(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
 DPS_DEV float2 fma2w(float w, float2 v, float2 acc) { return __ffma2_rn(make_float2(w, w), v, acc); }  // FFMA2 R, R, UR.F32, R
 
 // Every FMA of the four passes is an FFMA2 (fma.rn.f32x2) whose weight is a uniform-register broadcast.  The vertical passes
@@ -95,6 +144,8 @@ DPS_DEV float2 fma2w(float w, float2 v, float2 acc) { return __ffma2_rn(make_flo
 // the row), the horizontal passes pair two adjacent ROWS (a thread owns a row pair and a run of 16 / 18 columns: 128-bit loads
 // of a tile stored row-pair interleaved, T2[row pair][column] = (row a, row b), lanes along the row pairs).  All loops are
 // fully unrolled over compile-time offsets and free of branches, so a pass is "load, 16 FFMA2, load, …" and nothing else.
+// Both vertical passes start with the 16 window rows the CTA owns (61 % of the FMAs) BETWEEN the arrive and the wait of the
+// cluster barrier that publishes the tile, and read the 2R halo rows afterwards: the skew between the 8 CTAs hides behind work.
 template <int R>
 __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kT, SepCfg<R>::CTAS) sep_guidance_kernel(const __grid_constant__ SepFusedArgs a) {
   using Cfg = SepCfg<R>;
@@ -114,9 +165,8 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kT, SepCfg<R>
   const int p = tid & 127, h = tid >> 7;               // vertical passes: column pair, row half
   const int rp = tid & 15, cb = tid >> 4;              // horizontal passes: row pair, column block
   const int64_t poff = (int64_t)c * H * kW + (int64_t)q * kRI * kW;
-  const float* xg = a.src.x + n * a.src.x_stride + poff;
-  const float* eg = a.src.eps + n * a.src.eps_stride + poff;
 
+  SEPF_T(0);
   if (tid == 0) {
 #pragma unroll
     for (int ch = 0; ch < kChunks; ++ch) mbar_init(bar + ch, 1);
@@ -124,6 +174,8 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kT, SepCfg<R>
   }
   __syncthreads();
   if (tid == 0) {
+    const float* xg = a.src.x + n * a.src.x_stride + poff;
+    const float* eg = a.src.eps + n * a.src.eps_stride + poff;
     constexpr unsigned bytes = kChunkRows * kW * sizeof(float);
 #pragma unroll
     for (int ch = 0; ch < kChunks; ++ch) {
@@ -149,47 +201,62 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kT, SepCfg<R>
       }
     }
   }
-  const unsigned own_a = mapa_u32(smem_u32(Sx), (unsigned)q);  // region A of this CTA / its neighbours in the cluster window
-  const unsigned up_a = mapa_u32(smem_u32(Sx), (unsigned)(q > 0 ? q - 1 : q));
-  const unsigned dn_a = mapa_u32(smem_u32(Sx), (unsigned)(q < kCluster - 1 ? q + 1 : q));
-  cluster.sync();  // #1: every CTA's x̂₀ rows are in place; the ε rows are dead
+  asm volatile("" : "+r"(pass_bits));  // one register, not sixteen scalar-replaced (and spilled) row masks
+  SEPF_T(1);
+  cl_arrive_publish(false);  // #1 (arrive): my x̂₀ values are in place
 
   // ---- 1. vertical forward for my column pair, rows 16h..16h+15 → T2 (row-pair interleaved, column-padded by mirroring) ----
   {
-    // The first R and the last R rows of the window are halo rows for one of the two halves: neighbour rows over DSMEM or, at
-    // the image border, own rows mirrored without edge repeat (−m ↦ m, 31 + m ↦ 31 − m) — one base and one signed row stride.
-    unsigned a0, a1;
-    int s0, s1;
-    if (h == 0) {
-      a0 = q > 0 ? up_a + (kRI - R) * kRowB : own_a + R * kRowB;
-      s0 = q > 0 ? kRowB : -kRowB;
-      a1 = own_a + kG * kRowB;
-      s1 = kRowB;
-    } else {
-      a0 = own_a + (kG - R) * kRowB;
-      s0 = kRowB;
-      a1 = q < kCluster - 1 ? dn_a : own_a + (kRI - 2) * kRowB;
-      s1 = q < kCluster - 1 ? kRowB : -kRowB;
-    }
-    a0 += p * 8;
-    a1 += p * 8;
-    const float2* mid = reinterpret_cast<const float2*>(Sx + h * kG * kW) + p;  // rows 16h + (rr − R), R ≤ rr < 16 + R
     float2 acc[kG];
 #pragma unroll
     for (int j = 0; j < kG; ++j) acc[j] = make_float2(0.f, 0.f);
+    {  // window rows R ≤ rr < 16 + R: rows 16h + (rr − R), the x̂₀ values this very thread has just written
+      const float2* mid = reinterpret_cast<const float2*>(Sx + h * kG * kW) + p;
 #pragma unroll
-    for (int rr = 0; rr < kG + 2 * R; ++rr) {
-      float2 v;
-      if (rr < R) v = ld_cluster2(a0 + rr * s0);
-      else if (rr >= kG + R) v = ld_cluster2(a1 + (rr - kG - R) * s1);
-      else v = mid[(rr - R) * (kW / 2)];
+      for (int rr = R; rr < kG + R; ++rr) {
+        const float2 v = mid[(rr - R) * (kW / 2)];
 #pragma unroll
-      for (int j = 0; j < kG; ++j) {
-        const int k = rr - j;
-        if (k >= 0 && k < TAPS) acc[j] = fma2w(a.wv[k], v, acc[j]);
+        for (int j = 0; j < kG; ++j) {
+          const int k = rr - j;
+          if (k >= 0 && k < TAPS) acc[j] = fma2w(a.wv[k], v, acc[j]);
+        }
       }
     }
-    cl_arrive();  // #2 (arrive): my reads of the neighbours' x̂₀ rows are done
+    SEPF_T(2);
+    cl_wait();  // #1 (wait): every CTA's x̂₀ rows are in place; the ε rows are dead
+    SEPF_T(3);
+    {
+      // The first R and the last R rows of the window are halo rows for one of the two halves: neighbour rows over DSMEM or, at
+      // the image border, own rows mirrored without edge repeat (−m ↦ m, 31 + m ↦ 31 − m) — one base and one signed row stride.
+      const unsigned sx = smem_u32(Sx);
+      const unsigned own_a = mapa_u32(sx, (unsigned)q);
+      unsigned a0, a1;
+      int s0, s1;
+      if (h == 0) {
+        a0 = q > 0 ? mapa_u32(sx, (unsigned)(q - 1)) + (kRI - R) * kRowB : own_a + R * kRowB;
+        s0 = q > 0 ? kRowB : -kRowB;
+        a1 = own_a + kG * kRowB;
+        s1 = kRowB;
+      } else {
+        a0 = own_a + (kG - R) * kRowB;
+        s0 = kRowB;
+        a1 = q < kCluster - 1 ? mapa_u32(sx, (unsigned)(q + 1)) : own_a + (kRI - 2) * kRowB;
+        s1 = q < kCluster - 1 ? kRowB : -kRowB;
+      }
+      a0 += p * 8;
+      a1 += p * 8;
+#pragma unroll
+      for (int rr = 0; rr < kG + 2 * R; ++rr) {
+        if (rr >= R && rr < kG + R) continue;
+        const float2 v = rr < R ? ld_cluster2(a0 + rr * s0) : ld_cluster2(a1 + (rr - kG - R) * s1);
+#pragma unroll
+        for (int j = 0; j < kG; ++j) {
+          const int k = rr - j;
+          if (k >= 0 && k < TAPS) acc[j] = fma2w(a.wv[k], v, acc[j]);
+        }
+      }
+    }
+    cl_arrive_done_reading(acc[0].x, acc[kG - 1].x);  // #2 (arrive): my reads of the neighbours' x̂₀ rows are done (their values have been consumed)
     float2* row0 = T2 + (size_t)(h * (kG / 2)) * TPITCH + Cfg::TP;
 #pragma unroll
     for (int jp = 0; jp < kG / 2; ++jp)
@@ -207,11 +274,12 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kT, SepCfg<R>
       }
     }
   }
+  SEPF_T(4);
   __syncthreads();  // T2 complete
+  SEPF_T(5);
 
   // ---- 2. horizontal forward + residual: thread = row pair rp, columns 16cb..16cb+15 ----
   float2 o[kNB];  // (row a, row b) per column; 16 used here, 18 by the adjoint
-  float sq = 0.f, ab = 0.f;
   {
     const float4* tp = reinterpret_cast<const float4*>(T2 + (size_t)rp * TPITCH + 16 * cb);  // padded column 16cb = image column 16cb − R
 #pragma unroll
@@ -229,23 +297,32 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kT, SepCfg<R>
         }
       }
     }
+    SEPF_T(6);
     const int rowa = 2 * rp;
-    if (a.y) {
+    if (a.y) {  // the measurement rows (L2-resident: one y for all particles) are requested before the barrier, used after it
       const float* yp = a.y + n * a.y_stride + poff + rowa * kW + 16 * cb;
+      float4 ya[4], yb[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { ya[i] = ldg_ro4_pinned(yp + 4 * i); yb[i] = ldg_ro4_pinned(yp + kW + 4 * i); }
+      __syncthreads();  // everybody is done reading T2 → region B may take Z2
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const float4 ya = ldg_ro4(yp + 4 * i), yb = ldg_ro4(yp + kW + 4 * i);
-        o[4 * i + 0] = make_float2(__fsub_rn(ya.x, o[4 * i + 0].x), __fsub_rn(yb.x, o[4 * i + 0].y));
-        o[4 * i + 1] = make_float2(__fsub_rn(ya.y, o[4 * i + 1].x), __fsub_rn(yb.y, o[4 * i + 1].y));
-        o[4 * i + 2] = make_float2(__fsub_rn(ya.z, o[4 * i + 2].x), __fsub_rn(yb.z, o[4 * i + 2].y));
-        o[4 * i + 3] = make_float2(__fsub_rn(ya.w, o[4 * i + 3].x), __fsub_rn(yb.w, o[4 * i + 3].y));
+        o[4 * i + 0] = make_float2(__fsub_rn(ya[i].x, o[4 * i + 0].x), __fsub_rn(yb[i].x, o[4 * i + 0].y));
+        o[4 * i + 1] = make_float2(__fsub_rn(ya[i].y, o[4 * i + 1].x), __fsub_rn(yb[i].y, o[4 * i + 1].y));
+        o[4 * i + 2] = make_float2(__fsub_rn(ya[i].z, o[4 * i + 2].x), __fsub_rn(yb[i].z, o[4 * i + 2].y));
+        o[4 * i + 3] = make_float2(__fsub_rn(ya[i].w, o[4 * i + 3].x), __fsub_rn(yb[i].w, o[4 * i + 3].y));
       }
+    } else {
+      __syncthreads();
     }
+    // ---- 3a. Z2 = zero-padded r, same interleaved layout ----
+    float2* zrow = T2 + (size_t)rp * ZPITCH;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      sq = fmaf(o[j].x, o[j].x, fmaf(o[j].y, o[j].y, sq));
-      ab += fabsf(o[j].x) + fabsf(o[j].y);
-    }
+    for (int i = 0; i < 8; ++i)
+      *reinterpret_cast<float4*>(zrow + Cfg::ZP + 16 * cb + 2 * i) = make_float4(o[2 * i].x, o[2 * i].y, o[2 * i + 1].x, o[2 * i + 1].y);
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = cb; i < Cfg::ZP / 2; i += 16) *reinterpret_cast<float4*>(zrow + 2 * i) = z4;
+    for (int i = cb; i < (ZPITCH - Cfg::ZP - kW) / 2; i += 16) *reinterpret_cast<float4*>(zrow + Cfg::ZP + kW + 2 * i) = z4;
     if (a.r_out) {
       float* ro = a.r_out + ((int64_t)n * a.C + c) * H * kW + (int64_t)(q * kRI + rowa) * kW + 16 * cb;
 #pragma unroll
@@ -254,31 +331,36 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kT, SepCfg<R>
         stg_stream4(ro + kW + 4 * i, make_float4(o[4 * i].y, o[4 * i + 1].y, o[4 * i + 2].y, o[4 * i + 3].y));
       }
     }
+    if (a.partials) {  // per-CTA Σr², Σ|r|: warp sums now, the 8 per-warp values are added by warp 0 behind the next barrier
+      float sq = 0.f, ab = 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        sq = fmaf(o[j].x, o[j].x, fmaf(o[j].y, o[j].y, sq));
+        ab += fabsf(o[j].x) + fabsf(o[j].y);
+      }
+      sq = warp_sum(sq);
+      ab = warp_sum(ab);
+      if ((tid & 31) == 0) {
+        red[tid >> 5] = sq;
+        red[32 + (tid >> 5)] = ab;
+      }
+    }
   }
-  if (a.partials) {
-    block_sum2(sq, ab, red);
+  __syncthreads();  // Z2 and the per-warp sums are complete
+  SEPF_T(7);
+  if (a.partials && tid < 32) {
+    float sq = tid < kT / 32 ? red[tid] : 0.0f, ab = tid < kT / 32 ? red[32 + tid] : 0.0f;
+    sq = warp_sum(sq);
+    ab = warp_sum(ab);
     if (tid == 0) {
       float* pp = a.partials + ((int64_t)n * (a.C * kCluster) + c * kCluster + q) * 2;
       pp[0] = sq;
       pp[1] = ab;
     }
-  } else {
-    __syncthreads();
   }
-  // (a barrier has passed: everybody is done reading T2)
-  // ---- 3. horizontal adjoint on the PADDED domain: Z2 = zero-padded r, t[P] = Σ_d wh[R − d]·r[P + d] for P ∈ [−R, 256 + R),
-  //         thread = row pair rp, 18 columns from −16 + 18cb; the pad outputs are folded onto their mirror columns afterwards
-  //         (Aᵀ = Pᵀ Cᵀ: what the mirrored padding read twice comes back twice). ----
-  {
-    float2* zrow = T2 + (size_t)rp * ZPITCH;
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-      *reinterpret_cast<float4*>(zrow + Cfg::ZP + 16 * cb + 2 * i) = make_float4(o[2 * i].x, o[2 * i].y, o[2 * i + 1].x, o[2 * i + 1].y);
-    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int i = cb; i < Cfg::ZP / 2; i += 16) *reinterpret_cast<float4*>(zrow + 2 * i) = z4;
-    for (int i = cb; i < (ZPITCH - Cfg::ZP - kW) / 2; i += 16) *reinterpret_cast<float4*>(zrow + Cfg::ZP + kW + 2 * i) = z4;
-  }
-  __syncthreads();
+  // ---- 3b. horizontal adjoint on the PADDED domain: t[P] = Σ_d wh[R − d]·r[P + d] for P ∈ [−R, 256 + R), thread = row pair rp,
+  //          18 columns from −16 + 18cb; the pad outputs are folded onto their mirror columns afterwards (Aᵀ = Pᵀ Cᵀ: what the
+  //          mirrored padding read twice comes back twice). ----
   {
     const float4* tp = reinterpret_cast<const float4*>(T2 + (size_t)rp * ZPITCH + kNB * cb);  // Z2 index ZP + (−16 + 18cb) − R
 #pragma unroll
@@ -297,6 +379,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kT, SepCfg<R>
       }
     }
   }
+  SEPF_T(8);
   cl_wait();  // #2 (wait): the neighbours are done reading my x̂₀ rows → region A may take s
   {
     float* se = Sx + (size_t)rp * SPITCH + Cfg::SP - kSL + kNB * cb;  // row 2rp (even tile); the odd tile follows at STILE
@@ -310,36 +393,36 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kT, SepCfg<R>
     }
   }
   __syncthreads();
-  for (int id = tid; id < kRI * 2 * R; id += kT) {  // fold: (row, side, m)
-    const int row = id / (2 * R), rem = id - row * (2 * R), side = rem / R, m = rem - side * R + 1;
+  {  // fold the pad columns onto their mirrors: thread = row (tid & 31), m = 1 + (tid >> 5) + 8i, both sides
+    const int row = tid & 31;
     float* srow = Sx + (row & 1) * Cfg::STILE + (size_t)(row >> 1) * SPITCH + Cfg::SP;
-    if (side == 0) srow[m] += srow[-m];
-    else srow[kW - 1 - m] += srow[kW - 1 + m];
+#pragma unroll
+    for (int m = 1 + (tid >> 5); m <= R; m += kT / 32) {
+      srow[m] += srow[-m];
+      srow[kW - 1 - m] += srow[kW - 1 + m];
+    }
   }
-  cluster.sync();  // #3: every CTA's s rows are in place
+  __syncthreads();
+  SEPF_T(9);
+  cl_arrive_publish(true);  // #3 (arrive): my s rows are in place
 
   // ---- 4. vertical adjoint for my column pair, rows 16h..16h+15, + border folds + clamp mask ----
   {
     // window row lr = 16h − R + rr lives in parity tile (rr & 1) at tile row (lr >> 1): compile-time offsets from three bases
     constexpr int kRowPB = SPITCH * (int)sizeof(float), kTileB = Cfg::STILE * (int)sizeof(float);
-    const unsigned colb = (Cfg::SP + 2 * p) * (unsigned)sizeof(float);
-    const unsigned b0 = (h == 0 ? up_a + (kRI / 2) * kRowPB : own_a + (kG / 2) * kRowPB) + colb;   // rr < R: tile row (h ? 8 : 16 of the upper CTA) + (rr − R)/2
-    const unsigned b1 = (h == 0 ? own_a + (kG / 2) * kRowPB : dn_a) + colb;                        // rr ≥ 16 + R: tile row (h ? 0 of the lower CTA : 8) + (rr − 16 − R)/2
-    const int v0 = (h == 1 || q > 0) ? 1 : 0, v1 = (h == 0 || q < kCluster - 1) ? 1 : 0;           // rows outside the image contribute nothing to the plain part
-    const float* mid = Sx + (size_t)(h * (kG / 2)) * SPITCH + Cfg::SP + 2 * p;
     float2 acc[kG];
 #pragma unroll
     for (int j = 0; j < kG; ++j) acc[j] = make_float2(0.f, 0.f);
+    {
+      const float* mid = Sx + (size_t)(h * (kG / 2)) * SPITCH + Cfg::SP + 2 * p;
 #pragma unroll
-    for (int rr = 0; rr < kG + 2 * R; ++rr) {
-      float2 v;
-      if (rr < R) v = ld_cluster2_or_zero(b0 + (rr & 1) * kTileB + ((rr - R - (rr & 1)) / 2) * kRowPB, v0);
-      else if (rr >= kG + R) v = ld_cluster2_or_zero(b1 + (rr & 1) * kTileB + ((rr - kG - R) / 2) * kRowPB, v1);
-      else v = *reinterpret_cast<const float2*>(mid + (rr & 1) * Cfg::STILE + ((rr - R) / 2) * SPITCH);
+      for (int rr = R; rr < kG + R; ++rr) {
+        const float2 v = *reinterpret_cast<const float2*>(mid + (rr & 1) * Cfg::STILE + ((rr - R) / 2) * SPITCH);
 #pragma unroll
-      for (int j = 0; j < kG; ++j) {
-        const int k = rr - j;
-        if (k >= 0 && k < TAPS) acc[j] = fma2w(a.wv[2 * R - k], v, acc[j]);
+        for (int j = 0; j < kG; ++j) {
+          const int k = rr - j;
+          if (k >= 0 && k < TAPS) acc[j] = fma2w(a.wv[2 * R - k], v, acc[j]);
+        }
       }
     }
     if (q == 0 && h == 0) {  // image top: g[m] += Σ_{i=0}^{R−m} wv[R − m − i]·s[i],  1 ≤ m ≤ R
@@ -361,6 +444,29 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kT, SepCfg<R>
           if (b <= R - ap) acc[kG - 1 - ap] = fma2w(a.wv[R + ap + b], v, acc[kG - 1 - ap]);
       }
     }
+    SEPF_T(10);
+    cl_wait();  // #3 (wait): every CTA's s rows are in place
+    SEPF_T(11);
+    {
+      const unsigned sx = smem_u32(Sx);
+      const unsigned colb = (Cfg::SP + 2 * p) * (unsigned)sizeof(float);
+      // rr < R: tile row (h ? 8 : 16 of the upper CTA) + (rr − R)/2;  rr ≥ 16 + R: tile row (h ? 0 of the lower CTA : 8) + (rr − 16 − R)/2
+      const unsigned b0 = (h == 0 ? mapa_u32(sx, (unsigned)(q > 0 ? q - 1 : q)) + (kRI / 2) * kRowPB : mapa_u32(sx, (unsigned)q) + (kG / 2) * kRowPB) + colb;
+      const unsigned b1 = (h == 0 ? mapa_u32(sx, (unsigned)q) + (kG / 2) * kRowPB : mapa_u32(sx, (unsigned)(q < kCluster - 1 ? q + 1 : q))) + colb;
+      const int v0 = (h == 1 || q > 0) ? 1 : 0, v1 = (h == 0 || q < kCluster - 1) ? 1 : 0;  // rows outside the image contribute nothing to the plain part
+#pragma unroll
+      for (int rr = 0; rr < kG + 2 * R; ++rr) {
+        if (rr >= R && rr < kG + R) continue;
+        const float2 v = rr < R ? ld_cluster2_or_zero(b0 + (rr & 1) * kTileB + ((rr - R - (rr & 1)) / 2) * kRowPB, v0)
+                                : ld_cluster2_or_zero(b1 + (rr & 1) * kTileB + ((rr - kG - R) / 2) * kRowPB, v1);
+#pragma unroll
+        for (int j = 0; j < kG; ++j) {
+          const int k = rr - j;
+          if (k >= 0 && k < TAPS) acc[j] = fma2w(a.wv[2 * R - k], v, acc[j]);
+        }
+      }
+    }
+    cl_arrive_done_reading(acc[0].x, acc[kG - 1].x);  // #4 (arrive): my reads of the neighbours' s rows are done
     float* gp = a.g + n * a.g_stride + poff + (size_t)(h * kG) * kW + 2 * p;
 #pragma unroll
     for (int j = 0; j < kG; ++j) {
@@ -368,7 +474,11 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kT, SepCfg<R>
       stg_stream2(gp + j * kW, make_float2((bts & 1u) ? acc[j].x : 0.f, (bts & 2u) ? acc[j].y : 0.f));
     }
   }
-  cluster.sync();  // #4: the neighbours may still be reading my s rows
+  cl_wait();  // #4 (wait): no CTA leaves while a neighbour may still read its s rows
+  SEPF_T(12);
+#ifdef DPS_SEPF_TRACE
+  if (threadIdx.x == 0 && blockIdx.x < 4096) { unsigned sm; asm("mov.u32 %0, %smid;" : "=r"(sm)); sepf_trace[blockIdx.x * 16 + 15] = sm; }
+#endif
 }
 
 template <int R>
@@ -380,6 +490,12 @@ int launch_sepf(const dps_operator* op, const SepFusedArgs& a, int n, cudaStream
   return DPS_OK;
 }
 }  // namespace
+
+#ifdef DPS_SEPF_TRACE
+extern "C" int dps_debug_sepf_trace(long long* host_out) {
+  return (int)cudaMemcpyFromSymbol(host_out, sepf_trace, sizeof(long long) * 4096 * 16);
+}
+#endif
 
 // Called by sep_create with the raw 1-D taps (radius rv / rh around the centre).  Leaves op->sepfused null when not covered.
 int sep_fused_create(dps_operator* op, const float* taps_v, int rv, const float* taps_h, int rh) {
