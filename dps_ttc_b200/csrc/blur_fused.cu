@@ -74,7 +74,7 @@ __device__ long long sepf_trace[4096 * 16];
 #endif
 
 // Cluster barrier halves (arrive early, wait late).  What an arrive has to guarantee, and how (A/B switches for experiment
-// builds; see the stress test tools/sepf_stress.py):
+// builds; see the stress test tools/fused_stress.py):
 //   publish   — my CTA's shared-memory stores are visible to the neighbours that read them over DSMEM after their wait:
 //               DPS_SEPF_PUB 0: barrier.cluster.arrive.release by every thread (ptxas: MEMBAR.ALL.GPU per warp, ≈2.5 k cycles);
 //                            1: bar.sync, ONE warp executes fence.acq_rel.cluster (cumulative), every thread arrives relaxed.

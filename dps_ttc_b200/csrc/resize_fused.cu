@@ -68,8 +68,48 @@ size_t fused_smem() {
   return sizeof(float) * ((size_t)2 * kRI * kW + (size_t)kRI * 4 + 64) + 8 * kChunks;
 }
 
-DPS_DEV void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+// Cluster barrier halves (same scheme as blur_fused.cu, measured there with a per-phase clock trace): an
+// barrier.cluster.arrive.release costs every warp a MEMBAR.ALL.GPU (≈2.5 k cycles — a quarter of this kernel at 8 particles).
+//   publish  — bar.sync, then ONE warp executes the (cumulative) cluster-scope fence, every thread arrives relaxed;
+//   done     — "my loads from the neighbours' tiles have completed": a relaxed arrive predicated on a value that depends on
+//              every remote load, so that ptxas cannot schedule it above the instructions that consume them.
+// DPS_RSF_FULL_RELEASE=1 restores arrive.release everywhere (A/B builds).
+#ifdef DPS_RSF_TRACE  // experiment builds only (tools/build_variant.sh): per-CTA phase timestamps of the first 4096 CTAs
+__device__ long long rsf_trace[4096 * 16];
+#define RSF_T(i) do { if (threadIdx.x == 0 && blockIdx.x < 4096) rsf_trace[blockIdx.x * 16 + (i)] = clock64(); } while (0)
+#else
+#define RSF_T(i) do { } while (0)
+#endif
+DPS_DEV void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 DPS_DEV void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+DPS_DEV void cluster_arrive_publish_synced() {  // the caller has executed a bar.sync after the last store
+#ifdef DPS_RSF_FULL_RELEASE
+  cluster_arrive_release();
+#else
+  if (threadIdx.x < 32) asm volatile("fence.acq_rel.cluster;" ::: "memory");
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+#endif
+}
+DPS_DEV void cluster_arrive_done_reading(float dep0, float dep1) {
+#ifdef DPS_RSF_FULL_RELEASE
+  cluster_arrive_release();
+#else
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .f32 t;\n\tadd.rn.f32 t, %0, %1;\n\tsetp.neu.f32 p, t, t;\n\t"
+      "@p barrier.cluster.arrive.relaxed;\n\t@!p barrier.cluster.arrive.relaxed;\n\t}" ::"f"(dep0), "f"(dep1)
+      : "memory");
+#endif
+}
+DPS_DEV unsigned mapa_u32(unsigned addr, unsigned rank) {
+  unsigned r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+DPS_DEV float ld_cluster(unsigned addr) {  // volatile: never moved across a barrier
+  float v;
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
 
 template <int F>
 __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kT, 3) resize_guidance_kernel(const __grid_constant__ FusedArgs a) {
@@ -93,6 +133,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kT, 3) resize
   const float* xg = a.src.x + n * a.src.x_stride + poff;
   const float* eg = a.src.eps + n * a.src.eps_stride + poff;
 
+  RSF_T(0);
   if (tid == 0) {
 #pragma unroll
     for (int ch = 0; ch < kChunks; ++ch) mbar_init(bar + ch, 1);
@@ -120,6 +161,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kT, 3) resize
     yv[u] = (yp && o < RJ * OW) ? ldg_ro(yp + o) : 0.f;
   }
   stage_wait();
+  RSF_T(1);
   // ---- 0. x̂₀ in place, chunk by chunk as the copies land; clamp mask of my column → one register ----
   unsigned pass_bits = 0;
   {
@@ -136,29 +178,53 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kT, 3) resize
       }
     }
   }
-  cluster.sync();  // every CTA's x̂₀ rows are in place (and nobody reads the ε buffer any more)
+  RSF_T(2);
+  __syncthreads();
+  cluster_arrive_publish_synced();  // #1 (arrive): my x̂₀ rows are in place
 
   // ---- 1. H pass: t[jj][col] = Σ_k w[k] · x̂₀[sym(F·(RJ·q + jj) − HALO + k)][col] ----
   {
-    const float* up = q > 0 ? cluster.map_shared_rank(Sx, q - 1) : Sx;
-    const float* dn = q < kCluster - 1 ? cluster.map_shared_rank(Sx, q + 1) : Sx;
     float acc[RJ];
 #pragma unroll
     for (int jj = 0; jj < RJ; ++jj) acc[jj] = 0.f;
+    // Between the arrive and the wait: every term that needs only my own rows and comes FIRST in its accumulator (the order
+    // of the additions stays k = 0, 1, …: bit-identical to the two-kernel path) — residual rows whose window starts inside my
+    // rows, up to my last row; 69 % of the FMAs at F = 4.
+#pragma unroll
+    for (int lr = 0; lr < kRI; ++lr) {
+      const float v = Sx[lr * kW + tid];
+#pragma unroll
+      for (int jj = 0; jj < RJ; ++jj) {
+        const int k = lr + HALO - F * jj;  // compile-time after unrolling
+        if (F * jj - HALO >= 0 && k >= 0 && k < TAPS) acc[jj] = fmaf(a.w[k], v, acc[jj]);
+      }
+    }
+    RSF_T(3);
+    cluster_wait();  // #1 (wait): every CTA's x̂₀ rows are in place (and nobody reads the ε buffer any more)
+    RSF_T(4);
+    // halo rows: the neighbour's rows over DSMEM or, at the image border, my own rows mirrored WITH edge repeat
+    // (−1 ↦ 0, −2 ↦ 1 …; 32 ↦ 31, 33 ↦ 30 …) — one base and one signed row stride each
+    const unsigned sx = smem_u32(Sx) + tid * 4;
+    constexpr int kRowB = kW * (int)sizeof(float);
+    const unsigned a_up = q > 0 ? mapa_u32(sx, (unsigned)(q - 1)) + (kRI - HALO) * kRowB : mapa_u32(sx, (unsigned)q) + (HALO - 1) * kRowB;
+    const int s_up = q > 0 ? kRowB : -kRowB;
+    const unsigned a_dn = q < kCluster - 1 ? mapa_u32(sx, (unsigned)(q + 1)) : mapa_u32(sx, (unsigned)q) + (kRI - 1) * kRowB;
+    const int s_dn = q < kCluster - 1 ? kRowB : -kRowB;
 #pragma unroll
     for (int wdx = 0; wdx < kRI + 2 * HALO; ++wdx) {
       const int lr = wdx - HALO;  // row relative to my first image row
-      float v;
-      if (lr < 0)  // above my rows: the neighbour's last rows, or (top of the image) my own rows mirrored: −1 ↦ 0, −2 ↦ 1 …
-        v = q > 0 ? up[(kRI + lr) * kW + tid] : Sx[(-lr - 1) * kW + tid];
-      else if (lr >= kRI)
-        v = q < kCluster - 1 ? dn[(lr - kRI) * kW + tid] : Sx[(2 * kRI - 1 - lr) * kW + tid];
-      else
-        v = Sx[lr * kW + tid];
+      bool used = false;
 #pragma unroll
       for (int jj = 0; jj < RJ; ++jj) {
-        const int k = wdx - F * jj;  // compile-time after unrolling
-        if (k >= 0 && k < TAPS) acc[jj] = fmaf(a.w[k], v, acc[jj]);
+        const int k = wdx - F * jj;
+        used = used || (k >= 0 && k < TAPS && !(F * jj - HALO >= 0 && lr < kRI));
+      }
+      if (!used) continue;
+      const float v = lr < 0 ? ld_cluster(a_up + wdx * s_up) : (lr >= kRI ? ld_cluster(a_dn + (lr - kRI) * s_dn) : Sx[lr * kW + tid]);
+#pragma unroll
+      for (int jj = 0; jj < RJ; ++jj) {
+        const int k = wdx - F * jj;
+        if (k >= 0 && k < TAPS && !(F * jj - HALO >= 0 && lr < kRI)) acc[jj] = fmaf(a.w[k], v, acc[jj]);
       }
     }
 #pragma unroll
@@ -171,6 +237,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kT, 3) resize
   }
   __syncthreads();
 
+  RSF_T(5);
   // ---- 2. W pass, residual, partial sums ----
   float sq = 0.f, ab = 0.f;
 #pragma unroll
@@ -195,8 +262,9 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kT, 3) resize
       ab += fabsf(res);
     }
   }
-  __syncthreads();  // my residual rows are complete …
-  cluster_arrive();  // … and announced; the partial sums below overlap the other CTAs' arrival
+  RSF_T(6);
+  __syncthreads();                  // my residual rows are complete …
+  cluster_arrive_publish_synced();  // #2 (arrive) … and announced; the partial sums below overlap the other CTAs' arrival
   if (a.partials) {
     block_sum2(sq, ab, red);
     if (tid == 0) {
@@ -223,7 +291,9 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kT, 3) resize
     };
 #pragma unroll
     for (int m = 2; m < RJ + 2; ++m) uu[m] = urow(Sr + (m - 2) * OW);  // my own rows first
+    RSF_T(7);
     cluster_wait();                                                       // every CTA's residual rows are in place
+    RSF_T(8);
     const float* rup = q > 0 ? cluster.map_shared_rank(Sr, q - 1) : Sr;
     const float* rdn = q < kCluster - 1 ? cluster.map_shared_rank(Sr, q + 1) : Sr;
 #pragma unroll
@@ -231,7 +301,8 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kT, 3) resize
       uu[m] = q > 0 ? urow(rup + (RJ - 2 + m) * OW) : 0.f;                       // residual rows above the image do not exist
       uu[RJ + 2 + m] = q < kCluster - 1 ? urow(rdn + m * OW) : 0.f;
     }
-    cluster_arrive();  // my remote reads are done: the neighbours may exit once everybody has said so
+    cluster_arrive_done_reading(uu[0] + uu[1], uu[RJ + 2] + uu[RJ + 3]);  // #3: my remote reads are done: the neighbours may exit once everybody has said so
+    RSF_T(9);
     float* gp = a.g + n * a.g_stride + poff;
 #pragma unroll
     for (int ii = 0; ii < kRI; ++ii) {
@@ -242,7 +313,9 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kT, 3) resize
         if (m0 + d >= 0 && m0 + d < RU) s = fmaf(Ah[ii * 4 + d], uu[m0 + d], s);
       stg_stream(gp + ii * kW + tid, ((pass_bits >> ii) & 1u) ? s : 0.f);
     }
+    RSF_T(10);
     cluster_wait();
+    RSF_T(11);
   }
 }
 
@@ -292,6 +365,12 @@ int upload(float** dst, const std::vector<float>& v) {
   return DPS_OK;
 }
 }  // namespace
+
+#ifdef DPS_RSF_TRACE
+extern "C" int dps_debug_rsf_trace(long long* host_out) {
+  return (int)cudaMemcpyFromSymbol(host_out, rsf_trace, sizeof(long long) * 4096 * 16);
+}
+#endif
 
 // Called by resize_create with the dense operator matrices.  Leaves op->rfused null when the shape is not covered.
 int resize_fused_create(dps_operator* op, const std::vector<double>& Ah, const std::vector<double>& Aw, int out_h, int out_w) {
