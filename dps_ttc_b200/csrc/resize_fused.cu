@@ -64,16 +64,10 @@ struct Geo {
 };
 
 template <int F>
-size_t fused_smem() {
-  return sizeof(float) * ((size_t)2 * kRI * kW + (size_t)kRI * 4 + 64) + 8 * kChunks;
+constexpr size_t fused_smem() {  // x rows + H-pass tile + residual rows + A_hᵀ band + reduction scratch + mbarriers
+  return sizeof(float) * ((size_t)kRI * kW + (size_t)Geo<F>::RJ * Geo<F>::PADW + (size_t)Geo<F>::RJ * Geo<F>::OW + (size_t)kRI * 4 + 64) + 8 * kChunks;
 }
 
-// Cluster barrier halves (same scheme as blur_fused.cu, measured there with a per-phase clock trace): an
-// barrier.cluster.arrive.release costs every warp a MEMBAR.ALL.GPU (≈2.5 k cycles — a quarter of this kernel at 8 particles).
-//   publish  — bar.sync, then ONE warp executes the (cumulative) cluster-scope fence, every thread arrives relaxed;
-//   done     — "my loads from the neighbours' tiles have completed": a relaxed arrive predicated on a value that depends on
-//              every remote load, so that ptxas cannot schedule it above the instructions that consume them.
-// DPS_RSF_FULL_RELEASE=1 restores arrive.release everywhere (A/B builds).
 #ifdef DPS_RSF_TRACE  // experiment builds only (tools/build_variant.sh): per-CTA phase timestamps of the first 4096 CTAs
 __device__ long long rsf_trace[4096 * 16];
 #define RSF_T(i) do { if (threadIdx.x == 0 && blockIdx.x < 4096) rsf_trace[blockIdx.x * 16 + (i)] = clock64(); } while (0)
@@ -112,16 +106,14 @@ DPS_DEV float ld_cluster(unsigned addr) {  // volatile: never moved across a bar
 }
 
 template <int F>
-__global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kT, 3) resize_guidance_kernel(const __grid_constant__ FusedArgs a) {
+__global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kT, 4) resize_guidance_kernel(const __grid_constant__ FusedArgs a) {
   using G = Geo<F>;
   constexpr int TAPS = G::TAPS, HALO = G::HALO, RJ = G::RJ, OW = G::OW, RU = G::RU, PADW = G::PADW, H = kRI * kCluster;
-  static_assert((size_t)RJ * PADW + (size_t)RJ * OW <= (size_t)kRI * kW, "tile + residual rows fit into the dead ε buffer");
   extern __shared__ __align__(16) float smem[];
   float* Sx = smem;                       // (32, 256)  x → x̂₀ (clamped)
-  float* Se = Sx + kRI * kW;              // (32, 256)  ε; dead after step 0 → St, Sr
-  float* St = Se;                         // (RJ, PADW) H-pass result, column-padded by mirroring
+  float* St = Sx + kRI * kW;              // (RJ, PADW) H-pass result, column-padded by mirroring
   float* Sr = St + RJ * PADW;             // (RJ, OW)   residual rows of this CTA
-  float* Ah = Se + kRI * kW;              // (32, 4)    transposed H band of my image rows
+  float* Ah = Sr + RJ * OW;               // (32, 4)    transposed H band of my image rows
   float* red = Ah + kRI * 4;              // 64
   uint64_t* bar = reinterpret_cast<uint64_t*>(red + 64);  // kChunks barriers
 
@@ -134,6 +126,12 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kT, 3) resize
   const float* eg = a.src.eps + n * a.src.eps_stride + poff;
 
   RSF_T(0);
+  // ε never passes through shared memory: a thread owns a column, so a row of ε is one coalesced 1 KB request per CTA; all 32
+  // are in flight before the first x chunk has landed (registers are cheap here: the accumulators are not live yet).  Without
+  // the 32 KB staging buffer the CTA needs 44 KB and 4 CTAs fit per SM (72 resident clusters instead of 48).
+  float ev[kRI];
+#pragma unroll
+  for (int r = 0; r < kRI; ++r) ev[r] = ldg_stream(eg + r * kW + tid);
   if (tid == 0) {
 #pragma unroll
     for (int ch = 0; ch < kChunks; ++ch) mbar_init(bar + ch, 1);
@@ -144,9 +142,8 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kT, 3) resize
     constexpr unsigned bytes = kChunkRows * kW * sizeof(float);
 #pragma unroll
     for (int ch = 0; ch < kChunks; ++ch) {
-      mbar_expect_tx(bar + ch, 2u * bytes);
+      mbar_expect_tx(bar + ch, bytes);
       bulk_load(Sx + ch * kChunkRows * kW, xg + ch * kChunkRows * kW, bytes, bar + ch);
-      bulk_load(Se + ch * kChunkRows * kW, eg + ch * kChunkRows * kW, bytes, bar + ch);
     }
   }
   // tables and measurement values while the rows are in flight
@@ -172,7 +169,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kT, 3) resize
 #pragma unroll
       for (int rr = 0; rr < kChunkRows; ++rr) {
         const int r = ch * kChunkRows + rr;
-        const float pre = x0_pre(Sx[r * kW + tid], Se[r * kW + tid], a.src.c1, a.src.c2);
+        const float pre = x0_pre(Sx[r * kW + tid], ev[r], a.src.c1, a.src.c2);
         Sx[r * kW + tid] = fminf(fmaxf(pre, lo), hi);
         pass_bits |= (pre >= lo && pre <= hi) ? (1u << r) : 0u;
       }

@@ -32,7 +32,7 @@ assert rc == 0, rc
 nb = min(4096, 3 * n * 8)
 t = buf[:nb, :12].astype(np.float64)
 d = np.diff(t, axis=1)
-names = ["mbar init+TMA issue+tables+y", "pass 0 (TMA wait, x0)", "syncthreads+arrive#1", "H own rows", "wait #1", "H halo rows+tile stores+sync",
+names = ["mbar init+TMA issue+tables+y", "pass 0 (TMA wait, x0)", "syncthreads+arrive#1+H own rows", "wait #1", "H halo rows+tile stores+sync",
          "W pass+residual", "sync+arrive#2+sums+own u rows", "wait #2", "remote u rows+arrive#3", "A_h^T + stores", "wait #3"]
 print(f"CTAs traced {nb}; lifetime mean {np.mean(t[:, 11] - t[:, 0]):.0f} cycles; first start to last end {t[:, 11].max() - t[:, 0].min():.0f} (clocks of different SMs are not aligned)")
 for i, nm in enumerate(names):
