@@ -40,7 +40,10 @@ struct ResizeFused {
 };
 
 namespace {
-constexpr int kW = 256, kRI = 32, kCluster = 8, kT = 256, kChunks = 4, kChunkRows = kRI / kChunks;
+#ifndef DPS_RSF_CHUNKS
+#define DPS_RSF_CHUNKS 4
+#endif
+constexpr int kW = 256, kRI = 32, kCluster = 8, kT = 256, kChunks = DPS_RSF_CHUNKS, kChunkRows = kRI / kChunks;
 
 struct FusedArgs {
   float w[32];
