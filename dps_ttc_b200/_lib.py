@@ -81,6 +81,7 @@ SIGNATURES = {
     "dps_operator_forward": (_I, [_P, C.POINTER(Source), _P, _L, _P, _P, _P, _I, _P]),
     "dps_operator_adjoint": (_I, [_P, _P, _P, C.POINTER(Source), _P, _L, _P, _L, _P, _I, _P]),
     "dps_operator_guidance": (_I, [_P, C.POINTER(Source), _P, _L, _P, _P, _L, _P, _P, _I, _P]),
+    "dps_operator_project": (_I, [_P, _P, _L, _P, _L, _I, _P, _L, _P, _I, _P]),
     "dps_particle_norms": (_I, [_P, _I, _I, _P, _P, _P]),
     "dps_guidance_coef": (_I, [_P, _I, _I, _I, _F, _P, _P, _P]),
     "dps_particle_logweights": (_I, [_P, _P, _I, _F, _F, _I, _F, _I, _P, _P]),

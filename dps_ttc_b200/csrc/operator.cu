@@ -166,8 +166,8 @@ int dps_operator_forward(const dps_operator* op, const dps_source* src, const fl
                   dps_aligned16(aux) && src->x_stride % 4 == 0 && (!src->eps || src->eps_stride % 4 == 0) &&
                   y_stride % 4 == 0,
               DPS_ERR_ALIGN, "dps_operator_forward: tensors must be 16-byte aligned, strides multiples of 4");
-  DPS_REQUIRE(op->aux_floats == 0 || aux || op->kind == DPS_OP_PHASE, DPS_ERR_INVALID,
-              "dps_operator_forward: this operator needs the aux workspace");
+  DPS_REQUIRE(op->aux_floats == 0 || aux || op->kind == DPS_OP_PHASE || op->kind == DPS_OP_BLUR_SPARSE, DPS_ERR_INVALID,
+              "dps_operator_forward: this operator needs the aux workspace");  // (sparse blur: the workspace is the adjoint's)
   FwdArgs a;
   a.src = *src;
   a.y = y;

@@ -70,6 +70,10 @@ template <int F>
 constexpr size_t fused_smem() {  // x rows + H-pass tile + residual rows + A_hᵀ band + reduction scratch + mbarriers
   return sizeof(float) * ((size_t)kRI * kW + (size_t)Geo<F>::RJ * Geo<F>::PADW + (size_t)Geo<F>::RJ * Geo<F>::OW + (size_t)kRI * 4 + 64) + 8 * kChunks;
 }
+template <int F>
+constexpr size_t project_smem() {  // the same plus the measurement rows (kept beside A·data for the up-sampling epilogue)
+  return fused_smem<F>() + sizeof(float) * (size_t)Geo<F>::RJ * Geo<F>::OW + 16;
+}
 
 #ifdef DPS_RSF_TRACE  // experiment builds only (tools/build_variant.sh): per-CTA phase timestamps of the first 4096 CTAs
 __device__ long long rsf_trace[4096 * 16];
@@ -108,7 +112,13 @@ DPS_DEV float ld_cluster(unsigned addr) {  // volatile: never moved across a bar
   return v;
 }
 
-template <int F>
+// PROJ = false: the guidance kernel described above.
+// PROJ = true : SuperResolutionOperator.project / ortho_project (measurements.py:48-50, :90-91) in one launch:
+//               out = (data − up(A·data)) + up(y), up = the reference's transpose = nearest-neighbour ×F (F.interpolate).
+//               Passes 0-2 are shared (no ε, no clamp: src.x is the data itself); A·data and y stay in shared memory and the
+//               epilogue writes the image rows.  Same A·data bits as the forward kernel, same two roundings as torch's
+//               `data - up(..) + up(..)`.  y = null gives ortho_project (… + 0).
+template <int F, bool PROJ>
 __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kT, 4) resize_guidance_kernel(const __grid_constant__ FusedArgs a) {
   using G = Geo<F>;
   constexpr int TAPS = G::TAPS, HALO = G::HALO, RJ = G::RJ, OW = G::OW, RU = G::RU, PADW = G::PADW, H = kRI * kCluster;
@@ -119,6 +129,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kT, 4) resize
   float* Ah = Sr + RJ * OW;               // (32, 4)    transposed H band of my image rows
   float* red = Ah + kRI * 4;              // 64
   uint64_t* bar = reinterpret_cast<uint64_t*>(red + 64);  // kChunks barriers
+  float* Sy = reinterpret_cast<float*>(bar + kChunks + (kChunks & 1));  // PROJ only: (RJ, OW) measurement rows
 
   cg::cluster_group cluster = cg::this_cluster();
   const int q = (int)cluster.block_rank();
@@ -126,15 +137,17 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kT, 4) resize
   const int tid = threadIdx.x;
   const int64_t poff = (int64_t)c * H * kW + (int64_t)q * kRI * kW;
   const float* xg = a.src.x + n * a.src.x_stride + poff;
-  const float* eg = a.src.eps + n * a.src.eps_stride + poff;
+  const float* eg = PROJ ? nullptr : a.src.eps + n * a.src.eps_stride + poff;
 
   RSF_T(0);
   // ε never passes through shared memory: a thread owns a column, so a row of ε is one coalesced 1 KB request per CTA; all 32
   // are in flight before the first x chunk has landed (registers are cheap here: the accumulators are not live yet).  Without
   // the 32 KB staging buffer the CTA needs 44 KB and 4 CTAs fit per SM (72 resident clusters instead of 48).
   float ev[kRI];
+  if (!PROJ) {
 #pragma unroll
-  for (int r = 0; r < kRI; ++r) ev[r] = ldg_stream(eg + r * kW + tid);
+    for (int r = 0; r < kRI; ++r) ev[r] = ldg_stream(eg + r * kW + tid);
+  }
   if (tid == 0) {
 #pragma unroll
     for (int ch = 0; ch < kChunks; ++ch) mbar_init(bar + ch, 1);
@@ -150,8 +163,11 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kT, 4) resize
     }
   }
   // tables and measurement values while the rows are in flight
-  stage_async(Ah, a.at_h + (size_t)q * kRI * 4, kRI * 4, tid, kT);
-  const float4 aw = __ldg(reinterpret_cast<const float4*>(a.at_w) + tid);  // my column's transposed W band
+  float4 aw = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (!PROJ) {
+    stage_async(Ah, a.at_h + (size_t)q * kRI * 4, kRI * 4, tid, kT);
+    aw = __ldg(reinterpret_cast<const float4*>(a.at_w) + tid);  // my column's transposed W band
+  }
   constexpr int kRP = (RJ * OW + kT - 1) / kT;  // residual values per thread in the W pass
   float yv[kRP];
   const float* yp = a.y ? a.y + n * a.y_stride + (int64_t)c * (H / F) * OW + (int64_t)q * RJ * OW : nullptr;
@@ -169,6 +185,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kT, 4) resize
 #pragma unroll
     for (int ch = 0; ch < kChunks; ++ch) {
       mbar_wait(bar + ch, 0);
+      if (PROJ) continue;  // the rows ARE the data
 #pragma unroll
       for (int rr = 0; rr < kChunkRows; ++rr) {
         const int r = ch * kChunkRows + rr;
@@ -234,6 +251,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kT, 4) resize
       if (tid < HALO) row[-1 - tid] = acc[jj];                   // columns −1, −2, … mirror columns 0, 1, …
       if (tid >= kW - HALO) row[2 * kW - 1 - tid] = acc[jj];     // columns 256, 257, … mirror 255, 254, …
     }
+    if (PROJ) cluster_arrive_done_reading(acc[0], acc[RJ - 1]);  // #2 (arrive): my DSMEM reads have returned
   }
   __syncthreads();
 
@@ -255,14 +273,27 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kT, 4) resize
         acc = fmaf(a.w[4 * m + 2], t4.z, acc);
         acc = fmaf(a.w[4 * m + 3], t4.w, acc);
       }
-      const float res = yp ? yv[u] - acc : acc;
+      const float res = (yp && !PROJ) ? yv[u] - acc : acc;
       Sr[o] = res;
-      if (a.r_out) a.r_out[((int64_t)n * a.C + c) * (H / F) * OW + (int64_t)q * RJ * OW + o] = res;
+      if (PROJ) Sy[o] = yv[u];
+      if (!PROJ && a.r_out) a.r_out[((int64_t)n * a.C + c) * (H / F) * OW + (int64_t)q * RJ * OW + o] = res;
       sq = fmaf(res, res, sq);
       ab += fabsf(res);
     }
   }
   RSF_T(6);
+  if (PROJ) {
+    __syncthreads();
+    float* op_ = a.g + n * a.g_stride + poff;
+    const int l = tid / F;
+#pragma unroll
+    for (int ii = 0; ii < kRI; ++ii) {
+      const int o = (ii / F) * OW + l;
+      stg_stream(op_ + ii * kW + tid, __fadd_rn(__fsub_rn(Sx[ii * kW + tid], Sr[o]), Sy[o]));
+    }
+    cluster_wait();  // #2: nobody reads my rows over DSMEM any more
+    return;
+  }
   __syncthreads();                  // my residual rows are complete …
   cluster_arrive_publish_synced();  // #2 (arrive) … and announced; the partial sums below overlap the other CTAs' arrival
   if (a.partials) {
@@ -389,10 +420,13 @@ int resize_fused_create(dps_operator* op, const std::vector<double>& Ah, const s
   op->rfused = t;
   if (int rc = upload(&t->at_h, ath)) return rc;
   if (int rc = upload(&t->at_w, atw)) return rc;
-  if (F == 4)
-    DPS_CUDA(cudaFuncSetAttribute(resize_guidance_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem<4>()));
-  else
-    DPS_CUDA(cudaFuncSetAttribute(resize_guidance_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem<8>()));
+  if (F == 4) {
+    DPS_CUDA(cudaFuncSetAttribute(resize_guidance_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem<4>()));
+    DPS_CUDA(cudaFuncSetAttribute(resize_guidance_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)project_smem<4>()));
+  } else {
+    DPS_CUDA(cudaFuncSetAttribute(resize_guidance_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem<8>()));
+    DPS_CUDA(cudaFuncSetAttribute(resize_guidance_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)project_smem<8>()));
+  }
   op->guidance_P = op->C * kCluster;
   return DPS_OK;
 }
@@ -423,9 +457,36 @@ int resize_fused_guidance(const dps_operator* op, const dps_source& src, const f
   a.partials = partials;
   dim3 grid((unsigned)((int64_t)op->C * n * kCluster));
   if (t.F == 4)
-    resize_guidance_kernel<4><<<grid, kT, fused_smem<4>(), st>>>(a);
+    resize_guidance_kernel<4, false><<<grid, kT, fused_smem<4>(), st>>>(a);
   else
-    resize_guidance_kernel<8><<<grid, kT, fused_smem<8>(), st>>>(a);
+    resize_guidance_kernel<8, false><<<grid, kT, fused_smem<8>(), st>>>(a);
   DPS_LAUNCH_CHECK("resize_guidance");
+  return DPS_OK;
+}
+
+// out = (data − up(A·data)) + up(y)   (y null: ortho_project).  One launch of the cluster kernel in PROJ mode.
+int resize_fused_project(const dps_operator* op, const float* data, int64_t data_stride, const float* y, int64_t y_stride, float* out,
+                         int64_t out_stride, int n, cudaStream_t st) {
+  const ResizeFused& t = *op->rfused;
+  FusedArgs a;
+  for (int k = 0; k < 32; ++k) a.w[k] = t.w[k];
+  a.at_h = t.at_h;
+  a.at_w = t.at_w;
+  a.C = op->C;
+  a.src = dps_source{};
+  a.src.x = data;
+  a.src.x_stride = data_stride;
+  a.y = y;
+  a.y_stride = y_stride;
+  a.r_out = nullptr;
+  a.g = out;
+  a.g_stride = out_stride;
+  a.partials = nullptr;
+  dim3 grid((unsigned)((int64_t)op->C * n * kCluster));
+  if (t.F == 4)
+    resize_guidance_kernel<4, true><<<grid, kT, project_smem<4>(), st>>>(a);
+  else
+    resize_guidance_kernel<8, true><<<grid, kT, project_smem<8>(), st>>>(a);
+  DPS_LAUNCH_CHECK("resize_project");
   return DPS_OK;
 }

@@ -322,6 +322,39 @@ class OperatorPlan:
             TIMER.stop(tok)
         return partials, r, aux
 
+    def project(self, data, y=None, out=None):
+        """Operator.project(data, y) — or ortho_project(data) when y is None — with the elementwise part in the operator
+        kernels' epilogues (dps_operator_project; measurements.py:48-54, :90-91).  No autograd."""
+        self._check_in(data, "data")
+        n = data.shape[0]
+        dp, ds = particle_view(data, "data")
+        if out is None:
+            out = torch.empty((n,) + self.in_shape, device=data.device, dtype=torch.float32)
+        op_, os_ = particle_view(out, "out")
+        yp, ys, ny = None, 0, 0
+        if y is not None:
+            require_cuda_f32(y, "y")
+            if tuple(y.shape[-3:]) != self.out_shape:
+                raise DpsError(f"measurement shape {tuple(y.shape)} does not match operator output {self.out_shape}")
+            y = _lib.dense(y.reshape((-1,) + self.out_shape), "y")
+            ny = y.shape[0]
+            if ny not in (1, n):
+                raise DpsError(f"measurement batch {ny} must be 1 or {n}")
+            yp, ys = y.data_ptr(), y[0].numel()
+        scratch = None
+        if self.kind == "resize":
+            if self.guidance_partials == 0:
+                scratch = torch.empty((n,) + self.out_shape, device=data.device, dtype=torch.float32)
+        elif y is not None:
+            scratch = torch.empty((ny,) + self.out_shape, device=data.device, dtype=torch.float32)
+        tok = TIMER.start(f"{self.kind}_project") if TIMER else None
+        with _on(self.device):
+            check(lib().dps_operator_project(self._h, dp, ds, yp, ys, ny, op_, os_, ptr(scratch), n, stream_ptr(data.device)),
+                  f"dps_operator_project[{self.kind}]")
+        if tok:
+            TIMER.stop(tok)
+        return out
+
     def adjoint(self, r, coef=None, mask_x=None, mask_eps=None, k=None, clip=True, extra=None, out=None, aux=None):
         """g = 1[−1 ≤ c1·x − c2·ε ≤ 1] ⊙ (coef_n·Aᵀr + extra); mask only when mask_x/mask_eps given.
         `out` may be a channel-slice view of a larger buffer."""

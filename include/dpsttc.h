@@ -227,6 +227,18 @@ int dps_operator_guidance(const dps_operator* op, const dps_source* src, const f
                           float* r_out, float* g, int64_t g_stride, float* partials, float* aux,
                           int n_particles, dps_stream_t stream);
 
+/* Operator.project / ortho_project (measurements.py:48-54, :90-91) with the elementwise part in the
+ * operator kernels' epilogues.  `y == NULL` selects ortho_project, else project:
+ *   blur, inpainting (the reference's transpose is the identity):  ortho: out = d − A d   (one forward launch, the data as its
+ *       own measurement);  project: out = (y − A y) − A d   (two forward launches; `scratch` holds n_y measurement planes);
+ *   super-resolution (transpose = nearest ×F): out = (d − up(A d)) + up(y)  — ×4/×8 at 256²: ONE cluster-kernel launch
+ *       (A d and y never leave shared memory); other shapes: forward + a combine kernel (`scratch`: n measurement planes);
+ *   phase retrieval: DPS_ERR_UNSUPPORTED (image and measurement shapes differ; the reference cannot evaluate it either).
+ * data: (n, C·H·W) with data_stride; y: n_y ∈ {1, n} measurement planes with y_stride; out: out_stride (dense for blur /
+ * inpainting).  Bit-identical to the reference's composition evaluated with this library's forward kernel.               */
+int dps_operator_project(const dps_operator* op, const float* data, int64_t data_stride, const float* y, int64_t y_stride,
+                         int n_y, float* out, int64_t out_stride, float* scratch, int n_particles, dps_stream_t stream);
+
 /* Adjoint / Jacobian-transpose, fused with the gradient scaling and the clamp backward
  * (SURVEY.md App. A.4):  g = 1[−1 ≤ c1·x−c2·ε ≤ 1] ⊙ (coef_n · Aᵀ r + extra)
  * coef (nullable → 1): per-particle fp32;  mask_src (nullable → no clamp mask);
