@@ -5,12 +5,14 @@
 // keeps only the non-zero taps (dy, dx, w).
 //
 // forward : one CTA stages a strip of x̂₀ with its halo in shared memory, reflect-filled, and every thread
-//           accumulates 16 vertically adjacent outputs of a column PAIR on packed FFMA2.  The non-zero taps are
+//           accumulates 16 vertically adjacent outputs of TWO columns on packed FFMA2.  The non-zero taps are
 //           covered by vertical CHUNKS of 4 (same dx, dy0 … dy0+3, absent taps weigh 0): a chunk loads the 19 tile
 //           value pairs under it once and feeds 64 FFMA2 (128 FMAs) from registers (a motion path is 2-5 taps thick
-//           in every column, so a chunk is rarely more than half empty).  Chunks with an even dx read their pairs with
-//           one aligned 64-bit load, chunks with an odd dx with two 32-bit loads; the plan sorts the even ones first so
-//           that neither loop branches.  (One column and scalar FFMA per thread before: 409 → see DESIGN.md.)
+//           in every column, so a chunk is rarely more than half empty).  A warp owns a 64-column block and lane L the
+//           columns L and L + 32 of it: every tile load is 32 consecutive words for any dx (round 2: adjacent column
+//           pairs read with 64-bit loads were conflict-free only for even dx — a third of all shared-memory wavefronts
+//           were conflict replays; 377 → 345 µs at N = 128).  The plan still sorts even-dx chunks first: the summation
+//           order, hence every bit of the result, is the one of the earlier kernels.
 // adjoint : A = C·P (P = reflect pad, C = valid correlation) ⇒ Aᵀ = Pᵀ·Cᵀ, done literally in two kernels:
 //           (1) t = Cᵀu on the PADDED domain (H+2Ry, W+2Rx) — the same gather kernel with negated offsets over
 //               a zero-filled tile, no border cases at all — into the operator's workspace (stays in L2);
@@ -26,7 +28,11 @@
 
 namespace {
 constexpr int kRows = 32;
-constexpr int kGroup = 16;  // vertically adjacent outputs per thread and pass
+#ifndef DPS_SPARSE_GROUP
+#define DPS_SPARSE_GROUP 16
+#endif
+constexpr int kGroup = DPS_SPARSE_GROUP;  // vertically adjacent outputs per thread and pass
+constexpr int kMaxThreads = 320 * 16 / kGroup;
 constexpr int kSWFixed = 384;   // compile-time tile row strides of the 256-wide fast path: halo ≤ 64 columns per side,
 constexpr int kSWFixedS = 320;  // or ≤ 32 (smaller tile, one more CTA per SM)
 
@@ -61,7 +67,7 @@ DPS_DEV int tap_dx(int v) { return (int)(short)(v & 0xffff); }
 // kSW > 0: the tile row stride is the compile-time constant kSW (every LDS of the tap loop gets an immediate offset,
 // no address arithmetic); kSW = 0: stride W + 2·halo computed at run time.
 template <bool kAdjoint, int kSW>
-__global__ void __launch_bounds__(320) sparse_kernel(const Tap* __restrict__ taps_g, int ntaps, int n_even, int Ry, int Rx, int C,
+__global__ void __launch_bounds__(kMaxThreads) sparse_kernel(const Tap* __restrict__ taps_g, int ntaps, int n_even, int Ry, int Rx, int C,
                                                      int H, int W, int strips, const FwdArgs fa, const AdjArgs aa,
                                                      float* __restrict__ t_out) {
   extern __shared__ __align__(16) float smem[];
@@ -142,42 +148,36 @@ __global__ void __launch_bounds__(320) sparse_kernel(const Tap* __restrict__ tap
   __syncthreads();
 
   float sq = 0.f, ab = 0.f;
-  // items = (column pair, group of kGroup rows); consecutive threads take consecutive pairs of one group
-  const int OW2 = OW / 2;
+  // items = (64-column block, group of kGroup rows), one per WARP: lane L owns columns 64·blk + L and 64·blk + 32 + L.
+  // Every tile load of the tap loop is then a 32-bit access of 32 CONSECUTIVE words whatever the tap's dx: one wavefront,
+  // no bank conflict.  (Adjacent column pairs — one 64-bit load per pair — are conflict-free only for even dx; for odd dx
+  // the two 32-bit loads of a pair have stride 2 and cost two wavefronts each: ncu counted 28 M excessive wavefronts of
+  // 85 M at N = 128, profiles/r3c_ncu_motion_fwd_n128.csv, and shared-memory bandwidth is what bounds this kernel.)
+  const int nblk = (OW + 63) >> 6;
   constexpr int kGroups = kRows / kGroup;
-  for (int item = tid; item < OW2 * kGroups; item += nthreads) {
-    const int grp = item / OW2, cp = item - grp * OW2;
-    const int col = 2 * cp, g0 = grp * kGroup;
+  const int lane = tid & 31;
+  for (int item = tid >> 5; item < nblk * kGroups; item += nthreads >> 5) {
+    const int grp = item / nblk, blk = item - grp * nblk;
+    const int g0 = grp * kGroup;
+    const int col_lo = blk * 64 + lane;
+    const bool hi_ok = col_lo + 32 < OW, lo_ok = col_lo < OW;
+    const int col_hi = hi_ok ? col_lo + 32 : col_lo;  // (a block that sticks out of the row recomputes its low half)
     // tile element under output (o0+g0, col) with zero tap offset:
     //   forward: image (o0+g0, col)            → tile row g0+Ry,      tile col halo_x+col
     //   adjoint: padded (p, q) = image (p−Ry, q−Rx) → tile row g0+Ry, tile col halo_x+col−Rx
-    // SW, halo_x, Rx and col are even: the pair under a chunk is 8-byte aligned exactly when the chunk's dx is even
-    const float* base = tile + (Ry + g0) * SW + halo_x + col - (kAdjoint ? Rx : 0);
+    const float* base = tile + (Ry + g0) * SW + halo_x + (lo_ok ? col_lo : 0) - (kAdjoint ? Rx : 0);
+    const int dhi = col_hi - (lo_ok ? col_lo : 0);
     float2 acc[kGroup];
 #pragma unroll
     for (int j = 0; j < kGroup; ++j) acc[j] = make_float2(0.f, 0.f);
 #pragma unroll 2
-    for (int t = 0; t < n_even; ++t) {
-      const float4 w = *reinterpret_cast<const float4*>(taps[t].w);
-      const float2* p = reinterpret_cast<const float2*>(base + taps[t].off);
-      float2 v[kGroup + kChunk - 1];
-#pragma unroll
-      for (int i = 0; i < kGroup + kChunk - 1; ++i) v[i] = p[i * (SW / 2)];
-#pragma unroll
-      for (int j = 0; j < kGroup; ++j) {
-        acc[j] = __ffma2_rn(make_float2(w.x, w.x), v[j], acc[j]);
-        acc[j] = __ffma2_rn(make_float2(w.y, w.y), v[j + 1], acc[j]);
-        acc[j] = __ffma2_rn(make_float2(w.z, w.z), v[j + 2], acc[j]);
-        acc[j] = __ffma2_rn(make_float2(w.w, w.w), v[j + 3], acc[j]);
-      }
-    }
-#pragma unroll 2
-    for (int t = n_even; t < ntaps; ++t) {
+    for (int t = 0; t < ntaps; ++t) {
       const float4 w = *reinterpret_cast<const float4*>(taps[t].w);
       const float* p = base + taps[t].off;
+      const float* ph = p + dhi;
       float2 v[kGroup + kChunk - 1];
 #pragma unroll
-      for (int i = 0; i < kGroup + kChunk - 1; ++i) v[i] = make_float2(p[i * SW], p[i * SW + 1]);
+      for (int i = 0; i < kGroup + kChunk - 1; ++i) v[i] = make_float2(p[i * SW], ph[i * SW]);
 #pragma unroll
       for (int j = 0; j < kGroup; ++j) {
         acc[j] = __ffma2_rn(make_float2(w.x, w.x), v[j], acc[j]);
@@ -191,17 +191,19 @@ __global__ void __launch_bounds__(320) sparse_kernel(const Tap* __restrict__ tap
       const int row = o0 + g0 + j;
       if (row >= OH) continue;
       if (!kAdjoint) {
-        const int64_t off = plane + (int64_t)row * W + col;
+        const int64_t off = plane + (int64_t)row * W;
         float2 res = acc[j];
         if (fa.y) {
-          const float2 yv = __ldg(reinterpret_cast<const float2*>(fa.y + n * fa.y_stride + off));
-          res = make_float2(__fsub_rn(yv.x, res.x), __fsub_rn(yv.y, res.y));
+          const float* yr = fa.y + n * fa.y_stride + off;
+          res = make_float2(__fsub_rn(lo_ok ? __ldg(yr + col_lo) : 0.f, res.x), __fsub_rn(hi_ok ? __ldg(yr + col_hi) : 0.f, res.y));
         }
-        stg_stream2(fa.out + (int64_t)n * C * H * W + off, res);
-        sq += res.x * res.x + res.y * res.y;
-        ab += fabsf(res.x) + fabsf(res.y);
+        float* orow = fa.out + (int64_t)n * C * H * W + off;
+        if (lo_ok) { stg_stream(orow + col_lo, res.x); sq = fmaf(res.x, res.x, sq); ab += fabsf(res.x); }
+        if (hi_ok) { stg_stream(orow + col_hi, res.y); sq = fmaf(res.y, res.y, sq); ab += fabsf(res.y); }
       } else {
-        stg_stream2(t_out + (((int64_t)n * C + c) * OH + row) * OW + col, acc[j]);
+        float* trow = t_out + (((int64_t)n * C + c) * OH + row) * OW;
+        if (lo_ok) stg_stream(trow + col_lo, acc[j].x);
+        if (hi_ok) stg_stream(trow + col_hi, acc[j].y);
       }
     }
   }
@@ -343,14 +345,15 @@ int sparse_forward(const dps_operator* op, const FwdArgs& a, cudaStream_t st) {
   dim3 grid((unsigned)(op->C * strips), (unsigned)a.n);
   bool fx;
   const int SW = sparse_stride(op, false, &fx);
+  const int fthreads = std::max(256, std::min(kMaxThreads, 32 * ((op->W + 63) / 64) * (kRows / kGroup)));
   if (sparse_fixed(op, false) && SW == kSWFixedS)
-    sparse_kernel<false, kSWFixedS><<<grid, 256, sparse_smem(op, false), st>>>(t->taps_dev, t->ntaps, t->n_even, t->Ry, t->Rx, op->C,
+    sparse_kernel<false, kSWFixedS><<<grid, fthreads, sparse_smem(op, false), st>>>(t->taps_dev, t->ntaps, t->n_even, t->Ry, t->Rx, op->C,
                                                                                op->H, op->W, strips, a, dummy, nullptr);
   else if (sparse_fixed(op, false))
-    sparse_kernel<false, kSWFixed><<<grid, 256, sparse_smem(op, false), st>>>(t->taps_dev, t->ntaps, t->n_even, t->Ry, t->Rx, op->C,
+    sparse_kernel<false, kSWFixed><<<grid, fthreads, sparse_smem(op, false), st>>>(t->taps_dev, t->ntaps, t->n_even, t->Ry, t->Rx, op->C,
                                                                               op->H, op->W, strips, a, dummy, nullptr);
   else
-    sparse_kernel<false, 0><<<grid, 256, sparse_smem(op, false), st>>>(t->taps_dev, t->ntaps, t->n_even, t->Ry, t->Rx, op->C, op->H,
+    sparse_kernel<false, 0><<<grid, fthreads, sparse_smem(op, false), st>>>(t->taps_dev, t->ntaps, t->n_even, t->Ry, t->Rx, op->C, op->H,
                                                                        op->W, strips, a, dummy, nullptr);
   DPS_LAUNCH_CHECK("sparse_blur_forward");
   return DPS_OK;
@@ -364,7 +367,7 @@ int sparse_adjoint(const dps_operator* op, const AdjArgs& a, cudaStream_t st) {
   FwdArgs dummy = {};
   const int OH = op->H + 2 * t->Ry, OW = op->W + 2 * t->Rx;
   const int strips = (OH + kRows - 1) / kRows;
-  const int threads = OW >= 320 ? 320 : ((OW + 31) / 32) * 32;
+  const int threads = std::min(kMaxThreads, 32 * ((OW + 63) / 64) * (kRows / kGroup));  // one warp per (64-column block, row group)
   dim3 grid((unsigned)(op->C * strips), (unsigned)a.n);
   bool fx;
   const int SW = sparse_stride(op, true, &fx);

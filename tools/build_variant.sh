@@ -8,7 +8,7 @@ cd "$(dirname "$0")/../dps_ttc_b200/csrc"
 mkdir -p ../build_variants build
 nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC --expt-relaxed-constexpr -cudart static $flags -c -o build/${src%.cu}_$name.o $src
 objs=""
-for o in api update operator inpaint blur_separable blur_fused blur_sparse resize resize_fused phase resample; do
+for o in api update operator project inpaint blur_separable blur_fused blur_sparse resize resize_fused phase resample; do
   if [ "$o.cu" == "$src" ]; then objs="$objs build/${o}_$name.o"; else objs="$objs build/$o.o"; fi
 done
 nvcc -gencode arch=compute_100a,code=sm_100a -shared -cudart static -Xcompiler -fPIC -o ../build_variants/libdpsttc_$name.so $objs
