@@ -325,14 +325,25 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kT, 4) resize
     RSF_T(7);
     cluster_wait();                                                       // every CTA's residual rows are in place
     RSF_T(8);
+    // The 2+2 neighbour rows first come into LOCAL shared memory, one value per thread (DSMEM moves ≈17 B per cycle and SM:
+    // sixteen values per thread read straight from the neighbours were 16 KB per CTA and ≈1 500 cycles of the N = 8 trace;
+    // staged it is 1 KB).  St is free: every thread passed the barrier after the W pass.
     const float* rup = q > 0 ? cluster.map_shared_rank(Sr, q - 1) : Sr;
     const float* rdn = q < kCluster - 1 ? cluster.map_shared_rank(Sr, q + 1) : Sr;
+    float* Sn = St;  // (4, OW): residual rows RJ·q − 2, RJ·q − 1, RJ·(q+1), RJ·(q+1) + 1 (zero where the image ends)
+    float nv = 0.f;
+    if (tid < 4 * OW) {
+      const int m = tid / OW, l = tid - m * OW;
+      if (m < 2 ? q > 0 : q < kCluster - 1) nv = m < 2 ? rup[(RJ - 2 + m) * OW + l] : rdn[(m - 2) * OW + l];
+      Sn[tid] = nv;
+    }
+    cluster_arrive_done_reading(nv, 0.f);  // #3: my remote read has returned: the neighbours may exit once everybody has said so
+    __syncthreads();
 #pragma unroll
     for (int m = 0; m < 2; ++m) {
-      uu[m] = q > 0 ? urow(rup + (RJ - 2 + m) * OW) : 0.f;                       // residual rows above the image do not exist
-      uu[RJ + 2 + m] = q < kCluster - 1 ? urow(rdn + m * OW) : 0.f;
+      uu[m] = urow(Sn + m * OW);
+      uu[RJ + 2 + m] = urow(Sn + (2 + m) * OW);
     }
-    cluster_arrive_done_reading(uu[0] + uu[1], uu[RJ + 2] + uu[RJ + 3]);  // #3: my remote reads are done: the neighbours may exit once everybody has said so
     RSF_T(9);
     float* gp = a.g + n * a.g_stride + poff;
 #pragma unroll
