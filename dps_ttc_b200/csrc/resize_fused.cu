@@ -14,15 +14,16 @@
 //
 // Mapping: a thread-block CLUSTER of 8 CTAs owns one (particle, channel) plane; CTA q owns image rows [32q, 32q+32) and
 // residual rows [RJ·q, RJ·(q+1)), RJ = 32/F.
-//   0. x, ε rows → shared memory by TMA bulk copies in four 8-row chunks; each chunk becomes x̂₀ (clamped) in place as it
-//      lands; the clamp mask of a thread's column is one 32-bit register.  The ε buffer is dead afterwards and is reused
-//      for the H-pass tile and the residual rows (3 CTAs per SM).
-//   1. cluster barrier; H pass: a thread owns a column and walks the 32 + 2·HALO rows its RJ residual rows need — halo
-//      rows come from the neighbour CTAs' shared memory (DSMEM), mirrored own rows at the image border.
+//   0. x rows → shared memory by TMA bulk copies in four 8-row chunks, ε rows → registers (a thread owns a column); each
+//      chunk becomes x̂₀ (clamped) in place as it lands; the clamp mask of a thread's column is one 32-bit register; the
+//      first / last HALO rows are PUSHED into the neighbour CTAs' halo buffers (st.async over DSMEM, completing bytes on
+//      the neighbour's mbarrier) as they are produced.
+//   1. H pass: a thread owns a column and walks the 32 + 2·HALO rows its RJ residual rows need — own rows first, then
+//      (after the wait on its own halo barrier) the pushed rows, mirrored own rows at the image border.
 //   2. W pass from the column-padded RJ×(256+2·HALO) tile with 128-bit shared loads; r = y − (·), Σr², Σ|r| → one
-//      partial-sum pair per CTA; r stays in shared memory.
-//   3. cluster barrier (arrive early, wait late); Aᵀ: u = r·A_w for the RJ+4 residual rows that touch this CTA's image
-//      rows (2+2 of them from the neighbours), then g = A_hᵀ u, masked, one coalesced store per image row.
+//      partial-sum pair per CTA; r stays in shared memory; the first / last two residual rows are pushed to the neighbours.
+//   3. Aᵀ: u = r·A_w for the RJ+4 residual rows that touch this CTA's image rows (own rows first, then the 2+2 pushed
+//      ones), then g = A_hᵀ u, masked, one coalesced store per image row.
 // HBM traffic = the algorithmic minimum: x, ε read once, g written once, y read once.
 #include <cooperative_groups.h>
 
@@ -67,8 +68,9 @@ struct Geo {
 };
 
 template <int F>
-constexpr size_t fused_smem() {  // x rows + H-pass tile + residual rows + A_hᵀ band + reduction scratch + mbarriers
-  return sizeof(float) * ((size_t)kRI * kW + (size_t)Geo<F>::RJ * Geo<F>::PADW + (size_t)Geo<F>::RJ * Geo<F>::OW + (size_t)kRI * 4 + 64) + 8 * kChunks;
+constexpr size_t fused_smem() {  // x rows + halo rows (the H-pass tile aliases them) + residual rows + neighbour rows + A_hᵀ band + scratch + mbarriers
+  return sizeof(float) * ((size_t)kRI * kW + (size_t)2 * Geo<F>::HALO * kW + (size_t)Geo<F>::RJ * Geo<F>::OW + (size_t)4 * Geo<F>::OW + (size_t)kRI * 4 + 64) +
+         8 * (kChunks + 2);
 }
 template <int F>
 constexpr size_t project_smem() {  // the same plus the measurement rows (kept beside A·data for the up-sampling epilogue)
@@ -81,77 +83,82 @@ __device__ long long rsf_trace[4096 * 16];
 #else
 #define RSF_T(i) do { } while (0)
 #endif
-DPS_DEV void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
-DPS_DEV void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
-DPS_DEV void cluster_arrive_publish_synced() {  // the caller has executed a bar.sync after the last store
-#ifdef DPS_RSF_FULL_RELEASE
-  cluster_arrive_release();
-#else
-  if (threadIdx.x < 32) asm volatile("fence.acq_rel.cluster;" ::: "memory");
-  asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
-#endif
-}
-DPS_DEV void cluster_arrive_done_reading(float dep0, float dep1) {
-#ifdef DPS_RSF_FULL_RELEASE
-  cluster_arrive_release();
-#else
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t.reg .f32 t;\n\tadd.rn.f32 t, %0, %1;\n\tsetp.neu.f32 p, t, t;\n\t"
-      "@p barrier.cluster.arrive.relaxed;\n\t@!p barrier.cluster.arrive.relaxed;\n\t}" ::"f"(dep0), "f"(dep1)
-      : "memory");
-#endif
-}
 DPS_DEV unsigned mapa_u32(unsigned addr, unsigned rank) {
   unsigned r;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
-DPS_DEV float ld_cluster(unsigned addr) {  // volatile: never moved across a barrier
-  float v;
-  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(addr));
-  return v;
-}
-
 // PROJ = false: the guidance kernel described above.
 // PROJ = true : SuperResolutionOperator.project / ortho_project (measurements.py:48-50, :90-91) in one launch:
 //               out = (data − up(A·data)) + up(y), up = the reference's transpose = nearest-neighbour ×F (F.interpolate).
 //               Passes 0-2 are shared (no ε, no clamp: src.x is the data itself); A·data and y stay in shared memory and the
-//               epilogue writes the image rows.  Same A·data bits as the forward kernel, same two roundings as torch's
+//               epilogue writes the image rows.  Same A·data bits as the guidance kernel, same two roundings as torch's
 //               `data - up(..) + up(..)`.  y = null gives ortho_project (… + 0).
+//
+// Neighbour exchange = PUSH (st.async, SASS `STAS`): a CTA writes the x̂₀ rows its neighbours' windows need straight into THEIR
+// halo buffers as it produces them (pass 0), and later its first / last two residual rows into their Sn buffers (W pass).  Every
+// such store completes bytes on an mbarrier in the DESTINATION CTA, which waits on its own barrier like for a TMA copy and
+// then reads LOCAL shared memory.  Compared with the pull form of the first versions (cluster barrier, then
+// ld.shared::cluster from the neighbour):
+//   * no cluster-scope release: `fence.acq_rel.cluster` is MEMBAR.ALL.GPU + CCTL.IVALL in SASS, twice per CTA, on the
+//     critical path of an 8-CTA hardware barrier that waits for the slowest of the eight;
+//   * a CTA depends on its two neighbours only; nothing waits for "everybody has finished reading" before it may exit;
+//   * DSMEM moves ≈17–21 B per cycle and SM: pulled rows were latency AND bandwidth exposed in front of the H pass
+//     (≈1 500 cycles of a 13 000-cycle CTA at N = 8, tools/rsf_trace.py); pushed rows travel while pass 0 is still converting.
+// One cluster barrier remains, at the very top (arrive after the mbarrier init, wait before the first push): a neighbour must
+// not complete bytes on a barrier that is not initialised yet.  A CTA leaves only after both of its barriers have
+// completed, i.e. after every store aimed at it has landed.
+DPS_DEV void st_async_f32(unsigned remote_addr, float v, unsigned remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f32 [%0], %1, [%2];" ::"r"(remote_addr), "f"(v), "r"(remote_bar)
+               : "memory");
+}
+
 template <int F, bool PROJ>
 __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kT, 4) resize_guidance_kernel(const __grid_constant__ FusedArgs a) {
   using G = Geo<F>;
   constexpr int TAPS = G::TAPS, HALO = G::HALO, RJ = G::RJ, OW = G::OW, RU = G::RU, PADW = G::PADW, H = kRI * kCluster;
+  static_assert(2 * HALO * kW >= RJ * PADW, "the H-pass tile aliases the halo buffer");
+  static_assert(HALO <= kRI && 2 <= RJ, "a window reaches one neighbour only");
   extern __shared__ __align__(16) float smem[];
   float* Sx = smem;                       // (32, 256)  x → x̂₀ (clamped)
-  float* St = Sx + kRI * kW;              // (RJ, PADW) H-pass result, column-padded by mirroring
-  float* Sr = St + RJ * PADW;             // (RJ, OW)   residual rows of this CTA
-  float* Ah = Sr + RJ * OW;               // (32, 4)    transposed H band of my image rows
+  float* Sh = Sx + kRI * kW;              // (2·HALO, 256) x̂₀ of the HALO rows above and the HALO rows below mine, PUSHED by the neighbours
+  float* St = Sh;                         // (RJ, PADW) H-pass result, column-padded by mirroring — aliases Sh (dead by then)
+  float* Sr = Sh + 2 * HALO * kW;         // (RJ, OW)   residual rows of this CTA
+  float* Sn = Sr + RJ * OW;               // (4, OW)    residual rows RJ·q − 2, RJ·q − 1, RJ·(q+1), RJ·(q+1) + 1, pushed by the neighbours
+  float* Ah = Sn + 4 * OW;                // (32, 4)    transposed H band of my image rows
   float* red = Ah + kRI * 4;              // 64
-  uint64_t* bar = reinterpret_cast<uint64_t*>(red + 64);  // kChunks barriers
-  float* Sy = reinterpret_cast<float*>(bar + kChunks + (kChunks & 1));  // PROJ only: (RJ, OW) measurement rows
+  uint64_t* bar = reinterpret_cast<uint64_t*>(red + 64);  // kChunks TMA barriers, then hbar (halo rows), nbar (neighbour residual rows)
+  uint64_t* hbar = bar + kChunks;
+  uint64_t* nbar = hbar + 1;
+  float* Sy = reinterpret_cast<float*>(bar + kChunks + 2);  // PROJ only: (RJ, OW) measurement rows
 
   cg::cluster_group cluster = cg::this_cluster();
   const int q = (int)cluster.block_rank();
   const int plane = blockIdx.x / kCluster, c = plane % a.C, n = plane / a.C;
   const int tid = threadIdx.x;
+  const bool has_up = q > 0, has_dn = q < kCluster - 1;  // image borders: the halo is my own rows, mirrored
   const int64_t poff = (int64_t)c * H * kW + (int64_t)q * kRI * kW;
   const float* xg = a.src.x + n * a.src.x_stride + poff;
   const float* eg = PROJ ? nullptr : a.src.eps + n * a.src.eps_stride + poff;
 
   RSF_T(0);
+  if (tid == 0) {
+#pragma unroll
+    for (int ch = 0; ch < kChunks; ++ch) mbar_init(bar + ch, 1);
+    mbar_init(hbar, 1);
+    mbar_init(nbar, 1);
+    mbar_init_fence();
+    // my single arrival on the two neighbour barriers, with the bytes the neighbours will complete
+    mbar_expect_tx(hbar, ((has_up ? 1u : 0u) + (has_dn ? 1u : 0u)) * HALO * kW * (unsigned)sizeof(float));
+    if (!PROJ) mbar_expect_tx(nbar, ((has_up ? 1u : 0u) + (has_dn ? 1u : 0u)) * 2 * OW * (unsigned)sizeof(float));
+  }
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");  // (thread 0: after its init fence)
   // ε never passes through shared memory: a thread owns a column, so a row of ε is one coalesced 1 KB request per CTA; all 32
-  // are in flight before the first x chunk has landed (registers are cheap here: the accumulators are not live yet).  Without
-  // the 32 KB staging buffer the CTA needs 44 KB and 4 CTAs fit per SM (72 resident clusters instead of 48).
+  // are in flight before the first x chunk has landed (registers are cheap here: the accumulators are not live yet).
   float ev[kRI];
   if (!PROJ) {
 #pragma unroll
     for (int r = 0; r < kRI; ++r) ev[r] = ldg_stream(eg + r * kW + tid);
-  }
-  if (tid == 0) {
-#pragma unroll
-    for (int ch = 0; ch < kChunks; ++ch) mbar_init(bar + ch, 1);
-    mbar_init_fence();
   }
   __syncthreads();
   if (tid == 0) {
@@ -167,6 +174,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kT, 4) resize
   if (!PROJ) {
     stage_async(Ah, a.at_h + (size_t)q * kRI * 4, kRI * 4, tid, kT);
     aw = __ldg(reinterpret_cast<const float4*>(a.at_w) + tid);  // my column's transposed W band
+    if (tid < 4 * OW && (tid < 2 * OW ? !has_up : !has_dn)) Sn[tid] = 0.f;  // residual rows beyond the image do not exist
   }
   constexpr int kRP = (RJ * OW + kT - 1) / kT;  // residual values per thread in the W pass
   float yv[kRP];
@@ -177,36 +185,44 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kT, 4) resize
     yv[u] = (yp && o < RJ * OW) ? ldg_ro(yp + o) : 0.f;
   }
   stage_wait();
+  // where my rows go: rows 0 … HALO−1 are the DOWN halo of CTA q−1, rows 32−HALO … 31 the UP halo of CTA q+1
+  const unsigned sh_mine = smem_u32(Sh) + tid * 4, hb_mine = smem_u32(hbar);
+  const unsigned up_dst = has_up ? mapa_u32(sh_mine, (unsigned)(q - 1)) + HALO * kW * 4 : 0u, up_bar = has_up ? mapa_u32(hb_mine, (unsigned)(q - 1)) : 0u;
+  const unsigned dn_dst = has_dn ? mapa_u32(sh_mine, (unsigned)(q + 1)) : 0u, dn_bar = has_dn ? mapa_u32(hb_mine, (unsigned)(q + 1)) : 0u;
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");  // every CTA of the cluster has initialised its barriers
   RSF_T(1);
-  // ---- 0. x̂₀ in place, chunk by chunk as the copies land; clamp mask of my column → one register ----
+  // ---- 0. x̂₀ in place, chunk by chunk as the copies land; clamp mask of my column → one register; boundary rows → neighbours ----
   unsigned pass_bits = 0;
   {
     const float lo = a.src.clip ? -1.0f : -INFINITY, hi = a.src.clip ? 1.0f : INFINITY;
 #pragma unroll
     for (int ch = 0; ch < kChunks; ++ch) {
       mbar_wait(bar + ch, 0);
-      if (PROJ) continue;  // the rows ARE the data
 #pragma unroll
       for (int rr = 0; rr < kChunkRows; ++rr) {
         const int r = ch * kChunkRows + rr;
-        const float pre = x0_pre(Sx[r * kW + tid], ev[r], a.src.c1, a.src.c2);
-        Sx[r * kW + tid] = fminf(fmaxf(pre, lo), hi);
-        pass_bits |= (pre >= lo && pre <= hi) ? (1u << r) : 0u;
+        float v = Sx[r * kW + tid];
+        if (!PROJ) {
+          const float pre = x0_pre(v, ev[r], a.src.c1, a.src.c2);
+          v = fminf(fmaxf(pre, lo), hi);
+          Sx[r * kW + tid] = v;
+          pass_bits |= (pre >= lo && pre <= hi) ? (1u << r) : 0u;
+        }
+        if (r < HALO && has_up) st_async_f32(up_dst + r * kW * 4, v, up_bar);
+        if (r >= kRI - HALO && has_dn) st_async_f32(dn_dst + (r - (kRI - HALO)) * kW * 4, v, dn_bar);
       }
     }
   }
   RSF_T(2);
-  __syncthreads();
-  cluster_arrive_publish_synced();  // #1 (arrive): my x̂₀ rows are in place
 
   // ---- 1. H pass: t[jj][col] = Σ_k w[k] · x̂₀[sym(F·(RJ·q + jj) − HALO + k)][col] ----
   {
     float acc[RJ];
 #pragma unroll
     for (int jj = 0; jj < RJ; ++jj) acc[jj] = 0.f;
-    // Between the arrive and the wait: every term that needs only my own rows and comes FIRST in its accumulator (the order
-    // of the additions stays k = 0, 1, …: bit-identical to the two-kernel path) — residual rows whose window starts inside my
-    // rows, up to my last row; 69 % of the FMAs at F = 4.
+    // Before the halo rows are needed: every term that uses only my own rows and comes FIRST in its accumulator (the order of
+    // the additions stays k = 0, 1, …: bit-identical to the two-kernel path) — residual rows whose window starts inside my
+    // rows, up to my last row; 69 % of the FMAs at F = 4.  A thread reads only the column it wrote: no barrier.
 #pragma unroll
     for (int lr = 0; lr < kRI; ++lr) {
       const float v = Sx[lr * kW + tid];
@@ -217,16 +233,14 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kT, 4) resize
       }
     }
     RSF_T(3);
-    cluster_wait();  // #1 (wait): every CTA's x̂₀ rows are in place (and nobody reads the ε buffer any more)
+    mbar_wait_guarded(hbar, 0);  // the neighbours' rows have landed in Sh
     RSF_T(4);
-    // halo rows: the neighbour's rows over DSMEM or, at the image border, my own rows mirrored WITH edge repeat
+    // halo rows: pushed by the neighbour or, at the image border, my own rows mirrored WITH edge repeat
     // (−1 ↦ 0, −2 ↦ 1 …; 32 ↦ 31, 33 ↦ 30 …) — one base and one signed row stride each
-    const unsigned sx = smem_u32(Sx) + tid * 4;
-    constexpr int kRowB = kW * (int)sizeof(float);
-    const unsigned a_up = q > 0 ? mapa_u32(sx, (unsigned)(q - 1)) + (kRI - HALO) * kRowB : mapa_u32(sx, (unsigned)q) + (HALO - 1) * kRowB;
-    const int s_up = q > 0 ? kRowB : -kRowB;
-    const unsigned a_dn = q < kCluster - 1 ? mapa_u32(sx, (unsigned)(q + 1)) : mapa_u32(sx, (unsigned)q) + (kRI - 1) * kRowB;
-    const int s_dn = q < kCluster - 1 ? kRowB : -kRowB;
+    const float* pu = has_up ? Sh + tid : Sx + (HALO - 1) * kW + tid;
+    const int su = has_up ? kW : -kW;
+    const float* pd = has_dn ? Sh + HALO * kW + tid : Sx + (kRI - 1) * kW + tid;
+    const int sd = has_dn ? kW : -kW;
 #pragma unroll
     for (int wdx = 0; wdx < kRI + 2 * HALO; ++wdx) {
       const int lr = wdx - HALO;  // row relative to my first image row
@@ -237,13 +251,14 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kT, 4) resize
         used = used || (k >= 0 && k < TAPS && !(F * jj - HALO >= 0 && lr < kRI));
       }
       if (!used) continue;
-      const float v = lr < 0 ? ld_cluster(a_up + wdx * s_up) : (lr >= kRI ? ld_cluster(a_dn + (lr - kRI) * s_dn) : Sx[lr * kW + tid]);
+      const float v = lr < 0 ? pu[wdx * su] : (lr >= kRI ? pd[(lr - kRI) * sd] : Sx[lr * kW + tid]);
 #pragma unroll
       for (int jj = 0; jj < RJ; ++jj) {
         const int k = wdx - F * jj;
         if (k >= 0 && k < TAPS && !(F * jj - HALO >= 0 && lr < kRI)) acc[jj] = fmaf(a.w[k], v, acc[jj]);
       }
     }
+    __syncthreads();  // St aliases Sh: every thread has read its halo column
 #pragma unroll
     for (int jj = 0; jj < RJ; ++jj) {
       float* row = St + jj * PADW + HALO;
@@ -251,39 +266,50 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kT, 4) resize
       if (tid < HALO) row[-1 - tid] = acc[jj];                   // columns −1, −2, … mirror columns 0, 1, …
       if (tid >= kW - HALO) row[2 * kW - 1 - tid] = acc[jj];     // columns 256, 257, … mirror 255, 254, …
     }
-    if (PROJ) cluster_arrive_done_reading(acc[0], acc[RJ - 1]);  // #2 (arrive): my DSMEM reads have returned
   }
   __syncthreads();
 
   RSF_T(5);
-  // ---- 2. W pass, residual, partial sums ----
+  // ---- 2. W pass, residual, partial sums; my first / last two residual rows → the neighbours' Sn ----
   float sq = 0.f, ab = 0.f;
+  {
+    const unsigned sn_mine = smem_u32(Sn), nb_mine = smem_u32(nbar);
+    // my rows 0, 1 are rows RJ, RJ+1 of CTA q−1 (its Sn rows 2, 3); my rows RJ−2, RJ−1 are rows −2, −1 of CTA q+1 (its Sn rows 0, 1)
+    const unsigned nup_dst = (!PROJ && has_up) ? mapa_u32(sn_mine, (unsigned)(q - 1)) + 2 * OW * 4 : 0u;
+    const unsigned nup_bar = (!PROJ && has_up) ? mapa_u32(nb_mine, (unsigned)(q - 1)) : 0u;
+    const unsigned ndn_dst = (!PROJ && has_dn) ? mapa_u32(sn_mine, (unsigned)(q + 1)) : 0u;
+    const unsigned ndn_bar = (!PROJ && has_dn) ? mapa_u32(nb_mine, (unsigned)(q + 1)) : 0u;
 #pragma unroll
-  for (int u = 0; u < kRP; ++u) {
-    const int o = tid + u * kT;
-    if (o < RJ * OW) {
-      const int jj = o / OW, l = o - jj * OW;
-      const float4* tr = reinterpret_cast<const float4*>(St + jj * PADW + F * l);  // padded column F·l = image column F·l − HALO
-      float acc = 0.f;
+    for (int u = 0; u < kRP; ++u) {
+      const int o = tid + u * kT;
+      if (o < RJ * OW) {
+        const int jj = o / OW, l = o - jj * OW;
+        const float4* tr = reinterpret_cast<const float4*>(St + jj * PADW + F * l);  // padded column F·l = image column F·l − HALO
+        float acc = 0.f;
 #pragma unroll
-      for (int m = 0; m < TAPS / 4; ++m) {
-        const float4 t4 = tr[m];
-        acc = fmaf(a.w[4 * m + 0], t4.x, acc);
-        acc = fmaf(a.w[4 * m + 1], t4.y, acc);
-        acc = fmaf(a.w[4 * m + 2], t4.z, acc);
-        acc = fmaf(a.w[4 * m + 3], t4.w, acc);
+        for (int m = 0; m < TAPS / 4; ++m) {
+          const float4 t4 = tr[m];
+          acc = fmaf(a.w[4 * m + 0], t4.x, acc);
+          acc = fmaf(a.w[4 * m + 1], t4.y, acc);
+          acc = fmaf(a.w[4 * m + 2], t4.z, acc);
+          acc = fmaf(a.w[4 * m + 3], t4.w, acc);
+        }
+        const float res = (yp && !PROJ) ? yv[u] - acc : acc;
+        Sr[o] = res;
+        if (PROJ) Sy[o] = yv[u];
+        if (!PROJ) {
+          if (jj < 2 && has_up) st_async_f32(nup_dst + o * 4, res, nup_bar);
+          if (jj >= RJ - 2 && has_dn) st_async_f32(ndn_dst + (o - (RJ - 2) * OW) * 4, res, ndn_bar);
+          if (a.r_out) a.r_out[((int64_t)n * a.C + c) * (H / F) * OW + (int64_t)q * RJ * OW + o] = res;
+        }
+        sq = fmaf(res, res, sq);
+        ab += fabsf(res);
       }
-      const float res = (yp && !PROJ) ? yv[u] - acc : acc;
-      Sr[o] = res;
-      if (PROJ) Sy[o] = yv[u];
-      if (!PROJ && a.r_out) a.r_out[((int64_t)n * a.C + c) * (H / F) * OW + (int64_t)q * RJ * OW + o] = res;
-      sq = fmaf(res, res, sq);
-      ab += fabsf(res);
     }
   }
   RSF_T(6);
+  __syncthreads();  // my residual rows are complete
   if (PROJ) {
-    __syncthreads();
     float* op_ = a.g + n * a.g_stride + poff;
     const int l = tid / F;
 #pragma unroll
@@ -291,11 +317,8 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kT, 4) resize
       const int o = (ii / F) * OW + l;
       stg_stream(op_ + ii * kW + tid, __fadd_rn(__fsub_rn(Sx[ii * kW + tid], Sr[o]), Sy[o]));
     }
-    cluster_wait();  // #2: nobody reads my rows over DSMEM any more
     return;
   }
-  __syncthreads();                  // my residual rows are complete …
-  cluster_arrive_publish_synced();  // #2 (arrive) … and announced; the partial sums below overlap the other CTAs' arrival
   if (a.partials) {
     block_sum2(sq, ab, red);
     if (tid == 0) {
@@ -323,22 +346,8 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kT, 4) resize
 #pragma unroll
     for (int m = 2; m < RJ + 2; ++m) uu[m] = urow(Sr + (m - 2) * OW);  // my own rows first
     RSF_T(7);
-    cluster_wait();                                                       // every CTA's residual rows are in place
+    mbar_wait_guarded(nbar, 0);  // the neighbours' two rows each have landed in Sn
     RSF_T(8);
-    // The 2+2 neighbour rows first come into LOCAL shared memory, one value per thread (DSMEM moves ≈17 B per cycle and SM:
-    // sixteen values per thread read straight from the neighbours were 16 KB per CTA and ≈1 500 cycles of the N = 8 trace;
-    // staged it is 1 KB).  St is free: every thread passed the barrier after the W pass.
-    const float* rup = q > 0 ? cluster.map_shared_rank(Sr, q - 1) : Sr;
-    const float* rdn = q < kCluster - 1 ? cluster.map_shared_rank(Sr, q + 1) : Sr;
-    float* Sn = St;  // (4, OW): residual rows RJ·q − 2, RJ·q − 1, RJ·(q+1), RJ·(q+1) + 1 (zero where the image ends)
-    float nv = 0.f;
-    if (tid < 4 * OW) {
-      const int m = tid / OW, l = tid - m * OW;
-      if (m < 2 ? q > 0 : q < kCluster - 1) nv = m < 2 ? rup[(RJ - 2 + m) * OW + l] : rdn[(m - 2) * OW + l];
-      Sn[tid] = nv;
-    }
-    cluster_arrive_done_reading(nv, 0.f);  // #3: my remote read has returned: the neighbours may exit once everybody has said so
-    __syncthreads();
 #pragma unroll
     for (int m = 0; m < 2; ++m) {
       uu[m] = urow(Sn + m * OW);
@@ -356,7 +365,6 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kT, 4) resize
       stg_stream(gp + ii * kW + tid, ((pass_bits >> ii) & 1u) ? s : 0.f);
     }
     RSF_T(10);
-    cluster_wait();
     RSF_T(11);
   }
 }
