@@ -1,4 +1,4 @@
-"""Round-2 kernels: the fused super-resolution guidance kernel (thread-block cluster, DSMEM halos), the posterior update
+"""Round-2 kernels: the fused super-resolution guidance kernel (thread-block cluster, halo rows pushed over DSMEM), the posterior update
 with the deferred guidance coefficient, and the in-kernel Philox noise — against the oracle and against the two-kernel
 path they replace.  All through the C ABI."""
 import numpy as np
@@ -69,6 +69,42 @@ def test_fused_sr_guidance_vs_two_kernels_and_oracle(factor, n, idx, clip):
     g3 = torch.zeros(n, 3, 256, 256, device=DEV)
     p3, r3, _ = plan.guidance(x, eps, k, clip, y, out=g3)
     assert r3 is None and torch.equal(g3, g1[:, :3]) and torch.equal(p3, p1)
+
+
+@pytest.mark.parametrize("factor", [4, 8])
+def test_fused_sr_push_exchange_repeatable_under_load(factor):
+    """The cluster kernel's neighbour exchange (st.async pushes completing on the destination CTA's mbarriers) under load:
+    more clusters than the machine holds at once, launches interleaved on two streams so clusters of different launches
+    share SMs, every repeat bit-identical and equal to the per-particle result of a one-particle launch (a plane's cluster
+    must not depend on who runs beside it)."""
+    from dps_ttc_b200 import tables
+    from dps_ttc_b200.kernels import OperatorPlan
+    (fh, wh), (fw, ww), _ = tables.resizer_tables((1, 3, 256, 256), 1.0 / factor)
+    plan = OperatorPlan.resize(fh, wh, fw, ww, 3, 256, 256, DEV)
+    k = _consts(700)
+    n = 80                                        # 240 clusters = 1 920 CTAs; at most 4 per SM are resident
+    gen = torch.Generator(DEV).manual_seed(77 + factor)
+    x = torch.randn(n, 3, 256, 256, device=DEV, generator=gen) / k.c1
+    eps = torch.randn(n, 3, 256, 256, device=DEV, generator=gen) * 0.3 / k.c2
+    y = torch.randn(1, 3, 256 // factor, 256 // factor, device=DEV, generator=gen)
+    g0 = torch.zeros(n, 3, 256, 256, device=DEV)
+    p0, _, _ = plan.guidance(x, eps, k, True, y, out=g0)
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    outs = []
+    for rep in range(6):
+        for st in (s1, s2):
+            with torch.cuda.stream(st):
+                g = torch.full((n, 3, 256, 256), float("nan"), device=DEV)
+                p, _, _ = plan.guidance(x, eps, k, True, y, out=g)
+                outs.append((g, p))
+    torch.cuda.synchronize()
+    for g, p in outs:
+        assert torch.equal(g, g0) and torch.equal(p, p0)
+    for i in (0, 41, n - 1):                      # one particle alone = the same particle inside the batch
+        gi = torch.zeros(1, 3, 256, 256, device=DEV)
+        pi, _, _ = plan.guidance(x[i:i + 1], eps[i:i + 1], k, True, y, out=gi)
+        assert torch.equal(gi[0], g0[i]) and torch.equal(pi[0], p0[i])
 
 
 @pytest.mark.parametrize("sampler,mode", [("ddpm", 1), ("ddpm", 2), ("ddim", 1)])
