@@ -27,12 +27,12 @@
 #include "operator.cuh"
 
 namespace {
-constexpr int kRows = 32;
+constexpr int kRows = 32;   // rows per CTA of the standard variant; small grids use 16 (template parameter kR)
 #ifndef DPS_SPARSE_GROUP
 #define DPS_SPARSE_GROUP 16
 #endif
 constexpr int kGroup = DPS_SPARSE_GROUP;  // vertically adjacent outputs per thread and pass
-constexpr int kMaxThreads = 320 * 16 / kGroup;
+constexpr int kMaxThreads = 320 * 16 / kGroup;  // 32-row CTAs: 5 column blocks x 2 row groups; 16-row CTAs launch half of that
 constexpr int kSWFixed = 384;   // compile-time tile row strides of the 256-wide fast path: halo ≤ 64 columns per side,
 constexpr int kSWFixedS = 320;  // or ≤ 32 (smaller tile, one more CTA per SM)
 
@@ -66,8 +66,12 @@ DPS_DEV int tap_dx(int v) { return (int)(short)(v & 0xffff); }
 //                   cols [−2Rx, W+2Rx).  blockDim.x ≥ number of output columns is NOT required (columns loop).
 // kSW > 0: the tile row stride is the compile-time constant kSW (every LDS of the tap loop gets an immediate offset,
 // no address arithmetic); kSW = 0: stride W + 2·halo computed at run time.
-template <bool kAdjoint, int kSW>
-__global__ void __launch_bounds__(kMaxThreads) sparse_kernel(const Tap* __restrict__ taps_g, int ntaps, int n_even, int Ry, int Rx, int C,
+// kR: output rows per CTA — 32, or 16 when the 32-row grid would leave most SMs with one CTA (N ≲ 12 particles: a CTA's tap
+// loop is a ≈40 µs dependent chain, so the launch time IS one CTA's time; twice as many half-size CTAs halve it).  The
+// residual partial sums are kept per 16-ROW GROUP in both variants (one warp per (group, 64-column block), warp sums added in
+// block order), so a launch's variant never changes a norm: P = C · 2 · ⌈H/32⌉ pairs per particle either way.
+template <bool kAdjoint, int kSW, int kR>
+__global__ void __launch_bounds__(kMaxThreads * kR / 32) sparse_kernel(const Tap* __restrict__ taps_g, int ntaps, int n_even, int Ry, int Rx, int C,
                                                      int H, int W, int strips, const FwdArgs fa, const AdjArgs aa,
                                                      float* __restrict__ t_out) {
   extern __shared__ __align__(16) float smem[];
@@ -75,7 +79,7 @@ __global__ void __launch_bounds__(kMaxThreads) sparse_kernel(const Tap* __restri
   const int OH = kAdjoint ? H + 2 * Ry : H;      // output rows
   const int halo_x = kAdjoint ? 2 * Rx : Rx;     // tile columns left of image column 0
   const int SW = kSW > 0 ? kSW : W + 2 * halo_x;
-  const int tile_rows = kRows + 2 * Ry;
+  const int tile_rows = kR + 2 * Ry;
   float* tile = smem;
   TapOff* taps = reinterpret_cast<TapOff*>(tile + ((tile_rows * SW + 3) & ~3));
   float* red = reinterpret_cast<float*>(taps + ntaps);
@@ -83,7 +87,7 @@ __global__ void __launch_bounds__(kMaxThreads) sparse_kernel(const Tap* __restri
   const int strip = blockIdx.x % strips;
   const int c = blockIdx.x / strips;
   const int n = blockIdx.y;
-  const int o0 = strip * kRows;                  // first output row of this CTA (padded coords for the adjoint)
+  const int o0 = strip * kR;                     // first output row of this CTA (padded coords for the adjoint)
   const int img_row0 = kAdjoint ? o0 - 2 * Ry : o0 - Ry;  // image row held by tile row 0
   const int tid = threadIdx.x, nthreads = blockDim.x;
   const int64_t plane = (int64_t)c * H * W;
@@ -109,8 +113,10 @@ __global__ void __launch_bounds__(kMaxThreads) sparse_kernel(const Tap* __restri
       c1 = fa.src.c1; c2 = fa.src.c2; clip = fa.src.clip;
     }
     const int w4 = W / 4;
-    // four independent 16-byte requests (eight with ε) per thread in flight before the first shared store
-    constexpr int kSB = 4;
+    // kSB independent 16-byte requests (twice that with ε) per thread in flight before the first shared store: at N = 8
+    // (one or two CTAs per SM) every batch is a full DRAM / L2 round trip on the launch's critical path
+    // — the small-grid variant (kR = 16) therefore keeps 7 (14) in flight, the full-machine variant 4 (8) and 64 registers.
+    constexpr int kSB = kR == 16 ? 7 : 4;
     for (int i0 = tid; i0 < tile_rows * w4; i0 += kSB * nthreads) {
       float4 v[kSB];
 #pragma unroll
@@ -147,18 +153,18 @@ __global__ void __launch_bounds__(kMaxThreads) sparse_kernel(const Tap* __restri
   }
   __syncthreads();
 
-  float sq = 0.f, ab = 0.f;
   // items = (64-column block, group of kGroup rows), one per WARP: lane L owns columns 64·blk + L and 64·blk + 32 + L.
   // Every tile load of the tap loop is then a 32-bit access of 32 CONSECUTIVE words whatever the tap's dx: one wavefront,
   // no bank conflict.  (Adjacent column pairs — one 64-bit load per pair — are conflict-free only for even dx; for odd dx
   // the two 32-bit loads of a pair have stride 2 and cost two wavefronts each: ncu counted 28 M excessive wavefronts of
   // 85 M at N = 128, profiles/r3c_ncu_motion_fwd_n128.csv, and shared-memory bandwidth is what bounds this kernel.)
   const int nblk = (OW + 63) >> 6;
-  constexpr int kGroups = kRows / kGroup;
+  constexpr int kGroups = kR / kGroup;
   const int lane = tid & 31;
   for (int item = tid >> 5; item < nblk * kGroups; item += nthreads >> 5) {
     const int grp = item / nblk, blk = item - grp * nblk;
     const int g0 = grp * kGroup;
+    float sq = 0.f, ab = 0.f;
     const int col_lo = blk * 64 + lane;
     const bool hi_ok = col_lo + 32 < OW, lo_ok = col_lo < OW;
     const int col_hi = hi_ok ? col_lo + 32 : col_lo;  // (a block that sticks out of the row recomputes its low half)
@@ -186,6 +192,16 @@ __global__ void __launch_bounds__(kMaxThreads) sparse_kernel(const Tap* __restri
         acc[j] = __ffma2_rn(make_float2(w.w, w.w), v[j + 3], acc[j]);
       }
     }
+    constexpr bool kYBatch = !kAdjoint && kR == 16;  // small grids: the epilogue's y loads are a serial chain of L2 round trips
+    float2 yv[kYBatch ? kGroup : 1];
+    if (kYBatch && fa.y) {  // all measurement values of the group in flight at once (one round trip, not kGroup)
+#pragma unroll
+      for (int j = 0; j < kGroup; ++j) {
+        const int row = o0 + g0 + j;
+        const float* yr = fa.y + n * fa.y_stride + plane + (int64_t)row * W;
+        yv[j] = make_float2((row < OH && lo_ok) ? __ldg(yr + col_lo) : 0.f, (row < OH && hi_ok) ? __ldg(yr + col_hi) : 0.f);
+      }
+    }
 #pragma unroll
     for (int j = 0; j < kGroup; ++j) {
       const int row = o0 + g0 + j;
@@ -194,8 +210,12 @@ __global__ void __launch_bounds__(kMaxThreads) sparse_kernel(const Tap* __restri
         const int64_t off = plane + (int64_t)row * W;
         float2 res = acc[j];
         if (fa.y) {
-          const float* yr = fa.y + n * fa.y_stride + off;
-          res = make_float2(__fsub_rn(lo_ok ? __ldg(yr + col_lo) : 0.f, res.x), __fsub_rn(hi_ok ? __ldg(yr + col_hi) : 0.f, res.y));
+          if (kYBatch) {
+            res = make_float2(__fsub_rn(yv[j].x, res.x), __fsub_rn(yv[j].y, res.y));
+          } else {
+            const float* yr = fa.y + n * fa.y_stride + off;
+            res = make_float2(__fsub_rn(lo_ok ? __ldg(yr + col_lo) : 0.f, res.x), __fsub_rn(hi_ok ? __ldg(yr + col_hi) : 0.f, res.y));
+          }
         }
         float* orow = fa.out + (int64_t)n * C * H * W + off;
         if (lo_ok) { stg_stream(orow + col_lo, res.x); sq = fmaf(res.x, res.x, sq); ab += fabsf(res.x); }
@@ -206,11 +226,26 @@ __global__ void __launch_bounds__(kMaxThreads) sparse_kernel(const Tap* __restri
         if (hi_ok) stg_stream(trow + col_hi, acc[j].y);
       }
     }
+    if (!kAdjoint && fa.partials) {  // this item's sums → red[item]; added per row group, in block order, below
+      sq = warp_sum(sq);
+      ab = warp_sum(ab);
+      if (lane == 0) {
+        red[item] = sq;
+        red[32 + item] = ab;
+      }
+    }
   }
   if (!kAdjoint && fa.partials) {
-    block_sum2(sq, ab, red);
-    if (tid == 0) {
-      float* pp = fa.partials + ((int64_t)n * (C * strips) + blockIdx.x) * 2;
+    __syncthreads();
+    if (tid < kGroups) {
+      float sq = 0.f, ab = 0.f;
+      for (int blk = 0; blk < nblk; ++blk) {
+        sq += red[tid * nblk + blk];
+        ab += red[32 + tid * nblk + blk];
+      }
+      // slot of the 16-row group (o0 + 16·tid)/16 of channel c: the same for the 32-row and the 16-row variant
+      const int groups_per_plane = strips * kGroups;
+      float* pp = fa.partials + ((int64_t)n * (C * groups_per_plane) + c * groups_per_plane + strip * kGroups + tid) * 2;
       pp[0] = sq;
       pp[1] = ab;
     }
@@ -251,13 +286,13 @@ int sparse_stride(const dps_operator* op, bool adjoint, bool* fixed) {
   return !*fixed ? op->W + 2 * halo_x : (op->W + 2 * halo_x <= kSWFixedS ? kSWFixedS : kSWFixed);
 }
 
-size_t sparse_smem(const dps_operator* op, bool adjoint) {
+size_t sparse_smem(const dps_operator* op, bool adjoint, int rows = kRows) {
   const SparseTables* t = op->sparse;
   bool fixed;
   const int SW = sparse_stride(op, adjoint, &fixed);
-  size_t bytes = sizeof(float) * ((((size_t)(kRows + 2 * t->Ry) * SW + 3) & ~(size_t)3) + 64) + sizeof(TapOff) * (size_t)t->ntaps;
+  size_t bytes = sizeof(float) * ((((size_t)(rows + 2 * t->Ry) * SW + 3) & ~(size_t)3) + 64) + sizeof(TapOff) * (size_t)t->ntaps;
   if (fixed && bytes > 227 * 1024) {  // tall kernels: fall back to the tight run-time stride
-    bytes = sizeof(float) * ((((size_t)(kRows + 2 * t->Ry) * (op->W + 2 * (adjoint ? 2 * t->Rx : t->Rx)) + 3) & ~(size_t)3) + 64) +
+    bytes = sizeof(float) * ((((size_t)(rows + 2 * t->Ry) * (op->W + 2 * (adjoint ? 2 * t->Rx : t->Rx)) + 3) & ~(size_t)3) + 64) +
             sizeof(TapOff) * (size_t)t->ntaps;
   }
   return bytes;
@@ -270,6 +305,24 @@ bool sparse_fixed(const dps_operator* op, bool adjoint) {
   return fixed && bytes <= 227 * 1024;
 }
 
+}  // namespace
+
+namespace {
+template <bool kA, int kSW, int kR>
+int sparse_optin_one() {
+  DPS_CUDA(cudaFuncSetAttribute(sparse_kernel<kA, kSW, kR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  return DPS_OK;
+}
+int sparse_optin_all() {  // (per current device: called from every plan creation)
+  int rc = 0;
+  rc |= sparse_optin_one<false, 0, kRows>();         rc |= sparse_optin_one<true, 0, kRows>();
+  rc |= sparse_optin_one<false, kSWFixed, kRows>();  rc |= sparse_optin_one<true, kSWFixed, kRows>();
+  rc |= sparse_optin_one<false, kSWFixedS, kRows>(); rc |= sparse_optin_one<true, kSWFixedS, kRows>();
+  rc |= sparse_optin_one<false, 0, 16>();            rc |= sparse_optin_one<true, 0, 16>();
+  rc |= sparse_optin_one<false, kSWFixed, 16>();     rc |= sparse_optin_one<true, kSWFixed, 16>();
+  rc |= sparse_optin_one<false, kSWFixedS, 16>();    rc |= sparse_optin_one<true, kSWFixedS, 16>();
+  return rc ? DPS_ERR_CUDA : DPS_OK;
+}
 }  // namespace
 
 int sparse_create(dps_operator* op, const float* kernel, int ksize) {
@@ -319,13 +372,8 @@ int sparse_create(dps_operator* op, const float* kernel, int ksize) {
   DPS_REQUIRE(sparse_smem(op, true) <= 227 * 1024, DPS_ERR_UNSUPPORTED, "sparse blur: tile exceeds shared memory");
   DPS_CUDA(cudaMalloc(&t->taps_dev, taps.size() * sizeof(Tap)));
   DPS_CUDA(cudaMemcpy(t->taps_dev, taps.data(), taps.size() * sizeof(Tap), cudaMemcpyHostToDevice));
-  DPS_CUDA(cudaFuncSetAttribute(sparse_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  DPS_CUDA(cudaFuncSetAttribute(sparse_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  DPS_CUDA(cudaFuncSetAttribute(sparse_kernel<false, kSWFixed>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  DPS_CUDA(cudaFuncSetAttribute(sparse_kernel<true, kSWFixed>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  DPS_CUDA(cudaFuncSetAttribute(sparse_kernel<false, kSWFixedS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  DPS_CUDA(cudaFuncSetAttribute(sparse_kernel<true, kSWFixedS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  op->P = op->C * ((op->H + kRows - 1) / kRows);
+  if (int rc = sparse_optin_all()) return rc;
+  op->P = op->C * 2 * ((op->H + kRows - 1) / kRows);  // one pair per 16-row group
   op->taps = nnz;
   op->aux_floats = (int64_t)op->C * (op->H + 2 * Ry) * (op->W + 2 * Rx);  // padded t of the adjoint
   return DPS_OK;
@@ -338,23 +386,47 @@ void sparse_destroy(dps_operator* op) {
   op->sparse = nullptr;
 }
 
-int sparse_forward(const dps_operator* op, const FwdArgs& a, cudaStream_t st) {
+int sparse_sm_count(int device) {
+  static int sms[64] = {};
+  if (device < 0 || device >= 64) return 148;
+  if (!sms[device]) cudaDeviceGetAttribute(&sms[device], cudaDevAttrMultiProcessorCount, device);
+  return sms[device] > 0 ? sms[device] : 148;
+}
+
+// rows per CTA: 16 while the 32-row grid would leave the machine under two CTAs per SM
+int sparse_rows(const dps_operator* op, int strips32, int n) {
+  return (int64_t)op->C * strips32 * n < 2 * (int64_t)sparse_sm_count(op->device) ? 16 : kRows;
+}
+
+template <bool kAdjoint, int kSW, int kR>
+void sparse_launch(const dps_operator* op, int out_h, int out_w, int n, const FwdArgs& fa, const AdjArgs& aa, float* t_out, cudaStream_t st) {
   const SparseTables* t = op->sparse;
-  AdjArgs dummy = {};
-  const int strips = (op->H + kRows - 1) / kRows;
-  dim3 grid((unsigned)(op->C * strips), (unsigned)a.n);
+  const int strips = ((out_h + kRows - 1) / kRows) * (kRows / kR);  // the 16-row grid covers the same 32-row strips (slots of the partial sums)
+  const int threads = std::max(kAdjoint ? 32 : 128, std::min(kMaxThreads * kR / 32, 32 * ((out_w + 63) / 64) * (kR / kGroup)));
+  dim3 grid((unsigned)(op->C * strips), (unsigned)n);
+  sparse_kernel<kAdjoint, kSW, kR><<<grid, threads, sparse_smem(op, kAdjoint, kR), st>>>(t->taps_dev, t->ntaps, t->n_even, t->Ry, t->Rx, op->C, op->H,
+                                                                                      op->W, strips, fa, aa, t_out);
+}
+template <bool kAdjoint>
+void sparse_dispatch(const dps_operator* op, int out_h, int out_w, int n, const FwdArgs& fa, const AdjArgs& aa, float* t_out, cudaStream_t st) {
   bool fx;
-  const int SW = sparse_stride(op, false, &fx);
-  const int fthreads = std::max(256, std::min(kMaxThreads, 32 * ((op->W + 63) / 64) * (kRows / kGroup)));
-  if (sparse_fixed(op, false) && SW == kSWFixedS)
-    sparse_kernel<false, kSWFixedS><<<grid, fthreads, sparse_smem(op, false), st>>>(t->taps_dev, t->ntaps, t->n_even, t->Ry, t->Rx, op->C,
-                                                                               op->H, op->W, strips, a, dummy, nullptr);
-  else if (sparse_fixed(op, false))
-    sparse_kernel<false, kSWFixed><<<grid, fthreads, sparse_smem(op, false), st>>>(t->taps_dev, t->ntaps, t->n_even, t->Ry, t->Rx, op->C,
-                                                                              op->H, op->W, strips, a, dummy, nullptr);
-  else
-    sparse_kernel<false, 0><<<grid, fthreads, sparse_smem(op, false), st>>>(t->taps_dev, t->ntaps, t->n_even, t->Ry, t->Rx, op->C, op->H,
-                                                                       op->W, strips, a, dummy, nullptr);
+  const int SW = sparse_stride(op, kAdjoint, &fx);
+  const int rows = sparse_rows(op, (out_h + kRows - 1) / kRows, n);
+  const int sel = sparse_fixed(op, kAdjoint) ? (SW == kSWFixedS ? 1 : 2) : 0;
+#define DPS_SPARSE_CASE(S, SWV)                                                                          \
+  if (sel == S) {                                                                                        \
+    if (rows == 16) sparse_launch<kAdjoint, SWV, 16>(op, out_h, out_w, n, fa, aa, t_out, st);            \
+    else sparse_launch<kAdjoint, SWV, kRows>(op, out_h, out_w, n, fa, aa, t_out, st);                    \
+  }
+  DPS_SPARSE_CASE(1, kSWFixedS)
+  DPS_SPARSE_CASE(2, kSWFixed)
+  DPS_SPARSE_CASE(0, 0)
+#undef DPS_SPARSE_CASE
+}
+
+int sparse_forward(const dps_operator* op, const FwdArgs& a, cudaStream_t st) {
+  AdjArgs dummy = {};
+  sparse_dispatch<false>(op, op->H, op->W, a.n, a, dummy, nullptr, st);
   DPS_LAUNCH_CHECK("sparse_blur_forward");
   return DPS_OK;
 }
@@ -366,20 +438,7 @@ int sparse_adjoint(const dps_operator* op, const AdjArgs& a, cudaStream_t st) {
   float* scratch = const_cast<float*>(a.aux);
   FwdArgs dummy = {};
   const int OH = op->H + 2 * t->Ry, OW = op->W + 2 * t->Rx;
-  const int strips = (OH + kRows - 1) / kRows;
-  const int threads = std::min(kMaxThreads, 32 * ((OW + 63) / 64) * (kRows / kGroup));  // one warp per (64-column block, row group)
-  dim3 grid((unsigned)(op->C * strips), (unsigned)a.n);
-  bool fx;
-  const int SW = sparse_stride(op, true, &fx);
-  if (sparse_fixed(op, true) && SW == kSWFixedS)
-    sparse_kernel<true, kSWFixedS><<<grid, threads, sparse_smem(op, true), st>>>(t->taps_dev, t->ntaps, t->n_even, t->Ry, t->Rx, op->C,
-                                                                                 op->H, op->W, strips, dummy, a, scratch);
-  else if (sparse_fixed(op, true))
-    sparse_kernel<true, kSWFixed><<<grid, threads, sparse_smem(op, true), st>>>(t->taps_dev, t->ntaps, t->n_even, t->Ry, t->Rx, op->C,
-                                                                                op->H, op->W, strips, dummy, a, scratch);
-  else
-    sparse_kernel<true, 0><<<grid, threads, sparse_smem(op, true), st>>>(t->taps_dev, t->ntaps, t->n_even, t->Ry, t->Rx, op->C, op->H,
-                                                                         op->W, strips, dummy, a, scratch);
+  sparse_dispatch<true>(op, OH, OW, a.n, dummy, a, scratch, st);
   DPS_LAUNCH_CHECK("sparse_blur_adjoint_t");
   dim3 fgrid((unsigned)((op->H * op->W + 255) / 256), (unsigned)op->C, (unsigned)a.n);
   sparse_fold_kernel<<<fgrid, 256, 0, st>>>(scratch, t->Ry, t->Rx, op->C, op->H, op->W, a);
