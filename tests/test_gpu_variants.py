@@ -47,6 +47,7 @@ def test_lean_kernels_bit_identical_to_round1_kernels(op, n, envs):
     assert "PASS" in res.stdout
 
 
+@pytest.mark.gpu
 def test_motion_blur_row_variants_bit_identical():
     """blur_sparse.cu launches 16-row CTAs while the grid is small (N ≲ 12) and 32-row CTAs otherwise; a particle's residual,
     partial sums and cotangent must not depend on which one ran (sharded runs put 8 particles per launch where the unsharded
