@@ -114,7 +114,7 @@ DPS_DEV void st_async_f32(unsigned remote_addr, float v, unsigned remote_bar) {
 }
 
 template <int F, bool PROJ>
-__global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kT, 4) resize_guidance_kernel(const __grid_constant__ FusedArgs a) {
+__global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kT, F == 4 ? 4 : 3) resize_guidance_kernel(const __grid_constant__ FusedArgs a) {
   using G = Geo<F>;
   constexpr int TAPS = G::TAPS, HALO = G::HALO, RJ = G::RJ, OW = G::OW, RU = G::RU, PADW = G::PADW, H = kRI * kCluster;
   static_assert(2 * HALO * kW >= RJ * PADW, "the H-pass tile aliases the halo buffer");
