@@ -4,8 +4,9 @@
 // Jacobian-transpose
 //   Jᵀg [p] = (1/L)·Re Σ_k G[k]·conj(F[k])/|F[k]|·e^{−2πi k·p/L},   G = ifftshift(g),  zero where |F| = 0.
 //
-// L = H + 2·pad = 384 = 8·8·6: hand-written mixed-radix Stockham FFT in shared memory, three
-// register-blocked stages (radix 8, 8, 6), twiddles from a 384-entry table.  What makes it cheap:
+// L = H + 2·pad = 384 = 8·8·6 (256² images; also 256 = 8·8·4 for 128² and 192 = 8·8·3 for 64²: phase_impl.cuh is compiled once
+// per length): hand-written mixed-radix Stockham FFT in shared memory, three register-blocked stages (radix 8, 8, L/64),
+// twiddles from an L-entry table.  What makes it cheap:
 //   * real input  → two image rows ride one complex FFT; only the half spectrum k2 ∈ [0,192] is kept and
 //     the other half of the magnitude is written by Hermitian symmetry |F[−k]| = |F[k]|;
 //   * zero padding → only the 256 non-zero rows are row-transformed, the column pass reads 256 of 384;
@@ -23,33 +24,14 @@
 
 #include "operator.cuh"
 
-namespace {
-constexpr int kL = 384;
-constexpr int kHalf = kL / 2 + 1;  // 193
-constexpr int kLP = kL + kL / 8 + 1;  // padded length of a sequence in shared memory: 433, ODD so that the same element of
-                                      // consecutive sequences falls into different banks (loops that run over the sequence index)
-constexpr int kLF = kL + 1;           // row stride of the float planes staged per sequence (same reason)
-constexpr int kImg = 256;
-constexpr int kPad = 64;
-constexpr int kThreads = 256;
-constexpr int kRowsPerCta = 16;  // K1 / A2: image rows per CTA → 8 packed FFTs (55.9 KB of shared memory → 4 CTAs per SM)
-constexpr int kColsPerCta = 8;   // K2 / A1: spectrum columns per CTA
-constexpr int kColGroups = (kHalf + kColsPerCta - 1) / kColsPerCta;  // 25
-// the adjoint prefers wider CTAs: its scattered reads of r coalesce into 64-byte runs with 16 columns
-constexpr int kRowsAdj = 32;
-constexpr int kColsAdj = 16;
-constexpr int kColGroupsAdj = (kHalf + kColsAdj - 1) / kColsAdj;  // 13
-}  // namespace
 
 struct PhaseTables {
   float2* tw = nullptr;  // exp(−2πi j/384), j ∈ [0,384)
 };
 
-namespace {
 
-// Shared-memory sequences are padded by one element every 8: element i lives at i + (i >> 3).  With 8-byte
-// elements this makes the stride-8 / stride-64 scatter of the Stockham stages conflict-free (stride 9 / 72).
-DPS_DEV int P(int i) { return i + (i >> 3); }
+namespace {
+constexpr int kThreads = 256;
 
 // for (i = tid; i < kItems; i += kThreads) store(i, load(i)) with the loads of kBatch iterations issued before the
 // first store: a "load, then store to shared" loop otherwise serialises one global round trip per iteration.
@@ -127,194 +109,12 @@ DPS_DEV void dft6(float2* v) {
   v[2] = cadd(e2, t2); v[5] = csub(e2, t2);   // W6^5 = −W6^2
 }
 
-// Twiddle exp(−2πi j/384), j ∈ [0,384), from the half table in shared memory: tw[j+192] = −tw[j].  Halving the table
-// (1.5 KB instead of 3 KB) is what lets FOUR 8-sequence CTAs (57 KB each) share an SM instead of three.
-constexpr int kTW = kL / 2;
-DPS_DEV float2 twid(const float2* tw, int j) {
-  const bool hi = j >= kTW;
-  const float2 t = tw[hi ? j - kTW : j];
-  return hi ? make_float2(-t.x, -t.y) : t;
-}
-
-// `nfft` independent forward FFTs of length 384, sequence f at a[f*384 ...]; the result lands in b.
-// Stockham autosort, radices 8·8·6 (natural order in, natural order out).  All threads must call it.
-__device__ void fft384_batch(float2* a, float2* b, const float2* tw, int nfft) {
-  const int tid = threadIdx.x;
-  // stage 1: R = 8, Ns = 1 (no twiddles): b[8j + r] = DFT8(a[j + 48r])
-  for (int it = tid; it < nfft * 48; it += kThreads) {
-    const int f = it / 48, j = it - f * 48;
-    const float2* src = a + f * kLP + P(j);   // P(j + 48r) = P(j) + 54r
-    float2* dst = b + f * kLP + 9 * j;         // P(8j + r)  = 9j + r
-    float2 v[8];
-#pragma unroll
-    for (int r = 0; r < 8; ++r) v[r] = src[54 * r];
-    dft8(v);
-#pragma unroll
-    for (int r = 0; r < 8; ++r) dst[r] = v[r];
-  }
-  __syncthreads();
-  // stage 2: R = 8, Ns = 8: twiddle exp(−2πi·k·r/64) = tw[6·k·r]
-  for (int it = tid; it < nfft * 48; it += kThreads) {
-    const int f = it / 48, j = it - f * 48;
-    const int k = j & 7;
-    const float2* src = b + f * kLP + P(j);
-    float2* dst = a + f * kLP + 72 * (j >> 3) + k;  // P(64·(j>>3) + k + 8r) = 72·(j>>3) + k + 9r
-    float2 v[8];
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      v[r] = src[54 * r];
-      if (r) v[r] = cmul(v[r], twid(tw, 6 * k * r));
-    }
-    dft8(v);
-#pragma unroll
-    for (int r = 0; r < 8; ++r) dst[9 * r] = v[r];
-  }
-  __syncthreads();
-  // stage 3: R = 6, Ns = 64: twiddle exp(−2πi·k·r/384) = tw[k·r]
-  for (int it = tid; it < nfft * 64; it += kThreads) {
-    const int f = it >> 6, j = it & 63;
-    const float2* src = a + f * kLP + P(j);   // P(j + 64r) = P(j) + 72r
-    float2* dst = b + f * kLP + P(j);
-    float2 v[6];
-#pragma unroll
-    for (int r = 0; r < 6; ++r) {
-      v[r] = src[72 * r];
-      if (r) v[r] = cmul(v[r], twid(tw, j * r));
-    }
-    dft6(v);
-#pragma unroll
-    for (int r = 0; r < 6; ++r) dst[72 * r] = v[r];
-  }
-  __syncthreads();
-}
-
-// The same transform IN PLACE (one buffer): a stage first pulls all of a thread's butterfly inputs into registers, the
-// CTA synchronises, then the outputs go back into the same buffer (the last stage reads and writes the same words, so
-// it needs no extra barrier).  Half the shared memory of the ping-pong version — what decides how many 16-sequence CTAs
-// (the adjoint kernels) fit on an SM — for two more barriers and 48 live registers.
-template <int NFFT>
-__device__ void fft384_inplace(float2* a, const float2* tw) {
-  constexpr int N12 = NFFT * 48, I12 = (N12 + kThreads - 1) / kThreads;
-  constexpr int N3 = NFFT * 64, I3 = (N3 + kThreads - 1) / kThreads;
-  const int tid = threadIdx.x;
-  {  // stage 1: R = 8, Ns = 1: out[8j + r] = DFT8(in[j + 48r])
-    float2 v[I12][8];
-#pragma unroll
-    for (int q = 0; q < I12; ++q) {
-      const int it = tid + q * kThreads;
-      if (it < N12) {
-        const int f = it / 48, j = it - f * 48;
-        const float2* src = a + f * kLP + P(j);
-#pragma unroll
-        for (int r = 0; r < 8; ++r) v[q][r] = src[54 * r];
-      }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int q = 0; q < I12; ++q) {
-      const int it = tid + q * kThreads;
-      if (it < N12) {
-        const int f = it / 48, j = it - f * 48;
-        dft8(v[q]);
-        float2* dst = a + f * kLP + 9 * j;
-#pragma unroll
-        for (int r = 0; r < 8; ++r) dst[r] = v[q][r];
-      }
-    }
-    __syncthreads();
-  }
-  {  // stage 2: R = 8, Ns = 8
-    float2 v[I12][8];
-#pragma unroll
-    for (int q = 0; q < I12; ++q) {
-      const int it = tid + q * kThreads;
-      if (it < N12) {
-        const int f = it / 48, j = it - f * 48;
-        const int k = j & 7;
-        const float2* src = a + f * kLP + P(j);
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-          v[q][r] = src[54 * r];
-          if (r) v[q][r] = cmul(v[q][r], twid(tw, 6 * k * r));
-        }
-      }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int q = 0; q < I12; ++q) {
-      const int it = tid + q * kThreads;
-      if (it < N12) {
-        const int f = it / 48, j = it - f * 48;
-        dft8(v[q]);
-        float2* dst = a + f * kLP + 72 * (j >> 3) + (j & 7);
-#pragma unroll
-        for (int r = 0; r < 8; ++r) dst[9 * r] = v[q][r];
-      }
-    }
-    __syncthreads();
-  }
-  // stage 3: R = 6, Ns = 64: a butterfly reads and writes the same six words
-#pragma unroll
-  for (int q = 0; q < I3; ++q) {
-    const int it = tid + q * kThreads;
-    if (it < N3) {
-      const int f = it >> 6, j = it & 63;
-      float2* p = a + f * kLP + P(j);
-      float2 v[6];
-#pragma unroll
-      for (int r = 0; r < 6; ++r) {
-        v[r] = p[72 * r];
-        if (r) v[r] = cmul(v[r], twid(tw, j * r));
-      }
-      dft6(v);
-#pragma unroll
-      for (int r = 0; r < 6; ++r) p[72 * r] = v[r];
-    }
-  }
-  __syncthreads();
-}
-
-struct PhaseSmem {
-  float2* a;
-  float2* b;
-  float2* tw;
-  float* red;
-};
-DPS_DEV PhaseSmem carve(float* smem, int nfft) {
-  PhaseSmem s;
-  s.a = reinterpret_cast<float2*>(smem);
-  s.b = s.a + nfft * kLP;
-  s.tw = s.b + nfft * kLP;
-  s.red = reinterpret_cast<float*>(s.tw + kTW);
-  return s;
-}
-DPS_DEV PhaseSmem carve1(float* smem, int nfft) {  // one sequence buffer (in-place FFT)
-  PhaseSmem s;
-  s.a = reinterpret_cast<float2*>(smem);
-  s.b = s.a;
-  s.tw = s.a + nfft * kLP;
-  s.red = reinterpret_cast<float*>(s.tw + kTW);
-  return s;
-}
-size_t smem_bytes1(int nfft) { return sizeof(float2) * ((size_t)nfft * kLP + kTW) + 64 * sizeof(float); }
-size_t smem_bytes(int nfft) { return sizeof(float2) * ((size_t)2 * nfft * kLP + kTW) + 64 * sizeof(float); }
-
-// aux layout per particle (floats): [phase: C·193·384·2][scratch: C·193·256·2]
-DPS_DEV float2* aux_phase(float* aux, int n, int C, int c) {
-  return reinterpret_cast<float2*>(aux + (int64_t)n * C * kHalf * (kL + kImg) * 2) + (int64_t)c * kHalf * kL;
-}
-DPS_DEV float2* aux_scratch(float* aux, int n, int C, int c) {
-  return reinterpret_cast<float2*>(aux + (int64_t)n * C * kHalf * (kL + kImg) * 2) + (int64_t)C * kHalf * kL +
-         (int64_t)c * kHalf * kImg;
-}
-// Fused guidance path: the unit phase never leaves the column kernel, so its region of the workspace holds the second
-// scratch T[row][k2] (C·256·193 complex ≤ C·193·384) and, behind it, the clamp-mask bytes (C·256·256 bytes).
-DPS_DEV float2* aux_scratch2(float* aux, int n, int C, int c) {
-  return reinterpret_cast<float2*>(aux + (int64_t)n * C * kHalf * (kL + kImg) * 2) + (int64_t)c * kHalf * kImg;
-}
-DPS_DEV unsigned char* aux_mask(float* aux, int n, int C, int c) {
-  return reinterpret_cast<unsigned char*>(reinterpret_cast<float2*>(aux + (int64_t)n * C * kHalf * (kL + kImg) * 2) +
-                                          (int64_t)C * kHalf * kImg) + (int64_t)c * kImg * kImg;
+// in-register DFT-4 (forward sign)
+DPS_DEV void dft4(float2* v) {
+  const float2 a0 = cadd(v[0], v[2]), a1 = csub(v[0], v[2]);
+  const float2 a2 = cadd(v[1], v[3]), a3 = mul_mi(csub(v[1], v[3]));
+  v[0] = cadd(a0, a2); v[2] = csub(a0, a2);
+  v[1] = cadd(a1, a3); v[3] = csub(a1, a3);
 }
 
 // clamp-mask bytes of the fused guidance path (1 = gradient passes): written by the row kernel, read by the last kernel,
@@ -327,448 +127,6 @@ DPS_DEV unsigned pack_pass4(const float* x, const float* eps, int64_t i, float c
 }
 
 // ---- K1: row transforms of the 256 image rows, two real rows per complex FFT ---------------------
-template <bool kMaskOut>
-__global__ void __launch_bounds__(kThreads, 4) phase_rows_fwd(const FwdArgs fa, const float2* __restrict__ tw_g, int C) {
-  extern __shared__ __align__(16) float smem[];
-  constexpr int nfft = kRowsPerCta / 2;
-  PhaseSmem s = carve(smem, nfft);
-  const int tid = threadIdx.x;
-  const int groups = kImg / kRowsPerCta;
-  const int grp = blockIdx.x % groups, c = blockIdx.x / groups, n = blockIdx.y;
-  const int r0 = grp * kRowsPerCta;
-  stage_async(reinterpret_cast<float*>(s.tw), reinterpret_cast<const float*>(tw_g), 2 * kTW, tid, kThreads);
-  // zero the padding columns [0,64) and [320,384) of every sequence
-  for (int i = tid; i < nfft * 2 * kPad; i += kThreads) {
-    const int f = i / (2 * kPad), q = i - f * (2 * kPad);
-    s.a[f * kLP + P(q < kPad ? q : kImg + q)] = make_float2(0.f, 0.f);
-  }
-  const int64_t plane = (int64_t)c * kImg * kImg;
-  const float* x = fa.src.x + n * fa.src.x_stride + plane;
-  const float* eps = fa.src.eps ? fa.src.eps + n * fa.src.eps_stride + plane : nullptr;
-  struct RowPair { float4 re, im; };
-  unsigned* maskw = kMaskOut ? reinterpret_cast<unsigned*>(aux_mask(fa.aux, n, C, c)) : nullptr;
-  batched_copy<nfft * (kImg / 4), 2>(
-      tid,
-      [&](int i) {
-        const int f = i / (kImg / 4), q = i - f * (kImg / 4);
-        RowPair v;
-        v.re = src_load4(x, eps, (int64_t)(r0 + 2 * f) * kImg + q * 4, fa.src.c1, fa.src.c2, fa.src.clip);
-        v.im = src_load4(x, eps, (int64_t)(r0 + 2 * f + 1) * kImg + q * 4, fa.src.c1, fa.src.c2, fa.src.clip);
-        if constexpr (kMaskOut) {  // the same loads again hit L1/L2; the mask is the clamp-backward pass bit of each element
-          maskw[((r0 + 2 * f) * kImg + q * 4) >> 2] = pack_pass4(x, eps, (int64_t)(r0 + 2 * f) * kImg + q * 4, fa.src.c1, fa.src.c2, fa.src.clip);
-          maskw[((r0 + 2 * f + 1) * kImg + q * 4) >> 2] = pack_pass4(x, eps, (int64_t)(r0 + 2 * f + 1) * kImg + q * 4, fa.src.c1, fa.src.c2, fa.src.clip);
-        }
-        return v;
-      },
-      [&](int i, const RowPair& v) {
-        const int f = i / (kImg / 4), q = i - f * (kImg / 4);
-        float2* d = s.a + f * kLP;
-        const int i0 = kPad + q * 4;
-        d[P(i0)] = make_float2(v.re.x, v.im.x); d[P(i0 + 1)] = make_float2(v.re.y, v.im.y);
-        d[P(i0 + 2)] = make_float2(v.re.z, v.im.z); d[P(i0 + 3)] = make_float2(v.re.w, v.im.w);
-      });
-  stage_wait();
-  __syncthreads();
-  fft384_batch(s.a, s.b, s.tw, nfft);
-  // split Z = A + iB (A, B spectra of the even / odd row) and store Rt[k2][row] for k2 ∈ [0,192]
-  float2* rt = aux_scratch(fa.aux, n, C, c);
-  for (int i = tid; i < kHalf * nfft; i += kThreads) {
-    const int k = i / nfft, f = i - k * nfft;
-    const float2 z = s.b[f * kLP + P(k)];
-    const float2 zc = cconj(s.b[f * kLP + P(k ? kL - k : 0)]);
-    const float2 A = make_float2(0.5f * (z.x + zc.x), 0.5f * (z.y + zc.y));
-    const float2 d = make_float2(0.5f * (z.x - zc.x), 0.5f * (z.y - zc.y));
-    const float2 B = make_float2(d.y, -d.x);  // d / i
-    *reinterpret_cast<float4*>(rt + (int64_t)k * kImg + r0 + 2 * f) = make_float4(A.x, A.y, B.x, B.y);
-  }
-}
-
-DPS_DEV int shift_idx(int k) { return k + kL / 2 >= kL ? k - kL / 2 : k + kL / 2; }  // fftshift position of bin k
-
-// ---- K2: column transforms, magnitude, residual, partial sums, unit phase -----------------------
-// kLean (opt-in, DPSTTC_PHASE_LEAN=1, not launched by default): the output epilogue with its addressing hoisted.  Under the
-// 64-register cap of 4 CTAs/SM the compiler rematerialises, for EVERY one of a thread's 24 stores, the 64-bit product
-// (n·C + c)·384² + o, the `fa.out` / `y` null tests and a BSSY/BSYNC pair (≈20 instructions per output, 36 % of the kernel's
-// instructions in the ncu source page).  Here the plane pointers are formed once, the null tests become two CTA-uniform flags and
-// each output is: LDS, FSUB, STG [base + 4·o], FFMA, FADD.  Same values in the same order
-// (gate: tools/variant_check.py --op phase --n 4 --env DPSTTC_PHASE_LEAN=0 --env DPSTTC_PHASE_LEAN=1).
-template <bool kLean>
-__global__ void __launch_bounds__(kThreads, 4) phase_cols_fwd(const FwdArgs fa, const float2* __restrict__ tw_g, int C) {
-  extern __shared__ __align__(16) float smem[];
-  constexpr int nfft = kColsPerCta;
-  PhaseSmem s = carve(smem, nfft);
-  const int tid = threadIdx.x;
-  const int grp = blockIdx.x % kColGroups, c = blockIdx.x / kColGroups, n = blockIdx.y;
-  const int k20 = grp * kColsPerCta;
-  const int ncols = min(kColsPerCta, kHalf - k20);
-  stage_async(reinterpret_cast<float*>(s.tw), reinterpret_cast<const float*>(tw_g), 2 * kTW, tid, kThreads);
-  for (int i = tid; i < nfft * 2 * kPad; i += kThreads) {
-    const int f = i / (2 * kPad), q = i - f * (2 * kPad);
-    s.a[f * kLP + P(q < kPad ? q : kImg + q)] = make_float2(0.f, 0.f);
-  }
-  const float2* rt = aux_scratch(fa.aux, n, C, c);
-  batched_copy<nfft * (kImg / 2), 4>(
-      tid,
-      [&](int i) {
-        const int f = i / (kImg / 2), q = i - f * (kImg / 2);
-        return f < ncols ? *reinterpret_cast<const float4*>(rt + (int64_t)(k20 + f) * kImg + q * 2)
-                         : make_float4(0.f, 0.f, 0.f, 0.f);
-      },
-      [&](int i, const float4& v) {
-        const int f = i / (kImg / 2), q = i - f * (kImg / 2);
-        float2* d = s.a + f * kLP;
-        d[P(kPad + q * 2)] = make_float2(v.x, v.y);
-        d[P(kPad + q * 2 + 1)] = make_float2(v.z, v.w);
-      });
-  stage_wait();
-  __syncthreads();
-  fft384_batch(s.a, s.b, s.tw, nfft);
-  // unit phase conj(F)/|F| → aux[k2][k1] (contiguous in k1), magnitude → s.a reused as float storage
-  float2* ph = aux_phase(fa.aux, n, C, c);
-  float* amp = reinterpret_cast<float*>(s.a);  // (nfft, kLF)
-  const float inv_l = 1.0f / (float)kL;
-  {
-    // one spectrum column per warp, bins k1 = lane + 32·j: P(k1) = lane + (lane >> 3) + 36·j, so every address below is a
-    // per-thread base plus a compile-time offset; the unit phase goes out in 256-byte runs.
-    static_assert(kColsPerCta * 32 == kThreads && kL % 32 == 0, "one warp per spectrum column");
-    const int f = tid >> 5, lane = tid & 31;
-    if (f < ncols) {
-      const float2* fb = s.b + f * kLP + lane + (lane >> 3);
-      float2* php = ph + (int64_t)(k20 + f) * kL + lane;
-      float* ampp = amp + f * kLF + lane;
-#pragma unroll
-      for (int j = 0; j < kL / 32; ++j) {
-        const float2 F = fb[36 * j];
-        // |F| and 1/|F| without the slow paths of sqrtf and the division: rsqrt.approx (2 ulp) refined by one Newton
-        // step, then |F| = m·r corrected by its residual — both within 1 ulp of the correctly rounded values.
-        const float m2 = fmaf(F.x, F.x, F.y * F.y);
-        float r = rsqrtf(m2);
-        r = fmaf(r, fmaf(-0.5f * m2 * r, r, 0.5f), r);
-        float mag = m2 * r;
-        mag = fmaf(fmaf(-mag, mag, m2), 0.5f * r, mag);
-        const bool nz = m2 > 0.f;
-        const float inv = nz ? r : 0.f;
-        php[32 * j] = make_float2(F.x * inv, -F.y * inv);
-        ampp[32 * j] = nz ? mag * inv_l : 0.f;
-      }
-    }
-  }
-  __syncthreads();
-  // outputs: direct position (u, v) = shift(k1, k2) and, for 0 < k2 < 192, the mirror shift(−k1, −k2)
-  float sq = 0.f, ab = 0.f;
-  const int64_t oplane = ((int64_t)n * C + c) * kL * kL;
-  const float* y = fa.y ? fa.y + n * fa.y_stride + (int64_t)c * kL * kL : nullptr;
-  // A thread keeps ONE spectrum column f (so the column part of both output positions is loop-invariant) and walks
-  // k1 = kk, kk + 32, …: after unrolling every row index is kk plus a constant.  The measurement values of a batch of
-  // kYB output pairs are fetched before any is used (one round trip per batch, not per value).
-  static_assert(kColsPerCta == 8 && kThreads == 256 && kL % 32 == 0, "epilogue mapping");
-  constexpr int kIters = kL / 32, kYB = 4;
-  static_assert(kIters % kYB == 0, "batches");
-  {
-    const int f = tid & 7, kk = tid >> 3;
-    const int k2 = k20 + f;
-    const bool act = f < ncols, mir = act && k2 > 0 && k2 < kL / 2;
-    const int c1 = shift_idx(k2), c2 = mir ? shift_idx(kL - k2) : 0;
-    const float* ampf = amp + f * kLF;
-#pragma unroll
-    for (int it0 = 0; it0 < kIters; it0 += kYB) {
-      float y1[kYB], y2[kYB];
-      int o1[kYB], o2[kYB];
-#pragma unroll
-      for (int b = 0; b < kYB; ++b) {
-        const int k1 = kk + 32 * (it0 + b);
-        o1[b] = shift_idx(k1) * kL + c1;
-        o2[b] = shift_idx(k1 ? kL - k1 : 0) * kL + c2;
-        y1[b] = (y && act) ? ldg_ro(y + o1[b]) : 0.f;
-        y2[b] = (y && mir) ? ldg_ro(y + o2[b]) : 0.f;
-      }
-      if constexpr (kLean) {
-        float* const outp = fa.out ? fa.out + oplane : nullptr;
-        const bool st1 = act && outp != nullptr, st2 = mir && outp != nullptr, has_y = y != nullptr;
-#pragma unroll
-        for (int b = 0; b < kYB; ++b) {
-          const float a = ampf[kk + 32 * (it0 + b)];
-          const float r1 = has_y ? __fsub_rn(y1[b], a) : a;
-          const float r2 = has_y ? __fsub_rn(y2[b], a) : a;
-          if (st1) stg_stream(outp + o1[b], r1);
-          if (act) { sq += r1 * r1; ab += fabsf(r1); }
-          if (st2) stg_stream(outp + o2[b], r2);
-          if (mir) { sq += r2 * r2; ab += fabsf(r2); }
-        }
-        continue;
-      }
-#pragma unroll
-      for (int b = 0; b < kYB; ++b) {
-        const float a = ampf[kk + 32 * (it0 + b)];
-        if (act) {
-          const float res = y ? __fsub_rn(y1[b], a) : a;
-          if (fa.out) stg_stream(fa.out + oplane + o1[b], res);
-          sq += res * res;
-          ab += fabsf(res);
-        }
-        if (mir) {
-          const float res = y ? __fsub_rn(y2[b], a) : a;
-          if (fa.out) stg_stream(fa.out + oplane + o2[b], res);
-          sq += res * res;
-          ab += fabsf(res);
-        }
-      }
-    }
-  }
-  if (fa.partials) {
-    block_sum2(sq, ab, s.red);
-    if (tid == 0) {
-      float* pp = fa.partials + ((int64_t)n * (C * kColGroups) + blockIdx.x) * 2;
-      pp[0] = sq;
-      pp[1] = ab;
-    }
-  }
-}
-
-// ---- K2': the column kernel of the fused guidance path -------------------------------------------------------------------
-// Everything between the two column transforms is local to a spectrum column, and with the guidance coefficient deferred
-// to the update kernel nothing global (‖r‖) is needed in between.  So one CTA does, for its 8 columns: column FFT, |F|,
-// residual r = y − |F|/L at both Hermitian-mirrored output positions (Σr², Σ|r| → partial sums; r itself only if asked
-// for), the symmetrised cotangent ½(r(k) + r(−k))·conj(F)/|F| in place, and the second column transform whose rows
-// 64..319 go to the scratch T[row][k2].  The residual (2.25T), the unit phase (2.26T) and one launch of the two-kernel
-// path never touch HBM.
-__global__ void __launch_bounds__(kThreads, 4) phase_cols_fused(const FwdArgs fa, const float2* __restrict__ tw_g, int C) {
-  extern __shared__ __align__(16) float smem[];
-  constexpr int nfft = kColsPerCta;
-  PhaseSmem s = carve(smem, nfft);
-  const int tid = threadIdx.x;
-  const int grp = blockIdx.x % kColGroups, c = blockIdx.x / kColGroups, n = blockIdx.y;
-  const int k20 = grp * kColsPerCta;
-  const int ncols = min(kColsPerCta, kHalf - k20);
-  stage_async(reinterpret_cast<float*>(s.tw), reinterpret_cast<const float*>(tw_g), 2 * kTW, tid, kThreads);
-  for (int i = tid; i < nfft * 2 * kPad; i += kThreads) {
-    const int f = i / (2 * kPad), q = i - f * (2 * kPad);
-    s.a[f * kLP + P(q < kPad ? q : kImg + q)] = make_float2(0.f, 0.f);
-  }
-  const float2* rt = aux_scratch(fa.aux, n, C, c);
-  batched_copy<nfft * (kImg / 2), 4>(
-      tid,
-      [&](int i) {
-        const int f = i / (kImg / 2), q = i - f * (kImg / 2);
-        return f < ncols ? *reinterpret_cast<const float4*>(rt + (int64_t)(k20 + f) * kImg + q * 2)
-                         : make_float4(0.f, 0.f, 0.f, 0.f);
-      },
-      [&](int i, const float4& v) {
-        const int f = i / (kImg / 2), q = i - f * (kImg / 2);
-        float2* d = s.a + f * kLP;
-        d[P(kPad + q * 2)] = make_float2(v.x, v.y);
-        d[P(kPad + q * 2 + 1)] = make_float2(v.z, v.w);
-      });
-  stage_wait();
-  __syncthreads();
-  fft384_batch(s.a, s.b, s.tw, nfft);
-  // pass 1 (one column per warp, conflict-free): |F|/L → amp (float plane in s.a), unit phase conj(F)/|F| in place in s.b
-  float* amp = reinterpret_cast<float*>(s.a);  // (nfft, kLF)
-  const float inv_l = 1.0f / (float)kL;
-  {
-    static_assert(kColsPerCta * 32 == kThreads && kL % 32 == 0, "one warp per spectrum column");
-    const int f = tid >> 5, lane = tid & 31;
-    float2* fb = s.b + f * kLP + lane + (lane >> 3);
-    float* ampp = amp + f * kLF + lane;
-#pragma unroll
-    for (int j = 0; j < kL / 32; ++j) {
-      const float2 F = fb[36 * j];
-      const float m2 = fmaf(F.x, F.x, F.y * F.y);
-      float r = rsqrtf(m2);
-      r = fmaf(r, fmaf(-0.5f * m2 * r, r, 0.5f), r);
-      float mag = m2 * r;
-      mag = fmaf(fmaf(-mag, mag, m2), 0.5f * r, mag);
-      const bool nz = m2 > 0.f;
-      const float inv = nz ? r : 0.f;
-      fb[36 * j] = make_float2(F.x * inv, -F.y * inv);
-      ampp[32 * j] = nz ? mag * inv_l : 0.f;
-    }
-  }
-  __syncthreads();
-  // pass 2 (8 consecutive threads = 8 consecutive spectrum columns: 32-byte runs of y): residual at both mirrored output
-  // positions, partial sums, symmetrised cotangent × unit phase written back in place
-  float sq = 0.f, ab = 0.f;
-  {
-    static_assert(kColsPerCta == 8 && kThreads == 256 && kL % 32 == 0, "epilogue mapping");
-    constexpr int kIters = kL / 32, kYB = 4;
-    const int f = tid & 7, kk = tid >> 3;
-    const int k2 = k20 + f;
-    const bool act = f < ncols, mir = act && k2 > 0 && k2 < kL / 2;
-    const int c1 = shift_idx(k2), c2 = shift_idx(k2 ? kL - k2 : 0);
-    const float* y = fa.y ? fa.y + n * fa.y_stride + (int64_t)c * kL * kL : nullptr;
-    float* const outp = fa.out ? fa.out + ((int64_t)n * C + c) * kL * kL : nullptr;
-    const float* ampf = amp + f * kLF;
-    float2* ub = s.b + f * kLP;
-#pragma unroll
-    for (int it0 = 0; it0 < kIters; it0 += kYB) {
-      float y1[kYB], y2[kYB];
-      int o1[kYB], o2[kYB];
-#pragma unroll
-      for (int b = 0; b < kYB; ++b) {
-        const int k1 = kk + 32 * (it0 + b);
-        o1[b] = shift_idx(k1) * kL + c1;
-        o2[b] = shift_idx(k1 ? kL - k1 : 0) * kL + c2;
-        y1[b] = (y && act) ? ldg_ro(y + o1[b]) : 0.f;
-        y2[b] = (y && act) ? ldg_ro(y + o2[b]) : 0.f;
-      }
-#pragma unroll
-      for (int b = 0; b < kYB; ++b) {
-        const int k1 = kk + 32 * (it0 + b);
-        const float a = ampf[k1];
-        const float r1 = y ? __fsub_rn(y1[b], a) : a;
-        const float r2 = y ? __fsub_rn(y2[b], a) : a;
-        if (act) {
-          sq = fmaf(r1, r1, sq);
-          ab += fabsf(r1);
-          if (outp) stg_stream(outp + o1[b], r1);
-        }
-        if (mir) {  // for the self-conjugate columns k2 = 0, 192 the mirrored output is another element of the same column
-          sq = fmaf(r2, r2, sq);
-          ab += fabsf(r2);
-          if (outp) stg_stream(outp + o2[b], r2);
-        }
-        const float gs = act ? 0.5f * (r1 + r2) : 0.f;
-        float2* w = ub + P(k1);
-        const float2 u = *w;
-        *w = make_float2(gs * u.x, gs * u.y);
-      }
-    }
-  }
-  if (fa.partials) {
-    block_sum2(sq, ab, s.red);  // (contains the barriers that also order pass 2 against the transform below)
-    if (tid == 0) {
-      float* pp = fa.partials + ((int64_t)n * (C * kColGroups) + blockIdx.x) * 2;
-      pp[0] = sq;
-      pp[1] = ab;
-    }
-  }
-  __syncthreads();
-  fft384_batch(s.b, s.a, s.tw, nfft);  // second column transform: result in s.a
-  float2* t = aux_scratch2(fa.aux, n, C, c);
-#pragma unroll 4
-  for (int i = tid; i < kImg * kColsPerCta; i += kThreads) {
-    const int row = i / kColsPerCta, f = i - row * kColsPerCta;
-    if (f < ncols) t[(int64_t)row * kHalf + k20 + f] = s.a[f * kLP + P(kPad + row)];
-  }
-}
-
-// ---- A1: H_s[k1][k2] = ½(g[k]+g[−k])·conj(F)/|F|, column transform, keep rows 64..319 ------------
-__global__ void __launch_bounds__(kThreads, 3) phase_cols_adj(const AdjArgs aa, float* __restrict__ aux_rw,
-                                                              const float2* __restrict__ tw_g, int C) {
-  extern __shared__ __align__(16) float smem[];
-  constexpr int nfft = kColsAdj;
-  PhaseSmem s = carve1(smem, nfft);
-  const int tid = threadIdx.x;
-  const int grp = blockIdx.x % kColGroupsAdj, c = blockIdx.x / kColGroupsAdj, n = blockIdx.y;
-  const int k20 = grp * kColsAdj;
-  const int ncols = min(kColsAdj, kHalf - k20);
-  stage_async(reinterpret_cast<float*>(s.tw), reinterpret_cast<const float*>(tw_g), 2 * kTW, tid, kThreads);
-  const float* r = aa.r + ((int64_t)n * C + c) * kL * kL;
-  const float2* ph = aux_phase(aux_rw, n, C, c);
-  // symmetrised cotangent (coalesced over the CTA's columns), parked in the real parts of the sequence buffer
-  batched_copy<kL * kColsAdj, 8>(
-      tid,
-      [&](int i) {
-        const int k1 = i / kColsAdj, f = i - k1 * kColsAdj;
-        const int k2 = k20 + f;
-        if (f >= ncols) return make_float2(0.f, 0.f);
-        return make_float2(ldg_stream(r + (int64_t)shift_idx(k1) * kL + shift_idx(k2)),
-                           ldg_stream(r + (int64_t)shift_idx(k1 ? kL - k1 : 0) * kL + shift_idx(k2 ? kL - k2 : 0)));
-      },
-      [&](int i, const float2& g) {
-        const int k1 = i / kColsAdj, f = i - k1 * kColsAdj;
-        s.a[f * kLP + P(k1)].x = 0.5f * (g.x + g.y);
-      });
-  __syncthreads();
-  batched_copy<nfft * kL, 8>(
-      tid,
-      [&](int i) {
-        const int f = i / kL, k1 = i - f * kL;
-        return f < ncols ? ph[(int64_t)(k20 + f) * kL + k1] : make_float2(0.f, 0.f);
-      },
-      [&](int i, const float2& pv) {
-        const int f = i / kL, k1 = i - f * kL;
-        float2* w = s.a + f * kLP + P(k1);  // the thread that multiplies is the only one touching this word
-        const float g = w->x;
-        *w = make_float2(g * pv.x, g * pv.y);
-      });
-  stage_wait();
-  __syncthreads();
-  fft384_inplace<nfft>(s.a, s.tw);
-  // T[row][k2] for padded rows 64..319 → image rows 0..255; row stride 193 complex
-  float2* t = aux_scratch(aux_rw, n, C, c);
-#pragma unroll 4
-  for (int i = tid; i < kImg * kColsAdj; i += kThreads) {
-    const int row = i / kColsAdj, f = i - row * kColsAdj;
-    if (f < ncols) t[(int64_t)row * kHalf + k20 + f] = s.b[f * kLP + P(kPad + row)];
-  }
-}
-
-// ---- A2: Hermitian row back-transform, two real rows per complex FFT, crop + epilogue ------------
-template <bool kFused>
-__global__ void __launch_bounds__(kThreads, 3) phase_rows_adj(const AdjArgs aa, const float* __restrict__ aux_r,
-                                                              const float2* __restrict__ tw_g, int C) {
-  extern __shared__ __align__(16) float smem[];
-  constexpr int nfft = kRowsAdj / 2;
-  PhaseSmem s = carve1(smem, nfft);
-  const int tid = threadIdx.x;
-  const int groups = kImg / kRowsAdj;
-  const int grp = blockIdx.x % groups, c = blockIdx.x / groups, n = blockIdx.y;
-  const int r0 = grp * kRowsAdj;
-  stage_async(reinterpret_cast<float*>(s.tw), reinterpret_cast<const float*>(tw_g), 2 * kTW, tid, kThreads);
-  const float2* t = kFused ? aux_scratch2(const_cast<float*>(aux_r), n, C, c) : aux_scratch(const_cast<float*>(aux_r), n, C, c);
-  const unsigned* maskw = kFused ? reinterpret_cast<const unsigned*>(aux_mask(const_cast<float*>(aux_r), n, C, c)) : nullptr;
-  // X[k] = T1[k] + i·T2[k] with T[384−k] = conj(T[k]) for k > 192
-  batched_copy<nfft * kL, 8>(
-      tid,
-      [&](int i) {
-        const int f = i / kL, k = i - f * kL;
-        const int kk = k < kHalf ? k : kL - k;
-        const float2 t1 = t[(int64_t)(r0 + 2 * f) * kHalf + kk];
-        const float2 t2 = t[(int64_t)(r0 + 2 * f + 1) * kHalf + kk];
-        return make_float4(t1.x, t1.y, t2.x, t2.y);
-      },
-      [&](int i, const float4& v) {
-        const int f = i / kL, k = i - f * kL;
-        const float sg = k >= kHalf ? -1.f : 1.f;  // conj for the mirrored half
-        s.a[f * kLP + P(k)] = make_float2(v.x - sg * v.w, sg * v.y + v.z);
-      });
-  stage_wait();
-  __syncthreads();
-  fft384_inplace<nfft>(s.a, s.tw);
-  const float coef = (aa.coef ? aa.coef[n] : 1.0f) * (1.0f / (float)kL);
-  const int64_t plane = (int64_t)c * kImg * kImg;
-  struct Epi { float4 e, pass; };
-  batched_copy<kRowsAdj * (kImg / 4), 4>(
-      tid,
-      [&](int i) {
-        const int rr = i / (kImg / 4), q = i - rr * (kImg / 4);
-        const int64_t off = plane + (int64_t)(r0 + rr) * kImg + q * 4;
-        Epi v;
-        v.e = aa.extra ? ldg_stream4(aa.extra + n * aa.extra_stride + off) : make_float4(0.f, 0.f, 0.f, 0.f);
-        if constexpr (kFused) {
-          const unsigned m = __ldg(maskw + (((r0 + rr) * kImg + q * 4) >> 2));
-          v.pass = make_float4((m & 0xffu) ? 1.f : 0.f, (m & 0xff00u) ? 1.f : 0.f, (m & 0xff0000u) ? 1.f : 0.f, (m & 0xff000000u) ? 1.f : 0.f);
-        } else {
-          v.pass = mask_load4(aa.mask_src, aa.has_mask, n, off);
-        }
-        return v;
-      },
-      [&](int i, const Epi& v) {
-        const int rr = i / (kImg / 4), q = i - rr * (kImg / 4);
-        const int f = rr >> 1, odd = rr & 1;
-        const float2* zb = s.b + f * kLP;
-        const int i0 = kPad + q * 4;
-        const float2 z0 = zb[P(i0)], z1 = zb[P(i0 + 1)], z2 = zb[P(i0 + 2)], z3 = zb[P(i0 + 3)];
-        float4 res;
-        res.x = (coef * (odd ? z0.y : z0.x) + v.e.x) * v.pass.x;
-        res.y = (coef * (odd ? z1.y : z1.x) + v.e.y) * v.pass.y;
-        res.z = (coef * (odd ? z2.y : z2.x) + v.e.z) * v.pass.z;
-        res.w = (coef * (odd ? z3.y : z3.x) + v.e.w) * v.pass.w;
-        stg_stream4(aa.g + n * aa.g_stride + plane + (int64_t)(r0 + rr) * kImg + q * 4, res);
-      });
-}
-
 int set_smem(const void* fn, size_t bytes) {
   DPS_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
   return DPS_OK;
@@ -776,34 +134,38 @@ int set_smem(const void* fn, size_t bytes) {
 
 }  // namespace
 
+#define PHASE_R3 6
+namespace ph384 {
+#include "phase_impl.cuh"
+}
+#undef PHASE_R3
+#define PHASE_R3 4
+namespace ph256 {
+#include "phase_impl.cuh"
+}
+#undef PHASE_R3
+#define PHASE_R3 3
+namespace ph192 {
+#include "phase_impl.cuh"
+}
+#undef PHASE_R3
+
+// The reference pads by int((oversample / 8)·256) = 64 whatever the image size (measurements.py:181-183): 256² → 384²
+// (the shipped configs), 128² → 256², 64² → 192² (the size of the reference-made fixtures).
+#define DPS_PHASE_DISPATCH(op, call)                                                              \
+  switch ((op)->H) {                                                                              \
+    case 256: return ph384::call;                                                                 \
+    case 128: return ph256::call;                                                                 \
+    case 64: return ph192::call;                                                                  \
+  }                                                                                               \
+  dps_set_error("phase retrieval: no kernels for %dx%d images", (op)->H, (op)->W);               \
+  return DPS_ERR_UNSUPPORTED;
+
 int phase_create(dps_operator* op, int pad) {
-  DPS_REQUIRE(op->H == kImg && op->W == kImg && pad == kPad, DPS_ERR_UNSUPPORTED,
-              "phase retrieval: kernels are built for 256x256 images padded to 384x384 (got %dx%d, pad %d)", op->H,
+  DPS_REQUIRE(op->H == op->W && (op->H == 256 || op->H == 128 || op->H == 64) && pad == 64, DPS_ERR_UNSUPPORTED,
+              "phase retrieval: kernels are built for 256x256, 128x128 and 64x64 images padded by 64 (got %dx%d, pad %d)", op->H,
               op->W, pad);
-  PhaseTables* t = new PhaseTables();
-  op->phase = t;
-  std::vector<float2> tw(kL);
-  for (int j = 0; j < kL; ++j) {
-    const double a = -2.0 * M_PI * j / kL;
-    tw[j] = make_float2((float)cos(a), (float)sin(a));
-  }
-  DPS_CUDA(cudaMalloc(&t->tw, sizeof(float2) * kL));
-  DPS_CUDA(cudaMemcpy(t->tw, tw.data(), sizeof(float2) * kL, cudaMemcpyHostToDevice));
-  if (int rc = set_smem((const void*)phase_rows_fwd<false>, smem_bytes(kRowsPerCta / 2))) return rc;
-  if (int rc = set_smem((const void*)phase_rows_fwd<true>, smem_bytes(kRowsPerCta / 2))) return rc;
-  if (int rc = set_smem((const void*)phase_cols_fused, smem_bytes(kColsPerCta))) return rc;
-  if (int rc = set_smem((const void*)phase_cols_fwd<false>, smem_bytes(kColsPerCta))) return rc;
-  if (int rc = set_smem((const void*)phase_cols_fwd<true>, smem_bytes(kColsPerCta))) return rc;
-  if (int rc = set_smem((const void*)phase_cols_adj, smem_bytes1(kColsAdj))) return rc;
-  if (int rc = set_smem((const void*)phase_rows_adj<false>, smem_bytes1(kRowsAdj / 2))) return rc;
-  if (int rc = set_smem((const void*)phase_rows_adj<true>, smem_bytes1(kRowsAdj / 2))) return rc;
-  op->oC = op->C;
-  op->oH = op->oW = kL;
-  op->P = op->C * kColGroups;
-  op->aux_floats = (int64_t)op->C * kHalf * (kL + kImg) * 2;
-  op->taps = kL;
-  op->guidance_P = op->C * kColGroups;  // dps_operator_guidance: the three-kernel fused path below
-  return DPS_OK;
+  DPS_PHASE_DISPATCH(op, create(op))
 }
 
 void phase_destroy(dps_operator* op) {
@@ -813,68 +175,11 @@ void phase_destroy(dps_operator* op) {
   op->phase = nullptr;
 }
 
-int phase_forward(const dps_operator* op, const FwdArgs& a, cudaStream_t st) {
-  DPS_REQUIRE(a.aux, DPS_ERR_INVALID, "phase retrieval forward needs the aux workspace (%lld floats per particle)",
-              (long long)op->aux_floats);
-  dim3 g1((unsigned)(op->C * (kImg / kRowsPerCta)), (unsigned)a.n);
-  phase_rows_fwd<false><<<g1, kThreads, smem_bytes(kRowsPerCta / 2), st>>>(a, op->phase->tw, op->C);
-  DPS_LAUNCH_CHECK("phase_rows_fwd");
-  dim3 g2((unsigned)(op->C * kColGroups), (unsigned)a.n);
-  // lean output epilogue: default since round 2 (bit-identical gate passed, 95.3 → 92.6 µs at N = 32); =0: round-1 epilogue
-  static const bool lean = !(getenv("DPSTTC_PHASE_LEAN") && getenv("DPSTTC_PHASE_LEAN")[0] == '0');
-  if (lean)
-    phase_cols_fwd<true><<<g2, kThreads, smem_bytes(kColsPerCta), st>>>(a, op->phase->tw, op->C);
-  else
-    phase_cols_fwd<false><<<g2, kThreads, smem_bytes(kColsPerCta), st>>>(a, op->phase->tw, op->C);
-  DPS_LAUNCH_CHECK("phase_cols_fwd");
-  return DPS_OK;
-}
+int phase_forward(const dps_operator* op, const FwdArgs& a, cudaStream_t st) { DPS_PHASE_DISPATCH(op, forward(op, a, st)) }
 
-int phase_adjoint(const dps_operator* op, const AdjArgs& a, cudaStream_t st) {
-  DPS_REQUIRE(a.aux && a.r, DPS_ERR_INVALID, "phase retrieval adjoint needs r and the aux workspace of the forward pass");
-  float* aux = const_cast<float*>(a.aux);
-  dim3 g1((unsigned)(op->C * kColGroupsAdj), (unsigned)a.n);
-  phase_cols_adj<<<g1, kThreads, smem_bytes1(kColsAdj), st>>>(a, aux, op->phase->tw, op->C);
-  DPS_LAUNCH_CHECK("phase_cols_adj");
-  dim3 g2((unsigned)(op->C * (kImg / kRowsAdj)), (unsigned)a.n);
-  phase_rows_adj<false><<<g2, kThreads, smem_bytes1(kRowsAdj / 2), st>>>(a, aux, op->phase->tw, op->C);
-  DPS_LAUNCH_CHECK("phase_rows_adj");
-  return DPS_OK;
-}
+int phase_adjoint(const dps_operator* op, const AdjArgs& a, cudaStream_t st) { DPS_PHASE_DISPATCH(op, adjoint(op, a, st)) }
 
-// Fused guidance: residual (kept on chip unless r_out), partial sums and the UNSCALED masked cotangent g = mask ⊙ Jᵀ r in
-// three kernels — rows (+ clamp-mask bytes), columns (both transforms, see phase_cols_fused), rows back.
 int phase_guidance(const dps_operator* op, const dps_source& src, const float* y, int64_t y_stride, float* r_out, float* g,
                    int64_t g_stride, float* partials, float* aux, int n, cudaStream_t st) {
-  DPS_REQUIRE(aux && y, DPS_ERR_INVALID, "phase retrieval guidance needs the measurement and the aux workspace (%lld floats per particle)",
-              (long long)op->aux_floats);
-  FwdArgs fa;
-  fa.src = src;
-  fa.y = y;
-  fa.y_stride = y_stride;
-  fa.out = r_out;
-  fa.partials = partials;
-  fa.aux = aux;
-  fa.n = n;
-  dim3 g1((unsigned)(op->C * (kImg / kRowsPerCta)), (unsigned)n);
-  phase_rows_fwd<true><<<g1, kThreads, smem_bytes(kRowsPerCta / 2), st>>>(fa, op->phase->tw, op->C);
-  DPS_LAUNCH_CHECK("phase_rows_fwd");
-  dim3 g2((unsigned)(op->C * kColGroups), (unsigned)n);
-  phase_cols_fused<<<g2, kThreads, smem_bytes(kColsPerCta), st>>>(fa, op->phase->tw, op->C);
-  DPS_LAUNCH_CHECK("phase_cols_fused");
-  AdjArgs aa;
-  aa.r = nullptr;
-  aa.coef = nullptr;
-  aa.mask_src = dps_source{};
-  aa.has_mask = 0;
-  aa.extra = nullptr;
-  aa.extra_stride = 0;
-  aa.g = g;
-  aa.g_stride = g_stride;
-  aa.aux = aux;
-  aa.n = n;
-  dim3 g3((unsigned)(op->C * (kImg / kRowsAdj)), (unsigned)n);
-  phase_rows_adj<true><<<g3, kThreads, smem_bytes1(kRowsAdj / 2), st>>>(aa, aux, op->phase->tw, op->C);
-  DPS_LAUNCH_CHECK("phase_rows_adj");
-  return DPS_OK;
+  DPS_PHASE_DISPATCH(op, guidance(op, src, y, y_stride, r_out, g, g_stride, partials, aux, n, st))
 }

@@ -189,7 +189,9 @@ int dps_operator_create_resize(const int32_t* fov_h, const float* w_h, int taps_
                                const int32_t* fov_w, const float* w_w, int taps_w, int out_w,
                                int C, int H, int W, dps_operator** out);
 /* PhaseRetrievalOperator (measurements.py:179-189): zero-pad `pad` each side, centred ortho 2-D
- * FFT (util/fastmri_utils.py:67-89), magnitude.  (H+2pad, W+2pad) must be 2^a·3^b.              */
+ * FFT (util/fastmri_utils.py:67-89), magnitude.  Kernels exist for pad = 64 (the reference's
+ * int(oversample/8·256) with oversample = 2) and H = W ∈ {256, 128, 64}: transform lengths 384, 256,
+ * 192 = 8·8·{6, 4, 3}; other shapes return DPS_ERR_UNSUPPORTED.                                    */
 int dps_operator_create_phase(int pad, int C, int H, int W, dps_operator** out);
 void dps_operator_destroy(dps_operator* op);
 

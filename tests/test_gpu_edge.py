@@ -51,7 +51,24 @@ def test_phase_retrieval_rejects_unsupported_size():
     from dps_ttc_b200.registry import get_operator
     op = get_operator("phase_retrieval", oversample=2.0, device=DEV)
     with pytest.raises(DpsError):
-        op.forward(torch.zeros(1, 3, 64, 64, device=DEV))      # kernels are built for 256 → 384 only, and say so
+        op.forward(torch.zeros(1, 3, 96, 96, device=DEV))      # kernels exist for 256 → 384, 128 → 256 and 64 → 192, and say so
+
+
+def test_phase_retrieval_matches_reference_fixture_at_64():
+    """The reference's own phase-retrieval fixture (64² image → 192² measurement; oracle/make_golden.py gen_operators): A(x)
+    and ∇ₓ‖y − A(x)‖ recorded through its autograd, now reaching the CUDA kernels directly (radices 8·8·3)."""
+    from dps_ttc_b200.registry import get_operator
+    g = golden("operators.npz")
+    op = get_operator("phase_retrieval", oversample=2.0, device=DEV)
+    x = torch.from_numpy(g["x"]).to(DEV).requires_grad_(True)
+    y = torch.from_numpy(g["phase_retrieval_y"]).to(DEV)
+    ax = op.forward(x)
+    assert tuple(ax.shape[-2:]) == (192, 192)
+    assert np.abs(ax.detach().cpu().numpy() - g["phase_retrieval_Ax"]).max() <= 2e-5     # complex64 FFT in torch vs the Stockham kernel
+    norm = op.residual_norm(x, y)
+    (grad,) = torch.autograd.grad(norm.sum(), x)
+    assert np.abs(norm.detach().cpu().numpy() - g["phase_retrieval_norm"]).max() <= 1e-5 * g["phase_retrieval_norm"].max()
+    assert np.abs(grad.cpu().numpy() - g["phase_retrieval_grad"]).max() <= 2e-5
 
 
 @pytest.mark.parametrize("n", [1, 5, 257])

@@ -201,24 +201,25 @@ def test_deferred_step_vs_oracle_and_vs_round1_sequence(op_name, op_cfg, method,
     assert psnr(outs[True][0], outs[False][0]) >= 100.0
 
 
+@pytest.mark.parametrize("size", [256, 128, 64])
 @pytest.mark.parametrize("n,idx,clip", [(1, 999, True), (4, 500, True), (2, 10, False)])
-def test_fused_phase_guidance_vs_two_kernels_and_oracle(n, idx, clip):
+def test_fused_phase_guidance_vs_two_kernels_and_oracle(n, idx, clip, size):
     """Phase retrieval guidance as rows → fused columns (both transforms, residual and cotangent on chip) → rows, against
     the forward + adjoint kernels it replaces and against the oracle's |FFT| / Jᵀ restatement."""
     from dps_ttc_b200 import kernels
     from dps_ttc_b200.kernels import OperatorPlan
-    plan = OperatorPlan.phase(64, 3, 256, 256, DEV)
+    plan = OperatorPlan.phase(64, 3, size, size, DEV)
     assert plan.guidance_partials == plan.partials_per_particle > 0
     k = _consts(idx)
     gen = torch.Generator(DEV).manual_seed(31 + n)
-    x = torch.randn(n, 3, 256, 256, device=DEV, generator=gen) / k.c1
-    o6 = torch.randn(n, 6, 256, 256, device=DEV, generator=gen) * 0.3 / max(k.c2, 1e-3)
+    x = torch.randn(n, 3, size, size, device=DEV, generator=gen) / k.c1
+    o6 = torch.randn(n, 6, size, size, device=DEV, generator=gen) * 0.3 / max(k.c2, 1e-3)
     eps = o6[:, :3]
-    y = torch.rand(1, 3, 384, 384, device=DEV, generator=gen) * 1.5
+    y = torch.rand(1, 3, size + 128, size + 128, device=DEV, generator=gen) * 1.5
     r2, p2, aux2 = plan.forward(x, eps, k, clip, y, want_partials=True)
-    g2 = torch.zeros(n, 6, 256, 256, device=DEV)
+    g2 = torch.zeros(n, 6, size, size, device=DEV)
     plan.adjoint(r2, None, x, eps, k, clip, None, out=g2[:, :3], aux=aux2)
-    g1 = torch.full((n, 6, 256, 256), float("nan"), device=DEV)
+    g1 = torch.full((n, 6, size, size), float("nan"), device=DEV)
     g1[:, 3:] = 0
     p1, r1, _ = plan.guidance(x, eps, k, clip, y, out=g1[:, :3], want_r=True)
     assert torch.isfinite(g1).all()
@@ -236,7 +237,7 @@ def test_fused_phase_guidance_vs_two_kernels_and_oracle(n, idx, clip):
             g_ref = g_ref * ((pre >= -1) & (pre <= 1))
         assert np.abs(r1.cpu().numpy() - r_ref).max() <= 2e-5 * max(1.0, np.abs(r_ref).max())
         assert np.abs(g1[:, :3].cpu().numpy() - g_ref).max() <= 5e-5 * max(1.0, np.abs(g_ref).max())
-    g3 = torch.zeros(n, 3, 256, 256, device=DEV)
+    g3 = torch.zeros(n, 3, size, size, device=DEV)
     p3, r3, _ = plan.guidance(x, eps, k, clip, y, out=g3)
     assert r3 is None and torch.equal(g3, g1[:, :3]) and torch.equal(p3, p1)
 
