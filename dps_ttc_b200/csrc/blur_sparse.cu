@@ -252,30 +252,49 @@ __global__ void __launch_bounds__(kMaxThreads * kR / 32) sparse_kernel(const Tap
   }
 }
 
-// g[my][mx] = Σ_{rows p : reflect(p−Ry)=my} Σ_{cols q : reflect(q−Rx)=mx} t[p][q], then the cotangent epilogue
+// g[my][mx] = Σ_{rows p : reflect(p−Ry)=my} Σ_{cols q : reflect(q−Rx)=mx} t[p][q], then the cotangent epilogue.
+// A thread owns four adjacent pixels: the direct terms, the clamp-mask sources and the store are 128-bit accesses (five to
+// seven independent 16-byte requests per thread in flight; the scalar one-pixel-per-thread version reached a third of the HBM
+// rate: 185 µs of the 605 µs adjoint at N = 128); the mirrored column terms of border pixels stay scalar.  Every pixel sums
+// its terms in the order of the scalar version (rows: direct, top, bottom; columns: direct, left, right): same bits.
 __global__ void __launch_bounds__(256) sparse_fold_kernel(const float* __restrict__ t, int Ry, int Rx, int C, int H,
                                                           int W, const AdjArgs aa) {
   const int n = blockIdx.z, c = blockIdx.y;
   const int OH = H + 2 * Ry, OW = W + 2 * Rx;
   const float* tp = t + ((int64_t)n * C + c) * OH * OW;
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= H * W) return;
-  const int my = idx / W, mx = idx - my * W;
-  int rows[3], cols[3], nr = 0, nc = 0;
+  const int idx4 = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx4 * 4 >= H * W) return;
+  const int my = (idx4 * 4) / W, mx0 = idx4 * 4 - my * W;  // W % 4 == 0: the four pixels share the row
+  int rows[3], nr = 0;
   rows[nr++] = my + Ry;
   if (my >= 1 && my <= Ry) rows[nr++] = Ry - my;
   if (my <= H - 2 && my >= H - 1 - Ry) rows[nr++] = 2 * (H - 1) - my + Ry;
-  cols[nc++] = mx + Rx;
-  if (mx >= 1 && mx <= Rx) cols[nc++] = Rx - mx;
-  if (mx <= W - 2 && mx >= W - 1 - Rx) cols[nc++] = 2 * (W - 1) - mx + Rx;
-  float s = 0.f;
-  for (int a = 0; a < nr; ++a)
-    for (int b = 0; b < nc; ++b) s += tp[(int64_t)rows[a] * OW + cols[b]];
-  const int64_t off = (int64_t)c * H * W + idx;
-  float res = (aa.coef ? aa.coef[n] : 1.0f) * s;
-  if (aa.extra) res += ldg_stream(aa.extra + n * aa.extra_stride + off);
-  res *= mask_load(aa.mask_src, aa.has_mask, n, off);
-  stg_stream(aa.g + n * aa.g_stride + off, res);
+  const bool border_cols = mx0 <= Rx || mx0 + 3 >= W - 1 - Rx;
+  float s[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int a = 0; a < nr; ++a) {
+    const float* tr = tp + (int64_t)rows[a] * OW;
+    const float4 d = ldg_stream4(tr + mx0 + Rx);  // Rx % 4 == 0, OW % 4 == 0: aligned
+    const float dv[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      s[e] += dv[e];
+      if (border_cols) {
+        const int mx = mx0 + e;
+        if (mx >= 1 && mx <= Rx) s[e] += tr[Rx - mx];
+        if (mx <= W - 2 && mx >= W - 1 - Rx) s[e] += tr[2 * (W - 1) - mx + Rx];
+      }
+    }
+  }
+  const int64_t off = (int64_t)c * H * W + (int64_t)idx4 * 4;
+  const float cf = aa.coef ? aa.coef[n] : 1.0f;
+  float4 res = make_float4(cf * s[0], cf * s[1], cf * s[2], cf * s[3]);
+  if (aa.extra) {
+    const float4 ex = ldg_stream4(aa.extra + n * aa.extra_stride + off);
+    res.x += ex.x; res.y += ex.y; res.z += ex.z; res.w += ex.w;
+  }
+  const float4 m = mask_load4(aa.mask_src, aa.has_mask, n, off);
+  res.x *= m.x; res.y *= m.y; res.z *= m.z; res.w *= m.w;
+  stg_stream4(aa.g + n * aa.g_stride + off, res);
 }
 
 // tile row stride: the compile-time kSWFixed when the image is 256 wide and the halo fits, else W + 2·halo
@@ -440,7 +459,7 @@ int sparse_adjoint(const dps_operator* op, const AdjArgs& a, cudaStream_t st) {
   const int OH = op->H + 2 * t->Ry, OW = op->W + 2 * t->Rx;
   sparse_dispatch<true>(op, OH, OW, a.n, dummy, a, scratch, st);
   DPS_LAUNCH_CHECK("sparse_blur_adjoint_t");
-  dim3 fgrid((unsigned)((op->H * op->W + 255) / 256), (unsigned)op->C, (unsigned)a.n);
+  dim3 fgrid((unsigned)((op->H * op->W / 4 + 255) / 256), (unsigned)op->C, (unsigned)a.n);
   sparse_fold_kernel<<<fgrid, 256, 0, st>>>(scratch, t->Ry, t->Rx, op->C, op->H, op->W, a);
   DPS_LAUNCH_CHECK("sparse_blur_adjoint_fold");
   return DPS_OK;
