@@ -308,7 +308,15 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kT, F == 4 ? 
     }
   }
   RSF_T(6);
-  __syncthreads();  // my residual rows are complete
+  if (!PROJ && a.partials) {  // per-warp Σr², Σ|r| now (the values die here); warp 0 adds the eight behind the barrier below
+    sq = warp_sum(sq);
+    ab = warp_sum(ab);
+    if ((tid & 31) == 0) {
+      red[tid >> 5] = sq;
+      red[32 + (tid >> 5)] = ab;
+    }
+  }
+  __syncthreads();  // my residual rows (and the per-warp sums) are complete
   if (PROJ) {
     float* op_ = a.g + n * a.g_stride + poff;
     const int l = tid / F;
@@ -319,12 +327,14 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kT, F == 4 ? 
     }
     return;
   }
-  if (a.partials) {
-    block_sum2(sq, ab, red);
+  if (a.partials && tid < 32) {  // the second half of block_sum2 (same order, same bits) by warp 0 alone: no CTA barrier, the
+    float s2 = tid < kT / 32 ? red[tid] : 0.0f, a2 = tid < kT / 32 ? red[32 + tid] : 0.0f;  // other warps go straight on to Aᵀ
+    s2 = warp_sum(s2);
+    a2 = warp_sum(a2);
     if (tid == 0) {
       float* pp = a.partials + ((int64_t)n * (a.C * kCluster) + c * kCluster + q) * 2;
-      pp[0] = sq;
-      pp[1] = ab;
+      pp[0] = s2;
+      pp[1] = a2;
     }
   }
   // ---- 3. Aᵀ: u[m][col] = Σ_d aw[d] · r[RJ·q − 2 + m][l0(col) + d],  then g[ii][col] = mask · Σ_d Ah[ii][d] · u[m0(ii) + d] ----
