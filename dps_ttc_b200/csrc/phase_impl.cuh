@@ -1,45 +1,8 @@
 // Size-dependent part of phase.cu, included once per supported transform length L = 64·PHASE_R3 (PHASE_R3 = 6, 4, 3 ↔
 // 256², 128², 64² images zero-padded by 64 to 384², 256², 192²) inside a namespace of its own.  Stockham radices 8 · 8 · PHASE_R3.
-constexpr int kR3 = PHASE_R3;
-constexpr int kL = 64 * kR3;
-constexpr int kL8 = kL / 8;           // butterflies per sequence in the two radix-8 stages
-constexpr int kS8 = 9 * kR3;          // P(j + kL8·r) − P(j): shared-memory stride of a radix-8 butterfly's inputs
-constexpr int kHalf = kL / 2 + 1;     // 193 / 129 / 97
-constexpr int kLP = kL + kL / 8 + 1;  // padded length of a sequence in shared memory (433 / 289 / 217): ODD so that the same element of
-                                      // consecutive sequences falls into different banks (loops that run over the sequence index)
-constexpr int kLF = kL + 1;           // row stride of the float planes staged per sequence (same reason)
-constexpr int kPad = 64;              // int((oversample / 8) · 256) with oversample = 2, whatever the image size (measurements.py:181)
-constexpr int kImg = kL - 2 * kPad;
-constexpr int kRowsPerCta = 16;  // K1 / A2: image rows per CTA → 8 packed FFTs (55.9 KB of shared memory at L = 384 → 4 CTAs per SM)
-constexpr int kColsPerCta = 8;   // K2 / A1: spectrum columns per CTA
-constexpr int kColGroups = (kHalf + kColsPerCta - 1) / kColsPerCta;  // 25 / 17 / 13
-// the adjoint prefers wider CTAs: its scattered reads of r coalesce into 64-byte runs with 16 columns
-constexpr int kRowsAdj = 32;
-constexpr int kColsAdj = 16;
-constexpr int kColGroupsAdj = (kHalf + kColsAdj - 1) / kColsAdj;  // 13 / 9 / 7
-static_assert(kL8 % 8 == 0 && kImg % kRowsAdj == 0 && kImg % kRowsPerCta == 0 && kL % 32 == 0, "supported lengths");
+#include "phase_dims.cuh"
 
 namespace {
-
-// Shared-memory sequences are padded by one element every 8: element i lives at i + (i >> 3).  With 8-byte
-// elements this makes the stride-8 / stride-64 scatter of the Stockham stages conflict-free (stride 9 / 72).
-DPS_DEV int P(int i) { return i + (i >> 3); }
-
-// last stage: radix kR3
-DPS_DEV void dft_last(float2* v) {
-  if constexpr (kR3 == 6) dft6(v);
-  else if constexpr (kR3 == 4) dft4(v);
-  else dft3(v[0], v[1], v[2]);
-}
-
-// Twiddle exp(−2πi j/384), j ∈ [0,384), from the half table in shared memory: tw[j+192] = −tw[j].  Halving the table
-// (1.5 KB instead of 3 KB) is what lets FOUR 8-sequence CTAs (57 KB each) share an SM instead of three.
-constexpr int kTW = kL / 2;
-DPS_DEV float2 twid(const float2* tw, int j) {
-  const bool hi = j >= kTW;
-  const float2 t = tw[hi ? j - kTW : j];
-  return hi ? make_float2(-t.x, -t.y) : t;
-}
 
 // `nfft` independent forward FFTs of length 384, sequence f at a[f*384 ...]; the result lands in b.
 // Stockham autosort, radices 8·8·6 (natural order in, natural order out).  All threads must call it.
@@ -277,8 +240,6 @@ __global__ void __launch_bounds__(kThreads, 4) phase_rows_fwd(const FwdArgs fa, 
     *reinterpret_cast<float4*>(rt + (int64_t)k * kImg + r0 + 2 * f) = make_float4(A.x, A.y, B.x, B.y);
   }
 }
-
-DPS_DEV int shift_idx(int k) { return k + kL / 2 >= kL ? k - kL / 2 : k + kL / 2; }  // fftshift position of bin k
 
 // ---- K2: column transforms, magnitude, residual, partial sums, unit phase -----------------------
 // kLean (opt-in, DPSTTC_PHASE_LEAN=1, not launched by default): the output epilogue with its addressing hoisted.  Under the
@@ -547,6 +508,63 @@ __global__ void __launch_bounds__(kThreads, 4) phase_cols_fused(const FwdArgs fa
   }
 }
 
+// ---- K2'': the same column step with the butterflies in registers (phase_colsreg.cuh) -------------------------------------
+#include "phase_colsreg.cuh"
+
+size_t smem_bytes_reg() { return sizeof(float2) * ((size_t)2 * kSeq * kLQ + kL + 64) + 64 * sizeof(float); }
+
+// table layout behind PhaseTables::tw (create()): [0, L) exp(−2πi j/L) · [L, L + 64) W64^{k·r} at [8r + k] · [L + 64, 2L + 64) the
+// full table rebuilt from the half table with twid()'s sign rule
+template <bool kOut>
+__global__ void __launch_bounds__(kT2, 2) phase_cols_fused_reg(const FwdArgs fa, const float2* __restrict__ tw_g, int C) {
+  extern __shared__ __align__(16) float smem[];
+  const int tid = threadIdx.x;
+  const int grp = blockIdx.x % kColGroups, c = blockIdx.x / kColGroups, n = blockIdx.y;
+  ColsCtx cx;
+  cx.A = reinterpret_cast<float2*>(smem);
+  cx.B = cx.A + kSeq * kLQ;
+  float2* tw = cx.B + kSeq * kLQ;
+  float2* w64 = tw + kL;
+  float* red = reinterpret_cast<float*>(w64 + 64);
+  cx.tw = tw;
+  cx.w64 = w64;
+  cx.k20 = grp * kColsPerCta;
+  cx.ncols = min(kColsPerCta, kHalf - cx.k20);
+  cx.rt = aux_scratch(fa.aux, n, C, c);
+  cx.y = fa.y + n * fa.y_stride + (int64_t)c * kL * kL;
+  cx.outp = kOut ? fa.out + ((int64_t)n * C + c) * kL * kL : nullptr;
+  cx.t = aux_scratch2(fa.aux, n, C, c);
+  stage_async(reinterpret_cast<float*>(tw), reinterpret_cast<const float*>(tw_g + kL + 64), 2 * kL, tid, kT2);
+  stage_async(reinterpret_cast<float*>(w64), reinterpret_cast<const float*>(tw_g + kL), 2 * 64, tid, kT2);
+  ColsRegs R;
+  ColsY Y;
+  R.sq = R.ab = 0.f;
+  cr_load(tid, R, cx);
+  cr_stage_a(tid, R, cx.A);
+  stage_wait();
+  __syncthreads();
+  cr_stage_b(tid, R, cx.A, cx.B, cx.w64);
+  cr_yload(tid, Y, cx);  // in flight across the barrier
+  __syncthreads();
+  cr_epilogue<kOut>(tid, R, Y, cx);
+  if (fa.partials) {
+    block_sum2(R.sq, R.ab, red);  // (its barriers also order the epilogue's writes of A against the reads below)
+    if (tid == 0) {
+      float* pp = fa.partials + ((int64_t)n * (C * kColGroups) + blockIdx.x) * 2;
+      pp[0] = R.sq;
+      pp[1] = R.ab;
+    }
+  } else {
+    __syncthreads();
+  }
+  cr_read_a(tid, R, cx.A);
+  cr_stage_a(tid, R, cx.B);
+  __syncthreads();
+  cr_stage_b(tid, R, cx.B, cx.A, cx.w64);
+  __syncthreads();
+  cr_store(tid, R, cx);
+}
+
 // ---- A1: H_s[k1][k2] = ½(g[k]+g[−k])·conj(F)/|F|, column transform, keep rows 64..319 ------------
 __global__ void __launch_bounds__(kThreads, 3) phase_cols_adj(const AdjArgs aa, float* __restrict__ aux_rw,
                                                               const float2* __restrict__ tw_g, int C) {
@@ -674,11 +692,20 @@ int create(dps_operator* op) {
     const double a = -2.0 * M_PI * j / kL;
     tw[j] = make_float2((float)cos(a), (float)sin(a));
   }
-  DPS_CUDA(cudaMalloc(&t->tw, sizeof(float2) * kL));
-  DPS_CUDA(cudaMemcpy(t->tw, tw.data(), sizeof(float2) * kL, cudaMemcpyHostToDevice));
+  // W64^{k·r} at [kL + 8r + k], taken from the half table with the sign rule of twid() (bit-identical twiddles in both column kernels)
+  for (int r = 0; r < 8; ++r)
+    for (int k = 0; k < 8; ++k) {
+      const int j = kR3 * k * r;
+      tw.push_back(j >= kTW ? make_float2(-tw[j - kTW].x, -tw[j - kTW].y) : tw[j]);
+    }
+  for (int j = 0; j < kL; ++j) tw.push_back(j >= kTW ? make_float2(-tw[j - kTW].x, -tw[j - kTW].y) : tw[j]);
+  DPS_CUDA(cudaMalloc(&t->tw, sizeof(float2) * tw.size()));
+  DPS_CUDA(cudaMemcpy(t->tw, tw.data(), sizeof(float2) * tw.size(), cudaMemcpyHostToDevice));
   if (int rc = set_smem((const void*)phase_rows_fwd<false>, smem_bytes(kRowsPerCta / 2))) return rc;
   if (int rc = set_smem((const void*)phase_rows_fwd<true>, smem_bytes(kRowsPerCta / 2))) return rc;
   if (int rc = set_smem((const void*)phase_cols_fused, smem_bytes(kColsPerCta))) return rc;
+  if (int rc = set_smem((const void*)phase_cols_fused_reg<false>, smem_bytes_reg())) return rc;
+  if (int rc = set_smem((const void*)phase_cols_fused_reg<true>, smem_bytes_reg())) return rc;
   if (int rc = set_smem((const void*)phase_cols_fwd<false>, smem_bytes(kColsPerCta))) return rc;
   if (int rc = set_smem((const void*)phase_cols_fwd<true>, smem_bytes(kColsPerCta))) return rc;
   if (int rc = set_smem((const void*)phase_cols_adj, smem_bytes1(kColsAdj))) return rc;
@@ -740,7 +767,16 @@ int guidance(const dps_operator* op, const dps_source& src, const float* y, int6
   phase_rows_fwd<true><<<g1, kThreads, smem_bytes(kRowsPerCta / 2), st>>>(fa, op->phase->tw, op->C);
   DPS_LAUNCH_CHECK("phase_rows_fwd");
   dim3 g2((unsigned)(op->C * kColGroups), (unsigned)n);
-  phase_cols_fused<<<g2, kThreads, smem_bytes(kColsPerCta), st>>>(fa, op->phase->tw, op->C);
+  // column step: shared-memory stages (phase_cols_fused) or register-resident butterflies (phase_colsreg.cuh);
+  // DPSTTC_PHASE_COLS_REG=0 / 1 overrides the built-in choice (read once per process)
+  constexpr bool kRegDefault = false;
+  static const bool reg = getenv("DPSTTC_PHASE_COLS_REG") ? getenv("DPSTTC_PHASE_COLS_REG")[0] != '0' : kRegDefault;
+  if (reg && r_out)
+    phase_cols_fused_reg<true><<<g2, kT2, smem_bytes_reg(), st>>>(fa, op->phase->tw, op->C);
+  else if (reg)
+    phase_cols_fused_reg<false><<<g2, kT2, smem_bytes_reg(), st>>>(fa, op->phase->tw, op->C);
+  else
+    phase_cols_fused<<<g2, kThreads, smem_bytes(kColsPerCta), st>>>(fa, op->phase->tw, op->C);
   DPS_LAUNCH_CHECK("phase_cols_fused");
   AdjArgs aa;
   aa.r = nullptr;

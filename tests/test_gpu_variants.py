@@ -48,6 +48,16 @@ def test_lean_kernels_bit_identical_to_round1_kernels(op, n, envs):
 
 
 @pytest.mark.gpu
+def test_phase_register_column_kernel_agrees_with_shared_memory_kernel():
+    """phase_cols_fused_reg (butterflies in registers, the default) against phase_cols_fused (every stage through shared
+    memory) on the same inputs at 256², 128² and 64²: residual, per-particle norms and cotangent to rounding."""
+    cmd = [sys.executable, os.path.join(REPO, "tools", "phase_reg_check.py"), "--n", "3"]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert "PASS" in res.stdout
+
+
+@pytest.mark.gpu
 def test_motion_blur_row_variants_bit_identical():
     """blur_sparse.cu launches 16-row CTAs while the grid is small (N ≲ 12) and 32-row CTAs otherwise; a particle's residual,
     partial sums and cotangent must not depend on which one ran (sharded runs put 8 particles per launch where the unsharded

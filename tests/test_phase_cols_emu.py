@@ -1,0 +1,79 @@
+"""Index logic of the register-resident phase column kernel (dps_ttc_b200/csrc/phase_colsreg.cuh) on the CPU.
+
+The kernel is written as barrier-free per-thread phases; tests/emu/phase_cols_emu.cpp compiles the SAME headers for the host
+and runs the phases thread by thread.  Compared here with a plain numpy DFT of the same column step: |F|/L, the residual at
+both Hermitian-mirrored output positions, the partial sums and the second transform of the symmetrised cotangent × unit
+phase.  (Test infrastructure; the product path is the CUDA kernel, checked against the oracle by the -m gpu tests.)"""
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _build(r3, tmp_path):
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    so = str(tmp_path / f"phase_cols_emu_{r3}.so")
+    subprocess.run(["g++", "-O1", "-shared", "-fPIC", f"-DPHASE_R3={r3}", "-I", os.path.join(ROOT, "dps_ttc_b200", "csrc"),
+                    "-o", so, os.path.join(ROOT, "tests", "emu", "phase_cols_emu.cpp")], check=True)
+    return C.CDLL(so)
+
+
+@pytest.mark.parametrize("r3,want_r", [(6, True), (4, True), (3, True), (6, False)])
+def test_register_column_kernel_matches_numpy_dft(r3, want_r, tmp_path):
+    lib = _build(r3, tmp_path)
+    dims = (C.c_int * 4)()
+    lib.emu_dims(dims)
+    L, img, half, groups = list(dims)
+    assert L == 64 * r3 and img == L - 128 and half == L // 2 + 1
+    rng = np.random.default_rng(7 + r3)
+    rt = (rng.standard_normal((half, img)) + 1j * rng.standard_normal((half, img))).astype(np.complex64) * 8
+    with_y = True   # dps_operator_guidance always has the measurement
+    y = (rng.random((L, L)) * 1.5).astype(np.float32)
+    r_out = np.full((L, L), np.nan, np.float32) if want_r else None
+    t = np.full((img, half), np.nan + 0j, np.complex64)
+    partials = np.zeros((groups, 2), np.float32)
+    fp = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
+    assert lib.emu_cols(fp(rt), fp(y), fp(r_out), fp(t), fp(partials)) == 0
+
+    # plain restatement: column k2 of the half spectrum, rows zero-padded by 64
+    pad = np.zeros((half, L), np.complex128)
+    pad[:, 64:64 + img] = rt
+    F = np.fft.fft(pad, axis=1)                       # F[k2, k1]
+    amp = np.abs(F) / L
+    sh = lambda k: (k + L // 2) % L
+    k1 = np.arange(L)
+    k2 = np.arange(half)
+    ya = y.astype(np.float64) if with_y else None
+    pos1 = (sh(k1)[None, :], sh(k2)[:, None])                          # (row, col) of the direct output
+    pos2 = (sh((L - k1) % L)[None, :], sh((L - k2) % L)[:, None])      # mirrored output
+    r1 = (ya[pos1] - amp) if with_y else amp
+    r2 = (ya[pos2] - amp) if with_y else amp
+    mir = ((k2 > 0) & (k2 < L // 2))[:, None] & np.ones((1, L), bool)
+    ref_out = np.full((L, L), np.nan)
+    ref_out[pos1[0].repeat(half, 0), pos1[1].repeat(L, 1)] = r1
+    m_r, m_c = np.broadcast_to(pos2[0], (half, L))[mir], np.broadcast_to(pos2[1], (half, L))[mir]
+    ref_out[m_r, m_c] = r2[mir]
+    assert not np.isnan(ref_out).any(), "the two position sets must tile the L×L plane"
+    scale = max(1.0, np.abs(ref_out).max())
+    if want_r:
+        assert np.abs(r_out - ref_out).max() <= 2e-5 * scale
+    # partial sums per column group
+    sq = np.where(mir, r1 ** 2 + r2 ** 2, r1 ** 2).sum(1)
+    ab = np.where(mir, np.abs(r1) + np.abs(r2), np.abs(r1)).sum(1)
+    for g in range(groups):
+        cols = slice(8 * g, min(8 * g + 8, half))
+        assert abs(partials[g, 0] - sq[cols].sum()) <= 1e-4 * sq[cols].sum()
+        assert abs(partials[g, 1] - ab[cols].sum()) <= 1e-4 * ab[cols].sum()
+    # cotangent: ½(r(k) + r(−k)) · conj(F)/|F|, second (forward) transform over k1, rows 64..64+img
+    with np.errstate(invalid="ignore", divide="ignore"):
+        unit = np.where(np.abs(F) > 0, np.conj(F) / np.abs(F), 0)
+    Hs = 0.5 * (r1 + r2) * unit
+    T = np.fft.fft(Hs, axis=1)[:, 64:64 + img].T      # T[row, k2]
+    assert not np.isnan(t.view(np.float32)).any()
+    assert np.abs(t - T).max() <= 2e-5 * np.abs(T).max()
