@@ -164,8 +164,8 @@ DPS_DEV void cr_epilogue(int tid, ColsRegs& R, const ColsY& Y, const ColsCtx& c)
       R.ab += fabsf(r2);
       if constexpr (kOut) stg_stream(c.outp + shift_idx(k1 ? kL - k1 : 0) * kL + c2, r2);
     }
-    const float gs = (act ? 0.5f * (r1 + r2) : 0.f) * inv;
-    dst[72 * r] = make_float2(gs * F.x, -gs * F.y);
+    const float gs = act ? 0.5f * (r1 + r2) : 0.f;
+    dst[72 * r] = make_float2(gs * (F.x * inv), gs * (-F.y * inv));  // the association of phase_cols_fused: same bits
   }
 }
 // F role: last stage of the second transform; padded rows 64 .. 64 + H − 1 go to T[row][k2] (row stride L/2 + 1)
