@@ -55,6 +55,20 @@ DPS_DEV void batched_copy(int tid, Load load, Store store) {
 
 #include "phase_math.cuh"
 
+DPS_DEV void stg_u8(unsigned char* p, unsigned v) { asm volatile("st.global.u8 [%0], %1;" ::"l"(p), "r"(v)); }
+// read-only loads the compiler must not move across a barrier (issued early on purpose: in flight while a stage runs)
+DPS_DEV unsigned char ldg_u8_pinned(const unsigned char* p) {
+  unsigned v;
+  // ld.volatile: ptxas moves a non-coherent load below the barrier it is meant to be in flight across (seen in SASS)
+  asm volatile("ld.volatile.global.u8 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return (unsigned char)v;
+}
+DPS_DEV float ldg_ro_pinned(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+
 // clamp-mask bytes of the fused guidance path (1 = gradient passes): written by the row kernel, read by the last kernel,
 // so that x and ε are read ONCE per step (T/4 bytes each way instead of 2T)
 DPS_DEV unsigned pack_pass4(const float* x, const float* eps, int64_t i, float c1, float c2, int clip) {

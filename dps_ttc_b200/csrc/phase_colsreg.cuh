@@ -57,7 +57,7 @@ struct ColsY {
 DPS_DEV void cr_load(int tid, ColsRegs& R, const ColsCtx& c) {
   if (tid >= kJ) return;
   const int f = tid / kL8, j = tid - f * kL8;
-  const bool valid = f < c.ncols;
+  if (f >= c.ncols) return;  // (the last column group holds ONE column: its other sequences are never touched)
   const float2* src = c.rt + (int64_t)(c.k20 + f) * kImg;
 #pragma unroll
   for (int r = 0; r < 8; ++r) {
@@ -65,31 +65,34 @@ DPS_DEV void cr_load(int tid, ColsRegs& R, const ColsCtx& c) {
       R.v[r] = make_float2(0.f, 0.f);
     } else {
       const int row = j + kL8 * r - kPad;
-      R.v[r] = (valid && row >= 0 && row < kImg) ? ldg_stream2(src + row) : make_float2(0.f, 0.f);
+      R.v[r] = (row >= 0 && row < kImg) ? ldg_stream2(src + row) : make_float2(0.f, 0.f);
     }
   }
 }
 // J role: the inputs of the first stage from a buffer in natural order (second transform)
-DPS_DEV void cr_read_a(int tid, ColsRegs& R, const float2* buf) {
+DPS_DEV void cr_read_a(int tid, ColsRegs& R, const float2* buf, int nseq = kSeq) {
   if (tid >= kJ) return;
   const int f = tid / kL8, j = tid - f * kL8;
+  if (f >= nseq) return;
   const float2* src = buf + f * kLQ + P(j);  // P(j + (L/8)·r) = P(j) + kS8·r
 #pragma unroll
   for (int r = 0; r < 8; ++r) R.v[r] = src[kS8 * r];
 }
 // J role, stage 1 (R = 8, Ns = 1, no twiddles): out[8j + r] = DFT8(in[j + (L/8)·r]);  P(8j + r) = 9j + r
-DPS_DEV void cr_stage_a(int tid, ColsRegs& R, float2* dstbuf) {
+DPS_DEV void cr_stage_a(int tid, ColsRegs& R, float2* dstbuf, int nseq = kSeq) {
   if (tid >= kJ) return;
   const int f = tid / kL8, j = tid - f * kL8;
+  if (f >= nseq) return;
   dft8(R.v);
   float2* dst = dstbuf + f * kLQ + 9 * j;
 #pragma unroll
   for (int r = 0; r < 8; ++r) dst[r] = R.v[r];
 }
 // J role, stage 2 (R = 8, Ns = 8): twiddle W64^{k·r}, k = j & 7;  out[64·(j>>3) + k + 8r];  P(·) = 72·(j>>3) + k + 9r
-DPS_DEV void cr_stage_b(int tid, ColsRegs& R, const float2* srcbuf, float2* dstbuf, const float2* w64) {
+DPS_DEV void cr_stage_b(int tid, ColsRegs& R, const float2* srcbuf, float2* dstbuf, const float2* w64, int nseq = kSeq) {
   if (tid >= kJ) return;
   const int f = tid / kL8, j = tid - f * kL8;
+  if (f >= nseq) return;
   const int k = j & 7;
   const float2* src = srcbuf + f * kLQ + P(j);
 #pragma unroll
@@ -122,10 +125,12 @@ DPS_DEV void cr_yload(int tid, ColsY& Y, const ColsCtx& c) {
 #pragma unroll
   for (int r = 0; r < kR3; ++r) {
     const int k1 = j + 64 * r;
-    Y.y1[r] = act ? ldg_ro(c.y + shift_idx(k1) * kL + c1) : 0.f;
-    Y.y2[r] = act ? ldg_ro(c.y + shift_idx(k1 ? kL - k1 : 0) * kL + c2) : 0.f;
+    // (volatile loads: the compiler otherwise sinks them below the barrier they are meant to be in flight across)
+    Y.y1[r] = act ? ldg_ro_pinned(c.y + shift_idx(k1) * kL + c1) : 0.f;
+    Y.y2[r] = act ? ldg_ro_pinned(c.y + shift_idx(k1 ? kL - k1 : 0) * kL + c2) : 0.f;
   }
 }
+// (Inactive sequences of the last column group hold whatever was in shared memory; every use is guarded by `act`.)
 // F role: last stage of the first transform, then everything that is local to a bin: |F|/L, the unit phase conj(F)/|F|, the
 // residual at both mirrored output positions (partial sums; r itself only if asked for) and the symmetrised cotangent
 // ½(r(k) + r(−k)) × unit phase → dstbuf in natural order (the input of the second transform).

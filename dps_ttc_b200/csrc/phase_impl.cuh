@@ -519,7 +519,11 @@ template <bool kOut>
 __global__ void __launch_bounds__(kT2, 2) phase_cols_fused_reg(const FwdArgs fa, const float2* __restrict__ tw_g, int C) {
   extern __shared__ __align__(16) float smem[];
   const int tid = threadIdx.x;
-  const int grp = blockIdx.x % kColGroups, c = blockIdx.x / kColGroups, n = blockIdx.y;
+  // 1-D grid with the column group as the slowest index: the last group holds a single column (k2 = L/2) and its CTAs are
+  // light, so they fill the tail of the last wave instead of being spread over all of them
+  const int planes = fa.n * C;
+  const int grp = blockIdx.x / planes, pc = blockIdx.x - grp * planes;
+  const int n = pc / C, c = pc - n * C;
   ColsCtx cx;
   cx.A = reinterpret_cast<float2*>(smem);
   cx.B = cx.A + kSeq * kLQ;
@@ -540,29 +544,102 @@ __global__ void __launch_bounds__(kT2, 2) phase_cols_fused_reg(const FwdArgs fa,
   ColsY Y;
   R.sq = R.ab = 0.f;
   cr_load(tid, R, cx);
-  cr_stage_a(tid, R, cx.A);
+  cr_stage_a(tid, R, cx.A, cx.ncols);
   stage_wait();
   __syncthreads();
-  cr_stage_b(tid, R, cx.A, cx.B, cx.w64);
-  cr_yload(tid, Y, cx);  // in flight across the barrier
+  cr_yload(tid, Y, cx);  // in flight across the second stage and the barrier
+  cr_stage_b(tid, R, cx.A, cx.B, cx.w64, cx.ncols);
   __syncthreads();
   cr_epilogue<kOut>(tid, R, Y, cx);
   if (fa.partials) {
     block_sum2(R.sq, R.ab, red);  // (its barriers also order the epilogue's writes of A against the reads below)
     if (tid == 0) {
-      float* pp = fa.partials + ((int64_t)n * (C * kColGroups) + blockIdx.x) * 2;
+      float* pp = fa.partials + ((int64_t)n * (C * kColGroups) + c * kColGroups + grp) * 2;
       pp[0] = R.sq;
       pp[1] = R.ab;
     }
   } else {
     __syncthreads();
   }
-  cr_read_a(tid, R, cx.A);
-  cr_stage_a(tid, R, cx.B);
+  cr_read_a(tid, R, cx.A, cx.ncols);
+  cr_stage_a(tid, R, cx.B, cx.ncols);
   __syncthreads();
-  cr_stage_b(tid, R, cx.B, cx.A, cx.w64);
+  cr_stage_b(tid, R, cx.B, cx.A, cx.w64, cx.ncols);
   __syncthreads();
   cr_store(tid, R, cx);
+}
+
+// ---- K1'' / K3'': the row kernels of the fused path with the butterflies in registers (phase_rowsreg.cuh) -------------------
+#include "phase_rowsreg.cuh"
+#ifndef PHASE_ROWS_MINB
+#define PHASE_ROWS_MINB 2  // CTAs per SM the row kernels are compiled for (3: 40 registers, the loads of K3 in two batches)
+#endif
+
+__global__ void __launch_bounds__(kT2, PHASE_ROWS_MINB) phase_rows_fwd_reg(const FwdArgs fa, const float2* __restrict__ tw_g, int C) {
+  extern __shared__ __align__(16) float smem[];
+  const int tid = threadIdx.x;
+  constexpr int groups = kImg / kRowsReg;
+  const int grp = blockIdx.x % groups, c = blockIdx.x / groups, n = blockIdx.y;
+  RowsFwdCtx cx;
+  cx.A = reinterpret_cast<float2*>(smem);
+  cx.B = cx.A + kSeq * kLQ;
+  float2* tw = cx.B + kSeq * kLQ;
+  float2* w64 = tw + kL;
+  cx.tw = tw;
+  cx.w64 = w64;
+  const int64_t plane = (int64_t)c * kImg * kImg;
+  cx.x = fa.src.x + n * fa.src.x_stride + plane;
+  cx.eps = fa.src.eps + n * fa.src.eps_stride + plane;
+  cx.c1 = fa.src.c1;
+  cx.c2 = fa.src.c2;
+  cx.clip = fa.src.clip;
+  cx.maskb = aux_mask(fa.aux, n, C, c);
+  cx.rt = aux_scratch(fa.aux, n, C, c);
+  cx.r0 = grp * kRowsReg;
+  stage_async(reinterpret_cast<float*>(tw), reinterpret_cast<const float*>(tw_g + kL + 64), 2 * kL, tid, kT2);
+  stage_async(reinterpret_cast<float*>(w64), reinterpret_cast<const float*>(tw_g + kL), 2 * 64, tid, kT2);
+  ColsRegs R;
+  rf_load(tid, R, cx);
+  cr_stage_a(tid, R, cx.A);
+  stage_wait();
+  __syncthreads();
+  cr_stage_b(tid, R, cx.A, cx.B, cx.w64);
+  __syncthreads();
+  rf_spectrum(tid, R, cx);
+  __syncthreads();
+  rf_split_store(tid, cx);
+}
+
+__global__ void __launch_bounds__(kT2, PHASE_ROWS_MINB) phase_rows_adj_reg(const AdjArgs aa, const float* __restrict__ aux_r,
+                                                             const float2* __restrict__ tw_g, int C) {
+  extern __shared__ __align__(16) float smem[];
+  const int tid = threadIdx.x;
+  constexpr int groups = kImg / kRowsReg;
+  const int grp = blockIdx.x % groups, c = blockIdx.x / groups, n = blockIdx.y;
+  RowsAdjCtx cx;
+  cx.A = reinterpret_cast<float2*>(smem);
+  cx.B = cx.A + kSeq * kLQ;
+  float2* tw = cx.B + kSeq * kLQ;
+  float2* w64 = tw + kL;
+  cx.tw = tw;
+  cx.w64 = w64;
+  cx.t = aux_scratch2(const_cast<float*>(aux_r), n, C, c);
+  cx.maskb = aux_mask(const_cast<float*>(aux_r), n, C, c);
+  cx.g = aa.g + n * aa.g_stride + (int64_t)c * kImg * kImg;
+  cx.coef = (aa.coef ? aa.coef[n] : 1.0f) * (1.0f / (float)kL);
+  cx.r0 = grp * kRowsReg;
+  stage_async(reinterpret_cast<float*>(tw), reinterpret_cast<const float*>(tw_g + kL + 64), 2 * kL, tid, kT2);
+  stage_async(reinterpret_cast<float*>(w64), reinterpret_cast<const float*>(tw_g + kL), 2 * 64, tid, kT2);
+  ColsRegs R;
+  RowsMask M;
+  ra_load(tid, R, cx);
+  cr_stage_a(tid, R, cx.A);
+  stage_wait();
+  __syncthreads();
+  cr_stage_b(tid, R, cx.A, cx.B, cx.w64);
+  ra_maskload(tid, M, cx);  // in flight across the barrier
+  __syncthreads();
+  ra_store(tid, R, M, cx);
 }
 
 // ---- A1: H_s[k1][k2] = ½(g[k]+g[−k])·conj(F)/|F|, column transform, keep rows 64..319 ------------
@@ -704,6 +781,8 @@ int create(dps_operator* op) {
   if (int rc = set_smem((const void*)phase_rows_fwd<false>, smem_bytes(kRowsPerCta / 2))) return rc;
   if (int rc = set_smem((const void*)phase_rows_fwd<true>, smem_bytes(kRowsPerCta / 2))) return rc;
   if (int rc = set_smem((const void*)phase_cols_fused, smem_bytes(kColsPerCta))) return rc;
+  if (int rc = set_smem((const void*)phase_rows_fwd_reg, smem_bytes_reg())) return rc;
+  if (int rc = set_smem((const void*)phase_rows_adj_reg, smem_bytes_reg())) return rc;
   if (int rc = set_smem((const void*)phase_cols_fused_reg<false>, smem_bytes_reg())) return rc;
   if (int rc = set_smem((const void*)phase_cols_fused_reg<true>, smem_bytes_reg())) return rc;
   if (int rc = set_smem((const void*)phase_cols_fwd<false>, smem_bytes(kColsPerCta))) return rc;
@@ -763,18 +842,27 @@ int guidance(const dps_operator* op, const dps_source& src, const float* y, int6
   fa.partials = partials;
   fa.aux = aux;
   fa.n = n;
+  // row kernels: shared-memory stages (phase_rows_fwd / phase_rows_adj) or register-resident butterflies (phase_rowsreg.cuh);
+  // DPSTTC_PHASE_ROWS_REG=0 / 1 overrides the built-in choice (read once per process)
+  constexpr bool kRowsRegDefault = false;
+  static const bool rows_reg = getenv("DPSTTC_PHASE_ROWS_REG") ? getenv("DPSTTC_PHASE_ROWS_REG")[0] != '0' : kRowsRegDefault;
+  dim3 g1r((unsigned)(op->C * (kImg / kRowsReg)), (unsigned)n);
   dim3 g1((unsigned)(op->C * (kImg / kRowsPerCta)), (unsigned)n);
-  phase_rows_fwd<true><<<g1, kThreads, smem_bytes(kRowsPerCta / 2), st>>>(fa, op->phase->tw, op->C);
+  if (rows_reg)
+    phase_rows_fwd_reg<<<g1r, kT2, smem_bytes_reg(), st>>>(fa, op->phase->tw, op->C);
+  else
+    phase_rows_fwd<true><<<g1, kThreads, smem_bytes(kRowsPerCta / 2), st>>>(fa, op->phase->tw, op->C);
   DPS_LAUNCH_CHECK("phase_rows_fwd");
   dim3 g2((unsigned)(op->C * kColGroups), (unsigned)n);
   // column step: shared-memory stages (phase_cols_fused) or register-resident butterflies (phase_colsreg.cuh);
   // DPSTTC_PHASE_COLS_REG=0 / 1 overrides the built-in choice (read once per process)
   constexpr bool kRegDefault = false;
   static const bool reg = getenv("DPSTTC_PHASE_COLS_REG") ? getenv("DPSTTC_PHASE_COLS_REG")[0] != '0' : kRegDefault;
+  const dim3 g2r((unsigned)(op->C * kColGroups * n));
   if (reg && r_out)
-    phase_cols_fused_reg<true><<<g2, kT2, smem_bytes_reg(), st>>>(fa, op->phase->tw, op->C);
+    phase_cols_fused_reg<true><<<g2r, kT2, smem_bytes_reg(), st>>>(fa, op->phase->tw, op->C);
   else if (reg)
-    phase_cols_fused_reg<false><<<g2, kT2, smem_bytes_reg(), st>>>(fa, op->phase->tw, op->C);
+    phase_cols_fused_reg<false><<<g2r, kT2, smem_bytes_reg(), st>>>(fa, op->phase->tw, op->C);
   else
     phase_cols_fused<<<g2, kThreads, smem_bytes(kColsPerCta), st>>>(fa, op->phase->tw, op->C);
   DPS_LAUNCH_CHECK("phase_cols_fused");
@@ -790,7 +878,10 @@ int guidance(const dps_operator* op, const dps_source& src, const float* y, int6
   aa.aux = aux;
   aa.n = n;
   dim3 g3((unsigned)(op->C * (kImg / kRowsAdj)), (unsigned)n);
-  phase_rows_adj<true><<<g3, kThreads, smem_bytes1(kRowsAdj / 2), st>>>(aa, aux, op->phase->tw, op->C);
+  if (rows_reg)
+    phase_rows_adj_reg<<<g1r, kT2, smem_bytes_reg(), st>>>(aa, aux, op->phase->tw, op->C);
+  else
+    phase_rows_adj<true><<<g3, kThreads, smem_bytes1(kRowsAdj / 2), st>>>(aa, aux, op->phase->tw, op->C);
   DPS_LAUNCH_CHECK("phase_rows_adj");
   return DPS_OK;
 }

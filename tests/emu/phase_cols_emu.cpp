@@ -18,6 +18,7 @@ static inline float emu_rsqrtf(float x) { return 1.0f / std::sqrt(x); }
 static inline float __fsub_rn(float a, float b) { return a - b; }
 static inline float2 ldg_stream2(const float2* p) { return *p; }
 static inline float ldg_ro(const float* p) { return *p; }
+static inline float ldg_ro_pinned(const float* p) { return *p; }
 static inline void stg_stream(float* p, float v) { *p = v; }
 static inline void stg_stream2(float* p, const float2& v) { p[0] = v.x; p[1] = v.y; }
 
@@ -69,11 +70,11 @@ extern "C" int emu_cols(const float* rt, const float* y, float* r_out, float* t,
       R[tid].sq = R[tid].ab = 0.f;
       for (int r = 0; r < 8; ++r) R[tid].v[r] = make_float2(NAN, NAN);
       cr_load(tid, R[tid], cx);
-      cr_stage_a(tid, R[tid], cx.A);
+      cr_stage_a(tid, R[tid], cx.A, cx.ncols);
     }
     for (int tid = 0; tid < kT2; ++tid) {
-      cr_stage_b(tid, R[tid], cx.A, cx.B, cx.w64);
       cr_yload(tid, Y[tid], cx);
+      cr_stage_b(tid, R[tid], cx.A, cx.B, cx.w64, cx.ncols);
     }
     for (int tid = 0; tid < kT2; ++tid) {
       if (r_out) cr_epilogue<true>(tid, R[tid], Y[tid], cx);
@@ -84,10 +85,10 @@ extern "C" int emu_cols(const float* rt, const float* y, float* r_out, float* t,
     partials[2 * grp] = (float)sq;
     partials[2 * grp + 1] = (float)ab;
     for (int tid = 0; tid < kT2; ++tid) {
-      cr_read_a(tid, R[tid], cx.A);
-      cr_stage_a(tid, R[tid], cx.B);
+      cr_read_a(tid, R[tid], cx.A, cx.ncols);
+      cr_stage_a(tid, R[tid], cx.B, cx.ncols);
     }
-    for (int tid = 0; tid < kT2; ++tid) cr_stage_b(tid, R[tid], cx.B, cx.A, cx.w64);
+    for (int tid = 0; tid < kT2; ++tid) cr_stage_b(tid, R[tid], cx.B, cx.A, cx.w64, cx.ncols);
     for (int tid = 0; tid < kT2; ++tid) cr_store(tid, R[tid], cx);
   }
   return 0;

@@ -48,9 +48,10 @@ def test_lean_kernels_bit_identical_to_round1_kernels(op, n, envs):
 
 
 @pytest.mark.gpu
-def test_phase_register_column_kernel_agrees_with_shared_memory_kernel():
-    """phase_cols_fused_reg (butterflies in registers, the default) against phase_cols_fused (every stage through shared
-    memory) on the same inputs at 256², 128² and 64²: residual, per-particle norms and cotangent to rounding."""
+def test_phase_register_kernels_agree_with_shared_memory_kernels():
+    """The register-resident column / row kernels of the phase guidance (phase_colsreg.cuh, phase_rowsreg.cuh) against the
+    shared-memory kernels, in every combination, on the same inputs at 256², 128² and 64²: residual, per-particle norms and
+    cotangent to rounding."""
     cmd = [sys.executable, os.path.join(REPO, "tools", "phase_reg_check.py"), "--n", "3"]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]

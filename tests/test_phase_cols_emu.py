@@ -15,12 +15,13 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _build(r3, tmp_path):
+def _build(r3, tmp_path, which="cols"):
     if shutil.which("g++") is None:
         pytest.skip("g++ not available")
-    so = str(tmp_path / f"phase_cols_emu_{r3}.so")
-    subprocess.run(["g++", "-O1", "-shared", "-fPIC", f"-DPHASE_R3={r3}", "-I", os.path.join(ROOT, "dps_ttc_b200", "csrc"),
-                    "-o", so, os.path.join(ROOT, "tests", "emu", "phase_cols_emu.cpp")], check=True)
+    so = str(tmp_path / f"phase_{which}_emu_{r3}.so")
+    subprocess.run(["g++", "-O1", "-ffp-contract=off", "-shared", "-fPIC", f"-DPHASE_R3={r3}", "-I",
+                    os.path.join(ROOT, "dps_ttc_b200", "csrc"), "-o", so,
+                    os.path.join(ROOT, "tests", "emu", f"phase_{which}_emu.cpp")], check=True)
     return C.CDLL(so)
 
 
@@ -77,3 +78,48 @@ def test_register_column_kernel_matches_numpy_dft(r3, want_r, tmp_path):
     T = np.fft.fft(Hs, axis=1)[:, 64:64 + img].T      # T[row, k2]
     assert not np.isnan(t.view(np.float32)).any()
     assert np.abs(t - T).max() <= 2e-5 * np.abs(T).max()
+
+
+@pytest.mark.parametrize("r3,clip", [(6, True), (4, True), (3, False)])
+def test_register_row_kernels_match_numpy_dft(r3, clip, tmp_path):
+    """K1 (x, ε → x̂₀ → half spectrum of every image row, two rows per complex FFT, + clamp-pass bytes) and K3 (Hermitian half
+    rows → real rows × coefficient × clamp mask) of phase_rowsreg.cuh, emulated thread by thread."""
+    lib = _build(r3, tmp_path, "rows")
+    dims = (C.c_int * 4)()
+    lib.emu_dims(dims)
+    L, img, half, groups = list(dims)
+    assert L == 64 * r3 and img * 0 + groups == img // 16
+    rng = np.random.default_rng(11 + r3)
+    c1, c2 = np.float32(1.7), np.float32(0.9)
+    x = rng.standard_normal((img, img)).astype(np.float32)
+    eps = rng.standard_normal((img, img)).astype(np.float32)
+    rt = np.full((half, img), np.nan + 0j, np.complex64)
+    maskb = np.full((img, img), 7, np.uint8)
+    fp = lambda a: a.ctypes.data_as(C.c_void_p)
+    lib.emu_rows_fwd.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int, C.c_void_p, C.c_void_p]
+    assert lib.emu_rows_fwd(fp(x), fp(eps), float(c1), float(c2), int(clip), fp(rt), fp(maskb)) == 0
+    pre = c1 * x - c2 * eps                                   # float32, every product rounded on its own
+    x0 = np.clip(pre, -1, 1) if clip else pre
+    pad = np.zeros((img, L)); pad[:, 64:64 + img] = x0
+    ref = np.fft.fft(pad, axis=1)[:, :half].T                 # Rt[k2][row]
+    assert not np.isnan(rt.view(np.float32)).any()
+    assert np.abs(rt - ref).max() <= 2e-5 * np.abs(ref).max()
+    want_mask = ((pre >= -1) & (pre <= 1)).astype(np.uint8) if clip else np.ones((img, img), np.uint8)
+    assert np.array_equal(maskb, want_mask)
+
+    t = (rng.standard_normal((img, half)) + 1j * rng.standard_normal((img, half))).astype(np.complex64) * 4
+    g = np.full((img, img), np.nan, np.float32)
+    coef = 1.0 / L
+    lib.emu_rows_adj.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]
+    assert lib.emu_rows_adj(fp(t), fp(want_mask), coef, fp(g)) == 0
+    # X[k] = T1[k] + i T2[k] for k <= L/2, conj-mirrored above (row pairs); z = FFT(X); Re -> even row, Im -> odd row
+    k = np.arange(L)
+    kk = np.where(k < half, k, L - k)
+    full = np.where((k < half)[None, :], t[:, kk], np.conj(t[:, kk])).astype(np.complex128)
+    X = full[0::2] + 1j * full[1::2]
+    z = np.fft.fft(X, axis=1)[:, 64:64 + img]
+    ref_g = np.empty((img, img))
+    ref_g[0::2], ref_g[1::2] = z.real, z.imag
+    ref_g = ref_g * coef * want_mask
+    assert not np.isnan(g).any()
+    assert np.abs(g - ref_g).max() <= 2e-5 * np.abs(ref_g).max()

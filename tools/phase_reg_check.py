@@ -1,7 +1,8 @@
-"""A/B of the two column kernels of the fused phase-retrieval guidance (phase_cols_fused_reg, the default, against the
-shared-memory phase_cols_fused, DPSTTC_PHASE_COLS_REG=0): one child process per variant (the switch is read once per
-process) runs dps_operator_guidance on the same seeded inputs for 256², 128² and 64² images; the parent compares residual,
-per-particle norms and cotangent.  The two kernels do the same arithmetic per bin but accumulate the partial sums in a
+"""A/B of the kernel variants of the fused phase-retrieval guidance: register-resident butterflies (phase_colsreg.cuh,
+phase_rowsreg.cuh) against the shared-memory kernels they replace (DPSTTC_PHASE_COLS_REG / DPSTTC_PHASE_ROWS_REG = 0 / 1).
+One child process per variant (the switches are read once per process) runs dps_operator_guidance on the same seeded
+inputs for 256², 128² and 64² images; the parent compares residual, per-particle norms and cotangent of every variant
+with the all-shared-memory one.  The kernels do the same arithmetic per bin but accumulate the partial sums in a
 different order, so the comparison is to rounding, not bit for bit.
 
     python tools/phase_reg_check.py [--n 3]
@@ -54,24 +55,28 @@ def main():
         return
     os.makedirs(os.path.join(REPO, "gpurun_out"), exist_ok=True)
     outs = {}
-    for reg in ("0", "1"):
-        path = os.path.join(REPO, "gpurun_out", f"_phase_reg_{reg}.pt")
+    variants = ("00", "10", "01", "11")   # (columns, rows) in registers
+    for v in variants:
+        path = os.path.join(REPO, "gpurun_out", f"_phase_reg_{v}.pt")
         subprocess.run([sys.executable, os.path.abspath(__file__), "--n", str(a.n), "--child", path],
-                       env=dict(os.environ, DPSTTC_PHASE_COLS_REG=reg), check=True)
-        outs[reg] = torch.load(path)
+                       env=dict(os.environ, DPSTTC_PHASE_COLS_REG=v[0], DPSTTC_PHASE_ROWS_REG=v[1]), check=True)
+        outs[v] = torch.load(path)
         os.remove(path)
     ok = True
     for size in SIZES:
-        a0, a1 = outs["0"][size], outs["1"][size]
-        for key, tol in (("r", 2e-6), ("g", 2e-5), ("l2", 2e-6), ("l1", 2e-6)):
-            diff = (a0[key] - a1[key]).abs().max().item()
-            scale = max(1.0, a0[key].abs().max().item()) if key in ("r", "g") else a0[key].abs().max().item()
-            good = bool(torch.isfinite(a1[key]).all()) and diff <= tol * scale
-            ok &= good
-            print(f"[phase_reg_check] {size}x{size} n={a.n} {key}: max|smem - reg| = {diff:.3e} (scale {scale:.3e}, tol {tol:g}) "
-                  f"{'ok' if good else 'FAIL'}", flush=True)
-        ok &= a0["same_without_r"] and a1["same_without_r"]
-        print(f"[phase_reg_check] {size}x{size} with / without r_out bit-identical: smem={a0['same_without_r']} reg={a1['same_without_r']}")
+        a0 = outs["00"][size]
+        ok &= a0["same_without_r"]
+        for v in variants[1:]:
+            a1 = outs[v][size]
+            for key, tol in (("r", 2e-6), ("g", 2e-5), ("l2", 2e-6), ("l1", 2e-6)):
+                diff = (a0[key] - a1[key]).abs().max().item()
+                scale = max(1.0, a0[key].abs().max().item()) if key in ("r", "g") else a0[key].abs().max().item()
+                good = bool(torch.isfinite(a1[key]).all()) and diff <= tol * scale
+                ok &= good
+                print(f"[phase_reg_check] {size}x{size} n={a.n} cols/rows in registers = {v} {key}: max|smem - reg| = {diff:.3e} "
+                      f"(scale {scale:.3e}, tol {tol:g}) {'ok' if good else 'FAIL'}", flush=True)
+            ok &= a1["same_without_r"]
+            print(f"[phase_reg_check] {size}x{size} {v}: with / without r_out bit-identical: {a1['same_without_r']}")
     print("[phase_reg_check]", "PASS" if ok else "MISMATCH")
     sys.exit(0 if ok else 1)
 
