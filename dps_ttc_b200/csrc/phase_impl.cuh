@@ -511,12 +511,15 @@ __global__ void __launch_bounds__(kThreads, 4) phase_cols_fused(const FwdArgs fa
 // ---- K2'': the same column step with the butterflies in registers (phase_colsreg.cuh) -------------------------------------
 #include "phase_colsreg.cuh"
 
+#ifndef PHASE_COLS_MINB
+#define PHASE_COLS_MINB 3  // CTAs per SM the register column kernel is compiled for: 40 registers (24 bytes of spills at L = 384; 2: 56-64 registers); A/B on the B200: guidance 106.5 -> 102.4 us at N = 32
+#endif
 size_t smem_bytes_reg() { return sizeof(float2) * ((size_t)2 * kSeq * kLQ + kL + 64) + 64 * sizeof(float); }
 
 // table layout behind PhaseTables::tw (create()): [0, L) exp(−2πi j/L) · [L, L + 64) W64^{k·r} at [8r + k] · [L + 64, 2L + 64) the
 // full table rebuilt from the half table with twid()'s sign rule
 template <bool kOut>
-__global__ void __launch_bounds__(kT2, 2) phase_cols_fused_reg(const FwdArgs fa, const float2* __restrict__ tw_g, int C) {
+__global__ void __launch_bounds__(kT2, PHASE_COLS_MINB) phase_cols_fused_reg(const FwdArgs fa, const float2* __restrict__ tw_g, int C) {
   extern __shared__ __align__(16) float smem[];
   const int tid = threadIdx.x;
   // 1-D grid with the column group as the slowest index: the last group holds a single column (k2 = L/2) and its CTAs are
@@ -572,7 +575,7 @@ __global__ void __launch_bounds__(kT2, 2) phase_cols_fused_reg(const FwdArgs fa,
 // ---- K1'' / K3'': the row kernels of the fused path with the butterflies in registers (phase_rowsreg.cuh) -------------------
 #include "phase_rowsreg.cuh"
 #ifndef PHASE_ROWS_MINB
-#define PHASE_ROWS_MINB 2  // CTAs per SM the row kernels are compiled for (3: 40 registers, the loads of K3 in two batches)
+#define PHASE_ROWS_MINB 3  // CTAs per SM the row kernels are compiled for: 40 registers without spills (2: 48 / 56); A/B on the B200: guidance 111.8 -> 106.6 us at N = 32
 #endif
 
 __global__ void __launch_bounds__(kT2, PHASE_ROWS_MINB) phase_rows_fwd_reg(const FwdArgs fa, const float2* __restrict__ tw_g, int C) {
@@ -844,7 +847,7 @@ int guidance(const dps_operator* op, const dps_source& src, const float* y, int6
   fa.n = n;
   // row kernels: shared-memory stages (phase_rows_fwd / phase_rows_adj) or register-resident butterflies (phase_rowsreg.cuh);
   // DPSTTC_PHASE_ROWS_REG=0 / 1 overrides the built-in choice (read once per process)
-  constexpr bool kRowsRegDefault = false;
+  constexpr bool kRowsRegDefault = true;
   static const bool rows_reg = getenv("DPSTTC_PHASE_ROWS_REG") ? getenv("DPSTTC_PHASE_ROWS_REG")[0] != '0' : kRowsRegDefault;
   dim3 g1r((unsigned)(op->C * (kImg / kRowsReg)), (unsigned)n);
   dim3 g1((unsigned)(op->C * (kImg / kRowsPerCta)), (unsigned)n);
@@ -856,7 +859,7 @@ int guidance(const dps_operator* op, const dps_source& src, const float* y, int6
   dim3 g2((unsigned)(op->C * kColGroups), (unsigned)n);
   // column step: shared-memory stages (phase_cols_fused) or register-resident butterflies (phase_colsreg.cuh);
   // DPSTTC_PHASE_COLS_REG=0 / 1 overrides the built-in choice (read once per process)
-  constexpr bool kRegDefault = false;
+  constexpr bool kRegDefault = true;  // gated on the B200: profiles/r5a_phase_reg_check.log, r5b_*, r5c_*
   static const bool reg = getenv("DPSTTC_PHASE_COLS_REG") ? getenv("DPSTTC_PHASE_COLS_REG")[0] != '0' : kRegDefault;
   const dim3 g2r((unsigned)(op->C * kColGroups * n));
   if (reg && r_out)
