@@ -26,6 +26,20 @@
 // shared-memory kernel to the last bit up to FMA contraction; the partial sums are accumulated in a different order.
 // Every function below is one barrier-free phase of the kernel taking the thread index as an argument:
 // tests/emu/phase_cols_emu.cpp runs the same phases thread by thread on the CPU against a plain DFT (index logic check).
+#ifndef PHASE_PACKED
+#define PHASE_PACKED 0  // 1: packed fp32 arithmetic (FADD2 / FMUL2 / FFMA2) in the butterflies, twiddles as (w, −i·w) quadruples
+#endif
+#if PHASE_PACKED
+typedef float4 tw_t;  // (w.x, w.y, −w.y, w.x)
+DPS_DEV float2 cr_cmul(float2 a, float4 w) { return cmul_tw(a, w); }
+DPS_DEV void cr_dft8(float2* v) { dft8p(v); }
+DPS_DEV void cr_dft_last(float2* v) { dft_last_p(v); }
+#else
+typedef float2 tw_t;
+DPS_DEV float2 cr_cmul(float2 a, float2 w) { return cmul(a, w); }
+DPS_DEV void cr_dft8(float2* v) { dft8(v); }
+DPS_DEV void cr_dft_last(float2* v) { dft_last(v); }
+#endif
 constexpr int kT2 = 512;
 constexpr int kSeq = 8;
 constexpr int kJ = kSeq * kL8;                                   // 384 / 256 / 192 threads in the J role
@@ -36,8 +50,8 @@ static_assert(kLQ % 16 == 2 && kLQ > kL - 1 + (kL - 1) / 8, "sequence stride");
 struct ColsCtx {
   float2* A;
   float2* B;
-  const float2* tw;   // exp(−2πi j/L), j < L (full table: the upper half is −tw[j − L/2], the rule of twid())
-  const float2* w64;  // W64^{k·r} at [r·8 + k]
+  const tw_t* tw;     // exp(−2πi j/L), j < L (full table: the upper half is −tw[j − L/2], the rule of twid())
+  const tw_t* w64;    // W64^{k·r} at [r·8 + k]
   const float2* rt;   // Rt[k2][row] of this plane
   const float* y;     // measurement plane (L×L), never null (dps_operator_guidance requires it)
   float* outp;        // residual plane (L×L) or null
@@ -83,13 +97,13 @@ DPS_DEV void cr_stage_a(int tid, ColsRegs& R, float2* dstbuf, int nseq = kSeq) {
   if (tid >= kJ) return;
   const int f = tid / kL8, j = tid - f * kL8;
   if (f >= nseq) return;
-  dft8(R.v);
+  cr_dft8(R.v);
   float2* dst = dstbuf + f * kLQ + 9 * j;
 #pragma unroll
   for (int r = 0; r < 8; ++r) dst[r] = R.v[r];
 }
 // J role, stage 2 (R = 8, Ns = 8): twiddle W64^{k·r}, k = j & 7;  out[64·(j>>3) + k + 8r];  P(·) = 72·(j>>3) + k + 9r
-DPS_DEV void cr_stage_b(int tid, ColsRegs& R, const float2* srcbuf, float2* dstbuf, const float2* w64, int nseq = kSeq) {
+DPS_DEV void cr_stage_b(int tid, ColsRegs& R, const float2* srcbuf, float2* dstbuf, const tw_t* w64, int nseq = kSeq) {
   if (tid >= kJ) return;
   const int f = tid / kL8, j = tid - f * kL8;
   if (f >= nseq) return;
@@ -98,23 +112,23 @@ DPS_DEV void cr_stage_b(int tid, ColsRegs& R, const float2* srcbuf, float2* dstb
 #pragma unroll
   for (int r = 0; r < 8; ++r) {
     R.v[r] = src[kS8 * r];
-    if (r) R.v[r] = cmul(R.v[r], w64[8 * r + k]);
+    if (r) R.v[r] = cr_cmul(R.v[r], w64[8 * r + k]);
   }
-  dft8(R.v);
+  cr_dft8(R.v);
   float2* dst = dstbuf + f * kLQ + 72 * (j >> 3) + k;
 #pragma unroll
   for (int r = 0; r < 8; ++r) dst[9 * r] = R.v[r];
 }
 // F role, stage 3 (R = L/64, Ns = 64): twiddle exp(−2πi·j·r/L); the thread ends up with bins j + 64r in natural order
-DPS_DEV void cr_stage_c(int tid, float2* v, const float2* srcbuf, const float2* tw) {
+DPS_DEV void cr_stage_c(int tid, float2* v, const float2* srcbuf, const tw_t* tw) {
   const int f = tid & 7, j = tid >> 3;
   const float2* src = srcbuf + f * kLQ + P(j);  // P(j + 64r) = P(j) + 72r
 #pragma unroll
   for (int r = 0; r < kR3; ++r) {
     v[r] = src[72 * r];
-    if (r) v[r] = cmul(v[r], tw[j * r]);
+    if (r) v[r] = cr_cmul(v[r], tw[j * r]);
   }
-  dft_last(v);
+  cr_dft_last(v);
 }
 // F role: the measurement at the direct output position shift(k1, k2) and at the mirror shift(−k1, −k2) of the thread's bins
 DPS_DEV void cr_yload(int tid, ColsY& Y, const ColsCtx& c) {

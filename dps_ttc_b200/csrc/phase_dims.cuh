@@ -31,6 +31,12 @@ DPS_DEV void dft_last(float2* v) {
   else dft3(v[0], v[1], v[2]);
 }
 
+DPS_DEV void dft_last_p(float2* v) {  // packed variant (phase_math.cuh)
+  if constexpr (kR3 == 6) dft6p(v);
+  else if constexpr (kR3 == 4) dft4p(v);
+  else dft3p(v[0], v[1], v[2]);
+}
+
 // Twiddle exp(−2πi j/384), j ∈ [0,384), from the half table in shared memory: tw[j+192] = −tw[j].  Halving the table
 // (1.5 KB instead of 3 KB) is what lets FOUR 8-sequence CTAs (57 KB each) share an SM instead of three.
 constexpr int kTW = kL / 2;

@@ -514,7 +514,20 @@ __global__ void __launch_bounds__(kThreads, 4) phase_cols_fused(const FwdArgs fa
 #ifndef PHASE_COLS_MINB
 #define PHASE_COLS_MINB 3  // CTAs per SM the register column kernel is compiled for: 40 registers (24 bytes of spills at L = 384; 2: 56-64 registers); A/B on the B200: guidance 106.5 -> 102.4 us at N = 32
 #endif
-size_t smem_bytes_reg() { return sizeof(float2) * ((size_t)2 * kSeq * kLQ + kL + 64) + 64 * sizeof(float); }
+size_t smem_bytes_reg() { return sizeof(float2) * ((size_t)2 * kSeq * kLQ) + sizeof(tw_t) * (kL + 64) + 64 * sizeof(float); }
+// tables of the register kernels in shared memory: [tw: L entries][w64: 64 entries] behind the two exchange buffers
+DPS_DEV void reg_tables(float* smem, const float2* tw_g, int tid, const tw_t*& tw, const tw_t*& w64, float*& red) {
+  tw_t* t = reinterpret_cast<tw_t*>(reinterpret_cast<float2*>(smem) + 2 * kSeq * kLQ);
+  constexpr int kF = sizeof(tw_t) / sizeof(float);  // floats per entry
+  // PhaseTables::tw (create()): [0, L) exp(−2πi j/L) · [L, L+64) W64^{k·r} at [8r+k] · [L+64, 2L+64) the full table rebuilt from the
+  // half table with twid()'s sign rule · then the same two tables as (w.x, w.y, −w.y, w.x) quadruples: [64][L]
+  const float* src = PHASE_PACKED ? reinterpret_cast<const float*>(tw_g + 2 * kL + 64) : reinterpret_cast<const float*>(tw_g + kL);
+  stage_async(reinterpret_cast<float*>(t + kL), src, kF * 64, tid, kT2);
+  stage_async(reinterpret_cast<float*>(t), src + kF * 64, kF * kL, tid, kT2);
+  tw = t;
+  w64 = t + kL;
+  red = reinterpret_cast<float*>(t + kL + 64);
+}
 
 // table layout behind PhaseTables::tw (create()): [0, L) exp(−2πi j/L) · [L, L + 64) W64^{k·r} at [8r + k] · [L + 64, 2L + 64) the
 // full table rebuilt from the half table with twid()'s sign rule
@@ -530,19 +543,14 @@ __global__ void __launch_bounds__(kT2, PHASE_COLS_MINB) phase_cols_fused_reg(con
   ColsCtx cx;
   cx.A = reinterpret_cast<float2*>(smem);
   cx.B = cx.A + kSeq * kLQ;
-  float2* tw = cx.B + kSeq * kLQ;
-  float2* w64 = tw + kL;
-  float* red = reinterpret_cast<float*>(w64 + 64);
-  cx.tw = tw;
-  cx.w64 = w64;
+  float* red;
+  reg_tables(smem, tw_g, tid, cx.tw, cx.w64, red);
   cx.k20 = grp * kColsPerCta;
   cx.ncols = min(kColsPerCta, kHalf - cx.k20);
   cx.rt = aux_scratch(fa.aux, n, C, c);
   cx.y = fa.y + n * fa.y_stride + (int64_t)c * kL * kL;
   cx.outp = kOut ? fa.out + ((int64_t)n * C + c) * kL * kL : nullptr;
   cx.t = aux_scratch2(fa.aux, n, C, c);
-  stage_async(reinterpret_cast<float*>(tw), reinterpret_cast<const float*>(tw_g + kL + 64), 2 * kL, tid, kT2);
-  stage_async(reinterpret_cast<float*>(w64), reinterpret_cast<const float*>(tw_g + kL), 2 * 64, tid, kT2);
   ColsRegs R;
   ColsY Y;
   R.sq = R.ab = 0.f;
@@ -586,10 +594,8 @@ __global__ void __launch_bounds__(kT2, PHASE_ROWS_MINB) phase_rows_fwd_reg(const
   RowsFwdCtx cx;
   cx.A = reinterpret_cast<float2*>(smem);
   cx.B = cx.A + kSeq * kLQ;
-  float2* tw = cx.B + kSeq * kLQ;
-  float2* w64 = tw + kL;
-  cx.tw = tw;
-  cx.w64 = w64;
+  float* red;
+  reg_tables(smem, tw_g, tid, cx.tw, cx.w64, red);
   const int64_t plane = (int64_t)c * kImg * kImg;
   cx.x = fa.src.x + n * fa.src.x_stride + plane;
   cx.eps = fa.src.eps + n * fa.src.eps_stride + plane;
@@ -599,8 +605,6 @@ __global__ void __launch_bounds__(kT2, PHASE_ROWS_MINB) phase_rows_fwd_reg(const
   cx.maskb = aux_mask(fa.aux, n, C, c);
   cx.rt = aux_scratch(fa.aux, n, C, c);
   cx.r0 = grp * kRowsReg;
-  stage_async(reinterpret_cast<float*>(tw), reinterpret_cast<const float*>(tw_g + kL + 64), 2 * kL, tid, kT2);
-  stage_async(reinterpret_cast<float*>(w64), reinterpret_cast<const float*>(tw_g + kL), 2 * 64, tid, kT2);
   ColsRegs R;
   rf_load(tid, R, cx);
   cr_stage_a(tid, R, cx.A);
@@ -622,17 +626,13 @@ __global__ void __launch_bounds__(kT2, PHASE_ROWS_MINB) phase_rows_adj_reg(const
   RowsAdjCtx cx;
   cx.A = reinterpret_cast<float2*>(smem);
   cx.B = cx.A + kSeq * kLQ;
-  float2* tw = cx.B + kSeq * kLQ;
-  float2* w64 = tw + kL;
-  cx.tw = tw;
-  cx.w64 = w64;
+  float* red;
+  reg_tables(smem, tw_g, tid, cx.tw, cx.w64, red);
   cx.t = aux_scratch2(const_cast<float*>(aux_r), n, C, c);
   cx.maskb = aux_mask(const_cast<float*>(aux_r), n, C, c);
   cx.g = aa.g + n * aa.g_stride + (int64_t)c * kImg * kImg;
   cx.coef = (aa.coef ? aa.coef[n] : 1.0f) * (1.0f / (float)kL);
   cx.r0 = grp * kRowsReg;
-  stage_async(reinterpret_cast<float*>(tw), reinterpret_cast<const float*>(tw_g + kL + 64), 2 * kL, tid, kT2);
-  stage_async(reinterpret_cast<float*>(w64), reinterpret_cast<const float*>(tw_g + kL), 2 * 64, tid, kT2);
   ColsRegs R;
   RowsMask M;
   ra_load(tid, R, cx);
@@ -779,6 +779,12 @@ int create(dps_operator* op) {
       tw.push_back(j >= kTW ? make_float2(-tw[j - kTW].x, -tw[j - kTW].y) : tw[j]);
     }
   for (int j = 0; j < kL; ++j) tw.push_back(j >= kTW ? make_float2(-tw[j - kTW].x, -tw[j - kTW].y) : tw[j]);
+  // the same two tables as (w.x, w.y, −w.y, w.x) quadruples for the packed twiddle product (PHASE_PACKED): [64][L]
+  for (int j = 0; j < 64 + kL; ++j) {
+    const float2 w = tw[kL + j];
+    tw.push_back(w);
+    tw.push_back(make_float2(-w.y, w.x));
+  }
   DPS_CUDA(cudaMalloc(&t->tw, sizeof(float2) * tw.size()));
   DPS_CUDA(cudaMemcpy(t->tw, tw.data(), sizeof(float2) * tw.size(), cudaMemcpyHostToDevice));
   if (int rc = set_smem((const void*)phase_rows_fwd<false>, smem_bytes(kRowsPerCta / 2))) return rc;

@@ -13,8 +13,8 @@
 struct RowsFwdCtx {
   float2* A;
   float2* B;
-  const float2* tw;      // full table (see ColsCtx)
-  const float2* w64;
+  const tw_t* tw;        // full table (see ColsCtx)
+  const tw_t* w64;
   const float* x;        // plane of this particle and channel (H×H)
   const float* eps;      // plane, never null (guidance forms x̂₀ from x and ε)
   float c1, c2;
@@ -64,15 +64,15 @@ DPS_DEV void rf_load(int tid, ColsRegs& R, const RowsFwdCtx& c) {
   }
 }
 // K1 / K3, G role: last stage (R = L/64, Ns = 64) of sequence tid >> 6, bins (tid & 63) + 64r in natural order
-DPS_DEV void rr_stage_c(int tid, float2* v, const float2* srcbuf, const float2* tw) {
+DPS_DEV void rr_stage_c(int tid, float2* v, const float2* srcbuf, const tw_t* tw) {
   const int f = tid >> 6, j = tid & 63;
   const float2* src = srcbuf + f * kLQ + P(j);
 #pragma unroll
   for (int r = 0; r < kR3; ++r) {
     v[r] = src[72 * r];
-    if (r) v[r] = cmul(v[r], tw[j * r]);
+    if (r) v[r] = cr_cmul(v[r], tw[j * r]);
   }
-  dft_last(v);
+  cr_dft_last(v);
 }
 // K1, G role: spectrum Z of the packed row pair back into a buffer, natural order
 DPS_DEV void rf_spectrum(int tid, ColsRegs& R, const RowsFwdCtx& c) {
@@ -105,8 +105,8 @@ static_assert(kSeq == 8, "rf_split_store: i & 7");
 struct RowsAdjCtx {
   float2* A;
   float2* B;
-  const float2* tw;
-  const float2* w64;
+  const tw_t* tw;
+  const tw_t* w64;
   const float2* t;             // T[row][k2] of the plane, row stride L/2 + 1
   const unsigned char* maskb;  // clamp-pass bytes of the plane
   float* g;                    // cotangent plane (H×H)

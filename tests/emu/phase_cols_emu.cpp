@@ -3,7 +3,7 @@
 // intrinsics host shims, includes the very same headers and runs the phases thread by thread (a loop over tid stands for
 // the CTA, the end of each loop for __syncthreads) for every column group of one plane.  It checks the index logic of the
 // register-resident FFT (thread roles, Stockham maps, exchange layout, output positions) where no GPU is available;
-// tests/test_phase_cols_emu.py compares the result with a plain numpy DFT.  Built by the test with
+// tests/test_phase_emu.py compares the result with a plain numpy DFT.  Built by the test with
 //   g++ -O1 -shared -fPIC -DPHASE_R3={6,4,3} -I dps_ttc_b200/csrc
 #include <cmath>
 #include <cstdint>
@@ -11,8 +11,14 @@
 #include <vector>
 
 struct float2 { float x, y; };
+struct float4 { float x, y, z, w; };
 static inline float2 make_float2(float x, float y) { return float2{x, y}; }
+static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 #define DPS_DEV static inline
+// packed fp32 intrinsics of sm_100 (PHASE_PACKED builds): componentwise, every product / sum rounded as on the device
+static inline float2 __fadd2_rn(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+static inline float2 __fmul2_rn(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+static inline float2 __ffma2_rn(float2 a, float2 b, float2 c) { return make_float2(std::fmaf(a.x, b.x, c.x), std::fmaf(a.y, b.y, c.y)); }
 static inline float emu_rsqrtf(float x) { return 1.0f / std::sqrt(x); }
 #define rsqrtf emu_rsqrtf
 static inline float __fsub_rn(float a, float b) { return a - b; }
@@ -26,6 +32,32 @@ static inline void stg_stream2(float* p, const float2& v) { p[0] = v.x; p[1] = v
 #include "phase_dims.cuh"
 #include "phase_colsreg.cuh"
 
+
+// twiddle tables exactly as ph*::create builds them (float2 entries, or (w.x, w.y, −w.y, w.x) quadruples under PHASE_PACKED)
+static inline tw_t emu_tw_entry(float2 w) {
+#if PHASE_PACKED
+  return make_float4(w.x, w.y, -w.y, w.x);
+#else
+  return w;
+#endif
+}
+struct EmuTables {
+  std::vector<tw_t> twf, w64;
+  EmuTables() : twf(kL), w64(64) {
+    std::vector<float2> tw(kL);
+    for (int j = 0; j < kL; ++j) {
+      const double a = -2.0 * M_PI * j / kL;
+      tw[j] = make_float2((float)cos(a), (float)sin(a));
+    }
+    for (int r = 0; r < 8; ++r)
+      for (int k = 0; k < 8; ++k) {
+        const int j = kR3 * k * r;
+        w64[8 * r + k] = emu_tw_entry(j >= kTW ? make_float2(-tw[j - kTW].x, -tw[j - kTW].y) : tw[j]);
+      }
+    for (int j = 0; j < kL; ++j) twf[j] = emu_tw_entry(j >= kTW ? make_float2(-tw[j - kTW].x, -tw[j - kTW].y) : tw[j]);
+  }
+};
+
 extern "C" int emu_dims(int* out) {
   out[0] = kL; out[1] = kImg; out[2] = kHalf; out[3] = kColGroups;
   return 0;
@@ -34,20 +66,7 @@ extern "C" int emu_dims(int* out) {
 // rt: Rt[k2][row] (kHalf × kImg complex), y: L×L, r_out: L×L or null, t: T[row][k2] (kImg × kHalf complex),
 // partials: kColGroups × 2
 extern "C" int emu_cols(const float* rt, const float* y, float* r_out, float* t, float* partials) {
-  // tables exactly as ph*::create builds them
-  std::vector<float2> tw(kL);
-  for (int j = 0; j < kL; ++j) {
-    const double a = -2.0 * M_PI * j / kL;
-    tw[j] = make_float2((float)cos(a), (float)sin(a));
-  }
-  std::vector<float2> w64(64);
-  for (int r = 0; r < 8; ++r)
-    for (int k = 0; k < 8; ++k) {
-      const int j = kR3 * k * r;
-      w64[8 * r + k] = j >= kTW ? make_float2(-tw[j - kTW].x, -tw[j - kTW].y) : tw[j];
-    }
-  std::vector<float2> twf(kL);
-  for (int j = 0; j < kL; ++j) twf[j] = j >= kTW ? make_float2(-tw[j - kTW].x, -tw[j - kTW].y) : tw[j];
+  EmuTables T;
   std::vector<float2> A(kSeq * kLQ), B(kSeq * kLQ);
   std::vector<ColsRegs> R(kT2);
   std::vector<ColsY> Y(kT2);
@@ -58,8 +77,8 @@ extern "C" int emu_cols(const float* rt, const float* y, float* r_out, float* t,
     ColsCtx cx;
     cx.A = A.data();
     cx.B = B.data();
-    cx.tw = twf.data();
-    cx.w64 = w64.data();
+    cx.tw = T.twf.data();
+    cx.w64 = T.w64.data();
     cx.k20 = grp * kColsPerCta;
     cx.ncols = kColsPerCta < kHalf - cx.k20 ? kColsPerCta : kHalf - cx.k20;
     cx.rt = reinterpret_cast<const float2*>(rt);

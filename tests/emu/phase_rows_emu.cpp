@@ -12,6 +12,10 @@ struct float4 { float x, y, z, w; };
 static inline float2 make_float2(float x, float y) { return float2{x, y}; }
 static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 #define DPS_DEV static inline
+// packed fp32 intrinsics of sm_100 (PHASE_PACKED builds): componentwise, every product / sum rounded as on the device
+static inline float2 __fadd2_rn(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+static inline float2 __fmul2_rn(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+static inline float2 __ffma2_rn(float2 a, float2 b, float2 c) { return make_float2(std::fmaf(a.x, b.x, c.x), std::fmaf(a.y, b.y, c.y)); }
 static inline float emu_rsqrtf(float x) { return 1.0f / std::sqrt(x); }
 #define rsqrtf emu_rsqrtf
 static inline float __fsub_rn(float a, float b) { return a - b; }
@@ -34,10 +38,18 @@ static inline float clamp_pass(float pre) { return (pre >= -1.0f && pre <= 1.0f)
 #include "phase_colsreg.cuh"
 #include "phase_rowsreg.cuh"
 
-namespace {
-struct Tables {
-  std::vector<float2> twf, w64;
-  Tables() : twf(kL), w64(64) {
+
+// twiddle tables exactly as ph*::create builds them (float2 entries, or (w.x, w.y, −w.y, w.x) quadruples under PHASE_PACKED)
+static inline tw_t emu_tw_entry(float2 w) {
+#if PHASE_PACKED
+  return make_float4(w.x, w.y, -w.y, w.x);
+#else
+  return w;
+#endif
+}
+struct EmuTables {
+  std::vector<tw_t> twf, w64;
+  EmuTables() : twf(kL), w64(64) {
     std::vector<float2> tw(kL);
     for (int j = 0; j < kL; ++j) {
       const double a = -2.0 * M_PI * j / kL;
@@ -46,11 +58,13 @@ struct Tables {
     for (int r = 0; r < 8; ++r)
       for (int k = 0; k < 8; ++k) {
         const int j = kR3 * k * r;
-        w64[8 * r + k] = j >= kTW ? make_float2(-tw[j - kTW].x, -tw[j - kTW].y) : tw[j];
+        w64[8 * r + k] = emu_tw_entry(j >= kTW ? make_float2(-tw[j - kTW].x, -tw[j - kTW].y) : tw[j]);
       }
-    for (int j = 0; j < kL; ++j) twf[j] = j >= kTW ? make_float2(-tw[j - kTW].x, -tw[j - kTW].y) : tw[j];
+    for (int j = 0; j < kL; ++j) twf[j] = emu_tw_entry(j >= kTW ? make_float2(-tw[j - kTW].x, -tw[j - kTW].y) : tw[j]);
   }
 };
+namespace {
+typedef EmuTables Tables;
 void poison(std::vector<float2>& b) { for (auto& e : b) e = make_float2(NAN, NAN); }
 }  // namespace
 

@@ -15,19 +15,20 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _build(r3, tmp_path, which="cols"):
+def _build(r3, tmp_path, which="cols", packed=0):
     if shutil.which("g++") is None:
         pytest.skip("g++ not available")
-    so = str(tmp_path / f"phase_{which}_emu_{r3}.so")
-    subprocess.run(["g++", "-O1", "-ffp-contract=off", "-shared", "-fPIC", f"-DPHASE_R3={r3}", "-I",
+    so = str(tmp_path / f"phase_{which}_emu_{r3}_{packed}.so")
+    subprocess.run(["g++", "-O1", "-ffp-contract=off", "-shared", "-fPIC", f"-DPHASE_R3={r3}", f"-DPHASE_PACKED={packed}", "-I",
                     os.path.join(ROOT, "dps_ttc_b200", "csrc"), "-o", so,
                     os.path.join(ROOT, "tests", "emu", f"phase_{which}_emu.cpp")], check=True)
     return C.CDLL(so)
 
 
+@pytest.mark.parametrize("packed", [0, 1])
 @pytest.mark.parametrize("r3,want_r", [(6, True), (4, True), (3, True), (6, False)])
-def test_register_column_kernel_matches_numpy_dft(r3, want_r, tmp_path):
-    lib = _build(r3, tmp_path)
+def test_register_column_kernel_matches_numpy_dft(r3, want_r, packed, tmp_path):
+    lib = _build(r3, tmp_path, packed=packed)
     dims = (C.c_int * 4)()
     lib.emu_dims(dims)
     L, img, half, groups = list(dims)
@@ -80,11 +81,12 @@ def test_register_column_kernel_matches_numpy_dft(r3, want_r, tmp_path):
     assert np.abs(t - T).max() <= 2e-5 * np.abs(T).max()
 
 
+@pytest.mark.parametrize("packed", [0, 1])
 @pytest.mark.parametrize("r3,clip", [(6, True), (4, True), (3, False)])
-def test_register_row_kernels_match_numpy_dft(r3, clip, tmp_path):
+def test_register_row_kernels_match_numpy_dft(r3, clip, packed, tmp_path):
     """K1 (x, ε → x̂₀ → half spectrum of every image row, two rows per complex FFT, + clamp-pass bytes) and K3 (Hermitian half
     rows → real rows × coefficient × clamp mask) of phase_rowsreg.cuh, emulated thread by thread."""
-    lib = _build(r3, tmp_path, "rows")
+    lib = _build(r3, tmp_path, "rows", packed=packed)
     dims = (C.c_int * 4)()
     lib.emu_dims(dims)
     L, img, half, groups = list(dims)
