@@ -187,6 +187,44 @@ DPS_DEV void cr_epilogue(int tid, ColsRegs& R, const ColsY& Y, const ColsCtx& c)
     dst[72 * r] = make_float2(gs * (F.x * inv), gs * (-F.y * inv));  // the association of phase_cols_fused: same bits
   }
 }
+// F role, forward (two-kernel) path: last stage, |F|/L, the output y − |F|/L (or |F|/L itself) at both mirrored positions, partial
+// sums, and the unit phase conj(F)/|F| → ph[k2][k1] for the adjoint's column kernel (32-byte runs: 8 lanes = 8 columns, 4 bins each)
+template <bool kHasY>
+DPS_DEV void cr_fwd_epilogue(int tid, ColsRegs& R, const ColsY& Y, const ColsCtx& c, float2* ph) {
+  cr_stage_c(tid, R.v, c.B, c.tw);
+  const int f = tid & 7, j = tid >> 3;
+  const int k2 = c.k20 + f;
+  const bool act = f < c.ncols, mir = act && k2 > 0 && k2 < kL / 2;
+  const int c1 = shift_idx(k2), c2 = shift_idx(k2 ? kL - k2 : 0);
+  const float inv_l = 1.0f / (float)kL;
+  float2* php = ph + (int64_t)k2 * kL + j;
+#pragma unroll
+  for (int r = 0; r < kR3; ++r) {
+    const int k1 = j + 64 * r;
+    const float2 F = R.v[r];
+    const float m2 = fmaf(F.x, F.x, F.y * F.y);
+    float q = rsqrtf(m2);
+    q = fmaf(q, fmaf(-0.5f * m2 * q, q, 0.5f), q);
+    float mag = m2 * q;
+    mag = fmaf(fmaf(-mag, mag, m2), 0.5f * q, mag);
+    const bool nz = m2 > 0.f;
+    const float inv = nz ? q : 0.f;
+    const float a = nz ? mag * inv_l : 0.f;
+    const float r1 = kHasY ? __fsub_rn(Y.y1[r], a) : a;
+    const float r2 = kHasY ? __fsub_rn(Y.y2[r], a) : a;
+    if (act) {
+      stg_stream2(reinterpret_cast<float*>(php + 64 * r), make_float2(F.x * inv, -F.y * inv));
+      R.sq = fmaf(r1, r1, R.sq);
+      R.ab += fabsf(r1);
+      if (c.outp) stg_stream(c.outp + shift_idx(k1) * kL + c1, r1);
+    }
+    if (mir) {
+      R.sq = fmaf(r2, r2, R.sq);
+      R.ab += fabsf(r2);
+      if (c.outp) stg_stream(c.outp + shift_idx(k1 ? kL - k1 : 0) * kL + c2, r2);
+    }
+  }
+}
 // F role: last stage of the second transform; padded rows 64 .. 64 + H − 1 go to T[row][k2] (row stride L/2 + 1)
 DPS_DEV void cr_store(int tid, ColsRegs& R, const ColsCtx& c) {
   cr_stage_c(tid, R.v, c.A, c.tw);

@@ -580,13 +580,53 @@ __global__ void __launch_bounds__(kT2, PHASE_COLS_MINB) phase_cols_fused_reg(con
   cr_store(tid, R, cx);
 }
 
+// forward (two-kernel) path: one column transform, output y − |F|/L (or |F|/L), partial sums, unit phase → aux for the adjoint
+template <bool kHasY>
+__global__ void __launch_bounds__(kT2, PHASE_COLS_MINB) phase_cols_fwd_reg(const FwdArgs fa, const float2* __restrict__ tw_g, int C) {
+  extern __shared__ __align__(16) float smem[];
+  const int tid = threadIdx.x;
+  const int planes = fa.n * C;
+  const int grp = blockIdx.x / planes, pc = blockIdx.x - grp * planes;
+  const int n = pc / C, c = pc - n * C;
+  ColsCtx cx;
+  cx.A = reinterpret_cast<float2*>(smem);
+  cx.B = cx.A + kSeq * kLQ;
+  float* red;
+  reg_tables(smem, tw_g, tid, cx.tw, cx.w64, red);
+  cx.k20 = grp * kColsPerCta;
+  cx.ncols = min(kColsPerCta, kHalf - cx.k20);
+  cx.rt = aux_scratch(fa.aux, n, C, c);
+  cx.y = kHasY ? fa.y + n * fa.y_stride + (int64_t)c * kL * kL : nullptr;
+  cx.outp = fa.out ? fa.out + ((int64_t)n * C + c) * kL * kL : nullptr;
+  cx.t = nullptr;
+  ColsRegs R;
+  ColsY Y;
+  R.sq = R.ab = 0.f;
+  cr_load(tid, R, cx);
+  cr_stage_a(tid, R, cx.A, cx.ncols);
+  stage_wait();
+  __syncthreads();
+  if constexpr (kHasY) cr_yload(tid, Y, cx);
+  cr_stage_b(tid, R, cx.A, cx.B, cx.w64, cx.ncols);
+  __syncthreads();
+  cr_fwd_epilogue<kHasY>(tid, R, Y, cx, aux_phase(fa.aux, n, C, c));
+  if (fa.partials) {
+    block_sum2(R.sq, R.ab, red);
+    if (tid == 0) {
+      float* pp = fa.partials + ((int64_t)n * (C * kColGroups) + c * kColGroups + grp) * 2;
+      pp[0] = R.sq;
+      pp[1] = R.ab;
+    }
+  }
+}
+
 // ---- K1'' / K3'': the row kernels of the fused path with the butterflies in registers (phase_rowsreg.cuh) -------------------
 #include "phase_rowsreg.cuh"
 #ifndef PHASE_ROWS_MINB
 #define PHASE_ROWS_MINB 3  // CTAs per SM the row kernels are compiled for: 40 registers without spills (2: 48 / 56); A/B on the B200: guidance 111.8 -> 106.6 us at N = 32
 #endif
 
-__global__ void __launch_bounds__(kT2, PHASE_ROWS_MINB) phase_rows_fwd_reg(const FwdArgs fa, const float2* __restrict__ tw_g, int C) {
+__global__ void __launch_bounds__(kT2, PHASE_ROWS_MINB) phase_rows_fwd_reg(const FwdArgs fa, const float2* __restrict__ tw_g, int C, int mask_out) {
   extern __shared__ __align__(16) float smem[];
   const int tid = threadIdx.x;
   constexpr int groups = kImg / kRowsReg;
@@ -598,11 +638,11 @@ __global__ void __launch_bounds__(kT2, PHASE_ROWS_MINB) phase_rows_fwd_reg(const
   reg_tables(smem, tw_g, tid, cx.tw, cx.w64, red);
   const int64_t plane = (int64_t)c * kImg * kImg;
   cx.x = fa.src.x + n * fa.src.x_stride + plane;
-  cx.eps = fa.src.eps + n * fa.src.eps_stride + plane;
+  cx.eps = fa.src.eps ? fa.src.eps + n * fa.src.eps_stride + plane : nullptr;
   cx.c1 = fa.src.c1;
   cx.c2 = fa.src.c2;
   cx.clip = fa.src.clip;
-  cx.maskb = aux_mask(fa.aux, n, C, c);
+  cx.maskb = mask_out ? aux_mask(fa.aux, n, C, c) : nullptr;
   cx.rt = aux_scratch(fa.aux, n, C, c);
   cx.r0 = grp * kRowsReg;
   ColsRegs R;
@@ -793,6 +833,8 @@ int create(dps_operator* op) {
   if (int rc = set_smem((const void*)phase_rows_fwd_reg, smem_bytes_reg())) return rc;
   if (int rc = set_smem((const void*)phase_rows_adj_reg, smem_bytes_reg())) return rc;
   if (int rc = set_smem((const void*)phase_cols_fused_reg<false>, smem_bytes_reg())) return rc;
+  if (int rc = set_smem((const void*)phase_cols_fwd_reg<false>, smem_bytes_reg())) return rc;
+  if (int rc = set_smem((const void*)phase_cols_fwd_reg<true>, smem_bytes_reg())) return rc;
   if (int rc = set_smem((const void*)phase_cols_fused_reg<true>, smem_bytes_reg())) return rc;
   if (int rc = set_smem((const void*)phase_cols_fwd<false>, smem_bytes(kColsPerCta))) return rc;
   if (int rc = set_smem((const void*)phase_cols_fwd<true>, smem_bytes(kColsPerCta))) return rc;
@@ -811,6 +853,22 @@ int create(dps_operator* op) {
 int forward(const dps_operator* op, const FwdArgs& a, cudaStream_t st) {
   DPS_REQUIRE(a.aux, DPS_ERR_INVALID, "phase retrieval forward needs the aux workspace (%lld floats per particle)",
               (long long)op->aux_floats);
+  // register-resident kernels (phase_rowsreg.cuh, phase_colsreg.cuh) for the forward pass of the two-kernel path;
+  // DPSTTC_PHASE_FWD_REG=0 / 1 overrides the built-in choice (read once per process)
+  constexpr bool kFwdRegDefault = false;
+  static const bool fwd_reg = getenv("DPSTTC_PHASE_FWD_REG") ? getenv("DPSTTC_PHASE_FWD_REG")[0] != '0' : kFwdRegDefault;
+  if (fwd_reg) {
+    dim3 g1r((unsigned)(op->C * (kImg / kRowsReg)), (unsigned)a.n);
+    phase_rows_fwd_reg<<<g1r, kT2, smem_bytes_reg(), st>>>(a, op->phase->tw, op->C, 0);
+    DPS_LAUNCH_CHECK("phase_rows_fwd");
+    const dim3 g2r((unsigned)(op->C * kColGroups * a.n));
+    if (a.y)
+      phase_cols_fwd_reg<true><<<g2r, kT2, smem_bytes_reg(), st>>>(a, op->phase->tw, op->C);
+    else
+      phase_cols_fwd_reg<false><<<g2r, kT2, smem_bytes_reg(), st>>>(a, op->phase->tw, op->C);
+    DPS_LAUNCH_CHECK("phase_cols_fwd");
+    return DPS_OK;
+  }
   dim3 g1((unsigned)(op->C * (kImg / kRowsPerCta)), (unsigned)a.n);
   phase_rows_fwd<false><<<g1, kThreads, smem_bytes(kRowsPerCta / 2), st>>>(a, op->phase->tw, op->C);
   DPS_LAUNCH_CHECK("phase_rows_fwd");
@@ -858,7 +916,7 @@ int guidance(const dps_operator* op, const dps_source& src, const float* y, int6
   dim3 g1r((unsigned)(op->C * (kImg / kRowsReg)), (unsigned)n);
   dim3 g1((unsigned)(op->C * (kImg / kRowsPerCta)), (unsigned)n);
   if (rows_reg)
-    phase_rows_fwd_reg<<<g1r, kT2, smem_bytes_reg(), st>>>(fa, op->phase->tw, op->C);
+    phase_rows_fwd_reg<<<g1r, kT2, smem_bytes_reg(), st>>>(fa, op->phase->tw, op->C, 1);
   else
     phase_rows_fwd<true><<<g1, kThreads, smem_bytes(kRowsPerCta / 2), st>>>(fa, op->phase->tw, op->C);
   DPS_LAUNCH_CHECK("phase_rows_fwd");

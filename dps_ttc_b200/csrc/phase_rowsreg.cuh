@@ -16,10 +16,10 @@ struct RowsFwdCtx {
   const tw_t* tw;        // full table (see ColsCtx)
   const tw_t* w64;
   const float* x;        // plane of this particle and channel (H×H)
-  const float* eps;      // plane, never null (guidance forms x̂₀ from x and ε)
+  const float* eps;      // plane; null: x̂₀ = x (forward path only, operator.forward(x))
   float c1, c2;
   int clip;
-  unsigned char* maskb;  // clamp-pass bytes of the plane (1 = gradient passes)
+  unsigned char* maskb;  // clamp-pass bytes of the plane (1 = gradient passes); null: not wanted (forward path)
   float2* rt;            // Rt[k2][row] of the plane
   int r0;                // first image row of the CTA
 };
@@ -35,6 +35,7 @@ DPS_DEV void rf_load(int tid, ColsRegs& R, const RowsFwdCtx& c) {
   const int f = tid / kL8, j = tid - f * kL8;
   const int64_t row0 = (int64_t)(c.r0 + 2 * f) * kImg;
   float xa[8], ea[8], xb[8], eb[8];
+  const bool he = c.eps != nullptr;
 #pragma unroll
   for (int r = 0; r < 8; ++r) {
     if (rr_all_pad(r)) continue;
@@ -42,10 +43,11 @@ DPS_DEV void rf_load(int tid, ColsRegs& R, const RowsFwdCtx& c) {
     const bool ok = col >= 0 && col < kImg;
     const int64_t off = row0 + col;
     xa[r] = ok ? ldg_stream(c.x + off) : 0.f;
-    ea[r] = ok ? ldg_stream(c.eps + off) : 0.f;
+    ea[r] = (ok && he) ? ldg_stream(c.eps + off) : 0.f;
     xb[r] = ok ? ldg_stream(c.x + off + kImg) : 0.f;
-    eb[r] = ok ? ldg_stream(c.eps + off + kImg) : 0.f;
+    eb[r] = (ok && he) ? ldg_stream(c.eps + off + kImg) : 0.f;
   }
+  const bool clip = he && c.clip;  // x̂₀ = x is never clamped (x0_of / src_load)
 #pragma unroll
   for (int r = 0; r < 8; ++r) {
     if (rr_all_pad(r)) {
@@ -54,12 +56,12 @@ DPS_DEV void rf_load(int tid, ColsRegs& R, const RowsFwdCtx& c) {
     }
     const int col = j + kL8 * r - kPad;
     const bool ok = col >= 0 && col < kImg;
-    const float pa = x0_pre(xa[r], ea[r], c.c1, c.c2), pb = x0_pre(xb[r], eb[r], c.c1, c.c2);
-    R.v[r] = ok ? make_float2(c.clip ? clamp1(pa) : pa, c.clip ? clamp1(pb) : pb) : make_float2(0.f, 0.f);
-    if (ok) {
+    const float pa = he ? x0_pre(xa[r], ea[r], c.c1, c.c2) : xa[r], pb = he ? x0_pre(xb[r], eb[r], c.c1, c.c2) : xb[r];
+    R.v[r] = ok ? make_float2(clip ? clamp1(pa) : pa, clip ? clamp1(pb) : pb) : make_float2(0.f, 0.f);
+    if (ok && c.maskb) {
       const int64_t off = row0 + col;
-      stg_u8(c.maskb + off, (!c.clip || clamp_pass(pa) != 0.f) ? 1u : 0u);
-      stg_u8(c.maskb + off + kImg, (!c.clip || clamp_pass(pb) != 0.f) ? 1u : 0u);
+      stg_u8(c.maskb + off, (!clip || clamp_pass(pa) != 0.f) ? 1u : 0u);
+      stg_u8(c.maskb + off + kImg, (!clip || clamp_pass(pb) != 0.f) ? 1u : 0u);
     }
   }
 }

@@ -112,3 +112,45 @@ extern "C" int emu_cols(const float* rt, const float* y, float* r_out, float* t,
   }
   return 0;
 }
+
+// forward (two-kernel) path: rt → out = y − |F|/L (y null: |F|/L), partial sums, unit phase ph[k2][k1] (kHalf × L complex)
+extern "C" int emu_cols_fwd(const float* rt, const float* y, float* out, float* ph, float* partials) {
+  EmuTables T;
+  std::vector<float2> A(kSeq * kLQ), B(kSeq * kLQ);
+  std::vector<ColsRegs> R(kT2);
+  std::vector<ColsY> Y(kT2);
+  for (int grp = 0; grp < kColGroups; ++grp) {
+    for (auto& e : A) e = make_float2(NAN, NAN);
+    for (auto& e : B) e = make_float2(NAN, NAN);
+    ColsCtx cx;
+    cx.A = A.data();
+    cx.B = B.data();
+    cx.tw = T.twf.data();
+    cx.w64 = T.w64.data();
+    cx.k20 = grp * kColsPerCta;
+    cx.ncols = kColsPerCta < kHalf - cx.k20 ? kColsPerCta : kHalf - cx.k20;
+    cx.rt = reinterpret_cast<const float2*>(rt);
+    cx.y = y;
+    cx.outp = out;
+    cx.t = nullptr;
+    for (int tid = 0; tid < kT2; ++tid) {
+      R[tid].sq = R[tid].ab = 0.f;
+      for (int r = 0; r < 8; ++r) R[tid].v[r] = make_float2(NAN, NAN);
+      cr_load(tid, R[tid], cx);
+      cr_stage_a(tid, R[tid], cx.A, cx.ncols);
+    }
+    for (int tid = 0; tid < kT2; ++tid) {
+      if (y) cr_yload(tid, Y[tid], cx);
+      cr_stage_b(tid, R[tid], cx.A, cx.B, cx.w64, cx.ncols);
+    }
+    for (int tid = 0; tid < kT2; ++tid) {
+      if (y) cr_fwd_epilogue<true>(tid, R[tid], Y[tid], cx, reinterpret_cast<float2*>(ph));
+      else cr_fwd_epilogue<false>(tid, R[tid], Y[tid], cx, reinterpret_cast<float2*>(ph));
+    }
+    double sq = 0.0, ab = 0.0;
+    for (int tid = 0; tid < kT2; ++tid) { sq += R[tid].sq; ab += R[tid].ab; }
+    partials[2 * grp] = (float)sq;
+    partials[2 * grp + 1] = (float)ab;
+  }
+  return 0;
+}

@@ -109,6 +109,14 @@ def test_register_row_kernels_match_numpy_dft(r3, clip, packed, tmp_path):
     want_mask = ((pre >= -1) & (pre <= 1)).astype(np.uint8) if clip else np.ones((img, img), np.uint8)
     assert np.array_equal(maskb, want_mask)
 
+    # forward path of operator.forward(x): no ε (x̂₀ = x, never clamped), no mask bytes
+    rt2 = np.full((half, img), np.nan + 0j, np.complex64)
+    assert lib.emu_rows_fwd(fp(x), None, float(c1), float(c2), int(clip), fp(rt2), None) == 0
+    pad2 = np.zeros((img, L)); pad2[:, 64:64 + img] = x
+    ref2 = np.fft.fft(pad2, axis=1)[:, :half].T
+    assert not np.isnan(rt2.view(np.float32)).any()
+    assert np.abs(rt2 - ref2).max() <= 2e-5 * np.abs(ref2).max()
+
     t = (rng.standard_normal((img, half)) + 1j * rng.standard_normal((img, half))).astype(np.complex64) * 4
     g = np.full((img, img), np.nan, np.float32)
     coef = 1.0 / L
@@ -125,3 +133,42 @@ def test_register_row_kernels_match_numpy_dft(r3, clip, packed, tmp_path):
     ref_g = ref_g * coef * want_mask
     assert not np.isnan(g).any()
     assert np.abs(g - ref_g).max() <= 2e-5 * np.abs(ref_g).max()
+
+
+@pytest.mark.parametrize("r3,with_y", [(6, True), (6, False), (4, True), (3, False)])
+def test_register_forward_column_kernel_matches_numpy_dft(r3, with_y, tmp_path):
+    """phase_cols_fwd_reg (forward pass of the two-kernel path): y − |F|/L (or |F|/L) at both mirrored positions, partial sums
+    and the unit phase conj(F)/|F| laid out [k2][k1] for the adjoint."""
+    lib = _build(r3, tmp_path)
+    dims = (C.c_int * 4)()
+    lib.emu_dims(dims)
+    L, img, half, groups = list(dims)
+    rng = np.random.default_rng(23 + r3)
+    rt = (rng.standard_normal((half, img)) + 1j * rng.standard_normal((half, img))).astype(np.complex64) * 8
+    y = (rng.random((L, L)) * 1.5).astype(np.float32) if with_y else None
+    out = np.full((L, L), np.nan, np.float32)
+    ph = np.full((half, L), np.nan + 0j, np.complex64)
+    partials = np.zeros((groups, 2), np.float32)
+    fp = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
+    assert lib.emu_cols_fwd(fp(rt), fp(y), fp(out), fp(ph), fp(partials)) == 0
+    pad = np.zeros((half, L), np.complex128)
+    pad[:, 64:64 + img] = rt
+    F = np.fft.fft(pad, axis=1)
+    amp = np.abs(F) / L
+    sh = lambda k: (k + L // 2) % L
+    k1, k2 = np.arange(L), np.arange(half)
+    ref = np.full((L, L), np.nan)
+    r1 = (y[sh(k1)[None, :], sh(k2)[:, None]] - amp) if with_y else amp
+    r2 = (y[sh((L - k1) % L)[None, :], sh((L - k2) % L)[:, None]] - amp) if with_y else amp
+    mir = ((k2 > 0) & (k2 < L // 2))[:, None] & np.ones((1, L), bool)
+    ref[np.broadcast_to(sh(k1)[None, :], (half, L)), np.broadcast_to(sh(k2)[:, None], (half, L))] = r1
+    ref[np.broadcast_to(sh((L - k1) % L)[None, :], (half, L))[mir], np.broadcast_to(sh((L - k2) % L)[:, None], (half, L))[mir]] = r2[mir]
+    assert not np.isnan(ref).any() and not np.isnan(out).any()
+    assert np.abs(out - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max())
+    unit = np.conj(F) / np.abs(F)
+    assert not np.isnan(ph.view(np.float32)).any()
+    assert np.abs(ph - unit).max() <= 1e-4                      # |unit| = 1; bins with tiny |F| lose relative accuracy
+    sq = np.where(mir, r1 ** 2 + r2 ** 2, r1 ** 2).sum(1)
+    for g in range(groups):
+        cols = slice(8 * g, min(8 * g + 8, half))
+        assert abs(partials[g, 0] - sq[cols].sum()) <= 1e-4 * sq[cols].sum()

@@ -1,5 +1,6 @@
 """A/B of the kernel variants of the fused phase-retrieval guidance: register-resident butterflies (phase_colsreg.cuh,
-phase_rowsreg.cuh) against the shared-memory kernels they replace (DPSTTC_PHASE_COLS_REG / DPSTTC_PHASE_ROWS_REG = 0 / 1).
+phase_rowsreg.cuh) against the shared-memory kernels they replace (DPSTTC_PHASE_COLS_REG / DPSTTC_PHASE_ROWS_REG = 0 / 1 for
+the fused guidance, DPSTTC_PHASE_FWD_REG = 0 / 1 for the forward pass of the two-kernel path).
 One child process per variant (the switches are read once per process) runs dps_operator_guidance on the same seeded
 inputs for 256², 128² and 64² images; the parent compares residual, per-particle norms and cotangent of every variant
 with the all-shared-memory one.  The kernels do the same arithmetic per bin but accumulate the partial sums in a
@@ -39,8 +40,15 @@ def child(n, out_path):
         out2 = torch.full((n, 3, size, size), float("nan"), device=dev)
         p2, r2, _ = plan.guidance(x, o6[:, :3], k, True, y, out=out2)          # residual kept on chip
         norms = kernels.particle_norms(p, want_l1=True)
+        # two-kernel path: forward (residual + partial sums + unit phase), adjoint from it; A(x) alone without ε / y
+        rf, pf, aux = plan.forward(x, o6[:, :3], k, True, y, want_partials=True)
+        nf = kernels.particle_norms(pf, want_l1=True)
+        gf = torch.full((n, 3, size, size), float("nan"), device=dev)
+        plan.adjoint(rf, None, x, o6[:, :3], k, True, None, out=gf, aux=aux)
+        ax, _, _ = plan.forward(x * 0.01)
         torch.cuda.synchronize()
         res[size] = {"r": r.cpu(), "g": out.cpu(), "l2": norms[0].cpu(), "l1": norms[1].cpu(),
+                     "fwd_r": rf.cpu(), "fwd_l2": nf[0].cpu(), "fwd_l1": nf[1].cpu(), "fwd_adj_g": gf.cpu(), "Ax": ax.cpu(),
                      "same_without_r": bool(r2 is None and torch.equal(out, out2) and torch.equal(p, p2))}
     torch.save(res, out_path)
 
@@ -55,25 +63,27 @@ def main():
         return
     os.makedirs(os.path.join(REPO, "gpurun_out"), exist_ok=True)
     outs = {}
-    variants = ("00", "10", "01", "11")   # (columns, rows) in registers
+    variants = ("000", "100", "010", "111")   # (fused columns, fused rows, two-kernel forward) in registers
     for v in variants:
         path = os.path.join(REPO, "gpurun_out", f"_phase_reg_{v}.pt")
         subprocess.run([sys.executable, os.path.abspath(__file__), "--n", str(a.n), "--child", path],
-                       env=dict(os.environ, DPSTTC_PHASE_COLS_REG=v[0], DPSTTC_PHASE_ROWS_REG=v[1]), check=True)
+                       env=dict(os.environ, DPSTTC_PHASE_COLS_REG=v[0], DPSTTC_PHASE_ROWS_REG=v[1], DPSTTC_PHASE_FWD_REG=v[2]),
+                       check=True)
         outs[v] = torch.load(path)
         os.remove(path)
     ok = True
     for size in SIZES:
-        a0 = outs["00"][size]
+        a0 = outs["000"][size]
         ok &= a0["same_without_r"]
         for v in variants[1:]:
             a1 = outs[v][size]
-            for key, tol in (("r", 2e-6), ("g", 2e-5), ("l2", 2e-6), ("l1", 2e-6)):
+            for key, tol in (("r", 2e-6), ("g", 2e-5), ("l2", 2e-6), ("l1", 2e-6), ("fwd_r", 2e-6), ("fwd_l2", 2e-6),
+                             ("fwd_l1", 2e-6), ("fwd_adj_g", 2e-5), ("Ax", 2e-6)):
                 diff = (a0[key] - a1[key]).abs().max().item()
-                scale = max(1.0, a0[key].abs().max().item()) if key in ("r", "g") else a0[key].abs().max().item()
+                scale = max(1.0, a0[key].abs().max().item()) if key in ("r", "g", "fwd_r", "fwd_adj_g", "Ax") else a0[key].abs().max().item()
                 good = bool(torch.isfinite(a1[key]).all()) and diff <= tol * scale
                 ok &= good
-                print(f"[phase_reg_check] {size}x{size} n={a.n} cols/rows in registers = {v} {key}: max|smem - reg| = {diff:.3e} "
+                print(f"[phase_reg_check] {size}x{size} n={a.n} cols/rows/fwd in registers = {v} {key}: max|smem - reg| = {diff:.3e} "
                       f"(scale {scale:.3e}, tol {tol:g}) {'ok' if good else 'FAIL'}", flush=True)
             ok &= a1["same_without_r"]
             print(f"[phase_reg_check] {size}x{size} {v}: with / without r_out bit-identical: {a1['same_without_r']}")
