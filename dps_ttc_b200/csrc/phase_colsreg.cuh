@@ -225,6 +225,30 @@ DPS_DEV void cr_fwd_epilogue(int tid, ColsRegs& R, const ColsY& Y, const ColsCtx
     }
   }
 }
+// F role, adjoint (two-kernel) path: the symmetrised cotangent ½(g(k) + g(−k)) of the thread's bins (32-byte runs of the residual
+// plane, as the measurement loads above) × the unit phase the forward pass left in ph[k2][k1] → dstbuf in natural order
+DPS_DEV void ca_load(int tid, const float* rplane, const float2* ph, const ColsCtx& c) {
+  const int f = tid & 7, j = tid >> 3;
+  const int k2 = c.k20 + f;
+  const bool act = f < c.ncols;
+  const int c1 = shift_idx(k2), c2 = shift_idx(k2 ? kL - k2 : 0);
+  const float2* php = ph + (int64_t)k2 * kL + j;
+  float g1[kR3], g2[kR3];
+  float2 u[kR3];
+#pragma unroll
+  for (int r = 0; r < kR3; ++r) {
+    const int k1 = j + 64 * r;
+    g1[r] = act ? ldg_stream(rplane + shift_idx(k1) * kL + c1) : 0.f;
+    g2[r] = act ? ldg_stream(rplane + shift_idx(k1 ? kL - k1 : 0) * kL + c2) : 0.f;
+    u[r] = act ? ldg_stream2(php + 64 * r) : make_float2(0.f, 0.f);
+  }
+  float2* dst = c.A + f * kLQ + P(j);
+#pragma unroll
+  for (int r = 0; r < kR3; ++r) {
+    const float g = 0.5f * (g1[r] + g2[r]);
+    dst[72 * r] = make_float2(g * u[r].x, g * u[r].y);
+  }
+}
 // F role: last stage of the second transform; padded rows 64 .. 64 + H − 1 go to T[row][k2] (row stride L/2 + 1)
 DPS_DEV void cr_store(int tid, ColsRegs& R, const ColsCtx& c) {
   cr_stage_c(tid, R.v, c.A, c.tw);

@@ -657,8 +657,9 @@ __global__ void __launch_bounds__(kT2, PHASE_ROWS_MINB) phase_rows_fwd_reg(const
   rf_split_store(tid, cx);
 }
 
+template <bool kFused>
 __global__ void __launch_bounds__(kT2, PHASE_ROWS_MINB) phase_rows_adj_reg(const AdjArgs aa, const float* __restrict__ aux_r,
-                                                             const float2* __restrict__ tw_g, int C) {
+                                                                           const float2* __restrict__ tw_g, int C) {
   extern __shared__ __align__(16) float smem[];
   const int tid = threadIdx.x;
   constexpr int groups = kImg / kRowsReg;
@@ -668,9 +669,16 @@ __global__ void __launch_bounds__(kT2, PHASE_ROWS_MINB) phase_rows_adj_reg(const
   cx.B = cx.A + kSeq * kLQ;
   float* red;
   reg_tables(smem, tw_g, tid, cx.tw, cx.w64, red);
-  cx.t = aux_scratch2(const_cast<float*>(aux_r), n, C, c);
-  cx.maskb = aux_mask(const_cast<float*>(aux_r), n, C, c);
-  cx.g = aa.g + n * aa.g_stride + (int64_t)c * kImg * kImg;
+  const int64_t plane = (int64_t)c * kImg * kImg;
+  cx.t = kFused ? aux_scratch2(const_cast<float*>(aux_r), n, C, c) : aux_scratch(const_cast<float*>(aux_r), n, C, c);
+  cx.maskb = kFused ? aux_mask(const_cast<float*>(aux_r), n, C, c) : nullptr;
+  const bool src_mask = !kFused && aa.has_mask && aa.mask_src.eps && aa.mask_src.clip;
+  cx.mx = src_mask ? aa.mask_src.x + n * aa.mask_src.x_stride + plane : nullptr;
+  cx.meps = src_mask ? aa.mask_src.eps + n * aa.mask_src.eps_stride + plane : nullptr;
+  cx.mc1 = aa.mask_src.c1;
+  cx.mc2 = aa.mask_src.c2;
+  cx.extra = aa.extra ? aa.extra + n * aa.extra_stride + plane : nullptr;
+  cx.g = aa.g + n * aa.g_stride + plane;
   cx.coef = (aa.coef ? aa.coef[n] : 1.0f) * (1.0f / (float)kL);
   cx.r0 = grp * kRowsReg;
   ColsRegs R;
@@ -683,6 +691,37 @@ __global__ void __launch_bounds__(kT2, PHASE_ROWS_MINB) phase_rows_adj_reg(const
   ra_maskload(tid, M, cx);  // in flight across the barrier
   __syncthreads();
   ra_store(tid, R, M, cx);
+}
+
+// adjoint (two-kernel) path, columns: H_s[k1][k2] = ½(g[k] + g[−k])·conj(F)/|F| → column transform → rows 64 .. 64 + H − 1 of T
+__global__ void __launch_bounds__(kT2, PHASE_COLS_MINB) phase_cols_adj_reg(const AdjArgs aa, float* __restrict__ aux_rw,
+                                                                           const float2* __restrict__ tw_g, int C) {
+  extern __shared__ __align__(16) float smem[];
+  const int tid = threadIdx.x;
+  const int planes = aa.n * C;
+  const int grp = blockIdx.x / planes, pc = blockIdx.x - grp * planes;
+  const int n = pc / C, c = pc - n * C;
+  ColsCtx cx;
+  cx.A = reinterpret_cast<float2*>(smem);
+  cx.B = cx.A + kSeq * kLQ;
+  float* red;
+  reg_tables(smem, tw_g, tid, cx.tw, cx.w64, red);
+  cx.k20 = grp * kColsPerCta;
+  cx.ncols = min(kColsPerCta, kHalf - cx.k20);
+  cx.rt = nullptr;
+  cx.y = nullptr;
+  cx.outp = nullptr;
+  cx.t = aux_scratch(aux_rw, n, C, c);
+  ColsRegs R;
+  ca_load(tid, aa.r + ((int64_t)n * C + c) * kL * kL, aux_phase(aux_rw, n, C, c), cx);
+  stage_wait();
+  __syncthreads();
+  cr_read_a(tid, R, cx.A, cx.ncols);
+  cr_stage_a(tid, R, cx.B, cx.ncols);
+  __syncthreads();
+  cr_stage_b(tid, R, cx.B, cx.A, cx.w64, cx.ncols);
+  __syncthreads();
+  cr_store(tid, R, cx);
 }
 
 // ---- A1: H_s[k1][k2] = ½(g[k]+g[−k])·conj(F)/|F|, column transform, keep rows 64..319 ------------
@@ -831,7 +870,9 @@ int create(dps_operator* op) {
   if (int rc = set_smem((const void*)phase_rows_fwd<true>, smem_bytes(kRowsPerCta / 2))) return rc;
   if (int rc = set_smem((const void*)phase_cols_fused, smem_bytes(kColsPerCta))) return rc;
   if (int rc = set_smem((const void*)phase_rows_fwd_reg, smem_bytes_reg())) return rc;
-  if (int rc = set_smem((const void*)phase_rows_adj_reg, smem_bytes_reg())) return rc;
+  if (int rc = set_smem((const void*)phase_rows_adj_reg<true>, smem_bytes_reg())) return rc;
+  if (int rc = set_smem((const void*)phase_rows_adj_reg<false>, smem_bytes_reg())) return rc;
+  if (int rc = set_smem((const void*)phase_cols_adj_reg, smem_bytes_reg())) return rc;
   if (int rc = set_smem((const void*)phase_cols_fused_reg<false>, smem_bytes_reg())) return rc;
   if (int rc = set_smem((const void*)phase_cols_fwd_reg<false>, smem_bytes_reg())) return rc;
   if (int rc = set_smem((const void*)phase_cols_fwd_reg<true>, smem_bytes_reg())) return rc;
@@ -886,6 +927,18 @@ int forward(const dps_operator* op, const FwdArgs& a, cudaStream_t st) {
 int adjoint(const dps_operator* op, const AdjArgs& a, cudaStream_t st) {
   DPS_REQUIRE(a.aux && a.r, DPS_ERR_INVALID, "phase retrieval adjoint needs r and the aux workspace of the forward pass");
   float* aux = const_cast<float*>(a.aux);
+  // register-resident kernels for the adjoint of the two-kernel path; DPSTTC_PHASE_ADJ_REG=0 / 1 overrides the built-in choice
+  constexpr bool kAdjRegDefault = false;
+  static const bool adj_reg = getenv("DPSTTC_PHASE_ADJ_REG") ? getenv("DPSTTC_PHASE_ADJ_REG")[0] != '0' : kAdjRegDefault;
+  if (adj_reg) {
+    const dim3 g1r((unsigned)(op->C * kColGroups * a.n));
+    phase_cols_adj_reg<<<g1r, kT2, smem_bytes_reg(), st>>>(a, aux, op->phase->tw, op->C);
+    DPS_LAUNCH_CHECK("phase_cols_adj");
+    dim3 g2r((unsigned)(op->C * (kImg / kRowsReg)), (unsigned)a.n);
+    phase_rows_adj_reg<false><<<g2r, kT2, smem_bytes_reg(), st>>>(a, aux, op->phase->tw, op->C);
+    DPS_LAUNCH_CHECK("phase_rows_adj");
+    return DPS_OK;
+  }
   dim3 g1((unsigned)(op->C * kColGroupsAdj), (unsigned)a.n);
   phase_cols_adj<<<g1, kThreads, smem_bytes1(kColsAdj), st>>>(a, aux, op->phase->tw, op->C);
   DPS_LAUNCH_CHECK("phase_cols_adj");
@@ -946,7 +999,7 @@ int guidance(const dps_operator* op, const dps_source& src, const float* y, int6
   aa.n = n;
   dim3 g3((unsigned)(op->C * (kImg / kRowsAdj)), (unsigned)n);
   if (rows_reg)
-    phase_rows_adj_reg<<<g1r, kT2, smem_bytes_reg(), st>>>(aa, aux, op->phase->tw, op->C);
+    phase_rows_adj_reg<true><<<g1r, kT2, smem_bytes_reg(), st>>>(aa, aux, op->phase->tw, op->C);
   else
     phase_rows_adj<true><<<g3, kThreads, smem_bytes1(kRowsAdj / 2), st>>>(aa, aux, op->phase->tw, op->C);
   DPS_LAUNCH_CHECK("phase_rows_adj");

@@ -110,13 +110,18 @@ struct RowsAdjCtx {
   const tw_t* tw;
   const tw_t* w64;
   const float2* t;             // T[row][k2] of the plane, row stride L/2 + 1
-  const unsigned char* maskb;  // clamp-pass bytes of the plane
+  const unsigned char* maskb;  // clamp-pass bytes of the plane (fused path) or null
+  const float* mx;             // two-kernel path: planes of x and ε the clamp mask is recomputed from (null: no mask)
+  const float* meps;
+  float mc1, mc2;
+  const float* extra;          // plane added before the mask (null: none)
   float* g;                    // cotangent plane (H×H)
   float coef;                  // 1/L (× the per-particle coefficient where one is given)
   int r0;
 };
 struct RowsMask {
-  unsigned char a[kR3], b[kR3];
+  float a[kR3], b[kR3];    // 1 = gradient passes
+  float ea[kR3], eb[kR3];  // extra term
 };
 
 // K3, J role: X[k] = T1[k] + i·T2[k] of the row pair, T[L − k] = conj(T[k]) for the upper half
@@ -140,19 +145,29 @@ DPS_DEV void ra_load(int tid, ColsRegs& R, const RowsAdjCtx& c) {
     R.v[r] = make_float2(u1[r].x - sg * u2[r].y, sg * u1[r].y + u2[r].x);
   }
 }
-// K3, G role: the clamp-pass bytes of the thread's outputs (requested before the last barrier)
+// K3, G role: the clamp mask (bytes of the fused path, or recomputed from x and ε) and the extra term of the thread's outputs,
+// requested before the last barrier
 DPS_DEV void ra_maskload(int tid, RowsMask& M, const RowsAdjCtx& c) {
   const int f = tid >> 6, j = tid & 63;
-  const unsigned char* m = c.maskb + (int64_t)(c.r0 + 2 * f) * kImg + j - kPad;
+  const int64_t o = (int64_t)(c.r0 + 2 * f) * kImg + j - kPad;
 #pragma unroll
   for (int r = 0; r < kR3; ++r) {
     if (64 * r >= kPad && 64 * r + 63 < kPad + kImg) {
-      M.a[r] = ldg_u8_pinned(m + 64 * r);
-      M.b[r] = ldg_u8_pinned(m + 64 * r + kImg);
+      if (c.maskb) {
+        M.a[r] = ldg_u8_pinned(c.maskb + o + 64 * r) ? 1.f : 0.f;
+        M.b[r] = ldg_u8_pinned(c.maskb + o + 64 * r + kImg) ? 1.f : 0.f;
+      } else if (c.mx) {
+        M.a[r] = clamp_pass(x0_pre(ldg_stream(c.mx + o + 64 * r), ldg_stream(c.meps + o + 64 * r), c.mc1, c.mc2));
+        M.b[r] = clamp_pass(x0_pre(ldg_stream(c.mx + o + 64 * r + kImg), ldg_stream(c.meps + o + 64 * r + kImg), c.mc1, c.mc2));
+      } else {
+        M.a[r] = M.b[r] = 1.f;
+      }
+      M.ea[r] = c.extra ? ldg_stream(c.extra + o + 64 * r) : 0.f;
+      M.eb[r] = c.extra ? ldg_stream(c.extra + o + 64 * r + kImg) : 0.f;
     }
   }
 }
-// K3, G role: last stage; Re → even row, Im → odd row, padded columns 64 .. 64 + H − 1, × coefficient × clamp mask
+// K3, G role: last stage; Re → even row, Im → odd row, padded columns 64 .. 64 + H − 1: (coefficient · value + extra) × clamp mask
 DPS_DEV void ra_store(int tid, ColsRegs& R, const RowsMask& M, const RowsAdjCtx& c) {
   rr_stage_c(tid, R.v, c.B, c.tw);
   const int f = tid >> 6, j = tid & 63;
@@ -160,8 +175,8 @@ DPS_DEV void ra_store(int tid, ColsRegs& R, const RowsMask& M, const RowsAdjCtx&
 #pragma unroll
   for (int r = 0; r < kR3; ++r) {
     if (64 * r >= kPad && 64 * r + 63 < kPad + kImg) {
-      stg_stream(g + 64 * r, M.a[r] ? c.coef * R.v[r].x : 0.f);
-      stg_stream(g + 64 * r + kImg, M.b[r] ? c.coef * R.v[r].y : 0.f);
+      stg_stream(g + 64 * r, (c.coef * R.v[r].x + M.ea[r]) * M.a[r]);
+      stg_stream(g + 64 * r + kImg, (c.coef * R.v[r].y + M.eb[r]) * M.b[r]);
     }
   }
 }

@@ -23,6 +23,7 @@ static inline float emu_rsqrtf(float x) { return 1.0f / std::sqrt(x); }
 #define rsqrtf emu_rsqrtf
 static inline float __fsub_rn(float a, float b) { return a - b; }
 static inline float2 ldg_stream2(const float2* p) { return *p; }
+static inline float ldg_stream(const float* p) { return *p; }
 static inline float ldg_ro(const float* p) { return *p; }
 static inline float ldg_ro_pinned(const float* p) { return *p; }
 static inline void stg_stream(float* p, float v) { *p = v; }
@@ -151,6 +152,39 @@ extern "C" int emu_cols_fwd(const float* rt, const float* y, float* out, float* 
     for (int tid = 0; tid < kT2; ++tid) { sq += R[tid].sq; ab += R[tid].ab; }
     partials[2 * grp] = (float)sq;
     partials[2 * grp + 1] = (float)ab;
+  }
+  return 0;
+}
+
+// adjoint (two-kernel) path, columns: r plane (L×L) and unit phase ph[k2][k1] → T[row][k2] (kImg × kHalf complex)
+extern "C" int emu_cols_adj(const float* rplane, const float* ph, float* t) {
+  EmuTables T;
+  std::vector<float2> A(kSeq * kLQ), B(kSeq * kLQ);
+  std::vector<ColsRegs> R(kT2);
+  for (int grp = 0; grp < kColGroups; ++grp) {
+    for (auto& e : A) e = make_float2(NAN, NAN);
+    for (auto& e : B) e = make_float2(NAN, NAN);
+    ColsCtx cx;
+    cx.A = A.data();
+    cx.B = B.data();
+    cx.tw = T.twf.data();
+    cx.w64 = T.w64.data();
+    cx.k20 = grp * kColsPerCta;
+    cx.ncols = kColsPerCta < kHalf - cx.k20 ? kColsPerCta : kHalf - cx.k20;
+    cx.rt = nullptr;
+    cx.y = nullptr;
+    cx.outp = nullptr;
+    cx.t = reinterpret_cast<float2*>(t);
+    for (int tid = 0; tid < kT2; ++tid) {
+      for (int r = 0; r < 8; ++r) R[tid].v[r] = make_float2(NAN, NAN);
+      ca_load(tid, rplane, reinterpret_cast<const float2*>(ph), cx);
+    }
+    for (int tid = 0; tid < kT2; ++tid) {
+      cr_read_a(tid, R[tid], cx.A, cx.ncols);
+      cr_stage_a(tid, R[tid], cx.B, cx.ncols);
+    }
+    for (int tid = 0; tid < kT2; ++tid) cr_stage_b(tid, R[tid], cx.B, cx.A, cx.w64, cx.ncols);
+    for (int tid = 0; tid < kT2; ++tid) cr_store(tid, R[tid], cx);
   }
   return 0;
 }

@@ -96,8 +96,10 @@ extern "C" int emu_rows_fwd(const float* x, const float* eps, float c1, float c2
   return 0;
 }
 
-// t: T[row][k2] (H × kHalf complex); maskb: H×H bytes; g: H×H
-extern "C" int emu_rows_adj(const float* t, const unsigned char* maskb, float coef, float* g) {
+// t: T[row][k2] (H × kHalf complex); clamp mask from maskb (H×H bytes) or recomputed from mx, meps (H×H planes) or none;
+// extra: H×H plane or null; g: H×H
+extern "C" int emu_rows_adj(const float* t, const unsigned char* maskb, const float* mx, const float* meps, float mc1, float mc2,
+                            const float* extra, float coef, float* g) {
   Tables T;
   std::vector<float2> A(kSeq * kLQ), B(kSeq * kLQ);
   std::vector<ColsRegs> R(kT2);
@@ -106,7 +108,8 @@ extern "C" int emu_rows_adj(const float* t, const unsigned char* maskb, float co
     poison(A); poison(B);
     RowsAdjCtx cx;
     cx.A = A.data(); cx.B = B.data(); cx.tw = T.twf.data(); cx.w64 = T.w64.data();
-    cx.t = reinterpret_cast<const float2*>(t); cx.maskb = maskb; cx.g = g; cx.coef = coef; cx.r0 = grp * kRowsReg;
+    cx.t = reinterpret_cast<const float2*>(t); cx.maskb = maskb; cx.mx = mx; cx.meps = meps; cx.mc1 = mc1; cx.mc2 = mc2;
+    cx.extra = extra; cx.g = g; cx.coef = coef; cx.r0 = grp * kRowsReg;
     for (int tid = 0; tid < kT2; ++tid) {
       for (int r = 0; r < 8; ++r) R[tid].v[r] = make_float2(NAN, NAN);
       ra_load(tid, R[tid], cx);

@@ -118,21 +118,28 @@ def test_register_row_kernels_match_numpy_dft(r3, clip, packed, tmp_path):
     assert np.abs(rt2 - ref2).max() <= 2e-5 * np.abs(ref2).max()
 
     t = (rng.standard_normal((img, half)) + 1j * rng.standard_normal((img, half))).astype(np.complex64) * 4
-    g = np.full((img, img), np.nan, np.float32)
     coef = 1.0 / L
-    lib.emu_rows_adj.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]
-    assert lib.emu_rows_adj(fp(t), fp(want_mask), coef, fp(g)) == 0
+    lib.emu_rows_adj.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_float, C.c_void_p]
     # X[k] = T1[k] + i T2[k] for k <= L/2, conj-mirrored above (row pairs); z = FFT(X); Re -> even row, Im -> odd row
     k = np.arange(L)
     kk = np.where(k < half, k, L - k)
     full = np.where((k < half)[None, :], t[:, kk], np.conj(t[:, kk])).astype(np.complex128)
     X = full[0::2] + 1j * full[1::2]
     z = np.fft.fft(X, axis=1)[:, 64:64 + img]
-    ref_g = np.empty((img, img))
-    ref_g[0::2], ref_g[1::2] = z.real, z.imag
-    ref_g = ref_g * coef * want_mask
-    assert not np.isnan(g).any()
-    assert np.abs(g - ref_g).max() <= 2e-5 * np.abs(ref_g).max()
+    rows = np.empty((img, img))
+    rows[0::2], rows[1::2] = z.real, z.imag
+    extra = (rng.standard_normal((img, img)) * 0.1).astype(np.float32)
+    # (a) fused path: mask bytes, no extra  (b) two-kernel path: mask recomputed from x and eps, extra term, another coefficient
+    # (c) no mask at all
+    for maskb, mx, me, ex, cf, want in ((want_mask, None, None, None, coef, rows * coef * want_mask),
+                                        (None, x, eps, extra, -0.37 * coef, (rows * (-0.37 * coef) + extra) * ((pre >= -1) & (pre <= 1))),
+                                        (None, None, None, None, coef, rows * coef)):
+        g = np.full((img, img), np.nan, np.float32)
+        assert lib.emu_rows_adj(fp(t), fp(maskb) if maskb is not None else None, fp(mx) if mx is not None else None,
+                                fp(me) if me is not None else None, float(c1), float(c2),
+                                fp(ex) if ex is not None else None, cf, fp(g)) == 0
+        assert not np.isnan(g).any()
+        assert np.abs(g - want).max() <= 2e-5 * np.abs(want).max()
 
 
 @pytest.mark.parametrize("r3,with_y", [(6, True), (6, False), (4, True), (3, False)])
@@ -172,3 +179,26 @@ def test_register_forward_column_kernel_matches_numpy_dft(r3, with_y, tmp_path):
     for g in range(groups):
         cols = slice(8 * g, min(8 * g + 8, half))
         assert abs(partials[g, 0] - sq[cols].sum()) <= 1e-4 * sq[cols].sum()
+
+
+@pytest.mark.parametrize("r3", [6, 4, 3])
+def test_register_adjoint_column_kernel_matches_numpy_dft(r3, tmp_path):
+    """phase_cols_adj_reg (adjoint of the two-kernel path): symmetrised cotangent × stored unit phase → column transform → T."""
+    lib = _build(r3, tmp_path)
+    dims = (C.c_int * 4)()
+    lib.emu_dims(dims)
+    L, img, half, groups = list(dims)
+    rng = np.random.default_rng(31 + r3)
+    rplane = rng.standard_normal((L, L)).astype(np.float32)
+    ph = np.exp(1j * rng.uniform(0, 2 * np.pi, (half, L))).astype(np.complex64)
+    t = np.full((img, half), np.nan + 0j, np.complex64)
+    fp = lambda a: a.ctypes.data_as(C.c_void_p)
+    assert lib.emu_cols_adj(fp(rplane), fp(ph), fp(t)) == 0
+    sh = lambda k: (k + L // 2) % L
+    k1, k2 = np.arange(L), np.arange(half)
+    g1 = rplane[sh(k1)[None, :], sh(k2)[:, None]].astype(np.float64)
+    g2 = rplane[sh((L - k1) % L)[None, :], sh((L - k2) % L)[:, None]].astype(np.float64)
+    Hs = 0.5 * (g1 + g2) * ph.astype(np.complex128)
+    T = np.fft.fft(Hs, axis=1)[:, 64:64 + img].T
+    assert not np.isnan(t.view(np.float32)).any()
+    assert np.abs(t - T).max() <= 2e-5 * np.abs(T).max()

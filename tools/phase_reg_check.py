@@ -1,6 +1,6 @@
 """A/B of the kernel variants of the fused phase-retrieval guidance: register-resident butterflies (phase_colsreg.cuh,
 phase_rowsreg.cuh) against the shared-memory kernels they replace (DPSTTC_PHASE_COLS_REG / DPSTTC_PHASE_ROWS_REG = 0 / 1 for
-the fused guidance, DPSTTC_PHASE_FWD_REG = 0 / 1 for the forward pass of the two-kernel path).
+the fused guidance, DPSTTC_PHASE_FWD_REG / DPSTTC_PHASE_ADJ_REG = 0 / 1 for the forward and adjoint pass of the two-kernel path).
 One child process per variant (the switches are read once per process) runs dps_operator_guidance on the same seeded
 inputs for 256², 128² and 64² images; the parent compares residual, per-particle norms and cotangent of every variant
 with the all-shared-memory one.  The kernels do the same arithmetic per bin but accumulate the partial sums in a
@@ -63,17 +63,18 @@ def main():
         return
     os.makedirs(os.path.join(REPO, "gpurun_out"), exist_ok=True)
     outs = {}
-    variants = ("000", "100", "010", "111")   # (fused columns, fused rows, two-kernel forward) in registers
+    variants = ("0000", "1000", "0100", "1110", "1111")   # (fused columns, fused rows, two-kernel forward, adjoint) in registers
     for v in variants:
         path = os.path.join(REPO, "gpurun_out", f"_phase_reg_{v}.pt")
         subprocess.run([sys.executable, os.path.abspath(__file__), "--n", str(a.n), "--child", path],
-                       env=dict(os.environ, DPSTTC_PHASE_COLS_REG=v[0], DPSTTC_PHASE_ROWS_REG=v[1], DPSTTC_PHASE_FWD_REG=v[2]),
+                       env=dict(os.environ, DPSTTC_PHASE_COLS_REG=v[0], DPSTTC_PHASE_ROWS_REG=v[1], DPSTTC_PHASE_FWD_REG=v[2],
+                                DPSTTC_PHASE_ADJ_REG=v[3]),
                        check=True)
         outs[v] = torch.load(path)
         os.remove(path)
     ok = True
     for size in SIZES:
-        a0 = outs["000"][size]
+        a0 = outs["0000"][size]
         ok &= a0["same_without_r"]
         for v in variants[1:]:
             a1 = outs[v][size]
@@ -83,7 +84,7 @@ def main():
                 scale = max(1.0, a0[key].abs().max().item()) if key in ("r", "g", "fwd_r", "fwd_adj_g", "Ax") else a0[key].abs().max().item()
                 good = bool(torch.isfinite(a1[key]).all()) and diff <= tol * scale
                 ok &= good
-                print(f"[phase_reg_check] {size}x{size} n={a.n} cols/rows/fwd in registers = {v} {key}: max|smem - reg| = {diff:.3e} "
+                print(f"[phase_reg_check] {size}x{size} n={a.n} cols/rows/fwd/adj in registers = {v} {key}: max|smem - reg| = {diff:.3e} "
                       f"(scale {scale:.3e}, tol {tol:g}) {'ok' if good else 'FAIL'}", flush=True)
             ok &= a1["same_without_r"]
             print(f"[phase_reg_check] {size}x{size} {v}: with / without r_out bit-identical: {a1['same_without_r']}")
