@@ -5,8 +5,7 @@
 //   Jᵀg [p] = (1/L)·Re Σ_k G[k]·conj(F[k])/|F[k]|·e^{−2πi k·p/L},   G = ifftshift(g),  zero where |F| = 0.
 //
 // L = H + 2·pad = 384 = 8·8·6 (256² images; also 256 = 8·8·4 for 128² and 192 = 8·8·3 for 64²: phase_impl.cuh is compiled once
-// per length): hand-written mixed-radix Stockham FFT in shared memory, three register-blocked stages (radix 8, 8, L/64),
-// twiddles from an L-entry table.  What makes it cheap:
+// per length): hand-written mixed-radix Stockham FFT, radices 8, 8, L/64.  What makes it cheap:
 //   * real input  → two image rows ride one complex FFT; only the half spectrum k2 ∈ [0,192] is kept and
 //     the other half of the magnitude is written by Hermitian symmetry |F[−k]| = |F[k]|;
 //   * zero padding → only the 256 non-zero rows are row-transformed, the column pass reads 256 of 384;
@@ -16,8 +15,13 @@
 //           K2 cols  Rt → |F|/L → out = y − A(x̂₀) (or A(x̂₀)), Σr², Σ|r|, unit phase conj(F)/|F| → aux
 // adjoint : A1 cols  (r, phase) → T[row][k2]      (scratch)
 //           A2 rows  T → g = clamp-mask ⊙ (coef/L·Re(·) + extra)
-// Roofline: ~16 MFLOP per particle against ≥ 13 MB of traffic: memory-bound; the scratch round trips
-// (1.5T each way) are the price of not fitting a 384² complex plane in one SM's shared memory.
+// guidance (dps_operator_guidance): K1 (+ clamp-mask bytes) → fused columns (both transforms, residual and cotangent on chip) → A2.
+// Two generations of kernels live here.  The default since the end of round 2 keeps the butterflies in REGISTERS (a thread owns a
+// butterfly, shared memory is only the exchange between stages: phase_colsreg.cuh, phase_rowsreg.cuh — 512-thread CTAs, 40
+// registers, 3 CTAs per SM); the earlier kernels run every Stockham stage through shared memory (fft_batch / fft_inplace in
+// phase_impl.cuh) and remain selectable (DPSTTC_PHASE_{COLS,ROWS,FWD,ADJ}_REG=0) as the baseline the new ones are gated against.
+// Roofline: ~16 MFLOP per particle against ≥ 13 MB of traffic, yet instruction- and barrier-bound: 20–26 % of the
+// HBM peak on the algorithmic bytes; the scratch round trips (1.5T each way) stay in L2 at the particle counts the configs use.
 #include <math.h>
 
 #include <vector>

@@ -928,7 +928,7 @@ int adjoint(const dps_operator* op, const AdjArgs& a, cudaStream_t st) {
   DPS_REQUIRE(a.aux && a.r, DPS_ERR_INVALID, "phase retrieval adjoint needs r and the aux workspace of the forward pass");
   float* aux = const_cast<float*>(a.aux);
   // register-resident kernels for the adjoint of the two-kernel path; DPSTTC_PHASE_ADJ_REG=0 / 1 overrides the built-in choice
-  constexpr bool kAdjRegDefault = false;
+  constexpr bool kAdjRegDefault = true;  // gate + 56 phase / drop-in / pin tests with the switch on: profiles/r5f_*; 98.6 -> 77.9 us at N = 32
   static const bool adj_reg = getenv("DPSTTC_PHASE_ADJ_REG") ? getenv("DPSTTC_PHASE_ADJ_REG")[0] != '0' : kAdjRegDefault;
   if (adj_reg) {
     const dim3 g1r((unsigned)(op->C * kColGroups * a.n));
