@@ -63,7 +63,7 @@ def main():
         return
     os.makedirs(os.path.join(REPO, "gpurun_out"), exist_ok=True)
     outs = {}
-    variants = ("0000", "1000", "0100", "1110", "1111")   # (fused columns, fused rows, two-kernel forward, adjoint) in registers
+    variants = ("0000", "1010", "0101", "1111")   # (fused columns, fused rows, two-kernel forward, adjoint) in registers
     for v in variants:
         path = os.path.join(REPO, "gpurun_out", f"_phase_reg_{v}.pt")
         subprocess.run([sys.executable, os.path.abspath(__file__), "--n", str(a.n), "--child", path],
