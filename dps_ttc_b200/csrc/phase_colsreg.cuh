@@ -27,13 +27,18 @@
 // Every function below is one barrier-free phase of the kernel taking the thread index as an argument:
 // tests/emu/phase_cols_emu.cpp runs the same phases thread by thread on the CPU against a plain DFT (index logic check).
 #ifndef PHASE_PACKED
-#define PHASE_PACKED 0  // 1: packed fp32 arithmetic (FADD2 / FMUL2 / FFMA2) in the butterflies, twiddles as (w, −i·w) quadruples
-#endif
-#if PHASE_PACKED
+#define PHASE_PACKED 0  // 0: scalar fp32 butterflies.  1: complex adds / subtracts as FADD2 (same values), twiddle products scalar.
+#endif                  // 2: also the twiddle products packed (FMUL2 + FFMA2 on (w, −i·w) quadruples; measured slower)
+#if PHASE_PACKED == 2
 typedef float4 tw_t;  // (w.x, w.y, −w.y, w.x)
 DPS_DEV float2 cr_cmul(float2 a, float4 w) { return cmul_tw(a, w); }
 DPS_DEV void cr_dft8(float2* v) { dft8p(v); }
-DPS_DEV void cr_dft_last(float2* v) { dft_last_p(v); }
+DPS_DEV void cr_dft_last(float2* v) { dft_last_p<true>(v); }
+#elif PHASE_PACKED == 1
+typedef float2 tw_t;
+DPS_DEV float2 cr_cmul(float2 a, float2 w) { return cmul(a, w); }
+DPS_DEV void cr_dft8(float2* v) { dft8p(v); }
+DPS_DEV void cr_dft_last(float2* v) { dft_last_p<false>(v); }
 #else
 typedef float2 tw_t;
 DPS_DEV float2 cr_cmul(float2 a, float2 w) { return cmul(a, w); }

@@ -31,8 +31,9 @@ DPS_DEV void dft_last(float2* v) {
   else dft3(v[0], v[1], v[2]);
 }
 
+template <bool kPackedMul>
 DPS_DEV void dft_last_p(float2* v) {  // packed variant (phase_math.cuh)
-  if constexpr (kR3 == 6) dft6p(v);
+  if constexpr (kR3 == 6) dft6p<kPackedMul>(v);
   else if constexpr (kR3 == 4) dft4p(v);
   else dft3p(v[0], v[1], v[2]);
 }

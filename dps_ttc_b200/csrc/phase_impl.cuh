@@ -521,7 +521,7 @@ DPS_DEV void reg_tables(float* smem, const float2* tw_g, int tid, const tw_t*& t
   constexpr int kF = sizeof(tw_t) / sizeof(float);  // floats per entry
   // PhaseTables::tw (create()): [0, L) exp(−2πi j/L) · [L, L+64) W64^{k·r} at [8r+k] · [L+64, 2L+64) the full table rebuilt from the
   // half table with twid()'s sign rule · then the same two tables as (w.x, w.y, −w.y, w.x) quadruples: [64][L]
-  const float* src = PHASE_PACKED ? reinterpret_cast<const float*>(tw_g + 2 * kL + 64) : reinterpret_cast<const float*>(tw_g + kL);
+  const float* src = PHASE_PACKED == 2 ? reinterpret_cast<const float*>(tw_g + 2 * kL + 64) : reinterpret_cast<const float*>(tw_g + kL);
   stage_async(reinterpret_cast<float*>(t + kL), src, kF * 64, tid, kT2);
   stage_async(reinterpret_cast<float*>(t), src + kF * 64, kF * kL, tid, kT2);
   tw = t;

@@ -107,14 +107,16 @@ DPS_DEV void dft3p(float2& x0, float2& x1, float2& x2) {
   x1 = padd(m, r);
   x2 = psub(m, r);
 }
+template <bool kPackedMul>
 DPS_DEV void dft6p(float2* v) {
   float2 e0 = v[0], e1 = v[2], e2 = v[4];
   float2 o0 = v[1], o1 = v[3], o2 = v[5];
   dft3p(e0, e1, e2);
   dft3p(o0, o1, o2);
   const float s = 0.86602540378443864676f;
-  const float2 t1 = cmul_tw(o1, make_float4(0.5f, -s, s, 0.5f));     // ·W6^1 = ½ − i·s
-  const float2 t2 = cmul_tw(o2, make_float4(-0.5f, -s, s, -0.5f));   // ·W6^2 = −½ − i·s
+  // ·W6^1 = ½ − i·s, ·W6^2 = −½ − i·s
+  const float2 t1 = kPackedMul ? cmul_tw(o1, make_float4(0.5f, -s, s, 0.5f)) : cmul(o1, make_float2(0.5f, -s));
+  const float2 t2 = kPackedMul ? cmul_tw(o2, make_float4(-0.5f, -s, s, -0.5f)) : cmul(o2, make_float2(-0.5f, -s));
   v[0] = padd(e0, o0); v[3] = psub(e0, o0);
   v[1] = padd(e1, t1); v[4] = psub(e1, t1);
   v[2] = padd(e2, t2); v[5] = psub(e2, t2);

@@ -34,9 +34,9 @@ static inline void stg_stream2(float* p, const float2& v) { p[0] = v.x; p[1] = v
 #include "phase_colsreg.cuh"
 
 
-// twiddle tables exactly as ph*::create builds them (float2 entries, or (w.x, w.y, −w.y, w.x) quadruples under PHASE_PACKED)
+// twiddle tables exactly as ph*::create builds them (float2 entries, or (w.x, w.y, −w.y, w.x) quadruples under PHASE_PACKED == 2)
 static inline tw_t emu_tw_entry(float2 w) {
-#if PHASE_PACKED
+#if PHASE_PACKED == 2
   return make_float4(w.x, w.y, -w.y, w.x);
 #else
   return w;

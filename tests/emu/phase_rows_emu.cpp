@@ -39,9 +39,9 @@ static inline float clamp_pass(float pre) { return (pre >= -1.0f && pre <= 1.0f)
 #include "phase_rowsreg.cuh"
 
 
-// twiddle tables exactly as ph*::create builds them (float2 entries, or (w.x, w.y, −w.y, w.x) quadruples under PHASE_PACKED)
+// twiddle tables exactly as ph*::create builds them (float2 entries, or (w.x, w.y, −w.y, w.x) quadruples under PHASE_PACKED == 2)
 static inline tw_t emu_tw_entry(float2 w) {
-#if PHASE_PACKED
+#if PHASE_PACKED == 2
   return make_float4(w.x, w.y, -w.y, w.x);
 #else
   return w;

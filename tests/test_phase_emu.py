@@ -25,7 +25,7 @@ def _build(r3, tmp_path, which="cols", packed=0):
     return C.CDLL(so)
 
 
-@pytest.mark.parametrize("packed", [0, 1])
+@pytest.mark.parametrize("packed", [0, 1, 2])
 @pytest.mark.parametrize("r3,want_r", [(6, True), (4, True), (3, True), (6, False)])
 def test_register_column_kernel_matches_numpy_dft(r3, want_r, packed, tmp_path):
     lib = _build(r3, tmp_path, packed=packed)
@@ -81,7 +81,7 @@ def test_register_column_kernel_matches_numpy_dft(r3, want_r, packed, tmp_path):
     assert np.abs(t - T).max() <= 2e-5 * np.abs(T).max()
 
 
-@pytest.mark.parametrize("packed", [0, 1])
+@pytest.mark.parametrize("packed", [0, 1, 2])
 @pytest.mark.parametrize("r3,clip", [(6, True), (4, True), (3, False)])
 def test_register_row_kernels_match_numpy_dft(r3, clip, packed, tmp_path):
     """K1 (x, ε → x̂₀ → half spectrum of every image row, two rows per complex FFT, + clamp-pass bytes) and K3 (Hermitian half
