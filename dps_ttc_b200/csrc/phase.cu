@@ -30,7 +30,9 @@
 
 
 struct PhaseTables {
-  float2* tw = nullptr;  // exp(−2πi j/384), j ∈ [0,384)
+  // [0, L) exp(−2πi j/L) (the shared-memory kernels stage its first half) · [L, L+64) W64^{k·r} at [8r+k] · [L+64, 2L+64) the full
+  // table rebuilt from the half table (tw[j+L/2] = −tw[j]) · the last two again as (w.x, w.y, −w.y, w.x) quadruples (PHASE_PACKED=2)
+  float2* tw = nullptr;
 };
 
 

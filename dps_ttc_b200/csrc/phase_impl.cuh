@@ -529,8 +529,7 @@ DPS_DEV void reg_tables(float* smem, const float2* tw_g, int tid, const tw_t*& t
   red = reinterpret_cast<float*>(t + kL + 64);
 }
 
-// table layout behind PhaseTables::tw (create()): [0, L) exp(−2πi j/L) · [L, L + 64) W64^{k·r} at [8r + k] · [L + 64, 2L + 64) the
-// full table rebuilt from the half table with twid()'s sign rule
+// K2'' of the fused guidance: both column transforms, residual and cotangent on chip (phases: phase_colsreg.cuh)
 template <bool kOut>
 __global__ void __launch_bounds__(kT2, PHASE_COLS_MINB) phase_cols_fused_reg(const FwdArgs fa, const float2* __restrict__ tw_g, int C) {
   extern __shared__ __align__(16) float smem[];
